@@ -1,0 +1,157 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of the cone plugins on conex's Newton-step hot path:
+//   * the dense-LMI / PSD cone   (conex/psd_constraint.{h,cc}, conex/dense_lmi_constraint.{h,cc})
+//   * the LP cone                (conex/linear_constraint.{h,cc}) — needed for the reference's
+//     "Mixed" known-answer SDP (conex/test/test_sdp.cc:13-59)
+// and of the dense math kernels below them (Padé map, two-sided Lanczos).
+// Parity status: PINNED against the reference's own known-answer tests at their
+// tolerances (see tests/test_oracle_golden.py and oracle/README.md); bit-level parity with
+// Eigen is not pinned because the reference cannot be built here (Eigen 3.3.9 absent).
+#pragma once
+#include <vector>
+
+#include "linalg.h"
+
+namespace oracle {
+
+// conex/newton_step.h:11-48 (plain data carried between driver and cones).
+struct SlackEigenvalues {
+  double frobenius_norm_squared = 0;
+  double trace = 0;
+  double lambda_min = 0;
+  double lambda_max = 0;
+  double rank = 0;
+};
+struct StepOptions {
+  bool affine = true;
+  double inv_sqrt_mu = 0;
+  double c_weight = 0;
+  double e_weight = 0;
+  double step_size = 1;
+};
+struct StepInfo {
+  double normsqrd = 0;
+  double norminfd = 0;
+};
+
+// conex/newton_step.h:51-107. G is m x m (lower triangle meaningful), AW / AQc are m-vectors.
+struct SchurSystem {
+  int m = 0;
+  bool residual_only = false;
+  double* AW = nullptr;
+  double* AQc = nullptr;
+  View G;
+  double inner_product_of_w_and_c = 0;
+  double inner_product_of_c_and_Qc = 0;
+  int SizeOf() const {
+    int s = 2 * AlignedSize(m);
+    if (!residual_only) s += AlignedSize(m * m);
+    return s;
+  }
+  void Bind(double* data) {
+    AW = data;
+    AQc = data + AlignedSize(m);
+    if (!residual_only) G = View(data + 2 * AlignedSize(m), m, m);
+  }
+  void SetZero();
+};
+
+// The role of conex::Constraint (conex/constraint.h:51-197): what the driver needs of a cone.
+class Cone {
+ public:
+  virtual ~Cone() {}
+  virtual int WorkspaceSize() const = 0;
+  virtual void BindWorkspace(double* data) = 0;
+  virtual void SetIdentity() = 0;
+  virtual int Rank() const = 0;
+  virtual int NumberOfVariables() const = 0;
+  virtual void ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) = 0;
+  virtual void PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) = 0;
+  virtual bool TakeStep(const StepOptions& opt) = 0;
+  virtual void GetWeightedSlackEigenvalues(const double* y, double c_weight,
+                                           SlackEigenvalues* p) = 0;
+  virtual const double* DualVariable() const = 0;
+  virtual int DualVariableSize() const = 0;
+};
+
+// How the Gram rows of the Schur complement are formed.
+enum class GramVariant {
+  kAsWritten = 0,  // m GEMVs over growing slabs: dense_lmi_constraint.cc:75-78
+  kBlas3 = 1,      // same numbers through one GEMM per 64-row panel (reordered summation)
+};
+
+// DenseLMIConstraint (conex/dense_lmi_constraint.h:24-41) on a PsdConstraint
+// (conex/psd_constraint.h:39-65).
+class DenseLmiCone final : public Cone {
+ public:
+  // A: m contiguous column-major n x n matrices (interfaces/conex.cc:143-151); C: n x n.
+  DenseLmiCone(int n, int m, const double* A, const double* C);
+  int WorkspaceSize() const override { return 3 * AlignedSize(n_ * n_); }
+  void BindWorkspace(double* data) override;
+  void SetIdentity() override;
+  int Rank() const override { return n_; }
+  int NumberOfVariables() const override { return m_; }
+  void ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) override;
+  void PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) override;
+  bool TakeStep(const StepOptions& opt) override;
+  void GetWeightedSlackEigenvalues(const double* y, double c_weight,
+                                   SlackEigenvalues* p) override;
+  const double* DualVariable() const override { return W_.p; }
+  int DualVariableSize() const override { return n_ * n_; }
+
+  void ComputeNegativeSlack(double k, const double* y, View s) const;
+  GramVariant gram_variant = GramVariant::kAsWritten;
+  View W_, temp_1_, temp_2_;
+
+ private:
+  void GeodesicUpdate(double scale, const StepOptions& opt, View WS);
+  void AffineUpdate(double w_e, View WS);
+  int n_, m_;
+  std::vector<double> Avect_;  // n*n x m, column i = vec(A_i)
+  std::vector<double> C_;      // n x n
+};
+
+// LinearConstraint (conex/linear_constraint.h:14-89): c - A y >= 0 with A n x m.
+class LinearCone final : public Cone {
+ public:
+  LinearCone(int n, int m, const double* A, const double* c);
+  int WorkspaceSize() const override { return 3 * AlignedSize(n_) + AlignedSize(n_ * m_); }
+  void BindWorkspace(double* data) override;
+  void SetIdentity() override;
+  int Rank() const override { return n_; }
+  int NumberOfVariables() const override { return m_; }
+  void ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) override;
+  void PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) override;
+  bool TakeStep(const StepOptions& opt) override;
+  void GetWeightedSlackEigenvalues(const double* y, double c_weight,
+                                   SlackEigenvalues* p) override;
+  const double* DualVariable() const override { return W_; }
+  int DualVariableSize() const override { return n_; }
+
+ private:
+  void ComputeNegativeSlack(double k, const double* y, double* minus_s) const;
+  int n_, m_;
+  std::vector<double> A_, c_;
+  double *W_ = nullptr, *temp_1_ = nullptr, *temp_2_ = nullptr, *WA_ = nullptr;
+};
+
+// --- dense math kernels -------------------------------------------------------------------
+// [3/3] Padé approximation of exp(X), no scaling/squaring (conex/exponential_map_pade.cc:10-32).
+void ExponentialMapPade(int n, const double* X, double* result);
+// Two-sided Lanczos on (WS, WS^T) in the W inner product (conex/approximate_eigenvalues.cc:173-239).
+// Returns the Ritz values (ascending).
+std::vector<double> AsymmetricLanczos(int n, const double* WS, const double* W, const double* r,
+                                      int num_iter);
+// conex/approximate_eigenvalues.cc:241-256 with compressed == true.
+std::vector<double> ApproximateEigenvalues(int n, const double* WS, const double* W,
+                                           const double* r, int num_iter);
+// Symmetric Lanczos, conex/approximate_eigenvalues.cc:147-171.
+std::vector<double> SymmetricLanczos(int n, const double* A, const double* r0, int num_iter);
+
+// conex/divergence.cc:96-111; returns -1 when neither branch yields a finite bound.
+double DivergenceUpperBoundInverse(double divergence_upper_bound, const SlackEigenvalues& p);
+// conex/divergence.cc:113-121.
+double DivergenceUpperBound(double k, const SlackEigenvalues& p);
+
+}  // namespace oracle
