@@ -1,0 +1,159 @@
+"""conex_b200 — B200-native Newton step of conex's geodesic interior-point method.
+
+The product is the shared library `conex_b200/lib/libconex_b200.so` (CONEX_* C ABI of
+include/conex.h over hand-written sm_100a CUDA). This module is the host-side mirror of the
+reference's Python front end (interfaces/python/ConexProgram.py:58-277, class `Conex`) over ctypes
+instead of SWIG: same method names, same argument meaning, same error behaviour (NameError on a
+failed call). There is no CPU fallback: if the library is missing, import fails loudly.
+"""
+import ctypes as _C
+import os as _os
+
+import numpy as _np
+
+_HERE = _os.path.dirname(_os.path.abspath(__file__))
+LIBRARY_PATH = _os.path.join(_HERE, "lib", "libconex_b200.so")
+
+if not _os.path.exists(LIBRARY_PATH):
+    raise ImportError(
+        f"{LIBRARY_PATH} not found. Build it with `make -C {_HERE}` (or __graft_entry__.build()); "
+        "conex_b200 has no CPU or PyTorch fallback.")
+
+_lib = _C.CDLL(LIBRARY_PATH)
+_dp = _C.POINTER(_C.c_double)
+
+
+class CONEX_SolverConfiguration(_C.Structure):
+    """include/conex.h (reference interfaces/conex.h:10-30)."""
+    _fields_ = [
+        ("prepare_dual_variables", _C.c_int), ("initialization_mode", _C.c_int),
+        ("inv_sqrt_mu_max", _C.c_double), ("minimum_mu", _C.c_double), ("maximum_mu", _C.c_double),
+        ("divergence_upper_bound", _C.c_double), ("enable_line_search", _C.c_int),
+        ("dinf_upper_bound", _C.c_double), ("final_centering_steps", _C.c_int),
+        ("final_centering_tolerance", _C.c_double), ("initial_centering_steps_warmstart", _C.c_int),
+        ("initial_centering_steps_coldstart", _C.c_int), ("warmstart_abort_threshold", _C.c_double),
+        ("max_iterations", _C.c_int), ("iterative_refinement_iterations", _C.c_int),
+        ("infeasibility_threshold", _C.c_double), ("kkt_error_tolerance", _C.c_double),
+        ("enable_rescaling", _C.c_int), ("kkt_solver", _C.c_int),
+    ]
+
+
+class CONEX_IterationStats(_C.Structure):
+    _fields_ = [("mu", _C.c_double), ("iteration_number", _C.c_int)]
+
+
+_lib.CONEX_CreateConeProgram.restype = _C.c_void_p
+_lib.CONEX_DeleteConeProgram.argtypes = [_C.c_void_p]
+_lib.CONEX_SetNumberOfVariables.argtypes = [_C.c_void_p, _C.c_int]
+_lib.CONEX_AddDenseLMIConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _C.c_int, _dp,
+                                             _C.c_int, _C.c_int]
+_lib.CONEX_AddSparseLMIConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _C.c_int, _dp,
+                                              _C.c_int, _C.c_int, _C.POINTER(_C.c_long), _C.c_int]
+_lib.CONEX_Maximize.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.POINTER(CONEX_SolverConfiguration), _dp,
+                                _C.c_int]
+_lib.CONEX_GetDualVariable.argtypes = [_C.c_void_p, _C.c_int, _dp, _C.c_int, _C.c_int]
+_lib.CONEX_GetDualVariableSize.argtypes = [_C.c_void_p, _C.c_int]
+_lib.CONEX_SetDefaultOptions.argtypes = [_C.POINTER(CONEX_SolverConfiguration)]
+_lib.CONEX_GetIterationStats.argtypes = [_C.c_void_p, _C.POINTER(CONEX_IterationStats), _C.c_int]
+
+
+def device_available():
+    return bool(_lib.CONEXB200_DeviceAvailable())
+
+
+class Solution:
+    def __init__(self):
+        self.y = None
+        self.status = 0
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Conex:
+    """Mirror of the reference's `Conex` class for the dense-LMI hot path."""
+
+    def __init__(self, m=-1):
+        self.a = _C.c_void_p(_lib.CONEX_CreateConeProgram())
+        if not self.a:
+            raise NameError("Failed to create program (is a B200 visible?).")
+        if m >= 0:
+            _lib.CONEX_SetNumberOfVariables(self.a, m)
+        self.num_constraints = 0
+        self.A = []
+        self.c = []
+        self.m = m
+
+    def __del__(self):
+        if getattr(self, "a", None):
+            _lib.CONEX_DeleteConeProgram(self.a)
+
+    def DefaultConfiguration(self):
+        # interfaces/python/ConexProgram.py:115-126
+        config = CONEX_SolverConfiguration()
+        _lib.CONEX_SetDefaultOptions(_C.byref(config))
+        config.inv_sqrt_mu_max = 1000
+        config.maximum_mu = 1e20
+        config.max_iterations = 100
+        config.final_centering_steps = 1
+        config.prepare_dual_variables = 1
+        config.infeasibility_threshold = 1e8
+        config.divergence_upper_bound = 1
+        return config
+
+    def AddDenseLinearMatrixInequality(self, A, c):
+        """A: array of shape (n, n, m) (A[:, :, i] is the i-th matrix), c: (n, n)."""
+        A = _np.asarray(A, dtype=_np.float64)
+        n, m = A.shape[1], A.shape[2]
+        packed = _np.ascontiguousarray(_np.stack([_np.asfortranarray(A[:, :, i]).ravel(order="F")
+                                                  for i in range(m)]))
+        cf = _np.asfortranarray(_np.asarray(c, dtype=_np.float64))
+        self.n, self.m = n, m
+        self.A.append(A)
+        self.c.append(cf)
+        _lib.CONEX_AddDenseLMIConstraint(self.a, _ptr(packed), n, n, m, _ptr(cf), n, n)
+        self.num_constraints += 1
+
+    def AddSparseLinearMatrixInequality(self, A, c, variables):
+        A = _np.asarray(A, dtype=_np.float64)
+        n, k = A.shape[1], A.shape[2]
+        if max(variables) + 1 > self.m:
+            raise NameError("Invalid sparse LMI.")
+        packed = _np.ascontiguousarray(_np.stack([_np.asfortranarray(A[:, :, i]).ravel(order="F")
+                                                  for i in range(k)]))
+        cf = _np.asfortranarray(_np.asarray(c, dtype=_np.float64))
+        v = (_C.c_long * k)(*[int(x) for x in variables])
+        self.A.append(A)
+        self.c.append(cf)
+        _lib.CONEX_AddSparseLMIConstraint(self.a, _ptr(packed), n, n, k, _ptr(cf), n, n, v, k)
+        self.num_constraints += 1
+
+    def Maximize(self, b, config=None):
+        if config is None:
+            config = self.DefaultConfiguration()
+        b = _np.ascontiguousarray(_np.asarray(b, dtype=_np.float64).ravel())
+        if b.shape[0] != self.m:
+            raise NameError("Cost vector dimension does not match number of variables.")
+        sol = Solution()
+        sol.y = _np.ones(self.m)
+        sol.status = _lib.CONEX_Maximize(self.a, _ptr(b), self.m, _C.byref(config), _ptr(sol.y), self.m)
+        return sol
+
+    def GetDualVariables(self):
+        x = []
+        for i in range(self.num_constraints):
+            n = self.c[i].shape[0]
+            xi = _np.zeros(n * n)
+            _lib.CONEX_GetDualVariable(self.a, i, _ptr(xi), n, n)
+            x.append(xi.reshape((n, n), order="F"))
+        return x
+
+    def GetIterationNumberStats(self, num):
+        stats = CONEX_IterationStats()
+        _lib.CONEX_GetIterationStats(self.a, _C.byref(stats), num)
+        return stats
+
+    def GetIterationStats(self):
+        last = self.GetIterationNumberStats(-1).iteration_number
+        return [self.GetIterationNumberStats(i) for i in range(last + 1)]

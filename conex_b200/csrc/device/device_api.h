@@ -1,0 +1,29 @@
+// Internal C++ view of the device layer (namespace cxb). The extern "C" surface that the host
+// orchestration and the tests bind is include/conex_b200_device.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../../include/conex_b200_device.h"
+
+namespace cxb {
+
+// gemm.cu
+int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, double alpha,
+          const double* A, long lda, long sA, const double* B, long ldb, long sB, double beta,
+          double* C, long ldc, long sC, int batch, bool lower_only);
+
+// blas1.cu
+int SetIdentity(cudaStream_t s, int n, double* W);
+int Symmetrize(cudaStream_t s, int n, double* W);                          // W <- (W + W^T)/2
+int ShiftScale(cudaStream_t s, int n, double* X, double e, double scale);  // X <- scale (X + e I)
+int ScaleAddDiag(cudaStream_t s, int n, const double* X, double a, double d, double* Y);  // Y = aX + dI
+int SumDiff(cudaStream_t s, long total, const double* U, const double* V, double* N, double* D);
+int Transpose(cudaStream_t s, int n, const double* X, double* XT);
+
+// lu.cu
+int LuFactor(cudaStream_t s, int n, double* A, long lda, int* ipiv, int* info);
+int LuSolveFactored(cudaStream_t s, int n, const double* LU, long lda, const int* ipiv, int nrhs,
+                    double* B, long ldb, double* tmp, int* perm);
+int PadeExpm(cudaStream_t s, int n, const double* X, double* out, double* work, int* iwork, int* info);
+
+}  // namespace cxb

@@ -1,0 +1,192 @@
+// K7: two-sided Lanczos on (WS, WS^T) in the W inner product — the step-size / mu eigen-bound
+// estimate. Replaces AsymmetricLanczos (approximate_eigenvalues.cc:173-239) with the same
+// recurrence, start vector, iteration count and breakdown test (beta^2 < 1e-6):
+//
+//   v1 = r; v0 = W r; V /= sqrt(v0.v1)
+//   step j: u0 = WS v0; u1 = WS^T v1; alpha_j = v0.u1; U -= alpha_j V (+ beta_{j-1} Vprev)
+//           beta_j^2 = u0.u1; stop if < 1e-6; Vprev = V; V = U / beta_j
+//
+// Bandwidth-bound: each step streams WS and WS^T once (both column-dot products, one warp per
+// column, fully coalesced; for n = 2000 the two matrices stay resident in the 126 MB L2). The
+// n-vector recurrence is executed by the last CTA to finish (ticket counter), so one launch per
+// step suffices and the arithmetic order is fixed (deterministic).
+#include "common.cuh"
+#include "device_api.h"
+
+namespace cxb {
+namespace {
+
+struct LanczosState {
+  int done;
+  int count;
+  unsigned int ticket;
+  int pad;
+};
+
+// Layout of d_work (doubles): [WST n*n][v0][v1][u0][u1][p0][p1][state (4 doubles)]
+struct LanczosBufs {
+  double *WST, *v0, *v1, *u0, *u1, *p0, *p1;
+  LanczosState* st;
+};
+
+__host__ __device__ inline LanczosBufs Carve(double* work, int n) {
+  LanczosBufs b;
+  const long nn = (long)n * n;
+  const long np = (n + 3) & ~3L;
+  b.WST = work;
+  b.v0 = work + nn;
+  b.v1 = b.v0 + np;
+  b.u0 = b.v1 + np;
+  b.u1 = b.u0 + np;
+  b.p0 = b.u1 + np;
+  b.p1 = b.p0 + np;
+  b.st = reinterpret_cast<LanczosState*>(b.p1 + np);
+  return b;
+}
+
+__device__ __forceinline__ double ColumnDot(const double* __restrict__ col,
+                                            const double* __restrict__ x, int n, int lane) {
+  double s = 0;
+  for (int i = lane; i < n; i += 32) s += col[i] * x[i];
+  return WarpSum(s);
+}
+
+// v0 = W^T r (= W r, W symmetric); the last CTA normalises: V /= sqrt(v0 . r).
+__global__ void __launch_bounds__(256) LanczosInitKernel(int n, const double* __restrict__ W,
+                                                         const double* __restrict__ rbase,
+                                                         const double* __restrict__ col_index,
+                                                         double* work) {
+  __shared__ double scratch[33];
+  __shared__ bool is_last;
+  const LanczosBufs b = Carve(work, n);
+  const double* __restrict__ r = col_index ? rbase + (long)(*col_index) * n : rbase;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c < n) {
+    const double v = ColumnDot(W + (long)c * n, r, n, lane);
+    if (lane == 0) b.v0[c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&b.st->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += __ldcg(b.v0 + i) * r[i];
+  s = BlockSum(s, scratch);
+  const double scale = sqrt(s);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    b.v0[i] = __ldcg(b.v0 + i) / scale;
+    b.v1[i] = r[i] / scale;
+  }
+  if (threadIdx.x == 0) {
+    b.st->ticket = 0;
+    b.st->done = 0;
+    b.st->count = 0;
+  }
+}
+
+__global__ void LanczosResetKernel(int n, double* work) {
+  const LanczosBufs b = Carve(work, n);
+  b.st->ticket = 0;
+  b.st->done = 0;
+  b.st->count = 0;
+}
+
+// One Lanczos step (index j).
+__global__ void __launch_bounds__(256) LanczosStepKernel(int n, int j, int num_iter,
+                                                         const double* __restrict__ WS, double* work,
+                                                         double* alpha, double* beta, int* count) {
+  __shared__ double scratch[33];
+  __shared__ bool is_last;
+  const LanczosBufs b = Carve(work, n);
+  if (b.st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c < n) {
+    const double a0 = ColumnDot(b.WST + (long)c * n, b.v0, n, lane);  // (WS v0)[c]
+    const double a1 = ColumnDot(WS + (long)c * n, b.v1, n, lane);     // (WS^T v1)[c]
+    if (lane == 0) {
+      b.u0[c] = a0;
+      b.u1[c] = a1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&b.st->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- n-vector recurrence, executed by one CTA in a fixed order ----
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += b.v0[i] * __ldcg(b.u1 + i);
+  const double a = BlockSum(s, scratch);
+  const double bprev = (j > 0) ? beta[j - 1] : 0.0;
+  s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double x0 = __ldcg(b.u0 + i) - a * b.v0[i];
+    double x1 = __ldcg(b.u1 + i) - a * b.v1[i];
+    if (j > 0) {
+      x0 -= bprev * b.p0[i];
+      x1 -= bprev * b.p1[i];
+    }
+    b.u0[i] = x0;
+    b.u1[i] = x1;
+    s += x0 * x1;
+  }
+  const double b2 = BlockSum(s, scratch);
+  bool stop = (j + 1 >= num_iter) || (b2 < 1e-6);
+  if (!stop) {
+    const double bj = sqrt(b2);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double x0 = b.u0[i], x1 = b.u1[i];
+      b.p0[i] = b.v0[i];
+      b.p1[i] = b.v1[i];
+      b.v0[i] = x0 / bj;
+      b.v1[i] = x1 / bj;
+    }
+    if (threadIdx.x == 0) beta[j] = bj;
+  }
+  if (threadIdx.x == 0) {
+    alpha[j] = a;
+    b.st->ticket = 0;
+    b.st->count = j;
+    *count = j;
+    if (stop) b.st->done = 1;
+  }
+}
+
+}  // namespace
+}  // namespace cxb
+
+using namespace cxb;
+
+extern "C" {
+
+size_t cxb_lanczos_worksize(int n) { return (size_t)n * n + 6 * (size_t)((n + 3) & ~3) + 8; }
+
+int cxb_lanczos_two_sided(void* stream, int n, const double* d_WS, const double* d_W,
+                          const double* d_r, const double* d_col_index, int num_iter,
+                          double* d_alpha, double* d_beta, int* d_count, double* d_work) {
+  cudaStream_t s = AsStream(stream);
+  if (n < 1 || num_iter < 1) return -1;
+  const LanczosBufs b = Carve(d_work, n);
+  int rc = Transpose(s, n, d_WS, b.WST);
+  if (rc) return rc;
+  const int grid = (n + 7) / 8;
+  CountLaunch(); LanczosResetKernel<<<1, 1, 0, s>>>(n, d_work);
+  CountLaunch(); LanczosInitKernel<<<grid, 256, 0, s>>>(n, d_W, d_r, d_col_index, d_work);
+  for (int j = 0; j < num_iter; j++) {
+    CountLaunch(); LanczosStepKernel<<<grid, 256, 0, s>>>(n, j, num_iter, d_WS, d_work, d_alpha, d_beta, d_count);
+  }
+  return LaunchStatus();
+}
+
+}  // extern "C"

@@ -1,0 +1,327 @@
+// K8: geodesic update of the PSD scaling point — [3/3] Padé matrix exponential as a GEMM chain on
+// the FP64 tensor cores plus a blocked partial-pivot LU solve.
+//
+// Replaces PsdConstraint::GeodesicUpdate (psd_constraint.cc:13-28) and
+// ExponentialMapPadeApproximation / ComputeWeightedPowers (exponential_map_pade.cc:10-32):
+//   X  = scale * (WS + e I);  X2 = X X;  U = X (X2 + 60 I);  V = 12 X2 + 120 I
+//   E  = (V - U)^{-1} (V + U)   (partial pivoting, like Eigen partialPivLu)
+//   W <- sym(E W)
+// There is deliberately no scaling-and-squaring: the reference relies on the step-size rule to
+// keep ||X|| small, and adding it would change the iterates.
+#include "common.cuh"
+#include "device_api.h"
+
+namespace cxb {
+namespace {
+
+constexpr int kLuNB = 32;      // LU panel width
+constexpr int kSolveNB = 128;  // block size of the multi-RHS triangular solves
+constexpr int kRhsCols = 32;   // RHS columns per CTA in the diagonal-block solves
+
+// Factor the panel A[j0:n, j0:j0+nb] with row pivoting. One CTA of 1024 threads working in
+// global memory (the panel is L2 resident). Row swaps are applied inside the panel only.
+__global__ void __launch_bounds__(1024) LuPanelKernel(int n, int j0, int nb, double* A, long ld,
+                                                      int* ipiv, int* info) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ double s_row[kLuNB];
+  __shared__ int s_piv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = 0; j < nb; j++) {
+    const int col = j0 + j;
+    double* Ac = A + (long)col * ld;
+    // 1. pivot search
+    double best = -1.0;
+    int arg = col;
+    for (int r = col + tid; r < n; r += 1024) {
+      const double v = fabs(Ac[r]);
+      if (v > best) {
+        best = v;
+        arg = r;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (lane == 0) {
+      s_val[warp] = best;
+      s_idx[warp] = arg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_val[0];
+      int a = s_idx[0];
+      for (int w = 1; w < 32; w++) {
+        if (s_val[w] > b || (s_val[w] == b && s_idx[w] < a)) {
+          b = s_val[w];
+          a = s_idx[w];
+        }
+      }
+      s_piv = a;
+      ipiv[col] = a;
+      if (b == 0.0 && *info == 0) *info = col + 1;
+    }
+    __syncthreads();
+    const int p = s_piv;
+    // 2. swap rows col <-> p inside the panel, and stage the pivot row
+    if (tid < nb) {
+      double* c = A + (long)(j0 + tid) * ld;
+      const double a = c[col], b = c[p];
+      if (p != col) {
+        c[col] = b;
+        c[p] = a;
+      }
+      s_row[tid] = b;  // new A[col, j0 + tid]
+    }
+    __syncthreads();
+    const double piv = s_row[j];
+    const double inv = (piv != 0.0) ? 1.0 / piv : 0.0;
+    // 3. multipliers + rank-1 update of the remaining panel columns
+    for (int r = col + 1 + tid; r < n; r += 1024) {
+      const double l = Ac[r] * inv;
+      Ac[r] = l;
+      for (int c = j + 1; c < nb; c++) A[(long)(j0 + c) * ld + r] -= l * s_row[c];
+    }
+    __syncthreads();
+  }
+}
+
+// Apply the panel's row interchanges (rows j0..j0+nb-1) to columns [c_begin, c_end) of M.
+__global__ void LaswpKernel(int j0, int nb, const int* __restrict__ ipiv, double* M, long ld,
+                            int c_begin, int c_end) {
+  const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_end) return;
+  double* col = M + (long)c * ld;
+  for (int i = 0; i < nb; i++) {
+    const int r = j0 + i, p = ipiv[r];
+    if (p != r) {
+      const double t = col[r];
+      col[r] = col[p];
+      col[p] = t;
+    }
+  }
+}
+
+// perm[i] = source row of row i after applying all interchanges. Single CTA; perm built in smem.
+__global__ void BuildPermKernel(int n, const int* __restrict__ ipiv, int* perm) {
+  extern __shared__ int sp[];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sp[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n; i++) {
+      const int p = ipiv[i];
+      if (p != i) {
+        const int t = sp[i];
+        sp[i] = sp[p];
+        sp[p] = t;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = sp[i];
+}
+
+// dst[i, c] = src[perm[i], c]
+__global__ void GatherRowsKernel(int n, int nrhs, const int* __restrict__ perm,
+                                 const double* __restrict__ src, long lds, double* dst, long ldd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i < n && c < nrhs) dst[(long)c * ldd + i] = src[(long)c * lds + perm[i]];
+}
+
+// Diagonal-block triangular solve with many right-hand sides. T: nb x nb block at (ld).
+// UPPER == false: unit lower (L of LU);  UPPER == true: non-unit upper (U of LU).
+// X: nb x nrhs block (ldx), CTA handles kRhsCols columns; thread (r = tid % 32 col, q) layout.
+template <bool UPPER>
+__global__ void __launch_bounds__(256) TrsmDiagKernel(int nb, const double* __restrict__ T, long ld,
+                                                      double* X, long ldx, int nrhs) {
+  extern __shared__ double s[];
+  const int PT = nb + 1;
+  double* st = s;            // st[c*PT + r] = T[r][c]
+  double* sx = s + nb * PT;  // sx[r*(kRhsCols+1) + c]   (row-major so a row step is conflict free)
+  constexpr int PX = kRhsCols + 1;
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * kRhsCols;
+  const int nc = min(kRhsCols, nrhs - c0);
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int r = e % nb, c = e / nb;
+    st[c * PT + r] = T[(long)c * ld + r];
+  }
+  for (int e = tid; e < nb * kRhsCols; e += 256) {
+    const int r = e % nb, c = e / nb;
+    sx[r * PX + c] = (c < nc) ? X[(long)(c0 + c) * ldx + r] : 0.0;
+  }
+  __syncthreads();
+  const int c = tid % kRhsCols;  // my RHS column
+  const int q = tid / kRhsCols;  // row phase 0..7
+  if (!UPPER) {
+    for (int j = 0; j < nb; j++) {
+      const double xj = sx[j * PX + c];  // unit diagonal
+      for (int r = j + 1 + q; r < nb; r += 8) sx[r * PX + c] -= st[j * PT + r] * xj;
+      __syncthreads();
+    }
+  } else {
+    for (int j = nb - 1; j >= 0; j--) {
+      if (q == 0) sx[j * PX + c] /= st[j * PT + j];
+      __syncthreads();
+      const double xj = sx[j * PX + c];
+      for (int r = q; r < j; r += 8) sx[r * PX + c] -= st[j * PT + r] * xj;
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < nb * kRhsCols; e += 256) {
+    const int r = e % nb, cc = e / nb;
+    if (cc < nc) X[(long)(c0 + cc) * ldx + r] = sx[r * PX + cc];
+  }
+}
+
+void ConfigureOnce() {
+  static bool configured = false;
+  if (configured) return;
+  const int bytes = (int)(sizeof(double) * (kSolveNB * (kSolveNB + 1) + kSolveNB * (kRhsCols + 1)));
+  cudaFuncSetAttribute(TrsmDiagKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(TrsmDiagKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(BuildPermKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  configured = true;
+}
+
+size_t TrsmSmem(int nb) {
+  return sizeof(double) * ((size_t)nb * (nb + 1) + (size_t)nb * (kRhsCols + 1));
+}
+
+__global__ void ResetInfoKernel2(int* info) { *info = 0; }
+
+}  // namespace
+
+// In-place LU with partial pivoting: P A = L U.
+int LuFactor(cudaStream_t s, int n, double* A, long lda, int* ipiv, int* info) {
+  ConfigureOnce();
+  CountLaunch(); ResetInfoKernel2<<<1, 1, 0, s>>>(info);
+  for (int j0 = 0; j0 < n; j0 += kLuNB) {
+    const int nb = min(kLuNB, n - j0);
+    CountLaunch(); LuPanelKernel<<<1, 1024, 0, s>>>(n, j0, nb, A, lda, ipiv, info);
+    if (j0 > 0) CountLaunch();
+    if (j0 > 0) LaswpKernel<<<(j0 + 127) / 128, 128, 0, s>>>(j0, nb, ipiv, A, lda, 0, j0);
+    const int rest = n - j0 - nb;
+    if (rest > 0) {
+      CountLaunch(); LaswpKernel<<<(rest + 127) / 128, 128, 0, s>>>(j0, nb, ipiv, A, lda, j0 + nb, n);
+      // U12 = L11^{-1} A12
+      double* A12 = A + (long)(j0 + nb) * lda + j0;
+      CountLaunch(); TrsmDiagKernel<false><<<(rest + kRhsCols - 1) / kRhsCols, 256, TrsmSmem(nb), s>>>(
+          nb, A + (long)j0 * lda + j0, lda, A12, lda, rest);
+      // A22 -= L21 U12
+      const double* L21 = A + (long)j0 * lda + j0 + nb;
+      double* A22 = A + (long)(j0 + nb) * lda + j0 + nb;
+      const int rc = Dgemm(s, false, false, rest, rest, nb, -1.0, L21, lda, 0, A12, lda, 0, 1.0, A22,
+                           lda, 0, 1, false);
+      if (rc != 0) return rc;
+    }
+  }
+  return LaunchStatus();
+}
+
+// Solve with the factors: X = U^{-1} L^{-1} P B. `B` is overwritten by X; `tmp` holds n*nrhs
+// doubles (ld n); `perm` holds n ints.
+int LuSolveFactored(cudaStream_t s, int n, const double* LU, long lda, const int* ipiv, int nrhs,
+                    double* B, long ldb, double* tmp, int* perm) {
+  ConfigureOnce();
+  CountLaunch(); BuildPermKernel<<<1, 1024, sizeof(int) * n, s>>>(n, ipiv, perm);
+  {
+    dim3 grid((n + 255) / 256, nrhs);
+    CountLaunch(); GatherRowsKernel<<<grid, 256, 0, s>>>(n, nrhs, perm, B, ldb, tmp, n);
+  }
+  // forward, unit lower
+  for (int j0 = 0; j0 < n; j0 += kSolveNB) {
+    const int nb = min(kSolveNB, n - j0);
+    CountLaunch(); TrsmDiagKernel<false><<<(nrhs + kRhsCols - 1) / kRhsCols, 256, TrsmSmem(nb), s>>>(
+        nb, LU + (long)j0 * lda + j0, lda, tmp + j0, n, nrhs);
+    const int rest = n - j0 - nb;
+    if (rest > 0) {
+      const int rc = Dgemm(s, false, false, rest, nrhs, nb, -1.0, LU + (long)j0 * lda + j0 + nb, lda,
+                           0, tmp + j0, n, 0, 1.0, tmp + j0 + nb, n, 0, 1, false);
+      if (rc != 0) return rc;
+    }
+  }
+  // backward, upper
+  const int nblk = (n + kSolveNB - 1) / kSolveNB;
+  for (int k = nblk - 1; k >= 0; k--) {
+    const int j0 = k * kSolveNB, nb = min(kSolveNB, n - j0);
+    CountLaunch(); TrsmDiagKernel<true><<<(nrhs + kRhsCols - 1) / kRhsCols, 256, TrsmSmem(nb), s>>>(
+        nb, LU + (long)j0 * lda + j0, lda, tmp + j0, n, nrhs);
+    if (j0 > 0) {
+      const int rc = Dgemm(s, false, false, j0, nrhs, nb, -1.0, LU + (long)j0 * lda, lda, 0,
+                           tmp + j0, n, 0, 1.0, tmp, n, 0, 1, false);
+      if (rc != 0) return rc;
+    }
+  }
+  // copy back
+  cudaMemcpy2DAsync(B, sizeof(double) * ldb, tmp, sizeof(double) * n, sizeof(double) * n, nrhs,
+                    cudaMemcpyDeviceToDevice, s);
+  return LaunchStatus();
+}
+
+// out = pade33(X). work: 3*n*n doubles; iwork: 2*n ints.
+int PadeExpm(cudaStream_t s, int n, const double* X, double* out, double* work, int* iwork,
+             int* info) {
+  const long nn = (long)n * n;
+  double* P2 = work;           // X^2, then V
+  double* T = work + nn;       // X^2 + 60 I, later LU scratch
+  double* U = work + 2 * nn;   // odd part, then the denominator
+  int rc = Dgemm(s, false, false, n, n, n, 1.0, X, n, 0, X, n, 0, 0.0, P2, n, 0, 1, false);
+  if (rc) return rc;
+  if ((rc = ScaleAddDiag(s, n, P2, 1.0, 60.0, T))) return rc;
+  if ((rc = Dgemm(s, false, false, n, n, n, 1.0, X, n, 0, T, n, 0, 0.0, U, n, 0, 1, false))) return rc;
+  if ((rc = ScaleAddDiag(s, n, P2, 12.0, 120.0, P2))) return rc;
+  // out = V + U (numerator), U <- V - U (denominator)
+  if ((rc = SumDiff(s, nn, U, P2, out, U))) return rc;
+  if ((rc = LuFactor(s, n, U, n, iwork, info))) return rc;
+  return LuSolveFactored(s, n, U, n, iwork, n, out, n, T, iwork + n);
+}
+
+}  // namespace cxb
+
+using namespace cxb;
+
+extern "C" {
+
+size_t cxb_geodesic_worksize(int n) { return (size_t)4 * n * n; }
+
+int cxb_lu_solve(void* stream, int n, double* dA, long lda, int nrhs, double* dB, long ldb,
+                 int* d_ipiv, int* d_info) {
+  // d_ipiv: 2n ints. Needs an n*nrhs scratch: allocate from the stream-ordered pool.
+  cudaStream_t s = AsStream(stream);
+  int rc = LuFactor(s, n, dA, lda, d_ipiv, d_info);
+  if (rc) return rc;
+  double* tmp = nullptr;
+  if (cudaMallocAsync(&tmp, sizeof(double) * (size_t)n * nrhs, s) != cudaSuccess) return -1;
+  rc = LuSolveFactored(s, n, dA, lda, d_ipiv, nrhs, dB, ldb, tmp, d_ipiv + n);
+  cudaFreeAsync(tmp, s);
+  return rc;
+}
+
+int cxb_pade_expm(void* stream, int n, const double* d_X, double* d_out, double* d_work,
+                  int* d_iwork, int* d_info) {
+  return PadeExpm(AsStream(stream), n, d_X, d_out, d_work, d_iwork, d_info);
+}
+
+int cxb_geodesic_update(void* stream, int n, double* d_W, double* d_WS, double e_weight,
+                        double scale, double* d_work, int* d_iwork, int* d_info) {
+  cudaStream_t s = AsStream(stream);
+  const long nn = (long)n * n;
+  int rc = ShiftScale(s, n, d_WS, e_weight, scale);
+  if (rc) return rc;
+  double* E = d_work + 3 * nn;
+  if ((rc = PadeExpm(s, n, d_WS, E, d_work, d_iwork, d_info))) return rc;
+  // W <- E W (into d_WS as scratch), then symmetrise.
+  if ((rc = Dgemm(s, false, false, n, n, n, 1.0, E, n, 0, d_W, n, 0, 0.0, d_WS, n, 0, 1, false)))
+    return rc;
+  cudaMemcpyAsync(d_W, d_WS, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s);
+  return Symmetrize(s, n, d_W);
+}
+
+}  // extern "C"

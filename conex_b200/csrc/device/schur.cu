@@ -1,0 +1,34 @@
+// K1 + K2: Schur-complement assembly for one dense LMI block, H_ij = tr(A_i W A_j W), entirely
+// on the FP64 tensor cores.
+//
+// Reference (dense_lmi_constraint.cc:62-103): per constraint two n x n x n GEMMs (A_i W, W A_i W)
+// followed by a GEMV against the growing slab Avect[:, 0:i+1] — BLAS-2 and memory bound. Here:
+//   K1  T_i = A_i W          one strided-batched DMMA GEMM per panel of constraints
+//       B_i = W T_i          one wide GEMM  W * [T_p .. T_q]  (n x (panel*n) x n)
+//   K2  Haug = Bmat^T Aall   one lower-trapezoid DMMA GEMM with K = n^2 (SYRK-style Gram)
+// The affine term C rides along as matrix m of Aall and W as row m+1 of Bmat, so the same Gram
+// launch also yields AQc_j = <W C W, A_j>, AW_j = <W, A_j>, <c,Qc> and <w,c> (rows m, m+1 of Haug).
+#include "common.cuh"
+#include "device_api.h"
+
+extern "C" int cxb_schur_dense_lmi(void* stream, int n, int m, const double* dAall, const double* dW,
+                                   double* dB, double* dT, int panel, double* dHaug, long ldh) {
+  using namespace cxb;
+  cudaStream_t s = AsStream(stream);
+  if (n < 1 || m < 1 || panel < 1 || ldh < m + 2) return -1;
+  const long nn = (long)n * n;
+  const int total = m + 1;  // A_0..A_{m-1}, C
+  for (int p0 = 0; p0 < total; p0 += panel) {
+    const int pb = (panel < total - p0) ? panel : (total - p0);
+    int rc = Dgemm(s, false, false, n, n, n, 1.0, dAall + (long)p0 * nn, n, nn, dW, n, 0, 0.0, dT, n,
+                   nn, pb, false);
+    if (rc) return rc;
+    // wide GEMM; split so that N stays below 2^30 columns
+    rc = Dgemm(s, false, false, n, pb * n, n, 1.0, dW, n, 0, dT, n, 0, 0.0, dB + (long)p0 * nn, n, 0,
+               1, false);
+    if (rc) return rc;
+  }
+  cudaMemcpyAsync(dB + (long)(m + 1) * nn, dW, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s);
+  return Dgemm(s, true, false, m + 2, m + 1, (int)nn, 1.0, dB, nn, 0, dAall, nn, 0, 0.0, dHaug, ldh, 0,
+               1, true);
+}

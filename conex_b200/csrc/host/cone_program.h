@@ -1,0 +1,193 @@
+// The IPM driver with device-resident workspaces — counterpart of the reference's
+// conex/cone_program.{h,cc}, conex/constraint_manager.h, conex/workspace.h and (for one dense
+// supernode) conex/kkt_solver.{h,cc} + conex/supernodal_assembler.{h,cc}.
+//
+// Host orchestration stays in C++ (loop control, mu rule, rescaling, termination, status); all
+// matrices and vectors of the Newton step live in HBM and are touched only by the cxb_* kernels.
+// Per iteration the host reads back O(10) scalars plus the Lanczos coefficients.
+#pragma once
+#include <any>
+#include <list>
+#include <memory>
+#include <vector>
+
+#include "constraint.h"
+
+namespace conex {
+
+enum : int {
+  CONEX_INITIALIZATION_MODE_COLDSTART = 0,
+  CONEX_INITIALIZATION_MODE_WARMSTART = 1,
+};
+enum : int { CONEX_LLT_FACTORIZATION = 0, CONEX_LDLT_FACTORIZATION = 1, CONEX_QR_FACTORIZATION = 2 };
+
+// reference cone_program.h:17-38 — same fields, same defaults.
+struct SolverConfiguration {
+  int prepare_dual_variables = 0;
+  int initialization_mode = 0;
+  double inv_sqrt_mu_max = 1000;
+  double minimum_mu = 1e-15;
+  double maximum_mu = 1e4;
+  double divergence_upper_bound = 1;
+  int enable_line_search = 0;
+  double dinf_upper_bound = 1;
+  int final_centering_steps = 5;
+  double final_centering_tolerance = .01;
+  int initial_centering_steps_warmstart = 0;
+  int initial_centering_steps_coldstart = 0;
+  double warmstart_abort_threshold = 2;
+  int max_iterations = 25;
+  double infeasibility_threshold = 1e5;
+  double kkt_error_tolerance = 1e10;
+  int kkt_solver = 0;
+  int enable_rescaling = 1;
+  int iterative_refinement_iterations = 0;
+};
+
+// reference cone_program.h:40-45
+struct ConexStatus {
+  int solved = 0;
+  int num_iterations = 0;
+  int primal_infeasible = 0;
+  int dual_infeasible = 0;
+};
+
+// Host-side iteration bookkeeping (reference workspace.h:73-117). The scalings persist across
+// solves so that a warm start reuses them (cone_program.cc:343-357).
+struct WorkspaceStats {
+  std::vector<double> sqrt_inv_mu;
+  double b_scaling = 1;
+  double c_scaling = 1;
+  int num_iter = 0;
+  bool initialized = false;
+};
+
+// What REPORT() prints per iteration in the reference (cone_program.cc:456-468).
+struct IterationRecord {
+  double inv_sqrt_mu, mu, d_2, d_inf, by, cx, kkt_error, step_size;
+  float milliseconds;  // device time of the whole Newton step (CUDA events on the program stream)
+  float phase_ms[5];   // assemble, factor, mu, solve, update (same events)
+};
+struct PhaseSeconds {
+  double assemble = 0, factor = 0, solve = 0, update = 0, mu = 0;
+};
+
+// A cone, its clique and its slice of the assembly (reference cone_program.h:47-57 `Container`
+// plus SupernodalAssembler, supernodal_assembler.h:56-131).
+class Container {
+ public:
+  template <typename T>
+  Container(const T& x, const std::vector<int>& vars)
+      : obj(x), constraint(std::any_cast<T>(&obj)), variables(vars) {}
+  std::any obj;
+  Constraint constraint;
+  std::vector<int> variables;
+  SchurComplementSystem submatrix_data_;
+  // The cone covers every variable in order: its G aliases the KKT matrix
+  // (reference supernodal_assembler.cc:72-93 `direct_update`).
+  bool direct_update = false;
+  bool identity_clique = false;
+  DeviceBuffer<int> d_variables;
+  DeviceBuffer<double> y_clique;
+};
+
+// Dense stand-in for SupernodalKKTSolver (reference kkt_solver.h:16-65): one supernode holding the
+// whole Schur complement, factored by the blocked device Cholesky.
+class DenseKKTSolver {
+ public:
+  DenseKKTSolver(DeviceContext* ctx, int N);
+  void Bind(std::list<Container>* eqs);  // symbolic step: who aliases H, who scatters
+  void Assemble();                       // reference kkt_solver.cc:164-170
+  bool Factor();                         // reference kkt_solver.cc:172-199 (LLT mode)
+  void SolveInPlace(Ref* b) const;       // reference kkt_solver.cc:220-263
+  Ref KKTMatrix() const { return Ref(H_.get(), N_, N_, ldh_); }
+  void SetSolverMode(int mode) { mode_ = mode; }
+  void SetIterativeRefinementIterations(int x) { iterative_refinement_iterations_ = x; }
+
+ private:
+  DeviceContext* ctx_;
+  int N_;
+  long ldh_;
+  DeviceBuffer<double> H_;
+  std::list<Container>* eqs_ = nullptr;
+  bool has_direct_ = false;
+  int mode_ = CONEX_LLT_FACTORIZATION;
+  int iterative_refinement_iterations_ = 0;
+};
+
+class Program {
+ public:
+  explicit Program(int number_of_variables) { SetNumberOfVariables(number_of_variables); }
+
+  void SetNumberOfVariables(int m) {
+    num_variables_ = m;
+    linear_cost_.assign(m, 0.0);
+  }
+  int GetNumberOfVariables() const { return num_variables_; }
+  int SizeOfKKTSystem() const { return num_variables_; }
+
+  // reference cone_program.h:191-218 / constraint_manager.h:50-70.
+  template <typename T>
+  bool AddConstraint(T&& d) {
+    std::vector<int> all(num_variables_);
+    for (int i = 0; i < num_variables_; i++) all[i] = i;
+    return AddConstraint(std::forward<T>(d), all);
+  }
+  template <typename T>
+  bool AddConstraint(T&& d, const std::vector<int>& variables) {
+    if (!VariablesAreUnique(variables)) return true;  // CONEX_FAILURE
+    using Cone = std::decay_t<T>;
+    eqs.emplace_back(static_cast<const Cone&>(d), variables);
+    eqs.back().constraint.bind(&ctx_);
+    constraints_.push_back(&eqs.back().constraint);
+    return false;  // CONEX_SUCCESS
+  }
+
+  int NumberOfConstraints() const { return static_cast<int>(eqs.size()); }
+  ConexStatus Status() const { return status_; }
+
+  // Copies the (rescaled) scaling point of cone i to host memory (reference cone_program.h:120-134).
+  void GetDualVariable(int i, double* host_out);
+  int GetDualVariableSize(int i);
+
+  bool AddLinearCost(const std::vector<double>& b);
+  void ClearLinearCosts() { linear_cost_.assign(num_variables_, 0.0); }
+
+  void InitializeWorkspace();  // reference cone_program.h:174-189 (device arena)
+
+  DeviceContext ctx_;
+  std::list<Container> eqs;  // std::list: addresses stay stable (constraint_manager.h:97-98)
+  std::vector<Constraint*> constraints_;
+  SchurComplementSystem sys;  // residual-only, program level (cone_program.cc:85-86)
+  WorkspaceStats stats;
+  std::unique_ptr<DenseKKTSolver> solver;
+  DeviceBuffer<double> memory_;  // the device arena: W, temporaries, per-cone G/AW/AQc, residuals
+  DeviceBuffer<double> vectors_;  // b, y, y2 (device copies of the host loop's m-vectors)
+  bool is_initialized = false;
+  ConexStatus status_;
+  std::vector<double> linear_cost_;
+
+  // diagnostics (not part of the reference ABI)
+  std::vector<IterationRecord> log;
+  PhaseSeconds seconds;
+  bool timing_enabled = false;
+  bool verbose = false;
+
+ private:
+  bool VariablesAreUnique(const std::vector<int>& x) const;
+  int num_variables_ = 0;
+};
+
+bool Initialize(Program& prog, const SolverConfiguration& config);
+// Maximises -linear_cost (reference cone_program.cc:235-533). Writes m doubles to host memory.
+bool Solve(Program& prog, const SolverConfiguration& config, double* primal_variable);
+// reference cone_program.cc:547-552
+bool Solve(const std::vector<double>& b, Program& prog, const SolverConfiguration& config,
+           double* primal_variable);
+// b = AW/2 at W = I: strictly feasible for both primal and dual (cone_program.cc:535-545).
+std::vector<double> GetFeasibleObjective(Program* prog);
+// Aggregates AW / AQc / {<w,c>, <c,Qc>} over all cones at the current iterate (after
+// solver->Assemble()) and copies them to host memory. Used by CONEXB200_AssembleNewtonSystem.
+void AssembleResidualsForExport(Program& prog, double* AW, double* AQc, double* scalars2);
+
+}  // namespace conex

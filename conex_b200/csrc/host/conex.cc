@@ -1,0 +1,408 @@
+// The conex C ABI (include/conex.h) on top of the device-resident Program — counterpart of the
+// reference's interfaces/conex.cc. Entry points on the Newton-step hot path are implemented; the
+// ones that build cones outside this round's scope (LP, SOC, Hermitian, quadratic costs) validate
+// their arguments like the reference and then report failure on stderr instead of silently doing
+// CPU work. Exceptions never cross the ABI: they are mapped to the call's failure value.
+#include <cuda_runtime_api.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "../../../include/conex_b200.h"
+#include "cone_program.h"
+#include "dense_lmi_constraint.h"
+#include "divergence.h"
+#include "tridiagonal_eigenvalues.h"
+
+namespace cxb {
+long g_launch_count = 0;
+}
+
+using conex::DenseLMIConstraint;
+using conex::Program;
+using conex::SolverConfiguration;
+
+namespace {
+
+// reference interfaces/conex.cc:20-33 (SAFER_CAST_TO_Program): null check only; the reference's
+// workspace-count heuristic has no device-side equivalent.
+#define CAST_PROGRAM_OR_FAIL(x, prog)                  \
+  CONEX_DEMAND(x, "Program pointer is null.");         \
+  Program* prog = static_cast<Program*>(x);
+
+SolverConfiguration Convert(const CONEX_SolverConfiguration* c) {
+  // reference interfaces/conex.cc:65-90
+  SolverConfiguration o;
+  o.prepare_dual_variables = c->prepare_dual_variables;
+  o.initialization_mode = c->initialization_mode;
+  o.inv_sqrt_mu_max = c->inv_sqrt_mu_max;
+  o.minimum_mu = c->minimum_mu;
+  o.maximum_mu = c->maximum_mu;
+  o.divergence_upper_bound = c->divergence_upper_bound;
+  o.enable_line_search = c->enable_line_search;
+  o.dinf_upper_bound = c->dinf_upper_bound;
+  o.final_centering_steps = c->final_centering_steps;
+  o.final_centering_tolerance = c->final_centering_tolerance;
+  o.initial_centering_steps_warmstart = c->initial_centering_steps_warmstart;
+  o.initial_centering_steps_coldstart = c->initial_centering_steps_coldstart;
+  o.warmstart_abort_threshold = c->warmstart_abort_threshold;
+  o.max_iterations = c->max_iterations;
+  o.iterative_refinement_iterations = c->iterative_refinement_iterations;
+  o.infeasibility_threshold = c->infeasibility_threshold;
+  o.kkt_error_tolerance = c->kkt_error_tolerance;
+  o.enable_rescaling = c->enable_rescaling;
+  o.kkt_solver = c->kkt_solver;
+  return o;
+}
+
+template <typename F>
+auto Guard(F&& f, decltype(f()) on_error) -> decltype(f()) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    std::cerr << e.what() << std::endl;
+    return on_error;
+  }
+}
+
+int NotOnHotPath(const char* what) {
+  std::cerr << "conex-b200: " << what
+            << " is outside the device hot path of this build (dense LMI / PSD cones only)."
+            << std::endl;
+  return CONEX_FAILURE;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* CONEX_CreateConeProgram() {
+  return Guard(
+      []() -> void* {
+        Program* p = new Program(0);
+        const char* v = std::getenv("CONEX_VERBOSE");
+        p->verbose = v && std::atoi(v) != 0;
+        return p;
+      },
+      nullptr);
+}
+
+void CONEX_DeleteConeProgram(void* prog) { delete static_cast<Program*>(prog); }
+
+CONEX_STATUS CONEX_SetNumberOfVariables(void* p, int m) {
+  // reference interfaces/conex.cc:399-407
+  CONEX_DEMAND(m >= 1, "Number of variables must be > 0.");
+  CAST_PROGRAM_OR_FAIL(p, prg);
+  CONEX_DEMAND(prg->GetNumberOfVariables() == 0, "Number of variables already set.");
+  prg->SetNumberOfVariables(m);
+  return CONEX_SUCCESS;
+}
+
+int CONEX_AddDenseLMIConstraint(void* prog, const double* A, int Ar, int Ac, int m, const double* c,
+                                int cr, int cc) {
+  // reference interfaces/conex.cc:137-160. A program created without SetNumberOfVariables takes
+  // its variable count from the first constraint.
+  (void)Ac;
+  (void)cr;
+  (void)cc;
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
+        const int id = program.NumberOfConstraints();
+        program.AddConstraint(DenseLMIConstraint(Ar, m, A, c));
+        return id;
+      },
+      -1);
+}
+
+int CONEX_AddSparseLMIConstraint(void* prog, const double* A, int Ar, int Ac, int num_vars,
+                                 const double* c, int cr, int cc, const long* vars, int vars_rows) {
+  // reference interfaces/conex.cc:162-188
+  (void)Ac;
+  (void)cr;
+  (void)cc;
+  (void)vars_rows;
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        std::vector<int> variables(num_vars);
+        for (int i = 0; i < num_vars; i++) variables[i] = static_cast<int>(vars[i]);
+        const int id = program.NumberOfConstraints();
+        program.AddConstraint(DenseLMIConstraint(Ar, num_vars, A, c), variables);
+        return id;
+      },
+      -1);
+}
+
+int CONEXB200_AddDenseLMIConstraintDevice(void* prog, const double* d_A, int n, int m,
+                                          const double* d_C) {
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
+        const int id = program.NumberOfConstraints();
+        program.AddConstraint(DenseLMIConstraint(n, m, DenseLMIConstraint::DevicePointers{d_A, d_C}));
+        return id;
+      },
+      -1);
+}
+
+int CONEX_Maximize(void* prog_ptr, const double* b, int br, const CONEX_SolverConfiguration* config,
+                   double* y, int yr) {
+  // reference interfaces/conex.cc:93-105
+  (void)yr;
+  return Guard(
+      [&]() -> int {
+        Program& prog = *static_cast<Program*>(prog_ptr);
+        std::vector<double> blinear(b, b + br);
+        return conex::Solve(blinear, prog, Convert(config), y) ? 1 : 0;
+      },
+      0);
+}
+
+int CONEX_Solve(void* prog_ptr, const CONEX_SolverConfiguration* config, double* y, int yr) {
+  // reference interfaces/conex.cc:107-112
+  (void)yr;
+  return Guard(
+      [&]() -> int {
+        Program& prog = *static_cast<Program*>(prog_ptr);
+        return conex::Solve(prog, Convert(config), y) ? 1 : 0;
+      },
+      0);
+}
+
+void CONEX_GetDualVariable(void* prog_ptr, int i, double* x, int xr, int xc) {
+  // reference interfaces/conex.cc:114-122
+  (void)xr;
+  (void)xc;
+  Guard(
+      [&]() -> int {
+        static_cast<Program*>(prog_ptr)->GetDualVariable(i, x);
+        return 0;
+      },
+      0);
+}
+
+int CONEX_GetDualVariableSize(void* prog_ptr, int i) {
+  return Guard([&]() -> int { return static_cast<Program*>(prog_ptr)->GetDualVariableSize(i); }, 1);
+}
+
+void CONEX_SetDefaultOptions(CONEX_SolverConfiguration* c) {
+  // reference interfaces/conex.cc:231-257; additionally sets the two fields the reference forgets
+  // (iterative_refinement_iterations, kkt_solver), which callers with stack structs otherwise
+  // pass uninitialised.
+  if (c == nullptr) {
+    std::cerr << "Received null pointer.";
+    return;
+  }
+  const SolverConfiguration d;
+  c->prepare_dual_variables = d.prepare_dual_variables;
+  c->initialization_mode = d.initialization_mode;
+  c->inv_sqrt_mu_max = d.inv_sqrt_mu_max;
+  c->minimum_mu = d.minimum_mu;
+  c->maximum_mu = d.maximum_mu;
+  c->divergence_upper_bound = d.divergence_upper_bound;
+  c->enable_line_search = d.enable_line_search;
+  c->dinf_upper_bound = d.dinf_upper_bound;
+  c->final_centering_steps = d.final_centering_steps;
+  c->final_centering_tolerance = d.final_centering_tolerance;
+  c->initial_centering_steps_warmstart = d.initial_centering_steps_warmstart;
+  c->initial_centering_steps_coldstart = d.initial_centering_steps_coldstart;
+  c->warmstart_abort_threshold = d.warmstart_abort_threshold;
+  c->max_iterations = d.max_iterations;
+  c->iterative_refinement_iterations = d.iterative_refinement_iterations;
+  c->infeasibility_threshold = d.infeasibility_threshold;
+  c->kkt_error_tolerance = d.kkt_error_tolerance;
+  c->enable_rescaling = d.enable_rescaling;
+  c->kkt_solver = d.kkt_solver;
+}
+
+void CONEX_GetIterationStats(void* prog, CONEX_IterationStats* stats, int iter_num_circular) {
+  // reference interfaces/conex.cc:259-285
+  if (prog == nullptr || stats == nullptr) {
+    std::cerr << "Received null pointer.";
+    return;
+  }
+  Program& program = *static_cast<Program*>(prog);
+  if (!program.stats.initialized) {
+    std::cerr << "No statistics available.";
+    return;
+  }
+  int iter = iter_num_circular;
+  if (iter < 0) iter = program.stats.num_iter + iter;
+  if (program.stats.num_iter <= iter || iter < 0) {
+    std::cerr << "Specified iteration is out of bounds.";
+    return;
+  }
+  const double k = program.stats.sqrt_inv_mu[iter];
+  stats->mu = 1.0 / (k * k);
+  stats->iteration_number = iter;
+}
+
+// ---- entry points whose cones are not on this round's device hot path ---------------------------
+int CONEX_AddDenseLinearConstraint(void*, const double*, int, int, const double*, int) {
+  NotOnHotPath("CONEX_AddDenseLinearConstraint (LP cone)");
+  return -1;
+}
+int CONEX_AddLinearInequalities(void*, const double*, int, int, const double*, int, const double*,
+                                int) {
+  NotOnHotPath("CONEX_AddLinearInequalities (LP cone / equalities)");
+  return -1;
+}
+int CONEX_AddQuadraticCost(void*, const double*, int, int) {
+  return NotOnHotPath("CONEX_AddQuadraticCost");
+}
+CONEX_STATUS CONEX_NewLinearMatrixInequality(void* p, int order, int hyper_complex_dim,
+                                             int* constraint_id) {
+  // argument validation as in the reference (interfaces/conex.cc:287-316)
+  CONEX_DEMAND(order >= 1, "Invalid LMI dimensions.");
+  CONEX_DEMAND(constraint_id, "Received output null pointer.");
+  CONEX_DEMAND(hyper_complex_dim == 1 || hyper_complex_dim == 2 || hyper_complex_dim == 4 ||
+                   hyper_complex_dim == 8,
+               "Hypercomplex dimension must be 1, 2, 4, or 8.");
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_NewLinearMatrixInequality (HermitianPsdConstraint)");
+}
+CONEX_STATUS CONEX_UpdateLinearOperator(void* p, int, double, int, int, int, int) {
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_UpdateLinearOperator");
+}
+CONEX_STATUS CONEX_UpdateAffineTerm(void* p, int, double, int, int, int) {
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_UpdateAffineTerm");
+}
+CONEX_STATUS CONEX_NewLorentzConeConstraint(void* p, int order, int* constraint_id) {
+  CONEX_DEMAND(order >= 1, "Received invalid n. Second order cone must have order (n + 1) >= 2.");
+  CONEX_DEMAND(constraint_id, "Received output null pointer.");
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_NewLorentzConeConstraint");
+}
+CONEX_STATUS CONEX_NewLinearInequality(void* p, int, int* constraint_id) {
+  CONEX_DEMAND(constraint_id, "Received output null pointer.");
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_NewLinearInequality");
+}
+CONEX_STATUS CONEX_NewQuadraticCost(void* p, int* constraint_id) {
+  CONEX_DEMAND(constraint_id, "Received output null pointer.");
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_NewQuadraticCost");
+}
+CONEX_STATUS CONEX_UpdateQuadraticCostMatrix(void* p, int, double, int, int) {
+  CONEX_DEMAND(p, "Program pointer is null.");
+  return NotOnHotPath("CONEX_UpdateQuadraticCostMatrix");
+}
+
+// ---- CONEXB200_* extensions ----------------------------------------------------------------------
+void CONEXB200_FeasibleObjective(void* prog, double* b) {
+  Guard(
+      [&]() -> int {
+        const auto v = conex::GetFeasibleObjective(static_cast<Program*>(prog));
+        std::memcpy(b, v.data(), sizeof(double) * v.size());
+        return 0;
+      },
+      0);
+}
+
+void CONEXB200_GetStatus(void* prog, int* out4) {
+  const conex::ConexStatus s = static_cast<Program*>(prog)->Status();
+  out4[0] = s.solved;
+  out4[1] = s.num_iterations;
+  out4[2] = s.primal_infeasible;
+  out4[3] = s.dual_infeasible;
+}
+
+int CONEXB200_GetIterationLog(void* prog, int iter, double* out8) {
+  const auto& log = static_cast<Program*>(prog)->log;
+  if (iter < 0 || iter >= static_cast<int>(log.size())) return 0;
+  const auto& r = log[iter];
+  const double v[8] = {r.inv_sqrt_mu, r.mu, r.d_2, r.d_inf, r.by, r.cx, r.kkt_error, r.step_size};
+  std::memcpy(out8, v, sizeof(v));
+  return 1;
+}
+
+int CONEXB200_GetIterationMilliseconds(void* prog, int iter, double* ms) {
+  const auto& log = static_cast<Program*>(prog)->log;
+  if (iter < 0 || iter >= static_cast<int>(log.size())) return 0;
+  *ms = log[iter].milliseconds;
+  return 1;
+}
+
+int CONEXB200_GetIterationPhaseMilliseconds(void* prog, int iter, double* out5) {
+  const auto& log = static_cast<Program*>(prog)->log;
+  if (iter < 0 || iter >= static_cast<int>(log.size())) return 0;
+  for (int p = 0; p < 5; p++) out5[p] = log[iter].phase_ms[p];
+  return 1;
+}
+
+void CONEXB200_SetTiming(void* prog, int enabled) {
+  static_cast<Program*>(prog)->timing_enabled = enabled != 0;
+}
+
+void CONEXB200_GetPhaseSeconds(void* prog, double* out5) {
+  const auto& s = static_cast<Program*>(prog)->seconds;
+  out5[0] = s.assemble;
+  out5[1] = s.factor;
+  out5[2] = s.solve;
+  out5[3] = s.update;
+  out5[4] = s.mu;
+}
+
+void CONEXB200_AssembleNewtonSystem(void* prog_ptr, int coldstart, double* H, double* AW,
+                                    double* AQc, double* scalars2) {
+  Guard(
+      [&]() -> int {
+        Program& prog = *static_cast<Program*>(prog_ptr);
+        SolverConfiguration cfg;
+        cfg.initialization_mode = coldstart ? conex::CONEX_INITIALIZATION_MODE_COLDSTART
+                                            : conex::CONEX_INITIALIZATION_MODE_WARMSTART;
+        conex::Initialize(prog, cfg);
+        prog.solver->Assemble();
+        // residual aggregation is internal to cone_program.cc; GetFeasibleObjective path reuses it
+        const int m = prog.SizeOfKKTSystem();
+        const conex::Ref Hd = prog.solver->KKTMatrix();
+        if (cudaMemcpy2DAsync(H, sizeof(double) * m, Hd.data, sizeof(double) * Hd.ld,
+                              sizeof(double) * m, m, cudaMemcpyDeviceToHost,
+                              prog.ctx_.cuda_stream()) != cudaSuccess) {
+          throw std::runtime_error("conex-b200: D2H copy of H failed");
+        }
+        prog.ctx_.Synchronize();
+        conex::AssembleResidualsForExport(prog, AW, AQc, scalars2);
+        return 0;
+      },
+      0);
+}
+
+// Host-logic probes (no GPU needed): the mu rule and the Jacobi-matrix eigenvalue extremes.
+double CONEXB200_DivergenceUpperBoundInverse(double bound, double frobenius_norm_squared,
+                                             double trace, double lambda_min, double lambda_max,
+                                             double rank) {
+  conex::WeightedSlackEigenvalues p;
+  p.frobenius_norm_squared = frobenius_norm_squared;
+  p.trace = trace;
+  p.lambda_min = lambda_min;
+  p.lambda_max = lambda_max;
+  p.rank = rank;
+  return conex::DivergenceUpperBoundInverse(bound, p);
+}
+
+void CONEXB200_TridiagonalExtremes(int n, const double* alpha, const double* beta, double* out2) {
+  const auto mm = conex::ExtremeEigenvaluesOfTridiagonal(
+      std::vector<double>(alpha, alpha + n), std::vector<double>(beta, beta + (n > 0 ? n - 1 : 0)));
+  out2[0] = mm.first;
+  out2[1] = mm.second;
+}
+
+long CONEXB200_LaunchCount() { return cxb::g_launch_count; }
+
+int CONEXB200_DeviceAvailable() {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// The dense-LMI / PSD cone plugin with device-resident state — counterpart of the reference's
+// PsdConstraint (conex/psd_constraint.{h,cc}) and DenseLMIConstraint
+// (conex/dense_lmi_constraint.{h,cc}).
+//
+//   c - sum_i y_i A_i  in  PSD(n),   A_i, c symmetric n x n.
+//
+// Device layout (HBM): `Aall` holds the m constraint matrices followed by the affine term C as
+// m+1 contiguous column-major n x n blocks, i.e. the n^2 x (m+1) matrix [vec(A_0) .. vec(A_{m-1})
+// vec(C)] (reference keeps three host copies: constraint_matrices_, constraint_matrices_vect_,
+// constraint_affine_; dense_lmi_constraint.h:13-15). W, temp_1, temp_2 are carved from the
+// program's device arena exactly like WorkspaceDensePSD (psd_constraint.h:9-37), so a warm start
+// finds the iterate where the previous solve left it.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "constraint.h"
+
+namespace conex {
+
+struct WorkspaceDensePSD {
+  explicit WorkspaceDensePSD(int n) : n_(n) {}
+  static size_t size_of(int n) {
+    return 3 * WorkspaceSchurComplement::Aligned(static_cast<size_t>(n) * n);
+  }
+  friend size_t SizeOf(const WorkspaceDensePSD& o) { return size_of(o.n_); }
+  friend void Initialize(WorkspaceDensePSD* o, double* data) {
+    const size_t stride = WorkspaceSchurComplement::Aligned(static_cast<size_t>(o->n_) * o->n_);
+    o->W = Ref(data, o->n_, o->n_);
+    o->temp_1 = Ref(data + stride, o->n_, o->n_);
+    o->temp_2 = Ref(data + 2 * stride, o->n_, o->n_);
+  }
+  Ref W, temp_1, temp_2;
+  int n_;
+};
+
+class DenseLMIConstraint {
+ public:
+  // Host data: `A` = m contiguous column-major n x n matrices, `C` = n x n (copied to the device;
+  // the caller may free them — reference interfaces/conex.cc:137-160).
+  DenseLMIConstraint(int n, int m, const double* A, const double* C);
+  // Device data (both pointers on the current device); copied device-to-device.
+  struct DevicePointers {
+    const double* A;
+    const double* C;
+  };
+  DenseLMIConstraint(int n, int m, DevicePointers dev);
+
+  WorkspaceDensePSD* workspace() { return &workspace_; }
+  int number_of_variables() const { return m_; }
+  int order() const { return n_; }
+  void bind(DeviceContext* ctx) { ctx_ = ctx; }
+  const double* device_matrices() const;  // Aall
+
+  friend int Rank(const DenseLMIConstraint& o) { return o.n_; }
+  friend void SetIdentity(DenseLMIConstraint* o);
+  friend void ConstructSchurComplementSystem(DenseLMIConstraint* o, bool initialize,
+                                             SchurComplementSystem* sys);
+  friend void PrepareStep(DenseLMIConstraint* o, const StepOptions& opt, const Ref& y, StepInfo*);
+  friend bool TakeStep(DenseLMIConstraint* o, const StepOptions& opt);
+  friend void GetWeightedSlackEigenvalues(DenseLMIConstraint* o, const Ref& y, double c_weight,
+                                          WeightedSlackEigenvalues* p);
+
+ private:
+  struct Storage;
+  void EnsureScratch();
+  // minus_s = sum_i y_i A_i - k C  (reference ComputeNegativeSlack, dense_lmi_constraint.cc:22-27)
+  void ComputeNegativeSlack(double k, const Ref& y, Ref* minus_s);
+  // Two-sided Lanczos extreme Ritz values of WS w.r.t. W started from column `index` of R, plus
+  // tr(WS) and tr(WS WS). Synchronises the stream.
+  struct SpectrumEstimate {
+    double ritz_min, ritz_max, trace, trace_of_square;
+  };
+  SpectrumEstimate EstimateSpectrum(const Ref& WS, const Ref& start_matrix);
+
+  int n_;
+  int m_;
+  WorkspaceDensePSD workspace_;
+  std::shared_ptr<Storage> data_;
+  DeviceContext* ctx_ = nullptr;
+};
+
+}  // namespace conex

@@ -1,0 +1,67 @@
+/* conex-b200 extensions to the conex C ABI (include/conex.h).
+ *
+ * None of these exist in the reference; they expose what its C++ tests reach through conex/*.h
+ * (GetFeasibleObjective, Program::Status, the REPORT() stream) plus device-resident construction
+ * and timing hooks needed to benchmark on the GPU. All take the opaque program handle returned by
+ * CONEX_CreateConeProgram. Host pointers unless a parameter is named d_*.
+ */
+#ifndef CONEX_B200_H
+#define CONEX_B200_H
+#include "conex.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* b = AW/2 at W = I (reference GetFeasibleObjective, cone_program.cc:535-545). Writes m doubles. */
+void CONEXB200_FeasibleObjective(void* prog, double* b);
+
+/* out4 = {solved, num_iterations, primal_infeasible, dual_infeasible} (Program::Status()). */
+void CONEXB200_GetStatus(void* prog, int* out4);
+
+/* out8 = {inv_sqrt_mu, mu, d_2, d_inf, by, cx, kkt_error, step_size} of iteration `iter` of the
+ * last solve — the values the reference REPORT()s to stdout (cone_program.cc:456-468).
+ * Returns 1, or 0 when `iter` is out of range. */
+int CONEXB200_GetIterationLog(void* prog, int iter, double* out8);
+
+/* Device time (ms, CUDA events on the program's stream) of Newton step `iter` of the last solve;
+ * returns 0 when out of range. */
+int CONEXB200_GetIterationMilliseconds(void* prog, int iter, double* ms);
+
+/* Device milliseconds of the five phases of Newton step `iter`: out5 = {assemble, factor, mu, solve,
+ * update} (CUDA events at the phase boundaries, cone_program.cc:338-437 in the reference). */
+int CONEXB200_GetIterationPhaseMilliseconds(void* prog, int iter, double* out5);
+
+/* Wall-clock seconds per phase {assemble, factor, solve, update, mu} of the last solve, the five
+ * phases the reference wraps in START_TIMER (cone_program.cc:338-437). Summed from the per-iteration
+ * CUDA events; CONEXB200_SetTiming is kept for ABI stability and has no effect. */
+void CONEXB200_SetTiming(void* prog, int enabled);
+void CONEXB200_GetPhaseSeconds(void* prog, double* out5);
+
+/* Assembles the Newton system at the current iterate (coldstart != 0: at W = I) and copies it to
+ * host memory: H (m x m column-major, lower triangle valid), AW, AQc (m), scalars2 = {<w,c>, <c,Qc>}. */
+void CONEXB200_AssembleNewtonSystem(void* prog, int coldstart, double* H, double* AW, double* AQc,
+                                    double* scalars2);
+
+/* CONEX_AddDenseLMIConstraint with the matrices already in device memory (d_A: m contiguous
+ * column-major n x n blocks, d_C: n x n). The data is copied device-to-device. */
+int CONEXB200_AddDenseLMIConstraintDevice(void* prog, const double* d_A, int n, int m,
+                                          const double* d_C);
+
+/* Host-logic probes that need no GPU: the closed-form mu rule (reference divergence.cc:96-111) and
+ * the extreme eigenvalues of a Lanczos Jacobi matrix (alpha: n, beta: n-1; out2 = {min, max}). */
+double CONEXB200_DivergenceUpperBoundInverse(double bound, double frobenius_norm_squared,
+                                             double trace, double lambda_min, double lambda_max,
+                                             double rank);
+void CONEXB200_TridiagonalExtremes(int n, const double* alpha, const double* beta, double* out2);
+
+/* Number of CUDA kernels launched by this library in the current process so far. */
+long CONEXB200_LaunchCount();
+
+/* 1 when a CUDA device of compute capability 10.x is usable, else 0 (the library has no CPU path:
+ * solves then fail with a message on stderr). */
+int CONEXB200_DeviceAvailable();
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,363 @@
+"""Kernel-level parity tests: every cxb_* entry point (include/conex_b200_device.h) against the CPU
+oracle / numpy on identical seeded inputs. Integer/index outputs must match exactly; FP64 results
+are compared at the tolerance BASELINE.json states for the Newton system (1e-10 relative,
+reordered summation), tightened where the kernel allows.
+"""
+import numpy as np
+import pytest
+
+from harness import dptr, fmat, oracle, pack_matrices, random_dense_lmi, random_sym
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(x, ref):
+    return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import devlib
+    return devlib
+
+
+def run_gemm(dev, ta, tb, M, N, K, alpha, beta, rng, lower=False, batch=1):
+    import torch
+    L = dev.product().lib
+    As = [rng.standard_normal((K, M) if ta else (M, K)) for _ in range(batch)]
+    Bs = [rng.standard_normal((N, K) if tb else (K, N)) for _ in range(batch)]
+    Cs = [rng.standard_normal((M, N)) for _ in range(batch)]
+    dA = torch.stack([dev.to_dev(a) for a in As]).contiguous()
+    dB = torch.stack([dev.to_dev(b) for b in Bs]).contiguous()
+    dC = torch.stack([dev.to_dev(c) for c in Cs]).contiguous()
+    lda = As[0].shape[0]
+    ldb = Bs[0].shape[0]
+    rc = L.cxb_dgemm(None, int(ta), int(tb), M, N, K, alpha, dev.ptr(dA), lda, As[0].size, dev.ptr(dB),
+                     ldb, Bs[0].size, beta, dev.ptr(dC), M, M * N, batch, int(lower))
+    assert rc == 0
+    torch.cuda.synchronize()
+    out = dC.cpu().numpy()
+    for i in range(batch):
+        opA = As[i].T if ta else As[i]
+        opB = Bs[i].T if tb else Bs[i]
+        ref = alpha * opA @ opB + beta * Cs[i]
+        got = out[i].T
+        if lower:
+            mask = np.tril(np.ones((M, N), dtype=bool))
+            assert rel_err(got[mask], ref[mask]) < 1e-13
+            assert np.array_equal(got[~mask], Cs[i][~mask])  # strictly-upper part untouched
+        else:
+            assert rel_err(got, ref) < 1e-13, (ta, tb, M, N, K)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(50, 50, 50), (64, 64, 16), (129, 257, 77), (33, 17, 5),
+                                   (300, 200, 1000), (128, 128, 4), (1, 1, 1), (257, 131, 64)])
+def test_dgemm_layouts_and_ragged_shapes(dev, ta, tb, shape):
+    rng = np.random.default_rng(hash((ta, tb) + shape) % 2**32)
+    M, N, K = shape
+    run_gemm(dev, ta, tb, M, N, K, 1.0, 0.0, rng)
+    run_gemm(dev, ta, tb, M, N, K, -0.5, 2.0, rng)
+
+
+def test_dgemm_batched_and_lower(dev):
+    rng = np.random.default_rng(7)
+    run_gemm(dev, 0, 0, 50, 50, 50, 1.0, 0.0, rng, batch=5)
+    run_gemm(dev, 1, 0, 100, 100, 2500, 1.0, 0.0, rng, lower=True)
+    run_gemm(dev, 0, 1, 300, 300, 128, -1.0, 1.0, rng, lower=True)
+    run_gemm(dev, 1, 0, 259, 258, 900, 1.0, 0.0, rng, lower=True)  # trapezoid, ragged tiles
+    run_gemm(dev, 1, 0, 131, 130, 49, 1.0, 0.0, rng, lower=True)   # odd K -> 8-byte copies
+
+
+def test_dgemm_zero_k_and_empty(dev):
+    import torch
+    L = dev.product().lib
+    C0 = np.arange(12.0).reshape(3, 4)
+    dC = dev.to_dev(C0)
+    dA = dev.dzeros(4)
+    assert L.cxb_dgemm(None, 0, 0, 3, 4, 0, 1.0, dev.ptr(dA), 3, 0, dev.ptr(dA), 1, 0, 2.0, dev.ptr(dC), 3,
+                       0, 1, 0) == 0
+    assert np.allclose(dev.from_dev(dC), 2.0 * C0)
+    assert L.cxb_dgemm(None, 0, 0, 0, 4, 5, 1.0, dev.ptr(dA), 1, 0, dev.ptr(dA), 5, 0, 0.0, dev.ptr(dC), 1,
+                       0, 1, 0) == 0
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n,m,seed", [(10, 7, 1), (50, 100, 2), (33, 20, 3), (4, 1, 4), (16, 129, 5)])
+def test_schur_dense_lmi_matches_oracle(dev, n, m, seed):
+    """K1+K2: H_ij = tr(A_i W A_j W), AW, AQc, <w,c>, <c,Qc> within 1e-10 relative of the oracle."""
+    import torch
+    L = dev.product().lib
+    O = oracle().lib
+    mats, _ = random_dense_lmi(n, m, seed)
+    rng = np.random.default_rng(seed + 100)
+    Cm = random_sym(rng, n) + np.eye(n)
+    R = rng.standard_normal((n, n))
+    W = R @ R.T / n + 0.1 * np.eye(n)
+    A = pack_matrices(mats)
+    G = np.zeros((m, m), order="F")
+    AW = np.zeros(m)
+    AQc = np.zeros(m)
+    sc = np.zeros(2)
+    O.ORACLE_SchurDenseLMI(n, m, dptr(A), dptr(fmat(Cm)), dptr(fmat(W)), 0, dptr(G), dptr(AW), dptr(AQc),
+                           dptr(sc))
+    Aall = np.concatenate([A.ravel(), np.asfortranarray(Cm).ravel(order="F")])
+    dA = torch.from_numpy(Aall).cuda()
+    dW = dev.to_dev(W)
+    dB = dev.dzeros((m + 2) * n * n)
+    for panel in (1, 3, m + 1):
+        dT = dev.dzeros(panel * n * n)
+        ldh = (m + 3) & ~1
+        dH = dev.dzeros(ldh * (m + 2))
+        assert L.cxb_schur_dense_lmi(None, n, m, dev.ptr(dA), dev.ptr(dW), dev.ptr(dB), dev.ptr(dT), panel,
+                                     dev.ptr(dH), ldh) == 0
+        Haug = dev.from_dev(dH, ldh, m + 2)
+        H = np.tril(Haug[:m, :m])
+        scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
+        assert (np.abs(H - np.tril(G)) / scale).max() < 1e-10
+        assert rel_err(Haug[m, :m], AQc) < 1e-10
+        assert rel_err(Haug[m + 1, :m], AW) < 1e-10
+        assert abs(Haug[m + 1, m] - sc[0]) <= 1e-10 * abs(sc[0])
+        assert abs(Haug[m, m] - sc[1]) <= 1e-10 * abs(sc[1])
+
+
+@pytest.mark.parametrize("m", [1, 5, 100, 128, 129, 300, 1000])
+def test_potrf_and_potrs(dev, m):
+    """K3/K5 against numpy's Cholesky and solve; lower triangle only is read."""
+    import torch
+    L = dev.product().lib
+    rng = np.random.default_rng(m)
+    R = rng.standard_normal((m, m + 5))
+    H = R @ R.T + m * np.eye(m)
+    ld = m + 2
+    Hp = np.zeros((ld, m))
+    Hp[:m, :] = np.tril(H) + np.triu(np.full((m, m), np.nan), 1)  # upper part must never be read
+    dH = dev.to_dev(Hp)
+    info = dev.izeros(1)
+    assert L.cxb_potrf_lower(None, m, dev.ptr(dH), ld, None, dev.ptr(info)) == 0
+    torch.cuda.synchronize()
+    assert int(info.cpu()[0]) == 0
+    Ld = np.tril(dev.from_dev(dH, ld, m)[:m, :])
+    Lref = np.linalg.cholesky(H)
+    assert rel_err(Ld, Lref) < 1e-12
+    for nrhs in (1, 3):
+        B = rng.standard_normal((m, nrhs))
+        dX = dev.to_dev(B)
+        assert L.cxb_potrs_lower(None, m, dev.ptr(dH), ld, dev.ptr(dX), m, nrhs) == 0
+        X = dev.from_dev(dX)
+        assert rel_err(H @ X, B) < 1e-10
+
+
+def test_potrf_reports_non_positive_pivot(dev):
+    import torch
+    L = dev.product().lib
+    m = 200
+    rng = np.random.default_rng(0)
+    R = rng.standard_normal((m, m))
+    H = R @ R.T + np.eye(m)
+    H[150, 150] = -1.0  # not positive definite: the failing pivot is at or before column 150
+    dH = dev.to_dev(np.tril(H))
+    info = dev.izeros(1)
+    assert L.cxb_potrf_lower(None, m, dev.ptr(dH), m, None, dev.ptr(info)) == 0
+    torch.cuda.synchronize()
+    assert 1 <= int(info.cpu()[0]) <= 151
+
+
+@pytest.mark.parametrize("nn,cols", [(2500, 101), (9, 3), (10000, 1030), (49, 7)])
+def test_gemv_n(dev, nn, cols):
+    L = dev.product().lib
+    rng = np.random.default_rng(nn)
+    A = rng.standard_normal((nn, cols))
+    x = rng.standard_normal(cols)
+    dA, dx, dy = dev.to_dev(A), dev.to_dev(x), dev.dzeros(nn)
+    assert L.cxb_gemv_n(None, nn, cols, dev.ptr(dA), dev.ptr(dx), dev.ptr(dy)) == 0
+    assert rel_err(dev.from_dev(dy), A @ x) < 1e-13
+
+
+def lanczos_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((n, n))
+    W = R @ R.T / n + 0.05 * np.eye(n)
+    W = 0.5 * (W + W.T)
+    S = random_sym(rng, n)
+    return W, S, W @ S
+
+
+@pytest.mark.parametrize("n,seed", [(4, 1), (25, 2), (64, 3), (200, 4), (7, 5)])
+def test_two_sided_lanczos_matches_oracle(dev, n, seed):
+    """K7: alpha/beta of the Jacobi matrix and the Ritz extremes vs. the oracle's recurrence."""
+    import torch
+    L = dev.product().lib
+    O = oracle().lib
+    W, S, WS = lanczos_inputs(n, seed)
+    num_iter = max(n // 2, 1)
+    idx = int(np.argmax(np.diag(WS)))
+    r = S[:, idx].copy()
+    ev = np.zeros(num_iter)
+    k = O.ORACLE_ApproximateEigenvalues(n, dptr(fmat(WS)), dptr(fmat(W)), dptr(r), num_iter, dptr(ev))
+    dWS, dW, dS = dev.to_dev(WS), dev.to_dev(W), dev.to_dev(S)
+    red = dev.dzeros(8)
+    assert L.cxb_ws_reductions(None, n, dev.ptr(dWS), dev.ptr(red)) == 0
+    r4 = dev.from_dev(red)
+    assert int(r4[2]) == idx
+    assert abs(r4[0] - np.trace(WS)) < 1e-12 * max(1, abs(np.trace(WS)))
+    assert abs(r4[1] - np.trace(WS @ WS)) < 1e-12 * abs(np.trace(WS @ WS))
+    alpha, beta, cnt = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(1)
+    work = dev.dzeros(L.cxb_lanczos_worksize(n))
+    idx_dev = red[2:3]
+    assert L.cxb_lanczos_two_sided(None, n, dev.ptr(dWS), dev.ptr(dW), dev.ptr(dS), dev.ptr(idx_dev),
+                                   num_iter, dev.ptr(alpha), dev.ptr(beta), dev.ptr(cnt),
+                                   dev.ptr(work)) == 0
+    torch.cuda.synchronize()
+    c = int(cnt.cpu()[0])
+    assert c + 1 == k
+    a = alpha.cpu().numpy()[: c + 1]
+    b = beta.cpu().numpy()[:c]
+    T = np.diag(a) + np.diag(b, 1) + np.diag(b, -1)
+    ritz = np.linalg.eigvalsh(T)
+    tol = 1e-9 * max(1.0, np.abs(ev[:k]).max())
+    assert abs(ritz[0] - ev[0]) < tol and abs(ritz[-1] - ev[k - 1]) < tol
+
+
+def test_lanczos_golden_4x4(dev):
+    """Reference known answer (conex/test/approximate_eigenvalues.cc:16-42): n steps on the 4x4
+    matrix from r0 = (1,2,0,4) reproduce the exact spectrum of W*A to 1e-12."""
+    import torch
+    L = dev.product().lib
+    A = np.array([[3, 1, 0, 1], [1, 3, 1, 0], [0, 1, 4, 1], [1, 0, 1, 5]], float)
+    A /= np.trace(A)
+    rng = np.random.default_rng(0)
+    R = rng.uniform(-1, 1, (4, 4))
+    W = R @ R.T
+    WS = W @ A
+    r0 = np.array([1.0, 2, 0, 4])
+    alpha, beta, cnt = dev.dzeros(5), dev.dzeros(5), dev.izeros(1)
+    work = dev.dzeros(L.cxb_lanczos_worksize(4))
+    assert L.cxb_lanczos_two_sided(None, 4, dev.ptr(dev.to_dev(WS)), dev.ptr(dev.to_dev(W)),
+                                   dev.ptr(dev.to_dev(r0)), None, 4, dev.ptr(alpha), dev.ptr(beta),
+                                   dev.ptr(cnt), dev.ptr(work)) == 0
+    torch.cuda.synchronize()
+    c = int(cnt.cpu()[0])
+    assert c == 3
+    a, b = alpha.cpu().numpy()[:4], beta.cpu().numpy()[:3]
+    ritz = np.linalg.eigvalsh(np.diag(a) + np.diag(b, 1) + np.diag(b, -1))
+    exact = np.sort(np.linalg.eigvals(WS).real)
+    assert np.abs(ritz - exact).max() < 1e-12
+
+
+@pytest.mark.parametrize("n", [4, 5, 31, 50, 129, 300])
+def test_pade_expm_matches_oracle(dev, n):
+    """K8 (Padé + pivoted LU): against the oracle's restatement of exponential_map_pade.cc."""
+    import torch
+    L = dev.product().lib
+    O = oracle().lib
+    rng = np.random.default_rng(n)
+    if n == 4:
+        X = np.array([[3, 1, 0, 1], [1, 3, 1, 0], [0, 1, 4, 1], [1, 0, 1, 5]], float)
+        X /= np.trace(X)
+    else:
+        X = rng.standard_normal((n, n))
+        X *= 1.2 / np.linalg.norm(X, 2)
+    ref = np.zeros((n, n), order="F")
+    O.ORACLE_PadeExpm(n, dptr(fmat(X)), dptr(ref))
+    dX, dout = dev.to_dev(X), dev.dzeros(n * n)
+    work, iwork, info = dev.dzeros(4 * n * n), dev.izeros(2 * n + 2), dev.izeros(1)
+    assert L.cxb_pade_expm(None, n, dev.ptr(dX), dev.ptr(dout), dev.ptr(work), dev.ptr(iwork),
+                           dev.ptr(info)) == 0
+    got = dev.from_dev(dout, n, n)
+    assert int(info.cpu()[0]) == 0
+    assert rel_err(got, ref) < 1e-11
+    if n == 4:
+        import scipy.linalg
+        assert np.abs(got - scipy.linalg.expm(X)).max() < 1e-7  # exponential_map_pade_test.cc:16-37
+
+
+@pytest.mark.parametrize("n,nrhs", [(3, 2), (40, 40), (100, 7), (257, 257)])
+def test_lu_solve_with_pivoting(dev, n, nrhs):
+    L = dev.product().lib
+    rng = np.random.default_rng(n + nrhs)
+    A = rng.standard_normal((n, n))
+    A[0, 0] = 0.0  # forces a row interchange in the first column
+    B = rng.standard_normal((n, nrhs))
+    dA, dB = dev.to_dev(A), dev.to_dev(B)
+    ipiv, info = dev.izeros(2 * n), dev.izeros(1)
+    assert L.cxb_lu_solve(None, n, dev.ptr(dA), n, nrhs, dev.ptr(dB), n, dev.ptr(ipiv), dev.ptr(info)) == 0
+    X = dev.from_dev(dB)
+    assert int(info.cpu()[0]) == 0
+    assert rel_err(A @ X, B) < 1e-9
+    assert rel_err(X, np.linalg.solve(A, B)) < 1e-8
+
+
+@pytest.mark.parametrize("n,m,seed", [(6, 4, 1), (50, 20, 2), (100, 10, 3)])
+def test_geodesic_update_matches_oracle_psd_step(dev, n, m, seed):
+    """K6+K7+K8 chained exactly as PrepareStep/TakeStep do (psd_constraint.cc:45-90)."""
+    import torch
+    L = dev.product().lib
+    O = oracle().lib
+    mats, Cm = random_dense_lmi(n, m, seed)
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((n, n))
+    W = R @ R.T / n + 0.5 * np.eye(n)
+    W = 0.5 * (W + W.T)
+    y = 0.1 * rng.standard_normal(m)
+    k = 0.7
+    A = pack_matrices(mats)
+    Wref = fmat(W)
+    out4 = np.zeros(4)
+    WSref = np.zeros((n, n), order="F")
+    O.ORACLE_PsdStep(n, m, dptr(A), dptr(fmat(Cm)), dptr(Wref), dptr(y), k, 1.0, 0, 1, dptr(out4),
+                     dptr(WSref))
+    S = sum(y[i] * mats[i] for i in range(m)) - k * Cm
+    Aall = np.concatenate([A.ravel(), np.asfortranarray(Cm).ravel(order="F")])
+    dA = torch.from_numpy(Aall).cuda()
+    coef = dev.to_dev(np.concatenate([y, [-k]]))
+    dS = dev.dzeros(n * n)
+    assert L.cxb_gemv_n(None, n * n, m + 1, dev.ptr(dA), dev.ptr(coef), dev.ptr(dS)) == 0
+    assert rel_err(dev.from_dev(dS, n, n), S) < 1e-13
+    dW = dev.to_dev(W)
+    dWS = dev.dzeros(n * n)
+    assert L.cxb_dgemm(None, 0, 0, n, n, n, 1.0, dev.ptr(dW), n, 0, dev.ptr(dS), n, 0, 0.0, dev.ptr(dWS), n,
+                       0, 1, 0) == 0
+    assert rel_err(dev.from_dev(dWS, n, n), WSref) < 1e-12
+    work, iwork, info = dev.dzeros(4 * n * n), dev.izeros(2 * n + 2), dev.izeros(1)
+    assert L.cxb_geodesic_update(None, n, dev.ptr(dW), dev.ptr(dWS), 1.0, out4[2], dev.ptr(work),
+                                 dev.ptr(iwork), dev.ptr(info)) == 0
+    Wnew = dev.from_dev(dW, n, n)
+    assert np.array_equal(Wnew, Wnew.T)
+    assert rel_err(Wnew, np.asarray(Wref)) < 1e-10
+
+
+def test_small_vector_helpers(dev):
+    import torch
+    L = dev.product().lib
+    rng = np.random.default_rng(3)
+    n = 1000
+    x, y, z = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    dx, dy, dz, out = dev.to_dev(x), dev.to_dev(y), dev.to_dev(z), dev.dzeros(1)
+    assert L.cxb_dot(None, n, dev.ptr(dx), dev.ptr(dy), dev.ptr(out)) == 0
+    assert abs(dev.from_dev(out)[0] - x @ y) < 1e-11
+    assert L.cxb_axpbypcz(None, n, 2.0, dev.ptr(dx), -1.0, dev.ptr(dy), 0.5, dev.ptr(dz)) == 0
+    assert np.allclose(dev.from_dev(dy), 2 * x - y + 0.5 * z, rtol=0, atol=1e-14)
+    idx = rng.permutation(n)[:100].astype(np.int32)
+    didx = torch.from_numpy(idx).cuda()
+    dst = dev.dzeros(n)
+    src = dev.to_dev(rng.standard_normal(100))
+    assert L.cxb_scatter_add_vec(None, 100, dev.ptr(src), dev.ptr(didx), dev.ptr(dst)) == 0
+    ref = np.zeros(n)
+    ref[idx] += dev.from_dev(src)
+    assert np.array_equal(dev.from_dev(dst), ref)
+    g = dev.dzeros(100)
+    assert L.cxb_gather_vec(None, 100, dev.ptr(dst), dev.ptr(didx), dev.ptr(g)) == 0
+    assert np.array_equal(dev.from_dev(g), ref[idx])
+    # scatter-add of a lower triangle through a clique index list
+    mc = 40
+    G = np.tril(rng.standard_normal((mc, mc)))
+    cl = rng.permutation(60)[:mc].astype(np.int32)
+    dH = dev.dzeros(60 * 60)
+    assert L.cxb_scatter_add_lower(None, mc, dev.ptr(dev.to_dev(G)), mc, dev.ptr(torch.from_numpy(cl).cuda()),
+                                   dev.ptr(dH), 60) == 0
+    Href = np.zeros((60, 60))
+    for a in range(mc):
+        for b in range(a + 1):
+            Href[max(cl[a], cl[b]), min(cl[a], cl[b])] += G[a, b]
+    assert np.array_equal(dev.from_dev(dH, 60, 60), Href)

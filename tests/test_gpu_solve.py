@@ -1,0 +1,210 @@
+"""End-to-end parity through the drop-in boundary: the same CONEX_* calls drive the CPU oracle and
+libconex_b200.so on identical inputs. Gates (BASELINE.json): Newton-system entries within 1e-10
+relative, primal/dual objectives within 1e-7 relative, iteration counts within +-1; plus the
+reference's own property checks (conex/test/test_sdp.cc:195-197).
+"""
+import numpy as np
+import pytest
+
+from harness import lovasz_theta_lmi, maxcut_lmi, oracle, random_dense_lmi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs():
+    import devlib
+    return oracle(), devlib.product()
+
+
+def solve_both(libs, mats, Cm, b=None, variables=None, m=None, **cfg_kw):
+    out = []
+    for L in libs:
+        P = L.program(m if m is not None else 0)
+        P.add_dense_lmi(mats, Cm, variables)
+        bb = P.feasible_objective() if b is None else b
+        cfg = L.default_config(**cfg_kw)
+        solved, y = P.maximize(bb, cfg)
+        out.append((P, solved, y, bb))
+    return out
+
+
+def check_parity(res, obj_tol=1e-7):
+    (Po, so, yo, bo), (Pd, sd, yd, bd) = res
+    assert so == sd
+    lo, ld = Po.iteration_log(), Pd.iteration_log()
+    assert abs(len(lo) - len(ld)) <= 1, (len(lo), len(ld))
+    assert np.allclose(bo, bd, rtol=1e-12, atol=1e-14)
+    # objectives of the final iterate
+    for key in ("by", "cx"):
+        a, c = lo[-1][key], ld[-1][key]
+        assert abs(a - c) <= obj_tol * max(1.0, abs(a)), (key, a, c)
+    # trajectories agree step by step while both run (mu rule, step size, distance to the path)
+    for i in range(min(len(lo), len(ld)) - 1):
+        assert abs(lo[i]["inv_sqrt_mu"] - ld[i]["inv_sqrt_mu"]) <= 1e-6 * abs(lo[i]["inv_sqrt_mu"]), i
+    assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+
+
+def test_newton_system_entries_c1(libs):
+    """BASELINE config 1 (n=50, m=100): H, AW, AQc at W = I within 1e-10 relative."""
+    mats, Cm = random_dense_lmi(50, 100, 1)
+    sys_ = []
+    for L in libs:
+        P = L.program()
+        P.add_dense_lmi(mats, Cm)
+        sys_.append(P.newton_system(coldstart=True))
+    (Ho, AWo, AQo, so), (Hd, AWd, AQd, sd) = sys_
+    scale = np.sqrt(np.outer(np.diag(Ho), np.diag(Ho)))
+    assert (np.abs(Ho - Hd) / scale).max() < 1e-10
+    nz = np.abs(Ho) > 1e-3 * scale
+    assert (np.abs(Ho - Hd)[nz] / np.abs(Ho)[nz]).max() < 1e-10
+    assert np.abs(AWo - AWd).max() <= 1e-10 * np.abs(AWo).max()
+    assert np.abs(AQo - AQd).max() <= 1e-10 * np.abs(AQo).max()
+    assert np.allclose(so, sd, rtol=1e-10)
+
+
+def test_c1_random_dense_lmi_solve(libs):
+    """BASELINE config 1 through CONEX_AddDenseLMIConstraint / CONEX_Maximize on both libraries."""
+    mats, Cm = random_dense_lmi(50, 100, 1)
+    res = solve_both(libs, mats, Cm, prepare_dual_variables=1)
+    check_parity(res)
+    Pd, solved, y, b = res[1]
+    assert solved == 1
+    # reference property checks (test_sdp.cc:187-197)
+    X = Pd.dual_variable(0)
+    slack = Cm - sum(y[i] * mats[i] for i in range(len(mats)))
+    resid = b - np.array([np.trace(A @ X) for A in mats])
+    assert abs(np.linalg.eigvalsh(slack).min()) < 1e-5
+    assert np.linalg.norm(resid) < 1e-8
+    assert abs(np.trace(slack @ X)) < 1e-4
+    Xo = res[0][0].dual_variable(0)
+    assert np.abs(X - Xo).max() <= 1e-6 * np.abs(Xo).max()
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (3, 2), (5, 3), (18, 9), (10, 1), (17, 8), (12, 5)])
+def test_profile_sdp_shapes(libs, n, m):
+    """The reference's property harness shapes (test_sdp.cc:170-208), incl. n = 1..3 edge cases."""
+    mats, Cm = random_dense_lmi(n, m, 100 + n * 31 + m)
+    res = solve_both(libs, mats, Cm, prepare_dual_variables=1)
+    check_parity(res, obj_tol=1e-6)
+    Pd, solved, y, b = res[1]
+    X = Pd.dual_variable(0)
+    slack = Cm - sum(y[i] * mats[i] for i in range(m))
+    assert abs(np.linalg.eigvalsh(slack).min()) < 1e-5
+    assert np.linalg.norm(b - np.array([np.trace(A @ X) for A in mats])) < 1e-8
+    assert abs(np.trace(slack @ X)) < 1e-4
+
+
+def test_hermitian_known_answer_through_dense_path(libs):
+    """interfaces/python/test/run_tests.py:299-321: 3x3 LMI [[1,x,0],[x,2,y],[0,y,1]] >= 0,
+    maximise -(x + y) -> y = (-1, -1) within 1e-6."""
+    A0 = np.zeros((3, 3)); A0[1, 0] = A0[0, 1] = -1.0
+    A1 = np.zeros((3, 3)); A1[2, 1] = A1[1, 2] = -1.0
+    Cm = np.diag([1.0, 2.0, 1.0])
+    kw = dict(inv_sqrt_mu_max=1000, maximum_mu=1e20, max_iterations=100, final_centering_steps=1,
+              prepare_dual_variables=1, infeasibility_threshold=1e8, divergence_upper_bound=1)
+    for L in libs:
+        P = L.program()
+        P.add_dense_lmi([A0, A1], Cm)
+        solved, y = P.maximize([-1.0, -1.0], L.default_config(**kw))
+        assert solved == 1
+        assert np.linalg.norm(y + 1.0) < 1e-6
+
+
+def test_sparse_and_dense_agree(libs):
+    """test_sdp.cc:112-168: two LMIs on disjoint variable subsets, dense vs sparse formulation."""
+    _, dev = libs
+    v2, v1 = [0, 2, 4, 6, 7, 8], [1, 3, 5]
+    m = 9
+    m1s, _ = random_dense_lmi(5, m, 11)
+    m2s, _ = random_dense_lmi(5, m, 12)
+    s1 = [m1s[i] for i in v1]
+    s2 = [m2s[i] for i in v2]
+    for i in v1:
+        m2s[i] = np.zeros((5, 5))
+    for i in v2:
+        m1s[i] = np.zeros((5, 5))
+    ys = []
+    for L in libs:
+        P = L.program(m)
+        P.add_dense_lmi(m1s, np.eye(5))
+        P.add_dense_lmi(m2s, np.eye(5))
+        b = P.feasible_objective()
+        s, y = P.maximize(b)
+        assert s == 1
+        Ps = L.program(m)
+        Ps.add_dense_lmi(s1, np.eye(5), variables=v1)
+        Ps.add_dense_lmi(s2, np.eye(5), variables=v2)
+        s, ysp = Ps.maximize(b)
+        assert s == 1
+        assert np.linalg.norm(y - ysp) < 1e-8
+        ys.append(y)
+    assert np.abs(ys[0] - ys[1]).max() < 1e-7
+
+
+def test_warmstart_agrees_with_full_solve(libs):
+    """test_warmstart.cc:14-45: ten 1-iteration warm solves == one 10-iteration solve (1e-12):
+    all solver state lives in the device arena."""
+    _, dev = libs
+    mats, Cm = random_dense_lmi(15, 13, 21)
+    P = dev.program()
+    P.add_dense_lmi(mats, Cm)
+    b = P.feasible_objective()
+    cfg = dev.default_config(inv_sqrt_mu_max=1e7, final_centering_steps=0, max_iterations=10)
+    _, y = P.maximize(b, cfg)
+    for i in range(10):
+        cfg = dev.default_config(inv_sqrt_mu_max=1e7, final_centering_steps=0, max_iterations=1,
+                                 initialization_mode=0 if i == 0 else 1)
+        _, yw = P.maximize(b, cfg)
+    assert np.linalg.norm(y - yw) < 1e-12
+
+
+def test_maxcut_small(libs):
+    """BASELINE config 2 shape at n = 60 (dense path): dual variable has unit diagonal."""
+    mats, Cm, b = maxcut_lmi(60, 2)
+    res = solve_both(libs, mats, Cm, b=b, prepare_dual_variables=1)
+    check_parity(res)
+    X = res[1][0].dual_variable(0)
+    assert np.abs(np.diag(X) - 1.0).max() < 1e-6
+
+
+def test_lovasz_theta_small(libs):
+    """BASELINE config 4 shape at n = 30, 80 edges."""
+    mats, Cm, b = lovasz_theta_lmi(30, 80, 4)
+    res = solve_both(libs, mats, Cm, b=b)
+    check_parity(res)
+
+
+def test_infeasible_status_flags(libs):
+    """Infeasibility reporting (cone_program.cc:486-499) matches the oracle."""
+    A0 = np.array([[1.0, 0], [0, -1.0]])
+    Cm = -np.eye(2)  # -I - y*A0 >= 0 has no solution
+    out = []
+    for L in libs:
+        P = L.program()
+        P.add_dense_lmi([A0], Cm)
+        solved, _ = P.maximize([1.0], L.default_config(max_iterations=50))
+        out.append((solved, P.status()))
+    assert out[0][0] == out[1][0] == 0
+    assert out[0][1]["primal_infeasible"] == out[1][1]["primal_infeasible"]
+    assert out[0][1]["dual_infeasible"] == out[1][1]["dual_infeasible"]
+
+
+def test_iteration_stats_and_abi_conventions(libs):
+    _, dev = libs
+    mats, Cm = random_dense_lmi(8, 4, 5)
+    P = dev.program()
+    cid = P.add_dense_lmi(mats, Cm)
+    assert cid == 0
+    assert P.add_dense_lmi(mats, Cm) == 1
+    b = P.feasible_objective()
+    solved, _ = P.maximize(b)
+    assert solved == 1
+    n_it = P.status()["num_iterations"]
+    mu_last, it_last = P.iteration_stats(-1)
+    assert it_last == n_it - 1 and mu_last > 0
+    mu0, it0 = P.iteration_stats(0)
+    assert it0 == 0 and mu0 >= mu_last
+    _, bad = P.iteration_stats(n_it)  # out of bounds: struct untouched
+    assert bad == -12345
+    assert dev.lib.CONEX_SetNumberOfVariables(P.h, 3) == 1  # already set -> CONEX_FAILURE
