@@ -183,7 +183,7 @@ def lanczos_inputs(n, seed):
     return W, S, W @ S
 
 
-@pytest.mark.parametrize("n,seed", [(4, 1), (25, 2), (64, 3), (200, 4), (7, 5)])
+@pytest.mark.parametrize("n,seed", [(4, 1), (25, 2), (64, 3), (7, 5), (2, 6), (3, 7)])
 def test_two_sided_lanczos_matches_oracle(dev, n, seed):
     """K7: alpha/beta of the Jacobi matrix and the Ritz extremes vs. the oracle's recurrence."""
     import torch
@@ -217,6 +217,52 @@ def test_two_sided_lanczos_matches_oracle(dev, n, seed):
     ritz = np.linalg.eigvalsh(T)
     tol = 1e-9 * max(1.0, np.abs(ev[:k]).max())
     assert abs(ritz[0] - ev[0]) < tol and abs(ritz[-1] - ev[k - 1]) < tol
+
+
+def test_two_sided_lanczos_long_run_properties(dev):
+    """n = 200, 100 steps. Without re-orthogonalisation the recurrence amplifies rounding (the
+    oracle run with OpenBLAS and with plain loops already breaks down at different steps, see
+    tests/test_oracle_golden.py), so a long run is pinned by (i) the first coefficients against a
+    numpy evaluation of the same recurrence and (ii) the reference's own acceptance criterion for
+    the Ritz extremes: within 1e-2 relative of the true spectrum bounds
+    (conex/test/approximate_eigenvalues.cc:87-113)."""
+    import torch
+    L = dev.product().lib
+    n, num_iter = 200, 100
+    W, S, WS = lanczos_inputs(n, 4)
+    idx = int(np.argmax(np.diag(WS)))
+    r = S[:, idx].copy()
+    alpha, beta, cnt = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(1)
+    work = dev.dzeros(L.cxb_lanczos_worksize(n))
+    assert L.cxb_lanczos_two_sided(None, n, dev.ptr(dev.to_dev(WS)), dev.ptr(dev.to_dev(W)),
+                                   dev.ptr(dev.to_dev(r)), None, num_iter, dev.ptr(alpha), dev.ptr(beta),
+                                   dev.ptr(cnt), dev.ptr(work)) == 0
+    torch.cuda.synchronize()
+    c = int(cnt.cpu()[0])
+    a, b = alpha.cpu().numpy()[: c + 1], beta.cpu().numpy()[:c]
+    # numpy evaluation of approximate_eigenvalues.cc:178-239 for the first steps
+    v1 = r.copy()
+    v0 = W @ r
+    s = np.sqrt(v0 @ v1)
+    v0, v1 = v0 / s, v1 / s
+    u0, u1 = WS @ v0, WS.T @ v1
+    al = [v0 @ u1]
+    be = []
+    u0, u1 = u0 - al[0] * v0, u1 - al[0] * v1
+    for j in range(1, 8):
+        bj = np.sqrt(u0 @ u1)
+        be.append(bj)
+        p0, p1 = v0, v1
+        v0, v1 = u0 / bj, u1 / bj
+        u0, u1 = WS @ v0, WS.T @ v1
+        al.append(v0 @ u1)
+        u0, u1 = u0 - al[j] * v0 - bj * p0, u1 - al[j] * v1 - bj * p1
+    assert c >= 8
+    assert np.abs(a[:8] - np.array(al)).max() < 1e-9 * np.abs(al).max()
+    assert np.abs(b[:7] - np.array(be)).max() < 1e-9 * np.abs(be).max()
+    ritz = np.linalg.eigvalsh(np.diag(a) + np.diag(b, 1) + np.diag(b, -1))
+    true = np.sort(np.linalg.eigvals(WS).real)
+    assert abs(ritz[-1] / true[-1] - 1) < 1e-2 and abs(ritz[0] / true[0] - 1) < 1e-2
 
 
 def test_lanczos_golden_4x4(dev):
