@@ -1,16 +1,25 @@
 // FP64 tensor-core GEMM for sm_100a: C = alpha * op(A) * op(B) + beta * C.
 //
-// The B200's FP64 tensor path is the legacy warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4);
-// tcgen05 has no f64 kind, so there is no TMEM/UMMA involvement. The kernel is a classic
-// multi-stage cp.async (LDGSTS) pipeline feeding register-tiled DMMA fragments:
+// The B200's FP64 tensor path is the warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, one per
+// 8 cycles per SM sub-partition = 37 TFLOP/s at 1965 MHz); tcgen05 has no f64 kind, so there is no
+// TMEM/UMMA involvement. The kernel is a multi-stage cp.async (LDGSTS) pipeline feeding
+// register-tiled DMMA fragments:
 //
 //   * CTA tile BM x BN x BK, warp tile WM x WN -> (WM/8) x (WN/8) independent 8x8 accumulators per
 //     warp, so every k-step issues (WM/8)*(WN/8) DMMAs for (WM/8)+(WN/8) 8-byte LDS per lane;
-//   * both operand tiles are stored in shared memory with a pitch == 4 (mod 16) doubles, which
-//     makes the 8x4 / 4x8 fragment loads bank-conflict free for either operand orientation
+//   * both operand tiles sit in shared memory with a pitch == 4 (mod 16) doubles, which makes the
+//     8x4 / 4x8 fragment loads bank-conflict free for either operand orientation
 //     ("K-contiguous" = transposed A / plain B, "M/N-contiguous" = plain A / transposed B);
-//   * ragged edges are zero-filled by cp.async's src-size operand, so no branches in the MMA loop;
-//   * lower_only launches only the tiles on/below the diagonal (SYRK / Gram / Cholesky updates).
+//   * ragged edges are zero-filled by cp.async's src-size operand: no branches in the MMA loop;
+//   * lower_only skips the tiles strictly above the diagonal (SYRK / Gram / Cholesky updates) and
+//     `mirror` additionally stores the transposed entry, producing an exactly symmetric result
+//     (used for W (A_i W), which is symmetric in exact arithmetic);
+//   * split-K (deterministic): K is cut into `splits` fixed ranges, every range writes its partial
+//     tile to a workspace and a second kernel sums the partials in a fixed order. Used by the Gram
+//     contraction (K = n^2) when the lower tile triangle alone cannot fill 148 SMs.
+//
+// Several tile configurations are compiled; Dgemm() picks one from the shape (see PickConfig) and
+// cxb_dgemm_ex lets the tuning harness (tools/gemm_tune.py) force one.
 //
 // Replaces the Eigen GEMM calls of the reference hot path (see include/conex_b200_device.h).
 #include "common.cuh"
@@ -28,8 +37,12 @@ struct GemmArgs {
   long ldb, sB;
   double* C;
   long ldc, sC;
-  int lower;
+  int lower;    // only entries with row >= col
+  int mirror;   // also store C[col, row] (requires lower, M == N)
   int tiles_m, tiles_n;
+  int splits;   // split-K factor (>1: partials go to `partials`, batch must be 1)
+  int k_per_split;  // multiple of BK
+  double* partials;  // splits x (M x N, ld = M)
 };
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AKC, bool BKC, int VEC>
@@ -46,38 +59,86 @@ struct GemmCfg {
   static constexpr size_t kSmemBytes = sizeof(double) * STAGES * (kStageA + kStageB);
 };
 
-// Copies one operand tile (ROWS x COLS logical, contiguous along COLS in global memory) into
-// shared memory with row pitch PITCH. Element (r, c) lives at g[(r0 + r) * ld + c0 + c]; rows
-// beyond `rmax` and columns beyond `cmax` are zero-filled.
-template <int ROWS, int COLS, int PITCH, int VEC, int THREADS>
-__device__ __forceinline__ void LoadTile(double* smem, const double* __restrict__ g, long ld,
-                                         int r0, int c0, int rmax, int cmax, int tid) {
-  constexpr int kChunks = COLS / VEC;
-  constexpr int kTotal = ROWS * kChunks;
+// Streams one operand's tiles (ROWS x COLS logical, contiguous along COLS in global memory) into
+// shared memory with row pitch PITCH. KC == true: rows index M (or N), columns index K;
+// KC == false: rows index K, columns index M (or N). The per-thread column and the row of its
+// first chunk never change, so the 64-bit address arithmetic is hoisted out of the k loop.
+template <int ROWS, int COLS, int PITCH, int VEC, int THREADS, bool KC>
+struct TileLoader {
+  static constexpr int kChunksPerRow = COLS / VEC;
+  static constexpr int kTotal = ROWS * kChunksPerRow;
+  static constexpr int kIters = (kTotal + THREADS - 1) / THREADS;
+  static_assert(THREADS % kChunksPerRow == 0 || kChunksPerRow % THREADS == 0,
+                "a thread must keep one column across its chunks");
+  static constexpr int kRowStep = (THREADS >= kChunksPerRow) ? THREADS / kChunksPerRow : 0;
+  static_assert(kRowStep > 0, "tile row wider than the CTA");
+
+  const double* base;   // &g[(mn0 + r_first) * ld + cc]  (KC) or &g[r_first * ld + mn0 + cc] (!KC)
+  const double* safe;   // any valid address for fully masked chunks
+  long row_stride;      // kRowStep * ld
+  long ld;
+  int r_first, cc;
+  int mn_bytes;         // !KC: valid bytes of this thread's column chunk (fixed)
+  unsigned row_mask;    // KC: bit i set when row r_first + i*kRowStep is inside the matrix
+  int smem_off;         // r_first * PITCH + cc
+
+  __device__ __forceinline__ void Init(const double* g, long ld_, int mn0, int mn_max, int tid) {
+    ld = ld_;
+    safe = g;
+    r_first = tid / kChunksPerRow;
+    cc = (tid % kChunksPerRow) * VEC;
+    row_stride = (long)kRowStep * ld;
+    smem_off = r_first * PITCH + cc;
+    if (KC) {
+      base = g + (long)(mn0 + r_first) * ld + cc;
+      row_mask = 0;
 #pragma unroll
-  for (int i = 0; i < (kTotal + THREADS - 1) / THREADS; i++) {
-    const int c = tid + i * THREADS;
-    if ((kTotal % THREADS != 0) && c >= kTotal) break;
-    const int r = c / kChunks;
-    const int cc = (c % kChunks) * VEC;
-    const int gr = r0 + r, gc = c0 + cc;
-    int valid = 0;
-    if (gr < rmax) {
-      valid = cmax - gc;
-      valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
-    }
-    const double* src = valid ? (g + (long)gr * ld + gc) : g;
-    double* dst = smem + r * PITCH + cc;
-    if (VEC == 2) {
-      CpAsync16(dst, src, valid * 8);
+      for (int i = 0; i < kIters; i++) {
+        const int r = r_first + i * kRowStep;
+        if (r < ROWS && mn0 + r < mn_max) row_mask |= (1u << i);
+      }
+      mn_bytes = 0;
     } else {
-      CpAsync8(dst, src, valid * 8);
+      base = g + (long)r_first * ld + mn0 + cc;
+      int v = mn_max - (mn0 + cc);
+      v = v < 0 ? 0 : (v > VEC ? VEC : v);
+      mn_bytes = v * 8;
+      row_mask = 0;
     }
   }
-}
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AKC, bool BKC, int VEC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+  // Issue the cp.asyncs of the k-tile starting at k0 (k < k_end are valid) into `smem`.
+  __device__ __forceinline__ void Load(double* smem, int k0, int k_end) const {
+    if (KC) {
+      int v = k_end - (k0 + cc);
+      v = v < 0 ? 0 : (v > VEC ? VEC : v);
+      const int kbytes = v * 8;
+      const double* p = base + k0;
+#pragma unroll
+      for (int i = 0; i < kIters; i++) {
+        if ((kTotal % THREADS != 0) && (r_first + i * kRowStep >= ROWS)) break;
+        const int bytes = ((row_mask >> i) & 1u) ? kbytes : 0;
+        const double* src = bytes ? p + i * row_stride : safe;
+        double* dst = smem + smem_off + i * kRowStep * PITCH;
+        if (VEC == 2) CpAsync16(dst, src, bytes); else CpAsync8(dst, src, bytes);
+      }
+    } else {
+      const double* p = base + (long)k0 * ld;
+#pragma unroll
+      for (int i = 0; i < kIters; i++) {
+        const int r = r_first + i * kRowStep;
+        if ((kTotal % THREADS != 0) && (r >= ROWS)) break;
+        const int bytes = (k0 + r < k_end) ? mn_bytes : 0;
+        const double* src = bytes ? p + i * row_stride : safe;
+        double* dst = smem + smem_off + i * kRowStep * PITCH;
+        if (VEC == 2) CpAsync16(dst, src, bytes); else CpAsync8(dst, src, bytes);
+      }
+    }
+  }
+};
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AKC, bool BKC, int VEC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
     DgemmKernel(const GemmArgs g) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES, AKC, BKC, VEC>;
   constexpr int MI = WM / 8, NI = WN / 8;
@@ -87,24 +148,15 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   double* Bs = smem + STAGES * Cfg::kStageA;
 
   // ---- tile coordinates ----
-  int tm, tn;
-  if (g.lower) {
-    // linear index over tiles with tm >= tn (BM == BN)
-    const int t = blockIdx.x;
-    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long)(r + 1) * (r + 2) / 2 <= t) r++;
-    while ((long)r * (r + 1) / 2 > t) r--;
-    tm = r;
-    tn = t - r * (r + 1) / 2;
-  } else {
-    tm = blockIdx.x % g.tiles_m;
-    tn = blockIdx.x / g.tiles_m;
-  }
+  const int tm = blockIdx.x % g.tiles_m;
+  const int tn = blockIdx.x / g.tiles_m;
   const int m0 = tm * BM, n0 = tn * BN;
-  if (m0 >= g.M || n0 >= g.N) return;
+  if (g.lower && m0 + BM - 1 < n0) return;  // tile strictly above the diagonal
   const double* A = g.A + (long)blockIdx.z * g.sA;
   const double* B = g.B + (long)blockIdx.z * g.sB;
   double* C = g.C + (long)blockIdx.z * g.sC;
+  const int k_begin = blockIdx.y * g.k_per_split;
+  const int k_end = min(g.K, k_begin + g.k_per_split);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -118,62 +170,84 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 #pragma unroll
     for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int KT = (g.K + BK - 1) / BK;
+  using LoaderA = TileLoader<Cfg::kRowsA, AKC ? BK : BM, Cfg::kPitchA, VEC, NT, AKC>;
+  using LoaderB = TileLoader<Cfg::kRowsB, BKC ? BK : BN, Cfg::kPitchB, VEC, NT, BKC>;
+  LoaderA la;
+  LoaderB lb;
+  la.Init(A, g.lda, m0, g.M, tid);
+  lb.Init(B, g.ldb, n0, g.N, tid);
 
-  auto load_stage = [&](int stage, int kt) {
-    const int k0 = kt * BK;
-    double* as = As + stage * Cfg::kStageA;
-    double* bs = Bs + stage * Cfg::kStageB;
-    if (AKC) {
-      LoadTile<BM, BK, Cfg::kPitchA, VEC, NT>(as, A, g.lda, m0, k0, g.M, g.K, tid);
-    } else {
-      LoadTile<BK, BM, Cfg::kPitchA, VEC, NT>(as, A, g.lda, k0, m0, g.K, g.M, tid);
-    }
-    if (BKC) {
-      LoadTile<BN, BK, Cfg::kPitchB, VEC, NT>(bs, B, g.ldb, n0, k0, g.N, g.K, tid);
-    } else {
-      LoadTile<BK, BN, Cfg::kPitchB, VEC, NT>(bs, B, g.ldb, k0, n0, g.K, g.N, tid);
-    }
-  };
+  const int KT = (k_end - k_begin + BK - 1) / BK;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
-    if (s < KT) load_stage(s, s);
+    if (s < KT) {
+      la.Load(As + s * Cfg::kStageA, k_begin + s * BK, k_end);
+      lb.Load(Bs + s * Cfg::kStageB, k_begin + s * BK, k_end);
+    }
     CpAsyncCommit();
   }
 
+  // fragment offsets inside a stage (doubles)
+  const int a_off = AKC ? (wm0 + gid) * Cfg::kPitchA + tig : tig * Cfg::kPitchA + wm0 + gid;
+  const int b_off = BKC ? (wn0 + gid) * Cfg::kPitchB + tig : tig * Cfg::kPitchB + wn0 + gid;
+  constexpr int kAStepI = AKC ? 8 * Cfg::kPitchA : 8;     // next 8 rows of the warp tile
+  constexpr int kAStepK = AKC ? 1 : Cfg::kPitchA;          // next k
+  constexpr int kBStepJ = BKC ? 8 * Cfg::kPitchB : 8;
+  constexpr int kBStepK = BKC ? 1 : Cfg::kPitchB;
+
+  int stage = 0;
   for (int kt = 0; kt < KT; kt++) {
     CpAsyncWait<STAGES - 2>();
     __syncthreads();
     {
       const int nk = kt + STAGES - 1;
-      if (nk < KT) load_stage(nk % STAGES, nk);
+      int ns = stage + STAGES - 1;
+      if (ns >= STAGES) ns -= STAGES;
+      if (nk < KT) {
+        la.Load(As + ns * Cfg::kStageA, k_begin + nk * BK, k_end);
+        lb.Load(Bs + ns * Cfg::kStageB, k_begin + nk * BK, k_end);
+      }
       CpAsyncCommit();
     }
-    const double* as = As + (kt % STAGES) * Cfg::kStageA;
-    const double* bs = Bs + (kt % STAGES) * Cfg::kStageB;
+    const double* as = As + stage * Cfg::kStageA + a_off;
+    const double* bs = Bs + stage * Cfg::kStageB + b_off;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       double a[MI], b[NI];
 #pragma unroll
-      for (int i = 0; i < MI; i++) {
-        a[i] = AKC ? as[(wm0 + i * 8 + gid) * Cfg::kPitchA + kk + tig]
-                   : as[(kk + tig) * Cfg::kPitchA + wm0 + i * 8 + gid];
-      }
+      for (int i = 0; i < MI; i++) a[i] = as[i * kAStepI + kk * kAStepK];
 #pragma unroll
-      for (int j = 0; j < NI; j++) {
-        b[j] = BKC ? bs[(wn0 + j * 8 + gid) * Cfg::kPitchB + kk + tig]
-                   : bs[(kk + tig) * Cfg::kPitchB + wn0 + j * 8 + gid];
-      }
+      for (int j = 0; j < NI; j++) b[j] = bs[j * kBStepJ + kk * kBStepK];
 #pragma unroll
       for (int i = 0; i < MI; i++)
 #pragma unroll
         for (int j = 0; j < NI; j++) Dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    if (++stage == STAGES) stage = 0;
   }
   CpAsyncWait<0>();
 
   // ---- epilogue ----
+  if (g.splits > 1) {
+    double* P = g.partials + (long)blockIdx.y * g.M * g.N;
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+      const int r = m0 + wm0 + i * 8 + gid;
+      if (r >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = n0 + wn0 + j * 8 + tig * 2 + e;
+          if (c >= g.N) continue;
+          if (g.lower && r < c) continue;
+          P[(long)c * g.M + r] = acc[i][j][e];
+        }
+      }
+    }
+    return;
+  }
   const bool use_beta = g.beta != 0.0;
 #pragma unroll
   for (int i = 0; i < MI; i++) {
@@ -190,15 +264,53 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
         double v = g.alpha * acc[i][j][e];
         if (use_beta) v += g.beta * (*p);
         *p = v;
+        if (g.mirror && r != c) C[(long)r * g.ldc + c] = v;
       }
     }
   }
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AKC, bool BKC, int VEC>
-int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch) {
+// C = alpha * sum_s partials[s] + beta * C (fixed summation order s = 0, 1, ...).
+__global__ void __launch_bounds__(256) SplitKReduceKernel(int M, int N, int splits,
+                                                          const double* __restrict__ partials,
+                                                          double alpha, double beta, double* C, long ldc,
+                                                          int lower) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= M || (lower && r < c)) return;
+  const long mn = (long)M * N;
+  const double* p = partials + (long)c * M + r;
+  double s = 0;
+  for (int k = 0; k < splits; k++) s += p[k * mn];
+  double* out = C + (long)c * ldc + r;
+  double v = alpha * s;
+  if (beta != 0.0) v += beta * (*out);
+  *out = v;
+}
+
+// Split-K workspace: grown on demand, owned by the library (one per process; kernels of one
+// program run on one stream, and programs on different streams must not share it concurrently —
+// the host layer creates one stream per process).
+double* g_splitk_ws = nullptr;
+size_t g_splitk_ws_doubles = 0;
+
+double* SplitKWorkspace(size_t doubles) {
+  if (doubles > g_splitk_ws_doubles) {
+    if (g_splitk_ws) cudaFree(g_splitk_ws);
+    g_splitk_ws = nullptr;
+    g_splitk_ws_doubles = 0;
+    if (cudaMalloc(&g_splitk_ws, doubles * sizeof(double)) != cudaSuccess) return nullptr;
+    g_splitk_ws_doubles = doubles;
+  }
+  return g_splitk_ws;
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AKC, bool BKC, int VEC>
+int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES, AKC, BKC, VEC>;
-  auto kernel = DgemmKernel<BM, BN, BK, WM, WN, STAGES, AKC, BKC, VEC>;
+  static_assert(MINB * (Cfg::kSmemBytes + 1024) <= 227 * 1024, "tile configuration exceeds shared memory");
+  auto kernel = DgemmKernel<BM, BN, BK, WM, WN, STAGES, MINB, AKC, BKC, VEC>;
+  constexpr int kSlots = kNumSMs * MINB;  // CTAs resident at once
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -206,32 +318,96 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch) {
   }
   g.tiles_m = (g.M + BM - 1) / BM;
   g.tiles_n = (g.N + BN - 1) / BN;
-  // lower_only: enumerate the full tile triangle over tiles_m block rows (tn <= tm); tiles whose
-  // column block lies beyond N exit immediately in the kernel.
-  const long tiles = g.lower ? (long)g.tiles_m * (g.tiles_m + 1) / 2 : (long)g.tiles_m * g.tiles_n;
-  dim3 grid((unsigned)tiles, 1, (unsigned)batch);
+  const long tiles = (long)g.tiles_m * g.tiles_n;
+  long active = tiles;
+  if (g.lower) {
+    active = 0;
+    for (int tn = 0; tn < g.tiles_n; tn++) {
+      const int first = (tn * BN - BM + 1 + BM - 1) / BM;  // smallest tm with tm*BM + BM - 1 >= tn*BN
+      const int f = first < 0 ? 0 : first;
+      if (f < g.tiles_m) active += g.tiles_m - f;
+    }
+  }
+  const int kt_total = (g.K + BK - 1) / BK;
+  if (splits == 0) {
+    // automatic: split only when the tiles cannot fill the machine once and K is deep
+    splits = 1;
+    const long waves1 = (active + kSlots - 1) / kSlots;
+    if (batch == 1 && (double)active / (double)(waves1 * kSlots) < 0.9 && kt_total >= 64) {
+      double best_eff = (double)active / (double)(waves1 * kSlots);
+      for (int s = 2; s <= 32; s++) {
+        if (kt_total / s < 32) break;
+        const long ctas = active * s;
+        const long waves = (ctas + kSlots - 1) / kSlots;
+        const double eff = (double)ctas / (double)(waves * kSlots);
+        if (eff > best_eff + 0.04) {
+          best_eff = eff;
+          splits = s;
+        }
+      }
+    }
+  }
+  if (batch != 1 || g.mirror) splits = 1;
+  if (splits > kt_total) splits = kt_total > 0 ? kt_total : 1;
+  g.splits = splits;
+  const int kt_per = (kt_total + splits - 1) / (splits > 0 ? splits : 1);
+  g.k_per_split = (splits > 1) ? kt_per * BK : (g.K > 0 ? g.K : 1);
+  if (splits > 1) {
+    // drop empty trailing splits
+    g.splits = splits = (kt_total + kt_per - 1) / kt_per;
+    g.partials = SplitKWorkspace((size_t)splits * g.M * g.N);
+    if (g.partials == nullptr) return (int)cudaErrorMemoryAllocation;
+  }
+  dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)batch);
   CountLaunch(); kernel<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(g);
+  if (splits > 1) {
+    dim3 rg((g.M + 255) / 256, g.N);
+    CountLaunch(); SplitKReduceKernel<<<rg, 256, 0, stream>>>(g.M, g.N, splits, g.partials, g.alpha, g.beta,
+                                                  g.C, g.ldc, g.lower);
+  }
   return LaunchStatus();
 }
 
+// Tile configurations (BM, BN, BK, WM, WN, STAGES, CTAs/SM):
+//   0: 64x64, 4 warps of 32x32, 3 stages, >=3 CTAs/SM (small problems)
+//   1: 128x128, 8 warps of 64x32, 4 stages, 1 CTA/SM (fewest L2 bytes per flop)
+//   2: 64x64, 4 warps of 32x32, 2 stages, 4 CTAs/SM (<=128 registers)
+//   3: 128x64, 8 warps of 32x32, 3 stages, 2 CTAs/SM
+//   4: 128x128, BK = 32, 3 stages, 1 CTA/SM
+//   5: 64x128, 8 warps of 32x32, 3 stages, 2 CTAs/SM
+// Several independent CTAs per SM keep the DMMA pipe busy across each other's barriers and
+// fragment-load latencies (the profile of the one-CTA configurations shows `wait` and
+// `short_scoreboard` stalls at every k-tile boundary).
 template <bool AKC, bool BKC, int VEC>
-int LaunchLayout(cudaStream_t stream, const GemmArgs& g, int batch) {
-  const bool small = (g.M <= 96 || g.N <= 96);
-  if (small) {
-    return LaunchCfg<64, 64, 16, 32, 32, 3, AKC, BKC, VEC>(stream, g, batch);
+int LaunchLayout(cudaStream_t stream, const GemmArgs& g, int batch, int config, int splits) {
+  switch (config) {
+    case 0: return LaunchCfg<64, 64, 16, 32, 32, 3, 3, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 1: return LaunchCfg<128, 128, 16, 64, 32, 4, 1, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 2: return LaunchCfg<64, 64, 16, 32, 32, 2, 4, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 3: return LaunchCfg<128, 64, 16, 32, 32, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 4: return LaunchCfg<128, 128, 32, 64, 32, 3, 1, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 5: return LaunchCfg<64, 128, 16, 32, 32, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
+    default: return -1;
   }
-  return LaunchCfg<128, 128, 16, 64, 32, 4, AKC, BKC, VEC>(stream, g, batch);
 }
 
 bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+int g_default_large_config = 2;
+
+int PickConfig(int M, int N) {
+  if (M <= 96 || N <= 96) return 0;
+  return g_default_large_config;
+}
+
 }  // namespace
 
-int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, double alpha,
-          const double* A, long lda, long sA, const double* B, long ldb, long sB, double beta,
-          double* C, long ldc, long sC, int batch, bool lower_only) {
+int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool transB, int M, int N, int K,
+            double alpha, const double* A, long lda, long sA, const double* B, long ldb, long sB,
+            double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror) {
   if (M <= 0 || N <= 0 || batch <= 0) return 0;
   if (K < 0) return -1;
+  if (mirror && (!lower_only || M != N)) return -1;
   GemmArgs g;
   g.M = M;
   g.N = N;
@@ -248,14 +424,19 @@ int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, do
   g.ldc = ldc;
   g.sC = sC;
   g.lower = lower_only ? 1 : 0;
+  g.mirror = mirror ? 1 : 0;
   g.tiles_m = g.tiles_n = 0;
+  g.splits = 1;
+  g.k_per_split = K;
+  g.partials = nullptr;
+  if (config < 0) config = PickConfig(M, N);
   const bool vec2 = Aligned16(A) && Aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                     (sA % 2 == 0) && (sB % 2 == 0);
   const bool akc = transA, bkc = !transB;
-#define CXB_DISPATCH(AK, BK_)                                        \
-  if (akc == AK && bkc == BK_) {                                     \
-    return vec2 ? LaunchLayout<AK, BK_, 2>(stream, g, batch)         \
-                : LaunchLayout<AK, BK_, 1>(stream, g, batch);        \
+#define CXB_DISPATCH(AK, BK_)                                                     \
+  if (akc == AK && bkc == BK_) {                                                  \
+    return vec2 ? LaunchLayout<AK, BK_, 2>(stream, g, batch, config, splits)      \
+                : LaunchLayout<AK, BK_, 1>(stream, g, batch, config, splits);     \
   }
   CXB_DISPATCH(false, false)
   CXB_DISPATCH(false, true)
@@ -264,6 +445,15 @@ int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, do
 #undef CXB_DISPATCH
   return -1;
 }
+
+int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, double alpha,
+          const double* A, long lda, long sA, const double* B, long ldb, long sB, double beta,
+          double* C, long ldc, long sC, int batch, bool lower_only) {
+  return DgemmEx(stream, -1, 0, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+                 batch, lower_only, false);
+}
+
+void SetDefaultGemmConfig(int config) { g_default_large_config = config; }
 
 }  // namespace cxb
 
@@ -274,3 +464,14 @@ extern "C" int cxb_dgemm(void* stream, int transA, int transB, int M, int N, int
   return cxb::Dgemm(cxb::AsStream(stream), transA != 0, transB != 0, M, N, K, alpha, dA, lda,
                     strideA, dB, ldb, strideB, beta, dC, ldc, strideC, batch, lower_only != 0);
 }
+
+extern "C" int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, int M, int N,
+                            int K, double alpha, const double* dA, long lda, long strideA,
+                            const double* dB, long ldb, long strideB, double beta, double* dC,
+                            long ldc, long strideC, int batch, int lower_only, int mirror) {
+  return cxb::DgemmEx(cxb::AsStream(stream), config, splits, transA != 0, transB != 0, M, N, K, alpha,
+                      dA, lda, strideA, dB, ldb, strideB, beta, dC, ldc, strideC, batch,
+                      lower_only != 0, mirror != 0);
+}
+
+extern "C" void cxb_set_default_gemm_config(int config) { cxb::SetDefaultGemmConfig(config); }

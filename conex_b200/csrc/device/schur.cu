@@ -4,7 +4,7 @@
 // Reference (dense_lmi_constraint.cc:62-103): per constraint two n x n x n GEMMs (A_i W, W A_i W)
 // followed by a GEMV against the growing slab Avect[:, 0:i+1] — BLAS-2 and memory bound. Here:
 //   K1  T_i = A_i W          one strided-batched DMMA GEMM per panel of constraints
-//       B_i = W T_i          one wide GEMM  W * [T_p .. T_q]  (n x (panel*n) x n)
+//       B_i = W T_i          strided-batched, lower tiles only + mirrored store (B_i symmetric)
 //   K2  Haug = Bmat^T Aall   one lower-trapezoid DMMA GEMM with K = n^2 (SYRK-style Gram)
 // The affine term C rides along as matrix m of Aall and W as row m+1 of Bmat, so the same Gram
 // launch also yields AQc_j = <W C W, A_j>, AW_j = <W, A_j>, <c,Qc> and <w,c> (rows m, m+1 of Haug).
@@ -23,9 +23,10 @@ extern "C" int cxb_schur_dense_lmi(void* stream, int n, int m, const double* dAa
     int rc = Dgemm(s, false, false, n, n, n, 1.0, dAall + (long)p0 * nn, n, nn, dW, n, 0, 0.0, dT, n,
                    nn, pb, false);
     if (rc) return rc;
-    // wide GEMM; split so that N stays below 2^30 columns
-    rc = Dgemm(s, false, false, n, pb * n, n, 1.0, dW, n, 0, dT, n, 0, 0.0, dB + (long)p0 * nn, n, 0,
-               1, false);
+    // B_i = W T_i is symmetric in exact arithmetic: compute the lower tiles only and mirror them
+    // (3 n^3 instead of 4 n^3 flops per constraint, and B_i exactly symmetric).
+    rc = DgemmEx(s, -1, 1, false, false, n, n, n, 1.0, dW, n, 0, dT, n, nn, 0.0, dB + (long)p0 * nn, n,
+                 nn, pb, true, true);
     if (rc) return rc;
   }
   cudaMemcpyAsync(dB + (long)(m + 1) * nn, dW, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s);

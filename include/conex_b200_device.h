@@ -29,6 +29,17 @@ int cxb_dgemm(void* stream, int transA, int transB, int M, int N, int K, double 
               const double* dA, long lda, long strideA, const double* dB, long ldb, long strideB,
               double beta, double* dC, long ldc, long strideC, int batch, int lower_only);
 
+/* Same with explicit control, used by the tuning harness (tools/gemm_tune.py) and the Schur assembly:
+ * config = tile configuration (-1: chosen from the shape), splits = split-K factor (0: automatic,
+ * deterministic fixed-order reduction), mirror != 0 (needs lower_only, M == N) also stores
+ * C[col,row] so that the result is exactly symmetric. */
+int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, int M, int N, int K,
+                 double alpha, const double* dA, long lda, long strideA, const double* dB, long ldb,
+                 long strideB, double beta, double* dC, long ldc, long strideC, int batch,
+                 int lower_only, int mirror);
+/* Tile configuration used for large shapes when config < 0 (process-wide; tuning only). */
+void cxb_set_default_gemm_config(int config);
+
 /* ---- K1+K2: Schur complement of one dense LMI block -----------------------------------------
  * dAall: (m+1) contiguous column-major n x n matrices: A_0..A_{m-1} followed by C.
  * dW: n x n scaling point. dB: scratch of (m+2)*n*n doubles (receives W A_i W, W C W, W).

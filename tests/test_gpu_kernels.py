@@ -69,6 +69,61 @@ def test_dgemm_batched_and_lower(dev):
     run_gemm(dev, 1, 0, 131, 130, 49, 1.0, 0.0, rng, lower=True)   # odd K -> 8-byte copies
 
 
+@pytest.mark.parametrize("config", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_dgemm_every_tile_configuration(dev, config, ta, tb):
+    """Every compiled tile configuration, split-K (fixed-order reduction) and the mirrored store."""
+    import torch
+    L = dev.product().lib
+    rng = np.random.default_rng(100 * config + 2 * ta + tb)
+    for (M, N, K, lower, splits, odd) in [(391, 263, 530, 0, 1, 0), (391, 391, 1100, 1, 3, 0),
+                                         (200, 200, 2100, 1, 0, 0), (77, 130, 67, 0, 2, 1)]:
+        A = rng.standard_normal((K, M) if ta else (M, K))
+        B = rng.standard_normal((N, K) if tb else (K, N))
+        C0 = rng.standard_normal((M, N))
+        dA, dB, dC = dev.to_dev(A), dev.to_dev(B), dev.to_dev(C0)
+        rc = L.cxb_dgemm_ex(None, config, splits, ta, tb, M, N, K, 0.5, dev.ptr(dA), A.shape[0], 0,
+                            dev.ptr(dB), B.shape[0], 0, -1.0, dev.ptr(dC), M, 0, 1, lower, 0)
+        assert rc == 0
+        ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - C0
+        got = dev.from_dev(dC)
+        if lower:
+            mask = np.tril(np.ones((M, N), dtype=bool))
+            assert rel_err(got[mask], ref[mask]) < 1e-13
+            assert np.array_equal(got[~mask], C0[~mask])
+        else:
+            assert rel_err(got, ref) < 1e-13
+    # mirrored store: batched W * T_i with exactly symmetric output
+    n, batch = 150, 3
+    W = random_sym(rng, n)
+    Ts = [W @ random_sym(rng, n) @ W for _ in range(batch)]   # symmetric products
+    Winv_T = [np.linalg.solve(W, t) for t in Ts]               # so that W * (W^-1 T) = T symmetric
+    dW = dev.to_dev(W)
+    dT = torch.stack([dev.to_dev(x) for x in Winv_T]).contiguous()
+    dC = dev.dzeros(batch, n, n)
+    rc = L.cxb_dgemm_ex(None, config, 1, 0, 0, n, n, n, 1.0, dev.ptr(dW), n, 0, dev.ptr(dT), n, n * n, 0.0,
+                        dev.ptr(dC), n, n * n, batch, 1, 1)
+    assert rc == 0
+    torch.cuda.synchronize()
+    out = dC.cpu().numpy()
+    for i in range(batch):
+        assert np.array_equal(out[i], out[i].T)
+        assert rel_err(np.tril(out[i].T), np.tril(W @ Winv_T[i])) < 1e-12
+    # split-K is deterministic: two runs give identical bits
+    M = N = 260
+    K = 4096
+    A = rng.standard_normal((K, M))
+    B = rng.standard_normal((K, N))
+    dA, dB = dev.to_dev(A), dev.to_dev(B)
+    outs = []
+    for _ in range(2):
+        dC = dev.dzeros(N, M)
+        assert L.cxb_dgemm_ex(None, config, 4, 1, 0, M, N, K, 1.0, dev.ptr(dA), K, 0, dev.ptr(dB), K, 0, 0.0,
+                              dev.ptr(dC), M, 0, 1, 1, 0) == 0
+        outs.append(dev.from_dev(dC))
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_dgemm_zero_k_and_empty(dev):
     import torch
     L = dev.product().lib
