@@ -40,18 +40,22 @@ def algorithmic_flops(n, m):
     return dict(k1=k1, k2=k2, k3=k3, k78=k78, tensor=k1 + k2 + k3 + k78)
 
 
-def maxcut_on_device(n, seed, p=0.5):
-    """Device-resident MaxCut data: A (n, n*n) with A_i = -e_i e_i^T, C = -L/4 (column-major)."""
+def maxcut_on_device(n, seed, row_begin=0, row_count=None, p=0.5):
+    """Device-resident MaxCut data: the constraint matrices A_i = -e_i e_i^T for
+    i in [row_begin, row_begin + row_count) as dense column-major n x n blocks (this rank's shard;
+    all of them by default) and C = -L/4 (identical on every rank: same seed)."""
     import torch
+    row_count = n if row_count is None else row_count
     g = torch.Generator(device="cuda")
     g.manual_seed(seed)
     upper = torch.triu((torch.rand((n, n), generator=g, device="cuda") < p).double(), 1)
     adj = upper + upper.T
     lap = torch.diag(adj.sum(1)) - adj
     Cm = (-lap / 4.0).contiguous()  # symmetric: row-major == column-major
-    A = torch.zeros((n, n * n), dtype=torch.float64, device="cuda")
-    idx = torch.arange(n, device="cuda")
-    A[idx, idx * n + idx] = -1.0
+    A = torch.zeros((row_count, n * n), dtype=torch.float64, device="cuda")
+    idx = torch.arange(row_count, device="cuda")
+    gi = idx + row_begin
+    A[idx, gi * n + gi] = -1.0
     return A, Cm
 
 
@@ -172,7 +176,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"],
-        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "maxcut_sdp_n2000_dense_lmi", "n": 2000, "m": 2000,
                    "measured_on": f"n=m={n} sample, extrapolated"},
@@ -201,13 +205,20 @@ def run_b200(args):
     fl = algorithmic_flops(n, m)
     peak_tf = measure_fp64_peak() if rank == 0 else None
 
-    # ---- build the program with device-resident data ----
+    # ---- build the program with device-resident data (N > 1: this rank's shard of the rows) ----
     t_setup = time.perf_counter()
-    A, Cm = maxcut_on_device(n, 2 + rank)
+    if world > 1:
+        devlib.init_communicator(dev, rank, world)
+    rb, rc = devlib.shard_range(dev, m, world, rank)
+    A, Cm = maxcut_on_device(n, 2, rb, rc)
     torch.cuda.synchronize()
     P = dev.program()
-    cid = L.CONEXB200_AddDenseLMIConstraintDevice(P.h, C.c_void_p(A.data_ptr()), n, m,
-                                                  C.c_void_p(Cm.data_ptr()))
+    if world > 1:
+        cid = L.CONEXB200_AddDenseLMIConstraintShard(P.h, C.c_void_p(A.data_ptr()), n, m,
+                                                     C.c_void_p(Cm.data_ptr()))
+    else:
+        cid = L.CONEXB200_AddDenseLMIConstraintDevice(P.h, C.c_void_p(A.data_ptr()), n, m,
+                                                      C.c_void_p(Cm.data_ptr()))
     assert cid == 0
     P.m = m
     P.cone_shapes.append((n, n))
@@ -259,9 +270,11 @@ def run_b200(args):
     value = float(timed.mean())
     e2e_ms = e2e_wall * 1e3 / e2e_its
     if world > 1:
-        t = torch.tensor([value, e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([value, e2e_ms] + ph_timed.tolist(), dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         value, e2e_ms = float(t[0]), float(t[1])
+        ph_timed = t[2:].cpu().numpy()
+        L.CONEXB200_CommDestroy()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,20 +285,26 @@ def run_b200(args):
     achieved = asm_flops / (asm_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "maxcut_sdp_n2000_dense_lmi" if n == 2000 else f"maxcut_sdp_n{n}_dense_lmi",
                    "n": n, "m": m, "path": "CONEX_AddDenseLMIConstraint (dense A_i, 64 GB resident)",
                    "l2": "inputs (64 GB) exceed the 126 MB L2; no flush needed",
-                   "multi_gpu": "replicas only (one independent program per rank)" if world > 1 else "n/a"},
-        "newton_steps_per_s": world * 1e3 / value,
+                   "multi_gpu": (f"one Newton step sharded over {world} ranks: constraint matrices and the rows "
+                                 "of H partitioned 1-D (K1/K2/K6 sharded, peer matrices over NCCL "
+                                 "send/recv, H by all-reduce); factor/solve/eigen-bound/geodesic update "
+                                 "replicated") if world > 1 else "n/a"},
+        "newton_steps_per_s": 1e3 / value,
         "step_tflops_fp64": fl["tensor"] / (value * 1e-3) / 1e12,
         "phase_ms": dict(zip(["assemble", "factor", "mu", "solve", "update"], ph_timed.tolist())),
         "roofline": {
             "bound": "tensor", "kernel": "DgemmKernel (K1 scaling GEMMs + K2 Gram, Schur assembly phase)",
-            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no "
-                           "FP64 figure; nominal B200 FP64 tensor = 37 TFLOP/s)",
+            "achieved": achieved, "peak": peak_tf * world, "unit": "TFLOP/s",
+            "frac": achieved / (peak_tf * world),
+            "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run, times n_gpus "
+                           "(MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 tensor = 37 TFLOP/s). "
+                           "achieved counts the reference's dense flops (4mn^3 + m(m+1)n^2); the kernel "
+                           "executes 3mn^3 + m(m+1)n^2 because W(A_i W) is symmetric, so frac can exceed 1",
             "algorithmic_flops_per_step": asm_flops, "traffic": None,
         },
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * m / e2e_its,
@@ -310,7 +329,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=2000, help="MaxCut size (n = m); 2000 is the headline")
+    ap.add_argument("--size", dest="n", type=int, default=2000, help="MaxCut size (n = m); 2000 is the headline")
     ap.add_argument("--cpu-n", type=int, default=400, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

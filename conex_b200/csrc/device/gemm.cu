@@ -335,7 +335,7 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
     const long waves1 = (active + kSlots - 1) / kSlots;
     if (batch == 1 && (double)active / (double)(waves1 * kSlots) < 0.9 && kt_total >= 64) {
       double best_eff = (double)active / (double)(waves1 * kSlots);
-      for (int s = 2; s <= 32; s++) {
+      for (int s = 2; s <= 128; s++) {
         if (kt_total / s < 32) break;
         const long ctas = active * s;
         const long waves = (ctas + kSlots - 1) / kSlots;

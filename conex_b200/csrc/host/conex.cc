@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../../include/conex_b200.h"
+#include "communicator.h"
 #include "cone_program.h"
 #include "dense_lmi_constraint.h"
 #include "divergence.h"
@@ -148,6 +149,60 @@ int CONEXB200_AddDenseLMIConstraintDevice(void* prog, const double* d_A, int n, 
         return id;
       },
       -1);
+}
+
+int CONEXB200_AddDenseLMIConstraintShard(void* prog, const double* d_A_local, int n, int m,
+                                         const double* d_C) {
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
+        const int id = program.NumberOfConstraints();
+        program.AddConstraint(DenseLMIConstraint(n, m, DenseLMIConstraint::Sharded{},
+                                                 DenseLMIConstraint::DevicePointers{d_A_local, d_C}));
+        return id;
+      },
+      -1);
+}
+
+int CONEXB200_CommGetUniqueId(char* out128) {
+  return Guard(
+      [&]() -> int {
+        conex::Communicator::Get().GetUniqueId(out128);
+        return 0;
+      },
+      1);
+}
+
+int CONEXB200_CommInitRank(int world, int rank, const char* id128) {
+  return Guard(
+      [&]() -> int {
+        conex::Communicator::Get().InitRank(world, rank, id128);
+        return 0;
+      },
+      1);
+}
+
+void CONEXB200_CommDestroy(void) { conex::Communicator::Get().Destroy(); }
+int CONEXB200_CommWorld(void) { return conex::Communicator::Get().world(); }
+int CONEXB200_CommRank(void) { return conex::Communicator::Get().rank(); }
+
+void CONEXB200_ShardRange(int m, int world, int rank, int* begin, int* count) {
+  *begin = conex::ShardBegin(m, world, rank);
+  *count = conex::ShardBegin(m, world, rank + 1) - *begin;
+}
+
+int CONEXB200_ShardPlan(int m, int world, int rank, int* out5, int capacity) {
+  const auto plan = conex::ShardPlan(m, world, rank);
+  int k = 0;
+  for (const auto& t : plan) {
+    if (k < capacity) {
+      const int v[5] = {t.peer, t.row_begin, t.row_count, t.col_begin, t.col_count};
+      std::memcpy(out5 + 5 * k, v, sizeof(v));
+    }
+    k++;
+  }
+  return k;
 }
 
 int CONEX_Maximize(void* prog_ptr, const double* b, int br, const CONEX_SolverConfiguration* config,

@@ -4,6 +4,7 @@
 #include <cmath>
 
 #include "../../../include/conex_b200_device.h"
+#include "communicator.h"
 #include "tridiagonal_eigenvalues.h"
 
 namespace conex {
@@ -19,6 +20,20 @@ struct DenseLMIConstraint::Storage {
   DeviceBuffer<double> small;    // alpha | beta | reductions
   DeviceBuffer<int> iwork;       // LU pivots + permutation, Lanczos count, LU info
   int panel = 0;
+  // sharded blocks only
+  DeviceBuffer<double> Hloc;     // (m_local+2) x (m_local+1) augmented Gram of the local diagonal block
+  DeviceBuffer<double> recv[2];  // double-buffered chunks of a peer's constraint matrices
+  int chunk = 0;                 // constraint matrices per exchanged chunk
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t arrived[2] = {nullptr, nullptr};
+  cudaEvent_t consumed[2] = {nullptr, nullptr};
+  cudaEvent_t start = nullptr;
+  ~Storage() {
+    for (auto e : arrived) if (e) cudaEventDestroy(e);
+    for (auto e : consumed) if (e) cudaEventDestroy(e);
+    if (start) cudaEventDestroy(start);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
+  }
 };
 
 namespace {
@@ -26,7 +41,7 @@ size_t Sq(int n) { return static_cast<size_t>(n) * n; }
 }  // namespace
 
 DenseLMIConstraint::DenseLMIConstraint(int n, int m, const double* A, const double* C)
-    : n_(n), m_(m), workspace_(n), data_(std::make_shared<Storage>()) {
+    : n_(n), m_(m), m_local_(m), workspace_(n), data_(std::make_shared<Storage>()) {
   data_->Aall.Resize(Sq(n) * (m + 1));
   CudaCheck(cudaMemcpy(data_->Aall.get(), A, sizeof(double) * Sq(n) * m, cudaMemcpyHostToDevice),
             "upload of LMI matrices");
@@ -35,8 +50,26 @@ DenseLMIConstraint::DenseLMIConstraint(int n, int m, const double* A, const doub
             "upload of LMI affine term");
 }
 
+DenseLMIConstraint::DenseLMIConstraint(int n, int m_global, Sharded, DevicePointers dev)
+    : n_(n), m_(m_global), workspace_(n), data_(std::make_shared<Storage>()) {
+  const Communicator& comm = Communicator::Get();
+  if (m_global < comm.world()) {
+    throw std::runtime_error("conex-b200: a sharded LMI block needs at least one matrix per rank");
+  }
+  row_begin_ = ShardBegin(m_global, comm.world(), comm.rank());
+  m_local_ = ShardBegin(m_global, comm.world(), comm.rank() + 1) - row_begin_;
+  sharded_ = comm.distributed();
+  data_->Aall.Resize(Sq(n) * (m_local_ + 1));
+  CudaCheck(cudaMemcpy(data_->Aall.get(), dev.A, sizeof(double) * Sq(n) * m_local_,
+                       cudaMemcpyDeviceToDevice),
+            "copy of LMI matrices");
+  CudaCheck(cudaMemcpy(data_->Aall.get() + Sq(n) * m_local_, dev.C, sizeof(double) * Sq(n),
+                       cudaMemcpyDeviceToDevice),
+            "copy of LMI affine term");
+}
+
 DenseLMIConstraint::DenseLMIConstraint(int n, int m, DevicePointers dev)
-    : n_(n), m_(m), workspace_(n), data_(std::make_shared<Storage>()) {
+    : n_(n), m_(m), m_local_(m), workspace_(n), data_(std::make_shared<Storage>()) {
   data_->Aall.Resize(Sq(n) * (m + 1));
   CudaCheck(cudaMemcpy(data_->Aall.get(), dev.A, sizeof(double) * Sq(n) * m, cudaMemcpyDeviceToDevice),
             "copy of LMI matrices");
@@ -53,9 +86,26 @@ void DenseLMIConstraint::EnsureScratch() {
   const size_t nn = Sq(n_);
   // Panel of constraint matrices scaled per pass: as many as fit in ~1 GiB of scratch.
   const size_t budget = (size_t(1) << 27);  // doubles
-  d.panel = static_cast<int>(std::max<size_t>(1, std::min<size_t>(m_ + 1, budget / nn)));
+  d.panel = static_cast<int>(std::max<size_t>(1, std::min<size_t>(m_local_ + 1, budget / nn)));
   d.T.Resize(nn * d.panel);
-  d.B.Resize(nn * (m_ + 2));
+  d.B.Resize(nn * (m_local_ + 2));
+  if (sharded_) {
+    const long ldl = WorkspaceSchurComplement::AugLd(m_local_);
+    d.Hloc.Resize(static_cast<size_t>(ldl) * (m_local_ + 1));
+    CudaCheck(cudaMemset(d.Hloc.get(), 0, sizeof(double) * d.Hloc.size()), "memset");
+    // Exchanged chunks: up to 4 GiB each, never more than the largest shard
+    const int world = Communicator::Get().world();
+    const int largest = (m_ + world - 1) / world;
+    // (a multiple of the 64-wide GEMM tile so that the block contractions have no ragged columns)
+    size_t chunk = std::min<size_t>(largest, (size_t(1) << 29) / nn);
+    if (chunk >= 64) chunk -= chunk % 64;
+    d.chunk = static_cast<int>(std::max<size_t>(1, chunk));
+    for (auto& r : d.recv) r.Resize(nn * d.chunk);
+    CudaCheck(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : d.arrived) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+    for (auto& e : d.consumed) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+    CudaCheck(cudaEventCreateWithFlags(&d.start, cudaEventDisableTiming), "event");
+  }
   const size_t work = std::max(cxb_lanczos_worksize(n_), cxb_geodesic_worksize(n_));
   d.scratch.Resize(work);
   d.coef.Resize(m_ + 1);
@@ -78,6 +128,9 @@ void ConstructSchurComplementSystem(DenseLMIConstraint* o, bool initialize,
     throw std::runtime_error(
         "conex-b200: DenseLMIConstraint accumulates through the assembler (initialize == true)");
   }
+  if (o->sharded_) {
+    o->AssembleSharded(sys);
+  } else
   DeviceCheck(cxb_schur_dense_lmi(s, o->n_, m, d.Aall.get(), o->workspace_.W.data, d.B.get(),
                                   d.T.get(), d.panel, sys->G.data, sys->G.ld),
               "cxb_schur_dense_lmi");
@@ -91,13 +144,131 @@ void ConstructSchurComplementSystem(DenseLMIConstraint* o, bool initialize,
               "cxb_copy_strided");
 }
 
+// Sharded K1 + K2 (DESIGN.md "Multi-GPU"). Every rank
+//   1. scales its own matrices and contracts its diagonal block with the single-GPU kernel chain
+//      (cxb_schur_dense_lmi on the local m_local matrices; rows m_local, m_local+1 of the local
+//      augmented Gram carry AQc_j, AW_j of the local j),
+//   2. for each task of ShardPlan receives the peer's constraint matrices chunk by chunk
+//      (ncclSend/ncclRecv on a side stream, double-buffered under the DMMA contraction) and
+//      contracts them with its scaled matrices straight into the block's place in the global H,
+//   3. sums the disjoint contributions with one ncclAllReduce over the augmented H — every entry
+//      has exactly one non-zero contributor, so the sum is exact and H is bit-identical everywhere.
+void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
+  auto& d = *data_;
+  Communicator& comm = Communicator::Get();
+  cudaStream_t s = ctx_->cuda_stream();
+  const int n = n_, m = m_, ml = m_local_, rb = row_begin_;
+  const long nn = static_cast<long>(n) * n;
+  const long ldg = sys->G.ld;
+  const long ldl = WorkspaceSchurComplement::AugLd(ml);
+  double* G = sys->G.data;
+
+  CudaCheck(cudaMemsetAsync(G, 0, sizeof(double) * ldg * (m + 1), s), "memset of H");
+  // The side stream may start moving peer matrices as soon as this assembly begins.
+  CudaCheck(cudaEventRecord(d.start, s), "cudaEventRecord");
+  CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.start, 0), "cudaStreamWaitEvent");
+
+  // -- exchange schedule: a flat list of chunks over all distances --------------------------------
+  struct Chunk {
+    int from, recv_begin, recv_count;  // global indices of the matrices received (count 0: none)
+    int to, send_begin, send_count;
+    const PairTask* task;              // task the received chunk belongs to (nullptr: send only)
+  };
+  const std::vector<PairTask> plan = ShardPlan(m, comm.world(), comm.rank());
+  std::vector<Chunk> chunks;
+  for (int dist = 1; dist <= comm.world() / 2; dist++) {
+    const PairTask* task = nullptr;
+    for (const auto& t : plan) {
+      if (t.peer == (comm.rank() + dist) % comm.world()) task = &t;
+    }
+    const SendTask snd = ShardSend(m, comm.world(), comm.rank(), dist);
+    const int nrecv = task ? (task->col_count + d.chunk - 1) / d.chunk : 0;
+    const int nsend = (snd.count + d.chunk - 1) / d.chunk;
+    for (int c = 0; c < std::max(nrecv, nsend); c++) {
+      Chunk ch{};
+      ch.task = nullptr;
+      if (c < nrecv) {
+        ch.from = task->peer;
+        ch.recv_begin = task->col_begin + c * d.chunk;
+        ch.recv_count = std::min(d.chunk, task->col_begin + task->col_count - ch.recv_begin);
+        ch.task = task;
+      }
+      if (c < nsend) {
+        ch.to = snd.to;
+        ch.send_begin = snd.begin + c * d.chunk;
+        ch.send_count = std::min(d.chunk, snd.begin + snd.count - ch.send_begin);
+      }
+      chunks.push_back(ch);
+    }
+  }
+  auto post = [&](size_t c) {  // enqueue the transfer of chunk c on the side stream
+    const Chunk& ch = chunks[c];
+    const int buf = static_cast<int>(c % 2);
+    if (c >= 2) CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.consumed[buf], 0), "cudaStreamWaitEvent");
+    const double* src = ch.send_count ? d.Aall.get() + static_cast<long>(ch.send_begin - rb) * nn : nullptr;
+    comm.SendRecv(src, static_cast<size_t>(ch.send_count) * nn, ch.to, d.recv[buf].get(),
+                  static_cast<size_t>(ch.recv_count) * nn, ch.from, d.comm_stream);
+    CudaCheck(cudaEventRecord(d.arrived[buf], d.comm_stream), "cudaEventRecord");
+  };
+  if (!chunks.empty()) post(0);
+
+  // -- 1. local diagonal block (overlaps the first transfer) --------------------------------------
+  DeviceCheck(cxb_schur_dense_lmi(s, n, ml, d.Aall.get(), workspace_.W.data, d.B.get(), d.T.get(),
+                                  d.panel, d.Hloc.get(), ldl),
+              "cxb_schur_dense_lmi(local block)");
+  // H[rb.., rb..] <- Hloc[0:ml, 0:ml]; rows m, m+1 (AQc, AW) <- rows ml, ml+1 of the local columns
+  CudaCheck(cudaMemcpy2DAsync(G + static_cast<long>(rb) * ldg + rb, sizeof(double) * ldg, d.Hloc.get(),
+                              sizeof(double) * ldl, sizeof(double) * ml, ml, cudaMemcpyDeviceToDevice, s),
+            "copy of the diagonal block");
+  CudaCheck(cudaMemcpy2DAsync(G + static_cast<long>(rb) * ldg + m, sizeof(double) * ldg,
+                              d.Hloc.get() + ml, sizeof(double) * ldl, sizeof(double) * 2, ml,
+                              cudaMemcpyDeviceToDevice, s),
+            "copy of the residual rows");
+  if (comm.rank() == 0) {  // <c,Qc> and <w,c> are the same on every rank: contributed once
+    CudaCheck(cudaMemcpyAsync(G + static_cast<long>(m) * ldg + m, d.Hloc.get() + static_cast<long>(ml) * ldl + ml,
+                              sizeof(double) * 2, cudaMemcpyDeviceToDevice, s),
+              "copy of the scalars");
+  }
+
+  // -- 2. off-diagonal blocks ----------------------------------------------------------------------
+  for (size_t c = 0; c < chunks.size(); c++) {
+    if (c + 1 < chunks.size()) post(c + 1);
+    const Chunk& ch = chunks[c];
+    const int buf = static_cast<int>(c % 2);
+    CudaCheck(cudaStreamWaitEvent(s, d.arrived[buf], 0), "cudaStreamWaitEvent");
+    if (ch.recv_count > 0) {
+      const PairTask& t = *ch.task;
+      const double* Bl = d.B.get() + static_cast<long>(t.row_begin - rb) * nn;
+      if (t.peer < comm.rank()) {
+        // block below the diagonal: H[rows, cols] = B_rows^T A_cols
+        DeviceCheck(cxb_dgemm(s, 1, 0, t.row_count, ch.recv_count, static_cast<int>(nn), 1.0, Bl, nn, 0,
+                              d.recv[buf].get(), nn, 0, 0.0,
+                              G + static_cast<long>(ch.recv_begin) * ldg + t.row_begin, ldg, 0, 1, 0),
+                    "cxb_dgemm(off-diagonal block)");
+      } else {
+        // block above the diagonal: store its transpose H[cols, rows] = A_cols^T B_rows
+        DeviceCheck(cxb_dgemm(s, 1, 0, ch.recv_count, t.row_count, static_cast<int>(nn), 1.0,
+                              d.recv[buf].get(), nn, 0, Bl, nn, 0, 0.0,
+                              G + static_cast<long>(t.row_begin) * ldg + ch.recv_begin, ldg, 0, 1, 0),
+                    "cxb_dgemm(off-diagonal block, transposed)");
+      }
+    }
+    CudaCheck(cudaEventRecord(d.consumed[buf], s), "cudaEventRecord");
+  }
+  // -- 3. one all-reduce over the augmented H -------------------------------------------------------
+  comm.AllReduceSum(G, static_cast<size_t>(ldg) * (m + 1), s);
+}
+
 void DenseLMIConstraint::ComputeNegativeSlack(double k, const Ref& y, Ref* minus_s) {
   auto& d = *data_;
-  ctx_->CopyOnDevice(d.coef.get(), y.data, m_);
-  DeviceCheck(cxb_fill(ctx_->stream(), 1, -k, d.coef.get() + m_), "cxb_fill");
-  DeviceCheck(cxb_gemv_n(ctx_->stream(), (long)Sq(n_), m_ + 1, d.Aall.get(), d.coef.get(),
+  ctx_->CopyOnDevice(d.coef.get(), y.data + row_begin_, m_local_);
+  // the affine term is added once (rank 0); the other ranks contribute 0 * C
+  const double c_coef = (!sharded_ || Communicator::Get().rank() == 0) ? -k : 0.0;
+  DeviceCheck(cxb_fill(ctx_->stream(), 1, c_coef, d.coef.get() + m_local_), "cxb_fill");
+  DeviceCheck(cxb_gemv_n(ctx_->stream(), (long)Sq(n_), m_local_ + 1, d.Aall.get(), d.coef.get(),
                          minus_s->data),
               "cxb_gemv_n");
+  if (sharded_) Communicator::Get().AllReduceSum(minus_s->data, Sq(n_), ctx_->cuda_stream());
 }
 
 DenseLMIConstraint::SpectrumEstimate DenseLMIConstraint::EstimateSpectrum(const Ref& WS,

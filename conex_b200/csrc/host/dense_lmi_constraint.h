@@ -45,6 +45,13 @@ class DenseLMIConstraint {
     const double* C;
   };
   DenseLMIConstraint(int n, int m, DevicePointers dev);
+  // One rank's shard of a block whose m constraint matrices are partitioned over the ranks of the
+  // process-wide Communicator (communicator.h: rank r owns [ShardBegin(m, world, r),
+  // ShardBegin(m, world, r + 1))). `dev.A` holds only the local matrices, `dev.C` the full affine
+  // term (replicated). W, y and the whole Newton system stay replicated and bit-identical on every
+  // rank; only K1/K2 (assembly) and K6 (slack GEMV) are sharded — see DESIGN.md "Multi-GPU".
+  struct Sharded {};
+  DenseLMIConstraint(int n, int m_global, Sharded, DevicePointers dev);
 
   WorkspaceDensePSD* workspace() { return &workspace_; }
   int number_of_variables() const { return m_; }
@@ -73,8 +80,13 @@ class DenseLMIConstraint {
   };
   SpectrumEstimate EstimateSpectrum(const Ref& WS, const Ref& start_matrix);
 
+  void AssembleSharded(SchurComplementSystem* sys);
+
   int n_;
-  int m_;
+  int m_;             // number of variables of the block (global)
+  int m_local_;       // constraint matrices held by this rank (== m_ when not sharded)
+  int row_begin_ = 0;  // global index of the first local matrix
+  bool sharded_ = false;
   WorkspaceDensePSD workspace_;
   std::shared_ptr<Storage> data_;
   DeviceContext* ctx_ = nullptr;

@@ -47,6 +47,32 @@ void CONEXB200_AssembleNewtonSystem(void* prog, int coldstart, double* H, double
 int CONEXB200_AddDenseLMIConstraintDevice(void* prog, const double* d_A, int n, int m,
                                           const double* d_C);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink 5 / NVSwitch (DESIGN.md "Multi-GPU") ----------
+ * Rendezvous: rank 0 calls CONEXB200_CommGetUniqueId and ships the 128 bytes to the other ranks by
+ * any means (torch.distributed, MPI, a file); every rank then calls CONEXB200_CommInitRank after
+ * selecting its device (cudaSetDevice / torch.cuda.set_device). All return 0 on success, 1 on failure
+ * (message on stderr). With world == 1 no NCCL is needed and none is loaded. */
+int CONEXB200_CommGetUniqueId(char* out128);
+int CONEXB200_CommInitRank(int world, int rank, const char* id128);
+void CONEXB200_CommDestroy(void);
+int CONEXB200_CommWorld(void);
+int CONEXB200_CommRank(void);
+
+/* The 1-D row partition used for a sharded block: rank r owns the constraint matrices
+ * [begin, begin + count) of m. */
+void CONEXB200_ShardRange(int m, int world, int rank, int* begin, int* count);
+/* The off-diagonal block tasks of `rank` (host logic, no GPU): writes up to `capacity` records of
+ * five ints {peer, row_begin, row_count, col_begin, col_count} and returns the number of tasks. */
+int CONEXB200_ShardPlan(int m, int world, int rank, int* out5, int capacity);
+
+/* This rank's shard of a dense LMI block with m constraint matrices in total: d_A_local holds the
+ * rank's own matrices (CONEXB200_ShardRange) as contiguous column-major n x n blocks in device
+ * memory, d_C the full affine term. Every rank of the communicator must add the same block. The
+ * solve calls (CONEX_Maximize, ...) are then collective: every rank calls them with the same
+ * arguments and receives the same y. */
+int CONEXB200_AddDenseLMIConstraintShard(void* prog, const double* d_A_local, int n, int m,
+                                         const double* d_C);
+
 /* Host-logic probes that need no GPU: the closed-form mu rule (reference divergence.cc:96-111) and
  * the extreme eigenvalues of a Lanczos Jacobi matrix (alpha: n, beta: n-1; out2 = {min, max}). */
 double CONEXB200_DivergenceUpperBoundInverse(double bound, double frobenius_norm_squared,

@@ -54,6 +54,12 @@ def product():
         L.cxb_gather_vec.argtypes = [vp, C.c_int, vp, vp, vp]
         L.cxb_affine_update.argtypes = [vp, C.c_int, vp, vp, C.c_double]
         L.CONEXB200_AddDenseLMIConstraintDevice.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        L.CONEXB200_AddDenseLMIConstraintShard.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        L.CONEXB200_CommGetUniqueId.argtypes = [C.c_char_p]
+        L.CONEXB200_CommInitRank.argtypes = [C.c_int, C.c_int, C.c_char_p]
+        L.CONEXB200_CommDestroy.restype = None
+        L.CONEXB200_ShardRange.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.CONEXB200_ShardRange.restype = None
         L.CONEXB200_GetIterationMilliseconds.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
         L.CONEXB200_SetTiming.argtypes = [vp, C.c_int]
         L.CONEXB200_GetIterationPhaseMilliseconds.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
@@ -96,3 +102,24 @@ def izeros(n):
 
 def ptr(t):
     return C.c_void_p(t.data_ptr())
+
+
+def init_communicator(dev, rank, world):
+    """Rendezvous of the library's NCCL communicator over an initialised torch.distributed group:
+    rank 0 creates the unique id, torch broadcasts its 128 bytes, every rank joins."""
+    import torch
+    import torch.distributed as dist
+    L = dev.lib
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        assert L.CONEXB200_CommGetUniqueId(buf) == 0
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    ident = bytes(t.cpu().tolist())
+    assert L.CONEXB200_CommInitRank(world, rank, ident) == 0
+
+
+def shard_range(dev, m, world, rank):
+    b, c = C.c_int(), C.c_int()
+    dev.lib.CONEXB200_ShardRange(m, world, rank, C.byref(b), C.byref(c))
+    return b.value, c.value
