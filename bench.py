@@ -5,12 +5,14 @@ vs roofline).
   python bench.py --gpus N --steps K --warmup W          # B200 arm (one rank per GPU under torchrun)
   python bench.py --impl reference --steps K --warmup W  # CPU arm: the oracle port on the host cores
 
-Workload at N = 1 (config 2 of BASELINE.json): MaxCut dual SDP on a random graph, n = m = 2000,
-one dense PSD block driven through the dense-LMI path of the C ABI (A_i = -e_i e_i^T stored as dense
-n x n matrices, 64 GB in HBM — far larger than the 126 MB L2, so no L2 flush is needed between
-steps). A "step" is one full Newton step of CONEX_Maximize (assemble H, factor, choose mu, solve,
-eigen-bound, geodesic update) at the running iterate; W + K steps run inside one solve and every
-step is timed with CUDA events on the solver's stream.
+Default workload (config 2 of BASELINE.json, the one the metric is quoted on): MaxCut dual SDP on a
+random graph, n = m = 2000, one dense PSD block driven through the dense-LMI path of the C ABI
+(A_i = -e_i e_i^T stored as dense n x n matrices, 64 GB in HBM — far larger than the 126 MB L2, so
+no L2 flush is needed between steps). A "step" is one full Newton step of CONEX_Maximize (assemble
+H, factor, choose mu, solve, eigen-bound, geodesic update) at the running iterate; W + K steps run
+inside one solve and every step is timed with CUDA events on the solver's stream. With N > 1 the same
+step is sharded over the ranks (strong scaling). `--workload c5|c4|c1` selects the other single-block
+configurations of BASELINE.json (large-m dense LMI, Lovasz theta, the small reference case).
 """
 import argparse
 import ctypes as C
@@ -40,23 +42,98 @@ def algorithmic_flops(n, m):
     return dict(k1=k1, k2=k2, k3=k3, k78=k78, tensor=k1 + k2 + k3 + k78)
 
 
-def maxcut_on_device(n, seed, row_begin=0, row_count=None, p=0.5):
-    """Device-resident MaxCut data: the constraint matrices A_i = -e_i e_i^T for
-    i in [row_begin, row_begin + row_count) as dense column-major n x n blocks (this rank's shard;
-    all of them by default) and C = -L/4 (identical on every rank: same seed)."""
+WORKLOADS = {
+    "c2": dict(kind="maxcut", n=2000, m=2000, cpu=dict(n=400, m=400)),
+    "c5": dict(kind="random", n=1000, m=20000, cpu=dict(n=120, m=600)),
+    "c4": dict(kind="lovasz", n=500, m=10001, cpu=dict(n=100, m=401)),
+    "c1": dict(kind="random", n=50, m=100, cpu=dict(n=50, m=100)),
+}
+
+
+def workload_shape(args):
+    w = dict(WORKLOADS[args.workload])
+    if args.n:
+        w["n"] = args.n
+        if w["kind"] == "maxcut":
+            w["m"] = args.n
+    if args.m:
+        w["m"] = args.m
+    names = {"maxcut": "maxcut_sdp_n{n}_dense_lmi", "random": "dense_lmi_sdp_n{n}_m{m}",
+             "lovasz": "lovasz_theta_n{n}_m{m}"}
+    w["name"] = names[w["kind"]].format(**w)
+    return w
+
+
+def lovasz_edges(n, num_edges, seed=4):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    idx = np.sort(rng.choice(n * (n - 1) // 2, size=num_edges, replace=False))
+    # unrank the pair (i < j) from its index in row-major order of the strict upper triangle
+    i = (n - 2 - np.floor(np.sqrt(-8.0 * idx + 4.0 * n * (n - 1) - 7) / 2.0 - 0.5)).astype(np.int64)
+    j = (idx + i + 1 - n * (n - 1) // 2 + (n - i) * ((n - i) - 1) // 2).astype(np.int64)
+    return i, j
+
+
+class _Raw:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2}
+
+
+def device_view(ptr, count):
+    """torch view (no copy) of `count` doubles of library-owned device memory."""
     import torch
-    row_count = n if row_count is None else row_count
-    g = torch.Generator(device="cuda")
-    g.manual_seed(seed)
-    upper = torch.triu((torch.rand((n, n), generator=g, device="cuda") < p).double(), 1)
-    adj = upper + upper.T
-    lap = torch.diag(adj.sum(1)) - adj
-    Cm = (-lap / 4.0).contiguous()  # symmetric: row-major == column-major
-    A = torch.zeros((row_count, n * n), dtype=torch.float64, device="cuda")
+    return torch.as_tensor(_Raw(ptr, count), device="cuda")
+
+
+def fill_workload(kind, n, m, row_begin, row_count, A, Cm):
+    """Writes this rank's constraint matrices (global indices row_begin .. row_begin+row_count-1) into
+    A (row_count x n*n view, column-major n x n blocks) and the affine term into Cm (n x n), in place
+    on the device; returns the local slice of the cost vector b. Same bytes for any sharding."""
+    import torch
     idx = torch.arange(row_count, device="cuda")
     gi = idx + row_begin
-    A[idx, gi * n + gi] = -1.0
-    return A, Cm
+    if kind == "maxcut":  # A_i = -e_i e_i^T, C = -L/4, b = -1 (SURVEY.md 8d, C2)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(2)
+        upper = torch.triu((torch.rand((n, n), generator=g, device="cuda") < 0.5).double(), 1)
+        adj = upper + upper.T
+        Cm.copy_(-(torch.diag(adj.sum(1)) - adj) / 4.0)
+        A.zero_()
+        A[idx, gi * n + gi] = -1.0
+        return -np.ones(row_count)
+    if kind == "random":  # A_i = sym(U[-1,1]), C = I, b = tr(A_i)/2 (test_util.cc:19,67-73; C1/C5)
+        Cm.copy_(torch.eye(n, dtype=torch.float64, device="cuda"))
+        b = torch.empty(row_count, dtype=torch.float64, device="cuda")
+        blk = 32
+        A3 = A.view(row_count, n, n)
+        for g0 in range((row_begin // blk) * blk, row_begin + row_count, blk):
+            g = torch.Generator(device="cuda")
+            g.manual_seed(1000003 + g0)
+            R = torch.rand((blk, n, n), generator=g, device="cuda", dtype=torch.float64) * 2.0 - 1.0
+            R = 0.5 * (R + R.transpose(1, 2))
+            lo, hi = max(g0, row_begin), min(g0 + blk, row_begin + row_count)
+            A3[lo - row_begin:hi - row_begin] = R[lo - g0:hi - g0]
+            b[lo - row_begin:hi - row_begin] = 0.5 * R[lo - g0:hi - g0].diagonal(dim1=1, dim2=2).sum(-1)
+        return b.cpu().numpy()
+    if kind == "lovasz":  # vars (t, y_e): A_0 = -I, A_e = E_ij + E_ji, C = -J, maximise -t (C4)
+        Cm.fill_(-1.0)
+        A.zero_()
+        ei, ej = lovasz_edges(n, m - 1)
+        ei = torch.from_numpy(ei).cuda()
+        ej = torch.from_numpy(ej).cuda()
+        is0 = gi == 0
+        if bool(is0.any()):
+            d = torch.arange(n, device="cuda")
+            A[0, d * n + d] = -1.0
+        e = gi[~is0] - 1
+        rows = idx[~is0]
+        A[rows, ej[e] * n + ei[e]] = 1.0
+        A[rows, ei[e] * n + ej[e]] = 1.0
+        b = np.zeros(row_count)
+        if row_begin == 0:
+            b[0] = -1.0
+        return b
+    raise ValueError(kind)
 
 
 class ClockSampler:
@@ -133,36 +210,57 @@ def measure_fp64_peak():
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def cpu_baseline(n, steps, warmup, threads=None):
+def cpu_problem(kind, n, m):
+    from harness import lovasz_theta_lmi, maxcut_lmi, random_dense_lmi
+    if kind == "maxcut":
+        return maxcut_lmi(n, 2)
+    if kind == "lovasz":
+        return lovasz_theta_lmi(n, m - 1, 4)
+    mats, Cm = random_dense_lmi(n, m, 1)
+    return mats, Cm, None
+
+
+def phase_model(n, m):
+    """Work per phase used to extrapolate the CPU sample: assembly 4mn^3 + m^2 n^2
+    flop, factor m^3/3, each solve m^2, update/mu n^3-scale GEMMs + the mn^2 slack GEMV."""
+    return dict(assemble=4.0 * m * n ** 3 + float(m) * m * n ** 2, factor=m ** 3 / 3.0, solve=float(m) * m,
+                update=10.7 * n ** 3 + 2.0 * m * n ** 2, mu=4.0 * n ** 3 + 2.0 * m * n ** 2 + float(m) * m)
+
+
+def cpu_baseline(w, steps, warmup, threads=None):
     """Times the oracle port (reference algorithm as written, OpenBLAS underneath) on a reduced
-    MaxCut instance and extrapolates to n = m = 2000 with the F_iter cost model: with m = n the
-    assembly scales as n^5, factor/update as n^3, solves as n^2."""
-    from harness import maxcut_lmi, oracle
+    instance of the same workload and extrapolates each phase to the full shape with the work model
+    above (the full operators, 64-160 GB, do not fit the host; the as-written Gram alone would take
+    tens of minutes per step)."""
+    from harness import oracle
     O = oracle()
     cores = threads or os.cpu_count()
     O.lib.ORACLE_SetBlasThreads(cores)
-    mats, Cm, b = maxcut_lmi(n, 2)
+    ns, ms = w["cpu"]["n"], w["cpu"]["m"]
+    mats, Cm, b = cpu_problem(w["kind"], ns, ms)
     P = O.program()
     P.add_dense_lmi(mats, Cm)
+    if b is None:
+        b = P.feasible_objective()
     total = warmup + steps
     cfg = O.default_config(max_iterations=total, final_centering_steps=0, inv_sqrt_mu_max=1e12)
     t0 = time.perf_counter()
     P.maximize(b, cfg)
     wall = time.perf_counter() - t0
     its = max(P.status()["num_iterations"], 1)
-    ph = P.phase_seconds()
-    per = {k: v / its for k, v in ph.items()}
-    step_s = wall / its
-    r = 2000.0 / n
-    full_s = (per["assemble"] * r ** 5 + per["factor"] * r ** 3 + (per["update"] + per["mu"]) * r ** 3 +
-              per["solve"] * r ** 2)
+    per = {k: v / its for k, v in P.phase_seconds().items()}
+    full, small = phase_model(w["n"], w["m"]), phase_model(ns, ms)
+    ratio = {k: full[k] / small[k] for k in full}
+    full_s = sum(per[k] * ratio[k] for k in per)
+    same = (ns, ms) == (w["n"], w["m"])
     return {
-        "value": full_s * 1e3, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": (f"oracle port (as-written Gram, OpenBLAS x{cores} threads) on MaxCut n=m={n}, "
-                   f"{its} Newton steps, {step_s * 1e3:.1f} ms/step measured; value is the per-phase "
-                   f"extrapolation to n=m=2000 (assemble x{r ** 5:.0f}, factor/update x{r ** 3:.0f}, "
-                   f"solve x{r ** 2:.0f}) because 64 GB of A does not fit the host"),
-        "sample_ms_per_step": step_s * 1e3,
+        "value": (wall / its if same else full_s) * 1e3, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": (f"oracle port (as-written Gram, OpenBLAS x{cores} threads) on {w['kind']} n={ns} m={ms}, "
+                   f"{its} Newton steps, {wall / its * 1e3:.1f} ms/step measured" +
+                   ("" if same else "; value is the per-phase extrapolation to "
+                    f"n={w['n']} m={w['m']} by the work model (" +
+                    ", ".join(f"{k} x{ratio[k]:.0f}" for k in ratio) + ")")),
+        "sample_ms_per_step": wall / its * 1e3,
         "sample_phase_ms": {k: v * 1e3 for k, v in per.items()},
     }
 
@@ -171,15 +269,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_n
-    cb = cpu_baseline(n, args.steps, args.warmup)
+    w = workload_shape(args)
+    cb = cpu_baseline(w, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"],
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "maxcut_sdp_n2000_dense_lmi", "n": 2000, "m": 2000,
-                   "measured_on": f"n=m={n} sample, extrapolated"},
+        "config": {"workload": w["name"], "n": w["n"], "m": w["m"],
+                   "measured_on": f"n={w['cpu']['n']} m={w['cpu']['m']} sample, extrapolated"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -201,7 +299,8 @@ def run_b200(args):
     L = dev.lib
     assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
 
-    n = m = args.n
+    w = workload_shape(args)
+    n, m = w["n"], w["m"]
     fl = algorithmic_flops(n, m)
     peak_tf = measure_fp64_peak() if rank == 0 else None
 
@@ -210,22 +309,27 @@ def run_b200(args):
     if world > 1:
         devlib.init_communicator(dev, rank, world)
     rb, rc = devlib.shard_range(dev, m, world, rank)
-    A, Cm = maxcut_on_device(n, 2, rb, rc)
-    torch.cuda.synchronize()
     P = dev.program()
-    if world > 1:
-        cid = L.CONEXB200_AddDenseLMIConstraintShard(P.h, C.c_void_p(A.data_ptr()), n, m,
-                                                     C.c_void_p(Cm.data_ptr()))
-    else:
-        cid = L.CONEXB200_AddDenseLMIConstraintDevice(P.h, C.c_void_p(A.data_ptr()), n, m,
-                                                      C.c_void_p(Cm.data_ptr()))
-    assert cid == 0
+    if args.assembly_mode:
+        L.CONEXB200_SetAssemblyMode(P.h, args.assembly_mode)
+    pA, pC = C.c_void_p(), C.c_void_p()
+    cid = L.CONEXB200_NewDenseLMIConstraintStorage(P.h, n, m, C.byref(pA), C.byref(pC))
+    assert cid == 0, "allocation of the constraint matrices failed"
+    A = device_view(pA.value, rc * n * n).view(rc, n * n)
+    Cm = device_view(pC.value, n * n).view(n, n)
+    b_local = fill_workload(w["kind"], n, m, rb, rc, A, Cm)
+    torch.cuda.synchronize()
     P.m = m
     P.cone_shapes.append((n, n))
-    del A
+    del A, Cm
     torch.cuda.empty_cache()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, b_local)
+        b = np.concatenate(parts)
+    else:
+        b = b_local
     setup_s = time.perf_counter() - t_setup
-    b = -np.ones(m)
 
     total = args.warmup + args.steps
     cfg = dev.default_config(max_iterations=total, final_centering_steps=0, inv_sqrt_mu_max=1e12)
@@ -287,9 +391,10 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "maxcut_sdp_n2000_dense_lmi" if n == 2000 else f"maxcut_sdp_n{n}_dense_lmi",
-                   "n": n, "m": m, "path": "CONEX_AddDenseLMIConstraint (dense A_i, 64 GB resident)",
-                   "l2": "inputs (64 GB) exceed the 126 MB L2; no flush needed",
+        "config": {"workload": w["name"], "n": n, "m": m,
+                   "path": f"dense-LMI path of the C ABI (dense A_i, {8e-9 * m * n * n:.1f} GB resident)",
+                   "l2": f"inputs ({8e-9 * m * n * n:.1f} GB) vs 126 MB L2: " +
+                         ("no flush needed" if 8.0 * m * n * n > 4 * 126e6 else "L2-resident workload"),
                    "multi_gpu": (f"one Newton step sharded over {world} ranks: constraint matrices and the rows "
                                  "of H partitioned 1-D (K1/K2/K6 sharded, peer matrices over NCCL "
                                  "send/recv, H by all-reduce); factor/solve/eigen-bound/geodesic update "
@@ -317,7 +422,7 @@ def run_b200(args):
         "final": {"by": log[-1]["by"], "cx": log[-1]["cx"], "mu": log[-1]["mu"]},
     }
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_n, 2, 1)
+        line["cpu_baseline"] = cpu_baseline(w, 2, 1)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -329,8 +434,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=2000, help="MaxCut size (n = m); 2000 is the headline")
-    ap.add_argument("--cpu-n", type=int, default=400, help="size of the CPU-baseline sample")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration (c2 = MaxCut n=2000, the headline)")
+    ap.add_argument("--size", dest="n", type=int, default=0, help="override the PSD order n")
+    ap.add_argument("--constraints", dest="m", type=int, default=0, help="override the number of constraints m")
+    ap.add_argument("--assembly-mode", type=int, default=0, help="0 auto, 1 keep all W A_i W, 2 stream row panels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -12,10 +12,12 @@ int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, do
           const double* A, long lda, long sA, const double* B, long ldb, long sB, double beta,
           double* C, long ldc, long sC, int batch, bool lower_only);
 // Full-control variant: config < 0 = pick from the shape, splits == 0 = automatic split-K,
-// mirror = also store the transposed entries of a lower_only square result.
+// mirror = also store the transposed entries of a lower_only square result; with lower_only the
+// entries kept are those with row + diag_off >= col (row panels of a lower-triangular result).
 int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool transB, int M, int N, int K,
             double alpha, const double* A, long lda, long sA, const double* B, long ldb, long sB,
-            double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror);
+            double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror,
+            int diag_off = 0);
 
 // blas1.cu
 int SetIdentity(cudaStream_t s, int n, double* W);

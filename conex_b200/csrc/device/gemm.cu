@@ -37,7 +37,8 @@ struct GemmArgs {
   long ldb, sB;
   double* C;
   long ldc, sC;
-  int lower;    // only entries with row >= col
+  int lower;    // only entries with row + diag_off >= col
+  int diag_off; // row offset of this block relative to the diagonal (trapezoids / row panels)
   int mirror;   // also store C[col, row] (requires lower, M == N)
   int tiles_m, tiles_n;
   int splits;   // split-K factor (>1: partials go to `partials`, batch must be 1)
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
   const int tm = blockIdx.x % g.tiles_m;
   const int tn = blockIdx.x / g.tiles_m;
   const int m0 = tm * BM, n0 = tn * BN;
-  if (g.lower && m0 + BM - 1 < n0) return;  // tile strictly above the diagonal
+  if (g.lower && m0 + BM - 1 + g.diag_off < n0) return;  // tile strictly above the diagonal
   const double* A = g.A + (long)blockIdx.z * g.sA;
   const double* B = g.B + (long)blockIdx.z * g.sB;
   double* C = g.C + (long)blockIdx.z * g.sC;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
         for (int e = 0; e < 2; e++) {
           const int c = n0 + wn0 + j * 8 + tig * 2 + e;
           if (c >= g.N) continue;
-          if (g.lower && r < c) continue;
+          if (g.lower && r + g.diag_off < c) continue;
           P[(long)c * g.M + r] = acc[i][j][e];
         }
       }
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
       for (int e = 0; e < 2; e++) {
         const int c = n0 + wn0 + j * 8 + tig * 2 + e;
         if (c >= g.N) continue;
-        if (g.lower && r < c) continue;
+        if (g.lower && r + g.diag_off < c) continue;
         double* p = C + (long)c * g.ldc + r;
         double v = g.alpha * acc[i][j][e];
         if (use_beta) v += g.beta * (*p);
@@ -274,10 +275,10 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 __global__ void __launch_bounds__(256) SplitKReduceKernel(int M, int N, int splits,
                                                           const double* __restrict__ partials,
                                                           double alpha, double beta, double* C, long ldc,
-                                                          int lower) {
+                                                          int lower, int diag_off) {
   const int r = blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y;
-  if (r >= M || (lower && r < c)) return;
+  if (r >= M || (lower && r + diag_off < c)) return;
   const long mn = (long)M * N;
   const double* p = partials + (long)c * M + r;
   double s = 0;
@@ -323,8 +324,9 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
   if (g.lower) {
     active = 0;
     for (int tn = 0; tn < g.tiles_n; tn++) {
-      const int first = (tn * BN - BM + 1 + BM - 1) / BM;  // smallest tm with tm*BM + BM - 1 >= tn*BN
-      const int f = first < 0 ? 0 : first;
+      // smallest tm with tm*BM + BM - 1 + diag_off >= tn*BN
+      const long num = (long)tn * BN - g.diag_off;
+      const int f = num <= 0 ? 0 : (int)(num / BM);
       if (f < g.tiles_m) active += g.tiles_m - f;
     }
   }
@@ -363,7 +365,7 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
   if (splits > 1) {
     dim3 rg((g.M + 255) / 256, g.N);
     CountLaunch(); SplitKReduceKernel<<<rg, 256, 0, stream>>>(g.M, g.N, splits, g.partials, g.alpha, g.beta,
-                                                  g.C, g.ldc, g.lower);
+                                                  g.C, g.ldc, g.lower, g.diag_off);
   }
   return LaunchStatus();
 }
@@ -404,10 +406,11 @@ int PickConfig(int M, int N) {
 
 int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool transB, int M, int N, int K,
             double alpha, const double* A, long lda, long sA, const double* B, long ldb, long sB,
-            double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror) {
+            double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror,
+            int diag_off) {
   if (M <= 0 || N <= 0 || batch <= 0) return 0;
   if (K < 0) return -1;
-  if (mirror && (!lower_only || M != N)) return -1;
+  if (mirror && (!lower_only || M != N || diag_off != 0)) return -1;
   GemmArgs g;
   g.M = M;
   g.N = N;
@@ -424,6 +427,7 @@ int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool trans
   g.ldc = ldc;
   g.sC = sC;
   g.lower = lower_only ? 1 : 0;
+  g.diag_off = diag_off;
   g.mirror = mirror ? 1 : 0;
   g.tiles_m = g.tiles_n = 0;
   g.splits = 1;
@@ -450,7 +454,7 @@ int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, do
           const double* A, long lda, long sA, const double* B, long ldb, long sB, double beta,
           double* C, long ldc, long sC, int batch, bool lower_only) {
   return DgemmEx(stream, -1, 0, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
-                 batch, lower_only, false);
+                 batch, lower_only, false, 0);
 }
 
 void SetDefaultGemmConfig(int config) { g_default_large_config = config; }
@@ -468,10 +472,11 @@ extern "C" int cxb_dgemm(void* stream, int transA, int transB, int M, int N, int
 extern "C" int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, int M, int N,
                             int K, double alpha, const double* dA, long lda, long strideA,
                             const double* dB, long ldb, long strideB, double beta, double* dC,
-                            long ldc, long strideC, int batch, int lower_only, int mirror) {
+                            long ldc, long strideC, int batch, int lower_only, int mirror,
+                            int diag_off) {
   return cxb::DgemmEx(cxb::AsStream(stream), config, splits, transA != 0, transB != 0, M, N, K, alpha,
                       dA, lda, strideA, dB, ldb, strideB, beta, dC, ldc, strideC, batch,
-                      lower_only != 0, mirror != 0);
+                      lower_only != 0, mirror != 0, diag_off);
 }
 
 extern "C" void cxb_set_default_gemm_config(int config) { cxb::SetDefaultGemmConfig(config); }

@@ -33,3 +33,37 @@ extern "C" int cxb_schur_dense_lmi(void* stream, int n, int m, const double* dAa
   return Dgemm(s, true, false, m + 2, m + 1, (int)nn, 1.0, dB, nn, 0, dAall, nn, 0, 0.0, dHaug, ldh, 0,
                1, true);
 }
+
+// Same result without ever materialising all of B: one row panel of scaled matrices at a time is
+// formed and immediately contracted against the constraint matrices to its left
+// (Haug[p0 + q, c] = <B_q, A_c>, c <= p0 + q). dBp: (panel + 1) * n * n doubles, dT: panel * n * n.
+// Memory: A + two panels instead of 2 A — what lets config 5 (n = 1000, m = 20000, A = 160 GB) run on
+// one 192 GB B200. Cost: A is re-read once per row panel ((m / panel) / 2 passes over A in total).
+extern "C" int cxb_schur_dense_lmi_streamed(void* stream, int n, int m, const double* dAall,
+                                            const double* dW, double* dBp, double* dT, int panel,
+                                            double* dHaug, long ldh) {
+  using namespace cxb;
+  cudaStream_t s = AsStream(stream);
+  if (n < 1 || m < 1 || panel < 1 || ldh < m + 2) return -1;
+  const long nn = (long)n * n;
+  const int total = m + 1;  // A_0..A_{m-1}, C
+  for (int p0 = 0; p0 < total; p0 += panel) {
+    const int pb = (panel < total - p0) ? panel : (total - p0);
+    int rc = Dgemm(s, false, false, n, n, n, 1.0, dAall + (long)p0 * nn, n, nn, dW, n, 0, 0.0, dT, n,
+                   nn, pb, false);
+    if (rc) return rc;
+    rc = DgemmEx(s, -1, 1, false, false, n, n, n, 1.0, dW, n, 0, dT, n, nn, 0.0, dBp, n, nn, pb, true,
+                 true);
+    if (rc) return rc;
+    int rows = pb;
+    if (p0 + pb == total) {  // last panel: W rides along as row m + 1 (AW_j = <W, A_j>, <w,c>)
+      cudaMemcpyAsync(dBp + (long)pb * nn, dW, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s);
+      rows = pb + 1;
+    }
+    const int cols = (p0 + rows < total) ? (p0 + rows) : total;
+    rc = DgemmEx(s, -1, 0, true, false, rows, cols, (int)nn, 1.0, dBp, nn, 0, dAall, nn, 0, 0.0,
+                 dHaug + p0, ldh, 0, 1, true, false, p0);
+    if (rc) return rc;
+  }
+  return LaunchStatus();
+}

@@ -165,6 +165,22 @@ int CONEXB200_AddDenseLMIConstraintShard(void* prog, const double* d_A_local, in
       -1);
 }
 
+int CONEXB200_NewDenseLMIConstraintStorage(void* prog, int n, int m, double** d_A_local, double** d_C) {
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
+        const int id = program.NumberOfConstraints();
+        DenseLMIConstraint cone(n, m, DenseLMIConstraint::Sharded{}, DenseLMIConstraint::Uninitialized{});
+        // copies of the cone share one Storage (shared_ptr), so these pointers stay valid
+        *d_A_local = cone.mutable_device_matrices();
+        *d_C = cone.mutable_device_matrices() + static_cast<size_t>(n) * n * cone.local_matrices();
+        program.AddConstraint(cone);
+        return id;
+      },
+      -1);
+}
+
 int CONEXB200_CommGetUniqueId(char* out128) {
   return Guard(
       [&]() -> int {
@@ -394,6 +410,10 @@ int CONEXB200_GetIterationPhaseMilliseconds(void* prog, int iter, double* out5) 
 
 void CONEXB200_SetTiming(void* prog, int enabled) {
   static_cast<Program*>(prog)->timing_enabled = enabled != 0;
+}
+
+void CONEXB200_SetAssemblyMode(void* prog, int mode) {
+  static_cast<Program*>(prog)->ctx_.assembly_mode = mode;
 }
 
 void CONEXB200_GetPhaseSeconds(void* prog, double* out5) {

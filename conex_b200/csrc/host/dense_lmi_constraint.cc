@@ -20,6 +20,7 @@ struct DenseLMIConstraint::Storage {
   DeviceBuffer<double> small;    // alpha | beta | reductions
   DeviceBuffer<int> iwork;       // LU pivots + permutation, Lanczos count, LU info
   int panel = 0;
+  bool streamed = false;         // B holds one row panel only (cxb_schur_dense_lmi_streamed)
   // sharded blocks only
   DeviceBuffer<double> Hloc;     // (m_local+2) x (m_local+1) augmented Gram of the local diagonal block
   DeviceBuffer<double> recv[2];  // double-buffered chunks of a peer's constraint matrices
@@ -68,6 +69,20 @@ DenseLMIConstraint::DenseLMIConstraint(int n, int m_global, Sharded, DevicePoint
             "copy of LMI affine term");
 }
 
+DenseLMIConstraint::DenseLMIConstraint(int n, int m_global, Sharded, Uninitialized)
+    : n_(n), m_(m_global), workspace_(n), data_(std::make_shared<Storage>()) {
+  const Communicator& comm = Communicator::Get();
+  if (m_global < comm.world()) {
+    throw std::runtime_error("conex-b200: a sharded LMI block needs at least one matrix per rank");
+  }
+  row_begin_ = ShardBegin(m_global, comm.world(), comm.rank());
+  m_local_ = ShardBegin(m_global, comm.world(), comm.rank() + 1) - row_begin_;
+  sharded_ = comm.distributed();
+  data_->Aall.Resize(Sq(n) * (m_local_ + 1));
+}
+
+double* DenseLMIConstraint::mutable_device_matrices() { return data_->Aall.get(); }
+
 DenseLMIConstraint::DenseLMIConstraint(int n, int m, DevicePointers dev)
     : n_(n), m_(m), m_local_(m), workspace_(n), data_(std::make_shared<Storage>()) {
   data_->Aall.Resize(Sq(n) * (m + 1));
@@ -84,11 +99,24 @@ void DenseLMIConstraint::EnsureScratch() {
   Storage& d = *data_;
   if (d.panel != 0) return;
   const size_t nn = Sq(n_);
-  // Panel of constraint matrices scaled per pass: as many as fit in ~1 GiB of scratch.
-  const size_t budget = (size_t(1) << 27);  // doubles
-  d.panel = static_cast<int>(std::max<size_t>(1, std::min<size_t>(m_local_ + 1, budget / nn)));
+  // Keep every scaled matrix W A_i W (one GEMM for the whole Gram) when a second A-sized buffer fits
+  // next to ~4 GiB of other scratch; otherwise stream row panels through a bounded buffer.
+  const size_t full_bytes = sizeof(double) * nn * (m_local_ + 2);
+  size_t free_bytes = 0, total_bytes = 0;
+  CudaCheck(cudaMemGetInfo(&free_bytes, &total_bytes), "cudaMemGetInfo");
+  const size_t other = sizeof(double) * (4 * nn + (size_t(1) << 28)) + (size_t(2) << 30);
+  d.streamed = !sharded_ && (ctx_->assembly_mode == 2 ||
+                             (ctx_->assembly_mode == 0 && full_bytes + other > free_bytes));
+  if (sharded_ && full_bytes + other > free_bytes) {
+    throw std::runtime_error("conex-b200: the scaled matrices of this shard do not fit in HBM; use more ranks");
+  }
+  // Constraint matrices scaled per pass. Streamed: a multiple of the 64-row GEMM tile, <= 2 GiB.
+  const size_t budget = d.streamed ? (size_t(1) << 28) : (size_t(1) << 27);  // doubles
+  size_t panel = std::max<size_t>(1, std::min<size_t>(m_local_ + 1, budget / nn));
+  if (d.streamed && panel >= 64) panel -= panel % 64;
+  d.panel = static_cast<int>(panel);
   d.T.Resize(nn * d.panel);
-  d.B.Resize(nn * (m_local_ + 2));
+  d.B.Resize(d.streamed ? nn * (d.panel + 1) : nn * (m_local_ + 2));
   if (sharded_) {
     const long ldl = WorkspaceSchurComplement::AugLd(m_local_);
     d.Hloc.Resize(static_cast<size_t>(ldl) * (m_local_ + 1));
@@ -130,6 +158,10 @@ void ConstructSchurComplementSystem(DenseLMIConstraint* o, bool initialize,
   }
   if (o->sharded_) {
     o->AssembleSharded(sys);
+  } else if (d.streamed) {
+    DeviceCheck(cxb_schur_dense_lmi_streamed(s, o->n_, m, d.Aall.get(), o->workspace_.W.data, d.B.get(),
+                                             d.T.get(), d.panel, sys->G.data, sys->G.ld),
+                "cxb_schur_dense_lmi_streamed");
   } else
   DeviceCheck(cxb_schur_dense_lmi(s, o->n_, m, d.Aall.get(), o->workspace_.W.data, d.B.get(),
                                   d.T.get(), d.panel, sys->G.data, sys->G.ld),

@@ -52,6 +52,13 @@ class DenseLMIConstraint {
   // rank; only K1/K2 (assembly) and K6 (slack GEMV) are sharded — see DESIGN.md "Multi-GPU".
   struct Sharded {};
   DenseLMIConstraint(int n, int m_global, Sharded, DevicePointers dev);
+  // Same, but the block only allocates its storage (this rank's shard of A followed by C) and the
+  // caller fills it in place through mutable_device_matrices() before the first solve — no second
+  // copy of a 160 GB operator ever exists.
+  struct Uninitialized {};
+  DenseLMIConstraint(int n, int m_global, Sharded, Uninitialized);
+  double* mutable_device_matrices();  // local A_i blocks, then C
+  int local_matrices() const { return m_local_; }
 
   WorkspaceDensePSD* workspace() { return &workspace_; }
   int number_of_variables() const { return m_; }

@@ -112,6 +112,10 @@ class DeviceContext {
   DeviceContext(const DeviceContext&) = delete;
   DeviceContext& operator=(const DeviceContext&) = delete;
 
+  // How LMI blocks assemble their Schur complement: 0 = decide from free memory, 1 = keep all scaled
+  // matrices (fastest), 2 = stream row panels (A + two panels of scratch).
+  int assembly_mode = 0;
+
   void* stream() const { return reinterpret_cast<void*>(stream_); }
   cudaStream_t cuda_stream() const { return stream_; }
   void Synchronize() const { CudaCheck(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"); }

@@ -73,6 +73,17 @@ int CONEXB200_ShardPlan(int m, int world, int rank, int* out5, int capacity);
 int CONEXB200_AddDenseLMIConstraintShard(void* prog, const double* d_A_local, int n, int m,
                                          const double* d_C);
 
+/* Zero-copy variant for operators that only fit once: the library allocates this rank's storage
+ * (local_count = CONEXB200_ShardRange(m, world, rank) matrices, then C) and returns device pointers
+ * that the caller fills in place (column-major n x n blocks) before the first solve. With world == 1
+ * this is the whole block. Returns the constraint id, or -1. */
+int CONEXB200_NewDenseLMIConstraintStorage(void* prog, int n, int m, double** d_A_local, double** d_C);
+
+/* Schur assembly of LMI blocks of `prog`: 0 = decide from free HBM (default), 1 = keep all scaled
+ * matrices W A_i W (needs a second A-sized buffer; one Gram GEMM), 2 = stream row panels (A + 2 panels).
+ * Call before the first solve. Same H either way (different summation split). */
+void CONEXB200_SetAssemblyMode(void* prog, int mode);
+
 /* Host-logic probes that need no GPU: the closed-form mu rule (reference divergence.cc:96-111) and
  * the extreme eigenvalues of a Lanczos Jacobi matrix (alpha: n, beta: n-1; out2 = {min, max}). */
 double CONEXB200_DivergenceUpperBoundInverse(double bound, double frobenius_norm_squared,

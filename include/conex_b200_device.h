@@ -32,11 +32,13 @@ int cxb_dgemm(void* stream, int transA, int transB, int M, int N, int K, double 
 /* Same with explicit control, used by the tuning harness (tools/gemm_tune.py) and the Schur assembly:
  * config = tile configuration (-1: chosen from the shape), splits = split-K factor (0: automatic,
  * deterministic fixed-order reduction), mirror != 0 (needs lower_only, M == N) also stores
- * C[col,row] so that the result is exactly symmetric. */
+ * C[col,row] so that the result is exactly symmetric; diag_off shifts the lower_only test to
+ * row + diag_off >= col (a row panel starting diag_off rows below the top of a lower-triangular
+ * result). */
 int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, int M, int N, int K,
                  double alpha, const double* dA, long lda, long strideA, const double* dB, long ldb,
                  long strideB, double beta, double* dC, long ldc, long strideC, int batch,
-                 int lower_only, int mirror);
+                 int lower_only, int mirror, int diag_off);
 /* Tile configuration used for large shapes when config < 0 (process-wide; tuning only). */
 void cxb_set_default_gemm_config(int config);
 
@@ -51,6 +53,11 @@ void cxb_set_default_gemm_config(int config);
  */
 int cxb_schur_dense_lmi(void* stream, int n, int m, const double* dAall, const double* dW,
                         double* dB, double* dT, int panel, double* dHaug, long ldh);
+
+/* Same result with bounded scratch: dBp holds (panel + 1) * n * n doubles (one row panel of scaled
+ * matrices, contracted immediately), dT panel * n * n. Used when a second A-sized buffer does not fit. */
+int cxb_schur_dense_lmi_streamed(void* stream, int n, int m, const double* dAall, const double* dW,
+                                 double* dBp, double* dT, int panel, double* dHaug, long ldh);
 
 /* ---- K3: blocked right-looking Cholesky, lower, in place (block_triangular_operations.cc:184-219,
  * Eigen::LLT). d_info (device int) is set to 0 on success or to (1 + index of the first

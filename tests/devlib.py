@@ -28,10 +28,13 @@ def product():
                                 C.c_int, C.c_int]
         L.cxb_dgemm_ex.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, vp, C.c_long, C.c_long, vp, C.c_long, C.c_long, C.c_double,
-                                   vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int]
+                                   vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int]
         L.cxb_set_default_gemm_config.argtypes = [C.c_int]
         L.cxb_set_default_gemm_config.restype = None
         L.cxb_schur_dense_lmi.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_long]
+        L.cxb_schur_dense_lmi_streamed.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_long]
+        L.CONEXB200_SetAssemblyMode.argtypes = [vp, C.c_int]
+        L.CONEXB200_SetAssemblyMode.restype = None
         L.cxb_potrf_lower.argtypes = [vp, C.c_int, vp, C.c_long, vp, vp]
         L.cxb_potrs_lower.argtypes = [vp, C.c_int, vp, C.c_long, vp, C.c_long, C.c_int]
         L.cxb_gemv_n.argtypes = [vp, C.c_long, C.c_int, vp, vp, vp]
@@ -55,6 +58,7 @@ def product():
         L.cxb_affine_update.argtypes = [vp, C.c_int, vp, vp, C.c_double]
         L.CONEXB200_AddDenseLMIConstraintDevice.argtypes = [vp, vp, C.c_int, C.c_int, vp]
         L.CONEXB200_AddDenseLMIConstraintShard.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        L.CONEXB200_NewDenseLMIConstraintStorage.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]
         L.CONEXB200_CommGetUniqueId.argtypes = [C.c_char_p]
         L.CONEXB200_CommInitRank.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.CONEXB200_CommDestroy.restype = None

@@ -83,7 +83,7 @@ def test_dgemm_every_tile_configuration(dev, config, ta, tb):
         C0 = rng.standard_normal((M, N))
         dA, dB, dC = dev.to_dev(A), dev.to_dev(B), dev.to_dev(C0)
         rc = L.cxb_dgemm_ex(None, config, splits, ta, tb, M, N, K, 0.5, dev.ptr(dA), A.shape[0], 0,
-                            dev.ptr(dB), B.shape[0], 0, -1.0, dev.ptr(dC), M, 0, 1, lower, 0)
+                            dev.ptr(dB), B.shape[0], 0, -1.0, dev.ptr(dC), M, 0, 1, lower, 0, 0)
         assert rc == 0
         ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - C0
         got = dev.from_dev(dC)
@@ -102,13 +102,27 @@ def test_dgemm_every_tile_configuration(dev, config, ta, tb):
     dT = torch.stack([dev.to_dev(x) for x in Winv_T]).contiguous()
     dC = dev.dzeros(batch, n, n)
     rc = L.cxb_dgemm_ex(None, config, 1, 0, 0, n, n, n, 1.0, dev.ptr(dW), n, 0, dev.ptr(dT), n, n * n, 0.0,
-                        dev.ptr(dC), n, n * n, batch, 1, 1)
+                        dev.ptr(dC), n, n * n, batch, 1, 1, 0)
     assert rc == 0
     torch.cuda.synchronize()
     out = dC.cpu().numpy()
     for i in range(batch):
         assert np.array_equal(out[i], out[i].T)
         assert rel_err(np.tril(out[i].T), np.tril(W @ Winv_T[i])) < 1e-12
+    # row panel of a lower-triangular result: keep row + off >= col
+    M, N, K, off = 130, 300, 257, 70
+    A = rng.standard_normal((K, M))
+    B = rng.standard_normal((K, N))
+    C0 = rng.standard_normal((M, N))
+    dA, dB, dC = dev.to_dev(A), dev.to_dev(B), dev.to_dev(C0)
+    for splits in (1, 3):
+        dC = dev.to_dev(C0)
+        assert L.cxb_dgemm_ex(None, config, splits, 1, 0, M, N, K, 1.0, dev.ptr(dA), K, 0, dev.ptr(dB), K, 0,
+                              0.0, dev.ptr(dC), M, 0, 1, 1, 0, off) == 0
+        got = dev.from_dev(dC)
+        mask = (np.arange(M)[:, None] + off) >= np.arange(N)[None, :]
+        assert rel_err(got[mask], (A.T @ B)[mask]) < 1e-13
+        assert np.array_equal(got[~mask], C0[~mask])
     # split-K is deterministic: two runs give identical bits
     M = N = 260
     K = 4096
@@ -119,7 +133,7 @@ def test_dgemm_every_tile_configuration(dev, config, ta, tb):
     for _ in range(2):
         dC = dev.dzeros(N, M)
         assert L.cxb_dgemm_ex(None, config, 4, 1, 0, M, N, K, 1.0, dev.ptr(dA), K, 0, dev.ptr(dB), K, 0, 0.0,
-                              dev.ptr(dC), M, 0, 1, 1, 0) == 0
+                              dev.ptr(dC), M, 0, 1, 1, 0, 0) == 0
         outs.append(dev.from_dev(dC))
     assert np.array_equal(outs[0], outs[1])
 
@@ -170,6 +184,21 @@ def test_schur_dense_lmi_matches_oracle(dev, n, m, seed):
         H = np.tril(Haug[:m, :m])
         scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
         assert (np.abs(H - np.tril(G)) / scale).max() < 1e-10
+        assert rel_err(Haug[m, :m], AQc) < 1e-10
+        assert rel_err(Haug[m + 1, :m], AW) < 1e-10
+        assert abs(Haug[m + 1, m] - sc[0]) <= 1e-10 * abs(sc[0])
+        assert abs(Haug[m, m] - sc[1]) <= 1e-10 * abs(sc[1])
+    # streamed variant: one row panel of scaled matrices at a time, same Newton system
+    for panel in (1, 4, m + 1):
+        dT = dev.dzeros(panel * n * n)
+        dBp = dev.dzeros((panel + 1) * n * n)
+        ldh = (m + 3) & ~1
+        dH = dev.dzeros(ldh * (m + 2))
+        assert L.cxb_schur_dense_lmi_streamed(None, n, m, dev.ptr(dA), dev.ptr(dW), dev.ptr(dBp), dev.ptr(dT),
+                                              panel, dev.ptr(dH), ldh) == 0
+        Haug = dev.from_dev(dH, ldh, m + 2)
+        scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
+        assert (np.abs(np.tril(Haug[:m, :m]) - np.tril(G)) / scale).max() < 1e-10
         assert rel_err(Haug[m, :m], AQc) < 1e-10
         assert rel_err(Haug[m + 1, :m], AW) < 1e-10
         assert abs(Haug[m + 1, m] - sc[0]) <= 1e-10 * abs(sc[0])

@@ -199,6 +199,32 @@ def test_warmstart_agrees_with_full_solve(libs):
     assert np.linalg.norm(y - yw) < 1e-12
 
 
+def test_streamed_assembly_gives_the_same_solve(libs):
+    """Row-panel streaming of the scaled matrices (the mode that fits config 5 on one GPU) against
+    the keep-everything mode and the oracle."""
+    ora, dev = libs
+    mats, Cm = random_dense_lmi(20, 150, 9)   # m + 1 > 64: several row panels
+    out = []
+    for mode in (1, 2):
+        P = dev.program()
+        dev.lib.CONEXB200_SetAssemblyMode(P.h, mode)
+        P.add_dense_lmi(mats, Cm)
+        H, AW, AQc, sc = P.newton_system(coldstart=True)
+        b = P.feasible_objective()
+        solved, y = P.maximize(b, dev.default_config())
+        out.append((H, AW, AQc, y, solved, P.iteration_log()))
+    (H1, AW1, AQc1, y1, s1, l1), (H2, AW2, AQc2, y2, s2, l2) = out
+    scale = np.sqrt(np.outer(np.diag(H1), np.diag(H1)))
+    assert (np.abs(H1 - H2) / scale).max() < 1e-12
+    assert np.allclose(AW1, AW2, rtol=1e-12) and np.allclose(AQc1, AQc2, rtol=1e-12)
+    assert s1 == s2 == 1 and len(l1) == len(l2)
+    assert np.abs(y1 - y2).max() <= 1e-8 * max(1.0, np.abs(y1).max())
+    Po = ora.program()
+    Po.add_dense_lmi(mats, Cm)
+    so, yo = Po.maximize(Po.feasible_objective(), ora.default_config())
+    assert so == 1 and np.abs(yo - y2).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+
+
 def test_maxcut_small(libs):
     """BASELINE config 2 shape at n = 60 (dense path): dual variable has unit diagonal."""
     mats, Cm, b = maxcut_lmi(60, 2)

@@ -37,7 +37,7 @@ def stream():
 
 def gemm(cfg, splits, ta, tb, M, N, K, A, lda, sA, B, ldb, sB, Cm, ldc, sC, batch, lower, mirror, beta=0.0):
     rc = L.cxb_dgemm_ex(stream(), cfg, splits, ta, tb, M, N, K, 1.0, vp(A.data_ptr()), lda, sA,
-                        vp(B.data_ptr()), ldb, sB, beta, vp(Cm.data_ptr()), ldc, sC, batch, lower, mirror)
+                        vp(B.data_ptr()), ldb, sB, beta, vp(Cm.data_ptr()), ldc, sC, batch, lower, mirror, 0)
     assert rc == 0, rc
 
 

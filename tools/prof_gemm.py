@@ -21,5 +21,5 @@ Cm = torch.empty(n, n, **f64)
 for _ in range(2):
     torch.matmul(A, B, out=Cm)
     L.cxb_dgemm_ex(vp(torch.cuda.current_stream().cuda_stream), cfg, 1, 0, 0, n, n, n, 1.0, vp(A.data_ptr()), n,
-                   0, vp(B.data_ptr()), n, 0, 0.0, vp(Cm.data_ptr()), n, 0, 1, 0, 0)
+                   0, vp(B.data_ptr()), n, 0, 0.0, vp(Cm.data_ptr()), n, 0, 1, 0, 0, 0)
 torch.cuda.synchronize()
