@@ -1,194 +1,398 @@
 // K3 / K5: blocked right-looking Cholesky of the dense Schur complement and the triangular solves.
 //
 // Replaces BlockCholeskyInPlace / ApplyBlockInverse(OfTranspose)InPlace
-// (block_triangular_operations.cc:114-219) for one dense supernode. Structure per NB-wide panel:
-//   1. PotrfDiagKernel   — one CTA factors the NB x NB diagonal block in shared memory
-//                          (warp-shuffle free: column scale + rank-1 update per step);
-//   2. TrsmPanelKernel   — CTAs of 32 rows solve X L11^T = A21 by true substitution in shared
-//                          memory (backward stable; H can be very ill conditioned late in the IPM,
-//                          so no explicit inverses are used);
-//   3. DMMA SYRK update  — A22 -= L21 L21^T on the lower tiles only (gemm.cu, tensor cores).
+// (block_triangular_operations.cc:114-219) for one dense supernode.
+//
+// Factorisation, two levels of blocking:
+//   outer block column of kOuter = 512 columns:
+//     for each inner block of kNB = 128 columns inside it
+//       1. PotrfDiagKernel  — one CTA factors the 128 x 128 diagonal block in shared memory
+//                             (column scale + rank-1 update per step, fixed thread->(row, column
+//                             group) map, no integer division in the loop);
+//       2. TrsmPanelKernel  — X L11^T = A21 by true substitution (no explicit inverses: H becomes
+//                             very ill conditioned late in the IPM). One thread per row keeps 32
+//                             accumulators in registers; L11 is streamed through shared memory in
+//                             32-column slabs and read as 16-byte broadcasts;
+//       3. DMMA update of the rest of the outer block column (lower trapezoid, K = 128);
+//     DMMA SYRK of everything to the right with K = 512 (gemm.cu) — where the flops are.
 // A non-positive pivot sets *info = 1 + column (Eigen::LLT::info() != Success in the reference).
+//
+// Solves: one launch per 128-column block and direction. Every CTA redundantly solves the small
+// diagonal system (4 x (32 x 32 warp-shuffle substitution + block update) in shared memory) and then
+// applies the block's update to its own rows, so no second launch or inter-CTA flag is needed.
+// All global->shared staging keeps 8 loads in flight per thread (latency, not bandwidth, is the
+// limit of these small kernels).
 #include "common.cuh"
 #include "device_api.h"
 
 namespace cxb {
 namespace {
 
-constexpr int kNB = 128;      // panel width
-constexpr int kTrsmRows = 32;  // rows per TRSM CTA
+constexpr int kNB = 128;     // inner block
+constexpr int kOuter = 512;  // outer block column (K of the big SYRK)
+constexpr int kMaxRhs = 4;
 
-// Factor the nb x nb block at H (ld) in place; lower triangle. One CTA, blockDim = 1024.
-__global__ void __launch_bounds__(1024) PotrfDiagKernel(int nb, double* H, long ld, int col0,
-                                                        int* info) {
-  extern __shared__ double s[];  // nb x (nb+1), column-major with pitch nb+1
-  const int P = nb + 1;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (*info != 0) return;  // an earlier panel already failed
-  for (int e = tid; e < nb * nb; e += nt) {
-    const int r = e % nb, c = e / nb;
-    if (r >= c) s[c * P + r] = H[(long)c * ld + r];
+// Global -> shared staging with U loads in flight per thread (a plain load/store loop exposes the
+// full memory latency once per element).
+template <int U, typename LoadF, typename StoreF>
+__device__ __forceinline__ void BatchedCopy(int total, int tid, int nthreads, LoadF load, StoreF store) {
+  for (int base = tid; base < total; base += nthreads * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e = base + u * nthreads;
+      v[u] = (e < total) ? load(e) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e = base + u * nthreads;
+      if (e < total) store(e, v[u]);
+    }
   }
-  __syncthreads();
+}
+
+// ---- 1. diagonal block ---------------------------------------------------------------------------
+// Factor the nb x nb (nb <= 128) block at H (ld) in place; lower triangle. One CTA of 512 threads.
+// Thread t owns row r = t % 128 and the columns c with c % 4 == t / 128.
+__global__ void __launch_bounds__(512) PotrfDiagKernel(int nb, double* H, long ld, int col0,
+                                                       int* info) {
+  extern __shared__ double s[];  // s[c * P + r], P = 129
+  constexpr int P = kNB + 1;
   __shared__ int failed;
+  const int tid = threadIdx.x;
+  const int r = tid & (kNB - 1);
+  const int cg = tid >> 7;  // 0..3
+  if (*info != 0) return;   // an earlier block already failed
   if (tid == 0) failed = 0;
+  BatchedCopy<8>(
+      kNB * kNB, tid, 512,
+      [&](int e) {
+        const int rr = e & (kNB - 1), c = e >> 7;
+        return (rr < nb && c <= rr) ? H[(long)c * ld + rr] : 0.0;
+      },
+      [&](int e, double v) { s[(e >> 7) * P + (e & (kNB - 1))] = v; });
   __syncthreads();
   for (int j = 0; j < nb; j++) {
     const double d = s[j * P + j];
-    if (!(d > 0.0)) {
+    if (!(d > 0.0)) {  // every thread sees the same d: uniform branch
       if (tid == 0) {
         failed = 1;
         *info = col0 + j + 1;
       }
+      break;
     }
-    __syncthreads();
-    if (failed) break;
     const double rd = sqrt(d);
     const double inv = 1.0 / rd;
-    // scale column j
-    for (int r = j + tid; r < nb; r += nt) {
-      s[j * P + r] = (r == j) ? rd : s[j * P + r] * inv;
+    // l[r] for this thread's row (pre-scale value is still in s[j][r] until the barrier below)
+    const double lr = (r > j && r < nb) ? s[j * P + r] * inv : 0.0;
+    // trailing update of my row: s[c][r] -= l[r] * l[c] for j < c <= r, c in my column group
+    if (r > j && r < nb) {
+      int c = j + 1 + ((cg - (j + 1)) & 3);  // first c > j with c % 4 == cg
+      for (; c <= r; c += 4) s[c * P + r] -= lr * (s[j * P + c] * inv);
     }
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle: s[r][c] -= l[r] * l[c], c > j, r >= c
-    const int rem = nb - j - 1;
-    const int total = rem * rem;
-    for (int e = tid; e < total; e += nt) {
-      const int r = j + 1 + e % rem, c = j + 1 + e / rem;
-      if (r >= c) s[c * P + r] -= s[j * P + r] * s[j * P + c];
+    __syncthreads();  // all reads of the unscaled column j are done
+    if (cg == 0 && r < nb) {
+      if (r == j) s[j * P + j] = rd;
+      if (r > j) s[j * P + r] = lr;
     }
     __syncthreads();
   }
-  for (int e = tid; e < nb * nb; e += nt) {
-    const int r = e % nb, c = e / nb;
-    if (r >= c) H[(long)c * ld + r] = s[c * P + r];
+  __syncthreads();
+  if (failed) return;
+  if (r < nb) {
+    for (int c = cg; c <= r; c += 4) H[(long)c * ld + r] = s[c * P + r];
   }
 }
 
-// Solves X * L11^T = A21 for a strip of kTrsmRows rows. L11: nb x nb lower (ld), A21 strip at
-// A + row0 (ld), overwritten by X. blockDim = 256.
-__global__ void __launch_bounds__(256) TrsmPanelKernel(int nb, const double* __restrict__ L11,
-                                                       long ld, double* A21, int rows,
-                                                       const int* info) {
-  extern __shared__ double s[];
+// ---- 2. panel solve ---------------------------------------------------------------------------------
+// Solves X * L11^T = A21 for kNB-row strips: one thread per row. L11: nb x nb lower (ld), nb <= 128.
+// A21 (ld) is overwritten by X. Shared memory: sx[i][row] (the row's solved entries) and one slab of
+// L11 rows, sl[i][c'] = L11[c0 + c'][i] for the 32 columns c0.. of the current phase.
+__global__ void __launch_bounds__(kNB) TrsmPanelKernel(int nb, const double* __restrict__ L11, long ld,
+                                                      double* A21, int rows, const int* info) {
+  extern __shared__ __align__(16) double sm[];
   if (*info != 0) return;
-  const int PL = nb + 1;
-  double* sl = s;                 // nb x nb lower, sl[c*PL + r] = L11[r][c]
-  double* sx = s + nb * PL;       // strip: sx[c*(kTrsmRows+1) + r]
-  constexpr int PX = kTrsmRows + 1;
-  const int tid = threadIdx.x;
-  const int row0 = blockIdx.x * kTrsmRows;
-  const int nrows = min(kTrsmRows, rows - row0);
-  for (int e = tid; e < nb * nb; e += 256) {
-    const int r = e % nb, c = e / nb;
-    sl[c * PL + r] = (r >= c) ? L11[(long)c * ld + r] : 0.0;
-  }
-  for (int e = tid; e < nb * kTrsmRows; e += 256) {
-    const int r = e % kTrsmRows, c = e / kTrsmRows;
-    sx[c * PX + r] = (r < nrows) ? A21[(long)c * ld + row0 + r] : 0.0;
-  }
-  __syncthreads();
-  const int r = tid % kTrsmRows;  // my row
-  const int q = tid / kTrsmRows;  // column phase 0..7
-  for (int j = 0; j < nb; j++) {
-    // x[:, j] = a[:, j] / L[j][j]
-    if (q == 0) sx[j * PX + r] /= sl[j * PL + j];
+  double* sx = sm;                 // [kNB][kNB]: sx[i * kNB + t]
+  double* sl = sm + kNB * kNB;     // [kNB][32]:  sl[i * 32 + c']
+  double* srd = sl + kNB * 32;     // [32] reciprocal diagonal of the current slab
+  const int t = threadIdx.x;
+  const int row = blockIdx.x * kNB + t;
+  const bool active = row < rows;
+  for (int c0 = 0; c0 < nb; c0 += 32) {
+    const int cw = min(32, nb - c0);
     __syncthreads();
-    const double xj = sx[j * PX + r];
-    // a[:, c] -= x[:, j] * L[c][j] for c > j; columns dealt round-robin over the 8 phases
-    for (int c = j + 1 + q; c < nb; c += 8) sx[c * PX + r] -= xj * sl[j * PL + c];
+    // slab: columns i < c0 + cw of rows c0 .. c0 + cw - 1 of L11 (zero beyond the diagonal)
+    BatchedCopy<8>(
+        (c0 + 32) * 32, t, kNB,
+        [&](int e) {
+          const int cp = e & 31, i = e >> 5;
+          const int c = c0 + cp;
+          return (cp < cw && i <= c) ? L11[(long)i * ld + c] : 0.0;
+        },
+        [&](int e, double v) { sl[e] = v; });
+    if (t < 32) srd[t] = (t < cw) ? 1.0 / L11[(long)(c0 + t) * ld + c0 + t] : 0.0;
+    double acc[32];
+#pragma unroll
+    for (int cp = 0; cp < 32; cp++) {
+      acc[cp] = (active && cp < cw) ? A21[(long)(c0 + cp) * ld + row] : 0.0;
+    }
     __syncthreads();
-  }
-  for (int e = tid; e < nb * kTrsmRows; e += 256) {
-    const int rr = e % kTrsmRows, c = e / kTrsmRows;
-    if (rr < nrows) A21[(long)c * ld + row0 + rr] = sx[c * PX + rr];
+    // acc[c'] -= sum_{i < c0} x_i L11[c0 + c'][i]
+    for (int i = 0; i < c0; i++) {
+      const double xi = sx[i * kNB + t];
+      const double2* lrow = reinterpret_cast<const double2*>(sl + i * 32);
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const double2 l = lrow[q];
+        acc[2 * q] -= xi * l.x;
+        acc[2 * q + 1] -= xi * l.y;
+      }
+    }
+    // 32 x 32 diagonal block by substitution in registers
+#pragma unroll
+    for (int cp = 0; cp < 32; cp++) {
+      const double x = acc[cp] * srd[cp];
+      acc[cp] = x;
+      const double* lrow = sl + (c0 + cp) * 32;  // L11[c0 + c''][c0 + cp] for c'' > cp
+#pragma unroll
+      for (int cq = cp + 1; cq < 32; cq++) acc[cq] -= x * lrow[cq];
+    }
+#pragma unroll
+    for (int cp = 0; cp < 32; cp++) {
+      sx[(c0 + cp) * kNB + t] = acc[cp];
+      if (active && cp < cw) A21[(long)(c0 + cp) * ld + row] = acc[cp];
+    }
   }
 }
 
-// ---- triangular solves -----------------------------------------------------------------------
-// Forward: solve L_kk x_k = b_k for one diagonal block and all right-hand sides. One CTA.
-template <bool TRANS>
-__global__ void __launch_bounds__(256) TrsvDiagKernel(int nb, const double* __restrict__ L, long ld,
-                                                      double* X, long ldx, int nrhs) {
+// ---- triangular solves -------------------------------------------------------------------------------
+// Loads the nb x nb lower block L (ld) into shared memory, sl[c * P + r] = L[r][c], and the
+// reciprocals of its diagonal into srd.
+template <int P>
+__device__ __forceinline__ void LoadLowerBlock(double* sl, double* srd, const double* __restrict__ L,
+                                               long ld, int nb) {
+  BatchedCopy<8>(
+      kNB * kNB, threadIdx.x, blockDim.x,
+      [&](int e) {
+        const int r = e & (kNB - 1), c = e >> 7;
+        return (r < nb && c <= r) ? L[(long)c * ld + r] : 0.0;
+      },
+      [&](int e, double v) { sl[(e >> 7) * P + (e & (kNB - 1))] = v; });
+  if (threadIdx.x < kNB) {
+    srd[threadIdx.x] = (threadIdx.x < nb) ? 1.0 / L[(long)threadIdx.x * ld + threadIdx.x] : 0.0;
+  }
+}
+
+// Forward: x_k = L_kk^{-1} b_k (in shared memory sx[k * kNB + r]), all right-hand sides. 256 threads.
+template <int P>
+__device__ __forceinline__ void SolveLowerBlock(const double* sl, const double* srd, double* sx, int nb,
+                                                int nrhs) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int b0 = 0; b0 < nb; b0 += 32) {
+    const int bw = min(32, nb - b0);
+    if (warp < nrhs) {  // one warp per right-hand side solves the 32 x 32 diagonal sub-block
+      double v = (lane < bw) ? sx[warp * kNB + b0 + lane] : 0.0;
+      for (int j = 0; j < bw; j++) {
+        const double xj = __shfl_sync(0xffffffffu, v, j) * srd[b0 + j];
+        if (lane == j) v = xj;
+        if (lane > j && lane < bw) v -= sl[(b0 + j) * P + b0 + lane] * xj;
+      }
+      if (lane < bw) sx[warp * kNB + b0 + lane] = v;
+    }
+    __syncthreads();
+    // rows below the sub-block: b[r] -= sum_j L[r][b0 + j] x_j
+    for (int e = tid; e < (nb - b0 - bw) * nrhs; e += blockDim.x) {
+      const int r = b0 + bw + e % (nb - b0 - bw), k = e / (nb - b0 - bw);
+      double a = 0;
+      for (int j = 0; j < bw; j++) a += sl[(b0 + j) * P + r] * sx[k * kNB + b0 + j];
+      sx[k * kNB + r] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+// Backward: x_k = L_kk^{-T} z_k.
+template <int P>
+__device__ __forceinline__ void SolveLowerTransposedBlock(const double* sl, const double* srd, double* sx,
+                                                          int nb, int nrhs) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (nb + 31) / 32;
+  for (int bi = nblk - 1; bi >= 0; bi--) {
+    const int b0 = bi * 32;
+    const int bw = min(32, nb - b0);
+    if (warp < nrhs) {
+      double v = (lane < bw) ? sx[warp * kNB + b0 + lane] : 0.0;
+      for (int j = bw - 1; j >= 0; j--) {
+        const double xj = __shfl_sync(0xffffffffu, v, j) * srd[b0 + j];
+        if (lane == j) v = xj;
+        // x[r] -= L[j][r] x_j for r < j  (L^T[r][j] = L[j][r] = sl[r * P + j])
+        if (lane < j) v -= sl[(b0 + lane) * P + b0 + j] * xj;
+      }
+      if (lane < bw) sx[warp * kNB + b0 + lane] = v;
+    }
+    __syncthreads();
+    // rows above the sub-block: z[r] -= sum_j L[b0 + j][r] x_j, r < b0
+    for (int e = tid; e < b0 * nrhs; e += blockDim.x) {
+      const int r = e % b0, k = e / b0;
+      double a = 0;
+      for (int j = 0; j < bw; j++) a += sl[r * P + b0 + j] * sx[k * kNB + b0 + j];
+      sx[k * kNB + r] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int kFwdRows = 64;  // rows per CTA in the forward update (4 column groups of 32 each)
+
+// One forward step: every CTA solves block k (redundantly) from the working vector X, CTA 0 stores
+// the solved block into Out (a different array: other CTAs may still be reading the unsolved block
+// from X), then each CTA updates its 64 rows below: x[r] -= L[r, kblock] x_k. Thread (r, g) sums
+// the 32 columns of group g with all loads in flight; the 4 partials are added in a fixed order.
+__global__ void __launch_bounds__(256) TrsvFwdStepKernel(int m, int j0, int nb,
+                                                         const double* __restrict__ L, long ld,
+                                                         double* X, long ldx, double* Out, long ldo,
+                                                         int nrhs) {
+  constexpr int P = kNB + 1;
   extern __shared__ double s[];
-  const int PL = nb + 1;
   double* sl = s;
-  double* sx = s + nb * PL;  // nb x nrhs
+  double* sx = s + kNB * P;           // kMaxRhs x kNB
+  double* srd = sx + kMaxRhs * kNB;   // kNB
+  double* sp = srd + kNB;             // partial sums: kMaxRhs x 4 x kFwdRows
   const int tid = threadIdx.x;
-  for (int e = tid; e < nb * nb; e += 256) {
-    const int r = e % nb, c = e / nb;
-    if (r >= c) sl[c * PL + r] = L[(long)c * ld + r];
+  LoadLowerBlock<P>(sl, srd, L + (long)j0 * ld + j0, ld, nb);
+  for (int e = tid; e < kNB * nrhs; e += 256) {
+    const int r = e & (kNB - 1), k = e >> 7;
+    sx[k * kNB + r] = (r < nb) ? X[(long)k * ldx + j0 + r] : 0.0;
   }
-  for (int e = tid; e < nb * nrhs; e += 256) sx[e] = X[(long)(e / nb) * ldx + e % nb];
   __syncthreads();
-  if (!TRANS) {
-    for (int j = 0; j < nb; j++) {
-      if (tid < nrhs) sx[tid * nb + j] /= sl[j * PL + j];
-      __syncthreads();
-      for (int e = tid; e < (nb - j - 1) * nrhs; e += 256) {
-        const int r = j + 1 + e % (nb - j - 1), k = e / (nb - j - 1);
-        sx[k * nb + r] -= sl[j * PL + r] * sx[k * nb + j];
+  SolveLowerBlock<P>(sl, srd, sx, nb, nrhs);
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < nb * nrhs; e += 256) Out[(long)(e / nb) * ldo + j0 + e % nb] = sx[(e / nb) * kNB + e % nb];
+  }
+  const int rl = tid & (kFwdRows - 1), g = tid >> 6;
+  const int r = j0 + nb + blockIdx.x * kFwdRows + rl;
+  double acc[kMaxRhs] = {0, 0, 0, 0};
+  if (r < m) {
+    const double* Lr = L + (long)(j0 + g * 32) * ld + r;
+    double l[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) l[c] = (g * 32 + c < nb) ? Lr[(long)c * ld] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+#pragma unroll
+      for (int k = 0; k < kMaxRhs; k++) {
+        if (k < nrhs) acc[k] += l[c] * sx[k * kNB + g * 32 + c];
       }
-      __syncthreads();
-    }
-  } else {
-    for (int j = nb - 1; j >= 0; j--) {
-      if (tid < nrhs) sx[tid * nb + j] /= sl[j * PL + j];
-      __syncthreads();
-      // x[r] -= L[j][r] * x[j] for r < j   (L^T[r][j] = L[j][r])
-      for (int e = tid; e < j * nrhs; e += 256) {
-        const int r = e % j, k = e / j;
-        sx[k * nb + r] -= sl[r * PL + j] * sx[k * nb + j];
-      }
-      __syncthreads();
     }
   }
-  for (int e = tid; e < nb * nrhs; e += 256) X[(long)(e / nb) * ldx + e % nb] = sx[e];
+#pragma unroll
+  for (int k = 0; k < kMaxRhs; k++) {
+    if (k < nrhs) sp[(k * 4 + g) * kFwdRows + rl] = acc[k];
+  }
+  __syncthreads();
+  if (g == 0 && r < m) {
+#pragma unroll
+    for (int k = 0; k < kMaxRhs; k++) {
+      if (k < nrhs) {
+        const double t = ((sp[(k * 4 + 0) * kFwdRows + rl] + sp[(k * 4 + 1) * kFwdRows + rl]) +
+                          sp[(k * 4 + 2) * kFwdRows + rl]) + sp[(k * 4 + 3) * kFwdRows + rl];
+        X[(long)k * ldx + r] -= t;
+      }
+    }
+  }
 }
 
-// Forward update: x[rows below] -= L[rows, kblock] * x_k. One thread per row; coalesced over rows.
-__global__ void __launch_bounds__(256) TrsvUpdateFwdKernel(int rows, int nb,
-                                                           const double* __restrict__ Lblk, long ld,
-                                                           const double* __restrict__ xk,
-                                                           double* xrest, long ldx, int nrhs) {
-  __shared__ double sx[4 * kNB];
-  for (int e = threadIdx.x; e < nb * nrhs; e += 256) sx[e] = xk[(long)(e / nb) * ldx + e % nb];
-  __syncthreads();
-  const int r = blockIdx.x * 256 + threadIdx.x;
-  if (r >= rows) return;
-  double acc[4] = {0, 0, 0, 0};
-  for (int c = 0; c < nb; c++) {
-    const double l = Lblk[(long)c * ld + r];
-    for (int k = 0; k < nrhs; k++) acc[k] += l * sx[k * nb + c];
+// One backward step: every CTA solves block k with L_kk^T from the working vector X, CTA 0 stores
+// x_k into Out, then each CTA updates its 32 entries c < j0 (one warp per 4 columns of L, all four
+// columns' loads in flight): x[c] -= L[kblock rows, c]^T x_k.
+__global__ void __launch_bounds__(256) TrsvBwdStepKernel(int j0, int nb, const double* __restrict__ L,
+                                                         long ld, double* X, long ldx, double* Out,
+                                                         long ldo, int nrhs) {
+  constexpr int P = kNB + 1;
+  extern __shared__ double s[];
+  double* sl = s;
+  double* sx = s + kNB * P;
+  double* srd = sx + kMaxRhs * kNB;
+  const int tid = threadIdx.x, lane = tid & 31;
+  LoadLowerBlock<P>(sl, srd, L + (long)j0 * ld + j0, ld, nb);
+  for (int e = tid; e < kNB * nrhs; e += 256) {
+    const int r = e & (kNB - 1), k = e >> 7;
+    sx[k * kNB + r] = (r < nb) ? X[(long)k * ldx + j0 + r] : 0.0;
   }
-  for (int k = 0; k < nrhs; k++) xrest[(long)k * ldx + r] -= acc[k];
-}
-
-// Backward update: x[0:cols] -= L[kblock rows, 0:cols]^T * x_k. One warp per column.
-__global__ void __launch_bounds__(256) TrsvUpdateBwdKernel(int cols, int nb,
-                                                           const double* __restrict__ Lrow, long ld,
-                                                           const double* __restrict__ xk, double* x,
-                                                           long ldx, int nrhs) {
-  __shared__ double sx[4 * kNB];
-  for (int e = threadIdx.x; e < nb * nrhs; e += 256) sx[e] = xk[(long)(e / nb) * ldx + e % nb];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= cols) return;
-  double acc[4] = {0, 0, 0, 0};
-  for (int r = lane; r < nb; r += 32) {
-    const double l = Lrow[(long)c * ld + r];
-    for (int k = 0; k < nrhs; k++) acc[k] += l * sx[k * nb + r];
+  SolveLowerTransposedBlock<P>(sl, srd, sx, nb, nrhs);
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < nb * nrhs; e += 256) Out[(long)(e / nb) * ldo + j0 + e % nb] = sx[(e / nb) * kNB + e % nb];
   }
-  for (int k = 0; k < nrhs; k++) {
-    const double v = WarpSum(acc[k]);
-    if (lane == 0) x[(long)k * ldx + c] -= v;
+  const int cbase = (blockIdx.x * 8 + (tid >> 5)) * 4;
+  double l[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int c = cbase + q;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = lane + 32 * i;
+      l[q][i] = (c < j0 && r < nb) ? L[(long)c * ld + j0 + r] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int c = cbase + q;
+#pragma unroll
+    for (int k = 0; k < kMaxRhs; k++) {
+      if (k < nrhs) {
+        double a = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) a += l[q][i] * sx[k * kNB + lane + 32 * i];
+        const double v = WarpSum(a);
+        if (lane == 0 && c < j0) X[(long)k * ldx + c] -= v;
+      }
+    }
   }
 }
 
 __global__ void ResetInfoKernel(int* info) { *info = 0; }
 
+constexpr size_t kDiagSmem = sizeof(double) * kNB * (kNB + 1);
+constexpr size_t kTrsmSmem = sizeof(double) * (kNB * kNB + kNB * 32 + 32);
+constexpr size_t kTrsvSmem =
+    sizeof(double) * (kNB * (kNB + 1) + kMaxRhs * kNB + kNB + kMaxRhs * 4 * kFwdRows);
+
+void ConfigureOnce() {
+  static bool configured = false;
+  if (configured) return;
+  cudaFuncSetAttribute(PotrfDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
+  cudaFuncSetAttribute(TrsmPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
+  cudaFuncSetAttribute(TrsvFwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
+  cudaFuncSetAttribute(TrsvBwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
+  configured = true;
+}
+
 }  // namespace
+
+// Factors the block column [j0, j0 + w) x rows [j0, m) of H in place (w <= kOuter): inner
+// right-looking steps of kNB columns whose updates stay inside the block column.
+int PotrfBlockColumn(cudaStream_t s, int m, int j0, int w, double* H, long ldh, int* info) {
+  ConfigureOnce();
+  for (int i0 = j0; i0 < j0 + w; i0 += kNB) {
+    const int nb = min(kNB, j0 + w - i0);
+    double* Hii = H + (long)i0 * ldh + i0;
+    CountLaunch(); PotrfDiagKernel<<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info);
+    const int rows = m - i0 - nb;
+    if (rows <= 0) continue;
+    double* A21 = Hii + nb;
+    CountLaunch(); TrsmPanelKernel<<<(rows + kNB - 1) / kNB, kNB, kTrsmSmem, s>>>(nb, Hii, ldh, A21, rows, info);
+    const int rest = j0 + w - (i0 + nb);  // columns of this block column still to be updated
+    if (rest > 0) {
+      // trapezoid: rows i0+nb .. m-1, columns i0+nb .. j0+w-1 (lower part)
+      const int rc = DgemmEx(s, -1, 1, false, true, rows, rest, nb, -1.0, A21, ldh, 0, A21, ldh, 0, 1.0,
+                             H + (long)(i0 + nb) * ldh + (i0 + nb), ldh, 0, 1, true, false, 0);
+      if (rc != 0) return rc;
+    }
+  }
+  return LaunchStatus();
+}
+
 }  // namespace cxb
 
 using namespace cxb;
@@ -197,36 +401,24 @@ extern "C" {
 
 size_t cxb_potrf_worksize(int m) {
   (void)m;
-  return 1;  // the current algorithm works fully in place
+  return 1;  // the algorithm works fully in place
 }
 
 int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, int* d_info) {
   (void)d_work;
   cudaStream_t s = AsStream(stream);
   if (m <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(PotrfDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(double) * kNB * (kNB + 1)));
-    cudaFuncSetAttribute(TrsmPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(double) * (kNB * (kNB + 1) + kNB * (kTrsmRows + 1))));
-    configured = true;
-  }
   CountLaunch(); ResetInfoKernel<<<1, 1, 0, s>>>(d_info);
-  for (int j0 = 0; j0 < m; j0 += kNB) {
-    const int nb = min(kNB, m - j0);
-    double* Hjj = dH + (long)j0 * ldh + j0;
-    CountLaunch(); PotrfDiagKernel<<<1, 1024, sizeof(double) * nb * (nb + 1), s>>>(nb, Hjj, ldh, j0, d_info);
-    const int rows = m - j0 - nb;
+  for (int j0 = 0; j0 < m; j0 += kOuter) {
+    const int w = min(kOuter, m - j0);
+    int rc = PotrfBlockColumn(s, m, j0, w, dH, ldh, d_info);
+    if (rc != 0) return rc;
+    const int rows = m - j0 - w;
     if (rows > 0) {
-      double* A21 = Hjj + nb;
-      const size_t smem = sizeof(double) * ((size_t)nb * (nb + 1) + (size_t)nb * (kTrsmRows + 1));
-      CountLaunch(); TrsmPanelKernel<<<(rows + kTrsmRows - 1) / kTrsmRows, 256, smem, s>>>(nb, Hjj, ldh, A21, rows,
-                                                                            d_info);
-      double* A22 = dH + (long)(j0 + nb) * ldh + (j0 + nb);
-      // A22 -= L21 L21^T (lower tiles only)
-      const int rc = Dgemm(s, false, true, rows, rows, nb, -1.0, A21, ldh, 0, A21, ldh, 0, 1.0, A22,
-                           ldh, 0, 1, true);
+      // A22 -= L21 L21^T with K = w (lower tiles only)
+      const double* L21 = dH + (long)j0 * ldh + (j0 + w);
+      double* A22 = dH + (long)(j0 + w) * ldh + (j0 + w);
+      rc = Dgemm(s, false, true, rows, rows, w, -1.0, L21, ldh, 0, L21, ldh, 0, 1.0, A22, ldh, 0, 1, true);
       if (rc != 0) return rc;
     }
   }
@@ -236,37 +428,27 @@ int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, i
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs) {
   cudaStream_t s = AsStream(stream);
   if (m <= 0 || nrhs <= 0) return 0;
-  if (nrhs > 4) return -1;
-  static bool configured = false;
-  if (!configured) {
-    const int bytes = (int)(sizeof(double) * (kNB * (kNB + 1) + 4 * kNB));
-    cudaFuncSetAttribute(TrsvDiagKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(TrsvDiagKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    configured = true;
-  }
+  if (nrhs > kMaxRhs) return -1;
+  ConfigureOnce();
   const int nblk = (m + kNB - 1) / kNB;
+  // z (the forward solution) is collected in a scratch array while dX is the working vector; the
+  // backward sweep then works in the scratch array and collects x in dX.
+  double* Z = nullptr;
+  if (cudaMallocAsync(&Z, sizeof(double) * (size_t)m * nrhs, s) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
   // forward: L z = b
   for (int k = 0; k < nblk; k++) {
     const int j0 = k * kNB, nb = min(kNB, m - j0);
-    const double* Lkk = dL + (long)j0 * ldl + j0;
-    const size_t smem = sizeof(double) * ((size_t)nb * (nb + 1) + (size_t)nb * nrhs);
-    CountLaunch(); TrsvDiagKernel<false><<<1, 256, smem, s>>>(nb, Lkk, ldl, dX + j0, ldx, nrhs);
     const int rows = m - j0 - nb;
-    if (rows > 0) {
-      CountLaunch(); TrsvUpdateFwdKernel<<<(rows + 255) / 256, 256, 0, s>>>(rows, nb, Lkk + nb, ldl, dX + j0,
-                                                             dX + j0 + nb, ldx, nrhs);
-    }
+    const int grid = rows > 0 ? (rows + kFwdRows - 1) / kFwdRows : 1;
+    CountLaunch(); TrsvFwdStepKernel<<<grid, 256, kTrsvSmem, s>>>(m, j0, nb, dL, ldl, dX, ldx, Z, m, nrhs);
   }
   // backward: L^T x = z
   for (int k = nblk - 1; k >= 0; k--) {
     const int j0 = k * kNB, nb = min(kNB, m - j0);
-    const double* Lkk = dL + (long)j0 * ldl + j0;
-    const size_t smem = sizeof(double) * ((size_t)nb * (nb + 1) + (size_t)nb * nrhs);
-    CountLaunch(); TrsvDiagKernel<true><<<1, 256, smem, s>>>(nb, Lkk, ldl, dX + j0, ldx, nrhs);
-    if (j0 > 0) {
-      CountLaunch(); TrsvUpdateBwdKernel<<<(j0 + 7) / 8, 256, 0, s>>>(j0, nb, dL + j0, ldl, dX + j0, dX, ldx, nrhs);
-    }
+    const int grid = j0 > 0 ? (j0 + 31) / 32 : 1;
+    CountLaunch(); TrsvBwdStepKernel<<<grid, 256, kTrsvSmem, s>>>(j0, nb, dL, ldl, Z, m, dX, ldx, nrhs);
   }
+  cudaFreeAsync(Z, s);
   return LaunchStatus();
 }
 

@@ -19,6 +19,9 @@ int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool trans
             double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror,
             int diag_off = 0);
 
+// cholesky.cu: factors the block column [j0, j0 + w) x rows [j0, m) in place (w <= 512)
+int PotrfBlockColumn(cudaStream_t s, int m, int j0, int w, double* H, long ldh, int* info);
+
 // blas1.cu
 int SetIdentity(cudaStream_t s, int n, double* W);
 int Symmetrize(cudaStream_t s, int n, double* W);                          // W <- (W + W^T)/2

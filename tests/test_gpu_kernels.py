@@ -205,7 +205,7 @@ def test_schur_dense_lmi_matches_oracle(dev, n, m, seed):
         assert abs(Haug[m, m] - sc[1]) <= 1e-10 * abs(sc[1])
 
 
-@pytest.mark.parametrize("m", [1, 5, 100, 128, 129, 300, 1000])
+@pytest.mark.parametrize("m", [1, 5, 31, 33, 100, 128, 129, 300, 511, 513, 700, 1000, 2500])
 def test_potrf_and_potrs(dev, m):
     """K3/K5 against numpy's Cholesky and solve; lower triangle only is read."""
     import torch
