@@ -7,6 +7,7 @@
 //  (2) ORACLE_* entry points exposing individual kernels (Schur assembly, Padé map, Lanczos,
 //      Cholesky, mu rule, PSD step functions) for kernel-level parity tests.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -16,6 +17,7 @@
 
 using oracle::DenseLmiCone;
 using oracle::LinearCone;
+using oracle::SocCone;
 using oracle::Program;
 
 namespace {
@@ -102,6 +104,117 @@ int CONEX_AddDenseLinearConstraint(void* p, const double* A, int Ar, int Ac, con
   return id;
 }
 
+int CONEX_AddLinearInequalities(void* p, const double* A, int Ar, int Ac, const double* lb,
+                                int num_lb, const double* ub, int num_ub) {
+  // interfaces/conex.cc:190-215 + PreprocessLinearInequality (linear_constraint.cc:21-46):
+  // rows with lb == ub become scaled equalities; finite bounds become scaled inequality rows.
+  (void)num_lb;
+  (void)num_ub;
+  Program* prog = Cast(p);
+  std::vector<std::vector<double>> ineq_rows, eq_rows;
+  std::vector<double> ineq_rhs, eq_rhs;
+  for (int i = 0; i < Ar; i++) {
+    double rr = 0;
+    for (int j = 0; j < Ac; j++) rr += A[(size_t)j * Ar + i] * A[(size_t)j * Ar + i];
+    auto row = [&](double scale) {
+      std::vector<double> r(Ac);
+      for (int j = 0; j < Ac; j++) r[j] = scale * A[(size_t)j * Ar + i];
+      return r;
+    };
+    if (lb[i] == ub[i]) {
+      const double scale = 1.0 / std::sqrt(rr + ub[i] * ub[i]);
+      eq_rows.push_back(row(scale));
+      eq_rhs.push_back(scale * ub[i]);
+    } else {
+      if (ub[i] < 1e8) {
+        const double scale = 1.0 / std::sqrt(rr + ub[i] * ub[i]);
+        ineq_rows.push_back(row(scale));
+        ineq_rhs.push_back(scale * ub[i]);
+      }
+      if (lb[i] > -1e8) {
+        const double scale = 1.0 / std::sqrt(rr + lb[i] * lb[i]);
+        ineq_rows.push_back(row(-scale));
+        ineq_rhs.push_back(-scale * lb[i]);
+      }
+    }
+  }
+  auto pack = [&](const std::vector<std::vector<double>>& rows) {
+    const int r = (int)rows.size();
+    std::vector<double> M((size_t)r * Ac);
+    for (int i = 0; i < r; i++)
+      for (int j = 0; j < Ac; j++) M[(size_t)j * r + i] = rows[i][j];
+    return M;
+  };
+  if (!ineq_rows.empty()) {
+    const auto M = pack(ineq_rows);
+    prog->AddCone(std::make_unique<LinearCone>((int)ineq_rows.size(), Ac, M.data(), ineq_rhs.data()));
+  }
+  if (!eq_rows.empty()) {
+    const auto M = pack(eq_rows);
+    prog->AddEquality((int)eq_rows.size(), M.data(), eq_rhs.data());
+  }
+  return -1;
+}
+
+CONEX_STATUS CONEX_NewLorentzConeConstraint(void* p, int order, int* constraint_id) {
+  // interfaces/conex.cc:384-397
+  if (order < 1 || !constraint_id || !p) return CONEX_FAILURE;
+  Program* prog = Cast(p);
+  prog->AddCone(std::make_unique<SocCone>(order, prog->NumberOfVariables(), nullptr, nullptr));
+  *constraint_id = prog->NumberOfConstraints() - 1;
+  return CONEX_SUCCESS;
+}
+
+CONEX_STATUS CONEX_NewLinearInequality(void* p, int num_rows, int* constraint_id) {
+  // interfaces/conex.cc:318-329
+  if (!constraint_id || !p) return CONEX_FAILURE;
+  Program* prog = Cast(p);
+  const int m = prog->NumberOfVariables();
+  std::vector<double> A((size_t)num_rows * m, 0.0), c(num_rows, 0.0);
+  prog->AddCone(std::make_unique<LinearCone>(num_rows, m, A.data(), c.data()));
+  *constraint_id = prog->NumberOfConstraints() - 1;
+  return CONEX_SUCCESS;
+}
+
+CONEX_STATUS CONEX_UpdateLinearOperator(void* p, int constraint, double value, int variable, int row,
+                                        int col, int hyper_complex_dim) {
+  // interfaces/conex.cc:365-373; linear_constraint.cc:207-216; soc_constraint.cc:237-247
+  Program* prog = Cast(p);
+  if (constraint < 0 || constraint >= prog->NumberOfConstraints()) return CONEX_FAILURE;
+  if (hyper_complex_dim != 0 || col != 0 || variable < 0 || row < 0) return CONEX_FAILURE;
+  if (variable >= prog->NumberOfVariables()) return CONEX_FAILURE;
+  if (auto* lp = dynamic_cast<LinearCone*>(prog->cone(constraint))) {
+    if (row >= lp->rows()) return CONEX_FAILURE;
+    lp->SetOperatorEntry(row, variable, value);
+    return CONEX_SUCCESS;
+  }
+  if (auto* soc = dynamic_cast<SocCone*>(prog->cone(constraint))) {
+    if (row > soc->order()) return CONEX_FAILURE;
+    soc->SetOperatorEntry(row, variable, value);
+    return CONEX_SUCCESS;
+  }
+  return CONEX_FAILURE;
+}
+
+CONEX_STATUS CONEX_UpdateAffineTerm(void* p, int constraint, double value, int row, int col,
+                                    int hyper_complex_dim) {
+  // interfaces/conex.cc:375-382; linear_constraint.cc:218-226; soc_constraint.cc:249-259
+  Program* prog = Cast(p);
+  if (constraint < 0 || constraint >= prog->NumberOfConstraints()) return CONEX_FAILURE;
+  if (hyper_complex_dim != 0 || col != 0 || row < 0) return CONEX_FAILURE;
+  if (auto* lp = dynamic_cast<LinearCone*>(prog->cone(constraint))) {
+    if (row >= lp->rows()) return CONEX_FAILURE;
+    lp->SetAffineEntry(row, value);
+    return CONEX_SUCCESS;
+  }
+  if (auto* soc = dynamic_cast<SocCone*>(prog->cone(constraint))) {
+    if (row > soc->order()) return CONEX_FAILURE;
+    soc->SetAffineEntry(row, value);
+    return CONEX_SUCCESS;
+  }
+  return CONEX_FAILURE;
+}
+
 int CONEX_Maximize(void* p, const double* b, int br, const CONEX_SolverConfiguration* config,
                    double* y, int yr) {
   // interfaces/conex.cc:93-105
@@ -156,6 +269,44 @@ void CONEX_GetIterationStats(void* p, CONEX_IterationStats* stats, int iter_circ
 }
 
 // ---------------------------------------------------------------------------- ORACLE_* extras
+// C++-only constructors of the reference, exposed for the tests:
+// SOCConstraint(A, c) (soc_constraint.h:9-15): A is (n+1) x m column-major.
+int ORACLE_AddSocConstraint(void* p, int n, int m, const double* A, const double* c) {
+  Program* prog = Cast(p);
+  const int id = prog->NumberOfConstraints();
+  if (prog->NumberOfVariables() == 0) prog->SetNumberOfVariables(m);
+  prog->AddCone(std::make_unique<SocCone>(n, m, A, c));
+  return id;
+}
+// Program::AddConstraint(EqualityConstraints{A, b}[, vars]) (cone_program.h:193-217): A is
+// rows x nvars column-major; vars == nullptr means all variables.
+int ORACLE_AddEqualityConstraint(void* p, int rows, int nvars, const double* A, const double* b,
+                                 const long* vars) {
+  Program* prog = Cast(p);
+  const int id = prog->NumberOfConstraints();
+  bool ok;
+  if (vars) {
+    std::vector<int> v(nvars);
+    for (int i = 0; i < nvars; i++) v[i] = (int)vars[i];
+    ok = prog->AddEquality(rows, A, b, v);
+  } else {
+    ok = prog->AddEquality(rows, A, b);
+  }
+  return ok ? id : -1;
+}
+int ORACLE_SizeOfKKTSystem(void* p) { return Cast(p)->SizeOfKKTSystem(); }
+// In-place RLDLT of the lower triangle of A (n x n); transpositions written as ints. Returns 1
+// when no pivot was regularised.
+int ORACLE_LdltLower(int n, double* A, int* transpositions) {
+  std::vector<int> t;
+  const bool ok = oracle::LdltLower(n, A, n, &t);
+  for (int i = 0; i < n; i++) transpositions[i] = t[i];
+  return ok ? 1 : 0;
+}
+void ORACLE_SolveLdlt(int n, const double* LD, const int* transpositions, double* x) {
+  oracle::SolveLdlt(n, LD, n, std::vector<int>(transpositions, transpositions + n), x);
+}
+
 int ORACLE_BlasAvailable() { return oracle::BlasAvailable() ? 1 : 0; }
 void ORACLE_ForcePlainLoops(int on) { oracle::ForcePlainLoops(on != 0); }
 void ORACLE_SetBlasThreads(int n) { oracle::SetBlasThreads(n); }
@@ -202,7 +353,7 @@ void ORACLE_AssembleNewtonSystem(void* p, int coldstart, double* H, double* AW, 
   cfg.initialization_mode = coldstart ? 0 : 1;
   prog->Initialize(cfg);
   prog->Assemble();
-  const int m = prog->NumberOfVariables();
+  const int m = prog->SizeOfKKTSystem();
   std::memcpy(H, prog->H.data(), sizeof(double) * m * m);
   std::memcpy(AW, prog->sys.AW, sizeof(double) * m);
   std::memcpy(AQc, prog->sys.AQc, sizeof(double) * m);

@@ -459,4 +459,164 @@ void LinearCone::GetWeightedSlackEigenvalues(const double* y, double c_weight,
   p->trace = -sum;
 }
 
+// ============================================================================================
+// Second-order cone (spin factor algebra)
+// ============================================================================================
+namespace {
+
+// SpectralDecompSpinFactor::Compute + Idempotents (soc_constraint.cc:22-63), applied to a scalar
+// function f of the two eigenvalues: returns f(ev0) c0 + f(ev1) c1.
+template <typename F>
+void SpinFunction(int n, double x0, const double* x1, F f, double* out) {
+  double nq = 0;
+  for (int i = 0; i < n; i++) nq += x1[i] * x1[i];
+  nq = std::sqrt(nq);
+  const double f0 = f(x0 + nq), f1 = f(x0 - nq);
+  out[0] = f0 * .5 + f1 * .5;
+  for (int i = 0; i < n; i++) {
+    const double q = (nq > 0) ? x1[i] / nq : 0.0;
+    out[1 + i] = f0 * (.5 * q) + f1 * (-.5 * q);
+  }
+}
+
+// Q(x) y = 2 <x,y> x - det(x) R y, R = diag(1,-1,...,-1) (soc_constraint.cc:115-128).
+void QuadraticRepresentation(int order, const double* x, const double* y, double* out) {
+  double det = x[0] * x[0], xy = 0;
+  for (int i = 1; i < order; i++) det -= x[i] * x[i];
+  for (int i = 0; i < order; i++) xy += x[i] * y[i];
+  for (int i = 0; i < order; i++) {
+    double z = det * y[i];
+    if (i == 0) z *= -1;
+    out[i] = (2 * xy) * x[i] + z;
+  }
+}
+
+}  // namespace
+
+SocCone::SocCone(int n, int m, const double* A, const double* c)
+    : n_(n), m_(m), A_((size_t)(n + 1) * m, 0.0), c_(n + 1, 0.0), dual_(n + 1, 0.0) {
+  if (A) A_.assign(A, A + (size_t)(n + 1) * m);
+  if (c) c_.assign(c, c + n + 1);
+}
+
+void SocCone::BindWorkspace(double* data) {
+  // conex/workspace_soc.h:13-21
+  const int s = AlignedSize(n_);
+  W1_ = data;
+  temp1_ = data + s;
+  W0_ = data + 4 * s;
+}
+
+void SocCone::SetIdentity() {
+  *W0_ = 1;
+  std::fill(W1_, W1_ + n_, 0.0);
+}
+
+void SocCone::ComputeNegativeSlack(double k, const double* y, double* minus_s) const {
+  Gemv(false, n_ + 1, m_, 1.0, A_.data(), n_ + 1, y, 0.0, minus_s);
+  for (int i = 0; i <= n_; i++) minus_s[i] -= c_[i] * k;
+}
+
+void SocCone::GetWeightedSlackEigenvalues(const double* y, double c_weight, SlackEigenvalues* p) {
+  // conex/soc_constraint.cc:172-189
+  const int n = n_;
+  std::vector<double> minus_s(n + 1), wsqrt(n + 1), Ws(n + 1);
+  ComputeNegativeSlack(c_weight, y, minus_s.data());
+  SpinFunction(n, *W0_, W1_, [](double e) { return std::sqrt(e); }, wsqrt.data());
+  QuadraticRepresentation(n + 1, wsqrt.data(), minus_s.data(), Ws.data());
+  double nq = 0;
+  for (int i = 1; i <= n; i++) nq += Ws[i] * Ws[i];
+  nq = std::sqrt(nq);
+  const double ev0 = Ws[0] + nq, ev1 = Ws[0] - nq;
+  const double lmax = -std::min(ev0, ev1), lmin = -std::max(ev0, ev1);
+  p->lambda_max = lmax;
+  p->lambda_min = lmin;
+  p->frobenius_norm_squared = lmax * lmax + lmin * lmin;
+  p->trace = lmax + lmin;
+}
+
+void SocCone::PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) {
+  // conex/soc_constraint.cc:213-230. NB: W is overwritten by its square root here and the
+  // e_weight / affine options are not consulted.
+  const int n = n_;
+  std::vector<double> minus_s(n + 1), wsqrt(n + 1), d(n + 1);
+  ComputeNegativeSlack(opt.c_weight, y, minus_s.data());
+  SpinFunction(n, *W0_, W1_, [](double e) { return std::sqrt(e); }, wsqrt.data());
+  *W0_ = wsqrt[0];
+  std::copy(wsqrt.begin() + 1, wsqrt.end(), W1_);
+  QuadraticRepresentation(n + 1, wsqrt.data(), minus_s.data(), d.data());
+  d[0] += 1;
+  std::copy(d.begin() + 1, d.end(), temp1_);
+  d0_ = d[0];
+  double nq = 0, sq = 0;
+  for (int i = 1; i <= n; i++) nq += d[i] * d[i];
+  for (int i = 0; i <= n; i++) sq += d[i] * d[i];
+  nq = std::sqrt(nq);
+  info->norminfd = std::max(std::fabs(d[0] + nq), std::fabs(d[0] - nq));
+  info->normsqrd = 2 * sq;
+}
+
+bool SocCone::TakeStep(const StepOptions& opt) {
+  // conex/soc_constraint.cc:191-211
+  const int n = n_;
+  std::vector<double> wsqrt(n + 1), d1(temp1_, temp1_ + n), expd(n + 1), wn(n + 1);
+  double d0 = d0_;
+  wsqrt[0] = *W0_;
+  std::copy(W1_, W1_ + n, wsqrt.begin() + 1);
+  if (opt.step_size != 1.0) {
+    d0 *= opt.step_size;
+    for (auto& v : d1) v *= opt.step_size;
+  }
+  SpinFunction(n, d0, d1.data(), [](double e) { return std::exp(e); }, expd.data());
+  QuadraticRepresentation(n + 1, wsqrt.data(), expd.data(), wn.data());
+  *W0_ = wn[0];
+  std::copy(wn.begin() + 1, wn.end(), W1_);
+  return true;
+}
+
+void SocCone::ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) {
+  // conex/soc_constraint.cc:232-262
+  const int n = n_, m = m_, o = n + 1;
+  std::vector<double> wsqrt(o), W(o), WA((size_t)o * m), WC(o);
+  SpinFunction(n, *W0_, W1_, [](double e) { return std::sqrt(e); }, wsqrt.data());
+  W[0] = *W0_;
+  std::copy(W1_, W1_ + n, W.begin() + 1);
+  QuadraticRepresentation(o, wsqrt.data(), c_.data(), WC.data());
+  for (int i = 0; i < m; i++)
+    QuadraticRepresentation(o, wsqrt.data(), &A_[(size_t)i * o], &WA[(size_t)i * o]);
+  const double beta = initialize ? 0.0 : 1.0;
+  Gemm(true, false, m, m, o, 2.0, WA.data(), o, WA.data(), o, beta, sys->G.p, sys->G.rows);
+  Gemv(true, o, m, 2.0, A_.data(), o, W.data(), beta, sys->AW);
+  Gemv(true, o, m, 2.0, WA.data(), o, WC.data(), beta, sys->AQc);
+  double sq = 0;
+  for (int i = 0; i < o; i++) sq += WC[i] * WC[i];
+  Store(initialize, &sys->inner_product_of_w_and_c, 2 * WC[0]);
+  Store(initialize, &sys->inner_product_of_c_and_Qc, 2 * sq);
+}
+
+// ============================================================================================
+// Equality constraints
+// ============================================================================================
+
+void EqualityCone::ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) {
+  // conex/equality_constraint.cc:13-28: G = [0 A^T; A 0] on (variables, multipliers), AQc = [0; b].
+  const int t = nv_ + rows_;
+  if (initialize) sys->SetZero();
+  for (int j = 0; j < nv_; j++) {
+    for (int i = 0; i < rows_; i++) {
+      sys->G(nv_ + i, j) += A_[(size_t)j * rows_ + i];
+      sys->G(j, nv_ + i) += A_[(size_t)j * rows_ + i];
+    }
+  }
+  for (int i = 0; i < rows_; i++) sys->AQc[nv_ + i] += b_[i];
+  (void)t;
+}
+
+void EqualityCone::PrepareStep(const StepOptions&, const double* y, StepInfo* info) {
+  // conex/equality_constraint.cc:30-35
+  for (int i = 0; i < rows_; i++) lambda_[i] = y[nv_ + i];
+  info->normsqrd = 0;
+  info->norminfd = 0;
+}
+
 }  // namespace oracle

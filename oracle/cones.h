@@ -19,8 +19,8 @@ namespace oracle {
 struct SlackEigenvalues {
   double frobenius_norm_squared = 0;
   double trace = 0;
-  double lambda_min = 0;
-  double lambda_max = 0;
+  double lambda_min = 1.7976931348623157e308;   // newton_step.h:15-16: neutral for the min/max
+  double lambda_max = -1.7976931348623157e308;  // aggregation (the equality cone leaves them)
   double rank = 0;
 };
 struct StepOptions {
@@ -128,12 +128,73 @@ class LinearCone final : public Cone {
                                    SlackEigenvalues* p) override;
   const double* DualVariable() const override { return W_; }
   int DualVariableSize() const override { return n_; }
+  // incremental construction (linear_constraint.cc:207-226)
+  int rows() const { return n_; }
+  void SetOperatorEntry(int row, int var, double v) { A_[(size_t)var * n_ + row] = v; }
+  void SetAffineEntry(int row, double v) { c_[row] = v; }
 
  private:
   void ComputeNegativeSlack(double k, const double* y, double* minus_s) const;
   int n_, m_;
   std::vector<double> A_, c_;
   double *W_ = nullptr, *temp_1_ = nullptr, *temp_2_ = nullptr, *WA_ = nullptr;
+};
+
+// SOCConstraint (conex/soc_constraint.{h,cc}, conex/workspace_soc.h): c - A y in the Lorentz cone
+// of order n+1; A is (n+1) x m, scaling point w = (W0, W1).
+class SocCone final : public Cone {
+ public:
+  SocCone(int n, int m, const double* A, const double* c);
+  int WorkspaceSize() const override { return 5 * AlignedSize(n_); }  // workspace_soc.h:9-11
+  void BindWorkspace(double* data) override;
+  void SetIdentity() override;
+  int Rank() const override { return 2; }
+  int NumberOfVariables() const override { return m_; }
+  void ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) override;
+  void PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) override;
+  bool TakeStep(const StepOptions& opt) override;
+  void GetWeightedSlackEigenvalues(const double* y, double c_weight,
+                                   SlackEigenvalues* p) override;
+  const double* DualVariable() const override { return dual_.data(); }
+  int DualVariableSize() const override { return n_ + 1; }
+  // incremental construction (soc_constraint.cc:237-260)
+  int order() const { return n_; }
+  void SetOperatorEntry(int row, int var, double v) { A_[(size_t)var * (n_ + 1) + row] = v; }
+  void SetAffineEntry(int row, double v) { c_[row] = v; }
+  double* W0_ = nullptr;
+  double* W1_ = nullptr;
+
+ private:
+  void ComputeNegativeSlack(double k, const double* y, double* minus_s) const;
+  int n_, m_;
+  std::vector<double> A_, c_;
+  double* temp1_ = nullptr;
+  double d0_ = 0;
+  std::vector<double> dual_;  // the reference's dummy `W` member (workspace_soc.h:44)
+};
+
+// EqualityConstraints (conex/equality_constraint.{h,cc}): A x = b on `nv` variables with
+// A.rows() multipliers appended to the clique (constraint_manager.h:71-86). Rank 0, no state.
+class EqualityCone final : public Cone {
+ public:
+  EqualityCone(int rows, int nv, const double* A, const double* b)
+      : rows_(rows), nv_(nv), A_(A, A + (size_t)rows * nv), b_(b, b + rows), lambda_(rows, 0.0) {}
+  int WorkspaceSize() const override { return 0; }
+  void BindWorkspace(double*) override {}
+  void SetIdentity() override {}
+  int Rank() const override { return 0; }
+  int NumberOfVariables() const override { return nv_ + rows_; }  // size of its clique
+  int NumberOfMultipliers() const { return rows_; }
+  void ConstructSchurComplementSystem(bool initialize, SchurSystem* sys) override;
+  void PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) override;
+  bool TakeStep(const StepOptions&) override { return true; }
+  void GetWeightedSlackEigenvalues(const double*, double, SlackEigenvalues*) override {}
+  const double* DualVariable() const override { return lambda_.data(); }
+  int DualVariableSize() const override { return 0; }  // its workspace W is an empty map
+
+ private:
+  int rows_, nv_;
+  std::vector<double> A_, b_, lambda_;
 };
 
 // --- dense math kernels -------------------------------------------------------------------

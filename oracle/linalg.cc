@@ -167,6 +167,71 @@ bool CholeskyLower(int n, double* A, int lda) {
   return true;
 }
 
+bool LdltLower(int n, double* A, int lda, std::vector<int>* transpositions) {
+  // conex/RLDLT.h:297-431 (rldlt_inplace<Lower>::unblocked), real scalars.
+  auto a = [&](int i, int j) -> double& { return A[(size_t)j * lda + i]; };
+  const double reg = 1e-9;
+  transpositions->assign(n, 0);
+  bool ok = true;
+  if (n <= 1) {
+    if (n == 1) {
+      if (std::fabs(a(0, 0)) < reg) a(0, 0) = (a(0, 0) < 0) ? -reg : reg;  // :310-317 (returns true)
+    }
+    return true;
+  }
+  std::vector<double> temp(n);
+  for (int k = 0; k < n; k++) {
+    // largest |diagonal| of the trailing part, first occurrence (:330-334)
+    int p = k;
+    double best = std::fabs(a(k, k));
+    for (int i = k + 1; i < n; i++) {
+      if (std::fabs(a(i, i)) > best) {
+        best = std::fabs(a(i, i));
+        p = i;
+      }
+    }
+    (*transpositions)[k] = p;
+    if (p != k) {
+      // symmetric swap restricted to the lower triangle (:336-353)
+      for (int j = 0; j < k; j++) std::swap(a(k, j), a(p, j));
+      for (int i = p + 1; i < n; i++) std::swap(a(i, k), a(i, p));
+      std::swap(a(k, k), a(p, p));
+      for (int i = k + 1; i < p; i++) std::swap(a(i, k), a(p, i));
+    }
+    const int rs = n - k - 1;
+    if (k > 0) {
+      for (int j = 0; j < k; j++) temp[j] = a(j, j) * a(k, j);  // D * A10^T (:365-366)
+      double s = 0;
+      for (int j = 0; j < k; j++) s += a(k, j) * temp[j];
+      a(k, k) -= s;
+      for (int i = 0; i < rs; i++) {
+        double t = 0;
+        for (int j = 0; j < k; j++) t += a(k + 1 + i, j) * temp[j];
+        a(k + 1 + i, k) -= t;
+      }
+    }
+    double akk = a(k, k);
+    if (!(std::fabs(akk) > 1e-9)) {  // :378-389
+      ok = false;
+      a(k, k) = (akk < 0) ? -reg : reg;
+      akk = a(k, k);
+    }
+    for (int i = 0; i < rs; i++) a(k + 1 + i, k) /= akk;
+  }
+  return ok;
+}
+
+void SolveLdlt(int n, const double* LD, int lda, const std::vector<int>& tr, double* x) {
+  auto a = [&](int i, int j) { return LD[(size_t)j * lda + i]; };
+  for (int k = 0; k < n; k++) std::swap(x[k], x[tr[k]]);          // P x
+  for (int j = 0; j < n; j++)                                      // L^{-1}
+    for (int i = j + 1; i < n; i++) x[i] -= a(i, j) * x[j];
+  for (int j = 0; j < n; j++) x[j] /= a(j, j);                     // D^{-1}
+  for (int j = n - 1; j >= 0; j--)                                 // L^{-T}
+    for (int i = j + 1; i < n; i++) x[j] -= a(i, j) * x[i];
+  for (int k = n - 1; k >= 0; k--) std::swap(x[k], x[tr[k]]);      // P^T
+}
+
 void SolveLower(int n, const double* L, int ldl, double* x, bool transpose) {
   if (UseBlas() && n > 16) {
     g_blas.dtrsv(kColMajor, kLower, transpose ? kTrans : kNoTrans, kNonUnit, n, L, ldl,

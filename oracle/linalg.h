@@ -71,6 +71,16 @@ bool CholeskyLower(int n, double* A, int lda);
 // x <- L^{-1} x  or  x <- L^{-T} x  (triangularView<Lower>().solveInPlace,
 // conex/block_triangular_operations.cc:125-128,169,181).
 void SolveLower(int n, const double* L, int ldl, double* x, bool transpose);
+// In-place diagonally pivoted, regularised LDL^T of a symmetric (possibly indefinite) matrix,
+// restating Eigen::RLDLT::unblocked (conex/RLDLT.h:297-431): at step k the pivot is the largest
+// |diagonal entry| of the *stored* trailing diagonal (left-looking algorithm: those entries are
+// still the original ones), a symmetric swap brings it to position k, column k is formed from
+// the k previous columns, and a pivot with |d| <= 1e-9 is replaced by +-1e-9. On return the
+// strict lower triangle holds L, the diagonal holds D, transpositions[k] is the row swapped with
+// k. Returns true when no pivot was regularised (RLDLT::regularization_used() == false).
+bool LdltLower(int n, double* A, int lda, std::vector<int>* transpositions);
+// x <- P^T L^{-T} D^{-1} L^{-1} P x (conex/block_triangular_operations.cc:222-312 for one block).
+void SolveLdlt(int n, const double* LD, int lda, const std::vector<int>& transpositions, double* x);
 // Solves A X = B with partial (row) pivoting; A and B are overwritten (B <- X).
 // Stands in for Eigen partialPivLu().solve (conex/exponential_map_pade.cc:31).
 // Returns false if a zero pivot is met.

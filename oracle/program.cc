@@ -43,6 +43,26 @@ bool Program::AddCone(std::unique_ptr<Cone> cone) {
   return AddCone(std::move(cone), all);
 }
 
+bool Program::AddEquality(int rows, const double* A, const double* b, const std::vector<int>& vars) {
+  std::vector<int> seen(m_, 0);
+  for (int v : vars) {
+    if (v < 0 || v >= m_ || seen[v]++) return false;
+  }
+  std::vector<int> clique(vars);
+  for (int i = 0; i < rows; i++) clique.push_back(m_ + num_dual_ + i);
+  num_dual_ += rows;
+  cones_.push_back(std::make_unique<EqualityCone>(rows, (int)vars.size(), A, b));
+  cliques_.push_back(clique);
+  is_initialized_ = false;
+  return true;
+}
+
+bool Program::AddEquality(int rows, const double* A, const double* b) {
+  std::vector<int> all(m_);
+  for (int i = 0; i < m_; i++) all[i] = i;
+  return AddEquality(rows, A, b, all);
+}
+
 void Program::GatherVars(int c, const double* y, std::vector<double>* z) const {
   // conex/cone_program.h:59-67
   const auto& cl = cliques_[c];
@@ -63,7 +83,7 @@ bool Program::Initialize(const SolverConfiguration& config) {
   const size_t stats_offset = total;
   total += 2;  // c_scaling, b_scaling (conex/workspace.h:76-88; the per-iteration arrays live in
                // sqrt_inv_mu so that warm starts with a larger max_iterations stay in bounds)
-  sys.m = m_;
+  sys.m = SizeOfKKTSystem();
   sys.residual_only = true;
   const size_t sys_offset = total;
   total += sys.SizeOf();
@@ -78,7 +98,7 @@ bool Program::Initialize(const SolverConfiguration& config) {
   c_scaling_ = arena_.data() + stats_offset;
   b_scaling_ = arena_.data() + stats_offset + 1;
   sys.Bind(arena_.data() + sys_offset);
-  H.assign((size_t)m_ * m_, 0.0);
+  H.assign((size_t)SizeOfKKTSystem() * SizeOfKKTSystem(), 0.0);
   is_initialized_ = true;
   if (config.initialization_mode == 0) {
     *b_scaling_ = 1;
@@ -101,7 +121,7 @@ void Program::Assemble() {
     for (size_t a = 0; a < cl.size(); a++) {
       for (size_t b = 0; b <= a; b++) {
         const int ga = std::max(cl[a], cl[b]), gb = std::min(cl[a], cl[b]);
-        H[(size_t)gb * m_ + ga] += s.G((int)a, (int)b);
+        H[(size_t)gb * SizeOfKKTSystem() + ga] += s.G((int)a, (int)b);
       }
     }
     sys.inner_product_of_w_and_c += s.inner_product_of_w_and_c;
@@ -113,19 +133,31 @@ void Program::Assemble() {
   }
 }
 
-bool Program::Factor() { return CholeskyLower(m_, H.data(), m_); }
+bool Program::Factor() {
+  // conex/kkt_solver.cc:172-199: Cholesky unless some cone carries multipliers, then the
+  // regularised LDL^T, which never reports failure.
+  const int N = SizeOfKKTSystem();
+  if (num_dual_ == 0) return CholeskyLower(N, H.data(), N);
+  LdltLower(N, H.data(), N, &transpositions_);
+  return true;
+}
 
 void Program::SolveInPlace(double* rhs) const {
   // conex/kkt_solver.cc:220-246 for one dense supernode (identity permutation).
-  SolveLower(m_, H.data(), m_, rhs, false);
-  SolveLower(m_, H.data(), m_, rhs, true);
+  const int N = SizeOfKKTSystem();
+  if (num_dual_ == 0) {
+    SolveLower(N, H.data(), N, rhs, false);
+    SolveLower(N, H.data(), N, rhs, true);
+  } else {
+    SolveLdlt(N, H.data(), N, transpositions_, rhs);
+  }
 }
 
 double Program::ComputeMuFromDivergence(const SolverConfiguration& config, int rank,
                                         const std::vector<double>& b_scaled, double c_scaling,
                                         std::vector<double>* y) {
   // conex/cone_program.cc:173-214 with AQc := sys.AQc * c_scaling, b := b * b_scaling.
-  for (int i = 0; i < m_; i++) (*y)[i] = sys.AQc[i] * c_scaling - b_scaled[i];
+  for (int i = 0; i < SizeOfKKTSystem(); i++) (*y)[i] = sys.AQc[i] * c_scaling - b_scaled[i];
   SolveInPlace(y->data());
   // conex/cone_program.cc:31-57
   SlackEigenvalues p;
@@ -167,21 +199,23 @@ std::vector<double> Program::FeasibleObjective() {
 }
 
 bool Program::Maximize(const double* b_in, const SolverConfiguration& config, double* yout) {
-  const int m = m_;
+  const int mv = m_;                  // variables the caller sees
+  const int m = SizeOfKKTSystem();    // + multipliers of the equality constraints
   status = Status();
   log.clear();
   seconds = PhaseSeconds();
   bool max_iters_reached = true;
   if (cones_.empty()) {
     // conex/cone_program.cc:266-271
-    for (int i = 0; i < m; i++) yout[i] = b_in[i] * std::numeric_limits<double>::infinity();
+    for (int i = 0; i < mv; i++) yout[i] = b_in[i] * std::numeric_limits<double>::infinity();
     return false;
   }
   Initialize(config);
   sqrt_inv_mu.assign(std::max(config.max_iterations, 1), 0.0);
   const bool warm = config.initialization_mode != 0;
 
-  std::vector<double> b(b_in, b_in + m), y(m, 0.0), b_scaled(m), z;
+  std::vector<double> b(m, 0.0), y(m, 0.0), b_scaled(m), z;  // cone_program.cc:294-296
+  std::copy(b_in, b_in + mv, b.begin());
   double k = 0;  // inv_sqrt_mu
   double kmax = config.inv_sqrt_mu_max;
   double cx = 1, by = -1, kkt_error = 0;
@@ -309,7 +343,7 @@ bool Program::Maximize(const double* b_in, const SolverConfiguration& config, do
   }
 
   status.num_iterations = num_iter;
-  for (int j = 0; j < m; j++) yout[j] = y[j];
+  for (int j = 0; j < mv; j++) yout[j] = y[j];
   const double mu_final = (1.0 / k) * (1.0 / k);
   if (mu_final > config.infeasibility_threshold) {
     status.solved = 0;
@@ -337,7 +371,7 @@ bool Program::Maximize(const double* b_in, const SolverConfiguration& config, do
     }
   }
   if (status.solved) {
-    for (int j = 0; j < m; j++) yout[j] = yout[j] / k / c_scaling;
+    for (int j = 0; j < mv; j++) yout[j] = yout[j] / k / c_scaling;
     if (max_iters_reached) status.solved = 0;
   }
   return status.solved != 0;

@@ -60,6 +60,11 @@ class Program {
   // (conex/constraint_manager.h:10-24,62-70).
   bool AddCone(std::unique_ptr<Cone> cone, const std::vector<int>& vars);
   bool AddCone(std::unique_ptr<Cone> cone);
+  // conex/constraint_manager.h:71-94: the multipliers of A x = b become extra unknowns of the KKT
+  // system, appended to the cone's clique. A is rows x vars.size() column-major.
+  bool AddEquality(int rows, const double* A, const double* b, const std::vector<int>& vars);
+  bool AddEquality(int rows, const double* A, const double* b);
+  int SizeOfKKTSystem() const { return m_ + num_dual_; }
 
   // conex/cone_program.cc:235-533; b is maximised (Solve(b, prog, ...) :547-552).
   bool Maximize(const double* b, const SolverConfiguration& config, double* y);
@@ -93,6 +98,8 @@ class Program {
   void GatherVars(int cone, const double* y, std::vector<double>* z) const;
 
   int m_;
+  int num_dual_ = 0;
+  std::vector<int> transpositions_;  // RLDLT pivots (LDLT mode: any equality present)
   std::vector<std::unique_ptr<Cone>> cones_;
   std::vector<std::vector<int>> cliques_;
   std::vector<SchurSystem> cone_sys_;

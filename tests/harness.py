@@ -97,6 +97,13 @@ class ConexLib:
         L.CONEX_GetDualVariableSize.argtypes = [C.c_void_p, C.c_int]
         L.CONEX_SetDefaultOptions.argtypes = [C.POINTER(SolverConfiguration)]
         L.CONEX_GetIterationStats.argtypes = [C.c_void_p, C.POINTER(IterationStats), C.c_int]
+        L.CONEX_AddLinearInequalities.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_int, c_double_p,
+                                                  C.c_int, c_double_p, C.c_int]
+        L.CONEX_NewLorentzConeConstraint.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.CONEX_NewLinearInequality.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.CONEX_UpdateLinearOperator.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int,
+                                                 C.c_int, C.c_int]
+        L.CONEX_UpdateAffineTerm.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
         self.ext = "ORACLE" if kind == "oracle" else "CONEXB200"
         for name, args, res in [
             ("FeasibleObjective", [C.c_void_p, c_double_p], None),
@@ -105,6 +112,10 @@ class ConexLib:
             ("GetPhaseSeconds", [C.c_void_p, c_double_p], None),
             ("AssembleNewtonSystem", [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p,
                                       c_double_p], None),
+            ("AddSocConstraint", [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p], C.c_int),
+            ("AddEqualityConstraint", [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p,
+                                       C.POINTER(C.c_long)], C.c_int),
+            ("SizeOfKKTSystem", [C.c_void_p], C.c_int),
         ]:
             f = getattr(L, f"{self.ext}_{name}")
             f.argtypes = args
@@ -177,6 +188,72 @@ class Program:
         self.cone_shapes.append((Af.shape[0], 1))
         return cid
 
+    def add_soc(self, A, c, incremental=False):
+        """c - A y in the Lorentz cone of order n+1 (A is (n+1) x m). incremental=True goes through
+        CONEX_NewLorentzConeConstraint + CONEX_UpdateLinearOperator / CONEX_UpdateAffineTerm like
+        interfaces/python/test/run_tests.py:23-34; otherwise through the SOCConstraint(A, c)
+        constructor the reference's C++ tests use (conex/test/test_socp.cc:41-46)."""
+        Af = fmat(A)
+        cf = np.ascontiguousarray(np.array(c, dtype=np.float64).ravel())
+        order = Af.shape[0] - 1
+        if self.m == 0:
+            assert self.L.lib.CONEX_SetNumberOfVariables(self.h, Af.shape[1]) == 0
+            self.m = Af.shape[1]
+        if incremental:
+            cid = C.c_int(-1)
+            assert self.L.lib.CONEX_NewLorentzConeConstraint(self.h, order, C.byref(cid)) == 0
+            cid = cid.value
+            for r in range(order + 1):
+                assert self.L.lib.CONEX_UpdateAffineTerm(self.h, cid, float(cf[r]), r, 0, 0) == 0
+                for v in range(Af.shape[1]):
+                    assert self.L.lib.CONEX_UpdateLinearOperator(self.h, cid, float(Af[r, v]), v, r, 0, 0) == 0
+        else:
+            cid = self.L.fn("AddSocConstraint")(self.h, order, Af.shape[1], dptr(Af), dptr(cf))
+        self.cone_shapes.append((order + 1, 1))
+        return cid
+
+    def add_linear_incremental(self, A, c):
+        """CONEX_NewLinearInequality + per-entry updates (interfaces/conex.cc:318-329)."""
+        Af = fmat(A)
+        cf = np.array(c, dtype=np.float64).ravel()
+        cid = C.c_int(-1)
+        assert self.L.lib.CONEX_NewLinearInequality(self.h, Af.shape[0], C.byref(cid)) == 0
+        for r in range(Af.shape[0]):
+            assert self.L.lib.CONEX_UpdateAffineTerm(self.h, cid.value, float(cf[r]), r, 0, 0) == 0
+            for v in range(Af.shape[1]):
+                assert self.L.lib.CONEX_UpdateLinearOperator(self.h, cid.value, float(Af[r, v]), v, r, 0, 0) == 0
+        self.cone_shapes.append((Af.shape[0], 1))
+        return cid.value
+
+    def add_linear_inequalities(self, A, lb, ub):
+        """lb <= A y <= ub (CONEX_AddLinearInequalities, interfaces/conex.cc:190-215): equal bounds
+        become equality constraints, finite ones scaled inequality rows."""
+        Af = fmat(A)
+        lbf = np.ascontiguousarray(np.array(lb, dtype=np.float64).ravel())
+        ubf = np.ascontiguousarray(np.array(ub, dtype=np.float64).ravel())
+        r = self.L.lib.CONEX_AddLinearInequalities(self.h, dptr(Af), Af.shape[0], Af.shape[1], dptr(lbf),
+                                                   len(lbf), dptr(ubf), len(ubf))
+        eq = lbf == ubf
+        nin = int(((ubf < 1e8) & ~eq).sum() + ((lbf > -1e8) & ~eq).sum())
+        if nin:
+            self.cone_shapes.append((nin, 1))
+        if eq.any():
+            self.cone_shapes.append((0, 0))
+        return r
+
+    def add_equality(self, A, b, variables=None):
+        """A y[variables] = b (Program::AddConstraint(EqualityConstraints{A, b}[, vars]))."""
+        Af = fmat(A)
+        bf = np.ascontiguousarray(np.array(b, dtype=np.float64).ravel())
+        v = None if variables is None else (C.c_long * len(variables))(*variables)
+        cid = self.L.fn("AddEqualityConstraint")(self.h, Af.shape[0], Af.shape[1], dptr(Af), dptr(bf), v)
+        assert cid >= 0
+        self.cone_shapes.append((0, 0))
+        return cid
+
+    def kkt_size(self):
+        return self.L.fn("SizeOfKKTSystem")(self.h)
+
     def feasible_objective(self):
         b = np.zeros(self.m)
         self.L.fn("FeasibleObjective")(self.h, dptr(b))
@@ -227,7 +304,7 @@ class Program:
         return dict(zip(["assemble", "factor", "solve", "update", "mu"], buf.tolist()))
 
     def newton_system(self, coldstart=True):
-        m = self.m
+        m = self.kkt_size()
         H = np.zeros((m, m), order="F")
         AW = np.zeros(m)
         AQc = np.zeros(m)
@@ -274,6 +351,8 @@ def oracle():
         L.ORACLE_SetGramVariant.argtypes = [C.c_void_p, C.c_int]
         L.ORACLE_ForcePlainLoops.argtypes = [C.c_int]
         L.ORACLE_SetBlasThreads.argtypes = [C.c_int]
+        L.ORACLE_LdltLower.argtypes = [C.c_int, c_double_p, c_int_p]
+        L.ORACLE_SolveLdlt.argtypes = [C.c_int, c_double_p, c_int_p, c_double_p]
     return _oracle
 
 
