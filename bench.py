@@ -43,6 +43,7 @@ def algorithmic_flops(n, m):
 
 
 WORKLOADS = {
+    "c3": dict(kind="batched", n=20, m=40, programs=4096, cpu=dict(programs=128)),
     "c2": dict(kind="maxcut", n=2000, m=2000, cpu=dict(n=400, m=400)),
     "c5": dict(kind="random", n=1000, m=20000, cpu=dict(n=120, m=600)),
     "c4": dict(kind="lovasz", n=500, m=10001, cpu=dict(n=100, m=401)),
@@ -58,8 +59,11 @@ def workload_shape(args):
             w["m"] = args.n
     if args.m:
         w["m"] = args.m
+    if args.programs and w["kind"] == "batched":
+        w["programs"] = args.programs
     names = {"maxcut": "maxcut_sdp_n{n}_dense_lmi", "random": "dense_lmi_sdp_n{n}_m{m}",
-             "lovasz": "lovasz_theta_n{n}_m{m}"}
+             "lovasz": "lovasz_theta_n{n}_m{m}",
+             "batched": "batched_small_sdp_{programs}x(3xpsd20+2xsoc10+lp40)_m40"}
     w["name"] = names[w["kind"]].format(**w)
     return w
 
@@ -265,11 +269,166 @@ def cpu_baseline(w, steps, warmup, threads=None):
     }
 
 
+# ---- BASELINE config 3: many small multi-cone programs, batched per GPU ----------------------------
+def batched_flops_per_program_step(m=40, n=20, blocks=3):
+    """Dense algorithmic flops of one Newton step of one program: the PSD blocks
+    dominate (4 m n^3 + m(m+1) n^2 each), + m^3/3 for the KKT Cholesky."""
+    return blocks * (4.0 * m * n ** 3 + float(m) * (m + 1) * n ** 2) + m ** 3 / 3.0
+
+
+def batched_bytes_per_program_step(m=40, n=20, blocks=3):
+    """Algorithmic HBM bytes of the Schur kernel per program and step: the cone data read once and
+    the scaled matrices W A_i W written once and read once."""
+    return blocks * (m + 1) * n * n * 8.0 * 3
+
+
+def cpu_baseline_batched(w, count=None, threads=1):
+    """The oracle port solving a bounded sample of the batch one program after the other (what the
+    reference does), single BLAS thread (the matrices are 20 x 20)."""
+    from harness import add_cones, oracle, small_multicone_problem
+    O = oracle()
+    O.lib.ORACLE_SetBlasThreads(threads)
+    count = count or w["cpu"]["programs"]
+    steps, t_total = 0, 0.0
+    for p in range(count):
+        cones, b = small_multicone_problem(1000 + p)
+        P = O.program()
+        add_cones(P, cones)
+        t0 = time.perf_counter()
+        P.maximize(b)
+        t_total += time.perf_counter() - t0
+        steps += P.status()["num_iterations"]
+    per_program_step_ms = t_total / steps * 1e3
+    return {"value": per_program_step_ms * w["programs"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle port solving {count} of the {w['programs']} programs one after the other "
+                      f"({steps} Newton steps, {t_total:.2f} s, {per_program_step_ms:.3f} ms per program-step); "
+                      f"value = that x {w['programs']} programs (one lock-step Newton step of the whole batch)",
+            "sample_solve_s": t_total, "sample_programs": count,
+            "programs_per_s": count / t_total}
+
+
+def run_b200_batched(args):
+    import torch
+    import torch.distributed as dist
+    from harness import Batch, add_cones, small_multicone_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import devlib
+    dev = devlib.product()
+    L = dev.lib
+    assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
+    w = workload_shape(args)
+    total_programs = w["programs"]
+    lo = total_programs * rank // world
+    hi = total_programs * (rank + 1) // world
+    peak_tf = measure_fp64_peak() if rank == 0 else None
+
+    t_setup = time.perf_counter()
+    programs, bs = [], []
+    for p in range(lo, hi):
+        cones, b = small_multicone_problem(1000 + p)
+        P = dev.program()
+        add_cones(P, cones)
+        programs.append(P)
+        bs.append(b)
+    batch = Batch(dev, programs)
+    b = np.stack(bs)
+    del programs
+    setup_s = time.perf_counter() - t_setup
+
+    cfg = dev.default_config()
+    # warm-up solves (W >= 3 untimed Newton steps: one full solve is ~15), then the timed solve
+    batch.maximize(b, cfg)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.CONEXB200_LaunchCount()
+    t0 = time.perf_counter()
+    solved, y = batch.maximize(b, cfg)
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    launches = L.CONEXB200_LaunchCount() - launches0
+    clocks = sampler.stop()
+    its, by, cx, _ = batch.results()
+    step_ms = batch.step_milliseconds()
+    lock_steps = len(step_ms)
+    dev_ms = batch.milliseconds()
+    program_steps = int(its.sum())
+    t = torch.tensor([dev_ms, e2e_wall * 1e3, float(step_ms.mean())], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(program_steps), float(solved.sum()), float(hi - lo)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, mean_step_ms = float(t[0]), float(t[1]), float(t[2])
+    program_steps, nsolved, nprog = float(cnt[0]), int(cnt[1]), int(cnt[2])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    flops = batched_flops_per_program_step() * program_steps
+    bytes_ = batched_bytes_per_program_step() * program_steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6534.8))
+    line = {
+        "metric": METRIC, "value": mean_step_ms, "unit": UNIT, "n_gpus": world, "steps": lock_steps,
+        "warmup": lock_steps, "ms_per_step": mean_step_ms, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "programs": nprog, "m": 40,
+                   "path": "CONEXB200_BatchMaximize: all programs advance one Newton step per launch set, "
+                           "one CTA per program and cone",
+                   "l2": "a full solve (cone data 1.6 GB + scaled matrices 1.6 GB per step) separates repeats",
+                   "multi_gpu": (f"programs partitioned over {world} ranks, no collective" if world > 1 else "n/a"),
+                   "step": "one lock-step Newton step of the whole batch (mean over the solve; programs that "
+                           "have terminated are masked out of later steps)"},
+        "solve_ms": dev_ms, "programs_per_s": nprog / (dev_ms * 1e-3), "programs_solved": nsolved,
+        "program_steps": program_steps,
+        "step_tflops_fp64": flops / (dev_ms * 1e-3) / 1e12,
+        "roofline": {"bound": "hbm", "kernel": "SchurKernel (small_cones.cu: W A_i W and Gram of the 20x20 LMI blocks)",
+                     "achieved": bytes_ / (dev_ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                     "frac": bytes_ / (dev_ms * 1e-3) / 1e9 / (hbm_peak * world),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "B200_PROFILING.md fallback 6534.8 GB/s",
+                     "note": "whole-solve time, all kernels; the same work is 2 flop/byte-balanced: "
+                             f"{flops / (dev_ms * 1e-3) / 1e12:.2f} TFLOP/s FP64 (DFMA) vs {peak_tf:.1f} TFLOP/s cuBLAS DGEMM",
+                     "traffic": None},
+        "e2e": {"value": e2e_ms / max(lock_steps, 1), "unit": UNIT, "solve_ms": e2e_ms,
+                "h2d_bytes_per_step": 8.0 * 40 * nprog / max(lock_steps, 1) + 8.0 * 6 * nprog,
+                "d2h_bytes_per_step": 8.0 * 40 * nprog / max(lock_steps, 1) + 8.0 * (2 * 6 * 4 + 6) * nprog,
+                "note": "CONEXB200_BatchMaximize from host b to host y (wall clock / lock steps)"},
+        "gpu_launches": int(launches), "clocks": clocks, "setup_s": setup_s,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_batched(w)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = workload_shape(args)
+    if w["kind"] == "batched":
+        cb = cpu_baseline_batched(w, threads=1)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": w["name"], "programs": w["programs"]}, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
     cb = cpu_baseline(w, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -439,11 +598,14 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=0, help="override the PSD order n")
     ap.add_argument("--constraints", dest="m", type=int, default=0, help="override the number of constraints m")
     ap.add_argument("--assembly-mode", type=int, default=0, help="0 auto, 1 keep all W A_i W, 2 stream row panels")
+    ap.add_argument("--programs", type=int, default=0, help="c3: number of programs in the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif WORKLOADS[args.workload]["kind"] == "batched":
+        run_b200_batched(args)
     else:
         run_b200(args)
 

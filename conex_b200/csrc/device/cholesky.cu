@@ -54,15 +54,20 @@ __device__ __forceinline__ void BatchedCopy(int total, int tid, int nthreads, Lo
 // ---- 1. diagonal block ---------------------------------------------------------------------------
 // Factor the nb x nb (nb <= 128) block at H (ld) in place; lower triangle. One CTA of 512 threads.
 // Thread t owns row r = t % 128 and the columns c with c % 4 == t / 128.
+//
+// SIGNED = true factors a symmetric indefinite block as L S L^T with S = diag(+-1) ("signed
+// Cholesky" = LDL^T with D = S and the columns of L scaled by sqrt|d|): pivots with |d| <= 1e-9 are
+// replaced by +-1e-9 like Eigen::RLDLT (RLDLT.h:378-389) and reported through info[1]; it never fails.
+template <bool SIGNED>
 __global__ void __launch_bounds__(512) PotrfDiagKernel(int nb, double* H, long ld, int col0,
-                                                       int* info) {
+                                                       int* info, double* signs) {
   extern __shared__ double s[];  // s[c * P + r], P = 129
   constexpr int P = kNB + 1;
   __shared__ int failed;
   const int tid = threadIdx.x;
   const int r = tid & (kNB - 1);
   const int cg = tid >> 7;  // 0..3
-  if (*info != 0) return;   // an earlier block already failed
+  if (!SIGNED && *info != 0) return;  // an earlier block already failed
   if (tid == 0) failed = 0;
   BatchedCopy<8>(
       kNB * kNB, tid, 512,
@@ -73,8 +78,17 @@ __global__ void __launch_bounds__(512) PotrfDiagKernel(int nb, double* H, long l
       [&](int e, double v) { s[(e >> 7) * P + (e & (kNB - 1))] = v; });
   __syncthreads();
   for (int j = 0; j < nb; j++) {
-    const double d = s[j * P + j];
-    if (!(d > 0.0)) {  // every thread sees the same d: uniform branch
+    double d = s[j * P + j];
+    double sign = 1.0;
+    if (SIGNED) {
+      if (!(fabs(d) > 1e-9)) {
+        d = (d < 0) ? -1e-9 : 1e-9;
+        if (tid == 0) info[1] = 1;  // regularization_used
+      }
+      sign = (d < 0) ? -1.0 : 1.0;
+      if (tid == 0) signs[col0 + j] = sign;
+      d = fabs(d);
+    } else if (!(d > 0.0)) {  // every thread sees the same d: uniform branch
       if (tid == 0) {
         failed = 1;
         *info = col0 + j + 1;
@@ -83,17 +97,19 @@ __global__ void __launch_bounds__(512) PotrfDiagKernel(int nb, double* H, long l
     }
     const double rd = sqrt(d);
     const double inv = 1.0 / rd;
-    // l[r] for this thread's row (pre-scale value is still in s[j][r] until the barrier below)
+    // l[r] for this thread's row (pre-scale value is still in s[j][r] until the barrier below);
+    // signed: column j of L is sign * a_j / sqrt|d| and the update is sign * (a_r a_c / |d|)
     const double lr = (r > j && r < nb) ? s[j * P + r] * inv : 0.0;
     // trailing update of my row: s[c][r] -= l[r] * l[c] for j < c <= r, c in my column group
     if (r > j && r < nb) {
       int c = j + 1 + ((cg - (j + 1)) & 3);  // first c > j with c % 4 == cg
-      for (; c <= r; c += 4) s[c * P + r] -= lr * (s[j * P + c] * inv);
+      const double slr = SIGNED ? sign * lr : lr;
+      for (; c <= r; c += 4) s[c * P + r] -= slr * (s[j * P + c] * inv);
     }
     __syncthreads();  // all reads of the unscaled column j are done
     if (cg == 0 && r < nb) {
       if (r == j) s[j * P + j] = rd;
-      if (r > j) s[j * P + r] = lr;
+      if (r > j) s[j * P + r] = SIGNED ? sign * lr : lr;
     }
     __syncthreads();
   }
@@ -352,6 +368,49 @@ __global__ void __launch_bounds__(256) TrsvBwdStepKernel(int j0, int nb, const d
 }
 
 __global__ void ResetInfoKernel(int* info) { *info = 0; }
+__global__ void ResetInfo2Kernel(int* info) { info[0] = 0; info[1] = 0; }
+
+// After the panel solve Y = A21 L11^{-T} of the signed factorisation: keeps Y in `Yout` (rows x nb,
+// ld = rows) for the trailing update A22 -= Y (Y S)^T and stores L21 = Y S in place.
+__global__ void SignedPanelKernel(int rows, int nb, double* A21, long ld, const double* __restrict__ signs,
+                                  double* Yout) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= rows || c >= nb) return;
+  const double y = A21[(long)c * ld + r];
+  Yout[(long)c * rows + r] = y;
+  A21[(long)c * ld + r] = y * signs[c];
+}
+
+// Kp[i][j] = K[max(pi, pj)][min(pi, pj)], i >= j: the symmetric permutation P K P^T of a matrix
+// stored by its lower triangle.
+__global__ void SymPermuteLowerKernel(int N, const double* __restrict__ K, long ldk,
+                                      const int* __restrict__ perm, double* Kp, long ldp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= N || i < j) return;
+  const int pi = perm[i], pj = perm[j];
+  const int r = pi > pj ? pi : pj, c = pi > pj ? pj : pi;
+  Kp[(long)j * ldp + i] = K[(long)c * ldk + r];
+}
+
+// out[i] = in[perm[i]] (gather) or out[perm[i]] = in[i] (scatter)
+__global__ void PermuteVecKernel(int N, const int* __restrict__ perm, const double* __restrict__ in,
+                                 double* out, int scatter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (scatter) {
+    out[perm[i]] = in[i];
+  } else {
+    out[i] = in[perm[i]];
+  }
+}
+
+__global__ void ApplySignsKernel(int N, int nrhs, const double* __restrict__ signs, double* Z, long ldz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  for (int k = 0; k < nrhs; k++) Z[(long)k * ldz + i] *= signs[i];
+}
 
 constexpr size_t kDiagSmem = sizeof(double) * kNB * (kNB + 1);
 constexpr size_t kTrsmSmem = sizeof(double) * (kNB * kNB + kNB * 32 + 32);
@@ -361,7 +420,8 @@ constexpr size_t kTrsvSmem =
 void ConfigureOnce() {
   static bool configured = false;
   if (configured) return;
-  cudaFuncSetAttribute(PotrfDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
+  cudaFuncSetAttribute(PotrfDiagKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
+  cudaFuncSetAttribute(PotrfDiagKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
   cudaFuncSetAttribute(TrsmPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
   cudaFuncSetAttribute(TrsvFwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
   cudaFuncSetAttribute(TrsvBwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
@@ -377,7 +437,7 @@ int PotrfBlockColumn(cudaStream_t s, int m, int j0, int w, double* H, long ldh, 
   for (int i0 = j0; i0 < j0 + w; i0 += kNB) {
     const int nb = min(kNB, j0 + w - i0);
     double* Hii = H + (long)i0 * ldh + i0;
-    CountLaunch(); PotrfDiagKernel<<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info);
+    CountLaunch(); PotrfDiagKernel<false><<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info, nullptr);
     const int rows = m - i0 - nb;
     if (rows <= 0) continue;
     double* A21 = Hii + nb;
@@ -425,8 +485,9 @@ int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, i
   return LaunchStatus();
 }
 
-int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs) {
-  cudaStream_t s = AsStream(stream);
+// X <- L^{-T} S L^{-1} X; signs == nullptr means S = I (plain Cholesky solve).
+static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs,
+                          const double* signs) {
   if (m <= 0 || nrhs <= 0) return 0;
   if (nrhs > kMaxRhs) return -1;
   ConfigureOnce();
@@ -442,6 +503,9 @@ int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX,
     const int grid = rows > 0 ? (rows + kFwdRows - 1) / kFwdRows : 1;
     CountLaunch(); TrsvFwdStepKernel<<<grid, 256, kTrsvSmem, s>>>(m, j0, nb, dL, ldl, dX, ldx, Z, m, nrhs);
   }
+  if (signs) {
+    CountLaunch(); ApplySignsKernel<<<(m + 255) / 256, 256, 0, s>>>(m, nrhs, signs, Z, m);
+  }
   // backward: L^T x = z
   for (int k = nblk - 1; k >= 0; k--) {
     const int j0 = k * kNB, nb = min(kNB, m - j0);
@@ -449,6 +513,54 @@ int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX,
     CountLaunch(); TrsvBwdStepKernel<<<grid, 256, kTrsvSmem, s>>>(j0, nb, dL, ldl, Z, m, dX, ldx, nrhs);
   }
   cudaFreeAsync(Z, s);
+  return LaunchStatus();
+}
+
+int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs) {
+  return PotrsLowerImpl(AsStream(stream), m, dL, ldl, dX, ldx, nrhs, nullptr);
+}
+
+size_t cxb_ldlt_worksize(int N) { return (size_t)N * kNB + (size_t)N; }
+
+int cxb_sym_permute_lower(void* stream, int N, const double* dK, long ldk, const int* d_perm, double* dKp,
+                          long ldp) {
+  if (N <= 0) return 0;
+  dim3 grid((N + 127) / 128, N);
+  CountLaunch(); SymPermuteLowerKernel<<<grid, 128, 0, AsStream(stream)>>>(N, dK, ldk, d_perm, dKp, ldp);
+  return LaunchStatus();
+}
+
+int cxb_ldlt_lower(void* stream, int N, double* dK, long ldk, double* d_signs, double* d_work, int* d_info) {
+  cudaStream_t s = AsStream(stream);
+  if (N <= 0) return 0;
+  ConfigureOnce();
+  CountLaunch(); ResetInfo2Kernel<<<1, 1, 0, s>>>(d_info);
+  for (int i0 = 0; i0 < N; i0 += kNB) {
+    const int nb = min(kNB, N - i0);
+    double* Kii = dK + (long)i0 * ldk + i0;
+    CountLaunch(); PotrfDiagKernel<true><<<1, 512, kDiagSmem, s>>>(nb, Kii, ldk, i0, d_info, d_signs);
+    const int rows = N - i0 - nb;
+    if (rows <= 0) continue;
+    double* A21 = Kii + nb;
+    // d_info[0] stays 0 in signed mode, so the panel kernel's early-out never triggers
+    CountLaunch(); TrsmPanelKernel<<<(rows + kNB - 1) / kNB, kNB, kTrsmSmem, s>>>(nb, Kii, ldk, A21, rows, d_info);
+    dim3 grid((rows + 127) / 128, nb);
+    CountLaunch(); SignedPanelKernel<<<grid, 128, 0, s>>>(rows, nb, A21, ldk, d_signs + i0, d_work);
+    const int rc = DgemmEx(s, -1, 1, false, true, rows, rows, nb, -1.0, d_work, rows, 0, A21, ldk, 0, 1.0,
+                           dK + (long)(i0 + nb) * ldk + (i0 + nb), ldk, 0, 1, true, false, 0);
+    if (rc != 0) return rc;
+  }
+  return LaunchStatus();
+}
+
+int cxb_ldlt_solve(void* stream, int N, const double* dL, long ldl, const double* d_signs,
+                   const int* d_perm, double* dx, double* d_tmp) {
+  cudaStream_t s = AsStream(stream);
+  if (N <= 0) return 0;
+  CountLaunch(); PermuteVecKernel<<<(N + 255) / 256, 256, 0, s>>>(N, d_perm, dx, d_tmp, 0);
+  const int rc = PotrsLowerImpl(s, N, dL, ldl, d_tmp, N, 1, d_signs);
+  if (rc != 0) return rc;
+  CountLaunch(); PermuteVecKernel<<<(N + 255) / 256, 256, 0, s>>>(N, d_perm, d_tmp, dx, 1);
   return LaunchStatus();
 }
 

@@ -1,0 +1,649 @@
+// Per-problem arithmetic of the small cones — LP cone, second-order cone, small dense PSD/LMI
+// block — and of the small dense KKT system, written once against a "team" (team.cuh): every
+// function below is executed by ONE CTA on ONE cone of ONE program; the kernels in small_cones.cu
+// map blockIdx.x to the program of a batch. Used by
+//   * the batched solver (many small multi-cone programs in lock step, BASELINE config 3), and
+//   * the single-program LP / SOC plugins (batch of one).
+//
+// Reference arithmetic restated here (column-major FP64 throughout):
+//   LP   conex/linear_constraint.cc:105-205        SOC  conex/soc_constraint.cc:115-262
+//   PSD  conex/psd_constraint.cc:13-128, conex/dense_lmi_constraint.cc:8-103,
+//        conex/exponential_map_pade.cc:10-32, conex/approximate_eigenvalues.cc:173-256
+//   KKT  conex/block_triangular_operations.cc:114-219 (one dense supernode)
+//
+// Data layout of a cone with `rows` slack entries per variable (LP: n, SOC: n + 1, PSD: n * n):
+//   data  = rows x (m + 1) column-major, columns 0..m-1 the operator, column m the affine term.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define CXB_HD __device__ __forceinline__
+#else
+#define CXB_HD inline
+#endif
+
+namespace cxb {
+namespace small {
+
+CXB_HD void Accumulate(double* dst, double v, bool acc) { *dst = acc ? *dst + v : v; }
+
+// out[r] = sum_j data[r + j * rows] y[j] - k * data[r + m * rows]
+template <class T>
+CXB_HD void NegativeSlack(T& t, int rows, int m, const double* data, const double* y, double k,
+                          double* out) {
+  t.par(rows, [&](int r) {
+    double s = 0;
+    for (int j = 0; j < m; j++) s += data[(long)j * rows + r] * y[j];
+    out[r] = s - k * data[(long)m * rows + r];
+  });
+}
+
+// =================================================================================================
+// LP cone. state: W[n], t1[n], t2[n].
+// =================================================================================================
+template <class T>
+CXB_HD void LpSchur(T& t, int n, int m, const double* Ac, const double* W, double* G, long ldg,
+                    double* AW, double* AQc, double* scal, bool acc) {
+  const double* c = Ac + (long)m * n;
+  t.par(m * m, [&](int e) {
+    const int i = e % m, j = e / m;
+    if (i < j) return;
+    const double* ai = Ac + (long)i * n;
+    const double* aj = Ac + (long)j * n;
+    double s = 0;
+    for (int r = 0; r < n; r++) {
+      const double w = W[r];
+      s += (w * ai[r]) * (w * aj[r]);
+    }
+    Accumulate(G + (long)j * ldg + i, s, acc);
+  });
+  t.par(m, [&](int j) {
+    const double* aj = Ac + (long)j * n;
+    double aw = 0, aq = 0;
+    for (int r = 0; r < n; r++) {
+      const double w = W[r];
+      aw += aj[r] * w;
+      aq += (w * aj[r]) * (w * c[r]);
+    }
+    Accumulate(AW + j, aw, acc);
+    Accumulate(AQc + j, aq, acc);
+  });
+  const double s1 = t.sum(n, [&](int r) { return W[r] * c[r]; });
+  const double s2 = t.sum(n, [&](int r) {
+    const double v = W[r] * c[r];
+    return v * v;
+  });
+  t.single([&]() {
+    Accumulate(scal + 0, s1, acc);
+    Accumulate(scal + 1, s2, acc);
+  });
+}
+
+// out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} (linear_constraint.cc:148-166)
+template <class T>
+CXB_HD void LpEigen(T& t, int n, int m, const double* Ac, const double* y, double cw, const double* W,
+                    double* t1, double* t2, double* out4) {
+  NegativeSlack(t, n, m, Ac, y, cw, t1);
+  t.par(n, [&](int r) { t2[r] = W[r] * t1[r]; });
+  const double mn = t.minv(n, [&](int r) { return t2[r]; });
+  const double mx = t.maxv(n, [&](int r) { return t2[r]; });
+  const double sq = t.sum(n, [&](int r) { return t2[r] * t2[r]; });
+  const double sm = t.sum(n, [&](int r) { return t2[r]; });
+  t.single([&]() {
+    out4[0] = -mx;
+    out4[1] = -mn;
+    out4[2] = sq;
+    out4[3] = -sm;
+  });
+}
+
+// out2 = {norminfd, normsqrd} (linear_constraint.cc:108-129, affine branch :174-179)
+template <class T>
+CXB_HD void LpPrepare(T& t, int n, int m, const double* Ac, const double* y, bool affine, double cw,
+                      double ew, double* W, double* t1, double* t2, double* out2) {
+  if (!affine) {
+    NegativeSlack(t, n, m, Ac, y, cw, t2);
+    t.par(n, [&](int r) { t2[r] = t2[r] * W[r] + ew; });
+    const double ninf = t.maxv(n, [&](int r) { return fabs(t2[r]); });
+    const double nsq = t.sum(n, [&](int r) { return t2[r] * t2[r]; });
+    t.single([&]() {
+      out2[0] = ninf;
+      out2[1] = nsq;
+    });
+  } else {
+    NegativeSlack(t, n, m, Ac, y, 0.0, t1);
+    t.par(n, [&](int r) {
+      const double sw = t1[r] * W[r];
+      t1[r] = sw;
+      W[r] += W[r] * sw;
+    });
+    t.single([&]() {
+      out2[0] = 0;
+      out2[1] = 0;
+    });
+  }
+}
+
+// W <- W .* exp(step * d), d = t2 (linear_constraint.cc:131-145)
+template <class T>
+CXB_HD void LpTakeStep(T& t, int n, double step, double* W, double* t2) {
+  t.par(n, [&](int r) {
+    double d = t2[r];
+    if (step != 1.0) d *= step;
+    d = exp(d);
+    t2[r] = d;
+    W[r] *= d;
+  });
+}
+
+// =================================================================================================
+// Second-order cone of order o = n + 1 (spin factor). state: Wv[o] = (W0, W1), d[o].
+// work: o * (m + 1) + 3 * o doubles.
+// =================================================================================================
+// out = f(ev0) c0 + f(ev1) c1 with the spectral decomposition of x (soc_constraint.cc:22-63,131-170);
+// fn: 0 sqrt, 1 exp. out must not alias x.
+template <class T>
+CXB_HD void SpinFunction(T& t, int o, const double* x, int fn, double* out) {
+  const double nq = sqrt(t.sum(o - 1, [&](int i) { return x[1 + i] * x[1 + i]; }));
+  const double e0 = x[0] + nq, e1 = x[0] - nq;
+  const double f0 = fn ? exp(e0) : sqrt(e0);
+  const double f1 = fn ? exp(e1) : sqrt(e1);
+  t.par(o, [&](int i) {
+    if (i == 0) {
+      out[0] = f0 * .5 + f1 * .5;
+    } else {
+      const double q = (nq > 0) ? x[i] / nq : 0.0;
+      out[i] = f0 * (.5 * q) + f1 * (-.5 * q);
+    }
+  });
+}
+
+// det x = x0^2 - |x1|^2
+template <class T>
+CXB_HD double SpinDet(T& t, int o, const double* x) {
+  return x[0] * x[0] - t.sum(o - 1, [&](int i) { return x[1 + i] * x[1 + i]; });
+}
+
+// out = Q(x) y = 2 <x, y> x - det(x) R y (soc_constraint.cc:115-128); serial, one thread.
+CXB_HD void QuadRepSerial(int o, const double* x, double det, const double* y, double* out) {
+  double xy = 0;
+  for (int i = 0; i < o; i++) xy += x[i] * y[i];
+  for (int i = 0; i < o; i++) {
+    double z = det * y[i];
+    if (i == 0) z *= -1;
+    out[i] = (2 * xy) * x[i] + z;
+  }
+}
+// Same by the whole team; out must not alias x or y.
+template <class T>
+CXB_HD void QuadRep(T& t, int o, const double* x, const double* y, double* out) {
+  const double det = SpinDet(t, o, x);
+  const double xy = t.sum(o, [&](int i) { return x[i] * y[i]; });
+  t.par(o, [&](int i) {
+    double z = det * y[i];
+    if (i == 0) z *= -1;
+    out[i] = (2 * xy) * x[i] + z;
+  });
+}
+
+template <class T>
+CXB_HD void SocSetIdentity(T& t, int o, double* Wv) {
+  t.par(o, [&](int i) { Wv[i] = (i == 0) ? 1.0 : 0.0; });
+}
+
+template <class T>
+CXB_HD void SocSchur(T& t, int o, int m, const double* Ac, const double* Wv, double* work, double* G,
+                     long ldg, double* AW, double* AQc, double* scal, bool acc) {
+  double* wsqrt = work;
+  double* WA = work + o;  // o x (m + 1); column m = Q(w^{1/2}) c
+  SpinFunction(t, o, Wv, 0, wsqrt);
+  const double det = SpinDet(t, o, wsqrt);
+  t.par(m + 1, [&](int j) { QuadRepSerial(o, wsqrt, det, Ac + (long)j * o, WA + (long)j * o); });
+  const double* WC = WA + (long)m * o;
+  t.par(m * m, [&](int e) {
+    const int i = e % m, j = e / m;
+    if (i < j) return;
+    double s = 0;
+    for (int r = 0; r < o; r++) s += WA[(long)i * o + r] * WA[(long)j * o + r];
+    Accumulate(G + (long)j * ldg + i, 2 * s, acc);
+  });
+  t.par(m, [&](int j) {
+    double aw = 0, aq = 0;
+    for (int r = 0; r < o; r++) {
+      aw += Ac[(long)j * o + r] * Wv[r];
+      aq += WA[(long)j * o + r] * WC[r];
+    }
+    Accumulate(AW + j, 2 * aw, acc);
+    Accumulate(AQc + j, 2 * aq, acc);
+  });
+  const double sq = t.sum(o, [&](int r) { return WC[r] * WC[r]; });
+  t.single([&]() {
+    Accumulate(scal + 0, 2 * WC[0], acc);
+    Accumulate(scal + 1, 2 * sq, acc);
+  });
+}
+
+template <class T>
+CXB_HD void SocEigen(T& t, int o, int m, const double* Ac, const double* y, double cw, const double* Wv,
+                     double* work, double* out4) {
+  double* minus_s = work;
+  double* wsqrt = work + o;
+  double* Ws = work + 2 * o;
+  NegativeSlack(t, o, m, Ac, y, cw, minus_s);
+  SpinFunction(t, o, Wv, 0, wsqrt);
+  QuadRep(t, o, wsqrt, minus_s, Ws);
+  const double nq = sqrt(t.sum(o - 1, [&](int i) { return Ws[1 + i] * Ws[1 + i]; }));
+  t.single([&]() {
+    const double ev0 = Ws[0] + nq, ev1 = Ws[0] - nq;
+    const double lmax = -fmin(ev0, ev1), lmin = -fmax(ev0, ev1);
+    out4[0] = lmin;
+    out4[1] = lmax;
+    out4[2] = lmax * lmax + lmin * lmin;
+    out4[3] = lmax + lmin;
+  });
+}
+
+// NB (soc_constraint.cc:213-230): W is replaced by its square root, e_weight / affine are ignored.
+template <class T>
+CXB_HD void SocPrepare(T& t, int o, int m, const double* Ac, const double* y, double cw, double* Wv,
+                       double* d, double* work, double* out2) {
+  double* minus_s = work;
+  double* wsqrt = work + o;
+  NegativeSlack(t, o, m, Ac, y, cw, minus_s);
+  SpinFunction(t, o, Wv, 0, wsqrt);
+  QuadRep(t, o, wsqrt, minus_s, d);
+  t.par(o, [&](int i) {
+    Wv[i] = wsqrt[i];
+    if (i == 0) d[0] += 1;
+  });
+  const double nq = sqrt(t.sum(o - 1, [&](int i) { return d[1 + i] * d[1 + i]; }));
+  const double sq = t.sum(o, [&](int i) { return d[i] * d[i]; });
+  t.single([&]() {
+    out2[0] = fmax(fabs(d[0] + nq), fabs(d[0] - nq));
+    out2[1] = 2 * sq;
+  });
+}
+
+// W <- Q(w^{1/2}) exp(step * d)  (soc_constraint.cc:191-211; Wv already holds w^{1/2})
+template <class T>
+CXB_HD void SocTakeStep(T& t, int o, double step, double* Wv, const double* d, double* work) {
+  double* ds = work;
+  double* expd = work + o;
+  double* wn = work + 2 * o;
+  t.par(o, [&](int i) { ds[i] = (step != 1.0) ? d[i] * step : d[i]; });
+  SpinFunction(t, o, ds, 1, expd);
+  QuadRep(t, o, Wv, expd, wn);
+  t.par(o, [&](int i) { Wv[i] = wn[i]; });
+}
+
+// =================================================================================================
+// Small dense PSD / LMI block of order n (n*n doubles per matrix fit in shared memory).
+// state: W, T1, T2 (n*n each, global). sm: shared scratch of 6 n*n + 8 n + 16 doubles.
+// work (global): (m + 1) n*n doubles for the scaled matrices W A_i W, W C W.
+// =================================================================================================
+// C = A * B (n x n, column-major, all three distinct)
+template <class T>
+CXB_HD void MatMul(T& t, int n, const double* A, const double* B, double* C) {
+  t.par(n * n, [&](int e) {
+    const int r = e % n, c = e / n;
+    double s = 0;
+    for (int k = 0; k < n; k++) s += A[k * n + r] * B[c * n + k];
+    C[e] = s;
+  });
+}
+
+template <class T>
+CXB_HD void PsdSetIdentity(T& t, int n, double* W) {
+  t.par(n * n, [&](int e) { W[e] = (e % n == e / n) ? 1.0 : 0.0; });
+}
+
+// H_ij = <W A_i W, A_j> (lower), AW_j = <W, A_j>, AQc_j = <W C W, A_j>, <w,c> = <W, C>,
+// <c,Qc> = <W C W, C>  (dense_lmi_constraint.cc:62-103)
+template <class T>
+CXB_HD void PsdSchur(T& t, int n, int m, const double* AC, const double* W, double* work, double* sm,
+                     double* G, long ldg, double* AW, double* AQc, double* scal, bool acc) {
+  const int nn = n * n;
+  double* sW = sm;
+  double* sA = sm + nn;
+  double* sT = sm + 2 * nn;
+  t.par(nn, [&](int e) { sW[e] = W[e]; });
+  for (int i = 0; i <= m; i++) {
+    const double* Ai = AC + (long)i * nn;
+    t.par(nn, [&](int e) { sA[e] = Ai[e]; });
+    MatMul(t, n, sA, sW, sT);                   // T = A_i W
+    MatMul(t, n, sW, sT, work + (long)i * nn);  // B_i = W T
+  }
+  // rows i = 0..m+1 of the augmented Gram (row m: W C W, row m+1: W), columns j = 0..m
+  t.par((m + 2) * (m + 1), [&](int e) {
+    const int i = e % (m + 2), j = e / (m + 2);
+    if (i < j) return;
+    const double* Bi = (i <= m) ? work + (long)i * nn : sW;
+    const double* Aj = AC + (long)j * nn;
+    double s = 0;
+    for (int q = 0; q < nn; q++) s += Bi[q] * Aj[q];
+    if (i < m) {
+      Accumulate(G + (long)j * ldg + i, s, acc);
+    } else if (i == m) {
+      Accumulate(j < m ? AQc + j : scal + 1, s, acc);
+    } else {
+      Accumulate(j < m ? AW + j : scal + 0, s, acc);
+    }
+  });
+}
+
+// Extreme eigenvalues of the symmetric tridiagonal (alpha[0..k), beta[0..k-1)) by Sturm bisection —
+// device twin of host/tridiagonal_eigenvalues.cc (the reference takes min/max of the full spectrum,
+// approximate_eigenvalues.cc:235-237). Serial.
+CXB_HD int SturmCountBelow(const double* a, const double* b, int k, double x, double tiny) {
+  int count = 0;
+  double q = 1;
+  for (int i = 0; i < k; i++) {
+    const double off = (i == 0) ? 0.0 : (b[i - 1] * b[i - 1]) / q;
+    q = a[i] - x - off;
+    if (fabs(q) < tiny) q = -tiny;
+    if (q < 0) count++;
+  }
+  return count;
+}
+CXB_HD double SturmKth(const double* a, const double* b, int k, int which, double lo, double hi,
+                       double tiny) {
+  for (int it = 0; it < 200; it++) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    if (SturmCountBelow(a, b, k, mid, tiny) > which) {
+      hi = mid;
+    } else {
+      lo = mid;
+    }
+  }
+  return 0.5 * (lo + hi);
+}
+CXB_HD void ExtremeTridiagonal(const double* a, const double* b, int k, double* emin, double* emax) {
+  if (k == 1) {
+    *emin = *emax = a[0];
+    return;
+  }
+  const double eps = 2.220446049250313e-16;
+  double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308, scale = 0;
+  for (int i = 0; i < k; i++) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < k ? fabs(b[i]) : 0.0);
+    lo = fmin(lo, a[i] - r);
+    hi = fmax(hi, a[i] + r);
+    scale = fmax(scale, fabs(a[i]) + r);
+  }
+  const double pad = 4 * eps * (scale + 1e-300) * (double)k;
+  lo -= pad;
+  hi += pad;
+  double tiny = 2.2250738585072014e-308 / eps + 1e-30 * scale * scale;
+  tiny = fmax(tiny, eps * eps * scale);
+  *emin = SturmKth(a, b, k, 0, lo, hi, tiny);
+  *emax = SturmKth(a, b, k, k - 1, lo, hi, tiny);
+}
+
+// Two-sided Lanczos on (WS, WS^T) in the W inner product started from r
+// (approximate_eigenvalues.cc:178-239, num_iter = n/2, breakdown beta^2 < 1e-6), then the extreme
+// Ritz values. vec: 6 n + 2 (n/2 + 2) doubles of scratch. Returns through ritz[0..1].
+template <class T>
+CXB_HD void LanczosExtremes(T& t, int n, const double* WS, const double* W, const double* r, double* vec,
+                            double* ritz) {
+  double *v0 = vec, *v1 = vec + n, *u0 = vec + 2 * n, *u1 = vec + 3 * n, *p0 = vec + 4 * n,
+         *p1 = vec + 5 * n;
+  double* alpha = vec + 6 * n;
+  double* beta = alpha + n / 2 + 2;
+  const int num_iter = n / 2;
+  if (n == 1 || num_iter < 1) {  // ApproximateEigenvalues returns WS itself (:248-250)
+    t.single([&]() { ritz[0] = ritz[1] = WS[0]; });
+    return;
+  }
+  t.par(n, [&](int i) {
+    double s = 0;
+    for (int k = 0; k < n; k++) s += W[k * n + i] * r[k];
+    v0[i] = s;
+    v1[i] = r[i];
+  });
+  const double scale = sqrt(t.sum(n, [&](int i) { return v0[i] * v1[i]; }));
+  t.par(n, [&](int i) {
+    v0[i] /= scale;
+    v1[i] /= scale;
+  });
+  int count = 0;
+  double bprev = 0;
+  for (int j = 0; j < num_iter; j++) {
+    t.par(n, [&](int i) {
+      double a0 = 0, a1 = 0;
+      for (int k = 0; k < n; k++) {
+        a0 += WS[k * n + i] * v0[k];  // (WS v0)[i]
+        a1 += WS[i * n + k] * v1[k];  // (WS^T v1)[i]
+      }
+      u0[i] = a0;
+      u1[i] = a1;
+    });
+    const double a = t.sum(n, [&](int i) { return v0[i] * u1[i]; });
+    t.par(n, [&](int i) {
+      double x0 = u0[i] - a * v0[i], x1 = u1[i] - a * v1[i];
+      if (j > 0) {
+        x0 -= bprev * p0[i];
+        x1 -= bprev * p1[i];
+      }
+      u0[i] = x0;
+      u1[i] = x1;
+    });
+    const double b2 = t.sum(n, [&](int i) { return u0[i] * u1[i]; });
+    t.single([&]() { alpha[j] = a; });
+    count = j;
+    if (j + 1 >= num_iter || b2 < 1e-6) break;
+    const double bj = sqrt(b2);
+    t.par(n, [&](int i) {
+      p0[i] = v0[i];
+      p1[i] = v1[i];
+      v0[i] = u0[i] / bj;
+      v1[i] = u1[i] / bj;
+    });
+    t.single([&]() { beta[j] = bj; });
+    bprev = bj;
+  }
+  t.single([&]() { ExtremeTridiagonal(alpha, beta, count + 1, ritz + 0, ritz + 1); });
+}
+
+// S -> T1, WS = W S -> T2 (global state) and shared copies; returns tr(WS), tr(WS WS) and the
+// index of the largest diagonal entry of WS (first occurrence).
+// sm layout: sW | sS | sWS | vec...
+template <class T>
+CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double* y, double cw,
+                             const double* W, double* T1, double* T2, double* sm, double* trace,
+                             double* trace_sq, int* index) {
+  const int nn = n * n;
+  double* sW = sm;
+  double* sS = sm + nn;
+  double* sWS = sm + 2 * nn;
+  t.par(nn, [&](int e) { sW[e] = W[e]; });
+  NegativeSlack(t, nn, m, AC, y, cw, sS);
+  MatMul(t, n, sW, sS, sWS);
+  t.par(nn, [&](int e) {
+    T1[e] = sS[e];
+    T2[e] = sWS[e];
+  });
+  *trace = t.sum(n, [&](int i) { return sWS[i * n + i]; });
+  *trace_sq = t.sum(nn, [&](int e) { return sWS[e] * sWS[(e % n) * n + e / n]; });
+  *index = (int)t.bcast([&]() {
+    int best = 0;
+    for (int i = 1; i < n; i++)
+      if (sWS[i * n + i] > sWS[best * n + best]) best = i;
+    return (double)best;
+  });
+}
+
+// out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} (psd_constraint.cc:97-128)
+template <class T>
+CXB_HD void PsdEigen(T& t, int n, int m, const double* AC, const double* y, double cw, const double* W,
+                     double* T1, double* T2, double* sm, double* out4) {
+  const int nn = n * n;
+  double tr, trsq;
+  int index;
+  PsdWeightedSlack(t, n, m, AC, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
+  double* ritz = sm + 3 * nn;
+  // start vector: column `index` of the true -S
+  LanczosExtremes(t, n, sm + 2 * nn, sm, sm + nn + index * n, sm + 3 * nn + 2, ritz);
+  t.single([&]() {
+    out4[0] = -ritz[1];
+    out4[1] = -ritz[0];
+    out4[2] = trsq;
+    out4[3] = -tr;
+  });
+}
+
+// out2 = {norminfd, normsqrd} (psd_constraint.cc:45-84); affine: W <- (1 + ew) W + (W S) W (:33-43)
+template <class T>
+CXB_HD void PsdPrepare(T& t, int n, int m, const double* AC, const double* y, bool affine, double cw,
+                       double ew, double* W, double* T1, double* T2, double* sm, double* out2) {
+  const int nn = n * n;
+  double tr, trsq;
+  int index;
+  PsdWeightedSlack(t, n, m, AC, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
+  if (affine) {
+    double* sT = sm + nn;  // the slack is no longer needed
+    MatMul(t, n, sm + 2 * nn, sm, sT);
+    t.par(nn, [&](int e) {
+      double w = sm[e];
+      if (ew != 0.0) w *= (1.0 + ew);
+      W[e] = w + sT[e];
+    });
+    t.single([&]() {
+      out2[0] = 0;
+      out2[1] = 0;
+    });
+    return;
+  }
+  double* ritz = sm + 3 * nn;
+  // the reference starts from a column of WS here (minus_s aliases WS, psd_constraint.cc:48-69)
+  LanczosExtremes(t, n, sm + 2 * nn, sm, sm + 2 * nn + index * n, sm + 3 * nn + 2, ritz);
+  t.single([&]() {
+    out2[0] = fmax(fabs(ew + ritz[0]), fabs(ew + ritz[1]));
+    out2[1] = trsq + 2 * tr + n;
+  });
+}
+
+// W <- sym( pade33( step (WS + ew I) ) W ), WS = T2 (psd_constraint.cc:13-28,
+// exponential_map_pade.cc:10-32). sm: 6 n*n doubles. info: set to 1 + column on a zero pivot.
+template <class T>
+CXB_HD void PsdTakeStep(T& t, int n, double step, double ew, double* W, const double* T2, double* sm,
+                        int* info) {
+  const int nn = n * n;
+  double* X = sm;
+  double* X2 = sm + nn;
+  double* U = sm + 2 * nn;
+  double* M = sm + 3 * nn;  // n x 2n: [V - U | V + U]
+  double* sW = sm + 5 * nn;
+  t.par(nn, [&](int e) {
+    X[e] = (T2[e] + ((e % n == e / n) ? ew : 0.0)) * step;
+    sW[e] = W[e];
+  });
+  MatMul(t, n, X, X, X2);
+  t.par(nn, [&](int e) { M[e] = X2[e] + ((e % n == e / n) ? 60.0 : 0.0); });
+  MatMul(t, n, X, M, U);  // U = X (X^2 + 60 I)
+  t.par(nn, [&](int e) {
+    const double v = 12.0 * X2[e] + ((e % n == e / n) ? 120.0 : 0.0);
+    const double u = U[e];
+    M[e] = v - u;
+    M[nn + e] = v + u;
+  });
+  // Gaussian elimination with partial (row) pivoting on the n x 2n augmented matrix
+  for (int k = 0; k < n; k++) {
+    const int p = (int)t.bcast([&]() {
+      int best = k;
+      double bv = fabs(M[k * n + k]);
+      for (int i = k + 1; i < n; i++) {
+        const double v = fabs(M[k * n + i]);
+        if (v > bv) {
+          bv = v;
+          best = i;
+        }
+      }
+      if (bv == 0.0 && *info == 0) *info = k + 1;
+      return (double)best;
+    });
+    if (p != k) {
+      t.par(2 * n, [&](int c) {
+        const double tmp = M[c * n + k];
+        M[c * n + k] = M[c * n + p];
+        M[c * n + p] = tmp;
+      });
+    }
+    const double piv = M[k * n + k];
+    t.par(n - k - 1, [&](int i) { M[k * n + k + 1 + i] /= piv; });
+    t.par((n - k - 1) * (2 * n - k - 1), [&](int e) {
+      const int i = k + 1 + e % (n - k - 1), c = k + 1 + e / (n - k - 1);
+      M[c * n + i] -= M[k * n + i] * M[c * n + k];
+    });
+  }
+  // back substitution, one right-hand-side column per thread
+  t.par(n, [&](int c) {
+    double* b = M + nn + c * n;
+    for (int i = n - 1; i >= 0; i--) {
+      double s = b[i];
+      for (int k = i + 1; k < n; k++) s -= M[k * n + i] * b[k];
+      b[i] = s / M[i * n + i];
+    }
+  });
+  MatMul(t, n, M + nn, sW, X);  // E W
+  t.par(nn, [&](int e) { W[e] = 0.5 * (X[e] + X[(e % n) * n + e / n]); });
+}
+
+// =================================================================================================
+// Small dense KKT system (N x N lower, ld): Cholesky in shared memory and the two triangular solves.
+// =================================================================================================
+// sH: N*N doubles of shared memory. info: 0 or 1 + column of the first non-positive pivot.
+template <class T>
+CXB_HD void SmallPotrf(T& t, int N, double* H, long ld, double* sH, int* info) {
+  t.par(N * N, [&](int e) {
+    const int r = e % N, c = e / N;
+    sH[e] = (r >= c) ? H[(long)c * ld + r] : 0.0;
+  });
+  int failed = 0;
+  for (int j = 0; j < N; j++) {
+    // The diagonal keeps the pivot d_j until the end (every thread reads it here, so nobody may
+    // overwrite it in this phase); its square root is taken in one sweep after the loop.
+    const double d = sH[j * N + j];
+    if (!(d > 0.0)) {
+      failed = j + 1;
+      break;
+    }
+    const double rd = sqrt(d);
+    t.par(N - j - 1, [&](int i) { sH[j * N + j + 1 + i] /= rd; });
+    const int w = N - j - 1;
+    t.par(w * w, [&](int e) {
+      const int r = j + 1 + e % w, c = j + 1 + e / w;
+      if (r >= c) sH[c * N + r] -= sH[j * N + r] * sH[j * N + c];
+    });
+  }
+  if (failed) {
+    t.single([&]() { *info = failed; });
+    return;
+  }
+  t.par(N * N, [&](int e) {
+    const int r = e % N, c = e / N;
+    if (r > c) H[(long)c * ld + r] = sH[e];
+    if (r == c) H[(long)c * ld + r] = sqrt(sH[e]);
+  });
+  t.single([&]() { *info = 0; });
+}
+
+// x <- L^{-T} L^{-1} x. sx: N doubles shared.
+template <class T>
+CXB_HD void SmallPotrs(T& t, int N, const double* L, long ld, double* x, double* sx) {
+  t.par(N, [&](int i) { sx[i] = x[i]; });
+  for (int j = 0; j < N; j++) {
+    // sx[j] is final here and is not written in this phase (it is divided by L_jj afterwards)
+    const double xj = sx[j] / L[(long)j * ld + j];
+    t.par(N - j - 1, [&](int i) { sx[j + 1 + i] -= L[(long)j * ld + j + 1 + i] * xj; });
+  }
+  t.par(N, [&](int j) { sx[j] /= L[(long)j * ld + j]; });
+  for (int j = N - 1; j >= 0; j--) {
+    const double s = t.sum(N - j - 1, [&](int i) { return L[(long)j * ld + j + 1 + i] * sx[j + 1 + i]; });
+    t.single([&]() { sx[j] = (sx[j] - s) / L[(long)j * ld + j]; });
+  }
+  t.par(N, [&](int i) { x[i] = sx[i]; });
+}
+
+}  // namespace small
+}  // namespace cxb

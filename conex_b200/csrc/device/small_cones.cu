@@ -1,0 +1,330 @@
+// Small cones, batched: one CTA per program of a batch; all per-problem arithmetic lives in
+// small_cone_math.cuh (LP cone, second-order cone, small dense LMI block, small dense KKT system).
+// This file only maps blockIdx.x to the program, carves shared memory and exports the C entry
+// points declared in include/conex_b200_device.h.
+#include "common.cuh"
+#include "device_api.h"
+#include "small_cone_math.cuh"
+#include "team.cuh"
+
+namespace cxb {
+namespace {
+
+constexpr int kThreads = 128;
+
+__host__ __device__ inline long Align4(long n) { return (n + 3) & ~3L; }
+
+struct ConeArgs {
+  int type, n, m;
+  const double* data;
+  long data_stride;
+  double* state;
+  long state_stride;
+  double* work;
+  long work_stride;
+};
+
+ConeArgs Convert(const cxb_small_cone* c) {
+  return ConeArgs{c->type, c->n, c->m, c->data, c->data_stride, c->state, c->state_stride, c->work,
+                  c->work_stride};
+}
+
+// Shared memory (doubles) needed by the PSD paths: 6 n^2 matrices + Lanczos vectors + slack.
+size_t PsdSmemDoubles(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64; }
+size_t SmemBytes(const ConeArgs& c) {
+  return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? PsdSmemDoubles(c.n) : 0));
+}
+
+__global__ void __launch_bounds__(kThreads) SetIdentityKernel(ConeArgs c, const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  double* st = c.state + p * c.state_stride;
+  if (c.type == CXB_CONE_LP) {
+    t.par(c.n, [&](int i) { st[i] = 1.0; });
+  } else if (c.type == CXB_CONE_SOC) {
+    small::SocSetIdentity(t, c.n + 1, st);
+  } else {
+    small::PsdSetIdentity(t, c.n, st);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) SchurKernel(ConeArgs c, double* G, long ldg, long gstride,
+                                                        double* AW, double* AQc, long vstride,
+                                                        double* scal, long sstride, int accumulate,
+                                                        const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  const double* data = c.data + p * c.data_stride;
+  double* st = c.state + p * c.state_stride;
+  double* work = c.work ? c.work + p * c.work_stride : nullptr;
+  double* g = G + p * gstride;
+  double* aw = AW + p * vstride;
+  double* aq = AQc + p * vstride;
+  double* sc = scal + p * sstride;
+  const bool acc = accumulate != 0;
+  if (c.type == CXB_CONE_LP) {
+    small::LpSchur(t, c.n, c.m, data, st, g, ldg, aw, aq, sc, acc);
+  } else if (c.type == CXB_CONE_SOC) {
+    small::SocSchur(t, c.n + 1, c.m, data, st, work, g, ldg, aw, aq, sc, acc);
+  } else {
+    small::PsdSchur(t, c.n, c.m, data, st, work, sm + 64, g, ldg, aw, aq, sc, acc);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) EigenKernel(ConeArgs c, const double* y, long ystride,
+                                                        double cw, const double* cw_p, double* out4,
+                                                        long ostride, const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  const double* data = c.data + p * c.data_stride;
+  double* st = c.state + p * c.state_stride;
+  double* work = c.work ? c.work + p * c.work_stride : nullptr;
+  const double* yp = y + p * ystride;
+  const double k = cw_p ? cw_p[p] : cw;
+  double* out = out4 + p * ostride;
+  if (c.type == CXB_CONE_LP) {
+    const long np = Align4(c.n);
+    small::LpEigen(t, c.n, c.m, data, yp, k, st, st + np, st + 2 * np, out);
+  } else if (c.type == CXB_CONE_SOC) {
+    small::SocEigen(t, c.n + 1, c.m, data, yp, k, st, work, out);
+  } else {
+    const long nnp = Align4((long)c.n * c.n);
+    small::PsdEigen(t, c.n, c.m, data, yp, k, st, st + nnp, st + 2 * nnp, sm + 64, out);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) PrepareKernel(ConeArgs c, const double* y, long ystride,
+                                                          int affine, double cw, const double* cw_p,
+                                                          double ew, double* out2, long ostride,
+                                                          const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  const double* data = c.data + p * c.data_stride;
+  double* st = c.state + p * c.state_stride;
+  double* work = c.work ? c.work + p * c.work_stride : nullptr;
+  const double* yp = y + p * ystride;
+  const double k = cw_p ? cw_p[p] : cw;
+  double* out = out2 + p * ostride;
+  if (c.type == CXB_CONE_LP) {
+    const long np = Align4(c.n);
+    small::LpPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + np, st + 2 * np, out);
+  } else if (c.type == CXB_CONE_SOC) {
+    const long op = Align4(c.n + 1);
+    small::SocPrepare(t, c.n + 1, c.m, data, yp, k, st, st + op, work, out);
+  } else {
+    const long nnp = Align4((long)c.n * c.n);
+    small::PsdPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + nnp, st + 2 * nnp, sm + 64, out);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) TakeStepKernel(ConeArgs c, double step, const double* step_p,
+                                                           double ew, int* info, const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  double* st = c.state + p * c.state_stride;
+  double* work = c.work ? c.work + p * c.work_stride : nullptr;
+  const double s = step_p ? step_p[p] : step;
+  if (c.type == CXB_CONE_LP) {
+    const long np = Align4(c.n);
+    small::LpTakeStep(t, c.n, s, st, st + 2 * np);
+  } else if (c.type == CXB_CONE_SOC) {
+    const long op = Align4(c.n + 1);
+    small::SocTakeStep(t, c.n + 1, s, st, st + op, work);
+  } else {
+    const long nnp = Align4((long)c.n * c.n);
+    small::PsdTakeStep(t, c.n, s, ew, st, st + 2 * nnp, sm + 64, info + p);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) PotrfKernel(int N, double* H, long ldh, long hstride, int* info,
+                                                        const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  small::SmallPotrf(t, N, H + p * hstride, ldh, sm + 64, info + p);
+}
+
+__global__ void __launch_bounds__(kThreads) PotrsKernel(int N, const double* L, long ldl, long lstride,
+                                                        double* X, long xstride, const int* active) {
+  extern __shared__ double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  DeviceTeam t(sm);
+  small::SmallPotrs(t, N, L + p * lstride, ldl, X + p * xstride, sm + 64);
+}
+
+__global__ void LincombKernel(int n, const double* a, const double* x, long xs, const double* b,
+                              const double* y, long ys, const double* c, const double* z, long zs,
+                              double* out, long os, const int* active) {
+  const int p = blockIdx.y;
+  if (active && !active[p]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = 0;
+  if (a && x) v += a[p] * x[p * xs + i];
+  if (b && y) v += b[p] * y[p * ys + i];
+  if (c && z) v += c[p] * z[p * zs + i];
+  out[p * os + i] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) BatchedDotKernel(int n, const double* x, long xs,
+                                                             const double* y, long ys, double* out,
+                                                             long ostride) {
+  __shared__ double scratch[40];
+  const int p = blockIdx.x;
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[p * xs + i] * y[p * ys + i];
+  s = BlockSum(s, scratch);
+  if (threadIdx.x == 0) out[p * ostride] = s;
+}
+
+template <typename K>
+int EnsureSmem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) return -1;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+bool ValidCone(const cxb_small_cone* c) {
+  if (!c || c->n < 1 || c->m < 1 || !c->data || !c->state) return false;
+  if (c->type == CXB_CONE_LP) return true;
+  if (c->type == CXB_CONE_SOC) return c->work != nullptr;
+  if (c->type == CXB_CONE_PSD) return c->work != nullptr && c->n <= 64;
+  return false;
+}
+
+}  // namespace
+}  // namespace cxb
+
+using namespace cxb;
+
+extern "C" {
+
+size_t cxb_small_state_size(int type, int n) {
+  if (type == CXB_CONE_LP) return 3 * (size_t)Align4(n);
+  if (type == CXB_CONE_SOC) return 2 * (size_t)Align4(n + 1);
+  return 3 * (size_t)Align4((long)n * n);
+}
+
+size_t cxb_small_work_size(int type, int n, int m) {
+  if (type == CXB_CONE_LP) return 0;
+  if (type == CXB_CONE_SOC) return (size_t)(n + 1) * (m + 4);
+  return (size_t)(m + 1) * n * n;
+}
+
+int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active) {
+  if (batch <= 0) return 0;
+  if (!ValidCone(cone)) return -1;
+  const ConeArgs c = Convert(cone);
+  CountLaunch(); SetIdentityKernel<<<batch, kThreads, sizeof(double) * 64, AsStream(stream)>>>(c, d_active);
+  return LaunchStatus();
+}
+
+int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double* dG, long ldg,
+                    long gstride, double* dAW, double* dAQc, long vstride, double* d_scal, long sstride,
+                    int accumulate, const int* d_active) {
+  if (batch <= 0) return 0;
+  if (!ValidCone(cone)) return -1;
+  const ConeArgs c = Convert(cone);
+  const size_t smem = SmemBytes(c);
+  int rc = EnsureSmem(SchurKernel, smem);
+  if (rc) return rc;
+  CountLaunch(); SchurKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dG, ldg, gstride, dAW, dAQc, vstride,
+                                                            d_scal, sstride, accumulate, d_active);
+  return LaunchStatus();
+}
+
+int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const double* dy, long ystride,
+                    double c_weight, const double* d_cw, double* d_out4, long ostride,
+                    const int* d_active) {
+  if (batch <= 0) return 0;
+  if (!ValidCone(cone)) return -1;
+  const ConeArgs c = Convert(cone);
+  const size_t smem = SmemBytes(c);
+  int rc = EnsureSmem(EigenKernel, smem);
+  if (rc) return rc;
+  CountLaunch(); EigenKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dy, ystride, c_weight, d_cw, d_out4,
+                                                            ostride, d_active);
+  return LaunchStatus();
+}
+
+int cxb_small_prepare(void* stream, int batch, const cxb_small_cone* cone, const double* dy, long ystride,
+                      int affine, double c_weight, const double* d_cw, double e_weight, double* d_out2,
+                      long ostride, const int* d_active) {
+  if (batch <= 0) return 0;
+  if (!ValidCone(cone)) return -1;
+  const ConeArgs c = Convert(cone);
+  const size_t smem = SmemBytes(c);
+  int rc = EnsureSmem(PrepareKernel, smem);
+  if (rc) return rc;
+  CountLaunch(); PrepareKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dy, ystride, affine, c_weight, d_cw,
+                                                              e_weight, d_out2, ostride, d_active);
+  return LaunchStatus();
+}
+
+int cxb_small_take_step(void* stream, int batch, const cxb_small_cone* cone, double step,
+                        const double* d_step, double e_weight, int* d_info, const int* d_active) {
+  if (batch <= 0) return 0;
+  if (!ValidCone(cone)) return -1;
+  if (cone->type == CXB_CONE_PSD && !d_info) return -1;
+  const ConeArgs c = Convert(cone);
+  const size_t smem = SmemBytes(c);
+  int rc = EnsureSmem(TakeStepKernel, smem);
+  if (rc) return rc;
+  CountLaunch(); TakeStepKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, step, d_step, e_weight, d_info,
+                                                               d_active);
+  return LaunchStatus();
+}
+
+int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long hstride, int* d_info,
+                    const int* d_active) {
+  if (batch <= 0 || N <= 0) return 0;
+  const size_t smem = sizeof(double) * (64 + (size_t)N * N);
+  int rc = EnsureSmem(PotrfKernel, smem);
+  if (rc) return rc;
+  CountLaunch(); PotrfKernel<<<batch, kThreads, smem, AsStream(stream)>>>(N, dH, ldh, hstride, d_info, d_active);
+  return LaunchStatus();
+}
+
+int cxb_small_potrs(void* stream, int batch, int N, const double* dL, long ldl, long lstride, double* dX,
+                    long xstride, const int* d_active) {
+  if (batch <= 0 || N <= 0) return 0;
+  const size_t smem = sizeof(double) * (64 + (size_t)N);
+  int rc = EnsureSmem(PotrsKernel, smem);
+  if (rc) return rc;
+  CountLaunch(); PotrsKernel<<<batch, kThreads, smem, AsStream(stream)>>>(N, dL, ldl, lstride, dX, xstride, d_active);
+  return LaunchStatus();
+}
+
+int cxb_batched_lincomb(void* stream, int batch, int n, const double* d_a, const double* dx, long xs,
+                        const double* d_b, const double* dy, long ys, const double* d_c, const double* dz,
+                        long zs, double* d_out, long os, const int* d_active) {
+  if (batch <= 0 || n <= 0) return 0;
+  dim3 grid((n + 127) / 128, batch);
+  CountLaunch(); LincombKernel<<<grid, 128, 0, AsStream(stream)>>>(n, d_a, dx, xs, d_b, dy, ys, d_c, dz, zs, d_out, os,
+                                                     d_active);
+  return LaunchStatus();
+}
+
+int cxb_batched_dot(void* stream, int batch, int n, const double* dx, long xs, const double* dy, long ys,
+                    double* d_out, long ostride) {
+  if (batch <= 0) return 0;
+  CountLaunch(); BatchedDotKernel<<<batch, kThreads, 0, AsStream(stream)>>>(n, dx, xs, dy, ys, d_out, ostride);
+  return LaunchStatus();
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <iomanip>
 #include <limits>
+#include <set>
 
 #include "../../../include/conex_b200_device.h"
 #include "divergence.h"
@@ -72,9 +73,68 @@ void DenseKKTSolver::Assemble() {
   }
 }
 
+namespace {
+
+// The pivot order of Eigen::RLDLT (RLDLT.h:328-356): at step k the largest |diagonal entry| among
+// positions k.. of the *current* arrangement (first occurrence on ties) is swapped to position k.
+// The left-looking algorithm has not touched those entries yet, so they are the original diagonal
+// and the whole order follows from it. Returns perm with perm[k] = original index at position k.
+std::vector<int> RldltPivotOrder(const std::vector<double>& diag) {
+  const int n = static_cast<int>(diag.size());
+  std::vector<int> at(n);  // position -> original index
+  for (int i = 0; i < n; i++) at[i] = i;
+  // candidates ordered by (-|d|, position)
+  std::set<std::pair<double, int>> pool;
+  for (int i = 0; i < n; i++) pool.insert({-std::fabs(diag[i]), i});
+  for (int k = 0; k < n; k++) {
+    const auto best = *pool.begin();
+    const int p = best.second;
+    pool.erase(pool.begin());
+    if (p != k) {
+      // the element at position k moves to position p and stays a candidate
+      pool.erase({-std::fabs(diag[at[k]]), k});
+      std::swap(at[k], at[p]);
+      pool.insert({-std::fabs(diag[at[p]]), p});
+    }
+  }
+  return at;
+}
+
+}  // namespace
+
+std::vector<int> RldltPivotOrderForTest(const std::vector<double>& diag) { return RldltPivotOrder(diag); }
+
+void DenseKKTSolver::FactorLDLT() {
+  // reference block_triangular_operations.cc:315-349 + RLDLT.h:297-431 for one dense supernode
+  void* s = ctx_->stream();
+  const int N = N_;
+  if (Hp_.size() == 0) {
+    Hp_.Resize(static_cast<size_t>(ldh_) * N);
+    signs_.Resize(N);
+    diag_.Resize(2 * static_cast<size_t>(N));
+    ldlt_work_.Resize(cxb_ldlt_worksize(N));
+    perm_.Resize(N);
+  }
+  DeviceCheck(cxb_copy_strided(s, N, H_.get(), ldh_ + 1, diag_.get(), 1), "cxb_copy_strided");
+  std::vector<double> d(N);
+  ctx_->Download(d.data(), diag_.get(), N);
+  host_perm_ = RldltPivotOrder(d);
+  CudaCheck(cudaMemcpyAsync(perm_.get(), host_perm_.data(), sizeof(int) * N, cudaMemcpyHostToDevice,
+                            ctx_->cuda_stream()),
+            "upload of the pivot order");
+  DeviceCheck(cxb_sym_permute_lower(s, N, H_.get(), ldh_, perm_.get(), Hp_.get(), ldh_), "cxb_sym_permute_lower");
+  DeviceCheck(cxb_ldlt_lower(s, N, Hp_.get(), ldh_, signs_.get(), ldlt_work_.get(), ctx_->flags() + 2),
+              "cxb_ldlt_lower");
+  ctx_->Synchronize();  // host_perm_ is pageable
+}
+
 bool DenseKKTSolver::Factor() {
-  if (mode_ != CONEX_LLT_FACTORIZATION) {
-    throw std::runtime_error("conex-b200: only the LLT KKT mode is implemented on the device");
+  if (mode_ == CONEX_QR_FACTORIZATION) {
+    throw std::runtime_error("conex-b200: the QR KKT mode is not implemented on the device");
+  }
+  if (num_dual_ > 0) {
+    FactorLDLT();
+    return true;  // the regularised LDL^T never fails (kkt_solver.cc:187-193)
   }
   int* info = ctx_->flags();
   DeviceCheck(cxb_potrf_lower(ctx_->stream(), N_, H_.get(), ldh_, nullptr, info), "cxb_potrf_lower");
@@ -84,6 +144,14 @@ bool DenseKKTSolver::Factor() {
 }
 
 void DenseKKTSolver::SolveInPlace(Ref* b) const {
+  if (num_dual_ > 0) {
+    for (int k = 0; k < b->cols; k++) {
+      DeviceCheck(cxb_ldlt_solve(ctx_->stream(), N_, Hp_.get(), ldh_, signs_.get(), perm_.get(), b->col(k),
+                                 diag_.get() + N_),
+                  "cxb_ldlt_solve");
+    }
+    return;
+  }
   DeviceCheck(cxb_potrs_lower(ctx_->stream(), N_, H_.get(), ldh_, b->data, b->ld, b->cols),
               "cxb_potrs_lower");
 }
@@ -164,6 +232,7 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
   }
   prog.stats.initialized = true;
   prog.solver = std::make_unique<DenseKKTSolver>(&prog.ctx_, prog.SizeOfKKTSystem());
+  prog.solver->SetNumberOfMultipliers(prog.NumberOfMultipliers());
   prog.solver->Bind(&prog.eqs);
   prog.InitializeWorkspace();
   if (config.initialization_mode == CONEX_INITIALIZATION_MODE_COLDSTART) {
@@ -261,8 +330,8 @@ void NewtonDriver::UploadCost() {
   d_b_ = prog_.vectors_.get();
   d_y_ = d_b_ + stride;
   d_y2_ = d_y_ + stride;
-  b_.resize(m_);
-  for (int i = 0; i < m_; i++) b_[i] = -prog_.linear_cost_[i];
+  b_.assign(m_, 0.0);  // zero cost on the multipliers (reference cone_program.cc:294-296)
+  for (int i = 0; i < prog_.GetNumberOfVariables(); i++) b_[i] = -prog_.linear_cost_[i];
   CudaCheck(cudaMemcpyAsync(d_b_, b_.data(), sizeof(double) * m_, cudaMemcpyHostToDevice,
                             ctx_.cuda_stream()),
             "upload of b");
@@ -335,7 +404,7 @@ bool NewtonDriver::Run(double* primal_variable) {
 
   if (prog_.NumberOfConstraints() == 0) {
     // reference cone_program.cc:266-271
-    for (int i = 0; i < m_; i++) {
+    for (int i = 0; i < prog_.GetNumberOfVariables(); i++) {
       primal_variable[i] = -prog_.linear_cost_[i] * std::numeric_limits<double>::infinity();
     }
     return false;
@@ -490,7 +559,8 @@ bool NewtonDriver::Run(double* primal_variable) {
   }
 
   status.num_iterations = st.num_iter;
-  ctx_.Download(primal_variable, d_y_, m_);
+  const int num_vars = prog_.GetNumberOfVariables();
+  ctx_.Download(primal_variable, d_y_, num_vars);  // yout = y.topRows(m), cone_program.cc:486
   const double mu_final = (1.0 / k) * (1.0 / k);
   if (mu_final > cfg_.infeasibility_threshold) {
     status.solved = 0;
@@ -501,7 +571,7 @@ bool NewtonDriver::Run(double* primal_variable) {
   }
   if (cfg_.prepare_dual_variables) RecoverDualVariables(k);
   if (status.solved) {
-    for (int j = 0; j < m_; j++) primal_variable[j] = primal_variable[j] / k / st.c_scaling;
+    for (int j = 0; j < num_vars; j++) primal_variable[j] = primal_variable[j] / k / st.c_scaling;
     if (max_iters_reached) status.solved = 0;
   }
   ctx_.Synchronize();
@@ -528,7 +598,7 @@ std::vector<double> GetFeasibleObjective(Program* prog) {
   Initialize(*prog, SolverConfiguration());
   prog->solver->Assemble();
   AssembleSchurComplementResiduals(*prog);
-  const int m = prog->SizeOfKKTSystem();
+  const int m = prog->GetNumberOfVariables();
   std::vector<double> b(m);
   prog->ctx_.Download(b.data(), prog->sys.AW, m);
   for (auto& v : b) v *= .5;

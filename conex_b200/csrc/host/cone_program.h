@@ -9,9 +9,11 @@
 #include <any>
 #include <list>
 #include <memory>
+#include <type_traits>
 #include <vector>
 
 #include "constraint.h"
+#include "equality_constraint.h"
 
 namespace conex {
 
@@ -103,12 +105,23 @@ class DenseKKTSolver {
   Ref KKTMatrix() const { return Ref(H_.get(), N_, N_, ldh_); }
   void SetSolverMode(int mode) { mode_ = mode; }
   void SetIterativeRefinementIterations(int x) { iterative_refinement_iterations_ = x; }
+  // Any multiplier block switches Factor()/SolveInPlace() to the regularised LDL^T
+  // (reference kkt_solver.cc:180-193).
+  void SetNumberOfMultipliers(int n) { num_dual_ = n; }
+  bool factorization_regularized() const { return factorization_regularized_; }
 
  private:
+  void FactorLDLT();
   DeviceContext* ctx_;
   int N_;
   long ldh_;
   DeviceBuffer<double> H_;
+  // LDL^T mode: P H P^T factored as L S L^T in Hp_, the pivot order, S, scratch
+  int num_dual_ = 0;
+  bool factorization_regularized_ = false;
+  DeviceBuffer<double> Hp_, signs_, ldlt_work_, diag_;
+  DeviceBuffer<int> perm_;
+  std::vector<int> host_perm_;
   std::list<Container>* eqs_ = nullptr;
   bool has_direct_ = false;
   int mode_ = CONEX_LLT_FACTORIZATION;
@@ -124,7 +137,9 @@ class Program {
     linear_cost_.assign(m, 0.0);
   }
   int GetNumberOfVariables() const { return num_variables_; }
-  int SizeOfKKTSystem() const { return num_variables_; }
+  // variables + multipliers of the equality constraints (reference constraint_manager.h:42-48)
+  int SizeOfKKTSystem() const { return num_variables_ + num_dual_; }
+  int NumberOfMultipliers() const { return num_dual_; }
 
   // reference cone_program.h:191-218 / constraint_manager.h:50-70.
   template <typename T>
@@ -137,7 +152,18 @@ class Program {
   bool AddConstraint(T&& d, const std::vector<int>& variables) {
     if (!VariablesAreUnique(variables)) return true;  // CONEX_FAILURE
     using Cone = std::decay_t<T>;
-    eqs.emplace_back(static_cast<const Cone&>(d), variables);
+    std::vector<int> clique(variables);
+    if constexpr (std::is_same<Cone, EqualityConstraints>::value) {
+      // the multipliers become extra unknowns appended to the clique (constraint_manager.h:71-86)
+      const int rows = d.SizeOfDualVariable();
+      for (int i = 0; i < rows; i++) clique.push_back(num_variables_ + num_dual_ + i);
+      num_dual_ += rows;
+    }
+    return AddToClique(static_cast<const Cone&>(d), clique);
+  }
+  template <typename Cone>
+  bool AddToClique(const Cone& d, const std::vector<int>& variables) {
+    eqs.emplace_back(d, variables);
     eqs.back().constraint.bind(&ctx_);
     constraints_.push_back(&eqs.back().constraint);
     return false;  // CONEX_SUCCESS
@@ -176,7 +202,12 @@ class Program {
  private:
   bool VariablesAreUnique(const std::vector<int>& x) const;
   int num_variables_ = 0;
+  int num_dual_ = 0;
 };
+
+// Pivot order of the regularised LDL^T from the diagonal alone (RLDLT.h:328-356); exposed for the
+// host-logic tests.
+std::vector<int> RldltPivotOrderForTest(const std::vector<double>& diag);
 
 bool Initialize(Program& prog, const SolverConfiguration& config);
 // Maximises -linear_cost (reference cone_program.cc:235-533). Writes m doubles to host memory.

@@ -1,8 +1,8 @@
 // The conex C ABI (include/conex.h) on top of the device-resident Program — counterpart of the
-// reference's interfaces/conex.cc. Entry points on the Newton-step hot path are implemented; the
-// ones that build cones outside this round's scope (LP, SOC, Hermitian, quadratic costs) validate
-// their arguments like the reference and then report failure on stderr instead of silently doing
-// CPU work. Exceptions never cross the ABI: they are mapped to the call's failure value.
+// reference's interfaces/conex.cc. Dense/sparse LMI, LP, second-order-cone and equality constraints
+// are device cones; the entry points that build cones outside the scope (Hermitian LMIs, quadratic
+// costs) validate their arguments like the reference and then report failure on stderr instead of
+// silently doing CPU work. Exceptions never cross the ABI: they map to the call's failure value.
 #include <cuda_runtime_api.h>
 
 #include <cstdlib>
@@ -14,6 +14,9 @@
 #include "communicator.h"
 #include "cone_program.h"
 #include "dense_lmi_constraint.h"
+#include "small_cone_constraint.h"
+#include "batch_program.h"
+#include <cmath>
 #include "divergence.h"
 #include "tridiagonal_eigenvalues.h"
 
@@ -22,6 +25,9 @@ long g_launch_count = 0;
 }
 
 using conex::DenseLMIConstraint;
+using conex::EqualityConstraints;
+using conex::LinearConstraint;
+using conex::SOCConstraint;
 using conex::Program;
 using conex::SolverConfiguration;
 
@@ -313,16 +319,233 @@ void CONEX_GetIterationStats(void* prog, CONEX_IterationStats* stats, int iter_n
   stats->iteration_number = iter;
 }
 
-// ---- entry points whose cones are not on this round's device hot path ---------------------------
-int CONEX_AddDenseLinearConstraint(void*, const double*, int, int, const double*, int) {
-  NotOnHotPath("CONEX_AddDenseLinearConstraint (LP cone)");
-  return -1;
+// ---- LP cone, second-order cone, equality constraints ------------------------------------------
+int CONEX_AddDenseLinearConstraint(void* prog, const double* A, int Ar, int Ac, const double* c, int cr) {
+  // reference interfaces/conex.cc:216-229: Ar rows, Ac variables, column-major A
+  (void)cr;
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(Ac);
+        const int id = program.NumberOfConstraints();
+        program.AddConstraint(LinearConstraint(Ar, Ac, A, c));
+        return id;
+      },
+      -1);
 }
-int CONEX_AddLinearInequalities(void*, const double*, int, int, const double*, int, const double*,
-                                int) {
-  NotOnHotPath("CONEX_AddLinearInequalities (LP cone / equalities)");
-  return -1;
+
+int CONEX_AddLinearInequalities(void* prog, const double* A, int Ar, int Ac, const double* lb, int num_lb,
+                                const double* ub, int num_ub) {
+  // reference interfaces/conex.cc:190-215 + PreprocessLinearInequality (linear_constraint.cc:21-46):
+  // rows with lb == ub become scaled equality constraints, finite bounds scaled inequality rows.
+  (void)num_lb;
+  (void)num_ub;
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        std::vector<std::vector<double>> ineq_rows, eq_rows;
+        std::vector<double> ineq_rhs, eq_rhs;
+        for (int i = 0; i < Ar; i++) {
+          double rr = 0;
+          for (int j = 0; j < Ac; j++) rr += A[static_cast<size_t>(j) * Ar + i] * A[static_cast<size_t>(j) * Ar + i];
+          auto row = [&](double scale) {
+            std::vector<double> r(Ac);
+            for (int j = 0; j < Ac; j++) r[j] = scale * A[static_cast<size_t>(j) * Ar + i];
+            return r;
+          };
+          if (lb[i] == ub[i]) {
+            const double scale = 1.0 / std::sqrt(rr + ub[i] * ub[i]);
+            eq_rows.push_back(row(scale));
+            eq_rhs.push_back(scale * ub[i]);
+          } else {
+            if (ub[i] < 1e8) {
+              const double scale = 1.0 / std::sqrt(rr + ub[i] * ub[i]);
+              ineq_rows.push_back(row(scale));
+              ineq_rhs.push_back(scale * ub[i]);
+            }
+            if (lb[i] > -1e8) {
+              const double scale = 1.0 / std::sqrt(rr + lb[i] * lb[i]);
+              ineq_rows.push_back(row(-scale));
+              ineq_rhs.push_back(-scale * lb[i]);
+            }
+          }
+        }
+        auto pack = [&](const std::vector<std::vector<double>>& rows) {
+          const size_t r = rows.size();
+          std::vector<double> M(r * Ac);
+          for (size_t i = 0; i < r; i++)
+            for (int j = 0; j < Ac; j++) M[static_cast<size_t>(j) * r + i] = rows[i][j];
+          return M;
+        };
+        if (!ineq_rows.empty()) {
+          const auto M = pack(ineq_rows);
+          program.AddConstraint(LinearConstraint(static_cast<int>(ineq_rows.size()), Ac, M.data(), ineq_rhs.data()));
+        }
+        if (!eq_rows.empty()) {
+          const auto M = pack(eq_rows);
+          program.AddConstraint(EqualityConstraints(static_cast<int>(eq_rows.size()), Ac, M.data(), eq_rhs.data()));
+        }
+        return -1;  // the reference never returns an id here (conex.cc:213-214)
+      },
+      -1);
 }
+
+CONEX_STATUS CONEX_NewLorentzConeConstraint(void* p, int order, int* constraint_id) {
+  // reference interfaces/conex.cc:384-397
+  CONEX_DEMAND(order >= 1, "Received invalid n. Second order cone must have order (n + 1) >= 2.");
+  CONEX_DEMAND(constraint_id, "Received output null pointer.");
+  CAST_PROGRAM_OR_FAIL(p, prg);
+  CONEX_DEMAND(prg->GetNumberOfVariables() >= 1, "Number of variables must be set first.");
+  return Guard(
+      [&]() -> int {
+        prg->AddConstraint(SOCConstraint(order, prg->GetNumberOfVariables(), nullptr, nullptr));
+        *constraint_id = prg->NumberOfConstraints() - 1;
+        return CONEX_SUCCESS;
+      },
+      CONEX_FAILURE);
+}
+
+CONEX_STATUS CONEX_NewLinearInequality(void* p, int num_rows, int* constraint_id) {
+  // reference interfaces/conex.cc:318-329
+  CONEX_DEMAND(constraint_id, "Received output null pointer.");
+  CAST_PROGRAM_OR_FAIL(p, prg);
+  CONEX_DEMAND(num_rows >= 1 && prg->GetNumberOfVariables() >= 1, "Invalid dimensions.");
+  return Guard(
+      [&]() -> int {
+        const bool status = prg->AddConstraint(LinearConstraint(num_rows, prg->GetNumberOfVariables(), nullptr, nullptr));
+        *constraint_id = prg->NumberOfConstraints() - 1;
+        return status ? CONEX_FAILURE : CONEX_SUCCESS;
+      },
+      CONEX_FAILURE);
+}
+
+CONEX_STATUS CONEX_UpdateLinearOperator(void* p, int constraint, double value, int variable, int row,
+                                        int col, int hyper_complex_dim) {
+  // reference interfaces/conex.cc:365-373, cone_program.h:147-159
+  CAST_PROGRAM_OR_FAIL(p, prg);
+  CONEX_DEMAND(constraint >= 0 && constraint < prg->NumberOfConstraints(), "Invalid Constraint.");
+  return Guard(
+      [&]() -> int {
+        return UpdateLinearOperator(prg->constraints_[constraint], value, variable, row, col, hyper_complex_dim)
+                   ? CONEX_FAILURE
+                   : CONEX_SUCCESS;
+      },
+      CONEX_FAILURE);
+}
+
+CONEX_STATUS CONEX_UpdateAffineTerm(void* p, int constraint, double value, int row, int col,
+                                    int hyper_complex_dim) {
+  // reference interfaces/conex.cc:375-382
+  CAST_PROGRAM_OR_FAIL(p, prg);
+  CONEX_DEMAND(constraint >= 0 && constraint < prg->NumberOfConstraints(), "Invalid Constraint.");
+  return Guard(
+      [&]() -> int {
+        return UpdateAffineTerm(prg->constraints_[constraint], value, row, col, hyper_complex_dim) ? CONEX_FAILURE
+                                                                                                  : CONEX_SUCCESS;
+      },
+      CONEX_FAILURE);
+}
+
+// C++-only constructors of the reference exposed for tests and the batched bench:
+// SOCConstraint(A, c) (soc_constraint.h:9-15); A is (n + 1) x m column-major.
+int CONEXB200_AddSocConstraint(void* prog, int n, int m, const double* A, const double* c) {
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
+        const int id = program.NumberOfConstraints();
+        program.AddConstraint(SOCConstraint(n, m, A, c));
+        return id;
+      },
+      -1);
+}
+
+// Program::AddConstraint(EqualityConstraints{A, b}[, vars]) (cone_program.h:193-217); A is
+// rows x nvars column-major, vars == NULL: all variables. Returns the constraint id or -1.
+int CONEXB200_AddEqualityConstraint(void* prog, int rows, int nvars, const double* A, const double* b,
+                                    const long* vars) {
+  return Guard(
+      [&]() -> int {
+        Program& program = *static_cast<Program*>(prog);
+        const int id = program.NumberOfConstraints();
+        bool failed;
+        if (vars) {
+          std::vector<int> v(nvars);
+          for (int i = 0; i < nvars; i++) v[i] = static_cast<int>(vars[i]);
+          failed = program.AddConstraint(EqualityConstraints(rows, nvars, A, b), v);
+        } else {
+          failed = program.AddConstraint(EqualityConstraints(rows, nvars, A, b));
+        }
+        return failed ? -1 : id;
+      },
+      -1);
+}
+
+// ---- batched solves of structurally identical programs (batch_program.h) --------------------------
+void* CONEXB200_CreateBatch(void* const* programs, int count) {
+  return Guard(
+      [&]() -> void* {
+        std::vector<Program*> v(count);
+        for (int i = 0; i < count; i++) v[i] = static_cast<Program*>(programs[i]);
+        return new conex::BatchProgram(v);
+      },
+      nullptr);
+}
+
+void CONEXB200_DeleteBatch(void* batch) { delete static_cast<conex::BatchProgram*>(batch); }
+
+int CONEXB200_BatchMaximize(void* batch, const double* b, const CONEX_SolverConfiguration* config, double* y,
+                            int* solved) {
+  return Guard(
+      [&]() -> int {
+        auto* bp = static_cast<conex::BatchProgram*>(batch);
+        const int n = bp->Maximize(b, Convert(config), y);
+        if (solved) {
+          for (int p = 0; p < bp->size(); p++) solved[p] = bp->results()[p].solved;
+        }
+        return n;
+      },
+      -1);
+}
+
+void CONEXB200_BatchGetResults(void* batch, int* iterations, double* by, double* cx, double* inv_sqrt_mu) {
+  auto* bp = static_cast<conex::BatchProgram*>(batch);
+  for (int p = 0; p < bp->size(); p++) {
+    const auto& r = bp->results()[p];
+    if (iterations) iterations[p] = r.num_iterations;
+    if (by) by[p] = r.by;
+    if (cx) cx[p] = r.cx;
+    if (inv_sqrt_mu) inv_sqrt_mu[p] = r.inv_sqrt_mu;
+  }
+}
+
+double CONEXB200_BatchMilliseconds(void* batch) { return static_cast<conex::BatchProgram*>(batch)->milliseconds(); }
+
+int CONEXB200_BatchStepMilliseconds(void* batch, double* out, int capacity) {
+  const auto& v = static_cast<conex::BatchProgram*>(batch)->step_milliseconds();
+  for (int i = 0; i < static_cast<int>(v.size()) && i < capacity; i++) out[i] = v[i];
+  return static_cast<int>(v.size());
+}
+
+int CONEXB200_BatchGetDualVariable(void* batch, int program, int cone, double* x) {
+  return Guard(
+      [&]() -> int {
+        auto* bp = static_cast<conex::BatchProgram*>(batch);
+        bp->GetDualVariable(program, cone, x);
+        return bp->DualVariableSize(cone);
+      },
+      -1);
+}
+
+int CONEXB200_SizeOfKKTSystem(void* prog) { return static_cast<Program*>(prog)->SizeOfKKTSystem(); }
+
+// Host-logic probe: pivot order of the regularised LDL^T from the diagonal (RLDLT.h:328-356).
+void CONEXB200_RldltPivotOrder(int n, const double* diag, int* perm) {
+  const auto p = conex::RldltPivotOrderForTest(std::vector<double>(diag, diag + n));
+  for (int i = 0; i < n; i++) perm[i] = p[i];
+}
+
+// ---- entry points whose cones are not on the device hot path ------------------------------------
 int CONEX_AddQuadraticCost(void*, const double*, int, int) {
   return NotOnHotPath("CONEX_AddQuadraticCost");
 }
@@ -336,25 +559,6 @@ CONEX_STATUS CONEX_NewLinearMatrixInequality(void* p, int order, int hyper_compl
                "Hypercomplex dimension must be 1, 2, 4, or 8.");
   CONEX_DEMAND(p, "Program pointer is null.");
   return NotOnHotPath("CONEX_NewLinearMatrixInequality (HermitianPsdConstraint)");
-}
-CONEX_STATUS CONEX_UpdateLinearOperator(void* p, int, double, int, int, int, int) {
-  CONEX_DEMAND(p, "Program pointer is null.");
-  return NotOnHotPath("CONEX_UpdateLinearOperator");
-}
-CONEX_STATUS CONEX_UpdateAffineTerm(void* p, int, double, int, int, int) {
-  CONEX_DEMAND(p, "Program pointer is null.");
-  return NotOnHotPath("CONEX_UpdateAffineTerm");
-}
-CONEX_STATUS CONEX_NewLorentzConeConstraint(void* p, int order, int* constraint_id) {
-  CONEX_DEMAND(order >= 1, "Received invalid n. Second order cone must have order (n + 1) >= 2.");
-  CONEX_DEMAND(constraint_id, "Received output null pointer.");
-  CONEX_DEMAND(p, "Program pointer is null.");
-  return NotOnHotPath("CONEX_NewLorentzConeConstraint");
-}
-CONEX_STATUS CONEX_NewLinearInequality(void* p, int, int* constraint_id) {
-  CONEX_DEMAND(constraint_id, "Received output null pointer.");
-  CONEX_DEMAND(p, "Program pointer is null.");
-  return NotOnHotPath("CONEX_NewLinearInequality");
 }
 CONEX_STATUS CONEX_NewQuadraticCost(void* p, int* constraint_id) {
   CONEX_DEMAND(constraint_id, "Received output null pointer.");

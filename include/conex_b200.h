@@ -98,6 +98,40 @@ long CONEXB200_LaunchCount();
  * solves then fail with a message on stderr). */
 int CONEXB200_DeviceAvailable();
 
+/* ---- cones the reference builds through C++ constructors only -------------------------------- */
+/* SOCConstraint(A, c) (conex/soc_constraint.h:9-15): c - A y in the Lorentz cone of R^{n+1};
+ * A is (n + 1) x m column-major. Returns the constraint id. */
+int CONEXB200_AddSocConstraint(void* prog, int n, int m, const double* A, const double* c);
+/* Program::AddConstraint(EqualityConstraints{A, b}[, vars]) (conex/cone_program.h:193-217):
+ * A y[vars] = b, A rows x nvars column-major, vars == NULL means all variables. The multipliers
+ * become extra unknowns of the KKT system, which is then factored by the regularised LDL^T. */
+int CONEXB200_AddEqualityConstraint(void* prog, int rows, int nvars, const double* A, const double* b,
+                                    const long* vars);
+/* Variables + equality multipliers (conex/constraint_manager.h:42-48). */
+int CONEXB200_SizeOfKKTSystem(void* prog);
+/* Host-logic probe: the pivot order Eigen::RLDLT derives from the diagonal (RLDLT.h:328-356). */
+void CONEXB200_RldltPivotOrder(int n, const double* diag, int* perm);
+
+/* ---- many small programs in lock step (BASELINE config 3) ------------------------------------
+ * `programs`: `count` handles built through the CONEX_* calls with identical structure (same number
+ * of variables, same list of LP / second-order / dense-LMI cones, every cone on all variables, no
+ * equalities). CONEXB200_CreateBatch packs their data into batched device arrays (the handles may be
+ * deleted afterwards); CONEXB200_BatchMaximize solves all of them from a cold start: b and y are
+ * m x count column-major HOST arrays, solved[p] / the return value follow CONEX_Maximize (1 = solved;
+ * the return value is the number of solved programs, -1 on an error). Every program follows the same
+ * iteration sequence it would follow through CONEX_Maximize alone. */
+void* CONEXB200_CreateBatch(void* const* programs, int count);
+void CONEXB200_DeleteBatch(void* batch);
+int CONEXB200_BatchMaximize(void* batch, const double* b, const CONEX_SolverConfiguration* config, double* y,
+                            int* solved);
+/* Per-program iteration counts and final by / cx / inv_sqrt_mu (any pointer may be NULL). */
+void CONEXB200_BatchGetResults(void* batch, int* iterations, double* by, double* cx, double* inv_sqrt_mu);
+/* Device time of the last batched solve and of its Newton steps (CUDA events). */
+double CONEXB200_BatchMilliseconds(void* batch);
+int CONEXB200_BatchStepMilliseconds(void* batch, double* out, int capacity);
+/* Scaled dual variable of cone `cone` of program `program` (like CONEX_GetDualVariable); returns its size. */
+int CONEXB200_BatchGetDualVariable(void* batch, int program, int cone, double* x);
+
 #ifdef __cplusplus
 }
 #endif

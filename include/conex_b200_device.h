@@ -69,6 +69,26 @@ int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, i
  * X <- L^{-T} L^{-1} X for nrhs right-hand sides (columns of dX, leading dimension ldx). */
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs);
 
+/* ---- K4: diagonally pivoted, regularised LDL^T (block_triangular_operations.cc:315-349 +
+ * Eigen::RLDLT, RLDLT.h:297-431) for KKT systems with equality constraints.
+ * The reference picks pivots by the largest *stored* diagonal entry of a left-looking algorithm,
+ * i.e. by the ORIGINAL diagonal, so the whole permutation is known before any arithmetic: the host
+ * computes it from diag(K) (host/cone_program.cc), cxb_sym_permute_lower forms P K P^T from the
+ * lower triangle, and cxb_ldlt_lower factors it WITHOUT further pivoting as L S L^T, S = diag(+-1)
+ * (LDL^T with |D|^{1/2} folded into L) by a blocked right-looking algorithm: 128-column diagonal
+ * blocks in shared memory, panel solve, DMMA trailing update. Pivots with |d| <= 1e-9 become
+ * +-1e-9 (RLDLT.h:378-389); d_info[1] = 1 then (regularization_used), d_info[0] stays 0.
+ * d_signs: N doubles (S). d_work: cxb_ldlt_worksize(N) doubles. */
+size_t cxb_ldlt_worksize(int N);
+int cxb_sym_permute_lower(void* stream, int N, const double* dK, long ldk, const int* d_perm,
+                          double* dKp, long ldp);
+int cxb_ldlt_lower(void* stream, int N, double* dK, long ldk, double* d_signs, double* d_work,
+                   int* d_info);
+/* x <- P^T L^{-T} S L^{-1} P x (block_triangular_operations.cc:222-312); perm[i] = original index
+ * at pivot position i; d_tmp: N doubles. */
+int cxb_ldlt_solve(void* stream, int N, const double* dL, long ldl, const double* d_signs,
+                   const int* d_perm, double* dx, double* d_tmp);
+
 /* ---- K6: negative slack  out = sum_j coef[j] * Aall[:, j]  (dense_lmi_constraint.cc:8-27);
  * Aall is nn x cols column-major (ld = nn), d_coef has `cols` entries (y followed by -k for C). */
 int cxb_gemv_n(void* stream, long nn, int cols, const double* dAall, const double* d_coef,
@@ -128,6 +148,65 @@ int cxb_scatter_add_vec(void* stream, int n, const double* d_src, const int* d_i
 int cxb_gather_vec(void* stream, int n, const double* d_src, const int* d_idx, double* d_dst);
 /* W <- (1 + w_e) W + WSW  (psd_constraint.cc:33-43) */
 int cxb_affine_update(void* stream, int n, double* dW, const double* dWSW, double w_e);
+
+/* ---- small cones, batched: one CTA per program of a batch (small_cones.cu) --------------------
+ * The LP cone (conex/linear_constraint.cc), the second-order cone (conex/soc_constraint.cc) and
+ * small dense LMI blocks (n*n doubles fit in shared memory; conex/psd_constraint.cc +
+ * dense_lmi_constraint.cc) of `batch` structurally identical programs, advanced in lock step; the
+ * single-program LP / SOC plugins are the batch == 1 case. Problem p of the batch uses
+ * ptr + p * stride of every array below.
+ *   data : rows x (m + 1) column-major, rows = n (LP), n + 1 (SOC), n * n (PSD); columns 0..m-1 hold
+ *          the linear operator (PSD: vec(A_j)), column m the affine term.
+ *   state: LP  W[n] t1[n] t2[n] at offsets 0, np, 2 np (np = n rounded up to 4)
+ *          SOC (W0, W1)[n + 1] at 0, d[n + 1] at op (op = n + 1 rounded up to 4)
+ *          PSD W, T1, T2 (n x n each) at 0, nnp, 2 nnp (nnp = n * n rounded up to 4)
+ *   work : SOC (n + 1) * (m + 4) doubles; PSD (m + 1) * n * n doubles; LP none.
+ * active (device ints, may be NULL) masks programs that must not be touched. */
+enum { CXB_CONE_LP = 0, CXB_CONE_SOC = 1, CXB_CONE_PSD = 2 };
+typedef struct {
+  int type, n, m;
+  const double* data;
+  long data_stride;
+  double* state;
+  long state_stride;
+  double* work;
+  long work_stride;
+} cxb_small_cone;
+size_t cxb_small_state_size(int type, int n);
+size_t cxb_small_work_size(int type, int n, int m);
+int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active);
+/* G (ldg, lower triangle), AW, AQc (m each, stride vstride), scal[2] = {<w,c>, <c,Qc>} (stride
+ * sstride): assigned (accumulate == 0) or added to (ConstructSchurComplementSystem, initialize flag). */
+int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double* dG, long ldg,
+                    long gstride, double* dAW, double* dAQc, long vstride, double* d_scal,
+                    long sstride, int accumulate, const int* d_active);
+/* out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} of Q(w^{1/2})(c_weight c - A y)
+ * (GetWeightedSlackEigenvalues). c_weight: per-program device array d_cw (stride 1) when not NULL,
+ * else the scalar. */
+int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const double* dy, long ystride,
+                    double c_weight, const double* d_cw, double* d_out4, long ostride,
+                    const int* d_active);
+/* out2 = {norminfd, normsqrd} (PrepareStep); affine != 0: the dual-recovery update. */
+int cxb_small_prepare(void* stream, int batch, const cxb_small_cone* cone, const double* dy,
+                      long ystride, int affine, double c_weight, const double* d_cw, double e_weight,
+                      double* d_out2, long ostride, const int* d_active);
+/* TakeStep with step size `step` (or d_step[p]); d_info[p] != 0 reports a singular Padé system. */
+int cxb_small_take_step(void* stream, int batch, const cxb_small_cone* cone, double step,
+                        const double* d_step, double e_weight, int* d_info, const int* d_active);
+/* Cholesky of `batch` N x N matrices (lower, ld, stride) and solves with nrhs = 1; d_info[p] = 0 or
+ * 1 + first non-positive pivot (block_triangular_operations.cc:184-219, :114-182). */
+int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long hstride, int* d_info,
+                    const int* d_active);
+int cxb_small_potrs(void* stream, int batch, int N, const double* dL, long ldl, long lstride, double* dX,
+                    long xstride, const int* d_active);
+/* out[p] = a[p] x[p] + b[p] y[p] + c[p] z[p] (n entries each; coefficient arrays on the device,
+ * NULL coefficient array / vector = term absent). */
+int cxb_batched_lincomb(void* stream, int batch, int n, const double* d_a, const double* dx, long xs,
+                        const double* d_b, const double* dy, long ys, const double* d_c,
+                        const double* dz, long zs, double* d_out, long os, const int* d_active);
+/* out[p * ostride] = x[p] . y[p] */
+int cxb_batched_dot(void* stream, int batch, int n, const double* dx, long xs, const double* dy, long ys,
+                    double* d_out, long ostride);
 
 #ifdef __cplusplus
 }

@@ -294,6 +294,76 @@ int ORACLE_AddEqualityConstraint(void* p, int rows, int nvars, const double* A, 
   }
   return ok ? id : -1;
 }
+// Stand-alone cones for kernel-level parity tests. type: 0 LP (rows = n), 1 SOC (rows = n + 1),
+// 2 dense LMI (rows = n * n). data = rows x (m + 1) column-major: the operator, then the affine term.
+struct OracleCone {
+  std::unique_ptr<oracle::Cone> cone;
+  std::vector<double> workspace;
+  int m;
+};
+void* ORACLE_ConeCreate(int type, int n, int m, const double* data) {
+  auto* h = new OracleCone;
+  h->m = m;
+  if (type == 0) {
+    h->cone = std::make_unique<LinearCone>(n, m, data, data + (size_t)n * m);
+  } else if (type == 1) {
+    h->cone = std::make_unique<SocCone>(n, m, data, data + (size_t)(n + 1) * m);
+  } else {
+    h->cone = std::make_unique<DenseLmiCone>(n, m, data, data + (size_t)n * n * m);
+  }
+  h->workspace.assign(h->cone->WorkspaceSize() + 8, 0.0);
+  h->cone->BindWorkspace(h->workspace.data());
+  h->cone->SetIdentity();
+  return h;
+}
+void ORACLE_ConeDelete(void* h) { delete static_cast<OracleCone*>(h); }
+int ORACLE_ConeStateSize(void* h) { return static_cast<OracleCone*>(h)->cone->StateSize(); }
+void ORACLE_ConeGetState(void* h, double* w) { static_cast<OracleCone*>(h)->cone->GetState(w); }
+void ORACLE_ConeSetState(void* h, const double* w) { static_cast<OracleCone*>(h)->cone->SetState(w); }
+// G: m x m column-major (lower triangle written), AW, AQc: m, scal2 = {<w,c>, <c,Qc>}
+void ORACLE_ConeSchur(void* h, double* G, double* AW, double* AQc, double* scal2) {
+  auto* c = static_cast<OracleCone*>(h);
+  const int m = c->m;
+  oracle::SchurSystem sys;
+  sys.m = m;
+  std::vector<double> buf(sys.SizeOf(), 0.0);
+  sys.Bind(buf.data());
+  c->cone->ConstructSchurComplementSystem(true, &sys);
+  for (int j = 0; j < m; j++)
+    for (int i = 0; i < m; i++) G[(size_t)j * m + i] = (i >= j) ? sys.G(i, j) : 0.0;
+  std::memcpy(AW, sys.AW, sizeof(double) * m);
+  std::memcpy(AQc, sys.AQc, sizeof(double) * m);
+  scal2[0] = sys.inner_product_of_w_and_c;
+  scal2[1] = sys.inner_product_of_c_and_Qc;
+}
+// out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace}
+void ORACLE_ConeEigen(void* h, const double* y, double c_weight, double* out4) {
+  oracle::SlackEigenvalues p;
+  static_cast<OracleCone*>(h)->cone->GetWeightedSlackEigenvalues(y, c_weight, &p);
+  out4[0] = p.lambda_min;
+  out4[1] = p.lambda_max;
+  out4[2] = p.frobenius_norm_squared;
+  out4[3] = p.trace;
+}
+void ORACLE_ConePrepare(void* h, const double* y, int affine, double c_weight, double e_weight,
+                        double* out2) {
+  oracle::StepOptions opt;
+  opt.affine = affine != 0;
+  opt.c_weight = c_weight;
+  opt.e_weight = e_weight;
+  oracle::StepInfo info;
+  static_cast<OracleCone*>(h)->cone->PrepareStep(opt, y, &info);
+  out2[0] = info.norminfd;
+  out2[1] = info.normsqrd;
+}
+void ORACLE_ConeTakeStep(void* h, double step, double e_weight) {
+  oracle::StepOptions opt;
+  opt.affine = false;
+  opt.e_weight = e_weight;
+  opt.step_size = step;
+  static_cast<OracleCone*>(h)->cone->TakeStep(opt);
+}
+
 int ORACLE_SizeOfKKTSystem(void* p) { return Cast(p)->SizeOfKKTSystem(); }
 // In-place RLDLT of the lower triangle of A (n x n); transpositions written as ints. Returns 1
 // when no pivot was regularised.

@@ -73,6 +73,16 @@ class Cone {
                                            SlackEigenvalues* p) = 0;
   virtual const double* DualVariable() const = 0;
   virtual int DualVariableSize() const = 0;
+  // The scaling point as one vector (LP: w; SOC: (w0, w1); PSD: vec(W)) — tests only.
+  virtual int StateSize() const { return DualVariableSize(); }
+  virtual void GetState(double* out) const {
+    const double* w = DualVariable();
+    for (int i = 0; i < DualVariableSize(); i++) out[i] = w[i];
+  }
+  virtual void SetState(const double* in) {
+    double* w = const_cast<double*>(DualVariable());
+    for (int i = 0; i < DualVariableSize(); i++) w[i] = in[i];
+  }
 };
 
 // How the Gram rows of the Schur complement are formed.
@@ -157,6 +167,14 @@ class SocCone final : public Cone {
                                    SlackEigenvalues* p) override;
   const double* DualVariable() const override { return dual_.data(); }
   int DualVariableSize() const override { return n_ + 1; }
+  void GetState(double* out) const override {
+    out[0] = *W0_;
+    for (int i = 0; i < n_; i++) out[1 + i] = W1_[i];
+  }
+  void SetState(const double* in) override {
+    *W0_ = in[0];
+    for (int i = 0; i < n_; i++) W1_[i] = in[1 + i];
+  }
   // incremental construction (soc_constraint.cc:237-260)
   int order() const { return n_; }
   void SetOperatorEntry(int row, int var, double v) { A_[(size_t)var * (n_ + 1) + row] = v; }

@@ -401,3 +401,98 @@ def lovasz_theta_lmi(n, num_edges, seed):
     b = np.zeros(num_edges + 1)
     b[0] = -1.0
     return mats, -np.ones((n, n)), b
+
+
+def small_multicone_problem(seed, m=40, psd_blocks=3, psd_order=20, soc_cones=2, soc_order=10, lp_rows=40):
+    """One program of BASELINE config 3: `psd_blocks` dense LMI blocks
+    (A_i = sym(U[-1,1]), C = I), `soc_cones` Lorentz cones of order `soc_order` (A uniform,
+    c = (1, 0, ...), interfaces/python/test/run_tests.py:23-34) and one LP block (A uniform, c = 1),
+    all on the same m variables; b = sum over cones of the feasible objective AW/2 at W = I
+    (cone_program.cc:535-545), so both primal and dual are strictly feasible."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cones = []
+    b = np.zeros(m)
+    for _ in range(psd_blocks):
+        mats = [random_sym(rng, psd_order) for _ in range(m)]
+        cones.append(("psd", mats, np.eye(psd_order)))
+        b += 0.5 * np.array([np.trace(M) for M in mats])
+    for _ in range(soc_cones):
+        A = rng.uniform(-1.0, 1.0, size=(soc_order + 1, m))
+        c = np.zeros(soc_order + 1)
+        c[0] = 1.0
+        cones.append(("soc", A, c))
+        b += 0.5 * 2.0 * A[0, :]
+    if lp_rows:
+        A = rng.uniform(-1.0, 1.0, size=(lp_rows, m))
+        cones.append(("lp", A, np.ones(lp_rows)))
+        b += 0.5 * A.sum(axis=0)
+    return cones, b
+
+
+def add_cones(P, cones):
+    for kind, A, c in cones:
+        if kind == "psd":
+            P.add_dense_lmi(A, c)
+        elif kind == "soc":
+            P.add_soc(A, c)
+        else:
+            P.add_linear(A, c)
+
+
+class Batch:
+    """CONEXB200_CreateBatch / BatchMaximize on a list of harness Programs (product library only)."""
+
+    def __init__(self, lib, programs):
+        self.L = lib
+        L = lib.lib
+        L.CONEXB200_CreateBatch.restype = C.c_void_p
+        L.CONEXB200_CreateBatch.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.CONEXB200_DeleteBatch.argtypes = [C.c_void_p]
+        L.CONEXB200_BatchMaximize.argtypes = [C.c_void_p, c_double_p, C.POINTER(SolverConfiguration), c_double_p,
+                                              c_int_p]
+        L.CONEXB200_BatchGetResults.argtypes = [C.c_void_p, c_int_p, c_double_p, c_double_p, c_double_p]
+        L.CONEXB200_BatchMilliseconds.restype = C.c_double
+        L.CONEXB200_BatchMilliseconds.argtypes = [C.c_void_p]
+        L.CONEXB200_BatchStepMilliseconds.argtypes = [C.c_void_p, c_double_p, C.c_int]
+        L.CONEXB200_BatchGetDualVariable.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+        self.count = len(programs)
+        self.m = programs[0].m
+        handles = (C.c_void_p * self.count)(*[p.h for p in programs])
+        self.h = C.c_void_p(L.CONEXB200_CreateBatch(handles, self.count))
+        assert self.h.value, "CONEXB200_CreateBatch failed"
+
+    def __del__(self):
+        try:
+            self.L.lib.CONEXB200_DeleteBatch(self.h)
+        except Exception:
+            pass
+
+    def maximize(self, b, cfg=None):
+        """b: (count, m). Returns (solved (count,), y (count, m))."""
+        if cfg is None:
+            cfg = self.L.default_config()
+        b = np.ascontiguousarray(np.asarray(b, dtype=np.float64))
+        y = np.zeros((self.count, self.m))
+        solved = (C.c_int * self.count)()
+        rc = self.L.lib.CONEXB200_BatchMaximize(self.h, dptr(b), C.byref(cfg), dptr(y), solved)
+        assert rc >= 0, "CONEXB200_BatchMaximize failed"
+        return np.array(list(solved)), y
+
+    def results(self):
+        it = (C.c_int * self.count)()
+        by, cx, k = np.zeros(self.count), np.zeros(self.count), np.zeros(self.count)
+        self.L.lib.CONEXB200_BatchGetResults(self.h, it, dptr(by), dptr(cx), dptr(k))
+        return np.array(list(it)), by, cx, k
+
+    def milliseconds(self):
+        return self.L.lib.CONEXB200_BatchMilliseconds(self.h)
+
+    def step_milliseconds(self):
+        buf = np.zeros(256)
+        n = self.L.lib.CONEXB200_BatchStepMilliseconds(self.h, dptr(buf), 256)
+        return buf[:n].copy()
+
+    def dual_variable(self, p, cone, size):
+        x = np.zeros(size)
+        assert self.L.lib.CONEXB200_BatchGetDualVariable(self.h, p, cone, dptr(x)) == size
+        return x

@@ -210,3 +210,33 @@ def test_lp_dual_recovery(i):
     assert slack.min() >= -eps and x.min() >= -eps
     mu = 1.0 / cfg.inv_sqrt_mu_max ** 2
     assert slack @ x <= (mu + np.sqrt(eps)) * nc
+
+
+@pytest.mark.parametrize("n", [1, 5, 40, 300])
+def test_product_pivot_order_matches_rldlt(n):
+    """Host logic of the product (no GPU needed): the pivot order it derives from the diagonal alone
+    is the one the RLDLT restatement produces by actually factoring (RLDLT.h:328-356)."""
+    import devlib
+    L = devlib.product().lib
+    L.CONEXB200_RldltPivotOrder.argtypes = [C.c_int, C.POINTER(C.c_double), c_int_p]
+    O = oracle()
+    rng = np.random.Generator(np.random.PCG64(n))
+    k = n // 3
+    M = np.zeros((n, n))
+    R = rng.uniform(-1, 1, size=(n - k, n - k))
+    M[:n - k, :n - k] = R @ R.T + np.eye(n - k)
+    if k:
+        M[n - k:, :n - k] = rng.uniform(-1, 1, size=(k, n - k))
+        # a few exact ties and negative entries on the diagonal
+        M[0, 0] = M[1, 1]
+        M[n - 1, n - 1] = -M[2, 2]
+    diag = np.ascontiguousarray(np.diag(M).copy())
+    perm = (C.c_int * n)()
+    L.CONEXB200_RldltPivotOrder(n, dptr(diag), perm)
+    LD = np.asfortranarray(np.tril(M))
+    tr = (C.c_int * n)()
+    O.lib.ORACLE_LdltLower(n, dptr(LD), tr)
+    ref = list(range(n))
+    for i, t in enumerate(tr):
+        ref[i], ref[t] = ref[t], ref[i]
+    assert list(perm) == ref

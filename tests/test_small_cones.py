@@ -1,0 +1,203 @@
+"""Parity of the small-cone arithmetic (LP cone, second-order cone, small dense LMI block, small
+KKT Cholesky) with the CPU oracle, cone function by cone function, on batches of seeded problems.
+
+The same checks run twice: on the CPU through the host stand-in of the CTA (tests/emul, checks the
+header's index arithmetic where no GPU exists) and, marked gpu, through the real cxb_small_*
+kernels. Tolerances: 1e-10 relative on Newton-system entries (BASELINE.json), 1e-9 on the
+eigenvalue / norm outputs that pass through Lanczos.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from harness import dptr, oracle
+from small_backend import LP, PSD, SOC, Backend, rows_of
+
+c_double_p = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module", params=["emul", pytest.param("device", marks=pytest.mark.gpu)])
+def be(request):
+    return Backend(request.param)
+
+
+def oracle_cone_api():
+    O = oracle().lib
+    O.ORACLE_ConeCreate.restype = C.c_void_p
+    O.ORACLE_ConeCreate.argtypes = [C.c_int, C.c_int, C.c_int, c_double_p]
+    O.ORACLE_ConeDelete.argtypes = [C.c_void_p]
+    O.ORACLE_ConeStateSize.argtypes = [C.c_void_p]
+    O.ORACLE_ConeGetState.argtypes = [C.c_void_p, c_double_p]
+    O.ORACLE_ConeSetState.argtypes = [C.c_void_p, c_double_p]
+    O.ORACLE_ConeSchur.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    O.ORACLE_ConeEigen.argtypes = [C.c_void_p, c_double_p, C.c_double, c_double_p]
+    O.ORACLE_ConePrepare.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_double, C.c_double, c_double_p]
+    O.ORACLE_ConeTakeStep.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    return O
+
+
+class OracleCone:
+    def __init__(self, kind, n, m, data):
+        self.O = oracle_cone_api()
+        self.m = m
+        self.data = np.ascontiguousarray(data)
+        self.h = C.c_void_p(self.O.ORACLE_ConeCreate(kind, n, m, dptr(self.data)))
+        self.sz = self.O.ORACLE_ConeStateSize(self.h)
+
+    def __del__(self):
+        self.O.ORACLE_ConeDelete(self.h)
+
+    def state(self):
+        w = np.zeros(self.sz)
+        self.O.ORACLE_ConeGetState(self.h, dptr(w))
+        return w
+
+    def schur(self):
+        m = self.m
+        G, AW, AQc, sc = np.zeros((m, m), order="F"), np.zeros(m), np.zeros(m), np.zeros(2)
+        self.O.ORACLE_ConeSchur(self.h, dptr(G), dptr(AW), dptr(AQc), dptr(sc))
+        return np.tril(G), AW, AQc, sc
+
+    def eigen(self, y, cw):
+        out = np.zeros(4)
+        self.O.ORACLE_ConeEigen(self.h, dptr(np.ascontiguousarray(y)), cw, dptr(out))
+        return out
+
+    def prepare(self, y, cw, ew=1.0, affine=False):
+        out = np.zeros(2)
+        self.O.ORACLE_ConePrepare(self.h, dptr(np.ascontiguousarray(y)), int(affine), cw, ew, dptr(out))
+        return out
+
+    def take_step(self, step, ew=1.0):
+        self.O.ORACLE_ConeTakeStep(self.h, step, ew)
+
+
+def random_cone_data(kind, n, m, rng):
+    """rows x (m + 1) column-major block: operator columns then a strictly feasible affine term."""
+    rows = rows_of(kind, n)
+    cols = []
+    if kind == PSD:
+        for _ in range(m):
+            R = rng.uniform(-1, 1, size=(n, n))
+            cols.append((0.5 * (R + R.T)).ravel(order="F"))
+        cols.append(np.eye(n).ravel(order="F"))
+    elif kind == SOC:
+        for _ in range(m):
+            cols.append(rng.uniform(-1, 1, size=rows))
+        c = np.zeros(rows)
+        c[0] = 1.0
+        cols.append(c)
+    else:
+        for _ in range(m):
+            cols.append(rng.uniform(-1, 1, size=rows))
+        cols.append(np.ones(rows))
+    return np.concatenate(cols)
+
+
+def close(a, b, tol, what):
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b).max() / scale
+    assert err < tol, (what, err)
+
+
+SHAPES = [(LP, 1, 1), (LP, 7, 3), (LP, 40, 40), (SOC, 1, 2), (SOC, 10, 40), (SOC, 5, 3),
+          (PSD, 1, 2), (PSD, 2, 1), (PSD, 5, 3), (PSD, 20, 40), (PSD, 9, 4)]
+
+
+@pytest.mark.parametrize("kind,n,m", SHAPES)
+def test_cone_trajectory_matches_oracle(be, kind, n, m):
+    """Schur system, eigen-bounds, step norms and the updated scaling point along three damped
+    Newton-like steps, for a batch of 3 independent problems."""
+    rng = np.random.Generator(np.random.PCG64(1000 * kind + 10 * n + m))
+    B = 3
+    data = np.stack([random_cone_data(kind, n, m, rng) for _ in range(B)])
+    cone = be.cone(kind, n, m, data)
+    refs = [OracleCone(kind, n, m, data[p]) for p in range(B)]
+    for it in range(3):
+        G, AW, AQc, sc = cone.schur()
+        for p in range(B):
+            Go, AWo, AQco, sco = refs[p].schur()
+            dscale = np.sqrt(np.outer(np.diag(Go), np.diag(Go))) + 1e-300
+            assert (np.abs(G[p] - Go) / dscale).max() < 1e-10, ("H", it, p)
+            close(AW[p], AWo, 1e-10, "AW")
+            close(AQc[p], AQco, 1e-10, "AQc")
+            close(sc[p], sco, 1e-10, "scalars")
+        y = rng.uniform(-1, 1, size=(B, m)) * 0.3 / np.sqrt(m)
+        cw = rng.uniform(0.5, 1.5, size=B)
+        ev = cone.eigen(y, cw)
+        for p in range(B):
+            close(ev[p], refs[p].eigen(y[p], cw[p]), 1e-9, "eigen")
+        out = cone.prepare(y, cw, 1.0)
+        steps = np.zeros(B)
+        for p in range(B):
+            ro = refs[p].prepare(y[p], cw[p], 1.0)
+            close(out[p], ro, 1e-9, "prepare")
+            steps[p] = min(1.0, 2.0 / ro[0] ** 2)
+        info = cone.take_step(steps, 1.0)
+        assert (info == 0).all()
+        W = cone.get_state()
+        for p in range(B):
+            refs[p].take_step(steps[p], 1.0)
+            close(W[p], refs[p].state(), 1e-10, "W after step")
+
+
+@pytest.mark.parametrize("kind,n,m", [(LP, 6, 4), (PSD, 6, 4)])
+def test_affine_update_matches_oracle(be, kind, n, m):
+    # dual recovery: PrepareStep with affine = true, c_weight = e_weight = 0 (cone_program.cc:505-515)
+    rng = np.random.Generator(np.random.PCG64(77 + kind))
+    data = np.stack([random_cone_data(kind, n, m, rng) for _ in range(2)])
+    cone = be.cone(kind, n, m, data)
+    refs = [OracleCone(kind, n, m, data[p]) for p in range(2)]
+    y = rng.uniform(-1, 1, size=(2, m)) * 0.1
+    cone.prepare(y, 0.0, 0.0, affine=True)
+    W = cone.get_state()
+    for p in range(2):
+        refs[p].prepare(y[p], 0.0, 0.0, affine=True)
+        close(W[p], refs[p].state(), 1e-12, "W after affine update")
+
+
+def test_schur_accumulates_over_cones(be):
+    # several cones of one program add into the same H (supernodal_assembler.cc:144-164)
+    rng = np.random.Generator(np.random.PCG64(5))
+    m, B = 6, 2
+    kinds = [(PSD, 4), (SOC, 3), (LP, 5)]
+    total = None
+    ref = [None] * B
+    for kind, n in kinds:
+        data = np.stack([random_cone_data(kind, n, m, rng) for _ in range(B)])
+        cone = be.cone(kind, n, m, data)
+        got = cone.schur(accumulate_into=total)
+        total = cone.last
+        for p in range(B):
+            r = OracleCone(kind, n, m, data[p]).schur()
+            ref[p] = r if ref[p] is None else tuple(a + b for a, b in zip(ref[p], r))
+    for p in range(B):
+        for a, b, name in zip([g[p] for g in got], ref[p], ["H", "AW", "AQc", "scalars"]):
+            close(a, b, 1e-12, name)
+
+
+@pytest.mark.parametrize("N", [1, 2, 17, 40, 100])
+def test_small_cholesky_and_solve(be, N):
+    rng = np.random.Generator(np.random.PCG64(N))
+    B = 3
+    H = []
+    for _ in range(B):
+        R = rng.uniform(-1, 1, size=(N, N + 3))
+        H.append(R @ R.T + 0.1 * np.eye(N))
+    H = np.stack(H)
+    L, info, buf = be.potrf(H)
+    assert (info == 0).all()
+    for p in range(B):
+        close(L[p], np.linalg.cholesky(H[p]), 1e-12, "L")
+    X = rng.uniform(-1, 1, size=(B, N))
+    sol = be.potrs(buf, B, N, X)
+    for p in range(B):
+        close(sol[p], np.linalg.solve(H[p], X[p]), 1e-9, "solve")
+
+
+def test_small_cholesky_reports_first_bad_pivot(be):
+    # block_triangular_operations.cc:193-196: a non-positive pivot makes Factor() fail
+    H = np.stack([np.diag([1.0, 2.0, -1.0, 3.0]), np.eye(4)])
+    _, info, _ = be.potrf(H)
+    assert info.tolist() == [3, 0]
