@@ -561,6 +561,7 @@ def run_b200(args):
         "newton_steps_per_s": 1e3 / value,
         "step_tflops_fp64": fl["tensor"] / (value * 1e-3) / 1e12,
         "phase_ms": dict(zip(["assemble", "factor", "mu", "solve", "update"], ph_timed.tolist())),
+        "phase_ms_per_step": [[round(float(v), 3) for v in ph] for ph in phases[args.warmup:]],
         "roofline": {
             "bound": "tensor", "kernel": "DgemmKernel (K1 scaling GEMMs + K2 Gram, Schur assembly phase)",
             "achieved": achieved, "peak": peak_tf * world, "unit": "TFLOP/s",

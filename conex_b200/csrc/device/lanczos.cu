@@ -10,6 +10,10 @@
 // column, fully coalesced; for n = 2000 the two matrices stay resident in the 126 MB L2). The
 // n-vector recurrence is executed by the last CTA to finish (ticket counter), so one launch per
 // step suffices and the arithmetic order is fixed (deterministic).
+#include <cstring>
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "device_api.h"
 
@@ -98,9 +102,13 @@ __global__ void LanczosResetKernel(int n, double* work) {
 }
 
 // One Lanczos step (index j).
+// rel_tol == 0: the dense-LMI rule (stop when beta^2 < 1e-6, approximate_eigenvalues.cc:208);
+// rel_tol > 0: the Hermitian rule (stop when beta^2 < rel_tol * <U, U> of the first, not yet
+// orthogonalised, step — jordan_matrix_algebra.cc:421-433).
 __global__ void __launch_bounds__(256) LanczosStepKernel(int n, int j, int num_iter,
                                                          const double* __restrict__ WS, double* work,
-                                                         double* alpha, double* beta, int* count) {
+                                                         double* alpha, double* beta, int* count,
+                                                         double rel_tol) {
   __shared__ double scratch[33];
   __shared__ bool is_last;
   const LanczosBufs b = Carve(work, n);
@@ -128,6 +136,15 @@ __global__ void __launch_bounds__(256) LanczosStepKernel(int n, int j, int num_i
   double s = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += b.v0[i] * __ldcg(b.u1 + i);
   const double a = BlockSum(s, scratch);
+  double* scaling = reinterpret_cast<double*>(b.st) + 2;
+  if (rel_tol > 0 && j == 0) {
+    s = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __ldcg(b.u0 + i) * __ldcg(b.u1 + i);
+    const double raw = BlockSum(s, scratch);
+    if (threadIdx.x == 0) *scaling = raw;
+    __syncthreads();
+  }
+  const double threshold = (rel_tol > 0) ? rel_tol * (*scaling) : 1e-6;
   const double bprev = (j > 0) ? beta[j - 1] : 0.0;
   s = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -142,7 +159,7 @@ __global__ void __launch_bounds__(256) LanczosStepKernel(int n, int j, int num_i
     s += x0 * x1;
   }
   const double b2 = BlockSum(s, scratch);
-  bool stop = (j + 1 >= num_iter) || (b2 < 1e-6);
+  bool stop = (j + 1 >= num_iter) || (b2 < threshold);
   if (!stop) {
     const double bj = sqrt(b2);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -164,6 +181,46 @@ __global__ void __launch_bounds__(256) LanczosStepKernel(int n, int j, int num_i
 }
 
 }  // namespace
+
+namespace {
+
+// The chain of one transpose + one reset + one init + num_iter step launches.
+int EnqueueLanczos(cudaStream_t s, int n, const double* d_WS, const double* d_W, const double* d_r,
+                   const double* d_col_index, int num_iter, double* d_alpha, double* d_beta, int* d_count,
+                   double* d_work, double rel_tol) {
+  const LanczosBufs b = Carve(d_work, n);
+  int rc = Transpose(s, n, d_WS, b.WST);
+  if (rc) return rc;
+  const int grid = (n + 7) / 8;
+  CountLaunch(); LanczosResetKernel<<<1, 1, 0, s>>>(n, d_work);
+  CountLaunch(); LanczosInitKernel<<<grid, 256, 0, s>>>(n, d_W, d_r, d_col_index, d_work);
+  for (int j = 0; j < num_iter; j++) {
+    CountLaunch(); LanczosStepKernel<<<grid, 256, 0, s>>>(n, j, num_iter, d_WS, d_work, d_alpha, d_beta, d_count, rel_tol);
+  }
+  return LaunchStatus();
+}
+
+// Long chains (n/2 dependent launches of ~10 us kernels) are launch-bound from the host: they are
+// captured once per argument tuple into a CUDA graph and replayed with a single launch, so the
+// device runs the whole recurrence back to back whatever the host is doing.
+struct GraphKey {
+  int n, num_iter;
+  const void *ws, *w, *r, *col, *alpha, *beta, *count, *work;
+  double rel_tol;
+  bool operator<(const GraphKey& o) const {
+    return std::memcmp(this, &o, sizeof(GraphKey)) < 0;
+  }
+};
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  long launches = 0;
+};
+std::map<GraphKey, GraphEntry> g_graphs;
+std::mutex g_graph_mutex;
+constexpr int kGraphThreshold = 32;   // shorter chains are launched directly
+constexpr size_t kMaxGraphs = 64;
+
+}  // namespace
 }  // namespace cxb
 
 using namespace cxb;
@@ -175,18 +232,62 @@ size_t cxb_lanczos_worksize(int n) { return (size_t)n * n + 6 * (size_t)((n + 3)
 int cxb_lanczos_two_sided(void* stream, int n, const double* d_WS, const double* d_W,
                           const double* d_r, const double* d_col_index, int num_iter,
                           double* d_alpha, double* d_beta, int* d_count, double* d_work) {
+  return cxb_lanczos_two_sided_ex(stream, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count,
+                                  d_work, 0.0);
+}
+
+int cxb_lanczos_two_sided_ex(void* stream, int n, const double* d_WS, const double* d_W,
+                             const double* d_r, const double* d_col_index, int num_iter,
+                             double* d_alpha, double* d_beta, int* d_count, double* d_work,
+                             double rel_tol) {
   cudaStream_t s = AsStream(stream);
   if (n < 1 || num_iter < 1) return -1;
-  const LanczosBufs b = Carve(d_work, n);
-  int rc = Transpose(s, n, d_WS, b.WST);
-  if (rc) return rc;
-  const int grid = (n + 7) / 8;
-  CountLaunch(); LanczosResetKernel<<<1, 1, 0, s>>>(n, d_work);
-  CountLaunch(); LanczosInitKernel<<<grid, 256, 0, s>>>(n, d_W, d_r, d_col_index, d_work);
-  for (int j = 0; j < num_iter; j++) {
-    CountLaunch(); LanczosStepKernel<<<grid, 256, 0, s>>>(n, j, num_iter, d_WS, d_work, d_alpha, d_beta, d_count);
+  if (num_iter < kGraphThreshold || s == nullptr) {
+    return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
   }
-  return LaunchStatus();
+  GraphKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.n = n;
+  key.num_iter = num_iter;
+  key.ws = d_WS;
+  key.w = d_W;
+  key.r = d_r;
+  key.col = d_col_index;
+  key.alpha = d_alpha;
+  key.beta = d_beta;
+  key.count = d_count;
+  key.work = d_work;
+  key.rel_tol = rel_tol;
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  auto it = g_graphs.find(key);
+  if (it == g_graphs.end()) {
+    if (g_graphs.size() >= kMaxGraphs) {
+      for (auto& e : g_graphs) cudaGraphExecDestroy(e.second.exec);
+      g_graphs.clear();
+    }
+    const long before = g_launch_count;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+    }
+    const int rc = EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    GraphEntry entry;
+    entry.launches = g_launch_count - before;
+    g_launch_count = before;
+    if (rc != 0 || e != cudaSuccess || graph == nullptr ||
+        cudaGraphInstantiate(&entry.exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+    }
+    cudaGraphDestroy(graph);
+    it = g_graphs.emplace(key, entry).first;
+  }
+  g_launch_count += it->second.launches;
+  const cudaError_t e = cudaGraphLaunch(it->second.exec, s);
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
 }  // extern "C"

@@ -309,6 +309,34 @@ int cxb_pade_expm(void* stream, int n, const double* d_X, double* d_out, double*
   return PadeExpm(AsStream(stream), n, d_X, d_out, d_work, d_iwork, d_info);
 }
 
+int cxb_taylor_expm(void* stream, int n, const double* d_X, double* d_out, double* d_work) {
+  // (I + X/4 + X^2/32)^4 — DoExponentialMap<1>, exponential_map.cc:15-42 (degree 2, 2 squarings)
+  cudaStream_t s = AsStream(stream);
+  double* Y = d_work;
+  int rc = Dgemm(s, false, false, n, n, n, 1.0 / 32.0, d_X, n, 0, d_X, n, 0, 0.0, d_out, n, 0, 1, false);
+  if (rc) return rc;
+  if ((rc = ScaleAddDiag(s, n, d_X, 0.25, 1.0, Y))) return rc;                 // Y = I + X/4
+  if ((rc = cxb_axpbypcz(stream, (long)n * n, 1.0, d_out, 1.0, Y, 0.0, nullptr))) return rc;  // + X^2/32
+  if ((rc = Dgemm(s, false, false, n, n, n, 1.0, Y, n, 0, Y, n, 0, 0.0, d_out, n, 0, 1, false))) return rc;
+  if ((rc = Dgemm(s, false, false, n, n, n, 1.0, d_out, n, 0, d_out, n, 0, 0.0, Y, n, 0, 1, false))) return rc;
+  cudaMemcpyAsync(d_out, Y, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s);
+  return LaunchStatus();
+}
+
+int cxb_geodesic_update_taylor(void* stream, int n, double* d_W, double* d_WS, double e_weight,
+                               double scale, double* d_work) {
+  // hermitian_psd.cc:9-31: W <- sym( exp_taylor( scale (WS + e I) ) W ). d_work: 2 n^2 doubles.
+  cudaStream_t s = AsStream(stream);
+  const long nn = (long)n * n;
+  int rc = ShiftScale(s, n, d_WS, e_weight, scale);
+  if (rc) return rc;
+  double* E = d_work + nn;
+  if ((rc = cxb_taylor_expm(stream, n, d_WS, E, d_work))) return rc;
+  if ((rc = Dgemm(s, false, false, n, n, n, 1.0, E, n, 0, d_W, n, 0, 0.0, d_WS, n, 0, 1, false))) return rc;
+  cudaMemcpyAsync(d_W, d_WS, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s);
+  return Symmetrize(s, n, d_W);
+}
+
 int cxb_geodesic_update(void* stream, int n, double* d_W, double* d_WS, double e_weight,
                         double scale, double* d_work, int* d_iwork, int* d_info) {
   cudaStream_t s = AsStream(stream);

@@ -557,8 +557,18 @@ CONEX_STATUS CONEX_NewLinearMatrixInequality(void* p, int order, int hyper_compl
   CONEX_DEMAND(hyper_complex_dim == 1 || hyper_complex_dim == 2 || hyper_complex_dim == 4 ||
                    hyper_complex_dim == 8,
                "Hypercomplex dimension must be 1, 2, 4, or 8.");
-  CONEX_DEMAND(p, "Program pointer is null.");
-  return NotOnHotPath("CONEX_NewLinearMatrixInequality (HermitianPsdConstraint)");
+  CAST_PROGRAM_OR_FAIL(p, prg);
+  if (hyper_complex_dim != 1) {
+    return NotOnHotPath("CONEX_NewLinearMatrixInequality over the complex / quaternion / octonion algebras");
+  }
+  CONEX_DEMAND(prg->GetNumberOfVariables() >= 1, "Number of variables must be set first.");
+  return Guard(
+      [&]() -> int {
+        prg->AddConstraint(conex::HermitianPsdConstraint(order, prg->GetNumberOfVariables()));
+        *constraint_id = prg->NumberOfConstraints() - 1;
+        return CONEX_SUCCESS;
+      },
+      CONEX_FAILURE);
 }
 CONEX_STATUS CONEX_NewQuadraticCost(void* p, int* constraint_id) {
   CONEX_DEMAND(constraint_id, "Received output null pointer.");

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "../../../include/conex_b200_device.h"
 #include "communicator.h"
@@ -19,6 +20,7 @@ struct DenseLMIConstraint::Storage {
   DeviceBuffer<double> coef;     // [y; -k] for the slack GEMV
   DeviceBuffer<double> small;    // alpha | beta | reductions
   DeviceBuffer<int> iwork;       // LU pivots + permutation, Lanczos count, LU info
+  DeviceBuffer<double> rstart;   // Hermitian rule: the random Lanczos start vector
   int panel = 0;
   bool streamed = false;         // B holds one row panel only (cxb_schur_dense_lmi_streamed)
   // sharded blocks only
@@ -95,6 +97,54 @@ DenseLMIConstraint::DenseLMIConstraint(int n, int m, DevicePointers dev)
 
 const double* DenseLMIConstraint::device_matrices() const { return data_->Aall.get(); }
 
+void DenseLMIConstraint::ReloadMatrices(const double* A, const double* C) {
+  CudaCheck(cudaMemcpy(data_->Aall.get(), A, sizeof(double) * Sq(n_) * m_local_, cudaMemcpyHostToDevice),
+            "upload of LMI matrices");
+  CudaCheck(cudaMemcpy(data_->Aall.get() + Sq(n_) * m_local_, C, sizeof(double) * Sq(n_), cudaMemcpyHostToDevice),
+            "upload of LMI affine term");
+}
+
+// ---- HermitianPsdConstraint<Real> ------------------------------------------------------------------
+HermitianPsdConstraint::HermitianPsdConstraint(int n, int m)
+    : DenseLMIConstraint(n, m, std::vector<double>(Sq(n) * m, 0.0).data(), std::vector<double>(Sq(n), 0.0).data()),
+      host_(std::make_shared<Host>()) {
+  host_->A.assign(Sq(n) * m, 0.0);
+  host_->C.assign(Sq(n), 0.0);
+  set_hermitian_semantics(true);
+}
+
+DenseLMIConstraint* HermitianPsdConstraint::Synced() {
+  if (host_->dirty) {
+    ReloadMatrices(host_->A.data(), host_->C.data());
+    host_->dirty = false;
+  }
+  return this;
+}
+
+bool UpdateLinearOperator(HermitianPsdConstraint* o, double val, int var, int r, int c, int dim) {
+  const int n = o->order();
+  CONEX_DEMAND(dim < 1, "Complex dimension out of bounds.");
+  CONEX_DEMAND(r < n && c < n, "Matrix dimension out of bounds.");
+  CONEX_DEMAND((var >= 0) && (r >= 0) && (c >= 0), "Indices cannot be negative.");
+  CONEX_DEMAND(var < o->number_of_variables(), "Variable index out of bounds.");
+  double* A = o->host_->A.data() + Sq(n) * var;
+  A[static_cast<size_t>(c) * n + r] = val;
+  A[static_cast<size_t>(r) * n + c] = val;
+  o->host_->dirty = true;
+  return false;
+}
+
+bool UpdateAffineTerm(HermitianPsdConstraint* o, double val, int r, int c, int dim) {
+  const int n = o->order();
+  CONEX_DEMAND(dim < 1, "Complex dimension out of bounds.");
+  CONEX_DEMAND(r < n && c < n, "Matrix dimension out of bounds.");
+  CONEX_DEMAND((r >= 0) && (c >= 0), "Indices cannot be negative.");
+  o->host_->C[static_cast<size_t>(c) * n + r] = val;
+  o->host_->C[static_cast<size_t>(r) * n + c] = val;
+  o->host_->dirty = true;
+  return false;
+}
+
 void DenseLMIConstraint::EnsureScratch() {
   Storage& d = *data_;
   if (d.panel != 0) return;
@@ -139,6 +189,7 @@ void DenseLMIConstraint::EnsureScratch() {
   d.coef.Resize(m_ + 1);
   d.small.Resize(2 * (n_ / 2 + 2) + 8);
   d.iwork.Resize(2 * n_ + 8);
+  d.rstart.Resize(n_);
 }
 
 void SetIdentity(DenseLMIConstraint* o) {
@@ -309,14 +360,30 @@ DenseLMIConstraint::SpectrumEstimate DenseLMIConstraint::EstimateSpectrum(const 
   auto& d = *data_;
   void* s = ctx_->stream();
   const int n = n_;
-  const int num_iter = n / 2;
+  const int num_iter = hermitian_ ? n / 2 + 1 : n / 2;
   const int cap = n / 2 + 2;
   double* alpha = d.small.get();
   double* beta = alpha + cap;
   double* red = beta + cap;  // 8 slots
   int* count = d.iwork.get() + 2 * n;
   DeviceCheck(cxb_ws_reductions(s, n, WS.data, red), "cxb_ws_reductions");
-  if (n > 1 && num_iter >= 1) {
+  if (hermitian_) {
+    // T::Random(n, 1) = Eigen::MatrixXd::Random: n draws of -1 + 2 rand() / RAND_MAX
+    // (jordan_matrix_algebra.cc:81-87); drawn even for n == 1 so the libc stream stays aligned.
+    double* r = ctx_->pinned().get();
+    if (static_cast<size_t>(n) > ctx_->pinned().size()) {
+      ctx_->Synchronize();
+      ctx_->pinned().Reserve(n);
+      r = ctx_->pinned().get();
+    }
+    for (int i = 0; i < n; i++) r[i] = -1.0 + 2.0 * static_cast<double>(std::rand()) / static_cast<double>(RAND_MAX);
+    ctx_->Upload(d.rstart.get(), r, n);
+    if (n > 1) {
+      DeviceCheck(cxb_lanczos_two_sided_ex(s, n, WS.data, workspace_.W.data, d.rstart.get(), nullptr, num_iter,
+                                           alpha, beta, count, d.scratch.get(), 1e-5),
+                  "cxb_lanczos_two_sided_ex");
+    }
+  } else if (n > 1 && num_iter >= 1) {
     DeviceCheck(cxb_lanczos_two_sided(s, n, WS.data, workspace_.W.data, start_matrix.data, red + 2,
                                       num_iter, alpha, beta, count, d.scratch.get()),
                 "cxb_lanczos_two_sided");
@@ -379,6 +446,12 @@ bool TakeStep(DenseLMIConstraint* o, const StepOptions& opt) {
   // reference psd_constraint.cc:86-90 -> GeodesicUpdate :13-28
   auto& d = *o->data_;
   auto& w = o->workspace_;
+  if (o->hermitian_) {
+    DeviceCheck(cxb_geodesic_update_taylor(o->ctx_->stream(), o->n_, w.W.data, w.temp_2.data, opt.e_weight,
+                                           opt.step_size, d.scratch.get()),
+                "cxb_geodesic_update_taylor");
+    return true;
+  }
   DeviceCheck(cxb_geodesic_update(o->ctx_->stream(), o->n_, w.W.data, w.temp_2.data, opt.e_weight,
                                   opt.step_size, d.scratch.get(), d.iwork.get(),
                                   d.iwork.get() + 2 * o->n_ + 1),

@@ -60,6 +60,14 @@ class DenseLMIConstraint {
   double* mutable_device_matrices();  // local A_i blocks, then C
   int local_matrices() const { return m_local_; }
 
+  // Replaces the constraint matrices and the affine term (host data, same layout as the constructor).
+  void ReloadMatrices(const double* A, const double* C);
+  // Switches the eigen-bound and the exponential to the rules of the reference's incremental LMI
+  // (HermitianPsdConstraint<Real>, conex/hermitian_psd.cc): Lanczos started from an Eigen-style
+  // Random(n, 1) vector drawn with libc rand(), n/2 + 1 steps, relative breakdown test
+  // (jordan_matrix_algebra.cc:387-452); exp = (I + X/4 + X^2/32)^4 (exponential_map.cc:15-42).
+  void set_hermitian_semantics(bool on) { hermitian_ = on; }
+
   WorkspaceDensePSD* workspace() { return &workspace_; }
   int number_of_variables() const { return m_; }
   int order() const { return n_; }
@@ -94,9 +102,47 @@ class DenseLMIConstraint {
   int m_local_;       // constraint matrices held by this rank (== m_ when not sharded)
   int row_begin_ = 0;  // global index of the first local matrix
   bool sharded_ = false;
+  bool hermitian_ = false;
   WorkspaceDensePSD workspace_;
   std::shared_ptr<Storage> data_;
   DeviceContext* ctx_ = nullptr;
+};
+
+// The LMI built entry by entry through CONEX_NewLinearMatrixInequality / CONEX_UpdateLinearOperator /
+// CONEX_UpdateAffineTerm — the reference's HermitianPsdConstraint<Real> (conex/hermitian_psd.{h,cc}).
+// The host keeps the dense symmetric matrices it is given; they are uploaded when they changed since
+// the last use, and all device work is the dense-LMI path with the Hermitian eigen-bound and
+// exponential rules.
+class HermitianPsdConstraint : public DenseLMIConstraint {
+ public:
+  // order n, m variables (matrices of variables never updated stay zero)
+  HermitianPsdConstraint(int n, int m);
+
+  friend int Rank(const HermitianPsdConstraint& o) { return o.order(); }
+  friend void SetIdentity(HermitianPsdConstraint* o) { SetIdentity(o->Synced()); }
+  friend void ConstructSchurComplementSystem(HermitianPsdConstraint* o, bool initialize,
+                                             SchurComplementSystem* sys) {
+    ConstructSchurComplementSystem(o->Synced(), initialize, sys);
+  }
+  friend void PrepareStep(HermitianPsdConstraint* o, const StepOptions& opt, const Ref& y, StepInfo* info) {
+    PrepareStep(o->Synced(), opt, y, info);
+  }
+  friend bool TakeStep(HermitianPsdConstraint* o, const StepOptions& opt) { return TakeStep(o->Synced(), opt); }
+  friend void GetWeightedSlackEigenvalues(HermitianPsdConstraint* o, const Ref& y, double c_weight,
+                                          WeightedSlackEigenvalues* p) {
+    GetWeightedSlackEigenvalues(o->Synced(), y, c_weight, p);
+  }
+  // hermitian_psd.cc:248-322 for the real algebra
+  friend bool UpdateLinearOperator(HermitianPsdConstraint* o, double val, int var, int r, int c, int dim);
+  friend bool UpdateAffineTerm(HermitianPsdConstraint* o, double val, int r, int c, int dim);
+
+ private:
+  struct Host {
+    std::vector<double> A, C;
+    bool dirty = false;
+  };
+  DenseLMIConstraint* Synced();
+  std::shared_ptr<Host> host_;
 };
 
 }  // namespace conex

@@ -106,6 +106,14 @@ int cxb_lanczos_two_sided(void* stream, int n, const double* d_WS, const double*
                           const double* d_r, const double* d_col_index, int num_iter,
                           double* d_alpha, double* d_beta, int* d_count, double* d_work);
 
+/* Same with the breakdown rule of the incremental (Hermitian) LMI: rel_tol > 0 stops when
+ * beta^2 < rel_tol * <U, U> of the first step (jordan_matrix_algebra.cc:421-433, rel_tol = 1e-5);
+ * rel_tol == 0 is cxb_lanczos_two_sided. */
+int cxb_lanczos_two_sided_ex(void* stream, int n, const double* d_WS, const double* d_W,
+                             const double* d_r, const double* d_col_index, int num_iter,
+                             double* d_alpha, double* d_beta, int* d_count, double* d_work,
+                             double rel_tol);
+
 /* ---- K7 reductions (psd_constraint.cc:63-80,107-127). d_out slots (all device doubles):
  *   out[0] = tr(WS), out[1] = sum_ij WS_ij WS_ji = tr(WS WS), out[2] = argmax_i WS_ii (as double),
  *   out[3] = max_i WS_ii. */
@@ -118,6 +126,12 @@ int cxb_ws_reductions(void* stream, int n, const double* d_WS, double* d_out);
 size_t cxb_geodesic_worksize(int n);
 int cxb_geodesic_update(void* stream, int n, double* d_W, double* d_WS, double e_weight,
                         double scale, double* d_work, int* d_iwork, int* d_info);
+
+/* K9 exponential: d_out = (I + X/4 + X^2/32)^4 (DoExponentialMap<1>, exponential_map.cc:15-42);
+ * d_work: n*n doubles. And the geodesic update built on it (hermitian_psd.cc:9-31); d_work: 2 n*n. */
+int cxb_taylor_expm(void* stream, int n, const double* d_X, double* d_out, double* d_work);
+int cxb_geodesic_update_taylor(void* stream, int n, double* d_W, double* d_WS, double e_weight,
+                               double scale, double* d_work);
 
 /* Padé map alone: d_out = pade33(d_X) (exponential_map_pade.cc:23-32). d_X is preserved. */
 int cxb_pade_expm(void* stream, int n, const double* d_X, double* d_out, double* d_work,

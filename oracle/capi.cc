@@ -18,6 +18,7 @@
 using oracle::DenseLmiCone;
 using oracle::LinearCone;
 using oracle::SocCone;
+using oracle::HermitianLmiCone;
 using oracle::Program;
 
 namespace {
@@ -165,6 +166,15 @@ CONEX_STATUS CONEX_NewLorentzConeConstraint(void* p, int order, int* constraint_
   return CONEX_SUCCESS;
 }
 
+CONEX_STATUS CONEX_NewLinearMatrixInequality(void* p, int order, int hyper_complex_dim, int* constraint_id) {
+  // interfaces/conex.cc:287-316; only the real algebra is restated
+  if (order < 1 || !constraint_id || !p || hyper_complex_dim != 1) return CONEX_FAILURE;
+  Program* prog = Cast(p);
+  prog->AddCone(std::make_unique<HermitianLmiCone>(order, prog->NumberOfVariables()));
+  *constraint_id = prog->NumberOfConstraints() - 1;
+  return CONEX_SUCCESS;
+}
+
 CONEX_STATUS CONEX_NewLinearInequality(void* p, int num_rows, int* constraint_id) {
   // interfaces/conex.cc:318-329
   if (!constraint_id || !p) return CONEX_FAILURE;
@@ -181,8 +191,14 @@ CONEX_STATUS CONEX_UpdateLinearOperator(void* p, int constraint, double value, i
   // interfaces/conex.cc:365-373; linear_constraint.cc:207-216; soc_constraint.cc:237-247
   Program* prog = Cast(p);
   if (constraint < 0 || constraint >= prog->NumberOfConstraints()) return CONEX_FAILURE;
-  if (hyper_complex_dim != 0 || col != 0 || variable < 0 || row < 0) return CONEX_FAILURE;
-  if (variable >= prog->NumberOfVariables()) return CONEX_FAILURE;
+  if (variable < 0 || row < 0 || variable >= prog->NumberOfVariables()) return CONEX_FAILURE;
+  if (auto* lmi = dynamic_cast<HermitianLmiCone*>(prog->cone(constraint))) {
+    // hermitian_psd.cc:248-275
+    if (hyper_complex_dim != 0 || col < 0 || row >= lmi->order() || col >= lmi->order()) return CONEX_FAILURE;
+    lmi->SetOperatorEntry(variable, row, col, value);
+    return CONEX_SUCCESS;
+  }
+  if (hyper_complex_dim != 0 || col != 0) return CONEX_FAILURE;
   if (auto* lp = dynamic_cast<LinearCone*>(prog->cone(constraint))) {
     if (row >= lp->rows()) return CONEX_FAILURE;
     lp->SetOperatorEntry(row, variable, value);
@@ -201,7 +217,14 @@ CONEX_STATUS CONEX_UpdateAffineTerm(void* p, int constraint, double value, int r
   // interfaces/conex.cc:375-382; linear_constraint.cc:218-226; soc_constraint.cc:249-259
   Program* prog = Cast(p);
   if (constraint < 0 || constraint >= prog->NumberOfConstraints()) return CONEX_FAILURE;
-  if (hyper_complex_dim != 0 || col != 0 || row < 0) return CONEX_FAILURE;
+  if (row < 0) return CONEX_FAILURE;
+  if (auto* lmi = dynamic_cast<HermitianLmiCone*>(prog->cone(constraint))) {
+    // hermitian_psd.cc:284-313
+    if (hyper_complex_dim != 0 || col < 0 || row >= lmi->order() || col >= lmi->order()) return CONEX_FAILURE;
+    lmi->SetAffineEntry(row, col, value);
+    return CONEX_SUCCESS;
+  }
+  if (hyper_complex_dim != 0 || col != 0) return CONEX_FAILURE;
   if (auto* lp = dynamic_cast<LinearCone*>(prog->cone(constraint))) {
     if (row >= lp->rows()) return CONEX_FAILURE;
     lp->SetAffineEntry(row, value);
@@ -362,6 +385,14 @@ void ORACLE_ConeTakeStep(void* h, double step, double e_weight) {
   opt.e_weight = e_weight;
   opt.step_size = step;
   static_cast<OracleCone*>(h)->cone->TakeStep(opt);
+}
+
+void ORACLE_TaylorExpm(int n, const double* X, double* out) { oracle::ExponentialMapTaylor(n, X, out); }
+int ORACLE_HermitianLanczos(int n, const double* WS, const double* W, const double* r, int num_iter,
+                            double* out) {
+  const auto e = oracle::HermitianLanczos(n, WS, W, r, num_iter);
+  std::memcpy(out, e.data(), e.size() * sizeof(double));
+  return (int)e.size();
 }
 
 int ORACLE_SizeOfKKTSystem(void* p) { return Cast(p)->SizeOfKKTSystem(); }

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -617,6 +618,152 @@ void EqualityCone::PrepareStep(const StepOptions&, const double* y, StepInfo* in
   for (int i = 0; i < rows_; i++) lambda_[i] = y[nv_ + i];
   info->normsqrd = 0;
   info->norminfd = 0;
+}
+
+// ============================================================================================
+// Hermitian (real) LMI built incrementally
+// ============================================================================================
+
+std::vector<double> HermitianLanczos(int n, const double* WS, const double* W, const double* r,
+                                     int num_iter) {
+  // conex/jordan_matrix_algebra.cc:387-452 for d = 1
+  std::vector<double> v0(n), v1(n), u0(n), u1(n), p0(n), p1(n);
+  std::vector<double> alpha(std::max(num_iter, 1)), beta(std::max(num_iter - 1, 0));
+  for (int i = 0; i < n; i++) v1[i] = r[i];
+  Gemv(false, n, n, 1.0, W, n, r, 0.0, v0.data());
+  const double nrm = std::sqrt(Dot(n, v0.data(), v1.data()));
+  for (int i = 0; i < n; i++) {
+    v0[i] *= 1.0 / nrm;
+    v1[i] *= 1.0 / nrm;
+  }
+  Gemv(false, n, n, 1.0, WS, n, v0.data(), 0.0, u0.data());
+  Gemv(true, n, n, 1.0, WS, n, v1.data(), 0.0, u1.data());
+  const double scaling = Dot(n, u0.data(), u1.data());
+  alpha[0] = Dot(n, v0.data(), u1.data());
+  for (int i = 0; i < n; i++) {
+    u0[i] -= alpha[0] * v0[i];
+    u1[i] -= alpha[0] * v1[i];
+  }
+  int cnt = 0;
+  for (int j = 1; j < num_iter; j++) {
+    double b = Dot(n, u0.data(), u1.data());
+    if (b < 1e-5 * scaling) break;
+    b = std::sqrt(b);
+    beta[j - 1] = b;
+    p0 = v0;
+    p1 = v1;
+    for (int i = 0; i < n; i++) {
+      v0[i] = u0[i] * (1.0 / b);
+      v1[i] = u1[i] * (1.0 / b);
+    }
+    Gemv(false, n, n, 1.0, WS, n, v0.data(), 0.0, u0.data());
+    Gemv(true, n, n, 1.0, WS, n, v1.data(), 0.0, u1.data());
+    alpha[j] = Dot(n, v0.data(), u1.data());
+    for (int i = 0; i < n; i++) {
+      u0[i] = u0[i] - alpha[j] * v0[i] - b * p0[i];
+      u1[i] = u1[i] - alpha[j] * v1[i] - b * p1[i];
+    }
+    cnt++;
+  }
+  alpha.resize(cnt + 1);
+  beta.resize(cnt);
+  return TridiagonalEigenvalues(alpha, beta);
+}
+
+void ExponentialMapTaylor(int n, const double* X, double* result) {
+  // conex/exponential_map.cc:15-42 with squarings = 2, degree = 2
+  const size_t nn = (size_t)n * n;
+  std::vector<double> xpow(nn), y(nn), t(nn);
+  for (size_t k = 0; k < nn; k++) xpow[k] = X[k] * 1.0 / 4.0;
+  y = xpow;
+  for (int i = 0; i < n; i++) y[(size_t)i * n + i] += 1;
+  Gemm(false, false, n, n, n, 1.0, X, n, xpow.data(), n, 0.0, t.data(), n);
+  for (size_t k = 0; k < nn; k++) {
+    xpow[k] = t[k] * (1.0 / 2 * 1.0 / 4.0);
+    y[k] += xpow[k];
+  }
+  Gemm(false, false, n, n, n, 1.0, y.data(), n, y.data(), n, 0.0, xpow.data(), n);
+  Gemm(false, false, n, n, n, 1.0, xpow.data(), n, xpow.data(), n, 0.0, result, n);
+}
+
+namespace {
+// Eigen::MatrixXd::Random(n, 1): n draws of -1 + 2 rand() / RAND_MAX (Eigen 3.3 random<double>()).
+std::vector<double> EigenRandomVector(int n) {
+  std::vector<double> r(n);
+  for (int i = 0; i < n; i++) r[i] = -1.0 + 2.0 * double(std::rand()) / double(RAND_MAX);
+  return r;
+}
+}  // namespace
+
+HermitianLmiCone::HermitianLmiCone(int n, int m)
+    : DenseLmiCone(n, m, std::vector<double>((size_t)n * n * m, 0.0).data(),
+                   std::vector<double>((size_t)n * n, 0.0).data()) {}
+
+void HermitianLmiCone::PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) {
+  // conex/hermitian_psd.cc:34-74: minus_s and WS are distinct matrices here
+  const int n = n_;
+  View minus_s = temp_1_, WS = temp_2_;
+  ComputeNegativeSlack(opt.c_weight, y, minus_s);
+  Gemm(false, false, n, n, n, 1.0, W_.p, n, minus_s.p, n, 0.0, WS.p, n);
+  if (opt.affine) {
+    std::vector<double> WSW(WS.size());
+    Gemm(false, false, n, n, n, 1.0, WS.p, n, W_.p, n, 0.0, WSW.data(), n);
+    if (opt.e_weight != 0) {
+      for (size_t k = 0; k < W_.size(); k++) W_.p[k] *= (1 + opt.e_weight);
+    }
+    for (size_t k = 0; k < W_.size(); k++) W_.p[k] += WSW[k];
+    return;
+  }
+  const auto r = EigenRandomVector(n);
+  const auto eig = HermitianLanczos(n, WS.p, W_.p, r.data(), n / 2 + 1);
+  const double lambda_1 = std::fabs(opt.e_weight + eig.front());
+  const double lambda_2 = std::fabs(opt.e_weight + eig.back());
+  std::vector<double> WSWS(WS.size());
+  Gemm(false, false, n, n, n, 1.0, WS.p, n, WS.p, n, 0.0, WSWS.data(), n);
+  double tr2 = 0, tr = 0;
+  for (int i = 0; i < n; i++) {
+    tr2 += WSWS[(size_t)i * n + i];
+    tr += WS(i, i);
+  }
+  info->norminfd = std::max(lambda_1, lambda_2);
+  info->normsqrd = tr2 + 2 * tr + n;
+}
+
+bool HermitianLmiCone::TakeStep(const StepOptions& opt) {
+  // conex/hermitian_psd.cc:9-31
+  const int n = n_;
+  View WS = temp_2_;
+  for (int i = 0; i < n; i++) WS(i, i) += opt.e_weight;
+  if (opt.step_size != 1.0) {
+    for (size_t k = 0; k < WS.size(); k++) WS.p[k] *= opt.step_size;
+  }
+  std::vector<double> expWS(WS.size()), prod(WS.size());
+  ExponentialMapTaylor(n, WS.p, expWS.data());
+  Gemm(false, false, n, n, n, 1.0, expWS.data(), n, W_.p, n, 0.0, prod.data(), n);
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) W_(i, j) = (prod[(size_t)j * n + i] + prod[(size_t)i * n + j]) * .5;
+  return true;
+}
+
+void HermitianLmiCone::GetWeightedSlackEigenvalues(const double* y, double c_weight, SlackEigenvalues* p) {
+  // conex/hermitian_psd.cc:76-95
+  const int n = n_;
+  View minus_s = temp_1_, WS = temp_2_;
+  ComputeNegativeSlack(c_weight, y, minus_s);
+  Gemm(false, false, n, n, n, 1.0, W_.p, n, minus_s.p, n, 0.0, WS.p, n);
+  const auto r = EigenRandomVector(n);
+  const auto eig = HermitianLanczos(n, WS.p, W_.p, r.data(), n / 2 + 1);
+  p->lambda_max = -eig.front();
+  p->lambda_min = -eig.back();
+  std::vector<double> WSWS(WS.size());
+  Gemm(false, false, n, n, n, 1.0, WS.p, n, WS.p, n, 0.0, WSWS.data(), n);
+  double tr2 = 0, tr = 0;
+  for (int i = 0; i < n; i++) {
+    tr2 += WSWS[(size_t)i * n + i];
+    tr += WS(i, i);
+  }
+  p->frobenius_norm_squared = tr2;
+  p->trace = -tr;
 }
 
 }  // namespace oracle

@@ -93,7 +93,7 @@ enum class GramVariant {
 
 // DenseLMIConstraint (conex/dense_lmi_constraint.h:24-41) on a PsdConstraint
 // (conex/psd_constraint.h:39-65).
-class DenseLmiCone final : public Cone {
+class DenseLmiCone : public Cone {
  public:
   // A: m contiguous column-major n x n matrices (interfaces/conex.cc:143-151); C: n x n.
   DenseLmiCone(int n, int m, const double* A, const double* C);
@@ -114,13 +114,43 @@ class DenseLmiCone final : public Cone {
   GramVariant gram_variant = GramVariant::kAsWritten;
   View W_, temp_1_, temp_2_;
 
- private:
+ protected:
   void GeodesicUpdate(double scale, const StepOptions& opt, View WS);
   void AffineUpdate(double w_e, View WS);
   int n_, m_;
   std::vector<double> Avect_;  // n*n x m, column i = vec(A_i)
   std::vector<double> C_;      // n x n
 };
+
+// HermitianPsdConstraint<Real> (conex/hermitian_psd.{h,cc} on MatrixAlgebra<1>,
+// conex/jordan_matrix_algebra.cc, conex/exponential_map.cc): the LMI built entry by entry through
+// CONEX_NewLinearMatrixInequality / CONEX_UpdateLinearOperator. Same Schur complement as the dense
+// LMI cone, but its own eigen-bound (random start vector from libc rand() like Eigen's Random(),
+// n/2 + 1 Lanczos steps, relative breakdown test) and its own exponential (degree-2 Taylor with
+// two squarings instead of the Padé map).
+class HermitianLmiCone final : public DenseLmiCone {
+ public:
+  HermitianLmiCone(int n, int m);
+  void PrepareStep(const StepOptions& opt, const double* y, StepInfo* info) override;
+  bool TakeStep(const StepOptions& opt) override;
+  void GetWeightedSlackEigenvalues(const double* y, double c_weight, SlackEigenvalues* p) override;
+  // hermitian_psd.cc:248-322 (real algebra: symmetric pair set)
+  void SetOperatorEntry(int var, int r, int c, double v) {
+    Avect_[(size_t)var * n_ * n_ + (size_t)c * n_ + r] = v;
+    Avect_[(size_t)var * n_ * n_ + (size_t)r * n_ + c] = v;
+  }
+  void SetAffineEntry(int r, int c, double v) {
+    C_[(size_t)c * n_ + r] = v;
+    C_[(size_t)r * n_ + c] = v;
+  }
+  int order() const { return n_; }
+};
+// MatrixAlgebra<1>::ApproximateEigenvalues (jordan_matrix_algebra.cc:387-452): returns the Ritz
+// values (ascending).
+std::vector<double> HermitianLanczos(int n, const double* WS, const double* W, const double* r,
+                                     int num_iter);
+// DoExponentialMap<1> (exponential_map.cc:15-42): (I + X/4 + X^2/32)^4.
+void ExponentialMapTaylor(int n, const double* X, double* result);
 
 // LinearConstraint (conex/linear_constraint.h:14-89): c - A y >= 0 with A n x m.
 class LinearCone final : public Cone {

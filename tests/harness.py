@@ -101,6 +101,7 @@ class ConexLib:
                                                   C.c_int, c_double_p, C.c_int]
         L.CONEX_NewLorentzConeConstraint.argtypes = [C.c_void_p, C.c_int, c_int_p]
         L.CONEX_NewLinearInequality.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.CONEX_NewLinearMatrixInequality.argtypes = [C.c_void_p, C.c_int, C.c_int, c_int_p]
         L.CONEX_UpdateLinearOperator.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int,
                                                  C.c_int, C.c_int]
         L.CONEX_UpdateAffineTerm.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
@@ -211,6 +212,26 @@ class Program:
             cid = self.L.fn("AddSocConstraint")(self.h, order, Af.shape[1], dptr(Af), dptr(cf))
         self.cone_shapes.append((order + 1, 1))
         return cid
+
+    def add_hermitian_lmi(self, mats, Cmat):
+        """The incremental real LMI (HermitianPsdConstraint<Real>): CONEX_NewLinearMatrixInequality +
+        CONEX_UpdateLinearOperator / CONEX_UpdateAffineTerm on the lower triangle, as
+        interfaces/python/test/run_tests.py:5-21 does."""
+        n = Cmat.shape[0]
+        if self.m == 0:
+            assert self.L.lib.CONEX_SetNumberOfVariables(self.h, len(mats)) == 0
+            self.m = len(mats)
+        cid = C.c_int(-1)
+        assert self.L.lib.CONEX_NewLinearMatrixInequality(self.h, n, 1, C.byref(cid)) == 0
+        for r in range(n):
+            for c in range(r + 1):
+                if Cmat[r, c] != 0:
+                    assert self.L.lib.CONEX_UpdateAffineTerm(self.h, cid.value, float(Cmat[r, c]), r, c, 0) == 0
+                for v, M in enumerate(mats):
+                    if M[r, c] != 0:
+                        assert self.L.lib.CONEX_UpdateLinearOperator(self.h, cid.value, float(M[r, c]), v, r, c, 0) == 0
+        self.cone_shapes.append((n, n))
+        return cid.value
 
     def add_linear_incremental(self, A, c):
         """CONEX_NewLinearInequality + per-entry updates (interfaces/conex.cc:318-329)."""

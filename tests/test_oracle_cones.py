@@ -240,3 +240,71 @@ def test_product_pivot_order_matches_rldlt(n):
     for i, t in enumerate(tr):
         ref[i], ref[t] = ref[t], ref[i]
     assert list(perm) == ref
+
+
+def libc_srand(seed):
+    C.CDLL(None).srand(seed)
+
+
+def test_hermitian_lmi_known_answer():
+    # interfaces/python/test/run_tests.py:299-321 through the incremental API: y = (-1, -1) +- 1e-6
+    O = oracle()
+    A0 = np.zeros((3, 3)); A0[1, 0] = A0[0, 1] = -1.0
+    A1 = np.zeros((3, 3)); A1[2, 1] = A1[1, 2] = -1.0
+    P = O.program(2)
+    P.add_hermitian_lmi([A0, A1], np.diag([1.0, 2.0, 1.0]))
+    libc_srand(1)
+    solved, y = P.maximize([-1.0, -1.0])
+    assert solved == 1 and np.linalg.norm(y + 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("rank,dim", [(3, 2), (8, 5), (20, 4)])
+def test_hermitian_agrees_with_dense_lmi_under_tight_centering(rank, dim):
+    # conex/test/hermitian_psd_test.cc:24-63: the two LMI code paths agree to 1e-11
+    O = oracle()
+    rng = np.random.Generator(np.random.PCG64(rank * 10 + dim))
+    mats = []
+    for _ in range(dim):
+        R = rng.uniform(-1, 1, size=(rank, rank))
+        mats.append(R + R.T)
+    Cm = np.eye(rank)
+    cfg = O.default_config(inv_sqrt_mu_max=float(np.sqrt(1.0 / 1e-4)), final_centering_tolerance=1e-8,
+                           prepare_dual_variables=1)
+    P1 = O.program(dim)
+    P1.add_hermitian_lmi(mats, Cm)
+    b = P1.feasible_objective()
+    libc_srand(1)
+    s1, y1 = P1.maximize(b, cfg)
+    X1 = P1.dual_variable(0)
+    P2 = O.program()
+    P2.add_dense_lmi(mats, Cm)
+    s2, y2 = P2.maximize(b, cfg)
+    X2 = P2.dual_variable(0)
+    assert s1 == 1 and s2 == 1
+    assert np.linalg.norm(y1 - y2) < 1e-11
+    assert np.linalg.norm(X1 - X2) < 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 4, 9])
+def test_taylor_exponential_and_hermitian_lanczos(n):
+    O = oracle()
+    L = O.lib
+    L.ORACLE_TaylorExpm.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ORACLE_HermitianLanczos.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+    rng = np.random.Generator(np.random.PCG64(n))
+    X = np.asfortranarray(rng.uniform(-1, 1, size=(n, n)) * 0.2)
+    out = np.zeros((n, n), order="F")
+    L.ORACLE_TaylorExpm(n, dptr(X), dptr(out))
+    Y = np.eye(n) + X / 4 + X @ X / 32
+    assert np.abs(out - np.linalg.matrix_power(Y, 4)).max() < 1e-14
+    # exact spectrum after n steps for a symmetric positive W-weighted problem (cf. the 4x4 golden)
+    R = rng.uniform(-1, 1, size=(n, n))
+    W = np.asfortranarray(R @ R.T + np.eye(n))
+    S = rng.uniform(-1, 1, size=(n, n)); S = S + S.T
+    WS = np.asfortranarray(W @ S)
+    r = rng.uniform(-1, 1, size=n)
+    ritz = np.zeros(n + 1)
+    k = L.ORACLE_HermitianLanczos(n, dptr(WS), dptr(W), dptr(r), n, dptr(ritz))
+    ev = np.sort(np.linalg.eigvals(WS).real)
+    assert k == n and np.abs(np.sort(ritz[:k]) - ev).max() < 1e-8 * max(1.0, np.abs(ev).max())
