@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 
+# DRAM traffic of the assembly phase of one C2 Newton step (ncu --set full, see the roofline note)
+ASSEMBLY_TRAFFIC_C2 = 61 * (2.381e9 + 1.998e9) + 1.3545e12
+
 METRIC = "newton_step_ms"
 UNIT = "ms"
 
@@ -528,6 +531,10 @@ def run_b200(args):
     e2e_wall = time.perf_counter() - t0
     launches = L.CONEXB200_LaunchCount() - launches0
     e2e_its = max(P.status()["num_iterations"], 1)
+    e2e_step_ms = []
+    for i in range(e2e_its):
+        L.CONEXB200_GetIterationMilliseconds(P.h, i, ms.ctypes.data_as(C.POINTER(C.c_double)))
+        e2e_step_ms.append(round(float(ms[0]), 3))
     clocks = sampler.stop()
 
     value = float(timed.mean())
@@ -570,10 +577,16 @@ def run_b200(args):
                            "(MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 tensor = 37 TFLOP/s). "
                            "achieved counts the reference's dense flops (4mn^3 + m(m+1)n^2); the kernel "
                            "executes 3mn^3 + m(m+1)n^2 because W(A_i W) is symmetric, so frac can exceed 1",
-            "algorithmic_flops_per_step": asm_flops, "traffic": None,
+            "algorithmic_flops_per_step": asm_flops,
+            "traffic": ASSEMBLY_TRAFFIC_C2 if (w["kind"], n, m, world) == ("maxcut", 2000, 2000, 1) else None,
+            "traffic_note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of all DgemmKernel launches of one "
+                            "assembly phase, from profiles/r01_d_c2_dgemm_ncu_full.txt: 61 panels x (K1a 2.38 GB + K1b "
+                            "2.00 GB) + K2 1354.5 GB (tile re-reads of the two 64 GB operands at 36 % L2 hit; the kernel "
+                            "runs at 92.8 % DMMA-pipe active, so tensor-bound); algorithmic minimum 256 GB",
         },
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * m / e2e_its,
                 "d2h_bytes_per_step": 8 * m / e2e_its + 8 * (2 * (n // 2 + 2) + 8) * 2 + 4 * 8 + 4,
+                "device_step_ms": e2e_step_ms, "wall_ms": e2e_wall * 1e3,
                 "note": "CONEX_Maximize warm-start solve of K steps from host b to host y; "
                         "per-step D2H = Lanczos coefficients + scalars"},
         "gpu_launches": int(launches),
@@ -598,7 +611,7 @@ def main():
                     help="BASELINE.json configuration (c2 = MaxCut n=2000, the headline)")
     ap.add_argument("--size", dest="n", type=int, default=0, help="override the PSD order n")
     ap.add_argument("--constraints", dest="m", type=int, default=0, help="override the number of constraints m")
-    ap.add_argument("--assembly-mode", type=int, default=0, help="0 auto, 1 keep all W A_i W, 2 stream row panels")
+    ap.add_argument("--assembly-mode", type=int, default=0, help="0 auto, 1 classic (keep all W A_i W), 2 stream row panels, 3 symmetric form (packed L^T A_i L)")
     ap.add_argument("--programs", type=int, default=0, help="c3: number of programs in the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

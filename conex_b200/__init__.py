@@ -55,6 +55,20 @@ _lib.CONEX_GetDualVariable.argtypes = [_C.c_void_p, _C.c_int, _dp, _C.c_int, _C.
 _lib.CONEX_GetDualVariableSize.argtypes = [_C.c_void_p, _C.c_int]
 _lib.CONEX_SetDefaultOptions.argtypes = [_C.POINTER(CONEX_SolverConfiguration)]
 _lib.CONEX_GetIterationStats.argtypes = [_C.c_void_p, _C.POINTER(CONEX_IterationStats), _C.c_int]
+_ip = _C.POINTER(_C.c_int)
+_lib.CONEX_AddDenseLinearConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _dp, _C.c_int]
+_lib.CONEX_AddLinearInequalities.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _dp, _C.c_int, _dp, _C.c_int]
+_lib.CONEX_NewLinearMatrixInequality.argtypes = [_C.c_void_p, _C.c_int, _C.c_int, _ip]
+_lib.CONEX_NewLorentzConeConstraint.argtypes = [_C.c_void_p, _C.c_int, _ip]
+_lib.CONEX_NewLinearInequality.argtypes = [_C.c_void_p, _C.c_int, _ip]
+_lib.CONEX_UpdateLinearOperator.argtypes = [_C.c_void_p, _C.c_int, _C.c_double, _C.c_int, _C.c_int, _C.c_int,
+                                            _C.c_int]
+_lib.CONEX_UpdateAffineTerm.argtypes = [_C.c_void_p, _C.c_int, _C.c_double, _C.c_int, _C.c_int, _C.c_int]
+_lib.CONEXB200_CreateBatch.restype = _C.c_void_p
+_lib.CONEXB200_CreateBatch.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int]
+_lib.CONEXB200_DeleteBatch.argtypes = [_C.c_void_p]
+_lib.CONEXB200_BatchMaximize.argtypes = [_C.c_void_p, _dp, _C.POINTER(CONEX_SolverConfiguration), _dp, _ip]
+_lib.CONEXB200_BatchGetResults.argtypes = [_C.c_void_p, _ip, _dp, _dp, _dp]
 
 
 def device_available():
@@ -115,6 +129,58 @@ class Conex:
         _lib.CONEX_AddDenseLMIConstraint(self.a, _ptr(packed), n, n, m, _ptr(cf), n, n)
         self.num_constraints += 1
 
+    def AddLinearInequality(self, A, c):
+        """c - A y >= 0 (interfaces/python/ConexProgram.py:98-105)."""
+        Af = _np.asfortranarray(_np.asarray(A, dtype=_np.float64))
+        cf = _np.ascontiguousarray(_np.asarray(c, dtype=_np.float64).ravel())
+        _lib.CONEX_AddDenseLinearConstraint(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(cf), cf.shape[0])
+        self.m, self.n = Af.shape[1], Af.shape[0]
+        self.A.append(Af)
+        self.c.append(cf.reshape(-1, 1))
+        self.num_constraints += 1
+
+    def AddLinearInequalities(self, A, lb, ub):
+        """lb <= A y <= ub; rows with lb == ub become equality constraints (ConexProgram.py:107-114)."""
+        Af = _np.asfortranarray(_np.asarray(A, dtype=_np.float64))
+        lbf = _np.ascontiguousarray(_np.asarray(lb, dtype=_np.float64).ravel())
+        ubf = _np.ascontiguousarray(_np.asarray(ub, dtype=_np.float64).ravel())
+        _lib.CONEX_AddLinearInequalities(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(lbf), lbf.shape[0],
+                                         _ptr(ubf), ubf.shape[0])
+        self.A.append(Af)
+        self.c.append(ubf.reshape(-1, 1))
+        self.num_constraints += 1
+
+    def _new(self, fn, *args):
+        cid = _C.c_int(-1)
+        if fn(self.a, *args, _C.byref(cid)) != 0:
+            raise NameError("Failed to add constraint.")
+        self.num_constraints += 1
+        return cid.value
+
+    def NewLinearMatrixInequality(self, order, hyper_complex_dim):
+        cid = self._new(_lib.CONEX_NewLinearMatrixInequality, order, hyper_complex_dim)
+        self.c.append(_np.zeros((order, order)))
+        return cid
+
+    def NewLorentzConeConstraint(self, order):
+        cid = self._new(_lib.CONEX_NewLorentzConeConstraint, order)
+        self.c.append(_np.zeros((order + 1, 1)))
+        return cid
+
+    def NewLinearInequality(self, num_rows):
+        cid = self._new(_lib.CONEX_NewLinearInequality, num_rows)
+        self.c.append(_np.zeros((num_rows, 1)))
+        return cid
+
+    def UpdateLinearOperator(self, constraint, value, variable, row, col=0, hyper_complex_dim=0):
+        if _lib.CONEX_UpdateLinearOperator(self.a, constraint, float(value), variable, row, col,
+                                           hyper_complex_dim) != 0:
+            raise NameError("Failed to update operator.")
+
+    def UpdateAffineTerm(self, constraint, value, row, col=0, hyper_complex_dim=0):
+        if _lib.CONEX_UpdateAffineTerm(self.a, constraint, float(value), row, col, hyper_complex_dim) != 0:
+            raise NameError("Failed to update affine term.")
+
     def AddSparseLinearMatrixInequality(self, A, c, variables):
         A = _np.asarray(A, dtype=_np.float64)
         n, k = A.shape[1], A.shape[2]
@@ -143,10 +209,10 @@ class Conex:
     def GetDualVariables(self):
         x = []
         for i in range(self.num_constraints):
-            n = self.c[i].shape[0]
-            xi = _np.zeros(n * n)
-            _lib.CONEX_GetDualVariable(self.a, i, _ptr(xi), n, n)
-            x.append(xi.reshape((n, n), order="F"))
+            r, c = self.c[i].shape[0], self.c[i].shape[1]
+            xi = _np.zeros(r * c)
+            _lib.CONEX_GetDualVariable(self.a, i, _ptr(xi), r, c)
+            x.append(xi.reshape((r, c), order="F"))
         return x
 
     def GetIterationNumberStats(self, num):
@@ -157,3 +223,45 @@ class Conex:
     def GetIterationStats(self):
         last = self.GetIterationNumberStats(-1).iteration_number
         return [self.GetIterationNumberStats(i) for i in range(last + 1)]
+
+
+class ConexBatch:
+    """Many structurally identical `Conex` programs solved in lock step on one GPU
+    (CONEXB200_CreateBatch / CONEXB200_BatchMaximize, include/conex_b200.h). No counterpart in the
+    reference, which solves such programs one after the other."""
+
+    def __init__(self, programs):
+        self.count = len(programs)
+        self.m = programs[0].m
+        handles = (_C.c_void_p * self.count)(*[p.a for p in programs])
+        self.h = _C.c_void_p(_lib.CONEXB200_CreateBatch(handles, self.count))
+        if not self.h:
+            raise NameError("Failed to create the batch (programs must have identical structure).")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib.CONEXB200_DeleteBatch(self.h)
+
+    def Maximize(self, b, config=None):
+        """b: (count, m). Returns a list of Solution."""
+        if config is None:
+            config = programs_default_configuration()
+        b = _np.ascontiguousarray(_np.asarray(b, dtype=_np.float64))
+        if b.shape != (self.count, self.m):
+            raise NameError("Cost matrix dimension does not match the batch.")
+        y = _np.zeros((self.count, self.m))
+        status = (_C.c_int * self.count)()
+        if _lib.CONEXB200_BatchMaximize(self.h, _ptr(b), _C.byref(config), _ptr(y), status) < 0:
+            raise NameError("Batched solve failed.")
+        out = []
+        for p in range(self.count):
+            s = Solution()
+            s.y, s.status = y[p], status[p]
+            out.append(s)
+        return out
+
+
+def programs_default_configuration():
+    config = CONEX_SolverConfiguration()
+    _lib.CONEX_SetDefaultOptions(_C.byref(config))
+    return config

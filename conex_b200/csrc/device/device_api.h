@@ -19,6 +19,17 @@ int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool trans
             double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror,
             int diag_off = 0);
 
+// Structured variant: tri bit 0 = op(B) is lower triangular (op(B)[k, c] = 0 for k < c), bit 1 = op(A)
+// is upper triangular (op(A)[r, k] = 0 for k < r) — k-tiles inside the zero part are skipped, the
+// stored zeros cover the rest; pack = the (square, lower_only) result is written as packed 64 x 64
+// lower tiles, PackedSymmetricSize(n) doubles per matrix (stride sC), off-diagonal tiles scaled by
+// sqrt(2) so that the plain dot product of two packed symmetric matrices is their trace inner product.
+int DgemmStructured(cudaStream_t stream, int config, int splits, bool transA, bool transB, int M, int N,
+                    int K, double alpha, const double* A, long lda, long sA, const double* B, long ldb,
+                    long sB, double beta, double* C, long ldc, long sC, int batch, bool lower_only,
+                    bool mirror, int diag_off, int tri, bool pack);
+long PackedSymmetricSize(int n);
+
 // cholesky.cu: factors the block column [j0, j0 + w) x rows [j0, m) in place (w <= 512)
 int PotrfBlockColumn(cudaStream_t s, int m, int j0, int w, double* H, long ldh, int* info);
 

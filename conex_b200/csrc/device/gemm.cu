@@ -41,6 +41,9 @@ struct GemmArgs {
   int diag_off; // row offset of this block relative to the diagonal (trapezoids / row panels)
   int mirror;   // also store C[col, row] (requires lower, M == N)
   int tiles_m, tiles_n;
+  int tri;      // bit 0: op(B)[k, c] = 0 for k < c; bit 1: op(A)[r, k] = 0 for k < r: k-tiles that
+                // lie entirely in the zero part are skipped
+  int pack;     // store lower tiles (BM == BN) contiguously, off-diagonal ones scaled by sqrt(2)
   int splits;   // split-K factor (>1: partials go to `partials`, batch must be 1)
   int k_per_split;  // multiple of BK
   double* partials;  // splits x (M x N, ld = M)
@@ -156,8 +159,10 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
   const double* A = g.A + (long)blockIdx.z * g.sA;
   const double* B = g.B + (long)blockIdx.z * g.sB;
   double* C = g.C + (long)blockIdx.z * g.sC;
-  const int k_begin = blockIdx.y * g.k_per_split;
+  int k_begin = blockIdx.y * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
+  if (g.tri & 1) k_begin = max(k_begin, (n0 / BK) * BK);
+  if (g.tri & 2) k_begin = max(k_begin, (m0 / BK) * BK);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -244,6 +249,27 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
           if (c >= g.N) continue;
           if (g.lower && r + g.diag_off < c) continue;
           P[(long)c * g.M + r] = acc[i][j][e];
+        }
+      }
+    }
+    return;
+  }
+  if (g.pack) {
+    // Tile (tm, tn), tm >= tn, goes to slot tn * T - tn (tn - 1) / 2 + (tm - tn) of BM * BN doubles
+    // (column-major inside the tile). Entries beyond the matrix edge are exact zeros (zero-filled
+    // operands) and are stored too, so the packed vector has a fixed length.
+    const long slot = (long)tn * g.tiles_m - (long)tn * (tn - 1) / 2 + (tm - tn);
+    double* P = C + slot * (BM * BN);
+    const double sc = (tm == tn) ? g.alpha : g.alpha * 1.4142135623730951;
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+      const int rl = wm0 + i * 8 + gid;
+#pragma unroll
+      for (int j = 0; j < NI; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int cl = wn0 + j * 8 + tig * 2 + e;
+          P[cl * BM + rl] = sc * acc[i][j][e];
         }
       }
     }
@@ -349,7 +375,8 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
       }
     }
   }
-  if (batch != 1 || g.mirror) splits = 1;
+  if (batch != 1 || g.mirror || g.pack || g.tri) splits = 1;
+  if (g.pack && BM != BN) return -1;
   if (splits > kt_total) splits = kt_total > 0 ? kt_total : 1;
   g.splits = splits;
   const int kt_per = (kt_total + splits - 1) / (splits > 0 ? splits : 1);
@@ -408,9 +435,23 @@ int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool trans
             double alpha, const double* A, long lda, long sA, const double* B, long ldb, long sB,
             double beta, double* C, long ldc, long sC, int batch, bool lower_only, bool mirror,
             int diag_off) {
+  return DgemmStructured(stream, config, splits, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta,
+                         C, ldc, sC, batch, lower_only, mirror, diag_off, 0, false);
+}
+
+long PackedSymmetricSize(int n) {
+  const long t = (n + 63) / 64;
+  return t * (t + 1) / 2 * 4096;
+}
+
+int DgemmStructured(cudaStream_t stream, int config, int splits, bool transA, bool transB, int M, int N,
+                    int K, double alpha, const double* A, long lda, long sA, const double* B, long ldb,
+                    long sB, double beta, double* C, long ldc, long sC, int batch, bool lower_only,
+                    bool mirror, int diag_off, int tri, bool pack) {
   if (M <= 0 || N <= 0 || batch <= 0) return 0;
   if (K < 0) return -1;
   if (mirror && (!lower_only || M != N || diag_off != 0)) return -1;
+  if (pack && (!lower_only || M != N || diag_off != 0 || mirror || beta != 0.0)) return -1;
   GemmArgs g;
   g.M = M;
   g.N = N;
@@ -429,11 +470,14 @@ int DgemmEx(cudaStream_t stream, int config, int splits, bool transA, bool trans
   g.lower = lower_only ? 1 : 0;
   g.diag_off = diag_off;
   g.mirror = mirror ? 1 : 0;
+  g.tri = tri;
+  g.pack = pack ? 1 : 0;
   g.tiles_m = g.tiles_n = 0;
   g.splits = 1;
   g.k_per_split = K;
   g.partials = nullptr;
   if (config < 0) config = PickConfig(M, N);
+  if (pack && config != 0 && config != 2) config = 2;  // packing needs the 64 x 64 tile
   const bool vec2 = Aligned16(A) && Aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                     (sA % 2 == 0) && (sB % 2 == 0);
   const bool akc = transA, bkc = !transB;

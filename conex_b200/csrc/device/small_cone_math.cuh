@@ -18,8 +18,10 @@
 
 #ifdef __CUDACC__
 #define CXB_HD __device__ __forceinline__
+#define CXB_HOST_DEVICE __host__ __device__ inline
 #else
 #define CXB_HD inline
+#define CXB_HOST_DEVICE inline
 #endif
 
 namespace cxb {
@@ -279,7 +281,7 @@ CXB_HD void SocTakeStep(T& t, int o, double step, double* Wv, const double* d, d
 // =================================================================================================
 // Small dense PSD / LMI block of order n (n*n doubles per matrix fit in shared memory).
 // state: W, T1, T2 (n*n each, global). sm: shared scratch of 6 n*n + 8 n + 16 doubles.
-// work (global): (m + 1) n*n doubles for the scaled matrices W A_i W, W C W.
+// work (global): (m + 2) n*n doubles for the scaled matrices W A_i W, W C W and a copy of W.
 // =================================================================================================
 // C = A * B (n x n, column-major, all three distinct)
 template <class T>
@@ -298,29 +300,152 @@ CXB_HD void PsdSetIdentity(T& t, int n, double* W) {
 }
 
 // H_ij = <W A_i W, A_j> (lower), AW_j = <W, A_j>, AQc_j = <W C W, A_j>, <w,c> = <W, C>,
-// <c,Qc> = <W C W, C>  (dense_lmi_constraint.cc:62-103)
+// <c,Qc> = <W C W, C>  (dense_lmi_constraint.cc:62-103).
+//
+// Phase A scales the matrices, B_i = W (A_i W), `group` matrices at a time with 4 x 4 register tiles
+// (per k: two 4-vectors from shared memory feed 16 FMAs); T = A_i W is kept row-major so that both
+// operands of the second product are contiguous. Phase B is the Gram contraction C = B^T A over the
+// n^2 entries (an (m+2) x (m+1) x n^2 GEMM, lower tiles only) with 4 x 2 register tiles, the
+// operands staged through shared memory in chunks of kGramChunk entries (coalesced global reads)
+// and the accumulators parked in shared memory between chunks.
+// work (global): (m + 2) n^2 doubles. sm: PsdSchurSmemDoubles(n, m, team size) doubles.
+constexpr int kGramChunk = 40;
+CXB_HOST_DEVICE int PsdSchurGroup(int n, int team) {
+  const int tn = (n + 3) / 4;
+  const int g = team / (tn * tn);
+  return g < 1 ? 1 : g;
+}
+CXB_HOST_DEVICE long PsdSchurSmemDoubles(int n, int m, int team) {
+  const long nn = (long)n * n;
+  const long a = nn + 2 * PsdSchurGroup(n, team) * nn;
+  const long ti = (m + 2 + 3) / 4, tj = (m + 1 + 1) / 2;
+  const long b = (long)(2 * m + 3) * (kGramChunk + 1) + ti * tj * 8;
+  return a > b ? a : b;
+}
+
 template <class T>
 CXB_HD void PsdSchur(T& t, int n, int m, const double* AC, const double* W, double* work, double* sm,
                      double* G, long ldg, double* AW, double* AQc, double* scal, bool acc) {
   const int nn = n * n;
-  double* sW = sm;
-  double* sA = sm + nn;
-  double* sT = sm + 2 * nn;
-  t.par(nn, [&](int e) { sW[e] = W[e]; });
-  for (int i = 0; i <= m; i++) {
-    const double* Ai = AC + (long)i * nn;
-    t.par(nn, [&](int e) { sA[e] = Ai[e]; });
-    MatMul(t, n, sA, sW, sT);                   // T = A_i W
-    MatMul(t, n, sW, sT, work + (long)i * nn);  // B_i = W T
+  const int tn = (n + 3) / 4, tiles = tn * tn;
+  const int group = PsdSchurGroup(n, t.size());
+  // ---- phase A ---------------------------------------------------------------------------------------
+  {
+    double* sW = sm;
+    double* sA = sm + nn;
+    double* sT = sA + (long)group * nn;
+    t.par(nn, [&](int e) { sW[e] = W[e]; });
+    for (int i0 = 0; i0 <= m; i0 += group) {
+      const int gc = (m + 1 - i0 < group) ? m + 1 - i0 : group;
+      const double* src = AC + (long)i0 * nn;
+      t.par(gc * nn, [&](int e) { sA[e] = src[e]; });
+      // T = A W, stored row-major: sT[r * n + c]. W is symmetric: W[k][c] = sW[k * n + c].
+      t.par(gc * tiles, [&](int w) {
+        const int g = w / tiles, tile = w % tiles;
+        const int r0 = (tile % tn) * 4, c0 = (tile / tn) * 4;
+        const double* A = sA + (long)g * nn;
+        double c[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int k = 0; k < n; k++) {
+          double a[4], b[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) a[x] = (r0 + x < n) ? A[k * n + r0 + x] : 0.0;
+#pragma unroll
+          for (int y = 0; y < 4; y++) b[y] = (c0 + y < n) ? sW[k * n + c0 + y] : 0.0;
+#pragma unroll
+          for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) c[x][y] += a[x] * b[y];
+        }
+        double* Tg = sT + (long)g * nn;
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++)
+            if (r0 + x < n && c0 + y < n) Tg[(r0 + x) * n + c0 + y] = c[x][y];
+      });
+      // B = W T -> global work (column-major)
+      t.par(gc * tiles, [&](int w) {
+        const int g = w / tiles, tile = w % tiles;
+        const int r0 = (tile % tn) * 4, c0 = (tile / tn) * 4;
+        const double* Tg = sT + (long)g * nn;
+        double c[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int k = 0; k < n; k++) {
+          double a[4], b[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) a[x] = (r0 + x < n) ? sW[k * n + r0 + x] : 0.0;
+#pragma unroll
+          for (int y = 0; y < 4; y++) b[y] = (c0 + y < n) ? Tg[k * n + c0 + y] : 0.0;
+#pragma unroll
+          for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) c[x][y] += a[x] * b[y];
+        }
+        double* Bg = work + (long)(i0 + g) * nn;
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+          for (int x = 0; x < 4; x++)
+            if (r0 + x < n && c0 + y < n) Bg[(c0 + y) * n + r0 + x] = c[x][y];
+      });
+    }
+    t.par(nn, [&](int e) { work[(long)(m + 1) * nn + e] = sW[e]; });  // row m + 1 of the Gram: W itself
   }
-  // rows i = 0..m+1 of the augmented Gram (row m: W C W, row m+1: W), columns j = 0..m
-  t.par((m + 2) * (m + 1), [&](int e) {
-    const int i = e % (m + 2), j = e / (m + 2);
-    if (i < j) return;
-    const double* Bi = (i <= m) ? work + (long)i * nn : sW;
-    const double* Aj = AC + (long)j * nn;
-    double s = 0;
-    for (int q = 0; q < nn; q++) s += Bi[q] * Aj[q];
+  // ---- phase B ---------------------------------------------------------------------------------------
+  const int MI = m + 2, MJ = m + 1;
+  const int ti = (MI + 3) / 4, tj = (MJ + 1) / 2;
+  const int P = kGramChunk + 1;
+  double* sB = sm;
+  double* sAc = sm + (long)MI * P;
+  double* sAcc = sAc + (long)MJ * P;
+  t.par(ti * tj * 8, [&](int e) { sAcc[e] = 0.0; });
+  for (int q0 = 0; q0 < nn; q0 += kGramChunk) {
+    const int kc = (nn - q0 < kGramChunk) ? nn - q0 : kGramChunk;
+    t.par((MI + MJ) * kc, [&](int e) {
+      const int row = e / kc, q = e % kc;
+      if (row < MI) {
+        sB[row * P + q] = work[(long)row * nn + q0 + q];
+      } else {
+        sAc[(row - MI) * P + q] = AC[(long)(row - MI) * nn + q0 + q];
+      }
+    });
+    t.par(ti * tj, [&](int w) {
+      const int i0 = (w % ti) * 4, j0 = (w / ti) * 2;
+      if (i0 + 3 < j0) return;  // tile entirely above the diagonal
+      double c[4][2];
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        c[x][0] = sAcc[w * 8 + 2 * x];
+        c[x][1] = sAcc[w * 8 + 2 * x + 1];
+      }
+      const double* b0 = sB + (long)(i0 + 0 < MI ? i0 + 0 : MI - 1) * P;
+      const double* b1 = sB + (long)(i0 + 1 < MI ? i0 + 1 : MI - 1) * P;
+      const double* b2 = sB + (long)(i0 + 2 < MI ? i0 + 2 : MI - 1) * P;
+      const double* b3 = sB + (long)(i0 + 3 < MI ? i0 + 3 : MI - 1) * P;
+      const double* a0 = sAc + (long)(j0 + 0 < MJ ? j0 + 0 : MJ - 1) * P;
+      const double* a1 = sAc + (long)(j0 + 1 < MJ ? j0 + 1 : MJ - 1) * P;
+      for (int q = 0; q < kc; q++) {
+        const double x0 = b0[q], x1 = b1[q], x2 = b2[q], x3 = b3[q], y0 = a0[q], y1 = a1[q];
+        c[0][0] += x0 * y0;
+        c[0][1] += x0 * y1;
+        c[1][0] += x1 * y0;
+        c[1][1] += x1 * y1;
+        c[2][0] += x2 * y0;
+        c[2][1] += x2 * y1;
+        c[3][0] += x3 * y0;
+        c[3][1] += x3 * y1;
+      }
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        sAcc[w * 8 + 2 * x] = c[x][0];
+        sAcc[w * 8 + 2 * x + 1] = c[x][1];
+      }
+    });
+  }
+  t.par(ti * tj * 8, [&](int e) {
+    const int w = e / 8, x = (e % 8) / 2, y = e % 2;
+    const int i = (w % ti) * 4 + x, j = (w / ti) * 2 + y;
+    if (i >= MI || j >= MJ || i < j) return;
+    const double s = sAcc[e];
     if (i < m) {
       Accumulate(G + (long)j * ldg + i, s, acc);
     } else if (i == m) {

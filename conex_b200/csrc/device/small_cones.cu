@@ -34,6 +34,9 @@ size_t PsdSmemDoubles(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64; }
 size_t SmemBytes(const ConeArgs& c) {
   return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? PsdSmemDoubles(c.n) : 0));
 }
+size_t SchurSmemBytes(const ConeArgs& c) {
+  return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? (size_t)small::PsdSchurSmemDoubles(c.n, c.m, kThreads) : 0));
+}
 
 __global__ void __launch_bounds__(kThreads) SetIdentityKernel(ConeArgs c, const int* active) {
   extern __shared__ double sm[];
@@ -223,7 +226,7 @@ size_t cxb_small_state_size(int type, int n) {
 size_t cxb_small_work_size(int type, int n, int m) {
   if (type == CXB_CONE_LP) return 0;
   if (type == CXB_CONE_SOC) return (size_t)(n + 1) * (m + 4);
-  return (size_t)(m + 1) * n * n;
+  return (size_t)(m + 2) * n * n;
 }
 
 int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active) {
@@ -240,7 +243,7 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
-  const size_t smem = SmemBytes(c);
+  const size_t smem = SchurSmemBytes(c);
   int rc = EnsureSmem(SchurKernel, smem);
   if (rc) return rc;
   CountLaunch(); SchurKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dG, ldg, gstride, dAW, dAQc, vstride,

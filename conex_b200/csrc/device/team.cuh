@@ -15,6 +15,8 @@ struct DeviceTeam {
 
   __device__ DeviceTeam(double* scratch) : tid(threadIdx.x), nt(blockDim.x), red(scratch) {}
 
+  __device__ __forceinline__ int size() const { return nt; }
+
   template <class F>
   __device__ __forceinline__ void par(int n, F f) {
     for (int i = tid; i < n; i += nt) f(i);

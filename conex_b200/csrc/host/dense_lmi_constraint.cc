@@ -15,6 +15,9 @@ namespace conex {
 struct DenseLMIConstraint::Storage {
   DeviceBuffer<double> Aall;     // n^2 x (m+1): constraint matrices then C
   DeviceBuffer<double> B;        // n^2 x (m+2): W A_i W, W C W, W        (K1 output / K2 operand)
+  DeviceBuffer<double> X;        // symmetric form: packed L^T A_i L, L^T C L, I  ((m+2) x packed size)
+  DeviceBuffer<double> Lw;       // symmetric form: Cholesky factor of W
+  bool symmetric = false;        // assemble through cxb_schur_dense_lmi_sym
   DeviceBuffer<double> T;        // panel scratch for A_i W
   DeviceBuffer<double> scratch;  // Lanczos / Padé / LU work
   DeviceBuffer<double> coef;     // [y; -k] for the slack GEMV
@@ -149,15 +152,19 @@ void DenseLMIConstraint::EnsureScratch() {
   Storage& d = *data_;
   if (d.panel != 0) return;
   const size_t nn = Sq(n_);
-  // Keep every scaled matrix W A_i W (one GEMM for the whole Gram) when a second A-sized buffer fits
-  // next to ~4 GiB of other scratch; otherwise stream row panels through a bounded buffer.
+  // Modes: symmetric form (packed L^T A_i L, 0.54 A-sized second buffer; default when it fits), classic
+  // form keeping every W A_i W (needed by the sharded exchange), or row panels through a bounded buffer.
+  const size_t kp = cxb_packed_symmetric_size(n_);
+  const size_t sym_bytes = sizeof(double) * (kp * (m_local_ + 2) + nn);
   const size_t full_bytes = sizeof(double) * nn * (m_local_ + 2);
   size_t free_bytes = 0, total_bytes = 0;
   CudaCheck(cudaMemGetInfo(&free_bytes, &total_bytes), "cudaMemGetInfo");
   const size_t other = sizeof(double) * (4 * nn + (size_t(1) << 28)) + (size_t(2) << 30);
-  d.streamed = !sharded_ && (ctx_->assembly_mode == 2 ||
-                             (ctx_->assembly_mode == 0 && full_bytes + other > free_bytes));
-  if (sharded_ && full_bytes + other > free_bytes) {
+  const int mode = ctx_->assembly_mode;
+  d.symmetric = (mode == 3 || (mode == 0 && sym_bytes + other <= free_bytes)) && !(sharded_ && mode == 1);
+  d.streamed = !sharded_ && !d.symmetric &&
+               (mode == 2 || ((mode == 0 || mode == 3) && full_bytes + other > free_bytes));
+  if (sharded_ && !d.symmetric && full_bytes + other > free_bytes) {
     throw std::runtime_error("conex-b200: the scaled matrices of this shard do not fit in HBM; use more ranks");
   }
   // Constraint matrices scaled per pass. Streamed: a multiple of the 64-row GEMM tile, <= 2 GiB.
@@ -166,7 +173,12 @@ void DenseLMIConstraint::EnsureScratch() {
   if (d.streamed && panel >= 64) panel -= panel % 64;
   d.panel = static_cast<int>(panel);
   d.T.Resize(nn * d.panel);
-  d.B.Resize(d.streamed ? nn * (d.panel + 1) : nn * (m_local_ + 2));
+  if (d.symmetric) {
+    d.X.Resize(kp * (m_local_ + 2));
+    d.Lw.Resize(nn);
+  } else {
+    d.B.Resize(d.streamed ? nn * (d.panel + 1) : nn * (m_local_ + 2));
+  }
   if (sharded_) {
     const long ldl = WorkspaceSchurComplement::AugLd(m_local_);
     d.Hloc.Resize(static_cast<size_t>(ldl) * (m_local_ + 1));
@@ -178,7 +190,7 @@ void DenseLMIConstraint::EnsureScratch() {
     size_t chunk = std::min<size_t>(largest, (size_t(1) << 29) / nn);
     if (chunk >= 64) chunk -= chunk % 64;
     d.chunk = static_cast<int>(std::max<size_t>(1, chunk));
-    for (auto& r : d.recv) r.Resize(nn * d.chunk);
+    for (auto& r : d.recv) r.Resize((d.symmetric ? kp : nn) * d.chunk);
     CudaCheck(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (auto& e : d.arrived) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
     for (auto& e : d.consumed) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
@@ -209,6 +221,20 @@ void ConstructSchurComplementSystem(DenseLMIConstraint* o, bool initialize,
   }
   if (o->sharded_) {
     o->AssembleSharded(sys);
+  } else if (d.symmetric) {
+    int* flag = o->ctx_->flags() + 4;
+    DeviceCheck(cxb_schur_dense_lmi_sym(s, o->n_, m, d.Aall.get(), o->workspace_.W.data, d.X.get(), d.T.get(),
+                                        d.panel, d.Lw.get(), flag, sys->G.data, sys->G.ld),
+                "cxb_schur_dense_lmi_sym");
+    int w_not_pd = 0;
+    o->ctx_->DownloadInts(&w_not_pd, flag, 1);
+    if (w_not_pd != 0) {
+      // W lost numerical positive definiteness: the classic form does not need its Cholesky factor
+      if (d.B.size() == 0) d.B.Resize(Sq(o->n_) * (o->m_local_ + 2));
+      DeviceCheck(cxb_schur_dense_lmi(s, o->n_, m, d.Aall.get(), o->workspace_.W.data, d.B.get(), d.T.get(),
+                                      d.panel, sys->G.data, sys->G.ld),
+                  "cxb_schur_dense_lmi");
+    }
   } else if (d.streamed) {
     DeviceCheck(cxb_schur_dense_lmi_streamed(s, o->n_, m, d.Aall.get(), o->workspace_.W.data, d.B.get(),
                                              d.T.get(), d.panel, sys->G.data, sys->G.ld),
@@ -245,11 +271,16 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
   const long ldg = sys->G.ld;
   const long ldl = WorkspaceSchurComplement::AugLd(ml);
   double* G = sys->G.data;
+  // Symmetric form: every block of H is a product of packed scaled matrices X = L^T A L (W = L L^T,
+  // factored redundantly and identically on every rank), and it is X that travels between ranks
+  // (0.54 of the bytes of the raw matrices). Classic form: local W A_i W against the peers' raw A_j.
+  const bool sym = d.symmetric;
+  const long stride = sym ? static_cast<long>(cxb_packed_symmetric_size(n)) : nn;
+  const double* local_scaled = sym ? d.X.get() : d.B.get();
+  const double* send_source = sym ? d.X.get() : d.Aall.get();
+  int* flag = ctx_->flags() + 4;
 
   CudaCheck(cudaMemsetAsync(G, 0, sizeof(double) * ldg * (m + 1), s), "memset of H");
-  // The side stream may start moving peer matrices as soon as this assembly begins.
-  CudaCheck(cudaEventRecord(d.start, s), "cudaEventRecord");
-  CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.start, 0), "cudaStreamWaitEvent");
 
   // -- exchange schedule: a flat list of chunks over all distances --------------------------------
   struct Chunk {
@@ -288,17 +319,31 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
     const Chunk& ch = chunks[c];
     const int buf = static_cast<int>(c % 2);
     if (c >= 2) CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.consumed[buf], 0), "cudaStreamWaitEvent");
-    const double* src = ch.send_count ? d.Aall.get() + static_cast<long>(ch.send_begin - rb) * nn : nullptr;
-    comm.SendRecv(src, static_cast<size_t>(ch.send_count) * nn, ch.to, d.recv[buf].get(),
-                  static_cast<size_t>(ch.recv_count) * nn, ch.from, d.comm_stream);
+    const double* src = ch.send_count ? send_source + static_cast<long>(ch.send_begin - rb) * stride : nullptr;
+    comm.SendRecv(src, static_cast<size_t>(ch.send_count) * stride, ch.to, d.recv[buf].get(),
+                  static_cast<size_t>(ch.recv_count) * stride, ch.from, d.comm_stream);
     CudaCheck(cudaEventRecord(d.arrived[buf], d.comm_stream), "cudaEventRecord");
   };
-  if (!chunks.empty()) post(0);
+  auto release_side_stream = [&]() {
+    CudaCheck(cudaEventRecord(d.start, s), "cudaEventRecord");
+    CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.start, 0), "cudaStreamWaitEvent");
+    if (!chunks.empty()) post(0);
+  };
+  // Classic form: the raw matrices can travel while the local block is computed. Symmetric form: the
+  // scaled matrices exist only after the local K1, so the first transfer starts after the local block.
+  if (!sym) release_side_stream();
 
-  // -- 1. local diagonal block (overlaps the first transfer) --------------------------------------
-  DeviceCheck(cxb_schur_dense_lmi(s, n, ml, d.Aall.get(), workspace_.W.data, d.B.get(), d.T.get(),
-                                  d.panel, d.Hloc.get(), ldl),
-              "cxb_schur_dense_lmi(local block)");
+  // -- 1. local diagonal block ----------------------------------------------------------------------
+  if (sym) {
+    DeviceCheck(cxb_schur_dense_lmi_sym(s, n, ml, d.Aall.get(), workspace_.W.data, d.X.get(), d.T.get(), d.panel,
+                                        d.Lw.get(), flag, d.Hloc.get(), ldl),
+                "cxb_schur_dense_lmi_sym(local block)");
+    release_side_stream();
+  } else {
+    DeviceCheck(cxb_schur_dense_lmi(s, n, ml, d.Aall.get(), workspace_.W.data, d.B.get(), d.T.get(),
+                                    d.panel, d.Hloc.get(), ldl),
+                "cxb_schur_dense_lmi(local block)");
+  }
   // H[rb.., rb..] <- Hloc[0:ml, 0:ml]; rows m, m+1 (AQc, AW) <- rows ml, ml+1 of the local columns
   CudaCheck(cudaMemcpy2DAsync(G + static_cast<long>(rb) * ldg + rb, sizeof(double) * ldg, d.Hloc.get(),
                               sizeof(double) * ldl, sizeof(double) * ml, ml, cudaMemcpyDeviceToDevice, s),
@@ -321,17 +366,17 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
     CudaCheck(cudaStreamWaitEvent(s, d.arrived[buf], 0), "cudaStreamWaitEvent");
     if (ch.recv_count > 0) {
       const PairTask& t = *ch.task;
-      const double* Bl = d.B.get() + static_cast<long>(t.row_begin - rb) * nn;
+      const double* Bl = local_scaled + static_cast<long>(t.row_begin - rb) * stride;
       if (t.peer < comm.rank()) {
-        // block below the diagonal: H[rows, cols] = B_rows^T A_cols
-        DeviceCheck(cxb_dgemm(s, 1, 0, t.row_count, ch.recv_count, static_cast<int>(nn), 1.0, Bl, nn, 0,
-                              d.recv[buf].get(), nn, 0, 0.0,
+        // block below the diagonal: H[rows, cols] = <scaled rows, received cols>
+        DeviceCheck(cxb_dgemm(s, 1, 0, t.row_count, ch.recv_count, static_cast<int>(stride), 1.0, Bl, stride, 0,
+                              d.recv[buf].get(), stride, 0, 0.0,
                               G + static_cast<long>(ch.recv_begin) * ldg + t.row_begin, ldg, 0, 1, 0),
                     "cxb_dgemm(off-diagonal block)");
       } else {
-        // block above the diagonal: store its transpose H[cols, rows] = A_cols^T B_rows
-        DeviceCheck(cxb_dgemm(s, 1, 0, ch.recv_count, t.row_count, static_cast<int>(nn), 1.0,
-                              d.recv[buf].get(), nn, 0, Bl, nn, 0, 0.0,
+        // block above the diagonal: store its transpose H[cols, rows]
+        DeviceCheck(cxb_dgemm(s, 1, 0, ch.recv_count, t.row_count, static_cast<int>(stride), 1.0,
+                              d.recv[buf].get(), stride, 0, Bl, stride, 0, 0.0,
                               G + static_cast<long>(t.row_begin) * ldg + ch.recv_begin, ldg, 0, 1, 0),
                     "cxb_dgemm(off-diagonal block, transposed)");
       }
@@ -340,6 +385,17 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
   }
   // -- 3. one all-reduce over the augmented H -------------------------------------------------------
   comm.AllReduceSum(G, static_cast<size_t>(ldg) * (m + 1), s);
+  if (sym) {
+    // W is replicated bit-identically, so every rank sees the same flag and takes the same branch.
+    int w_not_pd = 0;
+    ctx_->DownloadInts(&w_not_pd, flag, 1);
+    if (w_not_pd != 0) {
+      d.symmetric = false;
+      if (d.B.size() == 0) d.B.Resize(Sq(n) * (ml + 2));
+      for (auto& r : d.recv) r.Reserve(static_cast<size_t>(nn) * d.chunk);
+      AssembleSharded(sys);
+    }
+  }
 }
 
 void DenseLMIConstraint::ComputeNegativeSlack(double k, const Ref& y, Ref* minus_s) {

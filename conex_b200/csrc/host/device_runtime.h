@@ -112,8 +112,9 @@ class DeviceContext {
   DeviceContext(const DeviceContext&) = delete;
   DeviceContext& operator=(const DeviceContext&) = delete;
 
-  // How LMI blocks assemble their Schur complement: 0 = decide from free memory, 1 = keep all scaled
-  // matrices (fastest), 2 = stream row panels (A + two panels of scratch).
+  // How LMI blocks assemble their Schur complement: 0 = decide from free memory (symmetric form if it
+  // fits), 1 = classic W A_i W keeping all scaled matrices, 2 = stream row panels (A + two panels of
+  // scratch), 3 = symmetric form (packed L^T A_i L, fewest flops).
   int assembly_mode = 0;
 
   void* stream() const { return reinterpret_cast<void*>(stream_); }

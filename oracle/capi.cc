@@ -414,7 +414,8 @@ void ORACLE_SetBlasThreads(int n) { oracle::SetBlasThreads(n); }
 int ORACLE_GetBlasThreads() { return oracle::GetBlasThreads(); }
 
 void ORACLE_SetGramVariant(void* p, int v) {
-  Cast(p)->gram_variant = v ? oracle::GramVariant::kBlas3 : oracle::GramVariant::kAsWritten;
+  Cast(p)->gram_variant = (v == 2) ? oracle::GramVariant::kSymmetric
+                                   : (v ? oracle::GramVariant::kBlas3 : oracle::GramVariant::kAsWritten);
 }
 void ORACLE_FeasibleObjective(void* p, double* b) {
   const auto v = Cast(p)->FeasibleObjective();

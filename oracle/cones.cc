@@ -247,6 +247,30 @@ void DenseLmiCone::ConstructSchurComplementSystem(bool initialize, SchurSystem* 
       Store(initialize, &sys->AW[i], Trace(AW));                             // :79
       Store(initialize, &sys->AQc[i], TraceInnerProduct(n, C_.data(), WAW.p));  // :80
     }
+  } else if (gram_variant == GramVariant::kSymmetric) {
+    std::vector<double> L(W_.p, W_.p + nn), S((size_t)nn * (m + 1)), T(nn);
+    CholeskyLower(n, L.data(), n);
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < j; i++) L[(size_t)j * n + i] = 0.0;
+    for (int i = 0; i <= m; i++) {
+      const double* Ai = (i < m) ? Avect_.data() + (size_t)i * nn : C_.data();
+      Gemm(false, false, n, n, n, 1.0, Ai, n, L.data(), n, 0.0, T.data(), n);
+      Gemm(true, false, n, n, n, 1.0, L.data(), n, T.data(), n, 0.0, S.data() + (size_t)i * nn, n);
+    }
+    std::vector<double> out((size_t)(m + 1) * (m + 1));
+    Gemm(true, false, m + 1, m + 1, nn, 1.0, S.data(), nn, S.data(), nn, 0.0, out.data(), m + 1);
+    for (int i = 0; i < m; i++) {
+      for (int j = 0; j <= i; j++) Store(initialize, &sys->G(i, j), out[(size_t)j * (m + 1) + i]);
+      double tr = 0;
+      for (int r = 0; r < n; r++) tr += S[(size_t)i * nn + (size_t)r * n + r];
+      Store(initialize, &sys->AW[i], tr);
+      Store(initialize, &sys->AQc[i], out[(size_t)i * (m + 1) + m]);
+    }
+    double trc = 0;
+    for (int r = 0; r < n; r++) trc += S[(size_t)m * nn + (size_t)r * n + r];
+    Store(initialize, &sys->inner_product_of_w_and_c, trc);
+    Store(initialize, &sys->inner_product_of_c_and_Qc, out[(size_t)m * (m + 1) + m]);
+    return;
   } else {
     const int kPanel = 64;
     std::vector<double> B((size_t)nn * kPanel), out((size_t)kPanel * m);

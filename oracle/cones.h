@@ -89,6 +89,8 @@ class Cone {
 enum class GramVariant {
   kAsWritten = 0,  // m GEMVs over growing slabs: dense_lmi_constraint.cc:75-78
   kBlas3 = 1,      // same numbers through one GEMM per 64-row panel (reordered summation)
+  kSymmetric = 2,  // H_ij = <L^T A_i L, L^T A_j L> with W = L L^T: the same matrix through the Cholesky
+                   // factor of W (the form the product's default assembly uses); NOT in the reference
 };
 
 // DenseLMIConstraint (conex/dense_lmi_constraint.h:24-41) on a PsdConstraint

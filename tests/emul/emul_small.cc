@@ -14,6 +14,7 @@
 namespace {
 
 struct HostTeam {
+  int size() const { return 128; }
   template <class F>
   void par(int n, F f) {
     for (int i = 0; i < n; i++) f(i);
@@ -73,7 +74,7 @@ int emul_small_set_identity(int batch, const cxb_small_cone* c) {
 int emul_small_schur(int batch, const cxb_small_cone* c, double* G, long ldg, long gstride, double* AW,
                      double* AQc, long vstride, double* scal, long sstride, int accumulate) {
   HostTeam t;
-  std::vector<double> sm(PsdSmem(c->n));
+  std::vector<double> sm(PsdSchurSmemDoubles(c->n, c->m, t.size()));
   for (int p = 0; p < batch; p++) {
     const double* data = c->data + p * c->data_stride;
     double* st = c->state + p * c->state_stride;

@@ -42,7 +42,7 @@ def state_size(kind, n):
 
 
 def work_size(kind, n, m):
-    return {LP: 0, SOC: (n + 1) * (m + 4), PSD: (m + 1) * n * n}[kind]
+    return {LP: 0, SOC: (n + 1) * (m + 4), PSD: (m + 2) * n * n}[kind]
 
 
 def w_size(kind, n):

@@ -152,8 +152,10 @@ def test_dgemm_zero_k_and_empty(dev):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("n,m,seed", [(10, 7, 1), (50, 100, 2), (33, 20, 3), (4, 1, 4), (16, 129, 5)])
+@pytest.mark.parametrize("n,m,seed", [(10, 7, 1), (50, 100, 2), (33, 20, 3), (4, 1, 4), (16, 129, 5), (150, 9, 6),
+                                      (64, 5, 7), (65, 4, 8)])
 def test_schur_dense_lmi_matches_oracle(dev, n, m, seed):
+    import ctypes as C
     """K1+K2: H_ij = tr(A_i W A_j W), AW, AQc, <w,c>, <c,Qc> within 1e-10 relative of the oracle."""
     import torch
     L = dev.product().lib
@@ -180,6 +182,30 @@ def test_schur_dense_lmi_matches_oracle(dev, n, m, seed):
         dH = dev.dzeros(ldh * (m + 2))
         assert L.cxb_schur_dense_lmi(None, n, m, dev.ptr(dA), dev.ptr(dW), dev.ptr(dB), dev.ptr(dT), panel,
                                      dev.ptr(dH), ldh) == 0
+        Haug = dev.from_dev(dH, ldh, m + 2)
+        H = np.tril(Haug[:m, :m])
+        scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
+        assert (np.abs(H - np.tril(G)) / scale).max() < 1e-10
+        assert rel_err(Haug[m, :m], AQc) < 1e-10
+        assert rel_err(Haug[m + 1, :m], AW) < 1e-10
+        assert abs(Haug[m + 1, m] - sc[0]) <= 1e-10 * abs(sc[0])
+        assert abs(Haug[m, m] - sc[1]) <= 1e-10 * abs(sc[1])
+    # symmetric form: packed L^T A_i L (W = L L^T) and a SYRK-shaped Gram — same Newton system
+    vp = C.c_void_p
+    L.cxb_packed_symmetric_size.restype = C.c_size_t
+    L.cxb_packed_symmetric_size.argtypes = [C.c_int]
+    L.cxb_schur_dense_lmi_sym.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_long]
+    kp = L.cxb_packed_symmetric_size(n)
+    dX = dev.dzeros((m + 2) * kp)
+    dL = dev.dzeros(n * n)
+    info = dev.izeros(2)
+    for panel in (1, 3, m + 1):
+        dT = dev.dzeros(panel * n * n)
+        ldh = (m + 3) & ~1
+        dH = dev.dzeros(ldh * (m + 2))
+        assert L.cxb_schur_dense_lmi_sym(None, n, m, dev.ptr(dA), dev.ptr(dW), dev.ptr(dX), dev.ptr(dT), panel,
+                                         dev.ptr(dL), dev.ptr(info), dev.ptr(dH), ldh) == 0
+        assert int(info.cpu()[0]) == 0
         Haug = dev.from_dev(dH, ldh, m + 2)
         H = np.tril(Haug[:m, :m])
         scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
@@ -491,3 +517,50 @@ def test_small_vector_helpers(dev):
         for b in range(a + 1):
             Href[max(cl[a], cl[b]), min(cl[a], cl[b])] += G[a, b]
     assert np.array_equal(dev.from_dev(dH, 60, 60), Href)
+
+
+@pytest.mark.parametrize("n", [1, 17, 64, 100, 193])
+def test_triangular_gemm_and_symmetric_packing(dev, n):
+    """The structured GEMMs behind the symmetric Schur form: A L with L lower triangular (zero k-tiles
+    skipped) and L^T T stored as packed 64 x 64 lower tiles with sqrt(2)-scaled off-diagonal tiles —
+    checked through cxb_schur_dense_lmi_sym with m = 1 (the packed buffer holds L^T A L, L^T C L, I)
+    and cxb_pack_symmetric: <pack(X), pack(Y)> == tr(X Y) for symmetric X, Y."""
+    import ctypes as C
+    L = dev.product().lib
+    vp = C.c_void_p
+    L.cxb_packed_symmetric_size.restype = C.c_size_t
+    L.cxb_packed_symmetric_size.argtypes = [C.c_int]
+    L.cxb_pack_symmetric.argtypes = [vp, C.c_int, vp, vp]
+    L.cxb_schur_dense_lmi_sym.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_long]
+    rng = np.random.default_rng(n)
+    X, Y = random_sym(rng, n), random_sym(rng, n)
+    kp = L.cxb_packed_symmetric_size(n)
+    T = (n + 63) // 64
+    assert kp == T * (T + 1) // 2 * 4096
+    px, py = dev.dzeros(kp), dev.dzeros(kp)
+    assert L.cxb_pack_symmetric(None, n, dev.ptr(dev.to_dev(X)), dev.ptr(px)) == 0
+    assert L.cxb_pack_symmetric(None, n, dev.ptr(dev.to_dev(Y)), dev.ptr(py)) == 0
+    got = float((px * py).sum().cpu())
+    assert abs(got - np.trace(X @ Y)) <= 1e-12 * max(1.0, abs(np.trace(X @ Y)), np.abs(X).sum())
+    # scaled matrices: compare the packed L^T A L with numpy, tile by tile
+    R = rng.standard_normal((n, n))
+    W = R @ R.T / n + 0.5 * np.eye(n)
+    Lw = np.linalg.cholesky(W)
+    import torch
+    Aall = np.concatenate([np.asfortranarray(X).ravel(order="F"), np.asfortranarray(Y).ravel(order="F")])
+    dA = torch.from_numpy(Aall).cuda()
+    dX, dT, dL, info = dev.dzeros(3 * kp), dev.dzeros(n * n), dev.dzeros(n * n), dev.izeros(2)
+    dH = dev.dzeros(4 * 3)
+    assert L.cxb_schur_dense_lmi_sym(None, n, 1, dev.ptr(dA), dev.ptr(dev.to_dev(W)), dev.ptr(dX), dev.ptr(dT), 1,
+                                     dev.ptr(dL), dev.ptr(info), dev.ptr(dH), 4) == 0
+    assert np.abs(np.tril(dev.from_dev(dL, n, n)) - Lw).max() < 1e-12 * np.abs(Lw).max()
+    ref = dev.dzeros(kp)
+    S = Lw.T @ X @ Lw
+    assert L.cxb_pack_symmetric(None, n, dev.ptr(dev.to_dev(S)), dev.ptr(ref)) == 0
+    gotS = dX[:kp].cpu().numpy()
+    refS = ref.cpu().numpy()
+    # diagonal tiles of the GEMM output carry both triangles of S; the reference packs a symmetric S
+    assert np.abs(gotS - refS).max() < 1e-11 * max(1.0, np.abs(S).max())
+    H = dev.from_dev(dH, 4, 3)
+    assert abs(H[0, 0] - np.trace(X @ W @ X @ W)) <= 1e-10 * abs(np.trace(X @ W @ X @ W))
+    assert abs(H[2, 0] - np.trace(X @ W)) <= 1e-10 * max(1.0, np.abs(X @ W).sum())
