@@ -94,11 +94,13 @@ __global__ void __launch_bounds__(256) LanczosInitKernel(int n, const double* __
   }
 }
 
-__global__ void LanczosResetKernel(int n, double* work) {
+__global__ void LanczosResetKernel(int n, double* work, int* count) {
   const LanczosBufs b = Carve(work, n);
   b.st->ticket = 0;
   b.st->done = 0;
   b.st->count = 0;
+  count[0] = 0;
+  count[1] = 0;  // set to 1 by the step that stops the recurrence
 }
 
 // One Lanczos step (index j).
@@ -176,7 +178,10 @@ __global__ void __launch_bounds__(256) LanczosStepKernel(int n, int j, int num_i
     b.st->ticket = 0;
     b.st->count = j;
     *count = j;
-    if (stop) b.st->done = 1;
+    if (stop) {
+      b.st->done = 1;
+      count[1] = 1;
+    }
   }
 }
 
@@ -187,14 +192,16 @@ namespace {
 // The chain of one transpose + one reset + one init + num_iter step launches.
 int EnqueueLanczos(cudaStream_t s, int n, const double* d_WS, const double* d_W, const double* d_r,
                    const double* d_col_index, int num_iter, double* d_alpha, double* d_beta, int* d_count,
-                   double* d_work, double rel_tol) {
+                   double* d_work, double rel_tol, int j_begin, int j_end) {
   const LanczosBufs b = Carve(d_work, n);
-  int rc = Transpose(s, n, d_WS, b.WST);
-  if (rc) return rc;
   const int grid = (n + 7) / 8;
-  CountLaunch(); LanczosResetKernel<<<1, 1, 0, s>>>(n, d_work);
-  CountLaunch(); LanczosInitKernel<<<grid, 256, 0, s>>>(n, d_W, d_r, d_col_index, d_work);
-  for (int j = 0; j < num_iter; j++) {
+  if (j_begin == 0) {
+    int rc = Transpose(s, n, d_WS, b.WST);
+    if (rc) return rc;
+    CountLaunch(); LanczosResetKernel<<<1, 1, 0, s>>>(n, d_work, d_count);
+    CountLaunch(); LanczosInitKernel<<<grid, 256, 0, s>>>(n, d_W, d_r, d_col_index, d_work);
+  }
+  for (int j = j_begin; j < j_end; j++) {
     CountLaunch(); LanczosStepKernel<<<grid, 256, 0, s>>>(n, j, num_iter, d_WS, d_work, d_alpha, d_beta, d_count, rel_tol);
   }
   return LaunchStatus();
@@ -204,7 +211,7 @@ int EnqueueLanczos(cudaStream_t s, int n, const double* d_WS, const double* d_W,
 // captured once per argument tuple into a CUDA graph and replayed with a single launch, so the
 // device runs the whole recurrence back to back whatever the host is doing.
 struct GraphKey {
-  int n, num_iter;
+  int n, num_iter, j_begin, j_end;
   const void *ws, *w, *r, *col, *alpha, *beta, *count, *work;
   double rel_tol;
   bool operator<(const GraphKey& o) const {
@@ -240,15 +247,25 @@ int cxb_lanczos_two_sided_ex(void* stream, int n, const double* d_WS, const doub
                              const double* d_r, const double* d_col_index, int num_iter,
                              double* d_alpha, double* d_beta, int* d_count, double* d_work,
                              double rel_tol) {
+  return cxb_lanczos_two_sided_range(stream, n, d_WS, d_W, d_r, d_col_index, num_iter, 0, num_iter, d_alpha,
+                                     d_beta, d_count, d_work, rel_tol);
+}
+
+int cxb_lanczos_two_sided_range(void* stream, int n, const double* d_WS, const double* d_W,
+                                const double* d_r, const double* d_col_index, int num_iter, int j_begin,
+                                int j_end, double* d_alpha, double* d_beta, int* d_count, double* d_work,
+                                double rel_tol) {
   cudaStream_t s = AsStream(stream);
-  if (n < 1 || num_iter < 1) return -1;
-  if (num_iter < kGraphThreshold || s == nullptr) {
-    return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+  if (n < 1 || num_iter < 1 || j_begin < 0 || j_end > num_iter || j_begin > j_end) return -1;
+  if (j_end - j_begin < kGraphThreshold || s == nullptr) {
+    return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol, j_begin, j_end);
   }
   GraphKey key;
   std::memset(&key, 0, sizeof(key));
   key.n = n;
   key.num_iter = num_iter;
+  key.j_begin = j_begin;
+  key.j_end = j_end;
   key.ws = d_WS;
   key.w = d_W;
   key.r = d_r;
@@ -268,9 +285,9 @@ int cxb_lanczos_two_sided_ex(void* stream, int n, const double* d_WS, const doub
     const long before = g_launch_count;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
-      return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+      return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol, j_begin, j_end);
     }
-    const int rc = EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+    const int rc = EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol, j_begin, j_end);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s, &graph);
     GraphEntry entry;
@@ -280,7 +297,7 @@ int cxb_lanczos_two_sided_ex(void* stream, int n, const double* d_WS, const doub
         cudaGraphInstantiate(&entry.exec, graph, 0) != cudaSuccess) {
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
-      return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol);
+      return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol, j_begin, j_end);
     }
     cudaGraphDestroy(graph);
     it = g_graphs.emplace(key, entry).first;

@@ -1,6 +1,7 @@
 #include "cone_program.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <iomanip>
@@ -346,7 +347,15 @@ double NewtonDriver::MuFromDivergence() {
   DeviceCheck(cxb_axpbypcz(s, m_, st.c_scaling, prog_.sys.AQc, 0.0, d_y_, -st.b_scaling, d_b_),
               "cxb_axpbypcz");
   Ref y(d_y_, m_, 1);
+  static const bool trace = std::getenv("CONEX_TRACE_EIGEN") != nullptr;
+  const auto t0 = std::chrono::high_resolution_clock::now();
   prog_.solver->SolveInPlace(&y);
+  if (trace) {
+    ctx_.Synchronize();
+    std::cerr << "[conex-b200 trace] mu-phase solve (host wall, synchronised) "
+              << std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count()
+              << " ms" << std::endl;
+  }
   WeightedSlackEigenvalues p;
   GetWeightedSlackEigenvalues(prog_, y, st.c_scaling, &p);
   p.rank = rank_;

@@ -1,6 +1,7 @@
 #include "dense_lmi_constraint.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 
@@ -421,7 +422,7 @@ DenseLMIConstraint::SpectrumEstimate DenseLMIConstraint::EstimateSpectrum(const 
   double* alpha = d.small.get();
   double* beta = alpha + cap;
   double* red = beta + cap;  // 8 slots
-  int* count = d.iwork.get() + 2 * n;
+  int* count = d.iwork.get() + 2 * n + 2;  // two ints: step count, stop flag
   DeviceCheck(cxb_ws_reductions(s, n, WS.data, red), "cxb_ws_reductions");
   if (hermitian_) {
     // T::Random(n, 1) = Eigen::MatrixXd::Random: n draws of -1 + 2 rand() / RAND_MAX
@@ -434,15 +435,28 @@ DenseLMIConstraint::SpectrumEstimate DenseLMIConstraint::EstimateSpectrum(const 
     }
     for (int i = 0; i < n; i++) r[i] = -1.0 + 2.0 * static_cast<double>(std::rand()) / static_cast<double>(RAND_MAX);
     ctx_->Upload(d.rstart.get(), r, n);
-    if (n > 1) {
-      DeviceCheck(cxb_lanczos_two_sided_ex(s, n, WS.data, workspace_.W.data, d.rstart.get(), nullptr, num_iter,
-                                           alpha, beta, count, d.scratch.get(), 1e-5),
-                  "cxb_lanczos_two_sided_ex");
+  }
+  if (n > 1 && num_iter >= 1) {
+    const double* start = hermitian_ ? d.rstart.get() : start_matrix.data;
+    const double* column = hermitian_ ? nullptr : red + 2;
+    const double rel_tol = hermitian_ ? 1e-5 : 0.0;
+    // Long recurrences usually break down early (beta^2 below the threshold): run a short first range,
+    // look at the stop flag, and launch the rest only when needed.
+    constexpr int kProbe = 32;
+    int first_end = num_iter;
+    if (num_iter > 4 * kProbe) first_end = kProbe;
+    DeviceCheck(cxb_lanczos_two_sided_range(s, n, WS.data, workspace_.W.data, start, column, num_iter, 0, first_end,
+                                            alpha, beta, count, d.scratch.get(), rel_tol),
+                "cxb_lanczos_two_sided_range");
+    if (first_end < num_iter) {
+      int state[2] = {0, 0};
+      ctx_->DownloadInts(state, count, 2);
+      if (state[1] == 0) {
+        DeviceCheck(cxb_lanczos_two_sided_range(s, n, WS.data, workspace_.W.data, start, column, num_iter, first_end,
+                                                num_iter, alpha, beta, count, d.scratch.get(), rel_tol),
+                    "cxb_lanczos_two_sided_range");
+      }
     }
-  } else if (n > 1 && num_iter >= 1) {
-    DeviceCheck(cxb_lanczos_two_sided(s, n, WS.data, workspace_.W.data, start_matrix.data, red + 2,
-                                      num_iter, alpha, beta, count, d.scratch.get()),
-                "cxb_lanczos_two_sided");
   }
   std::vector<double> host(2 * cap + 8);
   int cnt = 0;
@@ -454,6 +468,8 @@ DenseLMIConstraint::SpectrumEstimate DenseLMIConstraint::EstimateSpectrum(const 
   } else {
     ctx_->Synchronize();
   }
+  static const bool trace = std::getenv("CONEX_TRACE_EIGEN") != nullptr;
+  if (trace) std::cerr << "[conex-b200 trace] Lanczos steps " << cnt + 1 << " of " << num_iter << std::endl;
   SpectrumEstimate e;
   e.trace = host[2 * cap + 0];
   e.trace_of_square = host[2 * cap + 1];
@@ -523,11 +539,32 @@ void GetWeightedSlackEigenvalues(DenseLMIConstraint* o, const Ref& y, double c_w
   const int n = o->n_;
   Ref minus_s = w.temp_1, WS = w.temp_2;
   o->EnsureScratch();
+  static const bool trace = std::getenv("CONEX_TRACE_EIGEN") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (trace) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], o->ctx_->cuda_stream());
+  }
   o->ComputeNegativeSlack(c_weight, y, &minus_s);
+  if (trace) cudaEventRecord(ev[1], o->ctx_->cuda_stream());
   DeviceCheck(cxb_dgemm(s, 0, 0, n, n, n, 1.0, w.W.data, n, 0, minus_s.data, n, 0, 0.0, WS.data, n, 0,
                         1, 0),
               "cxb_dgemm(W*S)");
+  if (trace) cudaEventRecord(ev[2], o->ctx_->cuda_stream());
+  const auto t0 = std::chrono::high_resolution_clock::now();
   const auto e = o->EstimateSpectrum(WS, minus_s);
+  if (trace) {
+    const double host_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    cudaEventRecord(ev[3], o->ctx_->cuda_stream());
+    cudaEventSynchronize(ev[3]);
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    std::cerr << "[conex-b200 trace] eigen-bound: slack " << a << " ms, W*S " << b << " ms, spectrum (host wall) "
+              << host_ms << " ms" << std::endl;
+    for (auto& x : ev) cudaEventDestroy(x);
+  }
   p->lambda_max = -e.ritz_min;
   p->lambda_min = -e.ritz_max;
   p->frobenius_norm_squared = e.trace_of_square;

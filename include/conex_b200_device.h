@@ -112,7 +112,7 @@ int cxb_gemv_n(void* stream, long nn, int cols, const double* dAall, const doubl
  * host round trip is needed after the diag-argmax reduction). Runs at most num_iter steps with the reference's
  * breakdown test (beta^2 < 1e-6). Outputs: d_alpha[num_iter], d_beta[num_iter], d_count[0] = number
  * of valid beta entries (alpha has d_count+1 valid entries). d_work: cxb_lanczos_worksize(n)
- * doubles. */
+ * doubles. d_count: 2 ints (see cxb_lanczos_two_sided_range). */
 size_t cxb_lanczos_worksize(int n);
 int cxb_lanczos_two_sided(void* stream, int n, const double* d_WS, const double* d_W,
                           const double* d_r, const double* d_col_index, int num_iter,
@@ -125,6 +125,14 @@ int cxb_lanczos_two_sided_ex(void* stream, int n, const double* d_WS, const doub
                              const double* d_r, const double* d_col_index, int num_iter,
                              double* d_alpha, double* d_beta, int* d_count, double* d_work,
                              double rel_tol);
+
+/* Steps j_begin .. j_end-1 only (j_begin == 0 also runs the set-up). d_count has TWO ints:
+ * d_count[0] as above, d_count[1] = 1 once the recurrence has stopped (breakdown or num_iter
+ * reached), so a caller can run a short first range, look, and skip the rest. */
+int cxb_lanczos_two_sided_range(void* stream, int n, const double* d_WS, const double* d_W,
+                                const double* d_r, const double* d_col_index, int num_iter, int j_begin,
+                                int j_end, double* d_alpha, double* d_beta, int* d_count, double* d_work,
+                                double rel_tol);
 
 /* ---- K7 reductions (psd_constraint.cc:63-80,107-127). d_out slots (all device doubles):
  *   out[0] = tr(WS), out[1] = sum_ij WS_ij WS_ji = tr(WS WS), out[2] = argmax_i WS_ii (as double),

@@ -150,7 +150,7 @@ def test_taylor_expm_and_hermitian_lanczos_kernels(libs, n):
     ritz = np.zeros(num_iter + 1)
     k = O.lib.ORACLE_HermitianLanczos(n, dptr(np.asfortranarray(WS)), dptr(np.asfortranarray(W)), dptr(r),
                                       num_iter, dptr(ritz))
-    alpha, beta, count = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(1)
+    alpha, beta, count = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(2)
     work = dev.dzeros(L.cxb_lanczos_worksize(n))
     assert L.cxb_lanczos_two_sided_ex(None, n, dev.ptr(dev.to_dev(WS)), dev.ptr(dev.to_dev(W)), dev.ptr(dev.to_dev(r)),
                                       None, num_iter, dev.ptr(alpha), dev.ptr(beta), dev.ptr(count), dev.ptr(work),

@@ -312,7 +312,7 @@ def test_two_sided_lanczos_matches_oracle(dev, n, seed):
     assert int(r4[2]) == idx
     assert abs(r4[0] - np.trace(WS)) < 1e-12 * max(1, abs(np.trace(WS)))
     assert abs(r4[1] - np.trace(WS @ WS)) < 1e-12 * abs(np.trace(WS @ WS))
-    alpha, beta, cnt = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(1)
+    alpha, beta, cnt = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(2)
     work = dev.dzeros(L.cxb_lanczos_worksize(n))
     idx_dev = red[2:3]
     assert L.cxb_lanczos_two_sided(None, n, dev.ptr(dWS), dev.ptr(dW), dev.ptr(dS), dev.ptr(idx_dev),
@@ -342,7 +342,7 @@ def test_two_sided_lanczos_long_run_properties(dev):
     W, S, WS = lanczos_inputs(n, 4)
     idx = int(np.argmax(np.diag(WS)))
     r = S[:, idx].copy()
-    alpha, beta, cnt = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(1)
+    alpha, beta, cnt = dev.dzeros(num_iter + 1), dev.dzeros(num_iter + 1), dev.izeros(2)
     work = dev.dzeros(L.cxb_lanczos_worksize(n))
     assert L.cxb_lanczos_two_sided(None, n, dev.ptr(dev.to_dev(WS)), dev.ptr(dev.to_dev(W)),
                                    dev.ptr(dev.to_dev(r)), None, num_iter, dev.ptr(alpha), dev.ptr(beta),
@@ -387,7 +387,7 @@ def test_lanczos_golden_4x4(dev):
     W = R @ R.T
     WS = W @ A
     r0 = np.array([1.0, 2, 0, 4])
-    alpha, beta, cnt = dev.dzeros(5), dev.dzeros(5), dev.izeros(1)
+    alpha, beta, cnt = dev.dzeros(5), dev.dzeros(5), dev.izeros(2)
     work = dev.dzeros(L.cxb_lanczos_worksize(4))
     assert L.cxb_lanczos_two_sided(None, 4, dev.ptr(dev.to_dev(WS)), dev.ptr(dev.to_dev(W)),
                                    dev.ptr(dev.to_dev(r0)), None, 4, dev.ptr(alpha), dev.ptr(beta),

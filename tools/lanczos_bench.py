@@ -25,7 +25,7 @@ def main():
         S = (S + S.T) / np.sqrt(n)
         dWS, dW, dr = dev.to_dev(W @ S), dev.to_dev(W), dev.to_dev(rng.standard_normal(n))
         it = n // 2
-        alpha, beta, count = dev.dzeros(it + 2), dev.dzeros(it + 2), dev.izeros(1)
+        alpha, beta, count = dev.dzeros(it + 2), dev.dzeros(it + 2), dev.izeros(2)
         work = dev.dzeros(L.cxb_lanczos_worksize(n))
         stream = torch.cuda.Stream()
         for name, sp in (("graph", C.c_void_p(stream.cuda_stream)), ("direct", None)):
