@@ -537,6 +537,19 @@ int CONEXB200_BatchGetDualVariable(void* batch, int program, int cone, double* x
       -1);
 }
 
+// 1 when constraint `id` is an incremental LMI currently held in entry-sparse form (after the first
+// solve / assembly), 0 when dense, -1 for other constraint types.
+int CONEXB200_ConstraintIsEntrySparse(void* prog, int id) {
+  Program& program = *static_cast<Program*>(prog);
+  int k = 0;
+  for (auto& c : program.eqs) {
+    if (k++ != id) continue;
+    if (auto* h = std::any_cast<conex::HermitianPsdConstraint>(&c.obj)) return h->entry_sparse() ? 1 : 0;
+    return -1;
+  }
+  return -1;
+}
+
 int CONEXB200_SizeOfKKTSystem(void* prog) { return static_cast<Program*>(prog)->SizeOfKKTSystem(); }
 
 // Host-logic probe: pivot order of the regularised LDL^T from the diagonal (RLDLT.h:328-356).

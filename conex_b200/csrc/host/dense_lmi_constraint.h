@@ -11,6 +11,7 @@
 // program's device arena exactly like WorkspaceDensePSD (psd_constraint.h:9-37), so a warm start
 // finds the iterate where the previous solve left it.
 #pragma once
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -60,8 +61,19 @@ class DenseLMIConstraint {
   double* mutable_device_matrices();  // local A_i blocks, then C
   int local_matrices() const { return m_local_; }
 
-  // Replaces the constraint matrices and the affine term (host data, same layout as the constructor).
-  void ReloadMatrices(const double* A, const double* C);
+  // Operator given by the non-zero entries of its matrices (lower triangle, r >= c): the block then
+  // runs the entry-sparse assembly and slack kernels (device/sparse_lmi.cu) and never allocates the
+  // dense n^2 x m operator. C: dense n x n (host).
+  struct Entry {
+    int var, r, c;
+    double val;
+  };
+  struct EntrySparse {};
+  DenseLMIConstraint(int n, int m, EntrySparse);
+  void LoadEntries(const std::vector<Entry>& lower_entries, const double* C);
+  // Dense storage for a block created with the EntrySparse constructor (allocated on first use).
+  void LoadDense(const std::vector<Entry>& lower_entries, const double* C);
+  bool entry_sparse() const;
   // Switches the eigen-bound and the exponential to the rules of the reference's incremental LMI
   // (HermitianPsdConstraint<Real>, conex/hermitian_psd.cc): Lanczos started from an Eigen-style
   // Random(n, 1) vector drawn with libc rand(), n/2 + 1 steps, relative breakdown test
@@ -110,9 +122,11 @@ class DenseLMIConstraint {
 
 // The LMI built entry by entry through CONEX_NewLinearMatrixInequality / CONEX_UpdateLinearOperator /
 // CONEX_UpdateAffineTerm — the reference's HermitianPsdConstraint<Real> (conex/hermitian_psd.{h,cc}).
-// The host keeps the dense symmetric matrices it is given; they are uploaded when they changed since
-// the last use, and all device work is the dense-LMI path with the Hermitian eigen-bound and
-// exponential rules.
+// The host keeps the entries it is given (a map per variable, lower triangle) and the dense affine
+// term; they are uploaded when they changed since the last use. Operators with few entries per matrix
+// (MaxCut, Lovasz theta, ...) run the entry-sparse kernels — O((sum nnz)^2) gathers instead of
+// 4 m n^3 + m^2 n^2 flops, O(nnz) memory instead of m n^2 doubles; dense ones the dense-LMI path. Both
+// use the Hermitian eigen-bound and exponential rules.
 class HermitianPsdConstraint : public DenseLMIConstraint {
  public:
   // order n, m variables (matrices of variables never updated stay zero)
@@ -138,8 +152,9 @@ class HermitianPsdConstraint : public DenseLMIConstraint {
 
  private:
   struct Host {
-    std::vector<double> A, C;
-    bool dirty = false;
+    std::vector<std::map<long, double>> entries;  // per variable: c * n + r (r >= c) -> value
+    std::vector<double> C;
+    bool dirty = true;
   };
   DenseLMIConstraint* Synced();
   std::shared_ptr<Host> host_;

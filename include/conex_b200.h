@@ -109,6 +109,10 @@ int CONEXB200_AddSocConstraint(void* prog, int n, int m, const double* A, const 
  * become extra unknowns of the KKT system, which is then factored by the regularised LDL^T. */
 int CONEXB200_AddEqualityConstraint(void* prog, int rows, int nvars, const double* A, const double* b,
                                     const long* vars);
+/* 1 when constraint `id` (an LMI built through CONEX_NewLinearMatrixInequality) is held in entry-sparse
+ * form and assembled by gathers from W, 0 when it is dense, -1 for other constraint types. Valid after
+ * the first solve. */
+int CONEXB200_ConstraintIsEntrySparse(void* prog, int id);
 /* Variables + equality multipliers (conex/constraint_manager.h:42-48). */
 int CONEXB200_SizeOfKKTSystem(void* prog);
 /* Host-logic probe: the pivot order Eigen::RLDLT derives from the diagonal (RLDLT.h:328-356). */

@@ -66,6 +66,19 @@ int cxb_pack_symmetric(void* stream, int n, const double* d_src, double* d_dst);
 int cxb_schur_dense_lmi_sym(void* stream, int n, int m, const double* dAall, const double* dW, double* dX,
                             double* dT, int panel, double* dL, int* d_info, double* dHaug, long ldh);
 
+/* ---- entry-sparse LMI operators (MaxCut, Lovasz theta, ...; sparse_lmi.cu) -----------------------
+ * A_i given by their non-zero entries (both triangles listed): entries offsets[i] .. offsets[i+1]-1 of
+ * rows / cols / vals. Same Haug as cxb_schur_dense_lmi, from O((sum nnz)^2) gathers out of W instead
+ * of matrix products. dC: dense n x n affine term. d_work: 2 n*n doubles (C W, W C W). */
+int cxb_sparse_lmi_schur(void* stream, int n, int m, const int* d_offsets, const int* d_rows,
+                         const int* d_cols, const double* d_vals, const double* dC, const double* dW,
+                         double* d_work, double* dHaug, long ldh);
+/* out = sum_i y_i A_i - k C with the entries grouped by matrix position (column-major index):
+ * position t holds entries pos_ptr[t] .. pos_ptr[t+1]-1 of (pos_var, pos_val); fixed summation order. */
+int cxb_sparse_lmi_slack(void* stream, int n, int npos, const int* d_pos_ptr, const long* d_pos_index,
+                         const int* d_pos_var, const double* d_pos_val, const double* dC, const double* dy,
+                         double k, double* d_out);
+
 /* Same result with bounded scratch: dBp holds (panel + 1) * n * n doubles (one row panel of scaled
  * matrices, contracted immediately), dT panel * n * n. Used when a second A-sized buffer does not fit. */
 int cxb_schur_dense_lmi_streamed(void* stream, int n, int m, const double* dAall, const double* dW,

@@ -163,3 +163,107 @@ def test_taylor_expm_and_hermitian_lanczos_kernels(libs, n):
     assert cnt + 1 == k
     assert abs(ev[0] - ritz[:k].min()) < 1e-8 * max(1.0, abs(ev[0]))
     assert abs(ev[-1] - ritz[:k].max()) < 1e-8 * max(1.0, abs(ev[-1]))
+
+
+def maxcut_instance(n, seed):
+    from harness import maxcut_lmi
+    return maxcut_lmi(n, seed)
+
+
+@pytest.mark.parametrize("kind,size", [("maxcut", 24), ("maxcut", 70), ("lovasz", 20)])
+def test_entry_sparse_operators_match_oracle(libs, kind, size):
+    """MaxCut / Lovasz-theta operators given entry by entry run the entry-sparse device kernels
+    (no dense A_i anywhere); the oracle runs the reference's dense HermitianPsdConstraint arithmetic."""
+    from harness import lovasz_theta_lmi, maxcut_lmi
+    O, D = libs
+    mats, Cm, b = maxcut_lmi(size, 2) if kind == "maxcut" else lovasz_theta_lmi(size, 3 * size, 4)
+    out = []
+    for L in (O, D):
+        P = L.program(len(mats))
+        cid = P.add_hermitian_lmi(mats, Cm)
+        srand(5)
+        solved, y = P.maximize(b, L.default_config(prepare_dual_variables=1))
+        out.append((solved, y, P.iteration_log(), P.dual_variable(cid)))
+        if L.kind == "b200":
+            assert L.lib.CONEXB200_ConstraintIsEntrySparse(P.h, cid) == 1
+    (so, yo, lo, Xo), (sd, yd, ld, Xd) = out
+    assert so == sd == 1
+    assert abs(len(lo) - len(ld)) <= 1
+    assert abs(lo[-1]["by"] - ld[-1]["by"]) <= 1e-7 * max(1.0, abs(lo[-1]["by"]))
+    assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+    assert np.abs(Xo - Xd).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    if kind == "maxcut":
+        assert np.abs(np.diag(Xd) - 1.0).max() < 1e-6  # the MaxCut relaxation has unit diagonal
+
+
+def test_dense_operator_through_incremental_api_stays_dense(libs):
+    _, D = libs
+    mats, Cm = random_instance(10, 4, 3)
+    P = D.program(4)
+    cid = P.add_hermitian_lmi(mats, Cm)
+    P.maximize(P.feasible_objective())
+    assert D.lib.CONEXB200_ConstraintIsEntrySparse(P.h, cid) == 0
+
+
+@pytest.mark.parametrize("n,m,per", [(7, 5, 2), (30, 40, 3), (64, 10, 12)])
+def test_sparse_schur_and_slack_kernels(libs, n, m, per):
+    """cxb_sparse_lmi_schur / cxb_sparse_lmi_slack against numpy with dense copies of the matrices."""
+    import devlib as dev
+    import torch
+    _, D = libs
+    L = D.lib
+    vp = C.c_void_p
+    L.cxb_sparse_lmi_schur.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_long]
+    L.cxb_sparse_lmi_slack.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, vp]
+    rng = np.random.Generator(np.random.PCG64(n * m))
+    mats = []
+    offsets, rows, cols, vals = [0], [], [], []
+    by_pos = {}
+    for i in range(m):
+        A = np.zeros((n, n))
+        for _ in range(per):
+            r, c = sorted(rng.integers(0, n, size=2), reverse=True)
+            A[r, c] = A[c, r] = rng.uniform(-1, 1)
+        mats.append(A)
+        for c in range(n):
+            for r in range(n):
+                if A[r, c] != 0:
+                    rows.append(r); cols.append(c); vals.append(A[r, c])
+                    by_pos.setdefault(c * n + r, []).append((i, A[r, c]))
+        offsets.append(len(rows))
+    R = rng.uniform(-1, 1, size=(n, n))
+    W = R @ R.T / n + np.eye(n)
+    Cm = rng.uniform(-1, 1, size=(n, n)); Cm = Cm + Cm.T
+    i32 = lambda a: torch.tensor(a, dtype=torch.int32, device="cuda")
+    dvals = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    ldh = (m + 3) & ~1
+    dH, work = dev.dzeros(ldh * (m + 2)), dev.dzeros(2 * n * n)
+    doff, drows, dcols = i32(offsets), i32(rows), i32(cols)
+    assert L.cxb_sparse_lmi_schur(None, n, m, dev.ptr(doff), dev.ptr(drows), dev.ptr(dcols), dev.ptr(dvals),
+                                  dev.ptr(dev.to_dev(Cm)), dev.ptr(dev.to_dev(W)), dev.ptr(work), dev.ptr(dH), ldh) == 0
+    Haug = dev.from_dev(dH, ldh, m + 2)
+    WCW = W @ Cm @ W
+    for i in range(m):
+        for j in range(i + 1):
+            ref = np.trace(mats[i] @ W @ mats[j] @ W)
+            assert abs(Haug[i, j] - ref) <= 1e-12 * max(1.0, abs(ref))
+        assert abs(Haug[m, i] - np.sum(mats[i] * WCW)) <= 1e-11 * max(1.0, np.abs(WCW).max())
+        assert abs(Haug[m + 1, i] - np.sum(mats[i] * W)) <= 1e-12 * max(1.0, np.abs(W).max())
+    assert abs(Haug[m, m] - np.sum(Cm * WCW)) <= 1e-11 * abs(np.sum(Cm * WCW))
+    assert abs(Haug[m + 1, m] - np.sum(Cm * W)) <= 1e-11 * max(1.0, abs(np.sum(Cm * W)))
+    # slack
+    keys = sorted(by_pos)
+    pos_ptr, pos_var, pos_val = [0], [], []
+    for k in keys:
+        for v, a in by_pos[k]:
+            pos_var.append(v); pos_val.append(a)
+        pos_ptr.append(len(pos_var))
+    y = rng.uniform(-1, 1, size=m)
+    out = dev.dzeros(n * n)
+    dpos = torch.tensor(keys, dtype=torch.int64, device="cuda")
+    dpv = torch.tensor(pos_val, dtype=torch.float64, device="cuda")
+    dptr_, dvar = i32(pos_ptr), i32(pos_var)
+    assert L.cxb_sparse_lmi_slack(None, n, len(keys), dev.ptr(dptr_), dev.ptr(dpos), dev.ptr(dvar),
+                                  dev.ptr(dpv), dev.ptr(dev.to_dev(Cm)), dev.ptr(dev.to_dev(y)), 0.7, dev.ptr(out)) == 0
+    ref = sum(y[i] * mats[i] for i in range(m)) - 0.7 * Cm
+    assert np.abs(dev.from_dev(out, n, n) - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
