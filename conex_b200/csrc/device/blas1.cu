@@ -93,6 +93,19 @@ __global__ void ScatterAddVecKernel(int n, const double* __restrict__ src,
   dst[k] += src[i];
 }
 
+// out = K x for a symmetric K stored by its lower triangle (ld): thread i sums row i of the lower
+// triangle (coalesced across the warp for every column) and, down column i, the mirrored part.
+__global__ void __launch_bounds__(128) SymvLowerKernel(int N, const double* __restrict__ K, long ld,
+                                                       const double* __restrict__ x, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double s = 0;
+  for (int j = 0; j <= i; j++) s += K[(long)j * ld + i] * x[j];       // K(i, j), j <= i
+  const double* col = K + (long)i * ld;
+  for (int r = i + 1; r < N; r++) s += col[r] * x[r];                  // K(r, i) = K(i, r), r > i
+  out[i] = s;
+}
+
 // dst[i] = src[idx[i]]
 __global__ void GatherVecKernel(int n, const double* __restrict__ src, const int* __restrict__ idx,
                                 double* dst) {
@@ -405,6 +418,12 @@ int cxb_scatter_add_vec(void* stream, int n, const double* d_src, const int* d_i
 int cxb_gather_vec(void* stream, int n, const double* d_src, const int* d_idx, double* d_dst) {
   if (n <= 0) return 0;
   CountLaunch(); GatherVecKernel<<<Blocks(n, 256), 256, 0, AsStream(stream)>>>(n, d_src, d_idx, d_dst);
+  return LaunchStatus();
+}
+
+int cxb_symv_lower(void* stream, int N, const double* dK, long ld, const double* dx, double* d_out) {
+  if (N <= 0) return 0;
+  CountLaunch(); SymvLowerKernel<<<Blocks(N, 128), 128, 0, AsStream(stream)>>>(N, dK, ld, dx, d_out);
   return LaunchStatus();
 }
 

@@ -229,6 +229,11 @@ int BatchProgram::Maximize(const double* b_in, const SolverConfiguration& cfg, d
   if (cfg.kkt_solver == CONEX_QR_FACTORIZATION) {
     throw std::runtime_error("conex-b200: the QR KKT mode is not implemented on the device");
   }
+  if (cfg.enable_line_search) {
+    bool lp_only = true;
+    for (const auto& c : d.cones) lp_only = lp_only && (c.type == CXB_CONE_LP);
+    if (lp_only) throw std::runtime_error("conex-b200: enable_line_search on LP-only programs is not implemented");
+  }
   void* s = d.s();
   cudaStream_t cs = d.ctx.cuda_stream();
   std::vector<ProgramState> st(B);

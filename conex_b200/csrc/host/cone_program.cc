@@ -133,6 +133,11 @@ bool DenseKKTSolver::Factor() {
   if (mode_ == CONEX_QR_FACTORIZATION) {
     throw std::runtime_error("conex-b200: the QR KKT mode is not implemented on the device");
   }
+  if (iterative_refinement_iterations_ > 0) {
+    // keep the assembled matrix for the residuals (kkt_solver.cc:174-178)
+    kkt_matrix_.Reserve(static_cast<size_t>(ldh_) * N_);
+    ctx_->CopyOnDevice(kkt_matrix_.get(), H_.get(), static_cast<size_t>(ldh_) * N_);
+  }
   if (num_dual_ > 0) {
     FactorLDLT();
     return true;  // the regularised LDL^T never fails (kkt_solver.cc:187-193)
@@ -144,17 +149,39 @@ bool DenseKKTSolver::Factor() {
   return host_info == 0;  // reference block_triangular_operations.cc:193-196
 }
 
-void DenseKKTSolver::SolveInPlace(Ref* b) const {
+void DenseKKTSolver::SolveOnce(double* rhs) const {
   if (num_dual_ > 0) {
-    for (int k = 0; k < b->cols; k++) {
-      DeviceCheck(cxb_ldlt_solve(ctx_->stream(), N_, Hp_.get(), ldh_, signs_.get(), perm_.get(), b->col(k),
-                                 diag_.get() + N_),
-                  "cxb_ldlt_solve");
-    }
-    return;
+    DeviceCheck(cxb_ldlt_solve(ctx_->stream(), N_, Hp_.get(), ldh_, signs_.get(), perm_.get(), rhs,
+                               diag_.get() + N_),
+                "cxb_ldlt_solve");
+  } else {
+    DeviceCheck(cxb_potrs_lower(ctx_->stream(), N_, H_.get(), ldh_, rhs, N_, 1), "cxb_potrs_lower");
   }
-  DeviceCheck(cxb_potrs_lower(ctx_->stream(), N_, H_.get(), ldh_, b->data, b->ld, b->cols),
-              "cxb_potrs_lower");
+}
+
+void DenseKKTSolver::SolveInPlace(Ref* b) const {
+  // reference kkt_solver.cc:220-263
+  void* s = ctx_->stream();
+  for (int k = 0; k < b->cols; k++) {
+    double* y = b->col(k);
+    if (iterative_refinement_iterations_ <= 0) {
+      SolveOnce(y);
+      continue;
+    }
+    refine_.Reserve(3 * static_cast<size_t>(N_));
+    double* total_residual = refine_.get();
+    double* r = total_residual + N_;
+    double* Ky = r + N_;
+    ctx_->CopyOnDevice(total_residual, y, N_);
+    SolveOnce(y);
+    for (int it = 0; it < iterative_refinement_iterations_; it++) {
+      DeviceCheck(cxb_symv_lower(s, N_, kkt_matrix_.get(), ldh_, y, Ky), "cxb_symv_lower");
+      // r = total_residual - K y ; solve ; y += r
+      DeviceCheck(cxb_axpbypcz(s, N_, 1.0, total_residual, 0.0, r, -1.0, Ky), "cxb_axpbypcz");
+      SolveOnce(r);
+      DeviceCheck(cxb_axpbypcz(s, N_, 1.0, r, 1.0, y, 0.0, nullptr), "cxb_axpbypcz");
+    }
+  }
 }
 
 // ================================================================================================
@@ -496,8 +523,12 @@ bool NewtonDriver::Run(double* primal_variable) {
     if (update_mu) {
       double candidate = -1;
       if (cfg_.enable_line_search) {
-        // PSD cones provide no PerformLineSearch (reference constraint.h:24-28): the search fails
-        // and the previous value is kept (cone_program.cc:376-384).
+        // PSD / second-order cones provide no PerformLineSearch (reference constraint.h:24-28): the
+        // search fails and the previous value is kept (cone_program.cc:376-384). Programs made of LP
+        // cones only would run the reference's real line search, which is not built here.
+        if (!prog_.LineSearchAlwaysFails()) {
+          throw std::runtime_error("conex-b200: enable_line_search on LP-only programs is not implemented");
+        }
         candidate = k;
       }
       if (candidate < 0) candidate = MuFromDivergence();

@@ -14,6 +14,7 @@
 
 #include "constraint.h"
 #include "equality_constraint.h"
+#include "small_cone_constraint.h"
 
 namespace conex {
 
@@ -120,6 +121,9 @@ class DenseKKTSolver {
   int num_dual_ = 0;
   bool factorization_regularized_ = false;
   DeviceBuffer<double> Hp_, signs_, ldlt_work_, diag_;
+  // iterative refinement (kkt_solver.cc:248-261): the assembled matrix and three N-vectors
+  void SolveOnce(double* rhs) const;
+  mutable DeviceBuffer<double> kkt_matrix_, refine_;
   DeviceBuffer<int> perm_;
   std::vector<int> host_perm_;
   std::list<Container>* eqs_ = nullptr;
@@ -163,6 +167,12 @@ class Program {
   }
   template <typename Cone>
   bool AddToClique(const Cone& d, const std::vector<int>& variables) {
+    // Only the LP cone (and equalities) implement PerformLineSearch in the reference
+    // (linear_constraint.cc:82-104, equality_constraint.h:49-54); with any other cone the search
+    // reports failure (constraint.h:24-28).
+    if constexpr (!(std::is_same<Cone, LinearConstraint>::value || std::is_same<Cone, EqualityConstraints>::value)) {
+      line_search_always_fails_ = true;
+    }
     eqs.emplace_back(d, variables);
     eqs.back().constraint.bind(&ctx_);
     constraints_.push_back(&eqs.back().constraint);
@@ -170,6 +180,7 @@ class Program {
   }
 
   int NumberOfConstraints() const { return static_cast<int>(eqs.size()); }
+  bool LineSearchAlwaysFails() const { return line_search_always_fails_; }
   ConexStatus Status() const { return status_; }
 
   // Copies the (rescaled) scaling point of cone i to host memory (reference cone_program.h:120-134).
@@ -203,6 +214,7 @@ class Program {
   bool VariablesAreUnique(const std::vector<int>& x) const;
   int num_variables_ = 0;
   int num_dual_ = 0;
+  bool line_search_always_fails_ = false;
 };
 
 // Pivot order of the regularised LDL^T from the diagonal alone (RLDLT.h:328-356); exposed for the

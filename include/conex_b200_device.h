@@ -193,6 +193,9 @@ int cxb_fill(void* stream, long n, double value, double* d_dst);
  * constraint_manager.h:107-124 and cone_program.h:59-67 */
 int cxb_scatter_add_vec(void* stream, int n, const double* d_src, const int* d_idx, double* d_dst);
 int cxb_gather_vec(void* stream, int n, const double* d_src, const int* d_idx, double* d_dst);
+/* out = K x, K symmetric N x N given by its lower triangle — the residual of the iterative refinement
+ * (kkt_solver.cc:248-261) */
+int cxb_symv_lower(void* stream, int N, const double* dK, long ld, const double* dx, double* d_out);
 /* W <- (1 + w_e) W + WSW  (psd_constraint.cc:33-43) */
 int cxb_affine_update(void* stream, int n, double* dW, const double* dWSW, double w_e);
 
