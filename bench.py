@@ -448,6 +448,13 @@ def structured_flops(n, m):
 
 def run_b200_structured(args):
     import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import devlib
     dev = devlib.product()
     L = dev.lib
@@ -457,7 +464,14 @@ def run_b200_structured(args):
     peak_tf = measure_fp64_peak()
     t_setup = time.perf_counter()
     entries, Cm, b = structured_problem(w)
+    if world > 1:
+        devlib.init_communicator(dev, rank, world)
+    configure_cholesky(L, args)
     P = dev.program(m)
+    if world > 1:
+        # every rank builds the same program and solves in lock step: the entry-sparse assembly and
+        # the n-sized phases are replicated, the Cholesky of the m x m Schur complement is distributed
+        L.CONEXB200_SetCollective(P.h, 1)
     cid = C.c_int(-1)
     assert L.CONEX_NewLinearMatrixInequality(P.h, n, 1, C.byref(cid)) == 0
     for (v, r, c, val) in entries:
@@ -469,9 +483,12 @@ def run_b200_structured(args):
     setup_s = time.perf_counter() - t_setup
     total = args.warmup + args.steps
     cfg = dev.default_config(max_iterations=total, final_centering_steps=0, inv_sqrt_mu_max=1e12)
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = L.CONEXB200_LaunchCount()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     solved, y = P.maximize(b, cfg)
     torch.cuda.synchronize()
@@ -490,6 +507,9 @@ def run_b200_structured(args):
     timed = np.array(step_ms[args.warmup:])
     ph_timed = np.array(phases[args.warmup:]).mean(axis=0)
     # e2e: a complete solve with the default configuration, host b -> host y
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     solved2, y2 = P.maximize(b, dev.default_config())
     torch.cuda.synchronize()
@@ -498,17 +518,29 @@ def run_b200_structured(args):
     log = P.iteration_log()
     clocks = sampler.stop()
     value = float(timed.mean())
+    if world > 1:
+        t = torch.tensor([value, solve_wall] + ph_timed.tolist(), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value, solve_wall = float(t[0]), float(t[1])
+        ph_timed = t[2:].cpu().numpy()
+        L.CONEXB200_CommDestroy()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     fl = structured_flops(n, m)
     upd = float(ph_timed[4])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": w["name"], "n": n, "m": m,
+        "config": {"workload": w["name"], "n": n, "m": m, "cholesky": cholesky_note(args, world, m),
                    "path": "incremental LMI (CONEX_NewLinearMatrixInequality + CONEX_UpdateLinearOperator), entry-sparse "
                            f"operator ({len(entries)} stored entries instead of {8e-9 * m * n * n:.1f} GB of dense matrices)",
                    "l2": "working set W, WS, H (tens of MB) is L2-resident by nature of the path; steps are not separated "
-                         "by a flush", "multi_gpu": "n/a"},
+                         "by a flush",
+                   "multi_gpu": (f"collective program on {world} ranks: Cholesky of the {m} x {m} Schur complement in 1-D "
+                                 "block-cyclic block columns with NCCL panel broadcasts; assembly, solves, eigen-bounds and "
+                                 "the geodesic update replicated") if world > 1 else "n/a"},
         "phase_ms": dict(zip(["assemble", "factor", "mu", "solve", "update"], ph_timed.tolist())),
         "step_tflops_fp64": fl / (value * 1e-3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "update phase: W.S GEMM, Taylor exponential GEMM chain, W <- E W (K7 + K8)",
@@ -526,6 +558,23 @@ def run_b200_structured(args):
         "final": {"by": log[-1]["by"], "cx": log[-1]["cx"], "mu": log[-1]["mu"]},
     }
     print(json.dumps(line))
+
+
+def configure_cholesky(L, args):
+    """--replicated-cholesky: factor on every rank (the A/B arm of the multi-GPU Cholesky);
+    --cholesky-block: block-column width of the distributed factorisation."""
+    if args.replicated_cholesky:
+        L.CONEXB200_SetDistributedCholesky(2 ** 30, 0)
+    elif args.cholesky_block:
+        L.CONEXB200_SetDistributedCholesky(-1, args.cholesky_block)
+
+
+def cholesky_note(args, world, order):
+    if world == 1:
+        return "single GPU"
+    if args.replicated_cholesky or order < 4096:
+        return "replicated on every rank"
+    return f"distributed: 1-D block-cyclic block columns of {args.cholesky_block or 512}, NCCL panel broadcasts"
 
 
 def run_reference(args):
@@ -583,6 +632,7 @@ def run_b200(args):
     t_setup = time.perf_counter()
     if world > 1:
         devlib.init_communicator(dev, rank, world)
+    configure_cholesky(L, args)
     rb, rc = devlib.shard_range(dev, m, world, rank)
     P = dev.program()
     if args.assembly_mode:
@@ -676,8 +726,8 @@ def run_b200(args):
                          ("no flush needed" if 8.0 * m * n * n > 4 * 126e6 else "L2-resident workload"),
                    "multi_gpu": (f"one Newton step sharded over {world} ranks: constraint matrices and the rows "
                                  "of H partitioned 1-D (K1/K2/K6 sharded, peer matrices over NCCL "
-                                 "send/recv, H by all-reduce); factor/solve/eigen-bound/geodesic update "
-                                 "replicated") if world > 1 else "n/a"},
+                                 "send/recv, H by all-reduce); Cholesky " + cholesky_note(args, world, m) +
+                                 "; solve/eigen-bound/geodesic update replicated") if world > 1 else "n/a"},
         "newton_steps_per_s": 1e3 / value,
         "step_tflops_fp64": fl["tensor"] / (value * 1e-3) / 1e12,
         "phase_ms": dict(zip(["assemble", "factor", "mu", "solve", "update"], ph_timed.tolist())),
@@ -727,6 +777,9 @@ def main():
     ap.add_argument("--assembly-mode", type=int, default=0, help="0 auto, 1 classic (keep all W A_i W), 2 stream row panels, 3 symmetric form (packed L^T A_i L)")
     ap.add_argument("--programs", type=int, default=0, help="c3: number of programs in the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicated-cholesky", action="store_true",
+                    help="N > 1: factor the Schur complement on every rank instead of across the ranks")
+    ap.add_argument("--cholesky-block", type=int, default=0, help="N > 1: block-column width (<= 512)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

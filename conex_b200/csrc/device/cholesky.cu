@@ -485,6 +485,19 @@ int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, i
   return LaunchStatus();
 }
 
+// ---- pieces of the same factorisation for the distributed driver (host/distributed_cholesky.cc) ----
+int cxb_potrf_max_panel(void) { return kOuter; }
+
+int cxb_potrf_begin(void* stream, int* d_info) {
+  CountLaunch(); ResetInfoKernel<<<1, 1, 0, AsStream(stream)>>>(d_info);
+  return LaunchStatus();
+}
+
+int cxb_potrf_panel(void* stream, int m, int j0, int w, double* dH, long ldh, int* d_info) {
+  if (m <= 0 || j0 < 0 || w <= 0 || w > kOuter || j0 + w > m) return -1;
+  return PotrfBlockColumn(AsStream(stream), m, j0, w, dH, ldh, d_info);
+}
+
 // X <- L^{-T} S L^{-1} X; signs == nullptr means S = I (plain Cholesky solve).
 static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs,
                           const double* signs) {

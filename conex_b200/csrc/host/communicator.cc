@@ -14,7 +14,9 @@ struct NcclUniqueId {
   char internal[128];
 };
 constexpr int kNcclFloat64 = 8;
+constexpr int kNcclInt32 = 2;
 constexpr int kNcclSum = 0;
+constexpr int kNcclMax = 2;
 }  // namespace
 
 struct Communicator::Api {
@@ -108,6 +110,11 @@ void Communicator::AllReduceSum(double* buf, size_t count, cudaStream_t stream) 
 void Communicator::Broadcast(double* buf, size_t count, int root, cudaStream_t stream) {
   if (world_ == 1 || count == 0) return;
   NCCL_CHECK(api_->Broadcast(buf, buf, count, kNcclFloat64, root, comm_, stream), "ncclBroadcast");
+}
+
+void Communicator::AllReduceMaxInt(int* buf, size_t count, cudaStream_t stream) {
+  if (world_ == 1 || count == 0) return;
+  NCCL_CHECK(api_->AllReduce(buf, buf, count, kNcclInt32, kNcclMax, comm_, stream), "ncclAllReduce(max)");
 }
 
 void Communicator::SendRecv(const double* send, size_t send_count, int to, double* recv,

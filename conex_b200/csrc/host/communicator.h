@@ -30,6 +30,8 @@ class Communicator {
   // All collectives are enqueued on `stream` and operate on FP64 device buffers.
   void AllReduceSum(double* buf, size_t count, cudaStream_t stream);
   void Broadcast(double* buf, size_t count, int root, cudaStream_t stream);
+  // Element-wise maximum of device ints over the ranks (status flags that every rank must agree on).
+  void AllReduceMaxInt(int* buf, size_t count, cudaStream_t stream);
   // One grouped exchange: send `send_count` doubles to `to` (skipped when send_count == 0) and
   // receive `recv_count` doubles from `from` (skipped when recv_count == 0).
   void SendRecv(const double* send, size_t send_count, int to, double* recv, size_t recv_count,

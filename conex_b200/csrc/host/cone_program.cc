@@ -9,6 +9,7 @@
 #include <set>
 
 #include "../../../include/conex_b200_device.h"
+#include "communicator.h"
 #include "divergence.h"
 
 namespace conex {
@@ -143,7 +144,13 @@ bool DenseKKTSolver::Factor() {
     return true;  // the regularised LDL^T never fails (kkt_solver.cc:187-193)
   }
   int* info = ctx_->flags();
-  DeviceCheck(cxb_potrf_lower(ctx_->stream(), N_, H_.get(), ldh_, nullptr, info), "cxb_potrf_lower");
+  const DistributedCholeskyPolicy& policy = DistributedCholeskyConfig();
+  if (ctx_->collective && Communicator::Get().distributed() && N_ >= policy.min_order) {
+    // H is replicated bit-identically (one all-reduce, or replicated deterministic kernels)
+    distributed_.Factor(ctx_->cuda_stream(), N_, H_.get(), ldh_, info, policy.block);
+  } else {
+    DeviceCheck(cxb_potrf_lower(ctx_->stream(), N_, H_.get(), ldh_, nullptr, info), "cxb_potrf_lower");
+  }
   int host_info = 0;
   ctx_->DownloadInts(&host_info, info, 1);
   return host_info == 0;  // reference block_triangular_operations.cc:193-196

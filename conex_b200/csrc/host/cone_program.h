@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "constraint.h"
+#include "distributed_cholesky.h"
 #include "equality_constraint.h"
 #include "small_cone_constraint.h"
 
@@ -113,6 +114,7 @@ class DenseKKTSolver {
 
  private:
   void FactorLDLT();
+  DistributedCholesky distributed_;  // used when the program is collective and N is large enough
   DeviceContext* ctx_;
   int N_;
   long ldh_;

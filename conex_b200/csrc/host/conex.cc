@@ -166,6 +166,7 @@ int CONEXB200_AddDenseLMIConstraintShard(void* prog, const double* d_A_local, in
         const int id = program.NumberOfConstraints();
         program.AddConstraint(DenseLMIConstraint(n, m, DenseLMIConstraint::Sharded{},
                                                  DenseLMIConstraint::DevicePointers{d_A_local, d_C}));
+        program.ctx_.collective = conex::Communicator::Get().distributed();
         return id;
       },
       -1);
@@ -182,6 +183,7 @@ int CONEXB200_NewDenseLMIConstraintStorage(void* prog, int n, int m, double** d_
         *d_A_local = cone.mutable_device_matrices();
         *d_C = cone.mutable_device_matrices() + static_cast<size_t>(n) * n * cone.local_matrices();
         program.AddConstraint(cone);
+        program.ctx_.collective = conex::Communicator::Get().distributed();
         return id;
       },
       -1);
@@ -225,6 +227,41 @@ int CONEXB200_ShardPlan(int m, int world, int rank, int* out5, int capacity) {
     k++;
   }
   return k;
+}
+
+void CONEXB200_SetCollective(void* prog, int collective) {
+  if (prog) static_cast<Program*>(prog)->ctx_.collective = collective != 0;
+}
+
+void CONEXB200_SetDistributedCholesky(int min_order, int block) {
+  auto& policy = conex::DistributedCholeskyConfig();
+  if (min_order >= 0) policy.min_order = min_order;
+  if (block > 0) policy.block = block;
+}
+
+int CONEXB200_CholeskySchedule(int N, int block, int world, int rank, int* out3, int capacity) {
+  const auto ops = conex::CholeskySchedule(N, block, world, rank);
+  int k = 0;
+  for (const auto& op : ops) {
+    if (k < capacity) {
+      const int v[3] = {op.kind, op.panel, op.target};
+      std::memcpy(out3 + 3 * k, v, sizeof(v));
+    }
+    k++;
+  }
+  return k;
+}
+
+int CONEXB200_DistributedPotrf(int N, double* d_H, long ld, int block, int* info) {
+  return Guard(
+      [&]() -> int {
+        conex::DeviceContext ctx;
+        conex::DistributedCholesky chol;
+        chol.Factor(ctx.cuda_stream(), N, d_H, ld, ctx.flags(), block);
+        ctx.DownloadInts(info, ctx.flags(), 1);
+        return 0;
+      },
+      1);
 }
 
 int CONEX_Maximize(void* prog_ptr, const double* b, int br, const CONEX_SolverConfiguration* config,

@@ -126,6 +126,10 @@ class DeviceContext {
   // fits), 1 = classic W A_i W keeping all scaled matrices, 2 = stream row panels (A + two panels of
   // scratch), 3 = symmetric form (packed L^T A_i L, fewest flops).
   int assembly_mode = 0;
+  // Every rank of the process-wide Communicator holds this program with identical replicated state
+  // and calls its solves in lock step (set by the sharded LMI constructors and by
+  // CONEXB200_SetCollective): the factorisation may then be distributed (distributed_cholesky.h).
+  bool collective = false;
 
   void* stream() const { return reinterpret_cast<void*>(stream_); }
   cudaStream_t cuda_stream() const { return stream_; }

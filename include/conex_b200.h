@@ -73,6 +73,28 @@ int CONEXB200_ShardPlan(int m, int world, int rank, int* out5, int capacity);
 int CONEXB200_AddDenseLMIConstraintShard(void* prog, const double* d_A_local, int n, int m,
                                          const double* d_C);
 
+/* Marks a program that is NOT sharded as collective: every rank of the communicator has built the
+ * same program (same data, same call sequence) and calls its solves in lock step, so that the
+ * replicated phases with enough flops may be split across the ranks — today the Cholesky of the
+ * Schur complement (below). Programs holding a sharded block are collective by construction. */
+void CONEXB200_SetCollective(void* prog, int collective);
+
+/* Multi-GPU Cholesky of collective programs (reference: BlockCholeskyInPlace on one thread,
+ * block_triangular_operations.cc:184-219): block columns of `block` columns (<= 512) dealt 1-D
+ * block-cyclically to the ranks, each factored panel broadcast over NCCL with a look-ahead of one
+ * panel, trailing updates on the owners; every rank ends with the complete factor. Used when the
+ * KKT order is >= min_order (default 4096; smaller systems are factored replicated). Process-wide;
+ * a negative min_order / non-positive block leaves that setting unchanged. */
+void CONEXB200_SetDistributedCholesky(int min_order, int block);
+/* Host logic of that schedule (no GPU): writes up to `capacity` records {kind, panel, target} of the
+ * operations `rank` enqueues — kind 0 factor `panel`, 1 broadcast `panel` from rank `target`, 2 wait
+ * for `panel`, 3 update block column `target` with `panel` — and returns their number. */
+int CONEXB200_CholeskySchedule(int N, int block, int world, int rank, int* out3, int capacity);
+/* The distributed factorisation alone, collective: d_H (N x N, lower, leading dimension ld, device)
+ * must hold the same matrix on every rank and is overwritten by the complete factor on every rank.
+ * *info = 0, or non-zero on every rank if the matrix is not positive definite. Returns 0 / 1. */
+int CONEXB200_DistributedPotrf(int N, double* d_H, long ld, int block, int* info);
+
 /* Zero-copy variant for operators that only fit once: the library allocates this rank's storage
  * (local_count = CONEXB200_ShardRange(m, world, rank) matrices, then C) and returns device pointers
  * that the caller fills in place (column-major n x n blocks) before the first solve. With world == 1

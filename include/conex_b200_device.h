@@ -89,6 +89,14 @@ int cxb_schur_dense_lmi_streamed(void* stream, int n, int m, const double* dAall
  * non-positive pivot). d_work: at least cxb_potrf_worksize(m) doubles. */
 size_t cxb_potrf_worksize(int m);
 int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, int* d_info);
+/* The same factorisation step by step, for the multi-GPU driver (host/distributed_cholesky.cc):
+ * cxb_potrf_begin clears d_info; cxb_potrf_panel factors the block column [j0, j0 + w) x rows
+ * [j0, m) in place (w <= cxb_potrf_max_panel(); the columns must already carry the updates of all
+ * block columns to their left) and is a no-op once d_info != 0; the trailing updates are
+ * cxb_dgemm(..., lower_only = 1) calls issued by the caller. */
+int cxb_potrf_max_panel(void);
+int cxb_potrf_begin(void* stream, int* d_info);
+int cxb_potrf_panel(void* stream, int m, int j0, int w, double* dH, long ldh, int* d_info);
 
 /* ---- K5: triangular solves with the Cholesky factor (block_triangular_operations.cc:114-182):
  * X <- L^{-T} L^{-1} X for nrhs right-hand sides (columns of dX, leading dimension ldx). */

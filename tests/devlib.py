@@ -71,6 +71,13 @@ def product():
         L.CONEXB200_DivergenceUpperBoundInverse.restype = C.c_double
         L.CONEXB200_TridiagonalExtremes.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.CONEXB200_LaunchCount.restype = C.c_long
+        L.CONEXB200_SetCollective.argtypes = [vp, C.c_int]
+        L.CONEXB200_SetCollective.restype = None
+        L.CONEXB200_SetDistributedCholesky.argtypes = [C.c_int, C.c_int]
+        L.CONEXB200_SetDistributedCholesky.restype = None
+        L.CONEXB200_DistributedPotrf.argtypes = [C.c_int, vp, C.c_long, C.c_int, C.POINTER(C.c_int)]
+        L.cxb_potrf_begin.argtypes = [vp, vp]
+        L.cxb_potrf_panel.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp]
     return _dev
 
 

@@ -258,6 +258,37 @@ def test_potrf_and_potrs(dev, m):
         assert rel_err(H @ X, B) < 1e-10
 
 
+@pytest.mark.parametrize("m,block", [(1, 4), (97, 8), (700, 128), (1500, 256), (2200, 512), (1300, 100)])
+def test_potrf_by_panels_single_rank(dev, m, block):
+    """The multi-GPU Cholesky driver (host/distributed_cholesky.cc) with a world of one: the same
+    schedule, panel kernels and per-block-column trailing updates, broadcasts being no-ops. The
+    multi-rank runs are in tests/test_multi_gpu.py."""
+    import ctypes as C
+
+    import torch
+    L = dev.product().lib
+    rng = np.random.default_rng(m + block)
+    R = rng.standard_normal((m, m + 5))
+    H = R @ R.T / m + np.eye(m)
+    ld = m + 2
+    Hp = np.zeros((ld, m))
+    Hp[:m, :] = np.tril(H) + np.triu(np.full((m, m), np.nan), 1)  # upper part must never be read
+    dH = dev.to_dev(Hp)
+    info = C.c_int(-1)
+    assert L.CONEXB200_DistributedPotrf(m, dev.ptr(dH), ld, block, C.byref(info)) == 0
+    torch.cuda.synchronize()
+    assert info.value == 0
+    Ld = np.tril(dev.from_dev(dH, ld, m)[:m, :])
+    assert rel_err(Ld, np.linalg.cholesky(H)) < 1e-12
+    # non-positive pivot in a later panel
+    if m >= 97:
+        H[m - 3, m - 3] = -1.0
+        Hp[:m, :] = np.tril(H)
+        dH = dev.to_dev(Hp)
+        assert L.CONEXB200_DistributedPotrf(m, dev.ptr(dH), ld, block, C.byref(info)) == 0
+        assert info.value != 0
+
+
 def test_potrf_reports_non_positive_pivot(dev):
     import torch
     L = dev.product().lib

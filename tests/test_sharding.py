@@ -158,3 +158,104 @@ def test_sharded_assembly_over_gloo_matches_oracle(tmp_path, world):
     assert np.allclose(H[m, :m], AQc, rtol=1e-12, atol=1e-12)
     assert np.allclose(H[m + 1, :m], AW, rtol=1e-12, atol=1e-12)
     assert np.allclose([H[m + 1, m], H[m, m]], sc, rtol=1e-12)
+
+
+# ---- distributed Cholesky (conex_b200/csrc/host/distributed_cholesky.{h,cc}) --------------------------
+FACTOR, BROADCAST, WAIT, UPDATE = 0, 1, 2, 3
+
+
+def cholesky_schedule(L, N, block, world, rank):
+    L.CONEXB200_CholeskySchedule.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int), C.c_int]
+    k = L.CONEXB200_CholeskySchedule(N, block, world, rank, None, 0)
+    buf = (C.c_int * (3 * max(k, 1)))()
+    assert L.CONEXB200_CholeskySchedule(N, block, world, rank, buf, k) == k
+    return [tuple(buf[3 * i:3 * i + 3]) for i in range(k)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("N,block", [(1, 4), (7, 8), (64, 8), (100, 16), (20000, 512)])
+def test_cholesky_schedule_is_a_valid_right_looking_order(world, N, block):
+    """Every panel is factored exactly once, by its owner, after its block column has received the
+    update of every earlier panel (each of which had arrived before it was used); every rank issues
+    the same broadcasts in the same order; every block column is updated only by its owner."""
+    L = product_lib()
+    nblk = (N + block - 1) // block
+    bcasts = None
+    factored_by = {}
+    for rank in range(world):
+        ops = cholesky_schedule(L, N, block, world, rank)
+        arrived, updates = set(), {}
+        mine = []
+        for kind, panel, target in ops:
+            if kind == BROADCAST:
+                assert target == panel % world
+                if target == rank:
+                    assert factored_by.get(panel) == rank                    # factored before it is sent
+                mine.append((panel, target))
+            elif kind == WAIT:
+                arrived.add(panel)
+            elif kind == UPDATE:
+                assert target % world == rank and target > panel
+                assert panel in arrived
+                assert updates.setdefault(target, []) == list(range(panel))  # panels applied in order
+                updates[target].append(panel)
+            elif kind == FACTOR:
+                assert panel % world == rank and panel not in factored_by
+                assert updates.get(panel, []) == list(range(panel))          # fully updated
+                factored_by[panel] = rank
+        assert arrived == set(range(nblk))
+        if bcasts is None:
+            bcasts = mine
+        assert mine == bcasts == [(J, J % world) for J in range(nblk)]
+    assert sorted(factored_by) == list(range(nblk))
+
+
+def _gloo_cholesky_rank(rank, world, port, N, block, out):
+    import scipy.linalg as sla
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        L = product_lib()
+        rng = np.random.default_rng(5)
+        M = rng.standard_normal((N, N))
+        H = np.tril(M @ M.T + N * np.eye(N))          # replicated input, lower triangle only
+        if rank != 0:
+            # block columns a rank does not own may hold anything before their panel arrives
+            for J in range((N + block - 1) // block):
+                if J % world != rank:
+                    H[:, J * block:(J + 1) * block] = np.nan
+        for kind, panel, target in cholesky_schedule(L, N, block, world, rank):
+            j0, j1 = panel * block, min(N, (panel + 1) * block)
+            if kind == FACTOR:
+                H[j0:j1, j0:j1] = np.linalg.cholesky(np.tril(H[j0:j1, j0:j1]) + np.tril(H[j0:j1, j0:j1], -1).T)
+                if j1 < N:
+                    H[j1:, j0:j1] = sla.solve_triangular(H[j0:j1, j0:j1], H[j1:, j0:j1].T, lower=True).T
+            elif kind == BROADCAST:
+                buf = torch.from_numpy(np.ascontiguousarray(H[j0:, j0:j1]))
+                dist.broadcast(buf, src=target)
+                H[j0:, j0:j1] = buf.numpy()
+            elif kind == UPDATE:
+                k0, k1 = target * block, min(N, (target + 1) * block)
+                upd = H[k0:, j0:j1] @ H[k0:k1, j0:j1].T
+                blockc = H[k0:, k0:k1]
+                blockc -= np.where(np.arange(k0, N)[:, None] >= np.arange(k0, k1)[None, :], upd, 0.0)
+        np.save(out + f".{rank}.npy", H)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_cholesky_schedule_over_gloo(tmp_path, world):
+    """The product's own schedule executed with numpy blocks and gloo broadcasts: every rank ends
+    with the complete factor of the replicated matrix."""
+    import torch.multiprocessing as mp
+    N, block = 45, 8
+    out = str(tmp_path / "L")
+    mp.spawn(_gloo_cholesky_rank, args=(world, _free_port(), N, block, out), nprocs=world, join=True)
+    rng = np.random.default_rng(5)
+    M = rng.standard_normal((N, N))
+    ref = np.linalg.cholesky(M @ M.T + N * np.eye(N))
+    for r in range(world):
+        Lr = np.tril(np.load(out + f".{r}.npy"))
+        assert np.abs(Lr - ref).max() < 1e-11
