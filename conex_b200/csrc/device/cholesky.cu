@@ -120,6 +120,123 @@ __global__ void __launch_bounds__(512) PotrfDiagKernel(int nb, double* H, long l
   }
 }
 
+// Plain Cholesky of the same block, blocked 32 x 32 inside the CTA (the rank-1 kernel above spends two
+// barriers per column: 132 us per 128 x 128 block, 40 % of the whole factorisation at m = 10^4):
+//   for each 32-column sub-block: warp 0 factors the 32 x 32 diagonal part in registers (lane = row,
+//   column entries exchanged by shuffles); one thread per row below solves its 32 entries by
+//   substitution in registers; all 512 threads apply the rank-32 update to the rest of the block
+//   with 3 x 6 register tiles (rows by lane: conflict-free, columns by warp: broadcast).
+__global__ void __launch_bounds__(512) PotrfDiagBlockedKernel(int nb, double* H, long ld, int col0, int* info) {
+  extern __shared__ double s[];  // s[c * P + r], P = 129
+  constexpr int P = kNB + 1;
+  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ int failed;
+  __shared__ double srd[32];  // reciprocal diagonal of the current sub-block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (*info != 0) return;  // an earlier block already failed
+  if (tid == 0) failed = 0;
+  BatchedCopy<8>(
+      kNB * kNB, tid, 512,
+      [&](int e) {
+        const int rr = e & (kNB - 1), c = e >> 7;
+        if (rr >= nb) return (c == rr) ? 1.0 : 0.0;  // identity padding keeps the arithmetic harmless
+        return (c <= rr) ? H[(long)c * ld + rr] : 0.0;
+      },
+      [&](int e, double v) { s[(e >> 7) * P + (e & (kNB - 1))] = v; });
+  __syncthreads();
+  for (int k0 = 0; k0 < nb; k0 += 32) {
+    // 1. diagonal sub-block
+    if (warp == 0) {
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; c++) a[c] = s[(k0 + c) * P + k0 + lane];
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const double d = __shfl_sync(kFull, a[j], j);
+        if (!(d > 0.0) && bad == 0) bad = j + 1;  // same d in every lane
+        const double rd = sqrt(d);
+        const double inv = 1.0 / rd;
+        const double l = (lane > j) ? a[j] * inv : ((lane == j) ? rd : 0.0);
+        a[j] = l;
+        if (lane == j) srd[j] = inv;
+#pragma unroll
+        for (int c = j + 1; c < 32; c++) {
+          const double lc = __shfl_sync(kFull, l, c);
+          a[c] -= l * lc;  // entries above the diagonal (c > lane) are never read again
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        if (c <= lane) s[(k0 + c) * P + k0 + lane] = a[c];
+      }
+      if (bad != 0 && lane == 0) {
+        failed = 1;
+        *info = col0 + k0 + bad;
+      }
+    }
+    __syncthreads();
+    if (failed) return;
+    const int base = k0 + 32;
+    const int below = kNB - base;  // rows base .. 127 (padded rows are zero)
+    if (below == 0) break;
+    // 2. rows below: x D^T = a, one thread per row
+    if (tid < below) {
+      const int r = base + tid;
+      double x[32];
+#pragma unroll
+      for (int c = 0; c < 32; c++) x[c] = s[(k0 + c) * P + r];
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        const double xc = x[c] * srd[c];
+        x[c] = xc;
+        const double* dcol = s + (k0 + c) * P + k0;  // D[cq][c], cq > c
+#pragma unroll
+        for (int cq = c + 1; cq < 32; cq++) x[cq] -= xc * dcol[cq];
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c++) s[(k0 + c) * P + r] = x[c];
+    }
+    __syncthreads();
+    // 3. rank-32 update of the trailing part: rows base + lane + 32 a, columns base + warp + 16 b
+    {
+      const int na = below >> 5, nbcol = below >> 4;  // 3 / 6, 2 / 4, 1 / 2
+      double acc[3][6];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = 0; b < 6; b++) acc[a][b] = 0.0;
+      }
+      for (int k = 0; k < 32; k++) {
+        const double* xk = s + (k0 + k) * P + base;
+        double xr[3], xc[6];
+#pragma unroll
+        for (int a = 0; a < 3; a++) xr[a] = (a < na) ? xk[lane + 32 * a] : 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) xc[b] = (b < nbcol) ? xk[warp + 16 * b] : 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+          for (int b = 0; b < 6; b++) acc[a][b] += xr[a] * xc[b];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+          const int r = base + lane + 32 * a, c = base + warp + 16 * b;
+          if (a < na && b < nbcol && c <= r) s[c * P + r] -= acc[a][b];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int r = tid & (kNB - 1), cg = tid >> 7;
+  if (r < nb) {
+    for (int c = cg; c <= r; c += 4) H[(long)c * ld + r] = s[c * P + r];
+  }
+}
+
 // ---- 2. panel solve ---------------------------------------------------------------------------------
 // Solves X * L11^T = A21 for kNB-row strips: one thread per row. L11: nb x nb lower (ld), nb <= 128.
 // A21 (ld) is overwritten by X. Shared memory: sx[i][row] (the row's solved entries) and one slab of
@@ -367,6 +484,204 @@ __global__ void __launch_bounds__(256) TrsvBwdStepKernel(int j0, int nb, const d
   }
 }
 
+// ---- single-launch sweeps (wavefront over block rows) ------------------------------------------------
+// One launch per direction instead of one per 128-column block (the stepwise kernels above reach
+// 0.2 TB/s at m = 10^4: 2 x 79 launches of ~26 us whose every CTA re-solves the diagonal block).
+// CTA with ticket i owns block row i of the sweep: it streams its own part of L exactly once,
+// consuming each earlier solution block x_k as soon as its owner publishes it (release/acquire flag
+// in global memory), then solves its 128 x 128 diagonal block by substitution and publishes x_i.
+// Tickets come from an atomic counter, so a CTA only ever waits for CTAs that started before it:
+// no co-residency assumption, no deadlock when m / 128 exceeds the number of SMs. Summation order is
+// fixed (independent of timing): results are deterministic. One right-hand side per launch.
+__device__ __forceinline__ void WaitFlag(const int* flag) {
+  if (threadIdx.x == 0) {
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    } while (v == 0);
+  }
+  __syncthreads();
+}
+// Call after a __syncthreads() that follows the block's global writes.
+__device__ __forceinline__ void SetFlag(int* flag) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+  }
+}
+
+// x (one right-hand side, sx[0..127]) <- L_kk^{-1} x by 32 x 32 warp-shuffle substitutions (warp 0, its
+// row of the sub-block in registers) and block updates by all threads. Rows >= nb are padded
+// (sl = 0, srd = 0) and come out as 0.
+template <int P>
+__device__ __forceinline__ void SolveLowerBlock1(const double* sl, const double* srd, double* sx) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+  for (int b0 = 0; b0 < kNB; b0 += 32) {
+    if (warp == 0) {
+      double lrow[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) lrow[j] = sl[(b0 + j) * P + b0 + lane];  // L[b0 + lane][b0 + j]
+      double v = sx[b0 + lane];
+      const double rd = srd[b0 + lane];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const double xj = __shfl_sync(0xffffffffu, v * rd, j);
+        if (lane == j) v = xj;
+        if (lane > j) v -= lrow[j] * xj;
+      }
+      sx[b0 + lane] = v;
+    }
+    __syncthreads();
+    // rows below the sub-block: 4 threads per row, 8 columns each, fixed-order combination
+    const int rows = kNB - b0 - 32;
+    if (tid < rows * 4) {
+      const int r = b0 + 32 + (tid >> 2), q = tid & 3;
+      double a = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) a += sl[(b0 + q * 8 + j) * P + r] * sx[b0 + q * 8 + j];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (q == 0) sx[r] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+// x <- L_kk^{-T} x, same organisation from the bottom up.
+template <int P>
+__device__ __forceinline__ void SolveLowerTransposedBlock1(const double* sl, const double* srd, double* sx) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+  for (int b0 = kNB - 32; b0 >= 0; b0 -= 32) {
+    if (warp == 0) {
+      double lcol[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) lcol[j] = sl[(b0 + lane) * P + b0 + j];  // L[b0 + j][b0 + lane]
+      double v = sx[b0 + lane];
+      const double rd = srd[b0 + lane];
+#pragma unroll
+      for (int j = 31; j >= 0; j--) {
+        const double xj = __shfl_sync(0xffffffffu, v * rd, j);
+        if (lane == j) v = xj;
+        if (lane < j) v -= lcol[j] * xj;
+      }
+      sx[b0 + lane] = v;
+    }
+    __syncthreads();
+    // entries above the sub-block: z[r] -= sum_j L[b0 + j][r] x_j for r < b0
+    if (tid < b0 * 4) {
+      const int r = tid >> 2, q = tid & 3;
+      double a = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) a += sl[r * P + b0 + q * 8 + j] * sx[b0 + q * 8 + j];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (q == 0) sx[r] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+// sync[0]: ticket counter, sync[1 + k]: block k solved. Both zero at launch.
+__global__ void __launch_bounds__(512) TrsvFwdWaveKernel(int m, const double* __restrict__ L, long ld,
+                                                         double* X, int* sync) {
+  constexpr int P = kNB + 1;
+  extern __shared__ double s[];
+  double* sl = s;
+  double* sx = s + kNB * P;   // kNB
+  double* srd = sx + kNB;     // kNB
+  double* sp = srd + kNB;     // 4 x kNB partial sums
+  __shared__ int s_block;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_block = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int i = s_block;
+  int* flags = sync + 1;
+  const int r0 = i * kNB;
+  const int nb = min(kNB, m - r0);
+  LoadLowerBlock<P>(sl, srd, L + (long)r0 * ld + r0, ld, nb);
+  const int rl = tid & (kNB - 1), g = tid >> 7;  // row of the strip, column group (32 of every 128)
+  const bool active = rl < nb;
+  const int r = r0 + rl;
+  double acc = 0;
+  for (int kb = 0; kb < i; kb++) {
+    const double* Lr = L + (long)(kb * kNB + g * 32) * ld + r;
+    double l[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) l[c] = active ? __ldcs(Lr + (long)c * ld) : 0.0;  // read exactly once
+    WaitFlag(flags + kb);
+    const double* xk = X + kb * kNB + g * 32;
+#pragma unroll
+    for (int c = 0; c < 32; c++) acc += l[c] * __ldcg(xk + c);  // L2: written by another SM
+  }
+  sp[g * kNB + rl] = acc;
+  __syncthreads();
+  if (g == 0) sx[rl] = active ? X[r] - (((sp[rl] + sp[kNB + rl]) + sp[2 * kNB + rl]) + sp[3 * kNB + rl]) : 0.0;
+  __syncthreads();
+  SolveLowerBlock1<P>(sl, srd, sx);
+  if (tid < nb) X[r0 + tid] = sx[tid];
+  __syncthreads();
+  SetFlag(flags + i);
+}
+
+__global__ void __launch_bounds__(512) TrsvBwdWaveKernel(int m, const double* __restrict__ L, long ld,
+                                                         double* X, int* sync) {
+  constexpr int P = kNB + 1;
+  extern __shared__ double s[];
+  double* sl = s;
+  double* sx = s + kNB * P;
+  double* srd = sx + kNB;
+  double* sp = srd + kNB;  // kNB column sums
+  __shared__ int s_block;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_block = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int nblk = (m + kNB - 1) / kNB;
+  const int i = nblk - 1 - s_block;
+  int* flags = sync + 1;
+  const int c0 = i * kNB;
+  const int nb = min(kNB, m - c0);
+  LoadLowerBlock<P>(sl, srd, L + (long)c0 * ld + c0, ld, nb);
+  // warp w owns the columns c0 + 8 w .. c0 + 8 w + 7 of L; lanes run down the rows of a block
+  double acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q] = 0;
+  for (int kb = nblk - 1; kb > i; kb--) {
+    const int rb = kb * kNB;
+    const int nrows = min(kNB, m - rb);
+    double l[8][4];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int cw = warp * 8 + q;
+      const double* Lc = L + (long)(c0 + cw) * ld + rb + lane;
+#pragma unroll
+      for (int p = 0; p < 4; p++) l[q][p] = (cw < nb && lane + 32 * p < nrows) ? __ldcs(Lc + 32 * p) : 0.0;
+    }
+    WaitFlag(flags + kb);
+    double xv[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) xv[p] = (lane + 32 * p < nrows) ? __ldcg(X + rb + lane + 32 * p) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+#pragma unroll
+      for (int p = 0; p < 4; p++) acc[q] += l[q][p] * xv[p];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const double v = WarpSum(acc[q]);
+    if (lane == 0) sp[warp * 8 + q] = v;
+  }
+  __syncthreads();
+  if (tid < kNB) sx[tid] = (tid < nb) ? X[c0 + tid] - sp[tid] : 0.0;
+  __syncthreads();
+  SolveLowerTransposedBlock1<P>(sl, srd, sx);
+  if (tid < nb) X[c0 + tid] = sx[tid];
+  __syncthreads();
+  SetFlag(flags + i);
+}
+
 __global__ void ResetInfoKernel(int* info) { *info = 0; }
 __global__ void ResetInfo2Kernel(int* info) { info[0] = 0; info[1] = 0; }
 
@@ -416,15 +731,22 @@ constexpr size_t kDiagSmem = sizeof(double) * kNB * (kNB + 1);
 constexpr size_t kTrsmSmem = sizeof(double) * (kNB * kNB + kNB * 32 + 32);
 constexpr size_t kTrsvSmem =
     sizeof(double) * (kNB * (kNB + 1) + kMaxRhs * kNB + kNB + kMaxRhs * 4 * kFwdRows);
+constexpr size_t kWaveSmem = sizeof(double) * (kNB * (kNB + 1) + 6 * kNB);
+// 0: single-launch wavefront sweeps (default); 1: one launch per block (the earlier scheme, kept for
+// A/B measurements through cxb_set_trsv_mode)
+int g_trsv_mode = 0;
 
 void ConfigureOnce() {
   static bool configured = false;
   if (configured) return;
   cudaFuncSetAttribute(PotrfDiagKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
   cudaFuncSetAttribute(PotrfDiagKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
+  cudaFuncSetAttribute(PotrfDiagBlockedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
   cudaFuncSetAttribute(TrsmPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
   cudaFuncSetAttribute(TrsvFwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
   cudaFuncSetAttribute(TrsvBwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
+  cudaFuncSetAttribute(TrsvFwdWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+  cudaFuncSetAttribute(TrsvBwdWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
   configured = true;
 }
 
@@ -437,7 +759,7 @@ int PotrfBlockColumn(cudaStream_t s, int m, int j0, int w, double* H, long ldh, 
   for (int i0 = j0; i0 < j0 + w; i0 += kNB) {
     const int nb = min(kNB, j0 + w - i0);
     double* Hii = H + (long)i0 * ldh + i0;
-    CountLaunch(); PotrfDiagKernel<false><<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info, nullptr);
+    CountLaunch(); PotrfDiagBlockedKernel<<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info);
     const int rows = m - i0 - nb;
     if (rows <= 0) continue;
     double* A21 = Hii + nb;
@@ -505,6 +827,24 @@ static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, dou
   if (nrhs > kMaxRhs) return -1;
   ConfigureOnce();
   const int nblk = (m + kNB - 1) / kNB;
+  if (g_trsv_mode == 0) {
+    // one ticket counter + nblk flags per sweep and right-hand side, zeroed once
+    const size_t per = (size_t)nblk + 1;
+    int* sync = nullptr;
+    if (cudaMallocAsync(&sync, sizeof(int) * per * 2 * nrhs, s) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+    cudaMemsetAsync(sync, 0, sizeof(int) * per * 2 * nrhs, s);
+    for (int k = 0; k < nrhs; k++) {
+      CountLaunch(); TrsvFwdWaveKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dX + (long)k * ldx, sync + per * (2 * k));
+    }
+    if (signs) {
+      CountLaunch(); ApplySignsKernel<<<(m + 255) / 256, 256, 0, s>>>(m, nrhs, signs, dX, ldx);
+    }
+    for (int k = 0; k < nrhs; k++) {
+      CountLaunch(); TrsvBwdWaveKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dX + (long)k * ldx, sync + per * (2 * k + 1));
+    }
+    cudaFreeAsync(sync, s);
+    return LaunchStatus();
+  }
   // z (the forward solution) is collected in a scratch array while dX is the working vector; the
   // backward sweep then works in the scratch array and collects x in dX.
   double* Z = nullptr;
@@ -528,6 +868,8 @@ static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, dou
   cudaFreeAsync(Z, s);
   return LaunchStatus();
 }
+
+void cxb_set_trsv_mode(int mode) { g_trsv_mode = mode; }
 
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs) {
   return PotrsLowerImpl(AsStream(stream), m, dL, ldl, dX, ldx, nrhs, nullptr);

@@ -101,6 +101,10 @@ int cxb_potrf_panel(void* stream, int m, int j0, int w, double* dH, long ldh, in
 /* ---- K5: triangular solves with the Cholesky factor (block_triangular_operations.cc:114-182):
  * X <- L^{-T} L^{-1} X for nrhs right-hand sides (columns of dX, leading dimension ldx). */
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs);
+/* 0 (default): each sweep is ONE launch — a wavefront over the 128-row blocks, L streamed exactly once,
+ * solution blocks handed from CTA to CTA through release/acquire flags; 1: one launch per block and
+ * direction (the earlier scheme). Process-wide; for A/B measurements only. */
+void cxb_set_trsv_mode(int mode);
 
 /* ---- K4: diagonally pivoted, regularised LDL^T (block_triangular_operations.cc:315-349 +
  * Eigen::RLDLT, RLDLT.h:297-431) for KKT systems with equality constraints.

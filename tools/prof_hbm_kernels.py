@@ -20,6 +20,8 @@ import devlib as dev  # noqa: E402
 import torch  # noqa: E402
 
 L = dev.product().lib
+L.cxb_set_trsv_mode.argtypes = [C.c_int]
+L.cxb_set_trsv_mode.restype = None
 vp = C.c_void_p
 f64 = dict(dtype=torch.float64, device="cuda")
 
@@ -89,10 +91,12 @@ def prof_chol(s, reps, out, sizes):
         out.append(dict(kernel="K3 cxb_potrf_lower", shape=f"m = {m}", ms=t, algorithmic_flops=m ** 3 / 3.0,
                         TFLOPs=m ** 3 / 3.0 / (t * 1e-3) / 1e12))
         x = torch.rand(m, **f64)
-        med, best = timed(lambda: L.cxb_potrs_lower(vp(s), m, vp(Hwork.data_ptr()), ld, vp(x.data_ptr()), m, 1), reps)
-        out.append(dict(kernel="K5 cxb_potrs_lower", shape=f"m = {m}, 1 rhs", ms=med, best_ms=best,
-                        algorithmic_bytes=8.0 * m * m, GBps=8.0 * m * m / (best * 1e-3) / 1e9,
-                        launches=2 * ((m + 127) // 128)))
+        for mode, name, launches in ((1, "one launch per block", 2 * ((m + 127) // 128)), (0, "wavefront", 2)):
+            L.cxb_set_trsv_mode(mode)
+            med, best = timed(lambda: L.cxb_potrs_lower(vp(s), m, vp(Hwork.data_ptr()), ld, vp(x.data_ptr()), m, 1), reps)
+            out.append(dict(kernel=f"K5 cxb_potrs_lower ({name})", shape=f"m = {m}, 1 rhs", ms=med, best_ms=best,
+                            algorithmic_bytes=8.0 * m * m, GBps=8.0 * m * m / (best * 1e-3) / 1e9,
+                            launches=launches))
         del H, Hwork, x
         torch.cuda.empty_cache()
 
