@@ -735,6 +735,8 @@ constexpr size_t kWaveSmem = sizeof(double) * (kNB * (kNB + 1) + 6 * kNB);
 // 0: single-launch wavefront sweeps (default); 1: one launch per block (the earlier scheme, kept for
 // A/B measurements through cxb_set_trsv_mode)
 int g_trsv_mode = 0;
+// 0: blocked diagonal kernel (default); 1: rank-1 kernel (the earlier one; A/B through cxb_set_potrf_mode)
+int g_potrf_mode = 0;
 
 void ConfigureOnce() {
   static bool configured = false;
@@ -759,7 +761,12 @@ int PotrfBlockColumn(cudaStream_t s, int m, int j0, int w, double* H, long ldh, 
   for (int i0 = j0; i0 < j0 + w; i0 += kNB) {
     const int nb = min(kNB, j0 + w - i0);
     double* Hii = H + (long)i0 * ldh + i0;
-    CountLaunch(); PotrfDiagBlockedKernel<<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info);
+    CountLaunch();
+    if (g_potrf_mode == 0) {
+      PotrfDiagBlockedKernel<<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info);
+    } else {
+      PotrfDiagKernel<false><<<1, 512, kDiagSmem, s>>>(nb, Hii, ldh, i0, info, nullptr);
+    }
     const int rows = m - i0 - nb;
     if (rows <= 0) continue;
     double* A21 = Hii + nb;
@@ -870,6 +877,7 @@ static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, dou
 }
 
 void cxb_set_trsv_mode(int mode) { g_trsv_mode = mode; }
+void cxb_set_potrf_mode(int mode) { g_potrf_mode = mode; }
 
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs) {
   return PotrsLowerImpl(AsStream(stream), m, dL, ldl, dX, ldx, nrhs, nullptr);

@@ -105,6 +105,10 @@ int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX,
  * solution blocks handed from CTA to CTA through release/acquire flags; 1: one launch per block and
  * direction (the earlier scheme). Process-wide; for A/B measurements only. */
 void cxb_set_trsv_mode(int mode);
+/* 0 (default): the 128 x 128 diagonal blocks of the factorisation are factored by the blocked kernel
+ * (32-wide sub-blocks, warp-shuffle factor); 1: by the rank-1 kernel with two barriers per column.
+ * Process-wide; for A/B measurements only. */
+void cxb_set_potrf_mode(int mode);
 
 /* ---- K4: diagonally pivoted, regularised LDL^T (block_triangular_operations.cc:315-349 +
  * Eigen::RLDLT, RLDLT.h:297-431) for KKT systems with equality constraints.

