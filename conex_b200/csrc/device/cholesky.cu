@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(512) TrsvFwdWaveKernel(int m, const double* __
   double* sx = s + kNB * P;   // kNB
   double* srd = sx + kNB;     // kNB
   double* sp = srd + kNB;     // 4 x kNB partial sums
+  double* sxk = sp + 4 * kNB; // 2 x kNB: solution block being consumed
   __shared__ int s_block;
   const int tid = threadIdx.x;
   if (tid == 0) s_block = atomicAdd(&sync[0], 1);
@@ -611,9 +612,15 @@ __global__ void __launch_bounds__(512) TrsvFwdWaveKernel(int m, const double* __
 #pragma unroll
     for (int c = 0; c < 32; c++) l[c] = active ? __ldcs(Lr + (long)c * ld) : 0.0;  // read exactly once
     WaitFlag(flags + kb);
-    const double* xk = X + kb * kNB + g * 32;
+    // x_kb goes through shared memory: one coalesced L2 read per CTA. (Every thread fetching its 32
+    // values itself put 512 requests per CTA and step on the same few L2 sectors — with ~150 CTAs in
+    // lock step that hot spot, not the substitution chain, set the pace.) Double-buffered: the
+    // barrier inside the next WaitFlag separates these reads from the write after next.
+    double* xs = sxk + (kb & 1) * kNB;
+    if (tid < kNB) xs[tid] = __ldcg(X + kb * kNB + tid);  // L2: written by another SM
+    __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 32; c++) acc += l[c] * __ldcg(xk + c);  // L2: written by another SM
+    for (int c = 0; c < 32; c++) acc += l[c] * xs[g * 32 + c];
   }
   sp[g * kNB + rl] = acc;
   __syncthreads();
@@ -633,6 +640,7 @@ __global__ void __launch_bounds__(512) TrsvBwdWaveKernel(int m, const double* __
   double* sx = s + kNB * P;
   double* srd = sx + kNB;
   double* sp = srd + kNB;  // kNB column sums
+  double* sxk = sp + 4 * kNB;
   __shared__ int s_block;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_block = atomicAdd(&sync[0], 1);
@@ -659,9 +667,12 @@ __global__ void __launch_bounds__(512) TrsvBwdWaveKernel(int m, const double* __
       for (int p = 0; p < 4; p++) l[q][p] = (cw < nb && lane + 32 * p < nrows) ? __ldcs(Lc + 32 * p) : 0.0;
     }
     WaitFlag(flags + kb);
+    double* xs = sxk + (kb & 1) * kNB;  // see the forward kernel
+    if (tid < kNB) xs[tid] = (tid < nrows) ? __ldcg(X + rb + tid) : 0.0;
+    __syncthreads();
     double xv[4];
 #pragma unroll
-    for (int p = 0; p < 4; p++) xv[p] = (lane + 32 * p < nrows) ? __ldcg(X + rb + lane + 32 * p) : 0.0;
+    for (int p = 0; p < 4; p++) xv[p] = xs[lane + 32 * p];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
 #pragma unroll
@@ -731,12 +742,13 @@ constexpr size_t kDiagSmem = sizeof(double) * kNB * (kNB + 1);
 constexpr size_t kTrsmSmem = sizeof(double) * (kNB * kNB + kNB * 32 + 32);
 constexpr size_t kTrsvSmem =
     sizeof(double) * (kNB * (kNB + 1) + kMaxRhs * kNB + kNB + kMaxRhs * 4 * kFwdRows);
-constexpr size_t kWaveSmem = sizeof(double) * (kNB * (kNB + 1) + 6 * kNB);
+constexpr size_t kWaveSmem = sizeof(double) * (kNB * (kNB + 1) + 8 * kNB);
 // 0: single-launch wavefront sweeps (default); 1: one launch per block (the earlier scheme, kept for
 // A/B measurements through cxb_set_trsv_mode)
 int g_trsv_mode = 0;
 // 0: blocked diagonal kernel (default); 1: rank-1 kernel (the earlier one; A/B through cxb_set_potrf_mode)
 int g_potrf_mode = 0;
+int g_potrf_lookahead = 1;  // bit 1 of cxb_set_potrf_mode clears it (sequential schedule, A/B)
 
 void ConfigureOnce() {
   static bool configured = false;
@@ -793,11 +805,72 @@ size_t cxb_potrf_worksize(int m) {
   return 1;  // the algorithm works fully in place
 }
 
+namespace {
+// Per host thread: a high-priority side stream and two events for the look-ahead below (a Program is
+// single-threaded; programs driven from different threads get their own).
+struct LookAhead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t updated = nullptr, factored = nullptr;
+  bool Prepare() {
+    if (side) return true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+    return cudaEventCreateWithFlags(&updated, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&factored, cudaEventDisableTiming) == cudaSuccess;
+  }
+};
+thread_local LookAhead t_lookahead;
+
+// Right-looking factorisation with a look-ahead of one outer block column: after panel J the update
+// of block column J + 1 is issued first, panel J + 1 is then factored on a high-priority side stream
+// (its chain of small latency-bound kernels: 4 x {diagonal block, panel solve, in-panel update})
+// WHILE the main stream applies panel J to the rest of the trailing matrix on the tensor cores.
+// Every entry still receives the same updates in the same order: the factor is bit-identical to the
+// sequential schedule's.
+int PotrfLookAhead(cudaStream_t s, int m, double* dH, long ldh, int* d_info) {
+  LookAhead& la = t_lookahead;
+  if (!la.Prepare()) return (int)cudaErrorUnknown;
+  int rc = PotrfBlockColumn(s, m, 0, min(kOuter, m), dH, ldh, d_info);
+  if (rc != 0) return rc;
+  for (int j0 = 0; j0 < m; j0 += kOuter) {
+    const int w = min(kOuter, m - j0);
+    const int rows = m - j0 - w;
+    if (rows <= 0) break;
+    const int n0 = j0 + w;               // first column of the next panel
+    const int wn = min(kOuter, rows);    // its width
+    const double* L21 = dH + (long)j0 * ldh + n0;
+    double* A22 = dH + (long)n0 * ldh + n0;
+    // 1. panel J -> block column J + 1 (lower trapezoid, rows x wn)
+    rc = Dgemm(s, false, true, rows, wn, w, -1.0, L21, ldh, 0, L21, ldh, 0, 1.0, A22, ldh, 0, 1, true);
+    if (rc != 0) return rc;
+    cudaEventRecord(la.updated, s);
+    cudaStreamWaitEvent(la.side, la.updated, 0);
+    // 2. factor panel J + 1 on the side stream
+    rc = PotrfBlockColumn(la.side, m, n0, wn, dH, ldh, d_info);
+    if (rc != 0) return rc;
+    cudaEventRecord(la.factored, la.side);
+    // 3. panel J -> everything right of block column J + 1
+    const int rest = rows - wn;
+    if (rest > 0) {
+      rc = Dgemm(s, false, true, rest, rest, w, -1.0, L21 + wn, ldh, 0, L21 + wn, ldh, 0, 1.0,
+                 A22 + (long)wn * ldh + wn, ldh, 0, 1, true);
+      if (rc != 0) return rc;
+    }
+    cudaStreamWaitEvent(s, la.factored, 0);
+  }
+  return LaunchStatus();
+}
+}  // namespace
+
 int cxb_potrf_lower(void* stream, int m, double* dH, long ldh, double* d_work, int* d_info) {
   (void)d_work;
   cudaStream_t s = AsStream(stream);
   if (m <= 0) return 0;
   CountLaunch(); ResetInfoKernel<<<1, 1, 0, s>>>(d_info);
+  // below three outer block columns there is nothing to overlap; the legacy default stream cannot
+  // run concurrently with a side stream's work ordering-wise in a useful way either
+  if (g_potrf_lookahead && m > 3 * kOuter) return PotrfLookAhead(s, m, dH, ldh, d_info);
   for (int j0 = 0; j0 < m; j0 += kOuter) {
     const int w = min(kOuter, m - j0);
     int rc = PotrfBlockColumn(s, m, j0, w, dH, ldh, d_info);
@@ -877,7 +950,10 @@ static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, dou
 }
 
 void cxb_set_trsv_mode(int mode) { g_trsv_mode = mode; }
-void cxb_set_potrf_mode(int mode) { g_potrf_mode = mode; }
+void cxb_set_potrf_mode(int mode) {
+  g_potrf_mode = mode & 1;
+  g_potrf_lookahead = (mode & 2) ? 0 : 1;
+}
 
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs) {
   return PotrsLowerImpl(AsStream(stream), m, dL, ldl, dX, ldx, nrhs, nullptr);

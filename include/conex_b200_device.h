@@ -107,7 +107,8 @@ int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX,
 void cxb_set_trsv_mode(int mode);
 /* 0 (default): the 128 x 128 diagonal blocks of the factorisation are factored by the blocked kernel
  * (32-wide sub-blocks, warp-shuffle factor); 1: by the rank-1 kernel with two barriers per column.
- * Process-wide; for A/B measurements only. */
+ * Adding 2 turns the look-ahead off (orders above 1536 factor panel J + 1 on a high-priority side
+ * stream while panel J updates the rest of the trailing matrix). Process-wide; for A/B measurements. */
 void cxb_set_potrf_mode(int mode);
 
 /* ---- K4: diagonally pivoted, regularised LDL^T (block_triangular_operations.cc:315-349 +

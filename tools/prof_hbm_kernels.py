@@ -22,6 +22,8 @@ import torch  # noqa: E402
 L = dev.product().lib
 L.cxb_set_trsv_mode.argtypes = [C.c_int]
 L.cxb_set_trsv_mode.restype = None
+L.cxb_set_potrf_mode.argtypes = [C.c_int]
+L.cxb_set_potrf_mode.restype = None
 vp = C.c_void_p
 f64 = dict(dtype=torch.float64, device="cuda")
 
@@ -42,6 +44,9 @@ def timed(fn, reps):
 
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "time"
+    # creating a program sets the release threshold of the stream-ordered pool the solves take their
+    # scratch from (host/device_runtime.h); without it every call re-acquires the memory from the driver
+    keep = dev.product().program()  # noqa: F841
     reps = 1 if mode == "once" else 5
     which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["gemv", "chol", "lanczos", "geo"]
     s = torch.cuda.current_stream().cuda_stream
@@ -84,12 +89,17 @@ def prof_chol(s, reps, out, sizes):
         def copy_only():
             Hwork.copy_(H)
 
-        medf, bestf = timed(factor, reps)
         medc, bestc = timed(copy_only, reps)
-        assert int(info.cpu()[0]) == 0
-        t = bestf - bestc
-        out.append(dict(kernel="K3 cxb_potrf_lower", shape=f"m = {m}", ms=t, algorithmic_flops=m ** 3 / 3.0,
-                        TFLOPs=m ** 3 / 3.0 / (t * 1e-3) / 1e12))
+        variants = ((3, "rank-1 diagonal kernel, sequential"), (2, "blocked diagonal kernel, sequential"),
+                    (0, "blocked diagonal kernel + look-ahead (default)"))
+        for mode, name in (variants if reps > 1 else variants[-1:]):
+            L.cxb_set_potrf_mode(mode)
+            medf, bestf = timed(factor, reps)
+            assert int(info.cpu()[0]) == 0
+            t = bestf - bestc
+            out.append(dict(kernel=f"K3 cxb_potrf_lower ({name})", shape=f"m = {m}", ms=t,
+                            algorithmic_flops=m ** 3 / 3.0, TFLOPs=m ** 3 / 3.0 / (t * 1e-3) / 1e12))
+        L.cxb_set_potrf_mode(0)
         x = torch.rand(m, **f64)
         for mode, name, launches in ((1, "one launch per block", 2 * ((m + 127) // 128)), (0, "wavefront", 2)):
             L.cxb_set_trsv_mode(mode)
