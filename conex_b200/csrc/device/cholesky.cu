@@ -693,6 +693,43 @@ __global__ void __launch_bounds__(512) TrsvBwdWaveKernel(int m, const double* __
   SetFlag(flags + i);
 }
 
+// ---- supernodal (multifrontal) pieces -----------------------------------------------------------------
+// dst[idx[e]] += sign * G[a, b] for the pairs a >= b of an n x n lower triangle, e = position of (a, b)
+// in column-major order of the lower triangle. idx < 0: entry dropped.
+__global__ void ScatterLowerIndexedKernel(int n, const double* __restrict__ G, long ldg,
+                                          const long* __restrict__ idx, double sign, double* dst) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (a >= n || a < b) return;
+  const long e = (long)b * n - (long)b * (b - 1) / 2 + (a - b);
+  const long d = idx[e];
+  if (d >= 0) dst[d] += sign * G[(long)b * ldg + a];
+}
+
+// Forward pass of one front: x[sep[r]] -= sum_c L21[r][c] xk[c], one warp per separator row.
+__global__ void FrontForwardKernel(int p, int sk, const double* __restrict__ L21, long ld,
+                                   const double* __restrict__ xk, const int* __restrict__ sep, double* x) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= p) return;
+  double a = 0;
+  for (int c = lane; c < sk; c += 32) a += L21[(long)c * ld + r] * xk[c];
+  a = WarpSum(a);
+  if (lane == 0) x[sep[r]] -= a;
+}
+
+// Backward pass of one front: xk[c] -= sum_r L21[r][c] x[sep[r]], one warp per column.
+__global__ void FrontBackwardKernel(int p, int sk, const double* __restrict__ L21, long ld, double* xk,
+                                    const int* __restrict__ sep, const double* __restrict__ x) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= sk) return;
+  double a = 0;
+  for (int r = lane; r < p; r += 32) a += L21[(long)c * ld + r] * x[sep[r]];
+  a = WarpSum(a);
+  if (lane == 0) xk[c] -= a;
+}
+
 __global__ void ResetInfoKernel(int* info) { *info = 0; }
 __global__ void ResetInfo2Kernel(int* info) { info[0] = 0; info[1] = 0; }
 
@@ -898,6 +935,68 @@ int cxb_potrf_begin(void* stream, int* d_info) {
 int cxb_potrf_panel(void* stream, int m, int j0, int w, double* dH, long ldh, int* d_info) {
   if (m <= 0 || j0 < 0 || w <= 0 || w > kOuter || j0 + w > m) return -1;
   return PotrfBlockColumn(AsStream(stream), m, j0, w, dH, ldh, d_info);
+}
+
+// Partial factorisation of a front: `rows` x `cols` lower trapezoid (rows >= cols), the first `cols`
+// columns are factored (L11 on top, L21 = A21 L11^{-T} below); trailing updates stay inside those
+// columns. d_info is NOT reset (a chain of fronts shares one flag; once set, later fronts are no-ops).
+int cxb_potrf_partial(void* stream, int rows, int cols, double* dF, long ld, int* d_info) {
+  cudaStream_t s = AsStream(stream);
+  if (rows < cols || cols < 0) return -1;
+  for (int j0 = 0; j0 < cols; j0 += kOuter) {
+    const int w = min(kOuter, cols - j0);
+    int rc = PotrfBlockColumn(s, rows, j0, w, dF, ld, d_info);
+    if (rc != 0) return rc;
+    const int rest = cols - j0 - w;
+    if (rest > 0) {
+      const double* L21 = dF + (long)j0 * ld + (j0 + w);
+      rc = Dgemm(s, false, true, rows - j0 - w, rest, w, -1.0, L21, ld, 0, L21, ld, 0, 1.0,
+                 dF + (long)(j0 + w) * ld + (j0 + w), ld, 0, 1, true);
+      if (rc != 0) return rc;
+    }
+  }
+  return LaunchStatus();
+}
+
+// One sweep with an m x m lower-triangular block: transposed == 0: x <- L^{-1} x, else x <- L^{-T} x.
+int cxb_trsv_lower(void* stream, int m, const double* dL, long ldl, double* dx, int transposed) {
+  cudaStream_t s = AsStream(stream);
+  if (m <= 0) return 0;
+  ConfigureOnce();
+  const int nblk = (m + kNB - 1) / kNB;
+  int* sync = nullptr;
+  if (cudaMallocAsync(&sync, sizeof(int) * ((size_t)nblk + 1), s) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+  cudaMemsetAsync(sync, 0, sizeof(int) * ((size_t)nblk + 1), s);
+  CountLaunch();
+  if (transposed) {
+    TrsvBwdWaveKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dx, sync);
+  } else {
+    TrsvFwdWaveKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dx, sync);
+  }
+  cudaFreeAsync(sync, s);
+  return LaunchStatus();
+}
+
+int cxb_scatter_lower_indexed(void* stream, int n, const double* dG, long ldg, const long* d_idx, double sign,
+                              double* d_dst) {
+  if (n <= 0) return 0;
+  dim3 grid((n + 127) / 128, n);
+  CountLaunch(); ScatterLowerIndexedKernel<<<grid, 128, 0, AsStream(stream)>>>(n, dG, ldg, d_idx, sign, d_dst);
+  return LaunchStatus();
+}
+
+int cxb_front_forward(void* stream, int p, int sk, const double* dL21, long ld, const double* d_xk,
+                      const int* d_sep, double* d_x) {
+  if (p <= 0 || sk <= 0) return 0;
+  CountLaunch(); FrontForwardKernel<<<(p + 7) / 8, 256, 0, AsStream(stream)>>>(p, sk, dL21, ld, d_xk, d_sep, d_x);
+  return LaunchStatus();
+}
+
+int cxb_front_backward(void* stream, int p, int sk, const double* dL21, long ld, double* d_xk,
+                       const int* d_sep, const double* d_x) {
+  if (p <= 0 || sk <= 0) return 0;
+  CountLaunch(); FrontBackwardKernel<<<(sk + 7) / 8, 256, 0, AsStream(stream)>>>(p, sk, dL21, ld, d_xk, d_sep, d_x);
+  return LaunchStatus();
 }
 
 // X <- L^{-T} S L^{-1} X; signs == nullptr means S = I (plain Cholesky solve).

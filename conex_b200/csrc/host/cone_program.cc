@@ -11,6 +11,7 @@
 #include "../../../include/conex_b200_device.h"
 #include "communicator.h"
 #include "divergence.h"
+#include "supernodal_kkt_solver.h"
 
 namespace conex {
 
@@ -266,7 +267,23 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
     return true;
   }
   prog.stats.initialized = true;
-  prog.solver = std::make_unique<DenseKKTSolver>(&prog.ctx_, prog.SizeOfKKTSystem());
+  // One dense supernode, or the multifrontal solver when the cones' cliques leave H block-sparse
+  // (reference: SupernodalKKTSolver always; here the dense solver is the special case of one clique).
+  prog.solver.reset();
+  const int N = prog.SizeOfKKTSystem();
+  if (prog.kkt_solver_kind != 1 && prog.NumberOfMultipliers() == 0 && !prog.ctx_.collective) {
+    std::vector<std::vector<int>> cliques;
+    for (const auto& c : prog.eqs) cliques.push_back(c.variables);
+    SupernodalStructure st = AnalyzeCliques(N, cliques);
+    const bool pays = st.supernodes.size() > 1 && N >= 256 && st.factor_flops < 0.5 * st.dense_flops;
+    if (prog.kkt_solver_kind == 2 || pays) {
+      prog.solver = std::make_unique<SupernodalKKTSolver>(&prog.ctx_, N, std::move(st));
+    }
+  } else if (prog.kkt_solver_kind == 2) {
+    throw std::runtime_error("conex-b200: the supernodal KKT solver handles neither equality multipliers nor "
+                             "collective (multi-GPU) programs");
+  }
+  if (!prog.solver) prog.solver = std::make_unique<DenseKKTSolver>(&prog.ctx_, N);
   prog.solver->SetNumberOfMultipliers(prog.NumberOfMultipliers());
   prog.solver->Bind(&prog.eqs);
   prog.InitializeWorkspace();

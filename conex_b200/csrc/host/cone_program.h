@@ -95,21 +95,40 @@ class Container {
   DeviceBuffer<double> y_clique;
 };
 
-// Dense stand-in for SupernodalKKTSolver (reference kkt_solver.h:16-65): one supernode holding the
-// whole Schur complement, factored by the blocked device Cholesky.
-class DenseKKTSolver {
+// What the Newton driver needs from a KKT solver (reference kkt_solver.h:16-65).
+class KKTSolver {
+ public:
+  virtual ~KKTSolver() = default;
+  virtual void Bind(std::list<Container>* eqs) = 0;  // symbolic step
+  virtual void Assemble() = 0;                       // reference kkt_solver.cc:164-170
+  virtual bool Factor() = 0;                         // reference kkt_solver.cc:172-199
+  virtual void SolveInPlace(Ref* b) const = 0;       // reference kkt_solver.cc:220-263
+  // The assembled matrix as one dense N x N block (lower triangle valid) — for the export used by
+  // the tests; the supernodal solver materialises it on demand.
+  virtual Ref KKTMatrix() const = 0;
+  virtual void SetSolverMode(int mode) = 0;
+  virtual void SetIterativeRefinementIterations(int x) = 0;
+  virtual void SetNumberOfMultipliers(int n) = 0;
+  virtual int NumberOfSupernodes() const { return 1; }
+};
+
+// Dense stand-in for SupernodalKKTSolver: one supernode holding the whole Schur complement, factored
+// by the blocked device Cholesky. Used whenever a cone couples all variables (every BASELINE
+// configuration); programs whose cones act on small overlapping subsets get SupernodalKKTSolver
+// (supernodal_kkt_solver.h).
+class DenseKKTSolver : public KKTSolver {
  public:
   DenseKKTSolver(DeviceContext* ctx, int N);
-  void Bind(std::list<Container>* eqs);  // symbolic step: who aliases H, who scatters
-  void Assemble();                       // reference kkt_solver.cc:164-170
-  bool Factor();                         // reference kkt_solver.cc:172-199 (LLT mode)
-  void SolveInPlace(Ref* b) const;       // reference kkt_solver.cc:220-263
-  Ref KKTMatrix() const { return Ref(H_.get(), N_, N_, ldh_); }
-  void SetSolverMode(int mode) { mode_ = mode; }
-  void SetIterativeRefinementIterations(int x) { iterative_refinement_iterations_ = x; }
+  void Bind(std::list<Container>* eqs) override;  // symbolic step: who aliases H, who scatters
+  void Assemble() override;
+  bool Factor() override;                          // LLT mode; LDL^T with multipliers
+  void SolveInPlace(Ref* b) const override;
+  Ref KKTMatrix() const override { return Ref(H_.get(), N_, N_, ldh_); }
+  void SetSolverMode(int mode) override { mode_ = mode; }
+  void SetIterativeRefinementIterations(int x) override { iterative_refinement_iterations_ = x; }
   // Any multiplier block switches Factor()/SolveInPlace() to the regularised LDL^T
   // (reference kkt_solver.cc:180-193).
-  void SetNumberOfMultipliers(int n) { num_dual_ = n; }
+  void SetNumberOfMultipliers(int n) override { num_dual_ = n; }
   bool factorization_regularized() const { return factorization_regularized_; }
 
  private:
@@ -199,7 +218,10 @@ class Program {
   std::vector<Constraint*> constraints_;
   SchurComplementSystem sys;  // residual-only, program level (cone_program.cc:85-86)
   WorkspaceStats stats;
-  std::unique_ptr<DenseKKTSolver> solver;
+  std::unique_ptr<KKTSolver> solver;
+  // 0: choose from the clique structure (supernodal when it saves at least half of the dense
+  // factorisation's flops), 1: one dense supernode, 2: supernodal (CONEXB200_SetKKTSolverKind)
+  int kkt_solver_kind = 0;
   DeviceBuffer<double> memory_;  // the device arena: W, temporaries, per-cone G/AW/AQc, residuals
   DeviceBuffer<double> vectors_;  // b, y, y2 (device copies of the host loop's m-vectors)
   bool is_initialized = false;

@@ -15,6 +15,7 @@
 #include "cone_program.h"
 #include "dense_lmi_constraint.h"
 #include "small_cone_constraint.h"
+#include "supernodal_kkt_solver.h"
 #include "batch_program.h"
 #include <cmath>
 #include "divergence.h"
@@ -227,6 +228,52 @@ int CONEXB200_ShardPlan(int m, int world, int rank, int* out5, int capacity) {
     k++;
   }
   return k;
+}
+
+void CONEXB200_SetKKTSolverKind(void* prog, int kind) {
+  if (prog && kind >= 0 && kind <= 2) static_cast<Program*>(prog)->kkt_solver_kind = kind;
+}
+
+int CONEXB200_GetNumberOfSupernodes(void* prog) {
+  if (!prog) return -1;
+  Program& program = *static_cast<Program*>(prog);
+  return program.solver ? program.solver->NumberOfSupernodes() : 0;
+}
+
+int CONEXB200_SupernodalAnalysis(int N, int num_cliques, const int* clique_ptr, const int* clique_vars,
+                                 int* position, int* node_of, int* node_ptr, int* node_vars, int* sep_ptr,
+                                 int* sep_vars, int sep_capacity, double* flops2) {
+  return Guard(
+      [&]() -> int {
+        std::vector<std::vector<int>> cliques(num_cliques);
+        for (int c = 0; c < num_cliques; c++) {
+          cliques[c].assign(clique_vars + clique_ptr[c], clique_vars + clique_ptr[c + 1]);
+        }
+        const conex::SupernodalStructure st = conex::AnalyzeCliques(N, cliques);
+        const int nodes = static_cast<int>(st.supernodes.size());
+        long seps = 0;
+        for (const auto& s : st.separators) seps += static_cast<long>(s.size());
+        if (seps > sep_capacity) return -static_cast<int>(std::min<long>(seps, 2000000000L));
+        int a = 0, b = 0;
+        for (int k = 0; k < nodes; k++) {
+          node_ptr[k] = a;
+          sep_ptr[k] = b;
+          for (int v : st.supernodes[k]) node_vars[a++] = v;
+          for (int v : st.separators[k]) sep_vars[b++] = v;
+        }
+        node_ptr[nodes] = a;
+        sep_ptr[nodes] = b;
+        for (int v = 0; v < N; v++) {
+          position[v] = st.position[v];
+          node_of[v] = st.node_of[v];
+        }
+        if (flops2) {
+          flops2[0] = st.factor_flops;
+          flops2[1] = st.dense_flops;
+        }
+        return nodes;
+      },
+      -1);
 }
 
 void CONEXB200_SetCollective(void* prog, int collective) {

@@ -135,6 +135,24 @@ int CONEXB200_AddEqualityConstraint(void* prog, int rows, int nvars, const doubl
  * form and assembled by gathers from W, 0 when it is dense, -1 for other constraint types. Valid after
  * the first solve. */
 int CONEXB200_ConstraintIsEntrySparse(void* prog, int id);
+/* ---- chordal-sparse programs: cones on overlapping subsets of the variables (reference
+ * SupernodalKKTSolver, kkt_solver.h:16-65 + clique_ordering.cc + block_triangular_operations.cc) -----
+ * kind 0 (default): decide from the cones' variable sets — the multifrontal solver
+ * (host/supernodal_kkt_solver.h) when there is more than one supernode, at least 256 unknowns and it
+ * saves at least half of the dense factorisation's flops; 1: always one dense supernode; 2: always
+ * multifrontal (fails for programs with equality multipliers or collective programs). Call before
+ * the first solve. */
+void CONEXB200_SetKKTSolverKind(void* prog, int kind);
+/* Supernodes of the KKT solver in use (1 = dense); valid after the first solve / assembly. */
+int CONEXB200_GetNumberOfSupernodes(void* prog);
+/* Host logic of the symbolic step (no GPU). Cliques in CSR form (clique_ptr: num_cliques + 1 entries).
+ * Outputs: position[v] = place of variable v in the elimination order, node_of[v] = supernode that
+ * eliminates it, supernodes and separators in CSR form (node_ptr / sep_ptr: nodes + 1 entries; at most
+ * N nodes; node_vars: N entries; sep_vars: sep_capacity entries), flops2 = {multifrontal, dense N^3/3}.
+ * Returns the number of supernodes, -(needed sep_capacity) if sep_vars is too small, -1 on bad input. */
+int CONEXB200_SupernodalAnalysis(int N, int num_cliques, const int* clique_ptr, const int* clique_vars,
+                                 int* position, int* node_of, int* node_ptr, int* node_vars, int* sep_ptr,
+                                 int* sep_vars, int sep_capacity, double* flops2);
 /* Variables + equality multipliers (conex/constraint_manager.h:42-48). */
 int CONEXB200_SizeOfKKTSystem(void* prog);
 /* Host-logic probe: the pivot order Eigen::RLDLT derives from the diagonal (RLDLT.h:328-356). */

@@ -98,6 +98,24 @@ int cxb_potrf_max_panel(void);
 int cxb_potrf_begin(void* stream, int* d_info);
 int cxb_potrf_panel(void* stream, int m, int j0, int w, double* dH, long ldh, int* d_info);
 
+/* ---- K3/K5 by supernodes (reference block_triangular_operations.cc:184-219 per supernode, :114-182
+ * for the solves; host/supernodal_kkt_solver.cc drives them front by front):
+ * cxb_potrf_partial factors the first `cols` columns of a rows x cols lower trapezoid (L11 on top,
+ * L21 = A21 L11^{-T} below) without resetting d_info; cxb_trsv_lower is one substitution sweep with a
+ * triangular block; cxb_scatter_lower_indexed adds sign * (lower triangle of an n x n matrix) into
+ * arbitrary destinations (d_idx: one offset per pair a >= b in column-major order of the lower
+ * triangle, negative = skip) — the assembly of a cone's G and the Schur update of a separator
+ * (supernodal_assembler.cc:103-165, block_triangular_operations.cc:205-216); cxb_front_forward /
+ * cxb_front_backward apply a front's L21 to the separator entries of the right-hand side. */
+int cxb_potrf_partial(void* stream, int rows, int cols, double* dF, long ld, int* d_info);
+int cxb_trsv_lower(void* stream, int m, const double* dL, long ldl, double* dx, int transposed);
+int cxb_scatter_lower_indexed(void* stream, int n, const double* dG, long ldg, const long* d_idx, double sign,
+                              double* d_dst);
+int cxb_front_forward(void* stream, int p, int sk, const double* dL21, long ld, const double* d_xk,
+                      const int* d_sep, double* d_x);
+int cxb_front_backward(void* stream, int p, int sk, const double* dL21, long ld, double* d_xk,
+                       const int* d_sep, const double* d_x);
+
 /* ---- K5: triangular solves with the Cholesky factor (block_triangular_operations.cc:114-182):
  * X <- L^{-T} L^{-1} X for nrhs right-hand sides (columns of dX, leading dimension ldx). */
 int cxb_potrs_lower(void* stream, int m, const double* dL, long ldl, double* dX, long ldx, int nrhs);
