@@ -37,8 +37,9 @@ void DenseKKTSolver::Bind(std::list<Container>* eqs) {
     c.submatrix_data_.residual_only_ = c.direct_update;  // its G aliases H
     if (!c.identity_clique) {
       c.d_variables.Resize(mc);
-      CudaCheck(cudaMemcpy(c.d_variables.get(), c.variables.data(), sizeof(int) * mc,
-                           cudaMemcpyHostToDevice),
+      // stream-ordered: the program's stream does not synchronise with the legacy default stream
+      CudaCheck(cudaMemcpyAsync(c.d_variables.get(), c.variables.data(), sizeof(int) * mc,
+                                cudaMemcpyHostToDevice, ctx_->cuda_stream()),
                 "upload of clique indices");
       c.y_clique.Resize(mc);
     }
@@ -66,8 +67,10 @@ void DenseKKTSolver::Assemble() {
         std::vector<int> id(mc);
         for (int i = 0; i < mc; i++) id[i] = i;
         c.d_variables.Resize(mc);
-        CudaCheck(cudaMemcpy(c.d_variables.get(), id.data(), sizeof(int) * mc, cudaMemcpyHostToDevice),
+        CudaCheck(cudaMemcpyAsync(c.d_variables.get(), id.data(), sizeof(int) * mc, cudaMemcpyHostToDevice,
+                                  ctx_->cuda_stream()),
                   "upload of clique indices");
+        ctx_->Synchronize();  // `id` is a local
       }
     }
     DeviceCheck(cxb_scatter_add_lower(s, mc, c.submatrix_data_.G.data, c.submatrix_data_.G.ld,

@@ -201,10 +201,16 @@ SupernodalKKTSolver::SupernodalKKTSolver(DeviceContext* ctx, int N, SupernodalSt
   schur_.Resize(std::max<size_t>(max_p * max_p, 1));
   x_.Resize(static_cast<size_t>(std::max(N_, 1)));
   perm_.Resize(static_cast<size_t>(std::max(N_, 1)));
-  CudaCheck(cudaMemcpy(perm_.get(), perm.data(), sizeof(int) * N_, cudaMemcpyHostToDevice), "upload of the order");
+  // Uploads are stream-ordered on the program's stream (pageable sources are staged before the call
+  // returns): the kernels that read these lists run on that stream, which does not synchronise with
+  // the legacy default stream.
+  cudaStream_t stream = ctx_->cuda_stream();
+  CudaCheck(cudaMemcpyAsync(perm_.get(), perm.data(), sizeof(int) * N_, cudaMemcpyHostToDevice, stream),
+            "upload of the order");
   sep_pos_.Resize(std::max<size_t>(sep_pos.size(), 1));
   if (!sep_pos.empty()) {
-    CudaCheck(cudaMemcpy(sep_pos_.get(), sep_pos.data(), sizeof(int) * sep_pos.size(), cudaMemcpyHostToDevice),
+    CudaCheck(cudaMemcpyAsync(sep_pos_.get(), sep_pos.data(), sizeof(int) * sep_pos.size(), cudaMemcpyHostToDevice,
+                              stream),
               "upload of the separator positions");
   }
   // Schur-update destinations: the pair (a >= b) of front k's separator lives in the front that
@@ -221,9 +227,44 @@ SupernodalKKTSolver::SupernodalKKTSolver(DeviceContext* ctx, int N, SupernodalSt
       }
     }
   }
+  // leaves of the assembly tree and the lanes that factor them concurrently
+  is_leaf_.assign(nodes, 1);
+  for (int k = 0; k < nodes; k++) {
+    if (st_.parent[k] >= 0) is_leaf_[st_.parent[k]] = 0;
+  }
+  for (int k = 0; k < nodes; k++) {
+    if (is_leaf_[k] && fronts_meta_[k].p > 0) leaves_.push_back(k);  // isolated roots stay on the main stream
+    else is_leaf_[k] = 0;
+  }
+  if (leaves_.size() >= 2) {
+    lanes_.resize(std::min<size_t>(4, leaves_.size()));
+    size_t leaf_p = 0;
+    for (int k : leaves_) leaf_p = std::max<size_t>(leaf_p, fronts_meta_[k].p);
+    for (auto& l : lanes_) {
+      CudaCheck(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+      CudaCheck(cudaEventCreateWithFlags(&l.factored, cudaEventDisableTiming), "cudaEventCreate");
+      CudaCheck(cudaEventCreateWithFlags(&l.scattered, cudaEventDisableTiming), "cudaEventCreate");
+      l.schur.Resize(std::max<size_t>(leaf_p * leaf_p, 1));
+    }
+    CudaCheck(cudaEventCreateWithFlags(&assembled_, cudaEventDisableTiming), "cudaEventCreate");
+  } else {
+    for (int k : leaves_) is_leaf_[k] = 0;
+    leaves_.clear();
+  }
   update_idx_.Resize(update.size());
-  CudaCheck(cudaMemcpy(update_idx_.get(), update.data(), sizeof(long) * update.size(), cudaMemcpyHostToDevice),
+  CudaCheck(cudaMemcpyAsync(update_idx_.get(), update.data(), sizeof(long) * update.size(), cudaMemcpyHostToDevice,
+                            stream),
             "upload of the update lists");
+  ctx_->Synchronize();
+}
+
+SupernodalKKTSolver::~SupernodalKKTSolver() {
+  for (auto& l : lanes_) {
+    if (l.factored) cudaEventDestroy(l.factored);
+    if (l.scattered) cudaEventDestroy(l.scattered);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  if (assembled_) cudaEventDestroy(assembled_);
 }
 
 long SupernodalKKTSolver::Locate(int u, int v) const {
@@ -250,7 +291,8 @@ void SupernodalKKTSolver::Bind(std::list<Container>* eqs) {
     c.submatrix_data_.m_ = mc;
     c.submatrix_data_.residual_only_ = false;  // every cone assembles into its own G
     c.d_variables.Resize(mc);
-    CudaCheck(cudaMemcpy(c.d_variables.get(), c.variables.data(), sizeof(int) * mc, cudaMemcpyHostToDevice),
+    CudaCheck(cudaMemcpyAsync(c.d_variables.get(), c.variables.data(), sizeof(int) * mc, cudaMemcpyHostToDevice,
+                              ctx_->cuda_stream()),
               "upload of clique indices");
     c.y_clique.Resize(mc);
     std::vector<long> idx(static_cast<size_t>(mc) * (mc + 1) / 2);
@@ -264,10 +306,12 @@ void SupernodalKKTSolver::Bind(std::list<Container>* eqs) {
     }
     cone_idx_.emplace_back(std::max<size_t>(idx.size(), 1));
     if (!idx.empty()) {
-      CudaCheck(cudaMemcpy(cone_idx_.back().get(), idx.data(), sizeof(long) * idx.size(), cudaMemcpyHostToDevice),
+      CudaCheck(cudaMemcpyAsync(cone_idx_.back().get(), idx.data(), sizeof(long) * idx.size(), cudaMemcpyHostToDevice,
+                                ctx_->cuda_stream()),
                 "upload of the assembly list");
     }
   }
+  ctx_->Synchronize();
 }
 
 void SupernodalKKTSolver::Assemble() {
@@ -291,23 +335,64 @@ bool SupernodalKKTSolver::Factor() {
     throw std::runtime_error("conex-b200: equality multipliers need the dense LDL^T solver");
   }
   void* s = ctx_->stream();
+  cudaStream_t main = ctx_->cuda_stream();
   int* info = ctx_->flags();
   DeviceCheck(cxb_potrf_begin(s, info), "cxb_potrf_begin");
-  for (const Front& f : fronts_meta_) {
+  if (!lanes_.empty()) {
+    CudaCheck(cudaEventRecord(assembled_, main), "cudaEventRecord");
+    for (auto& l : lanes_) CudaCheck(cudaStreamWaitEvent(l.stream, assembled_, 0), "cudaStreamWaitEvent");
+    for (size_t i = 0; i < lanes_.size(); i++) EnqueueLeaf(i, info);
+  }
+  size_t leaf_number = 0;
+  for (size_t k = 0; k < fronts_meta_.size(); k++) {
+    const Front& f = fronts_meta_[k];
     double* F = fronts_.get() + f.offset;
     const long ld = f.s + f.p;
-    DeviceCheck(cxb_potrf_partial(s, f.s + f.p, f.s, F, ld, info), "cxb_potrf_partial");
-    if (f.p == 0) continue;
-    const double* L21 = F + f.s;
-    DeviceCheck(cxb_dgemm(s, 0, 1, f.p, f.p, f.s, 1.0, L21, ld, 0, L21, ld, 0, 0.0, schur_.get(), f.p, 0, 1, 1),
-                "cxb_dgemm(Schur complement of a front)");
-    DeviceCheck(cxb_scatter_lower_indexed(s, f.p, schur_.get(), f.p, update_idx_.get() + f.update_offset, -1.0,
+    const double* schur = schur_.get();
+    Lane* lane = nullptr;
+    if (is_leaf_[k]) {
+      // factored (or being factored) on its lane: only the update is applied here, in node order
+      lane = &lanes_[leaf_number % lanes_.size()];
+      CudaCheck(cudaStreamWaitEvent(main, lane->factored, 0), "cudaStreamWaitEvent");
+      schur = lane->schur.get();
+    } else {
+      DeviceCheck(cxb_potrf_partial(s, f.s + f.p, f.s, F, ld, info), "cxb_potrf_partial");
+      if (f.p == 0) continue;
+      const double* L21 = F + f.s;
+      DeviceCheck(cxb_dgemm(s, 0, 1, f.p, f.p, f.s, 1.0, L21, ld, 0, L21, ld, 0, 0.0, schur_.get(), f.p, 0, 1, 1),
+                  "cxb_dgemm(Schur complement of a front)");
+    }
+    DeviceCheck(cxb_scatter_lower_indexed(s, f.p, schur, f.p, update_idx_.get() + f.update_offset, -1.0,
                                           fronts_.get()),
                 "cxb_scatter_lower_indexed(update)");
+    if (lane) {
+      // the lane's scratch is free again: hand the lane its next leaf
+      CudaCheck(cudaEventRecord(lane->scattered, main), "cudaEventRecord");
+      if (leaf_number + lanes_.size() < leaves_.size()) EnqueueLeaf(leaf_number + lanes_.size(), info);
+      leaf_number++;
+    }
   }
   int host_info = 0;
   ctx_->DownloadInts(&host_info, info, 1);
   return host_info == 0;  // reference block_triangular_operations.cc:193-196
+}
+
+// Leaf number i (in node order) runs on lane i mod L: partial factorisation of its front and its
+// Schur complement into the lane's scratch. Called only after the update of leaf i - L has been
+// enqueued on the main stream (its `scattered` event orders the reuse of the scratch).
+void SupernodalKKTSolver::EnqueueLeaf(size_t leaf_number, int* info) {
+  Lane& lane = lanes_[leaf_number % lanes_.size()];
+  const Front& f = fronts_meta_[leaves_[leaf_number]];
+  double* F = fronts_.get() + f.offset;
+  const long ld = f.s + f.p;
+  void* ls = reinterpret_cast<void*>(lane.stream);
+  if (leaf_number >= lanes_.size()) CudaCheck(cudaStreamWaitEvent(lane.stream, lane.scattered, 0), "cudaStreamWaitEvent");
+  DeviceCheck(cxb_potrf_partial(ls, f.s + f.p, f.s, F, ld, info), "cxb_potrf_partial");
+  // splits = 1: the split-K workspace of the GEMM layer is shared by all streams
+  DeviceCheck(cxb_dgemm_ex(ls, -1, 1, 0, 1, f.p, f.p, f.s, 1.0, F + f.s, ld, 0, F + f.s, ld, 0, 0.0, lane.schur.get(),
+                           f.p, 0, 1, 1, 0, 0),
+              "cxb_dgemm(Schur complement of a leaf front)");
+  CudaCheck(cudaEventRecord(lane.factored, lane.stream), "cudaEventRecord");
 }
 
 void SupernodalKKTSolver::SolveInPlace(Ref* b) const {
@@ -360,8 +445,10 @@ Ref SupernodalKKTSolver::KKTMatrix() const {
     }
   }
   dense_.Resize(dense.size());
-  CudaCheck(cudaMemcpy(dense_.get(), dense.data(), sizeof(double) * dense.size(), cudaMemcpyHostToDevice),
+  CudaCheck(cudaMemcpyAsync(dense_.get(), dense.data(), sizeof(double) * dense.size(), cudaMemcpyHostToDevice,
+                            ctx_->cuda_stream()),
             "upload of the dense export");
+  ctx_->Synchronize();
   return Ref(dense_.get(), N_, N_, ld);
 }
 

@@ -45,6 +45,7 @@ SupernodalStructure AnalyzeCliques(int N, const std::vector<std::vector<int>>& c
 class SupernodalKKTSolver : public KKTSolver {
  public:
   SupernodalKKTSolver(DeviceContext* ctx, int N, SupernodalStructure structure);
+  ~SupernodalKKTSolver() override;
   void Bind(std::list<Container>* eqs) override;
   void Assemble() override;
   bool Factor() override;
@@ -77,6 +78,18 @@ class SupernodalKKTSolver : public KKTSolver {
   DeviceBuffer<int> sep_pos_;                 // per front: elimination positions of the separator rows
   DeviceBuffer<int> perm_;                    // perm_[position] = original variable
   mutable DeviceBuffer<double> schur_;        // largest p_k x p_k
+  // Leaves of the assembly tree do not depend on each other: they are factored on side streams
+  // ("lanes", round-robin) while the main stream applies their Schur updates in node order.
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t factored = nullptr, scattered = nullptr;
+    DeviceBuffer<double> schur;
+  };
+  std::vector<Lane> lanes_;
+  cudaEvent_t assembled_ = nullptr;
+  std::vector<int> leaves_;                   // node indices without children, ascending
+  std::vector<char> is_leaf_;
+  void EnqueueLeaf(size_t leaf_number, int* info);
   mutable DeviceBuffer<double> x_;            // right-hand side in elimination order
   mutable DeviceBuffer<double> dense_;        // KKTMatrix() export
   std::vector<DeviceBuffer<long>> cone_idx_;  // per cone: destinations of the lower triangle of its G

@@ -17,7 +17,7 @@ from test_supernodal import block_arrow_program  # noqa: E402
 
 
 def main():
-    blocks, private, shared, order = [int(a) for a in sys.argv[1:5]] if len(sys.argv) >= 5 else (8, 1500, 100, 40)
+    blocks, private, shared, order = [int(a) for a in sys.argv[1:5]] if len(sys.argv) >= 5 else (8, 1500, 100, 60)
     dev = devlib.product()
     L = dev.lib
     L.CONEXB200_SetKKTSolverKind.argtypes = [C.c_void_p, C.c_int]
@@ -32,6 +32,7 @@ def main():
         for rep in range(2):  # second solve: warmed-up allocations
             solved, y = P.maximize(b, dev.default_config(prepare_dual_variables=1))
         its = P.status()["num_iterations"]
+        assert its > 2, "the solve did not run (singular Schur complement: each cone needs at most n(n+1)/2 variables)"
         phases = []
         for i in range(its):
             ph = np.zeros(5)
