@@ -320,12 +320,15 @@ CXB_HOST_DEVICE long PsdSchurSmemDoubles(int n, int m, int team) {
   const long a = nn + 2 * PsdSchurGroup(n, team) * nn;
   const long ti = (m + 2 + 3) / 4, tj = (m + 1 + 1) / 2;
   const long b = (long)(2 * m + 3) * (kGramChunk + 1) + ti * tj * 8;
-  return a > b ? a : b;
+  // symmetric form: W -> L and L^T (2 nn), then `group` matrices and their products (2 group nn)
+  const long c = 2 * nn + 2 * PsdSchurGroup(n, team) * nn;
+  const long ab = a > b ? a : b;
+  return ab > c ? ab : c;
 }
 
 template <class T>
-CXB_HD void PsdSchur(T& t, int n, int m, const double* AC, const double* W, double* work, double* sm,
-                     double* G, long ldg, double* AW, double* AQc, double* scal, bool acc) {
+CXB_HD void PsdSchurClassic(T& t, int n, int m, const double* AC, const double* W, double* work, double* sm,
+                            double* G, long ldg, double* AW, double* AQc, double* scal, bool acc) {
   const int nn = n * n;
   const int tn = (n + 3) / 4, tiles = tn * tn;
   const int group = PsdSchurGroup(n, t.size());
@@ -454,6 +457,175 @@ CXB_HD void PsdSchur(T& t, int n, int m, const double* AC, const double* W, doub
       Accumulate(j < m ? AW + j : scal + 0, s, acc);
     }
   });
+}
+
+// The same Schur system from the symmetric form (here for one small block): with
+// W = L L^T, H_ij = <L^T A_i L, L^T A_j L>, so phase A forms S_i = L^T (A_i L) — the first product skips
+// the zeros above L's diagonal, the second computes lower tiles only: 1.33 n^3 instead of 4 n^3 per
+// matrix — and stores only its lower triangle, off-diagonal entries scaled by sqrt(2) so that the plain
+// dot product of two packed matrices is their trace inner product; phase B is then X X^T over
+// n (n + 1) / 2 entries instead of n^2, with both operands read from the same array. The packed
+// identity stands in for W in the row that yields AW_j = tr(W A_j) = <I, S_j>.
+// Returns false (nothing written) when W is not numerically positive definite; the caller then uses
+// the classic form, which needs no factorisation.
+template <class T>
+CXB_HD bool PsdSchurSymmetric(T& t, int n, int m, const double* AC, const double* W, double* work, double* sm,
+                              double* G, long ldg, double* AW, double* AQc, double* scal, bool acc) {
+  const int nn = n * n;
+  const int kp = n * (n + 1) / 2;
+  const int tn = (n + 3) / 4, tiles = tn * tn;
+  const int group = PsdSchurGroup(n, t.size());
+  const double kSqrt2 = 1.4142135623730951;
+  // ---- L = chol(W): sL column-major (zeros above the diagonal), sLT its transpose --------------------
+  double* sL = sm;
+  double* sLT = sm + nn;
+  t.par(nn, [&](int e) { sL[e] = (e % n >= e / n) ? W[e] : 0.0; });
+  for (int j = 0; j < n; j++) {
+    const double d = sL[j * n + j];  // same value in every thread (barrier at the end of the last phase)
+    if (!(d > 0.0)) return false;
+    const int rem = n - j - 1;
+    t.par(rem * rem, [&](int e) {
+      const int r = j + 1 + e % rem, c = j + 1 + e / rem;
+      if (r >= c) sL[c * n + r] -= sL[j * n + r] * sL[j * n + c] / d;
+    });
+    const double rd = sqrt(d);
+    t.par(n - j, [&](int i) { sL[j * n + j + i] = (i == 0) ? rd : sL[j * n + j + i] / rd; });
+  }
+  t.par(nn, [&](int e) { sLT[(e % n) * n + e / n] = sL[e]; });  // sLT[k * n + c] = L(k, c)
+  // ---- phase A: S_i = L^T (A_i L), lower triangle, packed ---------------------------------------------
+  {
+    double* sA = sm + 2 * nn;
+    double* sT = sA + (long)group * nn;
+    for (int i0 = 0; i0 <= m; i0 += group) {
+      const int gc = (m + 1 - i0 < group) ? m + 1 - i0 : group;
+      const double* src = AC + (long)i0 * nn;
+      t.par(gc * nn, [&](int e) { sA[e] = src[e]; });
+      // T = A L, row-major sT[r * n + c]; L(k, c) = 0 for k < c: the k loop starts at the tile's column
+      t.par(gc * tiles, [&](int w) {
+        const int g = w / tiles, tile = w % tiles;
+        const int r0 = (tile % tn) * 4, c0 = (tile / tn) * 4;
+        const double* A = sA + (long)g * nn;
+        double c[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int k = c0; k < n; k++) {
+          double a[4], b[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) a[x] = (r0 + x < n) ? A[k * n + r0 + x] : 0.0;
+#pragma unroll
+          for (int y = 0; y < 4; y++) b[y] = (c0 + y < n) ? sLT[k * n + c0 + y] : 0.0;
+#pragma unroll
+          for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) c[x][y] += a[x] * b[y];
+        }
+        double* Tg = sT + (long)g * nn;
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++)
+            if (r0 + x < n && c0 + y < n) Tg[(r0 + x) * n + c0 + y] = c[x][y];
+      });
+      // S = L^T T, tiles on or below the diagonal only; L^T(r, k) = L(k, r) = 0 for k < r
+      t.par(gc * tiles, [&](int w) {
+        const int g = w / tiles, tile = w % tiles;
+        const int r0 = (tile % tn) * 4, c0 = (tile / tn) * 4;
+        if (r0 + 3 < c0) return;
+        const double* Tg = sT + (long)g * nn;
+        double c[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int k = r0; k < n; k++) {
+          double a[4], b[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) a[x] = (r0 + x < n) ? sLT[k * n + r0 + x] : 0.0;
+#pragma unroll
+          for (int y = 0; y < 4; y++) b[y] = (c0 + y < n) ? Tg[k * n + c0 + y] : 0.0;
+#pragma unroll
+          for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) c[x][y] += a[x] * b[y];
+        }
+        double* Sg = work + (long)(i0 + g) * kp;
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+          for (int x = 0; x < 4; x++) {
+            const int r = r0 + x, cc = c0 + y;
+            if (r < n && cc <= r) Sg[cc * n - cc * (cc - 1) / 2 + (r - cc)] = (r == cc) ? c[x][y] : kSqrt2 * c[x][y];
+          }
+      });
+    }
+    // row m + 1: the packed identity
+    t.par(nn, [&](int e) {
+      const int r = e % n, cc = e / n;
+      if (cc <= r) work[(long)(m + 1) * kp + cc * n - cc * (cc - 1) / 2 + (r - cc)] = (r == cc) ? 1.0 : 0.0;
+    });
+  }
+  // ---- phase B: Gram of the packed matrices -----------------------------------------------------------
+  const int MI = m + 2, MJ = m + 1;
+  const int ti = (MI + 3) / 4, tj = (MJ + 1) / 2;
+  const int P = kGramChunk + 1;
+  double* sB = sm;
+  double* sAcc = sm + (long)MI * P;
+  t.par(ti * tj * 8, [&](int e) { sAcc[e] = 0.0; });
+  for (int q0 = 0; q0 < kp; q0 += kGramChunk) {
+    const int kc = (kp - q0 < kGramChunk) ? kp - q0 : kGramChunk;
+    t.par(MI * kc, [&](int e) {
+      const int row = e / kc, q = e % kc;
+      sB[row * P + q] = work[(long)row * kp + q0 + q];
+    });
+    t.par(ti * tj, [&](int w) {
+      const int i0 = (w % ti) * 4, j0 = (w / ti) * 2;
+      if (i0 + 3 < j0) return;  // tile entirely above the diagonal
+      double c[4][2];
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        c[x][0] = sAcc[w * 8 + 2 * x];
+        c[x][1] = sAcc[w * 8 + 2 * x + 1];
+      }
+      const double* b0 = sB + (long)(i0 + 0 < MI ? i0 + 0 : MI - 1) * P;
+      const double* b1 = sB + (long)(i0 + 1 < MI ? i0 + 1 : MI - 1) * P;
+      const double* b2 = sB + (long)(i0 + 2 < MI ? i0 + 2 : MI - 1) * P;
+      const double* b3 = sB + (long)(i0 + 3 < MI ? i0 + 3 : MI - 1) * P;
+      const double* a0 = sB + (long)(j0 + 0 < MJ ? j0 + 0 : MJ - 1) * P;
+      const double* a1 = sB + (long)(j0 + 1 < MJ ? j0 + 1 : MJ - 1) * P;
+      for (int q = 0; q < kc; q++) {
+        const double x0 = b0[q], x1 = b1[q], x2 = b2[q], x3 = b3[q], y0 = a0[q], y1 = a1[q];
+        c[0][0] += x0 * y0;
+        c[0][1] += x0 * y1;
+        c[1][0] += x1 * y0;
+        c[1][1] += x1 * y1;
+        c[2][0] += x2 * y0;
+        c[2][1] += x2 * y1;
+        c[3][0] += x3 * y0;
+        c[3][1] += x3 * y1;
+      }
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        sAcc[w * 8 + 2 * x] = c[x][0];
+        sAcc[w * 8 + 2 * x + 1] = c[x][1];
+      }
+    });
+  }
+  t.par(ti * tj * 8, [&](int e) {
+    const int w = e / 8, x = (e % 8) / 2, y = e % 2;
+    const int i = (w % ti) * 4 + x, j = (w / ti) * 2 + y;
+    if (i >= MI || j >= MJ || i < j) return;
+    const double s = sAcc[e];
+    if (i < m) {
+      Accumulate(G + (long)j * ldg + i, s, acc);
+    } else if (i == m) {
+      Accumulate(j < m ? AQc + j : scal + 1, s, acc);
+    } else {
+      Accumulate(j < m ? AW + j : scal + 0, s, acc);
+    }
+  });
+  return true;
+}
+
+// form: 0 = symmetric when W factors, else classic (default); 1 = classic (the reference's formula).
+template <class T>
+CXB_HD void PsdSchur(T& t, int n, int m, const double* AC, const double* W, double* work, double* sm,
+                     double* G, long ldg, double* AW, double* AQc, double* scal, bool acc, int form = 0) {
+  if (form == 0 && PsdSchurSymmetric(t, n, m, AC, W, work, sm, G, ldg, AW, AQc, scal, acc)) return;
+  PsdSchurClassic(t, n, m, AC, W, work, sm, G, ldg, AW, AQc, scal, acc);
 }
 
 // Extreme eigenvalues of the symmetric tridiagonal (alpha[0..k), beta[0..k-1)) by Sturm bisection —

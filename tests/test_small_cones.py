@@ -201,3 +201,30 @@ def test_small_cholesky_reports_first_bad_pivot(be):
     H = np.stack([np.diag([1.0, 2.0, -1.0, 3.0]), np.eye(4)])
     _, info, _ = be.potrf(H)
     assert info.tolist() == [3, 0]
+
+
+def test_psd_schur_with_indefinite_scaling_point_uses_the_classic_form(be):
+    """The batched PSD Schur kernel takes the symmetric form (W = L L^T, packed L^T A_i L) and falls
+    back to the reference's formula H_ij = tr(A_i W A_j W) (dense_lmi_constraint.cc:62-103) when W
+    does not factor; the formula itself is defined for any symmetric W."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    n, m, B = 7, 5, 2
+    data = np.stack([random_cone_data(PSD, n, m, rng) for _ in range(B)])
+    cone = be.cone(PSD, n, m, data)
+    Ws = []
+    for p in range(B):
+        R = rng.uniform(-1, 1, size=(n, n))
+        W = 0.5 * (R + R.T)                      # indefinite
+        if p == 1:
+            W = W @ W.T + 0.1 * np.eye(n)        # positive definite: symmetric form
+        Ws.append(W)
+    cone.set_state(np.stack([W.ravel(order="F") for W in Ws]))
+    G, AW, AQc, sc = cone.schur()
+    for p in range(B):
+        mats = [data[p][i * n * n:(i + 1) * n * n].reshape(n, n, order="F") for i in range(m + 1)]
+        W, Cm = Ws[p], mats[m]
+        Href = np.array([[np.trace(mats[i] @ W @ mats[j] @ W) for j in range(m)] for i in range(m)])
+        close(G[p], np.tril(Href), 1e-11, "H")
+        close(AW[p], np.array([np.trace(W @ mats[j]) for j in range(m)]), 1e-11, "AW")
+        close(AQc[p], np.array([np.trace(W @ Cm @ W @ mats[j]) for j in range(m)]), 1e-11, "AQc")
+        close(sc[p], np.array([np.trace(W @ Cm), np.trace(W @ Cm @ W @ Cm)]), 1e-11, "scalars")
