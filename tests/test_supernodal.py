@@ -209,6 +209,22 @@ def chain_program(links, width, overlap, order, seed):
     return m, cones
 
 
+def lp_chain_program(links=50, width=5, rows=10, seed=1):
+    """The reference's own sparse test (conex/test/test_lp.cc:133-214, `LP Sparse`): 50 LP blocks of 10
+    rows on 5 variables each, consecutive blocks sharing one variable (201 variables), c_i = 1 + 0.01 i.
+    The C ABI has no LP constraint on a variable subset (the reference test uses the C++ AddConstraint),
+    so every block is given as the equivalent LMI with diagonal matrices."""
+    rng = np.random.default_rng(seed)
+    cones, start = [], 0
+    for i in range(links):
+        variables = list(range(start, start + width))
+        start = variables[-1]
+        A = rng.uniform(-1, 1, size=(rows, width))
+        mats = [np.diag(A[:, j]) for j in range(width)]
+        cones.append((mats, (1.0 + 0.01 * i) * np.eye(rows), variables))
+    return start + 1, cones
+
+
 def solve_with(L, m, cones, kind=None):
     P = L.program(m)
     if kind is not None:
@@ -224,7 +240,7 @@ def solve_with(L, m, cones, kind=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", ["arrow", "chain", "chain_long", "disconnected"])
+@pytest.mark.parametrize("shape", ["arrow", "chain", "chain_long", "disconnected", "lp_chain"])
 def test_sparse_programs_match_oracle_and_dense_solver(shape):
     import devlib
     dev, ora = devlib.product(), oracle()
@@ -234,6 +250,9 @@ def test_sparse_programs_match_oracle_and_dense_solver(shape):
         m, cones = chain_program(links=5, width=6, overlap=2, order=6, seed=2)
     elif shape == "chain_long":
         m, cones = chain_program(links=30, width=5, overlap=2, order=5, seed=3)
+    elif shape == "lp_chain":
+        m, cones = lp_chain_program()
+        assert m == 201
     else:
         m, cones = chain_program(links=3, width=4, overlap=0, order=5, seed=4)
     Po, so, yo, bo, _ = solve_with(ora, m, cones)
@@ -248,6 +267,17 @@ def test_sparse_programs_match_oracle_and_dense_solver(shape):
         assert abs(ref[-1]["by"] - ls[-1]["by"]) <= 1e-7 * max(1.0, abs(ref[-1]["by"]))
     assert np.abs(yo - ys).max() <= 1e-6 * max(1.0, np.abs(yo).max())
     assert np.abs(yd - ys).max() <= 1e-6 * max(1.0, np.abs(yd).max())
+    if shape == "lp_chain":
+        # the reference's checks on its sparse solve (test_lp.cc:186-202): slack >= -eps, A'x = b
+        assert ns == 50
+        Ax = np.zeros(m)
+        for i, (mats, Cm, variables) in enumerate(cones):
+            slack = Cm - sum(ys[v] * A for v, A in zip(variables, mats))
+            assert np.diag(slack).min() >= -1e-8
+            X = Ps.dual_variable(i)
+            for v, A in zip(variables, mats):
+                Ax[v] += np.sum(A * X)
+        assert np.linalg.norm(Ax - bs) < 1e-8 * max(1.0, np.linalg.norm(bs))
     # the assembled Newton systems agree entry by entry (dense export of the fronts)
     Hd = Pd.newton_system(coldstart=True)[0]
     Hs = Ps.newton_system(coldstart=True)[0]
