@@ -272,23 +272,38 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
   prog.stats.initialized = true;
   // One dense supernode, or the multifrontal solver when the cones' cliques leave H block-sparse
   // (reference: SupernodalKKTSolver always; here the dense solver is the special case of one clique).
-  prog.solver.reset();
   const int N = prog.SizeOfKKTSystem();
+  bool reused = false;
+  std::unique_ptr<KKTSolver> fresh;
   if (prog.kkt_solver_kind != 1 && prog.NumberOfMultipliers() == 0 && !prog.ctx_.collective) {
     std::vector<std::vector<int>> cliques;
     for (const auto& c : prog.eqs) cliques.push_back(c.variables);
-    SupernodalStructure st = AnalyzeCliques(N, cliques);
-    const bool pays = st.supernodes.size() > 1 && N >= 256 && st.factor_flops < 0.5 * st.dense_flops;
-    if (prog.kkt_solver_kind == 2 || pays) {
-      prog.solver = std::make_unique<SupernodalKKTSolver>(&prog.ctx_, N, std::move(st));
+    // The symbolic step depends on the cliques alone: a repeated cold start of the same program keeps
+    // the multifrontal solver with its destination lists (hundreds of ms of host work at order 10^4).
+    if (prog.solver && prog.solver_is_multifrontal_ && prog.solver_order_ == N &&
+        prog.solver_kind_ == prog.kkt_solver_kind && prog.solver_cliques_ == cliques) {
+      reused = true;
+    } else {
+      SupernodalStructure st = AnalyzeCliques(N, cliques);
+      const bool pays = st.supernodes.size() > 1 && N >= 256 && st.factor_flops < 0.5 * st.dense_flops;
+      if (prog.kkt_solver_kind == 2 || pays) {
+        fresh = std::make_unique<SupernodalKKTSolver>(&prog.ctx_, N, std::move(st));
+        prog.solver_cliques_ = std::move(cliques);
+        prog.solver_order_ = N;
+        prog.solver_kind_ = prog.kkt_solver_kind;
+      }
     }
   } else if (prog.kkt_solver_kind == 2) {
     throw std::runtime_error("conex-b200: the supernodal KKT solver handles neither equality multipliers nor "
                              "collective (multi-GPU) programs");
   }
-  if (!prog.solver) prog.solver = std::make_unique<DenseKKTSolver>(&prog.ctx_, N);
+  if (!reused) {
+    prog.solver_is_multifrontal_ = fresh != nullptr;
+    if (!fresh) fresh = std::make_unique<DenseKKTSolver>(&prog.ctx_, N);
+    prog.solver = std::move(fresh);
+  }
   prog.solver->SetNumberOfMultipliers(prog.NumberOfMultipliers());
-  prog.solver->Bind(&prog.eqs);
+  if (!reused) prog.solver->Bind(&prog.eqs);
   prog.InitializeWorkspace();
   if (config.initialization_mode == CONEX_INITIALIZATION_MODE_COLDSTART) {
     prog.stats.b_scaling = 1;

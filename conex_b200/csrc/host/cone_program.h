@@ -222,6 +222,11 @@ class Program {
   // 0: choose from the clique structure (supernodal when it saves at least half of the dense
   // factorisation's flops), 1: one dense supernode, 2: supernodal (CONEXB200_SetKKTSolverKind)
   int kkt_solver_kind = 0;
+  // what the current multifrontal solver was built from (Initialize keeps it across cold starts)
+  std::vector<std::vector<int>> solver_cliques_;
+  int solver_order_ = -1;
+  int solver_kind_ = -1;
+  bool solver_is_multifrontal_ = false;
   DeviceBuffer<double> memory_;  // the device arena: W, temporaries, per-cone G/AW/AQc, residuals
   DeviceBuffer<double> vectors_;  // b, y, y2 (device copies of the host loop's m-vectors)
   bool is_initialized = false;
