@@ -882,6 +882,11 @@ def run_b200(args):
                            "achieved counts the reference's dense flops (4mn^3 + m(m+1)n^2); the kernel "
                            "executes 3mn^3 + m(m+1)n^2 because W(A_i W) is symmetric, so frac can exceed 1",
             "algorithmic_flops_per_step": asm_flops,
+            # what the default (symmetric) form actually executes: A_i L with the zeros of L skipped (n^3),
+            # lower tiles of L^T (A_i L) (n^3 / 3), Gram over the packed length 0.54 n^2, lower triangle
+            "executed_flops_per_step_if_symmetric_form": (4.0 / 3.0) * m * n ** 3 + 0.54 * float(m) * (m + 1) * n ** 2,
+            "achieved_on_executed_flops_if_symmetric_form": ((4.0 / 3.0) * m * n ** 3 + 0.54 * float(m) * (m + 1) * n ** 2) / (asm_ms * 1e-3) / 1e12,
+            "frac_on_executed_flops_if_symmetric_form": ((4.0 / 3.0) * m * n ** 3 + 0.54 * float(m) * (m + 1) * n ** 2) / (asm_ms * 1e-3) / 1e12 / (peak_tf * world),
             "traffic": ASSEMBLY_TRAFFIC_C2 if (w["kind"], n, m, world) == ("maxcut", 2000, 2000, 1) else None,
             "traffic_note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of all DgemmKernel launches of one "
                             "assembly phase, from profiles/r01_d_c2_dgemm_ncu_full.txt: 61 panels x (K1a 2.38 GB + K1b "
