@@ -71,6 +71,13 @@ _lib.CONEXB200_BatchMaximize.argtypes = [_C.c_void_p, _dp, _C.POINTER(CONEX_Solv
 _lib.CONEXB200_BatchGetResults.argtypes = [_C.c_void_p, _ip, _dp, _dp, _dp]
 
 
+_lib.CONEXB200_SetKKTSolverKind.argtypes = [_C.c_void_p, _C.c_int]
+_lib.CONEXB200_SetKKTSolverKind.restype = None
+_lib.CONEXB200_GetNumberOfSupernodes.argtypes = [_C.c_void_p]
+_lib.CONEXB200_SetCollective.argtypes = [_C.c_void_p, _C.c_int]
+_lib.CONEXB200_SetCollective.restype = None
+
+
 def device_available():
     return bool(_lib.CONEXB200_DeviceAvailable())
 
@@ -194,6 +201,21 @@ class Conex:
         self.c.append(cf)
         _lib.CONEX_AddSparseLMIConstraint(self.a, _ptr(packed), n, n, k, _ptr(cf), n, n, v, k)
         self.num_constraints += 1
+
+    # ---- conex-b200 extensions (include/conex_b200.h) ----
+    def SetKKTSolverKind(self, kind):
+        """0: chosen from the cones' variable sets (default), 1: one dense supernode, 2: multifrontal
+        (cones on overlapping variable subsets, AddSparseLinearMatrixInequality). Before the first solve."""
+        _lib.CONEXB200_SetKKTSolverKind(self.a, int(kind))
+
+    def NumberOfSupernodes(self):
+        """Supernodes of the KKT solver in use (1 = dense); valid after the first solve."""
+        return _lib.CONEXB200_GetNumberOfSupernodes(self.a)
+
+    def SetCollective(self, collective=True):
+        """Every rank of the process-wide communicator builds this same program and solves in lock step
+        (the Cholesky of large Schur complements is then factored across the GPUs)."""
+        _lib.CONEXB200_SetCollective(self.a, int(bool(collective)))
 
     def Maximize(self, b, config=None):
         if config is None:
