@@ -848,8 +848,18 @@ namespace {
 struct LookAhead {
   cudaStream_t side = nullptr;
   cudaEvent_t updated = nullptr, factored = nullptr;
+  int device = -1;
   bool Prepare() {
-    if (side) return true;
+    int current = 0;
+    if (cudaGetDevice(&current) != cudaSuccess) return false;
+    if (side && device == current) return true;
+    if (side) {  // the thread moved to another device: streams and events belong to the old one
+      cudaStreamDestroy(side);
+      cudaEventDestroy(updated);
+      cudaEventDestroy(factored);
+      side = nullptr;
+    }
+    device = current;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
