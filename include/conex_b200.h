@@ -1,6 +1,6 @@
 /* conex-b200 extensions to the conex C ABI (include/conex.h).
  *
- * None of these exist in the reference; they expose what its C++ tests reach through conex/*.h
+ * None of these exist in the reference; they expose what its C++ tests reach through the headers under conex/
  * (GetFeasibleObjective, Program::Status, the REPORT() stream) plus device-resident construction
  * and timing hooks needed to benchmark on the GPU. All take the opaque program handle returned by
  * CONEX_CreateConeProgram. Host pointers unless a parameter is named d_*.
