@@ -42,28 +42,37 @@ class CONEX_IterationStats(_C.Structure):
     _fields_ = [("mu", _C.c_double), ("iteration_number", _C.c_int)]
 
 
-_lib.CONEX_CreateConeProgram.restype = _C.c_void_p
-_lib.CONEX_DeleteConeProgram.argtypes = [_C.c_void_p]
-_lib.CONEX_SetNumberOfVariables.argtypes = [_C.c_void_p, _C.c_int]
-_lib.CONEX_AddDenseLMIConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _C.c_int, _dp,
-                                             _C.c_int, _C.c_int]
-_lib.CONEX_AddSparseLMIConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _C.c_int, _dp,
-                                              _C.c_int, _C.c_int, _C.POINTER(_C.c_long), _C.c_int]
-_lib.CONEX_Maximize.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.POINTER(CONEX_SolverConfiguration), _dp,
-                                _C.c_int]
-_lib.CONEX_GetDualVariable.argtypes = [_C.c_void_p, _C.c_int, _dp, _C.c_int, _C.c_int]
-_lib.CONEX_GetDualVariableSize.argtypes = [_C.c_void_p, _C.c_int]
-_lib.CONEX_SetDefaultOptions.argtypes = [_C.POINTER(CONEX_SolverConfiguration)]
-_lib.CONEX_GetIterationStats.argtypes = [_C.c_void_p, _C.POINTER(CONEX_IterationStats), _C.c_int]
+def bind_conex_abi(lib):
+    """Declares the argument types of the CONEX_* entry points (include/conex.h) on `lib` — the product,
+    or any other library that speaks the same C ABI (the test-suite drives the CPU oracle through this
+    very class that way)."""
+    lib.CONEX_CreateConeProgram.restype = _C.c_void_p
+    lib.CONEX_DeleteConeProgram.argtypes = [_C.c_void_p]
+    lib.CONEX_SetNumberOfVariables.argtypes = [_C.c_void_p, _C.c_int]
+    lib.CONEX_AddDenseLMIConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _C.c_int, _dp,
+                                                 _C.c_int, _C.c_int]
+    lib.CONEX_AddSparseLMIConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _C.c_int, _dp,
+                                                  _C.c_int, _C.c_int, _C.POINTER(_C.c_long), _C.c_int]
+    lib.CONEX_Maximize.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.POINTER(CONEX_SolverConfiguration), _dp,
+                                    _C.c_int]
+    lib.CONEX_GetDualVariable.argtypes = [_C.c_void_p, _C.c_int, _dp, _C.c_int, _C.c_int]
+    lib.CONEX_GetDualVariableSize.argtypes = [_C.c_void_p, _C.c_int]
+    lib.CONEX_SetDefaultOptions.argtypes = [_C.POINTER(CONEX_SolverConfiguration)]
+    lib.CONEX_GetIterationStats.argtypes = [_C.c_void_p, _C.POINTER(CONEX_IterationStats), _C.c_int]
+    _ip = _C.POINTER(_C.c_int)
+    lib.CONEX_AddDenseLinearConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _dp, _C.c_int]
+    lib.CONEX_AddLinearInequalities.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _dp, _C.c_int, _dp, _C.c_int]
+    lib.CONEX_NewLinearMatrixInequality.argtypes = [_C.c_void_p, _C.c_int, _C.c_int, _ip]
+    lib.CONEX_NewLorentzConeConstraint.argtypes = [_C.c_void_p, _C.c_int, _ip]
+    lib.CONEX_NewLinearInequality.argtypes = [_C.c_void_p, _C.c_int, _ip]
+    lib.CONEX_UpdateLinearOperator.argtypes = [_C.c_void_p, _C.c_int, _C.c_double, _C.c_int, _C.c_int, _C.c_int,
+                                                _C.c_int]
+    lib.CONEX_UpdateAffineTerm.argtypes = [_C.c_void_p, _C.c_int, _C.c_double, _C.c_int, _C.c_int, _C.c_int]
+    return lib
+
+
 _ip = _C.POINTER(_C.c_int)
-_lib.CONEX_AddDenseLinearConstraint.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _dp, _C.c_int]
-_lib.CONEX_AddLinearInequalities.argtypes = [_C.c_void_p, _dp, _C.c_int, _C.c_int, _dp, _C.c_int, _dp, _C.c_int]
-_lib.CONEX_NewLinearMatrixInequality.argtypes = [_C.c_void_p, _C.c_int, _C.c_int, _ip]
-_lib.CONEX_NewLorentzConeConstraint.argtypes = [_C.c_void_p, _C.c_int, _ip]
-_lib.CONEX_NewLinearInequality.argtypes = [_C.c_void_p, _C.c_int, _ip]
-_lib.CONEX_UpdateLinearOperator.argtypes = [_C.c_void_p, _C.c_int, _C.c_double, _C.c_int, _C.c_int, _C.c_int,
-                                            _C.c_int]
-_lib.CONEX_UpdateAffineTerm.argtypes = [_C.c_void_p, _C.c_int, _C.c_double, _C.c_int, _C.c_int, _C.c_int]
+bind_conex_abi(_lib)
 _lib.CONEXB200_CreateBatch.restype = _C.c_void_p
 _lib.CONEXB200_CreateBatch.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int]
 _lib.CONEXB200_DeleteBatch.argtypes = [_C.c_void_p]
@@ -82,6 +91,16 @@ def device_available():
     return bool(_lib.CONEXB200_DeviceAvailable())
 
 
+class Errors:
+    """interfaces/python/ConexProgram.py `Errors`."""
+
+    def __init__(self):
+        self.Ax_minus_b = 0.0
+        self.x_dot_s = 0.0
+        self.min_eig_S = []
+        self.min_eig_X = []
+
+
 class Solution:
     def __init__(self):
         self.y = None
@@ -95,25 +114,28 @@ def _ptr(a):
 class Conex:
     """Mirror of the reference's `Conex` class for the dense-LMI hot path."""
 
-    def __init__(self, m=-1):
-        self.a = _C.c_void_p(_lib.CONEX_CreateConeProgram())
+    def __init__(self, m=-1, library=None):
+        # `library`: a ctypes library speaking the CONEX_* ABI (bind_conex_abi); default: the product
+        self._lib = library if library is not None else _lib
+        self.a = _C.c_void_p(self._lib.CONEX_CreateConeProgram())
         if not self.a:
             raise NameError("Failed to create program (is a B200 visible?).")
         if m >= 0:
-            _lib.CONEX_SetNumberOfVariables(self.a, m)
+            self._lib.CONEX_SetNumberOfVariables(self.a, m)
         self.num_constraints = 0
         self.A = []
+        self.variables = []  # per constraint: the variables its operator acts on (None: built entry by entry)
         self.c = []
         self.m = m
 
     def __del__(self):
-        if getattr(self, "a", None):
-            _lib.CONEX_DeleteConeProgram(self.a)
+        if getattr(self, "a", None) and getattr(self, "_lib", None) is not None:
+            self._lib.CONEX_DeleteConeProgram(self.a)
 
     def DefaultConfiguration(self):
         # interfaces/python/ConexProgram.py:115-126
         config = CONEX_SolverConfiguration()
-        _lib.CONEX_SetDefaultOptions(_C.byref(config))
+        self._lib.CONEX_SetDefaultOptions(_C.byref(config))
         config.inv_sqrt_mu_max = 1000
         config.maximum_mu = 1e20
         config.max_iterations = 100
@@ -133,17 +155,19 @@ class Conex:
         self.n, self.m = n, m
         self.A.append(A)
         self.c.append(cf)
-        _lib.CONEX_AddDenseLMIConstraint(self.a, _ptr(packed), n, n, m, _ptr(cf), n, n)
+        self.variables.append(_np.arange(m))
+        self._lib.CONEX_AddDenseLMIConstraint(self.a, _ptr(packed), n, n, m, _ptr(cf), n, n)
         self.num_constraints += 1
 
     def AddLinearInequality(self, A, c):
         """c - A y >= 0 (interfaces/python/ConexProgram.py:98-105)."""
         Af = _np.asfortranarray(_np.asarray(A, dtype=_np.float64))
         cf = _np.ascontiguousarray(_np.asarray(c, dtype=_np.float64).ravel())
-        _lib.CONEX_AddDenseLinearConstraint(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(cf), cf.shape[0])
+        self._lib.CONEX_AddDenseLinearConstraint(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(cf), cf.shape[0])
         self.m, self.n = Af.shape[1], Af.shape[0]
         self.A.append(Af)
         self.c.append(cf.reshape(-1, 1))
+        self.variables.append(_np.arange(Af.shape[1]))
         self.num_constraints += 1
 
     def AddLinearInequalities(self, A, lb, ub):
@@ -151,10 +175,11 @@ class Conex:
         Af = _np.asfortranarray(_np.asarray(A, dtype=_np.float64))
         lbf = _np.ascontiguousarray(_np.asarray(lb, dtype=_np.float64).ravel())
         ubf = _np.ascontiguousarray(_np.asarray(ub, dtype=_np.float64).ravel())
-        _lib.CONEX_AddLinearInequalities(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(lbf), lbf.shape[0],
+        self._lib.CONEX_AddLinearInequalities(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(lbf), lbf.shape[0],
                                          _ptr(ubf), ubf.shape[0])
         self.A.append(Af)
         self.c.append(ubf.reshape(-1, 1))
+        self.variables.append(_np.arange(Af.shape[1]))
         self.num_constraints += 1
 
     def _new(self, fn, *args):
@@ -165,27 +190,33 @@ class Conex:
         return cid.value
 
     def NewLinearMatrixInequality(self, order, hyper_complex_dim):
-        cid = self._new(_lib.CONEX_NewLinearMatrixInequality, order, hyper_complex_dim)
+        cid = self._new(self._lib.CONEX_NewLinearMatrixInequality, order, hyper_complex_dim)
         self.c.append(_np.zeros((order, order)))
+        self.A.append(None)
+        self.variables.append(None)
         return cid
 
     def NewLorentzConeConstraint(self, order):
-        cid = self._new(_lib.CONEX_NewLorentzConeConstraint, order)
+        cid = self._new(self._lib.CONEX_NewLorentzConeConstraint, order)
         self.c.append(_np.zeros((order + 1, 1)))
+        self.A.append(None)
+        self.variables.append(None)
         return cid
 
     def NewLinearInequality(self, num_rows):
-        cid = self._new(_lib.CONEX_NewLinearInequality, num_rows)
+        cid = self._new(self._lib.CONEX_NewLinearInequality, num_rows)
         self.c.append(_np.zeros((num_rows, 1)))
+        self.A.append(None)
+        self.variables.append(None)
         return cid
 
     def UpdateLinearOperator(self, constraint, value, variable, row, col=0, hyper_complex_dim=0):
-        if _lib.CONEX_UpdateLinearOperator(self.a, constraint, float(value), variable, row, col,
+        if self._lib.CONEX_UpdateLinearOperator(self.a, constraint, float(value), variable, row, col,
                                            hyper_complex_dim) != 0:
             raise NameError("Failed to update operator.")
 
     def UpdateAffineTerm(self, constraint, value, row, col=0, hyper_complex_dim=0):
-        if _lib.CONEX_UpdateAffineTerm(self.a, constraint, float(value), row, col, hyper_complex_dim) != 0:
+        if self._lib.CONEX_UpdateAffineTerm(self.a, constraint, float(value), row, col, hyper_complex_dim) != 0:
             raise NameError("Failed to update affine term.")
 
     def AddSparseLinearMatrixInequality(self, A, c, variables):
@@ -199,7 +230,8 @@ class Conex:
         v = (_C.c_long * k)(*[int(x) for x in variables])
         self.A.append(A)
         self.c.append(cf)
-        _lib.CONEX_AddSparseLMIConstraint(self.a, _ptr(packed), n, n, k, _ptr(cf), n, n, v, k)
+        self.variables.append(_np.array([int(x) for x in variables]))
+        self._lib.CONEX_AddSparseLMIConstraint(self.a, _ptr(packed), n, n, k, _ptr(cf), n, n, v, k)
         self.num_constraints += 1
 
     # ---- conex-b200 extensions (include/conex_b200.h) ----
@@ -225,7 +257,7 @@ class Conex:
             raise NameError("Cost vector dimension does not match number of variables.")
         sol = Solution()
         sol.y = _np.ones(self.m)
-        sol.status = _lib.CONEX_Maximize(self.a, _ptr(b), self.m, _C.byref(config), _ptr(sol.y), self.m)
+        sol.status = self._lib.CONEX_Maximize(self.a, _ptr(b), self.m, _C.byref(config), _ptr(sol.y), self.m)
         return sol
 
     def GetDualVariables(self):
@@ -233,13 +265,43 @@ class Conex:
         for i in range(self.num_constraints):
             r, c = self.c[i].shape[0], self.c[i].shape[1]
             xi = _np.zeros(r * c)
-            _lib.CONEX_GetDualVariable(self.a, i, _ptr(xi), r, c)
+            self._lib.CONEX_GetDualVariable(self.a, i, _ptr(xi), r, c)
             x.append(xi.reshape((r, c), order="F"))
         return x
 
+    def ComputeErrors(self, y, xa, b):
+        """interfaces/python/ConexProgram.py:243-277: slacks c_i - A_i y of every constraint and the
+        residuals |b - sum_i A_i' x_i|, sum_i <x_i, s_i>, smallest eigenvalues of s_i and x_i."""
+        y = _np.asarray(y, dtype=_np.float64).ravel()
+        b = _np.asarray(b, dtype=_np.float64).ravel()
+        err = Errors()
+        slacks = []
+        Ax = _np.zeros(self.m)
+        for i in range(self.num_constraints):
+            if self.A[i] is None:
+                raise NameError("ComputeErrors needs the operator: constraint %d was built entry by entry." % i)
+            A, c = self.A[i], _np.asarray(self.c[i], dtype=_np.float64)
+            variables = self.variables[i]
+            x = _np.asarray(xa[i], dtype=_np.float64)
+            if A.ndim == 3:   # LMI: A[:, :, k] is the matrix of variable variables[k]
+                s = c - _np.tensordot(A, y[variables], axes=([2], [0]))
+                Ax[variables] += _np.tensordot(A, x, axes=([0, 1], [0, 1]))
+                err.x_dot_s += float(_np.trace(s @ x))
+                err.min_eig_S.append(float(_np.linalg.eigvalsh(0.5 * (s + s.T)).min()))
+                err.min_eig_X.append(float(_np.linalg.eigvalsh(0.5 * (x + x.T)).min()))
+            else:             # linear inequality: rows x variables
+                s = c.ravel() - A @ y[variables]
+                Ax[variables] += A.T @ x.ravel()
+                err.x_dot_s += float(s @ x.ravel())
+                err.min_eig_S.append(float(s.min()))
+                err.min_eig_X.append(float(x.min()))
+            slacks.append(s)
+        err.Ax_minus_b = float(_np.linalg.norm(b - Ax))
+        return slacks, err
+
     def GetIterationNumberStats(self, num):
         stats = CONEX_IterationStats()
-        _lib.CONEX_GetIterationStats(self.a, _C.byref(stats), num)
+        self._lib.CONEX_GetIterationStats(self.a, _C.byref(stats), num)
         return stats
 
     def GetIterationStats(self):
