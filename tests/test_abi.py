@@ -144,3 +144,19 @@ def test_python_front_end_imports():
     assert os.path.exists(conex_b200.LIBRARY_PATH)
     assert hasattr(conex_b200.Conex, "AddDenseLinearMatrixInequality")
     assert hasattr(conex_b200.Conex, "Maximize")
+
+
+def test_plain_c_caller_compiles_links_and_runs(tmp_path):
+    """include/conex.h is plain C (MATLAB loadlibrary, SWIG) and every symbol a C caller uses resolves
+    against libconex_b200.so; the program solves when a device is present and is refused cleanly when
+    none is (reference: interfaces/test/test_app.cc, interfaces/Makefile:51-52)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "conex_b200", "lib")
+    exe = str(tmp_path / "c_caller")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "capp", "c_caller.c"), "-o", exe, "-L", libdir,
+                           "-lconex_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "solved" in out.stdout or "no device" in out.stdout
