@@ -308,3 +308,17 @@ def test_taylor_exponential_and_hermitian_lanczos(n):
     k = L.ORACLE_HermitianLanczos(n, dptr(WS), dptr(W), dptr(r), n, dptr(ritz))
     ev = np.sort(np.linalg.eigvals(WS).real)
     assert k == n and np.abs(np.sort(ritz[:k]) - ev).max() < 1e-8 * max(1.0, np.abs(ev).max())
+
+
+def test_known_bad_instance_equality_constraint_failing_ldlt():
+    """conex/test/solver_failures.cc:12-46 (`EqualityConstraintFailingLDLT`): x0 = x1, x0 + x1 <= 1,
+    maximise x0 + x1. The KKT matrix [[1, 1, 1], [1, 1, -1], [1, -1, 0]] has a singular leading block —
+    the reference lists it as a case its factorisation fails on; with the +-1e-9 pivot regularisation
+    restated from RLDLT.h:378-389 the program solves to (1/2, 1/2)."""
+    O = oracle()
+    P = O.program(2)
+    P.add_equality(np.array([[1.0, -1.0]]), np.array([0.0]), [0, 1])
+    P.add_linear(np.array([[1.0, 1.0]]), np.array([1.0]))
+    solved, y = P.maximize(np.array([1.0, 1.0]), O.default_config())
+    assert solved == 1
+    assert np.abs(y - 0.5).max() < 1e-5 and abs(y[0] - y[1]) < 1e-9

@@ -179,3 +179,20 @@ def test12_random_socp(Conex):  # run_tests.py:23-34, 348-356
         b[v] = col[0]
     prog.UpdateAffineTerm(con, 1.0, 0, 0, 0)
     assert prog.Maximize(b).status
+
+
+@pytest.mark.gpu
+def test_known_bad_instance_equality_constraint_failing_ldlt_on_the_device():
+    """conex/test/solver_failures.cc:12-46 (see tests/test_oracle_cones.py): the regularised LDL^T of the
+    device meets a singular leading block; same answer as the oracle."""
+    import devlib
+    from harness import oracle
+    res = []
+    for L in (oracle(), devlib.product()):
+        P = L.program(2)
+        P.add_equality(np.array([[1.0, -1.0]]), np.array([0.0]), [0, 1])
+        P.add_linear(np.array([[1.0, 1.0]]), np.array([1.0]))
+        res.append(P.maximize(np.array([1.0, 1.0]), L.default_config()))
+    (so, yo), (sd, yd) = res
+    assert so == sd == 1
+    assert np.abs(yd - yo).max() < 1e-5 and abs(yd[0] - yd[1]) < 1e-8
