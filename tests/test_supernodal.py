@@ -32,6 +32,16 @@ REFERENCE_PATTERNS = [
     # not chordal as given (a 4-cycle of pairwise overlaps): needs fill
     [[0, 1], [1, 2], [2, 3], [3, 0]],
     [[0, 1, 2], [2, 3, 4], [4, 5, 0], [1, 3, 5]],
+    # clique_ordering_test.cc:76-127: PerfectEliminationOrderFound (two forests with unused indices),
+    # SmallSize, ...Diagonal (five singletons), FillIn (the 4-cycle again, as the reference orders it),
+    # Nonmaximal (nested cliques)
+    [[1, 2, 3, 5], [3, 4, 5], [4, 5, 6, 7], [8, 9], [1, 11]],
+    [[0, 2, 3, 5], [3, 4, 5], [4, 5, 6, 7], [0, 11]],
+    [[0, 1]],
+    [[0, 1], [1, 2]],
+    [[1], [2], [3], [4], [5]],
+    [[0, 1], [1, 2], [0, 3], [2, 3]],
+    [[0, 1], [0, 1, 2], [0, 1, 2, 3, 4]],
 ]
 
 
@@ -139,7 +149,9 @@ def test_reference_clique_patterns(idx):
     position, node_of, supers, seps, flops = analysis(N, cliques)
     check_structure(N, cliques, position, node_of, supers, seps)
     rng = np.random.default_rng(idx)
-    H = pattern_matrix(N, cliques, rng)
+    # indices that no clique mentions (the reference's patterns skip some) get a diagonal entry only
+    used = set(v for c in cliques for v in c)
+    H = pattern_matrix(N, cliques + [[v] for v in range(N) if v not in used], rng)
     b = rng.standard_normal(N)
     x = multifrontal_solve(H, b, position, supers, seps)
     assert np.abs(x - np.linalg.solve(H, b)).max() < 1e-11 * max(1.0, np.abs(x).max())
@@ -240,7 +252,7 @@ def solve_with(L, m, cones, kind=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", ["arrow", "chain", "chain_long", "disconnected", "lp_chain"])
+@pytest.mark.parametrize("shape", ["arrow", "chain", "chain_long", "disconnected", "lp_chain", "cycle_fill_in"])
 def test_sparse_programs_match_oracle_and_dense_solver(shape):
     import devlib
     dev, ora = devlib.product(), oracle()
@@ -253,6 +265,13 @@ def test_sparse_programs_match_oracle_and_dense_solver(shape):
     elif shape == "lp_chain":
         m, cones = lp_chain_program()
         assert m == 201
+    elif shape == "cycle_fill_in":
+        # test_lp.cc:232-309 (`LP SparseWithFillIn`): cliques {0,1}, {1,2}, {2,3}, {0,3} — a 4-cycle, which
+        # is not chordal: the symbolic step has to add fill. LMI cones of order 4 on those pairs.
+        rng = np.random.default_rng(5)
+        m, cones = 4, []
+        for variables in ([0, 1], [1, 2], [2, 3], [0, 3]):
+            cones.append(([random_sym(rng, 4) for _ in variables], np.eye(4), variables))
     else:
         m, cones = chain_program(links=3, width=4, overlap=0, order=5, seed=4)
     Po, so, yo, bo, _ = solve_with(ora, m, cones)
