@@ -330,3 +330,22 @@ def test_rounding_sensitivity_of_final_objectives(O):
     assert abs(len(logs[0]) - len(logs[1])) <= 1
     assert abs(a["by"] - c["by"]) <= 1e-9 * abs(a["by"])
     assert abs(a["cx"] - c["cx"]) <= 1e-6 * abs(a["cx"])
+
+
+def test_warmstart_from_converged_iterate_returns_the_same_point(O):
+    """conex/test/test_warmstart.cc:47-79 (`TestWorkspaceInitialization`): after a full solve of an
+    LMI (n = 15, m = 13) + LP program, a warm start limited to two iterations returns the same y (1e-9).
+    (The reference hands the old arena to a second Program object; through the C ABI the same handle is
+    solved again with initialization_mode = 1 — the iterate lives in the arena either way.)"""
+    mats, Cm = random_dense_lmi(15, 13, 3)
+    rng = np.random.default_rng(4)
+    A, c = rng.uniform(-1, 1, size=(15, 13)), np.ones(15)
+    P = O.program(13)
+    P.add_dense_lmi(mats, Cm)
+    P.add_linear(A, c)
+    b = P.feasible_objective()
+    kw = dict(final_centering_steps=3, final_centering_tolerance=.01)
+    solved, y = P.maximize(b, O.default_config(**kw))
+    solved_w, y_warm = P.maximize(b, O.default_config(initialization_mode=1, max_iterations=2, **kw))
+    assert solved == 1 and solved_w == 1
+    assert np.linalg.norm(y - y_warm) < 1e-9

@@ -196,3 +196,24 @@ def test_known_bad_instance_equality_constraint_failing_ldlt_on_the_device():
     (so, yo), (sd, yd) = res
     assert so == sd == 1
     assert np.abs(yd - yo).max() < 1e-5 and abs(yd[0] - yd[1]) < 1e-8
+
+
+@pytest.mark.gpu
+def test_warmstart_from_converged_iterate_returns_the_same_point_on_the_device():
+    """conex/test/test_warmstart.cc:47-79 (see tests/test_oracle_golden.py): LMI + LP, full solve, then a
+    two-iteration warm start from the device-resident arena."""
+    import devlib
+    from harness import random_dense_lmi
+    L = devlib.product()
+    mats, Cm = random_dense_lmi(15, 13, 3)
+    rng = np.random.default_rng(4)
+    A, c = rng.uniform(-1, 1, size=(15, 13)), np.ones(15)
+    P = L.program(13)
+    P.add_dense_lmi(mats, Cm)
+    P.add_linear(A, c)
+    b = P.feasible_objective()
+    kw = dict(final_centering_steps=3, final_centering_tolerance=.01)
+    solved, y = P.maximize(b, L.default_config(**kw))
+    solved_w, y_warm = P.maximize(b, L.default_config(initialization_mode=1, max_iterations=2, **kw))
+    assert solved == 1 and solved_w == 1
+    assert np.linalg.norm(y - y_warm) < 1e-8
