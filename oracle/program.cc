@@ -137,19 +137,42 @@ bool Program::Factor() {
   // conex/kkt_solver.cc:172-199: Cholesky unless some cone carries multipliers, then the
   // regularised LDL^T, which never reports failure.
   const int N = SizeOfKKTSystem();
+  if (iterative_refinement_iterations_ > 0) kkt_matrix_ = H;  // kkt_solver.cc:174-178 (lower triangle)
   if (num_dual_ == 0) return CholeskyLower(N, H.data(), N);
   LdltLower(N, H.data(), N, &transpositions_);
   return true;
 }
 
 void Program::SolveInPlace(double* rhs) const {
-  // conex/kkt_solver.cc:220-246 for one dense supernode (identity permutation).
+  // conex/kkt_solver.cc:220-263 for one dense supernode (identity permutation).
   const int N = SizeOfKKTSystem();
-  if (num_dual_ == 0) {
-    SolveLower(N, H.data(), N, rhs, false);
-    SolveLower(N, H.data(), N, rhs, true);
-  } else {
-    SolveLdlt(N, H.data(), N, transpositions_, rhs);
+  auto solve_once = [&](double* v) {
+    if (num_dual_ == 0) {
+      SolveLower(N, H.data(), N, v, false);
+      SolveLower(N, H.data(), N, v, true);
+    } else {
+      SolveLdlt(N, H.data(), N, transpositions_, v);
+    }
+  };
+  if (iterative_refinement_iterations_ <= 0) {
+    solve_once(rhs);
+    return;
+  }
+  const std::vector<double> total_residual(rhs, rhs + N);
+  solve_once(rhs);
+  std::vector<double> r(N);
+  for (int it = 0; it < iterative_refinement_iterations_; it++) {
+    // residual = total_residual - K y with K given by its lower triangle (kkt_solver.cc:250-251)
+    for (int i = 0; i < N; i++) {
+      double s = 0;
+      for (int j = 0; j < N; j++) {
+        const double kij = (i >= j) ? kkt_matrix_[(size_t)j * N + i] : kkt_matrix_[(size_t)i * N + j];
+        s += kij * rhs[j];
+      }
+      r[i] = total_residual[i] - s;
+    }
+    solve_once(r.data());
+    for (int i = 0; i < N; i++) rhs[i] += r[i];
   }
 }
 
@@ -199,6 +222,7 @@ std::vector<double> Program::FeasibleObjective() {
 }
 
 bool Program::Maximize(const double* b_in, const SolverConfiguration& config, double* yout) {
+  iterative_refinement_iterations_ = config.iterative_refinement_iterations;  // cone_program.cc:303-304
   const int mv = m_;                  // variables the caller sees
   const int m = SizeOfKKTSystem();    // + multipliers of the equality constraints
   status = Status();

@@ -100,6 +100,10 @@ class Program {
   int m_;
   int num_dual_ = 0;
   std::vector<int> transpositions_;  // RLDLT pivots (LDLT mode: any equality present)
+  // conex/kkt_solver.cc:174-178,229-261: with iterative refinement the assembled matrix is kept
+  // and every solve is followed by `iterative_refinement_iterations_` correction solves.
+  int iterative_refinement_iterations_ = 0;
+  std::vector<double> kkt_matrix_;
   std::vector<std::unique_ptr<Cone>> cones_;
   std::vector<std::vector<int>> cliques_;
   std::vector<SchurSystem> cone_sys_;

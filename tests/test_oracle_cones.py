@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from harness import dptr, oracle
+from harness import random_dense_lmi, dptr, oracle
 
 c_int_p = C.POINTER(C.c_int)
 
@@ -185,6 +185,48 @@ def test_rldlt_regularises_zero_pivot():
     ok = O.lib.ORACLE_LdltLower(3, dptr(M), tr)
     assert ok == 0
     assert sorted(np.diag(M).tolist()) == [-1e-9, 1e-9, 2.0]
+
+
+@pytest.mark.parametrize("mode,refine", [(0, 0), (0, 3), (1, 0)])
+@pytest.mark.parametrize("i", range(3))
+def test_kkt_solver_options(i, mode, refine):
+    """kkt_solver_options_test.cc:70-88 (`UseLLT`, `UseIterativeRefinement` with 3 correction solves —
+    kkt_solver.cc:174-178,248-261 —, `LP UseLDLT`): the LP properties of :26-66 hold under every option.
+    (LLT and LDLT modes take the same branch in the reference: Cholesky unless multipliers exist,
+    kkt_solver.cc:180-193. The QR mode is outside the hot path.)"""
+    O = oracle()
+    rng = np.random.Generator(np.random.PCG64(170 + i))
+    nv, nc = 5, 6 + 2 * i
+    A = rng.uniform(-1, 1, size=(nc, nv))
+    Cv = np.abs(rng.uniform(-1, 1, size=nc))
+    x0 = np.abs(rng.uniform(-1, 1, size=nc))
+    x0 *= 0.01 / np.linalg.norm(x0)
+    b = A.T @ x0
+    cfg = O.default_config(prepare_dual_variables=1, inv_sqrt_mu_max=5e5, divergence_upper_bound=1000,
+                           dinf_upper_bound=1.35, final_centering_tolerance=1, kkt_solver=mode,
+                           iterative_refinement_iterations=refine)
+    P = O.program()
+    P.add_linear(A, Cv)
+    solved, y = P.maximize(b, cfg)
+    x = P.dual_variable(0).ravel()
+    slack = Cv - A @ y
+    assert solved == 1
+    assert np.linalg.norm(A.T @ x - b) <= 1e-11 * np.linalg.norm(b)
+    assert slack.min() >= -1e-12 and x.min() >= -1e-12 and slack @ x >= -1e-12
+    assert slack @ x <= (1.0 / 5e5 ** 2 + 1e-6) * nc
+
+
+def test_iterative_refinement_changes_nothing_on_a_well_conditioned_lmi():
+    O = oracle()
+    mats, Cm = random_dense_lmi(12, 7, 9)
+    ys = []
+    for refine in (0, 2):
+        P = O.program()
+        P.add_dense_lmi(mats, Cm)
+        solved, y = P.maximize(P.feasible_objective(), O.default_config(iterative_refinement_iterations=refine))
+        assert solved == 1
+        ys.append(y)
+    assert np.abs(ys[0] - ys[1]).max() < 1e-9
 
 
 @pytest.mark.parametrize("i", range(4))

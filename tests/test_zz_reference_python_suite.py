@@ -217,3 +217,38 @@ def test_warmstart_from_converged_iterate_returns_the_same_point_on_the_device()
     solved_w, y_warm = P.maximize(b, L.default_config(initialization_mode=1, max_iterations=2, **kw))
     assert solved == 1 and solved_w == 1
     assert np.linalg.norm(y - y_warm) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["lp", "lmi"])
+def test_iterative_refinement_on_the_device_matches_the_oracle(kind):
+    """kkt_solver_options_test.cc:70-75 (`UseIterativeRefinement`, 3 correction solves per solve,
+    kkt_solver.cc:248-261): same y as the oracle's restatement, and the LP properties hold."""
+    import devlib
+    from harness import oracle, random_dense_lmi
+    rng = np.random.Generator(np.random.PCG64(171))
+    res = []
+    for L in (oracle(), devlib.product()):
+        P = L.program()
+        if kind == "lp":
+            A = np.random.Generator(np.random.PCG64(171)).uniform(-1, 1, size=(8, 5))
+            Cv = np.abs(np.random.Generator(np.random.PCG64(172)).uniform(-1, 1, size=8))
+            P.add_linear(A, Cv)
+            x0 = np.abs(np.random.Generator(np.random.PCG64(173)).uniform(-1, 1, size=8))
+            b = A.T @ (x0 * 0.01 / np.linalg.norm(x0))
+            cfg = L.default_config(prepare_dual_variables=1, inv_sqrt_mu_max=5e5, divergence_upper_bound=1000,
+                                   dinf_upper_bound=1.35, final_centering_tolerance=1,
+                                   iterative_refinement_iterations=3)
+        else:
+            mats, Cm = random_dense_lmi(12, 7, 9)
+            P.add_dense_lmi(mats, Cm)
+            b = P.feasible_objective()
+            cfg = L.default_config(prepare_dual_variables=1, iterative_refinement_iterations=3)
+        solved, y = P.maximize(b, cfg)
+        res.append((solved, y, P))
+    (so, yo, Po), (sd, yd, Pd) = res
+    assert so == sd == 1
+    assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+    if kind == "lp":
+        x = Pd.dual_variable(0).ravel()
+        assert np.linalg.norm(A.T @ x - b) <= 1e-9 * np.linalg.norm(b) and x.min() >= -1e-12
