@@ -364,3 +364,16 @@ def test_known_bad_instance_equality_constraint_failing_ldlt():
     solved, y = P.maximize(np.array([1.0, 1.0]), O.default_config())
     assert solved == 1
     assert np.abs(y - 0.5).max() < 1e-5 and abs(y[0] - y[1]) < 1e-9
+
+
+def test_taylor_exponential_reference_known_answer():
+    """conex/test/exponential_map_test.cc:31-48: ExponentialMap of A * 0.001, A the 4 x 4 matrix of the
+    Pade test, against the true exponential at 1e-7."""
+    import scipy.linalg as sla
+    L = oracle().lib
+    L.ORACLE_TaylorExpm.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    A = np.array([[3, 1, 0, 1], [1, 3, 1, 0], [0, 1, 4, 1], [1, 0, 1, 5]], dtype=np.float64) * .001
+    X = np.asfortranarray(A)
+    out = np.zeros((4, 4), order="F")
+    L.ORACLE_TaylorExpm(4, dptr(X), dptr(out))
+    assert np.abs(out - sla.expm(A)).max() < 1e-7
