@@ -349,3 +349,32 @@ def test_warmstart_from_converged_iterate_returns_the_same_point(O):
     solved_w, y_warm = P.maximize(b, O.default_config(initialization_mode=1, max_iterations=2, **kw))
     assert solved == 1 and solved_w == 1
     assert np.linalg.norm(y - y_warm) < 1e-9
+
+
+def test_variables_specified_out_of_order(O):
+    """conex/test/assembly_test.cc:196-219 (`VariablesSpecifiedOutOfOrder`): a cone's variable list need
+    not be sorted — local index a acts on variables[a]. Here: the same two-cone program given with
+    unsorted lists and with the lists (and the matrices) sorted must have the same Newton system and y."""
+    rng = np.random.default_rng(8)
+    n, m = 5, 4
+    cones = []
+    for variables in ([1, 0, 3], [1, 0, 2]):
+        cones.append(([random_sym(rng, n) for _ in variables], np.eye(n), variables))
+    results = []
+    for sort in (False, True):
+        P = O.program(m)
+        for mats, Cm, variables in cones:
+            if sort:
+                order = np.argsort(variables)
+                P.add_dense_lmi([mats[i] for i in order], Cm, [variables[i] for i in order])
+            else:
+                P.add_dense_lmi(mats, Cm, variables)
+        H = P.newton_system(coldstart=True)[0]
+        b = P.feasible_objective()
+        solved, y = P.maximize(b, O.default_config())
+        results.append((np.tril(H), b, solved, y))
+    (H0, b0, s0, y0), (H1, b1, s1, y1) = results
+    assert s0 == s1 == 1
+    assert np.abs(H0 - H1).max() < 1e-13 and np.abs(b0 - b1).max() < 1e-14
+    assert H0[3, 2] == 0 and H0[2, 2] != 0 and H0[3, 3] != 0     # variables 2 and 3 never share a cone
+    assert np.abs(y0 - y1).max() < 1e-9

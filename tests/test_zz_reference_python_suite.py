@@ -252,3 +252,33 @@ def test_iterative_refinement_on_the_device_matches_the_oracle(kind):
     if kind == "lp":
         x = Pd.dual_variable(0).ravel()
         assert np.linalg.norm(A.T @ x - b) <= 1e-9 * np.linalg.norm(b) and x.min() >= -1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kkt_kind", [1, 2])
+def test_variables_specified_out_of_order_on_the_device(kkt_kind):
+    """conex/test/assembly_test.cc:196-219 (see tests/test_oracle_golden.py) through the dense and the
+    multifrontal KKT solver of the device."""
+    import devlib
+    from harness import oracle, random_sym
+    rng = np.random.default_rng(8)
+    n, m = 5, 4
+    cones = []
+    for variables in ([1, 0, 3], [1, 0, 2]):
+        cones.append(([random_sym(rng, n) for _ in variables], np.eye(n), variables))
+    res = []
+    for L, kind in ((oracle(), None), (devlib.product(), kkt_kind)):
+        P = L.program(m)
+        if kind is not None:
+            L.lib.CONEXB200_SetKKTSolverKind.argtypes = [C.c_void_p, C.c_int]
+            L.lib.CONEXB200_SetKKTSolverKind.restype = None
+            L.lib.CONEXB200_SetKKTSolverKind(P.h, kind)
+        for mats, Cm, variables in cones:
+            P.add_dense_lmi(mats, Cm, variables)
+        H = P.newton_system(coldstart=True)[0]
+        solved, y = P.maximize(P.feasible_objective(), L.default_config())
+        res.append((np.tril(H), solved, y))
+    (Ho, so, yo), (Hd, sd, yd) = res
+    assert so == sd == 1
+    assert np.abs(Ho - Hd).max() <= 1e-10 * np.abs(Ho).max()
+    assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
