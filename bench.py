@@ -25,6 +25,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: whatever NCCL logs (e.g. its version banner under
+# NCCL_DEBUG=VERSION) goes to a file instead. Must be set before NCCL initialises.
+os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
