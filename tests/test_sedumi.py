@@ -132,6 +132,23 @@ def test_block_diagonal_structure_inside_a_block_is_split():
     assert np.abs(y - y1).max() < 1e-5 and abs(b @ y - b @ y1) < 1e-7 * max(1.0, abs(b @ y1))
 
 
+def test_extract_constraints_reference_fixture():
+    """interfaces/matlab/test/test_extract_constraints.m: K.s = [2; 2], the 3 x 8 matrix given there
+    (entries below 0.5 zeroed): per block, the variables that touch it and their matrices."""
+    from conex_b200 import sedumi
+    A = np.array([[1, 2, 2, 1, 0, 0, 0, 0],
+                  [0, 0, 0, 0, 2, 1, 1, 2],
+                  [1, 3, 3, 1, 2, -3, -3, 2]], dtype=np.float64)
+    A[A < .5] = 0
+    c = np.random.default_rng(0).standard_normal(8)
+    cons = sedumi.extract_constraints(A, c, [2, 2])
+    assert cons[0]["variables"].tolist() == [0, 2] and cons[1]["variables"].tolist() == [1, 2]
+    assert np.array_equal(cons[0]["mats"], [[[1, 2], [2, 1]], [[1, 3], [3, 1]]])
+    assert np.array_equal(cons[1]["mats"], [[[2, 1], [1, 2]], [[2, 0], [0, 2]]])
+    for k, con in enumerate(cons):
+        assert np.array_equal(con["affine"], c[4 * k:4 * k + 4].reshape(2, 2, order="F"))
+
+
 def test_unsupported_cones_are_rejected_like_the_reference():
     from conex_b200 import sedumi
     A, b, c, K = sedumi_problem([3], 2, 5)

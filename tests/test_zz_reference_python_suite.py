@@ -181,6 +181,48 @@ def test12_random_socp(Conex):  # run_tests.py:23-34, 348-356
     assert prog.Maximize(b).status
 
 
+# ---- interfaces/matlab/test/run_conex_tests.m (LPTests, SDPTests, SparseTests) -----------------------
+MATLAB_A = np.stack([np.eye(3), np.array([[1.0, 1, 0], [1, 1, 0], [0, 0, 0]])], axis=2)
+
+
+def test_matlab_lp_tests(Conex):  # run_conex_tests.m:11-44
+    rng = np.random.default_rng(3)
+    A = rng.uniform(0, 1, size=(4, 2))
+    prog = Conex(2)
+    prog.AddLinearInequality(A, np.ones(4))
+    b = A.T @ np.ones(4)
+    assert prog.Maximize(b).status
+    prog = Conex(2)                                   # 1 >= y1, 1 >= y2, -2 >= -y1 ... : infeasible
+    prog.AddLinearInequality(np.array([[1.0, 0], [0, 1], [-1, 0], [0, -1]]), np.array([1.0, 1, -2, 1]))
+    assert prog.Maximize(b).status == 0
+
+
+def test_matlab_sdp_tests(Conex):  # run_conex_tests.m:46-68
+    prog = Conex(2)
+    prog.AddDenseLinearMatrixInequality(MATLAB_A, np.eye(3))
+    sol = prog.Maximize(np.array([1.0, 1.0]))
+    assert sol.status
+    slack = np.eye(3) - sol.y[0] * MATLAB_A[:, :, 0] - sol.y[1] * MATLAB_A[:, :, 1]
+    assert np.linalg.eigvalsh(slack).min() >= -1e-9
+
+
+def test_matlab_sparse_tests(Conex):  # run_conex_tests.m:71-103
+    prog = Conex(3)
+    prog.AddSparseLinearMatrixInequality(MATLAB_A, np.eye(3), [0, 1])
+    prog.AddSparseLinearMatrixInequality(MATLAB_A, np.eye(3), [1, 2])
+    b = np.ones(3)
+    sol = prog.Maximize(b)
+    assert sol.status
+    x = prog.GetDualVariables()
+    for variables in ([0, 1], [1, 2]):
+        slack = np.eye(3) - sum(sol.y[v] * MATLAB_A[:, :, k] for k, v in enumerate(variables))
+        assert np.linalg.eigvalsh(slack).min() >= -1e-9
+    Ax = np.zeros(3)
+    Ax[0:2] += np.tensordot(MATLAB_A, x[0], axes=([0, 1], [0, 1]))
+    Ax[1:3] += np.tensordot(MATLAB_A, x[1], axes=([0, 1], [0, 1]))
+    assert np.linalg.norm(Ax - b) < 1e-8            # the reference asserts 1e-12 on its own run
+
+
 @pytest.mark.gpu
 def test_known_bad_instance_equality_constraint_failing_ldlt_on_the_device():
     """conex/test/solver_failures.cc:12-46 (see tests/test_oracle_cones.py): the regularised LDL^T of the
