@@ -277,12 +277,19 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
   std::unique_ptr<KKTSolver> fresh;
   if (prog.kkt_solver_kind != 1 && prog.NumberOfMultipliers() == 0 && !prog.ctx_.collective) {
     std::vector<std::vector<int>> cliques;
-    for (const auto& c : prog.eqs) cliques.push_back(c.variables);
+    bool some_cone_couples_everything = false;
+    for (const auto& c : prog.eqs) {
+      cliques.push_back(c.variables);
+      some_cone_couples_everything = some_cone_couples_everything || static_cast<int>(c.variables.size()) == N;
+    }
     // The symbolic step depends on the cliques alone: a repeated cold start of the same program keeps
     // the multifrontal solver with its destination lists (hundreds of ms of host work at order 10^4).
     if (prog.solver && prog.solver_is_multifrontal_ && prog.solver_order_ == N &&
         prog.solver_kind_ == prog.kkt_solver_kind && prog.solver_cliques_ == cliques) {
       reused = true;
+    } else if (some_cone_couples_everything && prog.kkt_solver_kind != 2) {
+      // one clique on all the variables (unique indices: VariablesAreUnique): a single dense supernode,
+      // nothing to analyse
     } else {
       SupernodalStructure st = AnalyzeCliques(N, cliques);
       const bool pays = st.supernodes.size() > 1 && N >= 256 && st.factor_flops < 0.5 * st.dense_flops;

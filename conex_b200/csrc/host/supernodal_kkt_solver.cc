@@ -38,11 +38,21 @@ SupernodalStructure AnalyzeCliques(int N, const std::vector<std::vector<int>>& c
   }
 
   // ---- maximum-weight spanning forest of the clique graph (weight = |C_a n C_b|) -----------------
+  // A variable shared by t cliques contributes to t (t - 1) / 2 pairs; beyond kAllPairs cliques only
+  // the t - 1 pairs with the first of them are counted (a star: it still connects every clique that
+  // holds the variable and keeps the tree shallow; any spanning forest yields a valid structure — the
+  // fill step below does not rely on the weights), so that the analysis stays linear in the input when
+  // thousands of cones share variables.
+  constexpr size_t kAllPairs = 64;
   std::map<std::pair<int, int>, int> weight;
   for (int v = 0; v < N; v++) {
     const auto& cs = cliques_of[v];
-    for (size_t i = 0; i < cs.size(); i++) {
-      for (size_t j = i + 1; j < cs.size(); j++) weight[{cs[i], cs[j]}]++;
+    if (cs.size() <= kAllPairs) {
+      for (size_t i = 0; i < cs.size(); i++) {
+        for (size_t j = i + 1; j < cs.size(); j++) weight[{cs[i], cs[j]}]++;
+      }
+    } else {
+      for (size_t i = 1; i < cs.size(); i++) weight[{cs[0], cs[i]}]++;
     }
   }
   struct Edge {

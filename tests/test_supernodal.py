@@ -318,3 +318,23 @@ def test_supernodal_factor_and_solve_against_lapack():
     assert nodes == 3 and solved == solved_d == 1
     assert abs(P.iteration_log()[-1]["by"] - Pd.iteration_log()[-1]["by"]) <= 1e-7 * abs(Pd.iteration_log()[-1]["by"])
     assert np.abs(y - yd).max() <= 1e-6 * max(1.0, np.abs(yd).max())
+
+
+def test_analysis_stays_fast_when_many_cones_share_variables():
+    """400 blocks of 6 private variables, all coupled to the same 5 shared ones: every shared variable
+    sits in 400 cliques (beyond the all-pairs threshold of the clique-graph weights)."""
+    import time
+    blocks, private, shared = 400, 6, 5
+    N = blocks * private + shared
+    cliques = [list(range(k * private, (k + 1) * private)) + list(range(N - shared, N)) for k in range(blocks)]
+    t0 = time.perf_counter()
+    position, node_of, supers, seps, flops = analysis(N, cliques)
+    assert time.perf_counter() - t0 < 5.0
+    check_structure(N, cliques, position, node_of, supers, seps)
+    assert len(supers) == blocks and max(len(p) for p in seps) == shared
+    assert sorted(len(s) for s in supers)[-1] == private + shared             # the root also eliminates the shared ones
+    rng = np.random.default_rng(0)
+    H = pattern_matrix(N, cliques, rng)
+    b = rng.standard_normal(N)
+    x = multifrontal_solve(H, b, position, supers, seps)
+    assert np.abs(x - np.linalg.solve(H, b)).max() < 1e-9 * max(1.0, np.abs(x).max())
