@@ -21,7 +21,7 @@ if [ "$1" == "multi" ]; then
 fi
 timeout 300 python -m pytest tests -m gpu -q > gpurun_out/r2_t_all.log 2>&1
 tail -8 gpurun_out/r2_t_all.log
-bash tools/gpu_sanitize.sh
+bash tools/gpu_sanitize.sh r02
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --csv --launch-skip 4400 -c 2200 \
   --log-file gpurun_out/r2_bench_n2000_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 python tools/launch_summary.py gpurun_out/r2_bench_n2000_launches.csv > gpurun_out/r2_bench_n2000_launches.txt
