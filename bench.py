@@ -30,7 +30,6 @@ import numpy as np
 os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 
 # DRAM traffic of the assembly phase of one C2 Newton step (ncu --set full, see the roofline note)
@@ -231,8 +230,15 @@ def measure_fp64_peak():
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def _oracle_loader():
+    """The CPU oracle (oracle/, test infrastructure) is loaded only by the cpu_baseline / --impl reference legs."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle_loader import oracle
+    return oracle
+
+
 def cpu_problem(kind, n, m):
-    from harness import lovasz_theta_lmi, maxcut_lmi, random_dense_lmi
+    from conex_b200.workloads import lovasz_theta_lmi, maxcut_lmi, random_dense_lmi
     if kind == "maxcut":
         return maxcut_lmi(n, 2)
     if kind == "lovasz":
@@ -253,7 +259,7 @@ def cpu_baseline(w, steps, warmup, threads=None):
     instance of the same workload and extrapolates each phase to the full shape with the work model
     above (the full operators, 64-160 GB, do not fit the host; the as-written Gram alone would take
     tens of minutes per step)."""
-    from harness import oracle
+    oracle = _oracle_loader()
     O = oracle()
     cores = threads or os.cpu_count()
     O.lib.ORACLE_SetBlasThreads(cores)
@@ -314,7 +320,8 @@ def batched_bytes_per_program_step(m=40, n=20, blocks=3):
 def cpu_baseline_batched(w, count=None, threads=1):
     """The oracle port solving a bounded sample of the batch one program after the other (what the
     reference does), single BLAS thread (the matrices are 20 x 20)."""
-    from harness import add_cones, oracle, small_multicone_problem
+    from conex_b200.workloads import add_cones, small_multicone_problem
+    oracle = _oracle_loader()
     O = oracle()
     O.lib.ORACLE_SetBlasThreads(threads)
     count = count or w["cpu"]["programs"]
@@ -339,7 +346,8 @@ def cpu_baseline_batched(w, count=None, threads=1):
 def run_b200_batched(args):
     import torch
     import torch.distributed as dist
-    from harness import Batch, add_cones, small_multicone_problem
+    from conex_b200.binding import Batch
+    from conex_b200.workloads import add_cones, small_multicone_problem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -347,7 +355,7 @@ def run_b200_batched(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import devlib
+    import conex_b200.binding as devlib
     dev = devlib.product()
     L = dev.lib
     assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
@@ -476,7 +484,7 @@ def run_b200_structured(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import devlib
+    import conex_b200.binding as devlib
     dev = devlib.product()
     L = dev.lib
     assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
@@ -596,8 +604,8 @@ def run_b200_sparse(args):
     """Chordal-sparse program through CONEX_AddSparseLMIConstraint / CONEX_Maximize: the device picks the
     multifrontal KKT solver; the dense solver (one supernode of order m) is timed beside it."""
     import torch
-    import devlib
-    from test_supernodal import block_arrow_program
+    import conex_b200.binding as devlib
+    from conex_b200.workloads import block_arrow_program
     dev = devlib.product()
     L = dev.lib
     assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
@@ -685,8 +693,8 @@ def cpu_baseline_sparse(w):
     """The oracle port (dense KKT matrix, like its stand-in for kkt_solver.cc) on a reduced block-arrow
     program; reported per step as measured — no extrapolation (the reference's own solver is
     supernodal, so a dense extrapolation to order 12100 would overstate its cost)."""
-    from harness import oracle
-    from test_supernodal import block_arrow_program
+    oracle = _oracle_loader()
+    from conex_b200.workloads import block_arrow_program
     O = oracle()
     cores = os.cpu_count()
     O.lib.ORACLE_SetBlasThreads(cores)
@@ -775,7 +783,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import devlib
+    import conex_b200.binding as devlib
     dev = devlib.product()
     L = dev.lib
     assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"

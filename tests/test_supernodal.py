@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from harness import PRODUCT_SO, oracle, random_sym
+from harness import PRODUCT_SO, block_arrow_program, oracle, random_sym
 
 REFERENCE_PATTERNS = [
     [[0, 1, 2], [2]],
@@ -195,19 +195,6 @@ def test_chain_and_arrow_structures_save_flops():
 
 
 # ---- device -------------------------------------------------------------------------------------------
-
-def block_arrow_program(blocks, private, shared, order, seed):
-    """`blocks` LMI cones of order `order`, cone k on its own `private` variables plus the same
-    `shared` variables: H is block-arrow."""
-    rng = np.random.default_rng(seed)
-    m = blocks * private + shared
-    cones = []
-    for k in range(blocks):
-        variables = list(range(k * private, (k + 1) * private)) + list(range(blocks * private, m))
-        mats = [random_sym(rng, order) for _ in variables]
-        cones.append((mats, np.eye(order), variables))
-    return m, cones
-
 
 def chain_program(links, width, overlap, order, seed):
     rng = np.random.default_rng(seed)
