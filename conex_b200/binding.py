@@ -266,6 +266,37 @@ class Program:
         self.cone_shapes.append((0, 0))
         return cid
 
+    def dense_lmi_storage(self, n, m, world=1, rank=0):
+        """Library-owned device storage of a dense LMI block (CONEXB200_NewDenseLMIConstraintStorage):
+        returns torch views (no copy) `A` (row_count x n*n, one column-major n x n block per row) and
+        `Cm` (n x n) to be filled in place, and this rank's row range of the m constraint matrices."""
+        from .workloads import device_view
+        L = self.L.lib
+        b, c = C.c_int(), C.c_int()
+        L.CONEXB200_ShardRange(m, world, rank, C.byref(b), C.byref(c))
+        pA, pC = C.c_void_p(), C.c_void_p()
+        cid = L.CONEXB200_NewDenseLMIConstraintStorage(self.h, n, m, C.byref(pA), C.byref(pC))
+        assert cid >= 0, "allocation of the constraint matrices failed"
+        self.m = m
+        self.cone_shapes.append((n, n))
+        A = device_view(pA.value, c.value * n * n).view(c.value, n * n)
+        Cm = device_view(pC.value, n * n).view(n, n)
+        return A, Cm, b.value, c.value
+
+    def add_entry_lmi(self, n, entries, Cmat):
+        """An LMI given entry by entry (CONEX_NewLinearMatrixInequality + CONEX_UpdateLinearOperator /
+        CONEX_UpdateAffineTerm): entries = [(variable, row, col, value)] on the lower triangle."""
+        L = self.L.lib
+        cid = C.c_int(-1)
+        assert L.CONEX_NewLinearMatrixInequality(self.h, n, 1, C.byref(cid)) == 0
+        for (v, r, c, val) in entries:
+            assert L.CONEX_UpdateLinearOperator(self.h, cid.value, float(val), v, r, c, 0) == 0
+        rr, cc = np.nonzero(np.tril(Cmat))
+        for r, c in zip(rr.tolist(), cc.tolist()):
+            assert L.CONEX_UpdateAffineTerm(self.h, cid.value, float(Cmat[r, c]), r, c, 0) == 0
+        self.cone_shapes.append((n, n))
+        return cid.value
+
     def kkt_size(self):
         return self.L.fn("SizeOfKKTSystem")(self.h)
 

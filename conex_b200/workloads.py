@@ -94,3 +94,98 @@ def block_arrow_program(blocks, private, shared, order, seed):
         mats = [random_sym(rng, order) for _ in variables]
         cones.append((mats, np.eye(order), variables))
     return m, cones
+
+
+# ----------------------------------------------------------------------------------------------
+# Device-resident generators for operators that do not fit the host (C2: 64 GB, C5: 160 GB); torch
+# only owns / indexes device memory here.
+# ----------------------------------------------------------------------------------------------
+def lovasz_edges(n, num_edges, seed=4):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    idx = np.sort(rng.choice(n * (n - 1) // 2, size=num_edges, replace=False))
+    # unrank the pair (i < j) from its index in row-major order of the strict upper triangle
+    i = (n - 2 - np.floor(np.sqrt(-8.0 * idx + 4.0 * n * (n - 1) - 7) / 2.0 - 0.5)).astype(np.int64)
+    j = (idx + i + 1 - n * (n - 1) // 2 + (n - i) * ((n - i) - 1) // 2).astype(np.int64)
+    return i, j
+
+
+class _Raw:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2}
+
+
+def device_view(ptr, count):
+    """torch view (no copy) of `count` doubles of library-owned device memory."""
+    import torch
+    return torch.as_tensor(_Raw(ptr, count), device="cuda")
+
+
+def fill_workload(kind, n, m, row_begin, row_count, A, Cm):
+    """Writes this rank's constraint matrices (global indices row_begin .. row_begin+row_count-1) into
+    A (row_count x n*n view, column-major n x n blocks) and the affine term into Cm (n x n), in place
+    on the device; returns the local slice of the cost vector b. Same bytes for any sharding."""
+    import torch
+    idx = torch.arange(row_count, device="cuda")
+    gi = idx + row_begin
+    if kind == "maxcut":  # A_i = -e_i e_i^T, C = -L/4, b = -1 (SURVEY.md 8d, C2)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(2)
+        upper = torch.triu((torch.rand((n, n), generator=g, device="cuda") < 0.5).double(), 1)
+        adj = upper + upper.T
+        Cm.copy_(-(torch.diag(adj.sum(1)) - adj) / 4.0)
+        A.zero_()
+        A[idx, gi * n + gi] = -1.0
+        return -np.ones(row_count)
+    if kind == "random":  # A_i = sym(U[-1,1]), C = I, b = tr(A_i)/2 (test_util.cc:19,67-73; C1/C5)
+        Cm.copy_(torch.eye(n, dtype=torch.float64, device="cuda"))
+        b = torch.empty(row_count, dtype=torch.float64, device="cuda")
+        blk = 32
+        A3 = A.view(row_count, n, n)
+        for g0 in range((row_begin // blk) * blk, row_begin + row_count, blk):
+            g = torch.Generator(device="cuda")
+            g.manual_seed(1000003 + g0)
+            R = torch.rand((blk, n, n), generator=g, device="cuda", dtype=torch.float64) * 2.0 - 1.0
+            R = 0.5 * (R + R.transpose(1, 2))
+            lo, hi = max(g0, row_begin), min(g0 + blk, row_begin + row_count)
+            A3[lo - row_begin:hi - row_begin] = R[lo - g0:hi - g0]
+            b[lo - row_begin:hi - row_begin] = 0.5 * R[lo - g0:hi - g0].diagonal(dim1=1, dim2=2).sum(-1)
+        return b.cpu().numpy()
+    if kind == "lovasz":  # vars (t, y_e): A_0 = -I, A_e = E_ij + E_ji, C = -J, maximise -t (C4)
+        Cm.fill_(-1.0)
+        A.zero_()
+        ei, ej = lovasz_edges(n, m - 1)
+        ei = torch.from_numpy(ei).cuda()
+        ej = torch.from_numpy(ej).cuda()
+        is0 = gi == 0
+        if bool(is0.any()):
+            d = torch.arange(n, device="cuda")
+            A[0, d * n + d] = -1.0
+        e = gi[~is0] - 1
+        rows = idx[~is0]
+        A[rows, ej[e] * n + ei[e]] = 1.0
+        A[rows, ei[e] * n + ej[e]] = 1.0
+        b = np.zeros(row_count)
+        if row_begin == 0:
+            b[0] = -1.0
+        return b
+    raise ValueError(kind)
+
+
+def structured_problem(w):
+    """Entry-sparse form of the MaxCut / Lovasz-theta operators for the incremental API:
+    (list of (var, r, c, val) lower-triangle entries, dense C, b). w: dict(kind, n, m)."""
+    n, m = w["n"], w["m"]
+    if w["kind"] == "maxcut_entries":
+        rng = np.random.Generator(np.random.PCG64(2))
+        upper = np.triu(rng.random((n, n)) < 0.5, 1).astype(np.float64)
+        adj = upper + upper.T
+        Cm = -(np.diag(adj.sum(axis=1)) - adj) / 4.0
+        entries = [(i, i, i, -1.0) for i in range(n)]
+        return entries, Cm, -np.ones(n)
+    ei, ej = lovasz_edges(n, m - 1)
+    entries = [(0, d, d, -1.0) for d in range(n)]
+    entries += [(e + 1, int(max(ei[e], ej[e])), int(min(ei[e], ej[e])), 1.0) for e in range(m - 1)]
+    b = np.zeros(m)
+    b[0] = -1.0
+    return entries, -np.ones((n, n)), b

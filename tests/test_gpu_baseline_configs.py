@@ -1,0 +1,369 @@
+"""Parity at the FULL sizes of the BASELINE.json configurations (the sizes every perf number is quoted on).
+
+The CPU oracle cannot run these shapes (64-160 GB operators, minutes per step), so the checks are
+size-independent properties of the Newton system at the running iterate W, which is read back through
+the public CONEX_GetDualVariable:
+
+* C2 MaxCut n = m = 2000 (A_i = -e_i e_i^T):   H = W o W,  AW_i = -W_ii,  AQc_i = -(W C W)_ii;
+* C4 Lovasz theta n = 500, m = 10001:           H_(ij),(kl) = 2 (W_ik W_jl + W_il W_jk), ...;
+* C5 dense random LMI: H_ij = tr(A_i W A_j W) recomputed by cuBLAS (torch.matmul, FP64) from the
+  device-resident A_i — reduced (n = 500, m = 5000: all entries) and full (n = 1000, m = 20000: sampled);
+* C3: 256 programs of the batch against the oracle, program by program;
+* dense path vs entry-sparse (structured) path vs oracle where the oracle finishes in seconds (n = 400).
+
+Gates (BASELINE.json): Newton-system entries within 1e-10 relative (to sqrt(H_ii H_jj)), objectives within
+1e-7 relative, iteration counts within +-1. Reference tests this mirrors: conex/test/test_sdp.cc:170-208.
+"""
+import gc
+import os
+
+import numpy as np
+import pytest
+
+from harness import Batch, add_cones, fill_workload, maxcut_lmi, oracle, small_multicone_problem, structured_problem
+
+pytestmark = pytest.mark.gpu
+
+CLASSIC, SYMMETRIC = 1, 3
+
+
+@pytest.fixture(scope="module")
+def libs():
+    import devlib
+    return oracle(), devlib.product()
+
+
+def release():
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def device_program(dev, kind, n, m, mode=0):
+    """A dense-LMI program whose operator is generated in place in library-owned HBM (what bench.py times).
+    Returns (program, b, C on the host, torch view of the operator rows)."""
+    import torch
+    P = dev.program()
+    if mode:
+        dev.lib.CONEXB200_SetAssemblyMode(P.h, mode)
+    A, Cm, rb, rc = P.dense_lmi_storage(n, m)
+    b = fill_workload(kind, n, m, rb, rc, A, Cm)
+    torch.cuda.synchronize()
+    C_host = Cm.cpu().numpy().T.copy()
+    return P, b, C_host, A
+
+
+def steps_config(dev, steps, **kw):
+    return dev.default_config(max_iterations=steps, final_centering_steps=0, inv_sqrt_mu_max=1e12, **kw)
+
+
+def scaled_w(P, AW, diag_pick):
+    """W of the running iterate: CONEX_GetDualVariable returns W / scale; `diag_pick(X)` and AW give the
+    scale (AW_i = tr(A_i W) is linear in W). Returns (W, relative spread of the scale estimates)."""
+    X = P.dual_variable(0)
+    est = diag_pick(X, AW)
+    s = float(np.median(est))
+    return X * s, float(np.abs(est / s - 1.0).max())
+
+
+def gate(H, Href, what, tol=1e-10):
+    d = np.sqrt(np.abs(np.diag(Href)))
+    err = np.abs(np.tril(H) - np.tril(Href)) / np.outer(d, d)
+    assert err.max() <= tol, (what, float(err.max()))
+
+
+# ---- C2 ------------------------------------------------------------------------------------------------
+def check_maxcut_system(P, C_host, coldstart, what):
+    n = C_host.shape[0]
+    H, AW, AQc, sc = P.newton_system(coldstart=coldstart)
+    if coldstart:
+        W = np.eye(n)
+    else:
+        W, spread = scaled_w(P, AW, lambda X, aw: -aw / np.diag(X))
+        assert spread <= 1e-10, (what, spread)
+    gate(H, W * W, what + ": H vs W o W")
+    WCW = W @ C_host @ W
+    assert np.abs(AW + np.diag(W)).max() <= 1e-10 * np.abs(np.diag(W)).max(), what
+    assert np.abs(AQc + np.diag(WCW)).max() <= 1e-10 * np.abs(np.diag(WCW)).max(), what
+    assert abs(sc[0] - np.sum(C_host * W)) <= 1e-10 * np.abs(C_host * W).sum(), what
+    assert abs(sc[1] - np.sum(C_host * WCW)) <= 1e-10 * np.abs(C_host * WCW).sum(), what
+    return W
+
+
+@pytest.mark.parametrize("mode,steps", [(SYMMETRIC, 5), (CLASSIC, 3)])
+def test_c2_maxcut_n2000_dense_path_newton_system(libs, mode, steps):
+    """BASELINE config 2 at full size through the dense-LMI path, in both assembly forms, at W = I and at
+    the iterate after `steps` Newton steps: closed forms of H, AW, AQc, <w,c>, <c,Qc>."""
+    _, dev = libs
+    n = 2000
+    P, b, C_host, A = device_program(dev, "maxcut", n, n, mode)
+    del A
+    release()
+    check_maxcut_system(P, C_host, True, f"mode {mode} at W = I")
+    solved, y = P.maximize(b, steps_config(dev, steps))
+    log = P.iteration_log()
+    assert len(log) == steps
+    W = check_maxcut_system(P, C_host, False, f"mode {mode} after {steps} steps")
+    # the iterate is a genuine interior point: W > 0 and the slack Diag(y) - L/4 = C - sum y_i A_i > 0
+    assert np.linalg.eigvalsh(W).min() > 0
+    # mu decreases monotonically over these steps (run_tests.py: "mu non-increasing")
+    mus = [r["mu"] for r in log]
+    assert all(mus[i + 1] <= mus[i] * (1 + 1e-12) for i in range(len(mus) - 1))
+    del P
+    release()
+
+
+def test_c2_maxcut_n2000_dense_vs_structured_trajectory(libs):
+    """Same operators through the dense path (64 GB of matrices, DMMA assembly) and through the
+    incremental API (2000 stored entries, gather assembly): the first Newton steps agree step by step and
+    so does the iterate W."""
+    import torch
+    _, dev = libs
+    n, steps = 2000, 4
+    P, b, C_host, A = device_program(dev, "maxcut", n, n)
+    del A
+    release()
+    P.maximize(b, steps_config(dev, steps))
+    log_d, X_d = P.iteration_log(), P.dual_variable(0)
+    del P
+    release()
+    Q = dev.program(n)
+    Q.add_entry_lmi(n, [(i, i, i, -1.0) for i in range(n)], C_host)
+    Q.maximize(b, steps_config(dev, steps))
+    assert dev.lib.CONEXB200_ConstraintIsEntrySparse(Q.h, 0) == 1
+    log_s, X_s = Q.iteration_log(), Q.dual_variable(0)
+    assert len(log_d) == len(log_s) == steps
+    for i, (a, c) in enumerate(zip(log_d, log_s)):
+        for key in ("inv_sqrt_mu", "by", "cx"):
+            assert abs(a[key] - c[key]) <= 1e-7 * max(1.0, abs(a[key])), (i, key, a[key], c[key])
+    assert np.abs(X_d - X_s).max() <= 1e-7 * np.abs(X_d).max()
+    torch.cuda.synchronize()
+
+
+def primal_objective(P, C_host):
+    """<C, X> of the dual variable the public API returns (CONEX_GetDualVariable)."""
+    return float(np.sum(C_host * P.dual_variable(0)))
+
+
+def test_c2_maxcut_n400_dense_structured_oracle(libs):
+    """Complete solves at the size the CPU baseline of bench.py runs (n = m = 400): oracle vs dense path
+    (both forms) vs structured path. Iterations +-1, b'y and <C, X> within 1e-7."""
+    ora, dev = libs
+    n = 400
+    mats, Cm, b = maxcut_lmi(n, 2)
+    # the oracle in its three summation orders (as written, BLAS-3 Gram, symmetric Gram): its iteration count is
+    # only defined up to that choice (un-reorthogonalised Lanczos estimates)
+    counts = []
+    for variant in (0, 1, 2):
+        Po = ora.program()
+        Po.add_dense_lmi(mats, Cm)
+        ora.lib.ORACLE_SetGramVariant(Po.h, variant)
+        so_v, yo_v = Po.maximize(b, ora.default_config(prepare_dual_variables=1))
+        lo = Po.iteration_log()
+        assert so_v == 1
+        counts.append(len(lo))
+        if variant == 0:
+            yo, ref = yo_v, (len(lo), lo[-1]["by"], primal_objective(Po, Cm))
+    runs = {}
+    for name, mode in (("symmetric", SYMMETRIC), ("classic", CLASSIC), ("structured", None)):
+        P = dev.program(n)
+        if mode is None:
+            P.add_entry_lmi(n, [(i, i, i, -1.0) for i in range(n)], Cm)
+        else:
+            dev.lib.CONEXB200_SetAssemblyMode(P.h, mode)
+            P.add_dense_lmi(mats, Cm)
+        s, y = P.maximize(b, dev.default_config(prepare_dual_variables=1))
+        ld = P.iteration_log()
+        runs[name] = (s, len(ld), ld[-1]["by"], primal_objective(P, Cm), y)
+    for name, (s, its, by, cx, y) in runs.items():
+        assert s == 1, name
+        assert min(counts) - 1 <= its <= max(counts) + 1, (name, its, counts)
+        assert abs(by - ref[1]) <= 1e-7 * abs(ref[1]), (name, by, ref[1])
+        assert abs(cx - ref[2]) <= 1e-7 * abs(ref[2]), (name, cx, ref[2])
+        assert np.abs(y - yo).max() <= 1e-6 * np.abs(yo).max(), name
+
+
+# ---- C4 ------------------------------------------------------------------------------------------------
+def lovasz_closed_form(W, C_host, ei, ej):
+    """H, AW, AQc of the Lovasz-theta operators (A_0 = -I, A_e = E_ij + E_ji) at W."""
+    m = len(ei) + 1
+    W2 = W @ W
+    WCW = W @ C_host @ W
+    H = np.empty((m, m))
+    H[0, 0] = np.sum(W * W)
+    H[1:, 0] = H[0, 1:] = -2.0 * W2[ei, ej]
+    blk = 2048
+    for r0 in range(0, m - 1, blk):
+        r = slice(r0, min(r0 + blk, m - 1))
+        H[1 + r0:1 + r.stop, 1:] = 2.0 * (W[np.ix_(ei[r], ei)] * W[np.ix_(ej[r], ej)] +
+                                          W[np.ix_(ei[r], ej)] * W[np.ix_(ej[r], ei)])
+    AW = np.concatenate([[-np.trace(W)], 2.0 * W[ei, ej]])
+    AQc = np.concatenate([[-np.trace(WCW)], 2.0 * WCW[ei, ej]])
+    return H, AW, AQc
+
+
+def test_c4_lovasz_n500_m10001_dense_and_structured(libs):
+    """BASELINE config 4 at full size: the dense path (20 GB of matrices) and the entry-sparse path against
+    the closed form at W = I and after 3 Newton steps; the two paths against each other."""
+    from conex_b200.workloads import lovasz_edges
+    _, dev = libs
+    n, m, steps = 500, 10001, 3
+    ei, ej = lovasz_edges(n, m - 1)
+    P, b, C_host, A = device_program(dev, "lovasz", n, m)
+    del A
+    release()
+    entries, Cs, bs = structured_problem(dict(kind="lovasz_entries", n=n, m=m))
+    assert np.array_equal(Cs, C_host) and np.array_equal(bs, b)
+    Q = dev.program(m)
+    Q.add_entry_lmi(n, entries, Cs)
+    pick = lambda X, aw: np.array([-aw[0] / np.trace(X)])  # noqa: E731  (AW_0 = -tr W)
+    for coldstart in (True, False):
+        if not coldstart:
+            for R in (P, Q):
+                R.maximize(b, steps_config(dev, steps))
+            assert dev.lib.CONEXB200_ConstraintIsEntrySparse(Q.h, 0) == 1
+        sys_d = P.newton_system(coldstart=coldstart)
+        sys_s = Q.newton_system(coldstart=coldstart)
+        if coldstart:
+            W = np.eye(n)
+        else:
+            W, _ = scaled_w(P, sys_d[1], pick)
+            Ws, _ = scaled_w(Q, sys_s[1], pick)
+            assert np.abs(W - Ws).max() <= 1e-8 * np.abs(W).max()
+        Href, AWref, AQref = lovasz_closed_form(W, C_host, ei, ej)
+        where = "W = I" if coldstart else f"after {steps} steps"
+        gate(sys_d[0], Href, f"dense path, {where}")
+        assert np.abs(sys_d[1] - AWref).max() <= 1e-10 * np.abs(AWref).max()
+        assert np.abs(sys_d[2] - AQref).max() <= 1e-10 * np.abs(AQref).max()
+        if coldstart:
+            gate(sys_s[0], Href, f"structured path, {where}")
+            assert np.abs(sys_s[1] - AWref).max() <= 1e-10 * np.abs(AWref).max()
+        else:
+            Hs, AWs, AQs = lovasz_closed_form(Ws, C_host, ei, ej)
+            gate(sys_s[0], Hs, f"structured path, {where}")
+            assert np.abs(sys_s[2] - AQs).max() <= 1e-10 * np.abs(AQs).max()
+        del Href
+    ld, ls = P.iteration_log(), Q.iteration_log()
+    for i, (a, c) in enumerate(zip(ld, ls)):
+        for key in ("inv_sqrt_mu", "by", "cx"):
+            assert abs(a[key] - c[key]) <= 1e-7 * max(1.0, abs(a[key])), (i, key, a[key], c[key])
+    del P, Q
+    release()
+
+
+# ---- C5 ------------------------------------------------------------------------------------------------
+def cublas_schur_rows(A, W, rows, cols, n):
+    """H[rows, cols] = tr(A_i W A_j W) by cuBLAS FP64 (torch.matmul) from the device-resident operator."""
+    import torch
+    Wt = torch.from_numpy(np.ascontiguousarray(W)).cuda()
+    out = torch.empty((len(rows), len(cols)), dtype=torch.float64, device="cuda")
+    Aj = A if len(cols) == A.shape[0] else A[torch.as_tensor(cols, device="cuda")]
+    for r0 in range(0, len(rows), 64):
+        idx = torch.as_tensor(rows[r0:r0 + 64], device="cuda")
+        X = torch.matmul(Wt, torch.matmul(A[idx].view(-1, n, n), Wt)).reshape(len(idx), n * n)
+        out[r0:r0 + 64] = X @ Aj.T
+    return out.cpu().numpy()
+
+
+def random_lmi_scale(X, aw, A, n, probe):
+    """scale of W from AW_i = <A_i, W> on a few probe rows (the matrices are symmetric, so the column-major
+    blocks read as row-major ones)."""
+    Ai = A[probe].cpu().numpy().reshape(len(probe), n, n)
+    return np.array([aw[i] / np.sum(Ai[k] * X) for k, i in enumerate(probe)])
+
+
+def test_c5_reduced_n500_m5000_all_entries(libs):
+    """BASELINE config 5 at n = 500, m = 5000 (10 GB operator): every entry of H, AW and AQc at W = I and after
+    2 Newton steps against cuBLAS products of the device-resident matrices."""
+    import torch
+    _, dev = libs
+    n, m = 500, 5000
+    P, b, C_host, A = device_program(dev, "random", n, m)
+    rows = list(range(m))
+    for coldstart in (True, False):
+        if not coldstart:
+            P.maximize(b, steps_config(dev, 2))
+        H, AW, AQc, sc = P.newton_system(coldstart=coldstart)
+        if coldstart:
+            W = np.eye(n)
+        else:
+            probe = [0, 1, m // 2, m - 1]
+            W, spread = scaled_w(P, AW, lambda X, aw: random_lmi_scale(X, aw, A, n, probe))
+            assert spread <= 1e-9
+        Href = cublas_schur_rows(A, W, rows, rows, n)
+        gate(H, Href, "W = I" if coldstart else "after 2 steps")
+        Wt = torch.from_numpy(np.ascontiguousarray(W)).cuda().reshape(-1)
+        AWref = (A @ Wt).cpu().numpy()
+        assert np.abs(AW - AWref).max() <= 1e-10 * np.abs(AWref).max()
+        WCW = torch.from_numpy(np.ascontiguousarray(W @ C_host @ W)).cuda().reshape(-1)
+        AQref = (A @ WCW).cpu().numpy()
+        assert np.abs(AQc - AQref).max() <= 1e-10 * np.abs(AQref).max()
+    del A, P
+    release()
+
+
+@pytest.mark.skipif(os.environ.get("CONEX_B200_SKIP_FULL_C5") == "1", reason="160 GB resident operator")
+def test_c5_full_n1000_m20000_sampled_entries(libs):
+    """BASELINE config 5 at FULL size on one GPU (160 GB operator resident, row-panel assembly): after one
+    Newton step, 48 x 48 sampled entries of H plus the sampled AW / AQc rows against cuBLAS products of the
+    device-resident matrices."""
+    import torch
+    _, dev = libs
+    n, m = 1000, 20000
+    free, total = torch.cuda.mem_get_info()
+    if free < 172e9:
+        pytest.skip(f"needs 172 GB of free HBM, {free / 1e9:.0f} GB available")
+    P, b, C_host, A = device_program(dev, "random", n, m)
+    P.maximize(b, steps_config(dev, 1))
+    H, AW, AQc, sc = P.newton_system(coldstart=False)
+    rng = np.random.default_rng(5)
+    rows = sorted(rng.choice(m, size=48, replace=False).tolist())
+    cols = sorted(rng.choice(m, size=48, replace=False).tolist())
+    W, spread = scaled_w(P, AW, lambda X, aw: random_lmi_scale(X, aw, A, n, rows[:4]))
+    assert spread <= 1e-9
+    assert np.abs(W - np.eye(n)).max() > 1e-3  # a genuine non-identity iterate
+    Href = cublas_schur_rows(A, W, rows, cols, n)
+    Hs = np.array([[H[max(i, j), min(i, j)] for j in cols] for i in rows])
+    d = np.sqrt(np.diag(H))
+    err = np.abs(Hs - Href) / np.outer(d[rows], d[cols])
+    assert err.max() <= 1e-10, float(err.max())
+    Wt = torch.from_numpy(np.ascontiguousarray(W)).cuda().reshape(-1)
+    idx = torch.as_tensor(rows, device="cuda")
+    AWref = (A[idx] @ Wt).cpu().numpy()
+    assert np.abs(AW[rows] - AWref).max() <= 1e-10 * np.abs(AWref).max()
+    del A, P
+    release()
+
+
+# ---- C3 ------------------------------------------------------------------------------------------------
+def test_c3_256_programs_against_the_oracle(libs):
+    """BASELINE config 3: 256 programs of the batch (3 PSD 20 x 20 + 2 SOC of order 10 + LP 40 rows, m = 40),
+    each against the oracle solving it alone: solved flag, iterations +-1, b'y within 1e-7, y within 1e-6."""
+    O, D = libs
+    count = 256
+    problems = [small_multicone_problem(1000 + p) for p in range(count)]
+    programs = []
+    for cones, _ in problems:
+        P = D.program()
+        add_cones(P, cones)
+        programs.append(P)
+    batch = Batch(D, programs)
+    del programs
+    b = np.stack([pb for _, pb in problems])
+    solved, y = batch.maximize(b, D.default_config())
+    its, by, cx, k = batch.results()
+    worst = dict(by=0.0, y=0.0, its=0)
+    for p, (cones, pb) in enumerate(problems):
+        Po = O.program()
+        add_cones(Po, cones)
+        so, yo = Po.maximize(pb, O.default_config())
+        lo = Po.iteration_log()
+        assert solved[p] == so == 1, p
+        assert abs(int(its[p]) - len(lo)) <= 1, (p, its[p], len(lo))
+        worst["its"] = max(worst["its"], abs(int(its[p]) - len(lo)))
+        e_by = abs(by[p] - lo[-1]["by"]) / max(1.0, abs(lo[-1]["by"]))
+        e_y = np.abs(y[p] - yo).max() / max(1.0, np.abs(yo).max())
+        worst["by"], worst["y"] = max(worst["by"], e_by), max(worst["y"], e_y)
+        assert e_by <= 1e-7, (p, by[p], lo[-1]["by"])
+        assert e_y <= 1e-6, p
+    print("C3 x 256 worst deviations from the oracle:", worst)
