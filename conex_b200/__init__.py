@@ -74,6 +74,7 @@ def bind_conex_abi(lib):
 _ip = _C.POINTER(_C.c_int)
 bind_conex_abi(_lib)
 _lib.CONEXB200_CreateBatch.restype = _C.c_void_p
+_lib.CONEXB200_NumberOfConstraints.argtypes = [_C.c_void_p]
 _lib.CONEXB200_CreateBatch.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int]
 _lib.CONEXB200_DeleteBatch.argtypes = [_C.c_void_p]
 _lib.CONEXB200_BatchMaximize.argtypes = [_C.c_void_p, _dp, _C.POINTER(CONEX_SolverConfiguration), _dp, _ip]
@@ -117,6 +118,9 @@ class Conex:
     def __init__(self, m=-1, library=None):
         # `library`: a ctypes library speaking the CONEX_* ABI (bind_conex_abi); default: the product
         self._lib = library if library is not None else _lib
+        # extension entry point of whichever library is bound (the product, or the oracle in the CPU suite)
+        self._count = getattr(self._lib, "CONEXB200_NumberOfConstraints", None) or self._lib.ORACLE_NumberOfConstraints
+        self._count.argtypes = [_C.c_void_p]
         self.a = _C.c_void_p(self._lib.CONEX_CreateConeProgram())
         if not self.a:
             raise NameError("Failed to create program (is a B200 visible?).")
@@ -175,12 +179,16 @@ class Conex:
         Af = _np.asfortranarray(_np.asarray(A, dtype=_np.float64))
         lbf = _np.ascontiguousarray(_np.asarray(lb, dtype=_np.float64).ravel())
         ubf = _np.ascontiguousarray(_np.asarray(ub, dtype=_np.float64).ravel())
+        before = self._count(self.a)
         self._lib.CONEX_AddLinearInequalities(self.a, _ptr(Af), Af.shape[0], Af.shape[1], _ptr(lbf), lbf.shape[0],
                                          _ptr(ubf), ubf.shape[0])
-        self.A.append(Af)
-        self.c.append(ubf.reshape(-1, 1))
-        self.variables.append(_np.arange(Af.shape[1]))
-        self.num_constraints += 1
+        # the call adds zero, one or two constraints (an LP cone with one row per finite bound, an equality
+        # block for the rows with lb == ub): record each with the size the library reports for it
+        for i in range(before, self._count(self.a)):
+            self.A.append(None)
+            self.c.append(_np.zeros((self._lib.CONEX_GetDualVariableSize(self.a, i), 1)))
+            self.variables.append(None)
+            self.num_constraints += 1
 
     def _new(self, fn, *args):
         cid = _C.c_int(-1)
@@ -264,6 +272,9 @@ class Conex:
         x = []
         for i in range(self.num_constraints):
             r, c = self.c[i].shape[0], self.c[i].shape[1]
+            size = self._lib.CONEX_GetDualVariableSize(self.a, i)
+            if r * c != size:
+                r, c = size, 1
             xi = _np.zeros(r * c)
             self._lib.CONEX_GetDualVariable(self.a, i, _ptr(xi), r, c)
             x.append(xi.reshape((r, c), order="F"))

@@ -788,8 +788,8 @@ int g_potrf_mode = 0;
 int g_potrf_lookahead = 1;  // bit 1 of cxb_set_potrf_mode clears it (sequential schedule, A/B)
 
 void ConfigureOnce() {
-  static bool configured = false;
-  if (configured) return;
+  static std::atomic<unsigned long long> configured{0};
+  if (!FirstUseOnCurrentDevice(configured)) return;
   cudaFuncSetAttribute(PotrfDiagKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
   cudaFuncSetAttribute(PotrfDiagKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
   cudaFuncSetAttribute(PotrfDiagBlockedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
@@ -798,7 +798,6 @@ void ConfigureOnce() {
   cudaFuncSetAttribute(TrsvBwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
   cudaFuncSetAttribute(TrsvFwdWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
   cudaFuncSetAttribute(TrsvBwdWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
-  configured = true;
 }
 
 }  // namespace

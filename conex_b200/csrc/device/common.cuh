@@ -1,5 +1,6 @@
 // Shared device helpers for the conex-b200 kernels (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,8 +20,20 @@ inline int LaunchStatus() {
 inline cudaStream_t AsStream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Every kernel launch of the library is counted (reported by CONEXB200_LaunchCount / bench.py).
-extern long g_launch_count;
-inline void CountLaunch() { ++g_launch_count; }
+extern std::atomic<long> g_launch_count;
+inline void CountLaunch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+// Per-kernel attributes (cudaFuncSetAttribute) are per device: `mask` has one bit per device ordinal.
+// Returns true the first time the calling thread's current device is seen (programs may be driven from
+// several host threads and on several devices of one process, like the reference's Program objects).
+inline bool FirstUseOnCurrentDevice(std::atomic<unsigned long long>& mask) {
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) return true;
+  const unsigned long long bit = 1ull << device;
+  if (mask.load(std::memory_order_acquire) & bit) return false;
+  mask.fetch_or(bit, std::memory_order_acq_rel);
+  return true;
+}
 
 // ---- cp.async (LDGSTS) -------------------------------------------------------------------
 // 16-byte copy with zero fill of the bytes beyond src_bytes (0, 8 or 16).

@@ -315,21 +315,18 @@ __global__ void __launch_bounds__(256) SplitKReduceKernel(int M, int N, int spli
   *out = v;
 }
 
-// Split-K workspace: grown on demand, owned by the library (one per process; kernels of one
-// program run on one stream, and programs on different streams must not share it concurrently —
-// the host layer creates one stream per process).
-double* g_splitk_ws = nullptr;
-size_t g_splitk_ws_doubles = 0;
-
-double* SplitKWorkspace(size_t doubles) {
-  if (doubles > g_splitk_ws_doubles) {
-    if (g_splitk_ws) cudaFree(g_splitk_ws);
-    g_splitk_ws = nullptr;
-    g_splitk_ws_doubles = 0;
-    if (cudaMalloc(&g_splitk_ws, doubles * sizeof(double)) != cudaSuccess) return nullptr;
-    g_splitk_ws_doubles = doubles;
+// Split-K partial sums live in stream-ordered memory (cudaMallocAsync / cudaFreeAsync on the launching
+// stream): every program owns its stream (DeviceContext), programs may be driven from different host
+// threads and devices, and a process-wide buffer would be shared by concurrent GEMMs. The default pool
+// keeps the block cached between launches (release threshold set by DeviceContext), so this costs no
+// driver call in steady state.
+double* SplitKWorkspace(cudaStream_t stream, size_t doubles) {
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, doubles * sizeof(double), stream) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
   }
-  return g_splitk_ws;
+  return static_cast<double*>(p);
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AKC, bool BKC, int VEC>
@@ -338,10 +335,9 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
   static_assert(MINB * (Cfg::kSmemBytes + 1024) <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kernel = DgemmKernel<BM, BN, BK, WM, WN, STAGES, MINB, AKC, BKC, VEC>;
   constexpr int kSlots = kNumSMs * MINB;  // CTAs resident at once
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};
+  if (FirstUseOnCurrentDevice(configured)) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
-    configured = true;
   }
   g.tiles_m = (g.M + BM - 1) / BM;
   g.tiles_n = (g.N + BN - 1) / BN;
@@ -384,7 +380,7 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
   if (splits > 1) {
     // drop empty trailing splits
     g.splits = splits = (kt_total + kt_per - 1) / kt_per;
-    g.partials = SplitKWorkspace((size_t)splits * g.M * g.N);
+    g.partials = SplitKWorkspace(stream, (size_t)splits * g.M * g.N);
     if (g.partials == nullptr) return (int)cudaErrorMemoryAllocation;
   }
   dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)batch);
@@ -393,6 +389,7 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
     dim3 rg((g.M + 255) / 256, g.N);
     CountLaunch(); SplitKReduceKernel<<<rg, 256, 0, stream>>>(g.M, g.N, splits, g.partials, g.alpha, g.beta,
                                                   g.C, g.ldc, g.lower, g.diag_off);
+    cudaFreeAsync(g.partials, stream);
   }
   return LaunchStatus();
 }

@@ -282,7 +282,7 @@ int cxb_lanczos_two_sided_range(void* stream, int n, const double* d_WS, const d
       for (auto& e : g_graphs) cudaGraphExecDestroy(e.second.exec);
       g_graphs.clear();
     }
-    const long before = g_launch_count;
+    const long before = g_launch_count.load();
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
       return EnqueueLanczos(s, n, d_WS, d_W, d_r, d_col_index, num_iter, d_alpha, d_beta, d_count, d_work, rel_tol, j_begin, j_end);
@@ -291,8 +291,8 @@ int cxb_lanczos_two_sided_range(void* stream, int n, const double* d_WS, const d
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s, &graph);
     GraphEntry entry;
-    entry.launches = g_launch_count - before;
-    g_launch_count = before;
+    entry.launches = g_launch_count.load() - before;
+    g_launch_count.fetch_sub(entry.launches);
     if (rc != 0 || e != cudaSuccess || graph == nullptr ||
         cudaGraphInstantiate(&entry.exec, graph, 0) != cudaSuccess) {
       if (graph) cudaGraphDestroy(graph);
@@ -302,7 +302,7 @@ int cxb_lanczos_two_sided_range(void* stream, int n, const double* d_WS, const d
     cudaGraphDestroy(graph);
     it = g_graphs.emplace(key, entry).first;
   }
-  g_launch_count += it->second.launches;
+  g_launch_count.fetch_add(it->second.launches);
   const cudaError_t e = cudaGraphLaunch(it->second.exec, s);
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

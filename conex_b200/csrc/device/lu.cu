@@ -357,15 +357,14 @@ __global__ void __launch_bounds__(256) TrsmDiagKernel(int nb, const double* __re
 constexpr int kLuPanelSmemBytes = 200 * 1024;  // dynamic shared memory of LuPanelSmemKernel
 
 void ConfigureOnce() {
-  static bool configured = false;
-  if (configured) return;
+  static std::atomic<unsigned long long> configured{0};
+  if (!FirstUseOnCurrentDevice(configured)) return;
   const int bytes = (int)(sizeof(double) * (kSolveNB * (kSolveNB + 1) + kSolveNB * (kRhsCols + 1)));
   cudaFuncSetAttribute(TrsmDiagKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(TrsmDiagKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(BuildPermKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(LuPanelSmemKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLuPanelSmemBytes);
   cudaFuncSetAttribute(LuPanelSmemKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLuPanelSmemBytes);
-  configured = true;
 }
 
 size_t TrsmSmem(int nb) {

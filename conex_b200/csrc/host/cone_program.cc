@@ -275,7 +275,12 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
   const int N = prog.SizeOfKKTSystem();
   bool reused = false;
   std::unique_ptr<KKTSolver> fresh;
-  if (prog.kkt_solver_kind != 1 && prog.NumberOfMultipliers() == 0 && !prog.ctx_.collective) {
+  // Iterative refinement needs K y with the assembled matrix (kkt_solver.cc:248-261); the multifrontal solver
+  // factors its fronts in place and keeps no copy, so a configuration that asks for refinement gets the dense
+  // solver unless the multifrontal one was requested explicitly (kind 2, which then fails loudly in SolveInPlace).
+  const bool refinement_needs_dense = config.iterative_refinement_iterations > 0 && prog.kkt_solver_kind != 2;
+  if (prog.kkt_solver_kind != 1 && prog.NumberOfMultipliers() == 0 && !prog.ctx_.collective &&
+      !refinement_needs_dense) {
     std::vector<std::vector<int>> cliques;
     bool some_cone_couples_everything = false;
     for (const auto& c : prog.eqs) {
@@ -306,6 +311,8 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
   }
   if (!reused) {
     prog.solver_is_multifrontal_ = fresh != nullptr;
+    // the old solver's N x N buffers (3.2 GB each at m = 20000) are released before the new ones are allocated
+    prog.solver.reset();
     if (!fresh) fresh = std::make_unique<DenseKKTSolver>(&prog.ctx_, N);
     prog.solver = std::move(fresh);
   }

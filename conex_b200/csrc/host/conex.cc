@@ -3,6 +3,7 @@
 // are device cones; the entry points that build cones outside the scope (Hermitian LMIs, quadratic
 // costs) validate their arguments like the reference and then report failure on stderr instead of
 // silently doing CPU work. Exceptions never cross the ABI: they map to the call's failure value.
+#include <atomic>
 #include <cuda_runtime_api.h>
 
 #include <cstdlib>
@@ -22,7 +23,7 @@
 #include "tridiagonal_eigenvalues.h"
 
 namespace cxb {
-long g_launch_count = 0;
+std::atomic<long> g_launch_count{0};
 }
 
 using conex::DenseLMIConstraint;
@@ -120,7 +121,7 @@ int CONEX_AddDenseLMIConstraint(void* prog, const double* A, int Ar, int Ac, int
         Program& program = *static_cast<Program*>(prog);
         if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
         const int id = program.NumberOfConstraints();
-        program.AddConstraint(DenseLMIConstraint(Ar, m, A, c));
+        if (program.AddConstraint(DenseLMIConstraint(Ar, m, A, c))) return -1;
         return id;
       },
       -1);
@@ -139,7 +140,8 @@ int CONEX_AddSparseLMIConstraint(void* prog, const double* A, int Ar, int Ac, in
         std::vector<int> variables(num_vars);
         for (int i = 0; i < num_vars; i++) variables[i] = static_cast<int>(vars[i]);
         const int id = program.NumberOfConstraints();
-        program.AddConstraint(DenseLMIConstraint(Ar, num_vars, A, c), variables);
+        // duplicate or out-of-range variables: nothing was added, so `id` would name a later constraint
+        if (program.AddConstraint(DenseLMIConstraint(Ar, num_vars, A, c), variables)) return -1;
         return id;
       },
       -1);
@@ -152,7 +154,7 @@ int CONEXB200_AddDenseLMIConstraintDevice(void* prog, const double* d_A, int n, 
         Program& program = *static_cast<Program*>(prog);
         if (program.GetNumberOfVariables() == 0) program.SetNumberOfVariables(m);
         const int id = program.NumberOfConstraints();
-        program.AddConstraint(DenseLMIConstraint(n, m, DenseLMIConstraint::DevicePointers{d_A, d_C}));
+        if (program.AddConstraint(DenseLMIConstraint(n, m, DenseLMIConstraint::DevicePointers{d_A, d_C}))) return -1;
         return id;
       },
       -1);
@@ -337,11 +339,22 @@ int CONEX_Solve(void* prog_ptr, const CONEX_SolverConfiguration* config, double*
 
 void CONEX_GetDualVariable(void* prog_ptr, int i, double* x, int xr, int xc) {
   // reference interfaces/conex.cc:114-122
-  (void)xr;
-  (void)xc;
+  // The reference only asserts size == xr * xc (compiled out under NDEBUG) and then writes `size` doubles
+  // into the caller's buffer; a wrong shape is refused here instead of overrunning it.
   Guard(
       [&]() -> int {
-        static_cast<Program*>(prog_ptr)->GetDualVariable(i, x);
+        Program& prog = *static_cast<Program*>(prog_ptr);
+        if (x == nullptr || i < 0 || i >= prog.NumberOfConstraints()) {
+          std::cerr << "CONEX_GetDualVariable: invalid constraint or null buffer." << std::endl;
+          return 0;
+        }
+        const long size = prog.GetDualVariableSize(i);
+        if (static_cast<long>(xr) * xc != size) {
+          std::cerr << "CONEX_GetDualVariable: buffer is " << xr << " x " << xc << " but the dual variable of constraint "
+                    << i << " has " << size << " entries; nothing written." << std::endl;
+          return 0;
+        }
+        prog.GetDualVariable(i, x);
         return 0;
       },
       0);
@@ -781,7 +794,11 @@ void CONEXB200_TridiagonalExtremes(int n, const double* alpha, const double* bet
   out2[1] = mm.second;
 }
 
-long CONEXB200_LaunchCount() { return cxb::g_launch_count; }
+int CONEXB200_NumberOfConstraints(void* prog_ptr) {
+  return Guard([&]() -> int { return static_cast<Program*>(prog_ptr)->NumberOfConstraints(); }, -1);
+}
+
+long CONEXB200_LaunchCount() { return cxb::g_launch_count.load(); }
 
 int CONEXB200_DeviceAvailable() {
   int count = 0;

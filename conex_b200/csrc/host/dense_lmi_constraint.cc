@@ -276,10 +276,25 @@ void DenseLMIConstraint::EnsureScratch() {
   CudaCheck(cudaMemGetInfo(&free_bytes, &total_bytes), "cudaMemGetInfo");
   const size_t other = sizeof(double) * (4 * nn + (size_t(1) << 28)) + (size_t(2) << 30);
   const int mode = ctx_->assembly_mode;
-  d.symmetric = (mode == 3 || (mode == 0 && sym_bytes + other <= free_bytes)) && !(sharded_ && mode == 1);
-  d.streamed = !sharded_ && !d.symmetric &&
-               (mode == 2 || ((mode == 0 || mode == 3) && full_bytes + other > free_bytes));
-  if (sharded_ && !d.symmetric && full_bytes + other > free_bytes) {
+  bool sym_fits = sym_bytes + other <= free_bytes;
+  bool full_fits = full_bytes + other <= free_bytes;
+  if (sharded_) {
+    // The form decides WHAT travels between the ranks (packed X with stride kp, or raw A with stride n^2)
+    // and the size of the receive buffers, so it must be one decision for the whole communicator: a form
+    // is used only if it fits on EVERY rank (shards differ by one matrix, free memory by whatever else
+    // lives on each GPU). Both outcomes, including the failure below, are then identical on all ranks.
+    int does_not_fit[2] = {sym_fits ? 0 : 1, full_fits ? 0 : 1};
+    int* slot = ctx_->flags() + 6;
+    CudaCheck(cudaMemcpyAsync(slot, does_not_fit, sizeof(does_not_fit), cudaMemcpyHostToDevice, ctx_->cuda_stream()),
+              "H2D copy");
+    Communicator::Get().AllReduceMaxInt(slot, 2, ctx_->cuda_stream());
+    ctx_->DownloadInts(does_not_fit, slot, 2);
+    sym_fits = does_not_fit[0] == 0;
+    full_fits = does_not_fit[1] == 0;
+  }
+  d.symmetric = (mode == 3 || (mode == 0 && sym_fits)) && !(sharded_ && mode == 1);
+  d.streamed = !sharded_ && !d.symmetric && (mode == 2 || ((mode == 0 || mode == 3) && !full_fits));
+  if (sharded_ && !d.symmetric && !full_fits) {
     throw std::runtime_error("conex-b200: the scaled matrices of this shard do not fit in HBM; use more ranks");
   }
   // Constraint matrices scaled per pass. Streamed: a multiple of the 64-row GEMM tile, <= 2 GiB.

@@ -153,6 +153,9 @@ int CONEXB200_GetNumberOfSupernodes(void* prog);
 int CONEXB200_SupernodalAnalysis(int N, int num_cliques, const int* clique_ptr, const int* clique_vars,
                                  int* position, int* node_of, int* node_ptr, int* node_vars, int* sep_ptr,
                                  int* sep_vars, int sep_capacity, double* flops2);
+/* Constraints added so far (Program::NumberOfConstraints, conex/cone_program.h); CONEX_AddLinearInequalities adds
+ * zero, one or two (an LP cone for the finite bounds, an equality block for rows with lb == ub). */
+int CONEXB200_NumberOfConstraints(void* prog);
 /* Variables + equality multipliers (conex/constraint_manager.h:42-48). */
 int CONEXB200_SizeOfKKTSystem(void* prog);
 /* Host-logic probe: the pivot order Eigen::RLDLT derives from the diagonal (RLDLT.h:328-356). */

@@ -396,6 +396,7 @@ int ORACLE_HermitianLanczos(int n, const double* WS, const double* W, const doub
 }
 
 int ORACLE_SizeOfKKTSystem(void* p) { return Cast(p)->SizeOfKKTSystem(); }
+int ORACLE_NumberOfConstraints(void* p) { return Cast(p)->NumberOfConstraints(); }
 // In-place RLDLT of the lower triangle of A (n x n); transpositions written as ints. Returns 1
 // when no pivot was regularised.
 int ORACLE_LdltLower(int n, double* A, int* transpositions) {

@@ -294,6 +294,41 @@ def test_sparse_programs_match_oracle_and_dense_solver(shape):
 
 
 @pytest.mark.gpu
+def test_iterative_refinement_on_a_sparse_program_takes_the_dense_solver():
+    """A configuration that is valid in the reference (kkt_solver.cc:248-261, kkt_solver_options_test.cc) must not
+    turn into "not solved" because the clique structure made the library pick the multifrontal solver: with
+    iterative_refinement_iterations > 0 and the default solver kind the program is solved by the dense solver."""
+    import devlib
+    dev, ora = devlib.product(), oracle()
+    m, cones = block_arrow_program(blocks=4, private=80, shared=10, order=8, seed=3)   # m = 330 >= 256: pays
+    out = []
+    for L, kind in ((ora, None), (dev, 0)):
+        P = L.program(m)
+        if kind is not None:
+            L.lib.CONEXB200_SetKKTSolverKind.argtypes = [C.c_void_p, C.c_int]
+            L.lib.CONEXB200_SetKKTSolverKind.restype = None
+            L.lib.CONEXB200_SetKKTSolverKind(P.h, kind)
+        for mats, Cm, variables in cones:
+            P.add_dense_lmi(mats, Cm, variables)
+        b = P.feasible_objective()
+        Q = None
+        if kind is not None:   # without refinement the same program does take the multifrontal solver
+            Q = L.program(m)
+            for mats, Cm, variables in cones:
+                Q.add_dense_lmi(mats, Cm, variables)
+            assert Q.maximize(b, L.default_config())[0] == 1
+            assert L.lib.CONEXB200_GetNumberOfSupernodes(Q.h) > 1
+        solved, y = P.maximize(b, L.default_config(iterative_refinement_iterations=1))
+        out.append((solved, y, P.iteration_log()))
+        if kind is not None:
+            assert L.lib.CONEXB200_GetNumberOfSupernodes(P.h) == 1
+    (so, yo, lo), (sd, yd, ld) = out
+    assert so == sd == 1 and abs(len(lo) - len(ld)) <= 1
+    assert abs(lo[-1]["by"] - ld[-1]["by"]) <= 1e-7 * max(1.0, abs(lo[-1]["by"]))
+    assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+
+
+@pytest.mark.gpu
 def test_supernodal_factor_and_solve_against_lapack():
     """A bigger block-arrow system (supernodes of 300-340 unknowns, beyond one 128-column block)
     through the solver's own factor / solve calls, driven by LMI cones whose G is random SPD."""

@@ -223,6 +223,26 @@ def test_matlab_sparse_tests(Conex):  # run_conex_tests.m:71-103
     assert np.linalg.norm(Ax - b) < 1e-8            # the reference asserts 1e-12 on its own run
 
 
+def test_linear_inequalities_bookkeeping_of_dual_variables(Conex):
+    """CONEX_AddLinearInequalities adds zero, one or two constraints (interfaces/conex.cc:190-215: an LP cone with
+    one row per finite bound, an equality block for lb == ub). The wrapper must size every dual-variable buffer
+    from what the library reports, and later constraint indices must not shift."""
+    m = 3
+    prog = Conex(m)
+    A = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0], [1.0, 1.0, 1.0]])
+    lb = np.array([-1.0, -2.0, -1e20, 0.5])   # row 0, 1: both bounds; row 2: upper only; row 3: equality
+    ub = np.array([1.0, 2.0, 3.0, 0.5])
+    prog.AddLinearInequalities(A, lb, ub)
+    assert prog.num_constraints == 2            # LP cone with 5 rows + equality block with 1 row
+    prog.AddLinearInequality(np.eye(m), 10 * np.ones(m))
+    assert prog.num_constraints == 3
+    sol = prog.Maximize(np.array([1.0, 1.0, 0.0]))
+    assert sol.status
+    x = prog.GetDualVariables()
+    assert [xi.shape for xi in x][0] == (5, 1) and x[2].shape == (m, 1)
+    assert abs(sol.y.sum() - 0.5) < 1e-7 and sol.y[0] <= 1 + 1e-6 and sol.y[1] <= 2 + 1e-6
+
+
 @pytest.mark.gpu
 def test_known_bad_instance_equality_constraint_failing_ldlt_on_the_device():
     """conex/test/solver_failures.cc:12-46 (see tests/test_oracle_cones.py): the regularised LDL^T of the
