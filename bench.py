@@ -32,9 +32,6 @@ os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# DRAM traffic of the assembly phase of one C2 Newton step (ncu --set full, see the roofline note)
-ASSEMBLY_TRAFFIC_C2 = 61 * (2.381e9 + 1.998e9) + 1.3545e12
-
 METRIC = "newton_step_ms"
 UNIT = "ms"
 
@@ -61,7 +58,10 @@ WORKLOADS = {
     # variables through CONEX_AddSparseLMIConstraint -> block-arrow Schur complement of order 12100
     "sparse": dict(kind="arrow", n=60, m=12100, blocks=8, private=1500, shared=100,
                    cpu=dict(blocks=8, private=150, shared=10, n=20)),
-    "c2": dict(kind="maxcut", n=2000, m=2000, cpu=dict(n=400, m=400)),
+    # cpu: the sample the --impl reference arm times (n = m = 1000); cpu_small: the 10-30 s sample of
+    # the b200 arm's cpu_baseline leg; cpu_check: a second size that validates the per-phase work model
+    "c2": dict(kind="maxcut", n=2000, m=2000, cpu=dict(n=1000, m=1000), cpu_small=dict(n=500, m=500),
+               cpu_check=dict(n=400, m=400)),
     "c5": dict(kind="random", n=1000, m=20000, cpu=dict(n=120, m=600)),
     "c4": dict(kind="lovasz", n=500, m=10001, cpu=dict(n=100, m=401)),
     "c1": dict(kind="random", n=50, m=100, cpu=dict(n=50, m=100)),
@@ -169,13 +169,25 @@ def _oracle_loader():
 
 
 def cpu_problem(kind, n, m):
+    """(packed matrices (m x n^2, one column-major block per row), column-major C, b or None)."""
+    from conex_b200.binding import fmat, pack_matrices
     from conex_b200.workloads import lovasz_theta_lmi, maxcut_lmi, random_dense_lmi
     if kind == "maxcut":
-        return maxcut_lmi(n, 2)
+        if n <= 400:
+            mats, Cm, b = maxcut_lmi(n, 2)
+            return pack_matrices(mats), fmat(Cm), b
+        # same instance family without the m dense numpy matrices (8 GB at n = 1000): packed buffer directly
+        rng = np.random.Generator(np.random.PCG64(2))
+        upper = np.triu(rng.random((n, n)) < 0.5, 1).astype(np.float64)
+        adj = upper + upper.T
+        A = np.zeros((n, n * n))
+        A[np.arange(n), np.arange(n) * (n + 1)] = -1.0
+        return A, fmat(-(np.diag(adj.sum(axis=1)) - adj) / 4.0), -np.ones(n)
     if kind == "lovasz":
-        return lovasz_theta_lmi(n, m - 1, 4)
+        mats, Cm, b = lovasz_theta_lmi(n, m - 1, 4)
+        return pack_matrices(mats), fmat(Cm), b
     mats, Cm = random_dense_lmi(n, m, 1)
-    return mats, Cm, None
+    return pack_matrices(mats), fmat(Cm), None
 
 
 def phase_model(n, m):
@@ -185,54 +197,73 @@ def phase_model(n, m):
                 update=10.7 * n ** 3 + 2.0 * m * n ** 2, mu=4.0 * n ** 3 + 2.0 * m * n ** 2 + float(m) * m)
 
 
-def cpu_baseline(w, steps, warmup, threads=None):
-    """Times the oracle port (reference algorithm as written, OpenBLAS underneath) on a reduced
-    instance of the same workload and extrapolates each phase to the full shape with the work model
-    above (the full operators, 64-160 GB, do not fit the host; the as-written Gram alone would take
-    tens of minutes per step)."""
+def cpu_sample(O, kind, ns, ms, total_steps, gram_variant):
+    """One oracle solve of `total_steps` Newton steps on the (ns, ms) instance: per-step wall time and phases."""
+    A, Cf, b = cpu_problem(kind, ns, ms)
+    P = O.program()
+    P.add_dense_lmi_packed(A, Cf, ns, ms)
+    del A
+    # 0: the Gram rows as conex computes them (m matrix-vector products, dense_lmi_constraint.cc:77-78);
+    # 1: the same contraction as one BLAS-3 call — so that the GPU/CPU ratio is not inflated by the
+    # reference's own BLAS-2 formulation (SURVEY.md 8d)
+    O.lib.ORACLE_SetGramVariant(P.h, gram_variant)
+    bb = P.feasible_objective() if b is None else b
+    cfg = O.default_config(max_iterations=total_steps, final_centering_steps=0, inv_sqrt_mu_max=1e12)
+    t0 = time.perf_counter()
+    P.maximize(bb, cfg)
+    wall = time.perf_counter() - t0
+    its = max(P.status()["num_iterations"], 1)
+    per = {k: v / its for k, v in P.phase_seconds().items()}
+    return wall / its, its, per
+
+
+def cpu_baseline(w, steps, warmup, threads=None, sample_key="cpu"):
+    """Times the oracle port (reference algorithm as written, OpenBLAS underneath) on a reduced instance of the
+    same workload and extrapolates each phase to the full shape with the work model above (the full operators,
+    64-160 GB, do not fit the host; the as-written Gram alone would take many minutes per step). When the
+    workload names a second sample size (`cpu_check`), the same model predicts the larger sample from the
+    smaller one and the prediction is reported next to the measurement (`model_check`)."""
     oracle = _oracle_loader()
     O = oracle()
     cores = threads or os.cpu_count()
     O.lib.ORACLE_SetBlasThreads(cores)
-    ns, ms = w["cpu"]["n"], w["cpu"]["m"]
-    mats, Cm, b = cpu_problem(w["kind"], ns, ms)
+    size = w.get(sample_key) or w["cpu"]
+    ns, ms = size["n"], size["m"]
     total = warmup + steps
-    cfg = O.default_config(max_iterations=total, final_centering_steps=0, inv_sqrt_mu_max=1e12)
     full, small = phase_model(w["n"], w["m"]), phase_model(ns, ms)
     ratio = {k: full[k] / small[k] for k in full}
     same = (ns, ms) == (w["n"], w["m"])
-
-    def timed_solve(gram_variant):
-        # 0: the Gram rows as conex computes them (m matrix-vector products, dense_lmi_constraint.cc:77-78);
-        # 1: the same contraction as one BLAS-3 call — so that the GPU/CPU ratio is not inflated by the
-        # reference's own BLAS-2 formulation (SURVEY.md 8d)
-        P = O.program()
-        P.add_dense_lmi(mats, Cm)
-        O.lib.ORACLE_SetGramVariant(P.h, gram_variant)
-        bb = P.feasible_objective() if b is None else b
-        t0 = time.perf_counter()
-        P.maximize(bb, cfg)
-        wall = time.perf_counter() - t0
-        its = max(P.status()["num_iterations"], 1)
-        per = {k: v / its for k, v in P.phase_seconds().items()}
-        return wall, its, per, sum(per[k] * ratio[k] for k in per)
-
-    wall3, its3, per3, full3_s = timed_solve(1)
-    wall, its, per, full_s = timed_solve(0)
-    return {
-        "blas3_gram": {"value": (wall3 / its3 if same else full3_s) * 1e3, "unit": UNIT,
-                       "sample_ms_per_step": wall3 / its3 * 1e3,
+    step3, its3, per3 = cpu_sample(O, w["kind"], ns, ms, total, 1)
+    step0, its, per = cpu_sample(O, w["kind"], ns, ms, total, 0)
+    full_s = sum(per[k] * ratio[k] for k in per)
+    full3_s = sum(per3[k] * ratio[k] for k in per3)
+    out = {
+        "blas3_gram": {"value": (step3 if same else full3_s) * 1e3, "unit": UNIT, "sample_ms_per_step": step3 * 1e3,
                        "note": "same port with the Gram contraction as one BLAS-3 call instead of the reference's m "
                                "matrix-vector products"},
-        "value": (wall / its if same else full_s) * 1e3, "unit": UNIT, "cores": cores, "kind": "port",
+        "value": (step0 if same else full_s) * 1e3, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": (f"oracle port (as-written Gram, OpenBLAS x{cores} threads) on {w['kind']} n={ns} m={ms}, "
-                   f"{its} Newton steps, {wall / its * 1e3:.1f} ms/step measured" +
+                   f"{its} Newton steps, {step0 * 1e3:.1f} ms/step measured" +
                    ("" if same else "; value is the per-phase extrapolation to "
                     f"n={w['n']} m={w['m']} by the work model (" +
                     ", ".join(f"{k} x{ratio[k]:.0f}" for k in ratio) + ")")),
-        "sample_ms_per_step": wall / its * 1e3,
+        "sample_ms_per_step": step0 * 1e3,
         "sample_phase_ms": {k: v * 1e3 for k, v in per.items()},
     }
+    chk = w.get("cpu_check")
+    if chk and (chk["n"], chk["m"]) != (ns, ms):
+        # validate the model: predict THIS sample from a smaller one
+        stepc, itsc, perc = cpu_sample(O, w["kind"], chk["n"], chk["m"], total, 0)
+        tiny = phase_model(chk["n"], chk["m"])
+        predicted = sum(perc[k] * small[k] / tiny[k] for k in perc)
+        out["model_check"] = {
+            "smaller_sample": f"n={chk['n']} m={chk['m']}: {stepc * 1e3:.1f} ms/step measured ({itsc} steps)",
+            "predicted_ms_per_step": predicted * 1e3, "measured_ms_per_step": step0 * 1e3,
+            "measured_over_predicted": step0 / predicted,
+            "note": f"work model applied from n={chk['n']} to n={ns} (the same model carries n={ns} to n={w['n']}); a ratio "
+                    "above 1 means the extrapolated value UNDERSTATES the CPU time (cache effects of the larger "
+                    "operator), below 1 that it overstates it"}
+    return out
 
 
 # ---- BASELINE config 3: many small multi-cone programs, batched per GPU ----------------------------
@@ -274,28 +305,79 @@ def cpu_baseline_batched(w, count=None, threads=1):
             "programs_per_s": count / t_total}
 
 
-def run_b200_batched(args):
-    import torch
-    import torch.distributed as dist
+class Process:
+    """One rank of the benchmark: device selection, torch.distributed (NCCL) for the plumbing, the product library
+    and — on first use — its own NCCL communicator."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import conex_b200.binding as devlib
+        self.torch, self.dist, self.devlib = torch, dist, devlib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.dev = devlib.product()
+        self.L = self.dev.lib
+        assert self.L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
+        self._comm = False
+        self.peak_tf = measure_fp64_peak()
+
+    def communicator(self):
+        if self.world > 1 and not self._comm:
+            self.devlib.init_communicator(self.dev, self.rank, self.world)
+            self._comm = True
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return [float(v) for v in values]
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().tolist()
+
+    def sum_over_ranks(self, values):
+        if self.world == 1:
+            return [float(v) for v in values]
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().tolist()
+
+    def release(self):
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+    def close(self):
+        if self._comm:
+            self.L.CONEXB200_CommDestroy()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6534.8, "B200_PROFILING.md fallback 6534.8 GB/s"
+
+
+def batched_bench(proc, args, w, cpu_leg):
+    """BASELINE config 3 on this process' share of the programs; returns the JSON dict on rank 0, None elsewhere."""
     from conex_b200.binding import Batch
     from conex_b200.workloads import add_cones, small_multicone_problem
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import conex_b200.binding as devlib
-    dev = devlib.product()
-    L = dev.lib
-    assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
-    w = workload_shape(args)
+    torch, dev, L, world, rank = proc.torch, proc.dev, proc.L, proc.world, proc.rank
     total_programs = w["programs"]
     lo = total_programs * rank // world
     hi = total_programs * (rank + 1) // world
-    peak_tf = measure_fp64_peak() if rank == 0 else None
-
     t_setup = time.perf_counter()
     programs, bs = [], []
     for p in range(lo, hi):
@@ -310,12 +392,10 @@ def run_b200_batched(args):
     setup_s = time.perf_counter() - t_setup
 
     cfg = dev.default_config()
-    # warm-up solves (W >= 3 untimed Newton steps: one full solve is ~15), then the timed solve
+    # warm-up solve (W >= 3 untimed Newton steps: one full solve is ~17), then the timed solve
     batch.maximize(b, cfg)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    proc.barrier()
+    sampler = ClockSampler(proc.local_rank)
     sampler.start()
     launches0 = L.CONEXB200_LaunchCount()
     t0 = time.perf_counter()
@@ -328,46 +408,34 @@ def run_b200_batched(args):
     step_ms = batch.step_milliseconds()
     lock_steps = len(step_ms)
     dev_ms = batch.milliseconds()
-    program_steps = int(its.sum())
-    t = torch.tensor([dev_ms, e2e_wall * 1e3, float(step_ms.mean())], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(program_steps), float(solved.sum()), float(hi - lo)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, mean_step_ms = float(t[0]), float(t[1]), float(t[2])
-    program_steps, nsolved, nprog = float(cnt[0]), int(cnt[1]), int(cnt[2])
+    dev_ms, e2e_ms, mean_step_ms = proc.max_over_ranks([dev_ms, e2e_wall * 1e3, float(step_ms.mean())])
+    program_steps, nsolved, nprog = proc.sum_over_ranks([float(its.sum()), float(solved.sum()), float(hi - lo)])
+    nsolved, nprog = int(nsolved), int(nprog)
+    del batch
+    proc.release()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     flops = batched_flops_per_program_step() * program_steps
     bytes_ = batched_bytes_per_program_step() * program_steps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6534.8))
+    peak, peak_src = hbm_peak()
     line = {
         "metric": METRIC, "value": mean_step_ms, "unit": UNIT, "n_gpus": world, "steps": lock_steps,
         "warmup": lock_steps, "ms_per_step": mean_step_ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["name"], "programs": nprog, "m": 40,
-                   "path": "CONEXB200_BatchMaximize: all programs advance one Newton step per launch set, "
-                           "one CTA per program and cone",
-                   "l2": "a full solve (cone data 1.6 GB + scaled matrices 1.6 GB per step) separates repeats",
+                   "path": "CONEXB200_BatchMaximize: all programs advance one Newton step per launch set",
+                   "l2": "a full solve (cone data 1.6 GB per step) separates repeats",
                    "multi_gpu": (f"programs partitioned over {world} ranks, no collective" if world > 1 else "n/a"),
                    "step": "one lock-step Newton step of the whole batch (mean over the solve; programs that "
                            "have terminated are masked out of later steps)"},
         "solve_ms": dev_ms, "programs_per_s": nprog / (dev_ms * 1e-3), "programs_solved": nsolved,
         "program_steps": program_steps,
         "step_tflops_fp64": flops / (dev_ms * 1e-3) / 1e12,
-        "roofline": {"bound": "hbm", "kernel": "SchurKernel (small_cones.cu: W A_i W and Gram of the 20x20 LMI blocks)",
-                     "achieved": bytes_ / (dev_ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
-                     "frac": bytes_ / (dev_ms * 1e-3) / 1e9 / (hbm_peak * world),
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "B200_PROFILING.md fallback 6534.8 GB/s",
+        "roofline": {"bound": "hbm", "kernel": "batched Schur assembly of the 20x20 LMI blocks (small_cones.cu)",
+                     "achieved": bytes_ / (dev_ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                     "frac": bytes_ / (dev_ms * 1e-3) / 1e9 / (peak * world), "peak_source": peak_src,
                      "note": "whole-solve time, all kernels; the same work is 2 flop/byte-balanced: "
-                             f"{flops / (dev_ms * 1e-3) / 1e12:.2f} TFLOP/s FP64 (DFMA) vs {peak_tf:.1f} TFLOP/s cuBLAS DGEMM",
+                             f"{flops / (dev_ms * 1e-3) / 1e12:.2f} TFLOP/s FP64 vs {proc.peak_tf:.1f} TFLOP/s cuBLAS DGEMM",
                      "traffic": None},
         "e2e": {"value": e2e_ms / max(lock_steps, 1), "unit": UNIT, "solve_ms": e2e_ms,
                 "h2d_bytes_per_step": 8.0 * 40 * nprog / max(lock_steps, 1) + 8.0 * 6 * nprog,
@@ -375,11 +443,17 @@ def run_b200_batched(args):
                 "note": "CONEXB200_BatchMaximize from host b to host y (wall clock / lock steps)"},
         "gpu_launches": int(launches), "clocks": clocks, "setup_s": setup_s,
     }
-    if not args.no_cpu_baseline:
+    if cpu_leg:
         line["cpu_baseline"] = cpu_baseline_batched(w)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def run_b200_batched(args):
+    proc = Process()
+    line = batched_bench(proc, args, workload_shape(args), cpu_leg=not args.no_cpu_baseline)
+    if line is not None:
+        print(json.dumps(line))
+    proc.close()
 
 
 # ---- structured path: entry-sparse operators through the incremental API ---------------------------
@@ -672,58 +746,75 @@ def run_reference(args):
                           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}))
         return
-    cb = cpu_baseline(w, args.steps, args.warmup)
+    if args.cpu_size:
+        w["cpu"] = dict(n=args.cpu_size, m=args.cpu_size)
+        w["cpu_check"] = dict(n=max(args.cpu_size // 2, 8), m=max(args.cpu_size // 2, 8))
+    # a step of the CPU sample takes 20-40 s at n = m = 1000: the run is bounded to 1 warm-up + 2 timed steps whatever
+    # K and W ask for (the line still carries the requested K / W, `sample_steps` what was run)
+    k_cpu, w_cpu = min(args.steps, 2), min(args.warmup, 1)
+    cb = cpu_baseline(w, k_cpu, w_cpu)
+    same = (w["cpu"]["n"], w["cpu"]["m"]) == (w["n"], w["m"])
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"],
+        "steps": args.steps, "warmup": args.warmup, "sample_steps": {"timed": k_cpu, "warmup": w_cpu},
+        "ms_per_step": cb["value"],
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": w["name"], "n": w["n"], "m": w["m"],
-                   "measured_on": f"n={w['cpu']['n']} m={w['cpu']['m']} sample, extrapolated"},
+                   "measured_on": ("the full shape" if same else
+                                   f"n={w['cpu']['n']} m={w['cpu']['m']} sample of the same workload (the full operator, "
+                                   f"{8e-9 * w['m'] * w['n'] ** 2:.0f} GB, and its as-written Gram do not fit a host run of minutes); "
+                                   "value = per-phase extrapolation by the work model, validated on a second size in "
+                                   "cpu_baseline.model_check")},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the DgemmKernel launches of ONE assembly phase of
+# the C2 Newton step, per assembly form, from `ncu --set full` captures (per launch x launches per phase);
+# None until a capture of that form exists.
+ASSEMBLY_TRAFFIC_C2 = {
+    1: dict(bytes=61 * (2.381e9 + 1.998e9) + 1.3545e12, source="profiles/r01_d_c2_dgemm_ncu_full.txt (classic form: 61 panels x "
+            "(K1a 2.38 GB + K1b 2.00 GB) + K2 1354.5 GB of tile re-reads at 36 % L2 hit)"),
+    3: None,
+}
+FORM_NAMES = {0: "undecided", 1: "classic (W A_i W kept)", 2: "row panels (classic, streamed)", 3: "symmetric (packed L^T A_i L)",
+              4: "entry-sparse gathers"}
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import conex_b200.binding as devlib
-    dev = devlib.product()
-    L = dev.lib
-    assert L.CONEXB200_DeviceAvailable() == 1, "no sm_100 device: conex-b200 has no CPU fallback"
 
-    w = workload_shape(args)
+def executed_assembly_flops(form, n, m):
+    """What the assembly kernels of each form execute (not the dense algorithmic count): symmetric form — A_i L with
+    the zeros of L skipped (n^3), lower tiles of L^T (A_i L) (n^3 / 3), Gram over the packed length Kp ~ 0.54 n^2 on the
+    lower triangle of the (m + 2)-row operand; classic — A_i W (2 n^3), lower half of W (A_i W) mirrored (n^3), Gram
+    m (m + 1) n^2."""
+    if form == 3:
+        t = (n + 63) // 64
+        kp = t * (t + 1) // 2 * 4096
+        return (4.0 / 3.0) * (m + 1) * n ** 3 + float(kp) * (m + 2) * (m + 3)
+    return 3.0 * (m + 1) * n ** 3 + float(m) * (m + 1) * n ** 2
+
+
+def dense_bench(proc, args, w, steps, warmup, full_solve, cpu_leg):
+    """One dense-LMI workload (c1 / c2 / c4 / c5) on all ranks; returns the JSON dict on rank 0, None elsewhere."""
+    torch, dist, dev, L, world, rank = proc.torch, proc.dist, proc.dev, proc.L, proc.world, proc.rank
     n, m = w["n"], w["m"]
     fl = algorithmic_flops(n, m)
-    peak_tf = measure_fp64_peak() if rank == 0 else None
 
     # ---- build the program with device-resident data (N > 1: this rank's shard of the rows) ----
     t_setup = time.perf_counter()
-    if world > 1:
-        devlib.init_communicator(dev, rank, world)
+    proc.communicator()
     configure_cholesky(L, args)
-    rb, rc = devlib.shard_range(dev, m, world, rank)
     P = dev.program()
     if args.assembly_mode:
         L.CONEXB200_SetAssemblyMode(P.h, args.assembly_mode)
-    pA, pC = C.c_void_p(), C.c_void_p()
-    cid = L.CONEXB200_NewDenseLMIConstraintStorage(P.h, n, m, C.byref(pA), C.byref(pC))
-    assert cid == 0, "allocation of the constraint matrices failed"
-    A = device_view(pA.value, rc * n * n).view(rc, n * n)
-    Cm = device_view(pC.value, n * n).view(n, n)
+    try:
+        A, Cm, rb, rc = P.dense_lmi_storage(n, m, world, rank)
+    except AssertionError as e:
+        return {"error": f"{w['name']}: {e}"} if rank == 0 else None
     b_local = fill_workload(w["kind"], n, m, rb, rc, A, Cm)
     torch.cuda.synchronize()
-    P.m = m
-    P.cone_shapes.append((n, n))
     del A, Cm
     torch.cuda.empty_cache()
     if world > 1:
@@ -734,12 +825,10 @@ def run_b200(args):
         b = b_local
     setup_s = time.perf_counter() - t_setup
 
-    total = args.warmup + args.steps
+    total = warmup + steps
     cfg = dev.default_config(max_iterations=total, final_centering_steps=0, inv_sqrt_mu_max=1e12)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    proc.barrier()
+    sampler = ClockSampler(proc.local_rank)
     sampler.start()
     t0 = time.perf_counter()
     solved, y = P.maximize(b, cfg)
@@ -755,17 +844,16 @@ def run_b200(args):
         ph = np.zeros(5)
         L.CONEXB200_GetIterationPhaseMilliseconds(P.h, i, ph.ctypes.data_as(C.POINTER(C.c_double)))
         phases.append(ph)
-    timed = np.array(step_ms[args.warmup:])
-    ph_timed = np.array(phases[args.warmup:]).mean(axis=0)
+    timed = np.array(step_ms[warmup:])
+    ph_timed = np.array(phases[warmup:]).mean(axis=0)
     log = P.iteration_log()
+    form = L.CONEXB200_GetAssemblyForm(P.h, 0)
 
     # ---- e2e: exactly K more Newton steps through the C ABI with host buffers (warm start) ----
-    cfg_e2e = dev.default_config(max_iterations=args.steps, final_centering_steps=0,
+    cfg_e2e = dev.default_config(max_iterations=steps, final_centering_steps=0,
                                  inv_sqrt_mu_max=1e12, initialization_mode=1)
     launches0 = L.CONEXB200_LaunchCount()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    proc.barrier()
     t0 = time.perf_counter()
     P.maximize(b, cfg_e2e)
     torch.cuda.synchronize()
@@ -778,28 +866,48 @@ def run_b200(args):
         e2e_step_ms.append(round(float(ms[0]), 3))
     clocks = sampler.stop()
 
+    # ---- IPM solve time: a cold-start solve with the DEFAULT configuration, run to termination ----
+    solve = None
+    if full_solve:
+        proc.barrier()
+        t0 = time.perf_counter()
+        s_full, y_full = P.maximize(b, dev.default_config())
+        torch.cuda.synchronize()
+        solve_wall = time.perf_counter() - t0
+        flog = P.iteration_log()
+        solve_its = P.status()["num_iterations"]
+        dev_total = 0.0
+        for i in range(solve_its):
+            L.CONEXB200_GetIterationMilliseconds(P.h, i, ms.ctypes.data_as(C.POINTER(C.c_double)))
+            dev_total += float(ms[0])
+        solve_wall_max, dev_total = proc.max_over_ranks([solve_wall, dev_total])
+        solve = {"solve_ms": solve_wall_max * 1e3, "solve_device_ms": dev_total, "solve_iterations": solve_its,
+                 "solved": int(s_full), "by": flog[-1]["by"], "cx": flog[-1]["cx"], "mu": flog[-1]["mu"],
+                 "note": "CONEX_Maximize, default CONEX_SolverConfiguration, cold start, host b -> host y (wall clock, "
+                         "max over ranks)"}
+
     value = float(timed.mean())
     e2e_ms = e2e_wall * 1e3 / e2e_its
-    if world > 1:
-        t = torch.tensor([value, e2e_ms] + ph_timed.tolist(), dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        value, e2e_ms = float(t[0]), float(t[1])
-        ph_timed = t[2:].cpu().numpy()
-        L.CONEXB200_CommDestroy()
+    red = proc.max_over_ranks([value, e2e_ms] + ph_timed.tolist())
+    value, e2e_ms, ph_timed = red[0], red[1], np.array(red[2:])
+    del P
+    proc.release()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     asm_ms = float(ph_timed[0])
-    asm_flops = fl["k1"] + fl["k2"]
-    achieved = asm_flops / (asm_ms * 1e-3) / 1e12
+    dense_flops = fl["k1"] + fl["k2"]
+    exec_flops = executed_assembly_flops(form, n, m)
+    achieved = exec_flops / (asm_ms * 1e-3) / 1e12
+    peak = proc.peak_tf * world
+    traffic = ASSEMBLY_TRAFFIC_C2.get(form) if (w["kind"], n, m, world) == ("maxcut", 2000, 2000, 1) else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["name"], "n": n, "m": m,
                    "path": f"dense-LMI path of the C ABI (dense A_i, {8e-9 * m * n * n:.1f} GB resident)",
+                   "assembly_form": FORM_NAMES.get(form, str(form)),
                    "l2": f"inputs ({8e-9 * m * n * n:.1f} GB) vs 126 MB L2: " +
                          ("no flush needed" if 8.0 * m * n * n > 4 * 126e6 else "L2-resident workload"),
                    "multi_gpu": (f"one Newton step sharded over {world} ranks: constraint matrices and the rows "
@@ -809,42 +917,73 @@ def run_b200(args):
         "newton_steps_per_s": 1e3 / value,
         "step_tflops_fp64": fl["tensor"] / (value * 1e-3) / 1e12,
         "phase_ms": dict(zip(["assemble", "factor", "mu", "solve", "update"], ph_timed.tolist())),
-        "phase_ms_per_step": [[round(float(v), 3) for v in ph] for ph in phases[args.warmup:]],
+        "phase_ms_per_step": [[round(float(v), 3) for v in ph] for ph in phases[warmup:]],
         "roofline": {
             "bound": "tensor", "kernel": "DgemmKernel (K1 scaling GEMMs + K2 Gram, Schur assembly phase)",
-            "achieved": achieved, "peak": peak_tf * world, "unit": "TFLOP/s",
-            "frac": achieved / (peak_tf * world),
-            "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run, times n_gpus "
-                           "(MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 tensor = 37 TFLOP/s). "
-                           "achieved counts the reference's dense flops (4mn^3 + m(m+1)n^2); the kernel "
-                           "executes 3mn^3 + m(m+1)n^2 because W(A_i W) is symmetric, so frac can exceed 1",
-            "algorithmic_flops_per_step": asm_flops,
-            # what the default (symmetric) form actually executes: A_i L with the zeros of L skipped (n^3),
-            # lower tiles of L^T (A_i L) (n^3 / 3), Gram over the packed length 0.54 n^2, lower triangle
-            "executed_flops_per_step_if_symmetric_form": (4.0 / 3.0) * m * n ** 3 + 0.54 * float(m) * (m + 1) * n ** 2,
-            "achieved_on_executed_flops_if_symmetric_form": ((4.0 / 3.0) * m * n ** 3 + 0.54 * float(m) * (m + 1) * n ** 2) / (asm_ms * 1e-3) / 1e12,
-            "frac_on_executed_flops_if_symmetric_form": ((4.0 / 3.0) * m * n ** 3 + 0.54 * float(m) * (m + 1) * n ** 2) / (asm_ms * 1e-3) / 1e12 / (peak_tf * world),
-            "traffic": ASSEMBLY_TRAFFIC_C2 if (w["kind"], n, m, world) == ("maxcut", 2000, 2000, 1) else None,
-            "traffic_note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of all DgemmKernel launches of one "
-                            "assembly phase, from profiles/r01_d_c2_dgemm_ncu_full.txt: 61 panels x (K1a 2.38 GB + K1b "
-                            "2.00 GB) + K2 1354.5 GB (tile re-reads of the two 64 GB operands at 36 % L2 hit; the kernel "
-                            "runs at 92.8 % DMMA-pipe active, so tensor-bound); algorithmic minimum 256 GB",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run, times n_gpus (MEASURED_PEAKS.json has no FP64 "
+                           "figure; nominal B200 FP64 tensor = 37 TFLOP/s)",
+            "flops_counted": "EXECUTED flops of the assembly form in use (executed_flops_per_step) over the CUDA-event time "
+                             "of the assembly phase — a hardware fraction",
+            "executed_flops_per_step": exec_flops,
+            "algorithmic_flops_per_step": dense_flops,
+            "algorithmic_speedup": dense_flops / exec_flops,
+            "achieved_on_algorithmic_flops": dense_flops / (asm_ms * 1e-3) / 1e12,
+            "algorithmic_note": "SURVEY.md 8(d) dense count 4mn^3 + m(m+1)n^2 (what the reference's formulation executes); "
+                                "algorithmic_speedup is the saving of the assembly form, reported separately from frac",
+            "traffic": traffic["bytes"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else "no ncu --set full capture of this form / shape",
         },
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * m / e2e_its,
                 "d2h_bytes_per_step": 8 * m / e2e_its + 8 * (2 * (n // 2 + 2) + 8) * 2 + 4 * 8 + 4,
                 "device_step_ms": e2e_step_ms, "wall_ms": e2e_wall * 1e3,
-                "note": "CONEX_Maximize warm-start solve of K steps from host b to host y; "
-                        "per-step D2H = Lanczos coefficients + scalars"},
+                "note": "CONEX_Maximize warm-start solve of K steps from host b to host y; per-step D2H = Lanczos "
+                        "coefficients + scalars. The operator itself is generated in place in library-owned HBM "
+                        "(CONEXB200_NewDenseLMIConstraintStorage) once per program: setup_s; it is not re-sent per step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "setup_s": setup_s, "first_solve_wall_s": wall_cold,
         "final": {"by": log[-1]["by"], "cx": log[-1]["cx"], "mu": log[-1]["mu"]},
     }
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(w, 2, 1)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if solve:
+        line["solve"] = solve
+        line["solve_ms"], line["solve_iterations"], line["solved"] = solve["solve_ms"], solve["solve_iterations"], solve["solved"]
+    if cpu_leg:
+        line["cpu_baseline"] = cpu_baseline(w, 2, 1, sample_key="cpu_small")
+    return line
+
+
+def compact(line):
+    """The keys of a secondary workload's record that go inside the main JSON line."""
+    if line is None or "error" in line:
+        return line
+    keep = ("value", "unit", "n_gpus", "steps", "warmup", "config", "phase_ms", "solve_ms", "programs_per_s",
+            "programs_solved", "step_tflops_fp64", "gpu_launches")
+    out = {k: line[k] for k in keep if k in line}
+    out["roofline"] = {k: line["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac") if k in line["roofline"]}
+    out["e2e"] = {k: line["e2e"][k] for k in ("value", "unit") if k in line["e2e"]}
+    return out
+
+
+def run_b200(args):
+    proc = Process()
+    w = workload_shape(args)
+    line = dense_bench(proc, args, w, args.steps, args.warmup, full_solve=not args.no_full_solve,
+                       cpu_leg=not args.no_cpu_baseline and proc.rank == 0 and proc.world == 1)
+    if args.workload == "c2" and not args.no_extra and not args.n and not args.m:
+        # The other two shapes the north star quotes scaling on ride along in the same JSON line, so that the driver's
+        # 1/2/4/8-GPU runs carry them: C5 (n = 1000, m = 20000; multi-GPU Cholesky on) and C3 (4096 small programs).
+        c5w = workload_shape(argparse.Namespace(workload="c5", n=0, m=0, programs=0))
+        c5 = dense_bench(proc, args, c5w, 2, 1, full_solve=False, cpu_leg=False)
+        c3w = workload_shape(argparse.Namespace(workload="c3", n=0, m=0, programs=0))
+        c3 = batched_bench(proc, args, c3w, cpu_leg=False)
+        if line is not None:
+            line["c5"] = compact(c5)
+            line["c5"]["note"] = "1 warm-up + 2 timed Newton steps (a step is 1.3-14 s at this shape)"
+            line["c3"] = compact(c3)
+    if line is not None:
+        print(json.dumps(line))
+    proc.close()
 
 
 def main():
@@ -860,6 +999,9 @@ def main():
     ap.add_argument("--assembly-mode", type=int, default=0, help="0 auto, 1 classic (keep all W A_i W), 2 stream row panels, 3 symmetric form (packed L^T A_i L)")
     ap.add_argument("--programs", type=int, default=0, help="c3: number of programs in the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-solve", action="store_true", help="skip the default-configuration solve to termination")
+    ap.add_argument("--no-extra", action="store_true", help="c2: skip the C5 and C3 blocks that ride along in the line")
+    ap.add_argument("--cpu-size", type=int, default=0, help="override n = m of the CPU sample (testing)")
     ap.add_argument("--replicated-cholesky", action="store_true",
                     help="N > 1: factor the Schur complement on every rank instead of across the ranks")
     ap.add_argument("--cholesky-block", type=int, default=0, help="N > 1: block-column width (<= 512)")

@@ -647,6 +647,18 @@ int CONEXB200_ConstraintIsEntrySparse(void* prog, int id) {
   return -1;
 }
 
+int CONEXB200_GetAssemblyForm(void* prog, int id) {
+  Program& program = *static_cast<Program*>(prog);
+  int k = 0;
+  for (auto& c : program.eqs) {
+    if (k++ != id) continue;
+    if (auto* h = std::any_cast<conex::HermitianPsdConstraint>(&c.obj)) return h->assembly_form();
+    if (auto* d = std::any_cast<conex::DenseLMIConstraint>(&c.obj)) return d->assembly_form();
+    return -1;
+  }
+  return -1;
+}
+
 int CONEXB200_SizeOfKKTSystem(void* prog) { return static_cast<Program*>(prog)->SizeOfKKTSystem(); }
 
 // Host-logic probe: pivot order of the regularised LDL^T from the diagonal (RLDLT.h:328-356).

@@ -112,6 +112,14 @@ DenseLMIConstraint::DenseLMIConstraint(int n, int m, EntrySparse)
 
 bool DenseLMIConstraint::entry_sparse() const { return data_->sparse; }
 
+int DenseLMIConstraint::assembly_form() const {
+  const Storage& d = *data_;
+  if (d.panel == 0) return 0;  // not decided yet (EnsureScratch runs at the first assembly)
+  if (d.sparse) return 4;
+  if (d.symmetric) return 3;
+  return d.streamed ? 2 : 1;
+}
+
 namespace {
 template <typename T>
 void UploadVector(DeviceBuffer<T>* dst, const std::vector<T>& src) {

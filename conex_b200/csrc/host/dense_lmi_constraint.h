@@ -74,6 +74,9 @@ class DenseLMIConstraint {
   // Dense storage for a block created with the EntrySparse constructor (allocated on first use).
   void LoadDense(const std::vector<Entry>& lower_entries, const double* C);
   bool entry_sparse() const;
+  // How this block assembles its Schur complement: 0 undecided (before the first assembly), 1 classic
+  // (all W A_i W kept), 2 row panels, 3 symmetric (packed L^T A_i L), 4 entry-sparse gathers.
+  int assembly_form() const;
   // Switches the eigen-bound and the exponential to the rules of the reference's incremental LMI
   // (HermitianPsdConstraint<Real>, conex/hermitian_psd.cc): Lanczos started from an Eigen-style
   // Random(n, 1) vector drawn with libc rand(), n/2 + 1 steps, relative breakdown test

@@ -135,6 +135,9 @@ int CONEXB200_AddEqualityConstraint(void* prog, int rows, int nvars, const doubl
  * form and assembled by gathers from W, 0 when it is dense, -1 for other constraint types. Valid after
  * the first solve. */
 int CONEXB200_ConstraintIsEntrySparse(void* prog, int id);
+/* The form in which LMI constraint `id` assembles its Schur complement (CONEXB200_SetAssemblyMode; decided at the
+ * first assembly): 0 undecided, 1 classic, 2 row panels, 3 symmetric, 4 entry-sparse gathers; -1 for other cones. */
+int CONEXB200_GetAssemblyForm(void* prog, int id);
 /* ---- chordal-sparse programs: cones on overlapping subsets of the variables (reference
  * SupernodalKKTSolver, kkt_solver.h:16-65 + clique_ordering.cc + block_triangular_operations.cc) -----
  * kind 0 (default): decide from the cones' variable sets — the multifrontal solver
