@@ -677,6 +677,82 @@ CXB_HD void ExtremeTridiagonal(const double* a, const double* b, int k, double* 
   *emax = SturmKth(a, b, k, k - 1, lo, hi, tiny);
 }
 
+// The same two eigenvalues by multi-section with the whole team: every round evaluates the Sturm count at
+// kSections interior points of each of the two brackets at once (one point per thread) and keeps the
+// sub-interval that still holds the wanted eigenvalue, so a bracket shrinks by kSections + 1 per round
+// (12 rounds to full double precision) instead of by 2 per serial bisection step (60 - 200 steps of k
+// dependent divisions on ONE thread — that serial section used to be most of the time of the batched
+// eigen-bound kernels). Converges to the same eigenvalues as ExtremeTridiagonal up to the final bracket width.
+// scratch: 2 * kSections + 8 doubles.
+constexpr int kSections = 32;
+template <class T>
+CXB_HD void ExtremeTridiagonalTeam(T& t, const double* a, const double* b, int k, double* scratch, double* emin,
+                                   double* emax) {
+  if (k == 1) {
+    t.single([&]() { *emin = *emax = a[0]; });
+    return;
+  }
+  double* cnt = scratch;                  // [2][kSections] Sturm counts (as doubles)
+  double* br = scratch + 2 * kSections;   // lo_min, hi_min, lo_max, hi_max, tiny, done_min, done_max
+  t.single([&]() {
+    const double eps = 2.220446049250313e-16;
+    double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308, scale = 0;
+    for (int i = 0; i < k; i++) {
+      const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < k ? fabs(b[i]) : 0.0);
+      lo = fmin(lo, a[i] - r);
+      hi = fmax(hi, a[i] + r);
+      scale = fmax(scale, fabs(a[i]) + r);
+    }
+    const double pad = 4 * eps * (scale + 1e-300) * (double)k;
+    lo -= pad;
+    hi += pad;
+    double tiny = 2.2250738585072014e-308 / eps + 1e-30 * scale * scale;
+    tiny = fmax(tiny, eps * eps * scale);
+    br[0] = br[2] = lo;
+    br[1] = br[3] = hi;
+    br[4] = tiny;
+    br[5] = br[6] = 0.0;
+  });
+  for (int round = 0; round < 64; round++) {
+    if (br[5] != 0.0 && br[6] != 0.0) break;  // uniform: read after the barrier that ends the last phase
+    t.par(2 * kSections, [&](int e) {
+      const int side = e / kSections, q = e % kSections;
+      if (br[5 + side] != 0.0) return;
+      const double lo = br[2 * side], hi = br[2 * side + 1];
+      const double x = lo + (hi - lo) * ((double)(q + 1) / (double)(kSections + 1));
+      cnt[e] = (double)SturmCountBelow(a, b, k, x, br[4]);
+    });
+    t.single([&]() {
+      for (int side = 0; side < 2; side++) {
+        if (br[5 + side] != 0.0) continue;
+        const int which = side == 0 ? 0 : k - 1;
+        const double lo = br[2 * side], hi = br[2 * side + 1];
+        const double first = lo + (hi - lo) * (1.0 / (double)(kSections + 1));
+        const double last = lo + (hi - lo) * ((double)kSections / (double)(kSections + 1));
+        if (!(first > lo) || !(last < hi)) {  // the interior points no longer resolve the bracket: converged
+          br[5 + side] = 1.0;
+          continue;
+        }
+        double nlo = lo, nhi = hi;
+        for (int q = 0; q < kSections; q++) {
+          const double x = lo + (hi - lo) * ((double)(q + 1) / (double)(kSections + 1));
+          if ((int)cnt[side * kSections + q] > which) {
+            nhi = x;
+            break;
+          }
+          nlo = x;
+        }
+        br[2 * side] = nlo;
+        br[2 * side + 1] = nhi;
+      }
+    });
+  }
+  t.single([&]() {
+    *emin = 0.5 * (br[0] + br[1]);
+    *emax = 0.5 * (br[2] + br[3]);
+  });
+}
+
 // Two-sided Lanczos on (WS, WS^T) in the W inner product started from r
 // (approximate_eigenvalues.cc:178-239, num_iter = n/2, breakdown beta^2 < 1e-6), then the extreme
 // Ritz values. vec: 6 n + 2 (n/2 + 2) doubles of scratch. Returns through ritz[0..1].
@@ -739,7 +815,7 @@ CXB_HD void LanczosExtremes(T& t, int n, const double* WS, const double* W, cons
     t.single([&]() { beta[j] = bj; });
     bprev = bj;
   }
-  t.single([&]() { ExtremeTridiagonal(alpha, beta, count + 1, ritz + 0, ritz + 1); });
+  ExtremeTridiagonalTeam(t, alpha, beta, count + 1, beta + n / 2 + 2, ritz + 0, ritz + 1);
 }
 
 // S -> T1, WS = W S -> T2 (global state) and shared copies; returns tr(WS), tr(WS WS) and the

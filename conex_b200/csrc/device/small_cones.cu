@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "device_api.h"
 #include "small_cone_math.cuh"
+#include "small_psd_mma.cuh"
 #include "team.cuh"
 
 namespace cxb {
@@ -29,8 +30,9 @@ ConeArgs Convert(const cxb_small_cone* c) {
                   c->work_stride};
 }
 
-// Shared memory (doubles) needed by the PSD paths: 6 n^2 matrices + Lanczos vectors + slack.
-size_t PsdSmemDoubles(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64; }
+// Shared memory (doubles) needed by the PSD paths: 6 n^2 matrices + Lanczos vectors + slack + the scratch of the
+// multi-section eigenvalue brackets.
+size_t PsdSmemDoubles(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64 + 2 * small::kSections + 16; }
 size_t SmemBytes(const ConeArgs& c) {
   return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? PsdSmemDoubles(c.n) : 0));
 }
@@ -76,6 +78,20 @@ __global__ void __launch_bounds__(kThreads) SchurKernel(ConeArgs c, double* G, l
   } else {
     small::PsdSchur(t, c.n, c.m, data, st, work, sm + 64, g, ldg, aw, aq, sc, acc);
   }
+}
+
+// Dense LMI blocks of order n <= 32, n % 4 == 0: the DMMA kernel of small_psd_mma.cuh (one CTA of 8 warps per
+// program, scaled matrices kept in shared memory).
+__global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArgs c, double* G, long ldg, long gstride,
+                                                                       double* AW, double* AQc, long vstride,
+                                                                       double* scal, long sstride, int accumulate,
+                                                                       const int* active) {
+  extern __shared__ __align__(16) double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  psdmma::PsdSchurMma(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride,
+                      c.work + p * c.work_stride, sm, G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride,
+                      scal + p * sstride, accumulate != 0);
 }
 
 __global__ void __launch_bounds__(kThreads) EigenKernel(ConeArgs c, const double* y, long ystride,
@@ -202,6 +218,8 @@ int EnsureSmem(K kernel, size_t bytes) {
   return 0;
 }
 
+int g_small_psd_mma = 1;  // cxb_set_small_psd_mma(0): A/B switch back to the DFMA team kernel
+
 bool ValidCone(const cxb_small_cone* c) {
   if (!c || c->n < 1 || c->m < 1 || !c->data || !c->state) return false;
   if (c->type == CXB_CONE_LP) return true;
@@ -243,6 +261,15 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
+  size_t mma_smem = 0;
+  if (c.type == CXB_CONE_PSD && g_small_psd_mma && psdmma::Supported(c.n, c.m, &mma_smem) &&
+      (c.data_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0) {
+    int rc = EnsureSmem(PsdSchurMmaKernel, mma_smem);
+    if (rc) return rc;
+    CountLaunch(); PsdSchurMmaKernel<<<batch, psdmma::kThreads, mma_smem, AsStream(stream)>>>(
+        c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
+    return LaunchStatus();
+  }
   const size_t smem = SchurSmemBytes(c);
   int rc = EnsureSmem(SchurKernel, smem);
   if (rc) return rc;
@@ -250,6 +277,8 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
                                                             d_scal, sstride, accumulate, d_active);
   return LaunchStatus();
 }
+
+void cxb_set_small_psd_mma(int enabled) { g_small_psd_mma = enabled; }
 
 int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const double* dy, long ystride,
                     double c_weight, const double* d_cw, double* d_out4, long ostride,

@@ -1,0 +1,312 @@
+// Schur complement of one small dense LMI block on the FP64 tensor cores (DMMA m8n8k4), one CTA per program:
+// the batched counterpart of device/schur.cu for blocks of order n <= 32 (BASELINE config 3: n = 20, m = 40).
+//
+//   phase 0  cp.async of the whole cone data [A_0 .. A_{m-1} C] (n^2 doubles each) into shared memory, in commit
+//            groups of one matrix per warp; meanwhile warp 0 factors W = L L^T (left-looking, one lane per row);
+//   phase A  every warp takes the matrices i = warp, warp + W, ...:  T = A_i L (k-steps above L's diagonal
+//            skipped), written in place over A_i;  S = L^T T, lower tiles only (k-steps left of L^T's diagonal
+//            skipped), packed into row i of X (lower triangle, off-diagonal entries scaled by sqrt 2, so that the
+//            plain dot product of two rows is the trace inner product). Row m + 1 of X is the packed identity;
+//   phase B  Gram  X X^T  (lower) in 16 x 16 blocks of four DMMA tiles, the packed length split across warps;
+//            partial blocks are summed in a fixed order (deterministic) and written to G / AQc / AW / scal with the
+//            conventions of small::PsdSchur (row m: <S_C, S_j>, row m + 1: <I, S_j>).
+// Nothing but the cone data is read from HBM and nothing but the m (m + 1) / 2 + 2 m + 2 results is written: the
+// scaled matrices never leave shared memory (the DFMA kernel this replaces round-tripped them through HBM and
+// spent its time in ~80 barrier-separated phases).
+// If W is not numerically positive definite the CTA falls back to small::PsdSchurClassic (the reference's formula).
+#pragma once
+#include "common.cuh"
+#include "small_cone_math.cuh"
+#include "team.cuh"
+
+namespace cxb {
+namespace psdmma {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+// smallest p >= x with p == 4 (mod 16): row pitch (doubles) that makes the 8 x 4 / 4 x 8 DMMA fragment loads
+// bank-conflict free in both orientations
+__host__ __device__ inline int Pitch4Mod16(int x) {
+  int p = (x + 15) / 16 * 16 + 4;
+  if (p - 16 >= x) p -= 16;
+  return p;
+}
+
+struct Layout {
+  int n, m, kp, k4, pa, pl, px, nblk, ksplit;
+  long off_l, off_x, off_a, off_p, total;  // doubles, after the 64-double reduction scratch
+};
+
+__host__ __device__ inline Layout MakeLayout(int n, int m) {
+  Layout y;
+  y.n = n;
+  y.m = m;
+  y.kp = n * (n + 1) / 2;
+  y.k4 = (y.kp + 3) / 4 * 4;
+  y.pa = Pitch4Mod16(n);
+  y.pl = Pitch4Mod16(n);
+  y.px = Pitch4Mod16(y.k4);
+  const int mt = (m + 2 + 7) / 8;
+  const int nb = (mt + 1) / 2;
+  y.nblk = nb * (nb + 1) / 2;
+  y.ksplit = (2 * kWarps + y.nblk - 1) / y.nblk;
+  if (y.ksplit < 1) y.ksplit = 1;
+  if (y.ksplit > 8) y.ksplit = 8;
+  const long a_size = (long)(m + 1) * n * y.pa + 16;
+  const long p_size = (long)y.ksplit * y.nblk * 256;
+  y.off_l = 64;
+  y.off_x = y.off_l + (long)n * y.pl + 16;
+  y.off_a = y.off_x + (long)(m + 2) * y.px;
+  y.off_p = y.off_a;  // the partial Gram blocks reuse the operator's space
+  y.total = y.off_a + (a_size > p_size ? a_size : p_size);
+  return y;
+}
+
+__host__ inline bool Supported(int n, int m, size_t* smem_bytes) {
+  if (n < 4 || n > 32 || (n % 4) != 0 || m < 1 || m + 2 > 1024) return false;
+  const Layout y = MakeLayout(n, m);
+  // the fallback (classic form, team code) runs in the same dynamic shared memory
+  const long fallback = 64 + small::PsdSchurSmemDoubles(n, m, kThreads);
+  const long total = y.total > fallback ? y.total : fallback;
+  *smem_bytes = sizeof(double) * (size_t)total;
+  return *smem_bytes <= 227 * 1024;
+}
+
+__device__ __forceinline__ void WaitPending(int pending) {
+  // cp.async.wait_group takes an immediate: at most `pending` groups may still be in flight
+  switch (pending < 0 ? 0 : (pending > 7 ? 7 : pending)) {
+    case 0: CpAsyncWait<0>(); break;
+    case 1: CpAsyncWait<1>(); break;
+    case 2: CpAsyncWait<2>(); break;
+    case 3: CpAsyncWait<3>(); break;
+    case 4: CpAsyncWait<4>(); break;
+    case 5: CpAsyncWait<5>(); break;
+    case 6: CpAsyncWait<6>(); break;
+    default: CpAsyncWait<7>(); break;
+  }
+}
+
+// AC: (m + 1) column-major n x n matrices; W: n x n (global). sm: dynamic shared memory (MakeLayout(n, m).total
+// doubles, at least the fallback's size). work: global scratch of the classic fallback.
+__device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, const double* __restrict__ W,
+                                   double* work, double* sm, double* G, long ldg, double* AW, double* AQc,
+                                   double* scal, bool acc) {
+  const Layout y = MakeLayout(n, m);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nn = n * n, pa = y.pa, pl = y.pl, px = y.px, kp = y.kp;
+  double* sL = sm + y.off_l;   // L row-major: L(k, c) at sL[k * pl + c], zeros above the diagonal
+  double* sX = sm + y.off_x;   // packed scaled matrices, row i at sX[i * px]
+  double* sA = sm + y.off_a;   // matrix i, column c at sA[(i * n + c) * pa]
+  double* sP = sm + y.off_p;
+  int* s_fail = reinterpret_cast<int*>(sm + 40);
+
+  // ---- phase 0: operator in flight, L = chol(W) ------------------------------------------------------------
+  const int rounds = (m + 1 + kWarps - 1) / kWarps;
+  {
+    const int half = n / 2;  // 16-byte chunks per column
+    for (int r = 0; r < rounds; r++) {
+      const int i0 = r * kWarps;
+      const int cnt = min(kWarps, m + 1 - i0);
+      const int chunks = cnt * n * half;
+      const double* src = AC + (long)i0 * nn;
+      double* dst = sA + (long)i0 * n * pa;
+      for (int q = tid; q < chunks; q += kThreads) {
+        const int col = q / half, within = q - col * half;
+        CpAsync16(dst + (long)col * pa + 2 * within, src + (long)col * n + 2 * within, 16);
+      }
+      CpAsyncCommit();
+    }
+  }
+  if (tid == 0) *s_fail = 0;
+  for (int e = tid; e < n * pl + 16; e += kThreads) {
+    const int k = e / pl, c = e - k * pl;
+    sL[e] = (k < n && c <= k && c < n) ? W[(long)c * n + k] : 0.0;
+  }
+  // zero padding of the packed rows and the packed identity (row m + 1)
+  for (int e = tid; e < (m + 2) * (px - kp); e += kThreads) {
+    const int row = e / (px - kp), q = kp + e % (px - kp);
+    sX[(long)row * px + q] = 0.0;
+  }
+  for (int e = tid; e < kp; e += kThreads) sX[(long)(m + 1) * px + e] = 0.0;
+  __syncthreads();
+  for (int c = tid; c < n; c += kThreads) sX[(long)(m + 1) * px + c * n - c * (c - 1) / 2] = 1.0;
+  if (warp == 0) {
+    // left-looking Cholesky, lane = row
+    const int r = lane;
+    bool bad = false;
+    for (int j = 0; j < n; j++) {
+      double v0 = (r >= j && r < n) ? sL[r * pl + j] : 0.0, v1 = 0.0;
+      if (r >= j && r < n) {
+        int k = 0;
+        for (; k + 1 < j; k += 2) {
+          v0 -= sL[r * pl + k] * sL[j * pl + k];
+          v1 -= sL[r * pl + k + 1] * sL[j * pl + k + 1];
+        }
+        if (k < j) v0 -= sL[r * pl + k] * sL[j * pl + k];
+      }
+      const double v = v0 + v1;
+      const double d = __shfl_sync(0xffffffffu, v, j);
+      if (!(d > 0.0)) {
+        bad = true;
+        break;
+      }
+      const double rd = sqrt(d);
+      if (r >= j && r < n) sL[r * pl + j] = (r == j) ? rd : v / rd;
+      __syncwarp();
+    }
+    if (bad && lane == 0) *s_fail = 1;
+  }
+  __syncthreads();
+  if (*s_fail) {
+    CpAsyncWait<0>();
+    __syncthreads();
+    DeviceTeam t(sm);
+    small::PsdSchurClassic(t, n, m, AC, W, work, sm + 64, G, ldg, AW, AQc, scal, acc);
+    return;
+  }
+
+  // ---- phase A: S_i = L^T (A_i L), packed ------------------------------------------------------------------
+  const int nt = (n + 7) / 8;  // 8-wide tiles per side (the last one may be ragged: its extra rows / columns
+                               // re-read row / column n - 1 and are never stored)
+  const double kSqrt2 = 1.4142135623730951;
+  for (int r = 0; r < rounds; r++) {
+    WaitPending(rounds - 1 - r);
+    __syncthreads();
+    const int i = r * kWarps + warp;
+    if (i > m) continue;
+    double* Ai = sA + (long)i * n * pa;
+    double accT[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) accT[a][b][0] = accT[a][b][1] = 0.0;
+    // T = A_i L: a = A(r0 + gid, k + tig) = Ai[(k + tig) * pa + r0 + gid] (A_i symmetric, column-major),
+    //            b = L(k + tig, c0 + gid)
+#pragma unroll
+    for (int tc = 0; tc < 4; tc++) {
+      if (tc >= nt) break;
+      for (int k = tc * 8; k < n; k += 4) {
+        const double b = sL[(k + tig) * pl + min(tc * 8 + gid, n - 1)];
+#pragma unroll
+        for (int tr = 0; tr < 4; tr++) {
+          if (tr >= nt) break;
+          const double a = Ai[(k + tig) * pa + min(tr * 8 + gid, n - 1)];
+          Dmma884(accT[tr][tc][0], accT[tr][tc][1], a, b);
+        }
+      }
+    }
+    __syncwarp();
+    // T(row, col) -> Ai[row * pa + col] (row = the k index of the next product)
+#pragma unroll
+    for (int tr = 0; tr < 4; tr++) {
+      if (tr >= nt) break;
+#pragma unroll
+      for (int tc = 0; tc < 4; tc++) {
+        if (tc >= nt) break;
+        const int row = tr * 8 + gid, col = tc * 8 + tig * 2;
+        if (row < n) {
+          if (col < n) Ai[row * pa + col] = accT[tr][tc][0];
+          if (col + 1 < n) Ai[row * pa + col + 1] = accT[tr][tc][1];
+        }
+      }
+    }
+    __syncwarp();
+    // S = L^T T, tiles on or below the diagonal: a = L(k + tig, r0 + gid), b = T(k + tig, c0 + gid); L(k, r) = 0
+    // for k < r: the k loop starts at the tile's first row
+    double* Xi = sX + (long)i * px;
+#pragma unroll
+    for (int tr = 0; tr < 4; tr++) {
+      if (tr >= nt) break;
+      double accS[4][2];
+#pragma unroll
+      for (int b = 0; b < 4; b++) accS[b][0] = accS[b][1] = 0.0;
+      for (int k = tr * 8; k < n; k += 4) {
+        const double a = sL[(k + tig) * pl + min(tr * 8 + gid, n - 1)];
+#pragma unroll
+        for (int tc = 0; tc < 4; tc++) {
+          if (tc > tr) break;
+          const double b = Ai[(k + tig) * pa + min(tc * 8 + gid, n - 1)];
+          Dmma884(accS[tc][0], accS[tc][1], a, b);
+        }
+      }
+#pragma unroll
+      for (int tc = 0; tc < 4; tc++) {
+        if (tc > tr) break;
+        const int row = tr * 8 + gid;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int col = tc * 8 + tig * 2 + e;
+          if (row < n && col <= row) {
+            Xi[col * n - col * (col - 1) / 2 + (row - col)] = (row == col) ? accS[tc][e] : kSqrt2 * accS[tc][e];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();  // X complete; the operator's space is free for the partial blocks
+
+  // ---- phase B: Gram X X^T (lower), 16 x 16 blocks, packed length split across warps -----------------------
+  const int MI = m + 2, MJ = m + 1;
+  const int nb = ((MI + 7) / 8 + 1) / 2;
+  const int ksteps = y.k4 / 4;
+  const int per = (ksteps + y.ksplit - 1) / y.ksplit;
+  for (int task = warp; task < y.nblk * y.ksplit; task += kWarps) {
+    const int blk = task % y.nblk, ks = task / y.nblk;
+    int bj = 0, rem = blk;
+    while (rem >= nb - bj) {
+      rem -= nb - bj;
+      bj++;
+    }
+    const int bi = bj + rem;
+    const double* xa0 = sX + (long)min(16 * bi + gid, MI - 1) * px + tig;
+    const double* xa1 = sX + (long)min(16 * bi + 8 + gid, MI - 1) * px + tig;
+    const double* xb0 = sX + (long)min(16 * bj + gid, MI - 1) * px + tig;
+    const double* xb1 = sX + (long)min(16 * bj + 8 + gid, MI - 1) * px + tig;
+    double c00[2] = {0, 0}, c01[2] = {0, 0}, c10[2] = {0, 0}, c11[2] = {0, 0};
+    const int kbeg = ks * per, kend = min(ksteps, kbeg + per);
+    for (int k = kbeg; k < kend; k++) {
+      const double a0 = xa0[4 * k], a1 = xa1[4 * k], b0 = xb0[4 * k], b1 = xb1[4 * k];
+      Dmma884(c00[0], c00[1], a0, b0);
+      Dmma884(c01[0], c01[1], a0, b1);
+      Dmma884(c10[0], c10[1], a1, b0);
+      Dmma884(c11[0], c11[1], a1, b1);
+    }
+    // block stored column-major 16 x 16: entry (row, col) at [col * 16 + row]
+    double* P = sP + ((long)ks * y.nblk + blk) * 256;
+    const int col = tig * 2;
+    P[(col + 0) * 16 + gid] = c00[0];
+    P[(col + 1) * 16 + gid] = c00[1];
+    P[(col + 8) * 16 + gid] = c01[0];
+    P[(col + 9) * 16 + gid] = c01[1];
+    P[(col + 0) * 16 + 8 + gid] = c10[0];
+    P[(col + 1) * 16 + 8 + gid] = c10[1];
+    P[(col + 8) * 16 + 8 + gid] = c11[0];
+    P[(col + 9) * 16 + 8 + gid] = c11[1];
+  }
+  __syncthreads();
+  for (int e = tid; e < y.nblk * 256; e += kThreads) {
+    const int blk = e >> 8, in = e & 255;
+    int bj = 0, rem = blk;
+    while (rem >= nb - bj) {
+      rem -= nb - bj;
+      bj++;
+    }
+    const int bi = bj + rem;
+    const int i = 16 * bi + (in & 15), j = 16 * bj + (in >> 4);
+    if (i >= MI || j >= MJ || i < j) continue;
+    double s = 0;
+    for (int ks = 0; ks < y.ksplit; ks++) s += sP[((long)ks * y.nblk + blk) * 256 + in];
+    if (i < m) {
+      small::Accumulate(G + (long)j * ldg + i, s, acc);
+    } else if (i == m) {
+      small::Accumulate(j < m ? AQc + j : scal + 1, s, acc);
+    } else {
+      small::Accumulate(j < m ? AW + j : scal + 0, s, acc);
+    }
+  }
+}
+
+}  // namespace psdmma
+}  // namespace cxb

@@ -265,6 +265,9 @@ int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, 
 int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double* dG, long ldg,
                     long gstride, double* dAW, double* dAQc, long vstride, double* d_scal,
                     long sstride, int accumulate, const int* d_active);
+/* A/B switch of the dense-LMI branch of cxb_small_schur: 1 (default) = DMMA kernel with the scaled matrices in
+ * shared memory for blocks of order n <= 32, n % 4 == 0 (device/small_psd_mma.cuh); 0 = the DFMA team kernel. */
+void cxb_set_small_psd_mma(int enabled);
 /* out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} of Q(w^{1/2})(c_weight c - A y)
  * (GetWeightedSlackEigenvalues). c_weight: per-program device array d_cw (stride 1) when not NULL,
  * else the scalar. */

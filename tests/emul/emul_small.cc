@@ -48,7 +48,7 @@ struct HostTeam {
 };
 
 long Align4(long n) { return (n + 3) & ~3L; }
-size_t PsdSmem(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64; }
+size_t PsdSmem(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64 + 2 * cxb::small::kSections + 16; }
 
 }  // namespace
 

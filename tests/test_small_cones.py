@@ -102,7 +102,9 @@ def close(a, b, tol, what):
 
 
 SHAPES = [(LP, 1, 1), (LP, 7, 3), (LP, 40, 40), (SOC, 1, 2), (SOC, 10, 40), (SOC, 5, 3),
-          (PSD, 1, 2), (PSD, 2, 1), (PSD, 5, 3), (PSD, 20, 40), (PSD, 9, 4)]
+          (PSD, 1, 2), (PSD, 2, 1), (PSD, 5, 3), (PSD, 20, 40), (PSD, 9, 4),
+          # orders the DMMA Schur kernel takes (n % 4 == 0, n <= 32): every pitch class and ragged 8-wide tiles
+          (PSD, 4, 3), (PSD, 8, 5), (PSD, 12, 7), (PSD, 16, 30), (PSD, 24, 10), (PSD, 28, 6), (PSD, 32, 9)]
 
 
 @pytest.mark.parametrize("kind,n,m", SHAPES)
@@ -203,12 +205,13 @@ def test_small_cholesky_reports_first_bad_pivot(be):
     assert info.tolist() == [3, 0]
 
 
-def test_psd_schur_with_indefinite_scaling_point_uses_the_classic_form(be):
+@pytest.mark.parametrize("n,m", [(7, 5), (8, 5), (20, 40)])
+def test_psd_schur_with_indefinite_scaling_point_uses_the_classic_form(be, n, m):
     """The batched PSD Schur kernel takes the symmetric form (W = L L^T, packed L^T A_i L) and falls
     back to the reference's formula H_ij = tr(A_i W A_j W) (dense_lmi_constraint.cc:62-103) when W
     does not factor; the formula itself is defined for any symmetric W."""
     rng = np.random.Generator(np.random.PCG64(99))
-    n, m, B = 7, 5, 2
+    B = 2
     data = np.stack([random_cone_data(PSD, n, m, rng) for _ in range(B)])
     cone = be.cone(PSD, n, m, data)
     Ws = []
@@ -228,3 +231,36 @@ def test_psd_schur_with_indefinite_scaling_point_uses_the_classic_form(be):
         close(AW[p], np.array([np.trace(W @ mats[j]) for j in range(m)]), 1e-11, "AW")
         close(AQc[p], np.array([np.trace(W @ Cm @ W @ mats[j]) for j in range(m)]), 1e-11, "AQc")
         close(sc[p], np.array([np.trace(W @ Cm), np.trace(W @ Cm @ W @ Cm)]), 1e-11, "scalars")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(20, 40), (8, 3), (32, 12)])
+def test_dmma_schur_kernel_against_the_dfma_team_kernel(n, m):
+    """A/B of the two device kernels behind cxb_small_schur for dense LMI blocks (cxb_set_small_psd_mma): the DMMA
+    kernel with the scaled matrices in shared memory against the DFMA team kernel, on a random positive definite
+    scaling point, with and without accumulation into an existing system."""
+    be = Backend("device")
+    rng = np.random.Generator(np.random.PCG64(7 * n + m))
+    B = 5
+    data = np.stack([random_cone_data(PSD, n, m, rng) for _ in range(B)])
+    Ws = []
+    for p in range(B):
+        R = rng.uniform(-1, 1, size=(n, n))
+        Ws.append((R @ R.T / n + 0.5 * np.eye(n)).ravel(order="F"))
+    out = []
+    for enabled in (1, 0):
+        be.lib.cxb_set_small_psd_mma(enabled)
+        try:
+            cone = be.cone(PSD, n, m, data)
+            cone.set_state(np.stack(Ws))
+            first = cone.schur()
+            second = cone.schur(accumulate_into=cone.last)   # G <- 2 G
+            out.append((first, second))
+        finally:
+            be.lib.cxb_set_small_psd_mma(1)
+    for (a, b) in zip(out[0], out[1]):
+        for x, y, name in zip(a, b, ("H", "AW", "AQc", "scalars")):
+            close(x, y, 1e-12, name)
+    for x, y in zip(out[0][0], out[0][1]):
+        close(2 * x, y, 1e-12, "accumulate")
+
