@@ -129,14 +129,23 @@ class ConexLib:
     def program(self, m=0):
         return Program(self, m)
 
+    def program_on_memory_of(self, other, m=0):
+        """`Program prog2(m, &prog.memory_)` of the reference (cone_program.h:106-109): product library only."""
+        f = self.lib.CONEXB200_CreateConeProgramOnMemoryOf
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p]
+        handle = f(other.h)
+        assert handle, "CONEXB200_CreateConeProgramOnMemoryOf failed"
+        return Program(self, m, handle=handle)
+
 
 class Program:
     """Mirror of the reference's Python `Conex` class (interfaces/python/ConexProgram.py:58-277),
     reduced to the hot path."""
 
-    def __init__(self, lib, m=0):
+    def __init__(self, lib, m=0, handle=None):
         self.L = lib
-        self.h = C.c_void_p(lib.lib.CONEX_CreateConeProgram())
+        self.h = C.c_void_p(handle if handle is not None else lib.lib.CONEX_CreateConeProgram())
         self.m = 0
         self.cone_shapes = []
         if m > 0:

@@ -22,6 +22,7 @@
 // applies the block's update to its own rows, so no second launch or inter-CTA flag is needed.
 // All global->shared staging keeps 8 loads in flight per thread (latency, not bandwidth, is the
 // limit of these small kernels).
+#include <algorithm>
 #include "common.cuh"
 #include "device_api.h"
 
@@ -693,6 +694,207 @@ __global__ void __launch_bounds__(512) TrsvBwdWaveKernel(int m, const double* __
   SetFlag(flags + i);
 }
 
+// ---- single-launch sweeps, second version: the solution itself is the hand-off -----------------------
+// The flag version above spends per 128-row block: st X, barrier, fence, st.release flag | ld.acquire spin by one
+// thread, barrier, L2 read of x, barrier, 32 FMAs, two more barriers — about 5 us on top of the diagonal solve,
+// and that chain of m / 128 hand-offs, not bandwidth, sets the pace (profiles/r01_m_*). Here the output vector is
+// pre-filled with a sentinel (a quiet NaN with a payload no computation produces) and every consuming WARP polls the
+// 32 (forward) / 128 (backward) solution entries it needs with relaxed gpu-scope loads until none is the sentinel:
+// one L2 round trip, no flag, no fence (each entry is a single 64-bit store, so seeing it is seeing all of it) and
+// no CTA barrier between the producer's store and the consumer's FMAs. The right-hand side is read from a
+// separate array. The diagonal blocks are solved by the same true substitution, with the reciprocal of the
+// diagonal folded into the rows beforehand so that the 32-step chain is shuffle + FMA only.
+// Summation order is fixed, tickets as above: deterministic, no co-residency assumption.
+constexpr unsigned long long kSentinelBits = 0x7FF8DEADBEEF0001ull;
+__device__ __forceinline__ bool IsSentinel(double v) {
+  return static_cast<unsigned long long>(__double_as_longlong(v)) == kSentinelBits;
+}
+__device__ __forceinline__ double LoadRelaxed(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void StoreRelaxed(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__global__ void WaveInitKernel(double* out, long count, int* tickets, int ntickets) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = __longlong_as_double(static_cast<long long>(kSentinelBits));
+  if (i < ntickets) tickets[i] = 0;
+}
+
+template <int P>
+__device__ __forceinline__ void SolveLowerBlockScaled(const double* sl, const double* srd, double* sx) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+  for (int b0 = 0; b0 < kNB; b0 += 32) {
+    if (warp == 0) {
+      const double rd = srd[b0 + lane];
+      double lrow[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) lrow[j] = sl[(b0 + j) * P + b0 + lane] * rd;  // L[b0 + lane][b0 + j] / L_rr
+      double v = sx[b0 + lane] * rd;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const double xj = __shfl_sync(0xffffffffu, v, j);
+        if (lane > j) v -= lrow[j] * xj;
+      }
+      sx[b0 + lane] = v;
+    }
+    __syncthreads();
+    const int rows = kNB - b0 - 32;
+    if (tid < rows * 4) {
+      const int r = b0 + 32 + (tid >> 2), q = tid & 3;
+      double a = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) a += sl[(b0 + q * 8 + j) * P + r] * sx[b0 + q * 8 + j];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (q == 0) sx[r] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void SolveLowerTransposedBlockScaled(const double* sl, const double* srd, double* sx) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+  for (int b0 = kNB - 32; b0 >= 0; b0 -= 32) {
+    if (warp == 0) {
+      const double rd = srd[b0 + lane];
+      double lcol[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) lcol[j] = sl[(b0 + lane) * P + b0 + j] * rd;  // L[b0 + j][b0 + lane] / L_cc
+      double v = sx[b0 + lane] * rd;
+#pragma unroll
+      for (int j = 31; j >= 0; j--) {
+        const double xj = __shfl_sync(0xffffffffu, v, j);
+        if (lane < j) v -= lcol[j] * xj;
+      }
+      sx[b0 + lane] = v;
+    }
+    __syncthreads();
+    if (tid < b0 * 4) {
+      const int r = tid >> 2, q = tid & 3;
+      double a = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) a += sl[r * P + b0 + q * 8 + j] * sx[b0 + q * 8 + j];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (q == 0) sx[r] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+// Out must be sentinel-filled and *ticket zero at launch; B (the right-hand side) is not written.
+__global__ void __launch_bounds__(512) TrsvFwdPollKernel(int m, const double* __restrict__ L, long ld,
+                                                         const double* __restrict__ B, double* Out, int* ticket) {
+  constexpr int P = kNB + 1;
+  extern __shared__ double s[];
+  double* sl = s;
+  double* sx = s + kNB * P;
+  double* srd = sx + kNB;
+  double* sp = srd + kNB;  // 4 x kNB partial sums
+  __shared__ int s_block;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_block = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int i = s_block;
+  const int r0 = i * kNB;
+  const int nb = min(kNB, m - r0);
+  LoadLowerBlock<P>(sl, srd, L + (long)r0 * ld + r0, ld, nb);
+  const int rl = tid & (kNB - 1), g = tid >> 7;  // row of the strip, column group (32 of every 128)
+  const bool active = rl < nb;
+  const int r = r0 + rl;
+  double acc = 0;
+  for (int kb = 0; kb < i; kb++) {
+    const double* Lr = L + (long)(kb * kNB + g * 32) * ld + r;
+    double l[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) l[c] = active ? __ldcs(Lr + (long)c * ld) : 0.0;  // read exactly once
+    const double* xp = Out + kb * kNB + g * 32 + lane;  // blocks kb < i are full: always < m
+    double xv;
+    do {
+      xv = LoadRelaxed(xp);
+    } while (__any_sync(0xffffffffu, IsSentinel(xv)));
+#pragma unroll
+    for (int c = 0; c < 32; c++) acc += l[c] * __shfl_sync(0xffffffffu, xv, c);
+  }
+  sp[g * kNB + rl] = acc;
+  __syncthreads();
+  if (g == 0) sx[rl] = active ? B[r] - (((sp[rl] + sp[kNB + rl]) + sp[2 * kNB + rl]) + sp[3 * kNB + rl]) : 0.0;
+  __syncthreads();
+  SolveLowerBlockScaled<P>(sl, srd, sx);
+  if (tid < nb) StoreRelaxed(Out + r0 + tid, sx[tid]);
+}
+
+__global__ void __launch_bounds__(512) TrsvBwdPollKernel(int m, const double* __restrict__ L, long ld,
+                                                         const double* __restrict__ B, double* Out, int* ticket) {
+  constexpr int P = kNB + 1;
+  extern __shared__ double s[];
+  double* sl = s;
+  double* sx = s + kNB * P;
+  double* srd = sx + kNB;
+  double* sp = srd + kNB;  // kNB column sums
+  __shared__ int s_block;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_block = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int nblk = (m + kNB - 1) / kNB;
+  const int i = nblk - 1 - s_block;
+  const int c0 = i * kNB;
+  const int nb = min(kNB, m - c0);
+  LoadLowerBlock<P>(sl, srd, L + (long)c0 * ld + c0, ld, nb);
+  // warp w owns the columns c0 + 8 w .. c0 + 8 w + 7 of L; lanes run down the rows of a block
+  double acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q] = 0;
+  for (int kb = nblk - 1; kb > i; kb--) {
+    const int rb = kb * kNB;
+    const int nrows = min(kNB, m - rb);
+    double l[8][4];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int cw = warp * 8 + q;
+      const double* Lc = L + (long)(c0 + cw) * ld + rb + lane;
+#pragma unroll
+      for (int p = 0; p < 4; p++) l[q][p] = (cw < nb && lane + 32 * p < nrows) ? __ldcs(Lc + 32 * p) : 0.0;
+    }
+    double xv[4];
+    bool pending;
+    do {
+      pending = false;
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        if (lane + 32 * p < nrows) {
+          xv[p] = LoadRelaxed(Out + rb + lane + 32 * p);
+          pending = pending || IsSentinel(xv[p]);
+        } else {
+          xv[p] = 0.0;
+        }
+      }
+    } while (__any_sync(0xffffffffu, pending));
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+#pragma unroll
+      for (int p = 0; p < 4; p++) acc[q] += l[q][p] * xv[p];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const double v = WarpSum(acc[q]);
+    if (lane == 0) sp[warp * 8 + q] = v;
+  }
+  __syncthreads();
+  if (tid < kNB) sx[tid] = (tid < nb) ? B[c0 + tid] - sp[tid] : 0.0;
+  __syncthreads();
+  SolveLowerTransposedBlockScaled<P>(sl, srd, sx);
+  if (tid < nb) StoreRelaxed(Out + c0 + tid, sx[tid]);
+}
+
 // ---- supernodal (multifrontal) pieces -----------------------------------------------------------------
 // dst[idx[e]] += sign * G[a, b] for the pairs a >= b of an n x n lower triangle, e = position of (a, b)
 // in column-major order of the lower triangle. idx < 0: entry dropped.
@@ -780,9 +982,10 @@ constexpr size_t kTrsmSmem = sizeof(double) * (kNB * kNB + kNB * 32 + 32);
 constexpr size_t kTrsvSmem =
     sizeof(double) * (kNB * (kNB + 1) + kMaxRhs * kNB + kNB + kMaxRhs * 4 * kFwdRows);
 constexpr size_t kWaveSmem = sizeof(double) * (kNB * (kNB + 1) + 8 * kNB);
-// 0: single-launch wavefront sweeps (default); 1: one launch per block (the earlier scheme, kept for
-// A/B measurements through cxb_set_trsv_mode)
-int g_trsv_mode = 0;
+// 2: single-launch sweeps whose hand-off is the solution itself (default); 0: single-launch sweeps with
+// release/acquire flags; 1: one launch per block. The earlier schemes are kept for A/B measurements through
+// cxb_set_trsv_mode.
+int g_trsv_mode = 2;
 // 0: blocked diagonal kernel (default); 1: rank-1 kernel (the earlier one; A/B through cxb_set_potrf_mode)
 int g_potrf_mode = 0;
 int g_potrf_lookahead = 1;  // bit 1 of cxb_set_potrf_mode clears it (sequential schedule, A/B)
@@ -798,6 +1001,8 @@ void ConfigureOnce() {
   cudaFuncSetAttribute(TrsvBwdStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem);
   cudaFuncSetAttribute(TrsvFwdWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
   cudaFuncSetAttribute(TrsvBwdWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+  cudaFuncSetAttribute(TrsvFwdPollKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+  cudaFuncSetAttribute(TrsvBwdPollKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
 }
 
 }  // namespace
@@ -973,6 +1178,22 @@ int cxb_trsv_lower(void* stream, int m, const double* dL, long ldl, double* dx, 
   if (m <= 0) return 0;
   ConfigureOnce();
   const int nblk = (m + kNB - 1) / kNB;
+  if (g_trsv_mode == 2) {
+    // out-of-place sweep into a sentinel-filled scratch vector (+ the ticket behind it), copied back
+    double* Z = nullptr;
+    if (cudaMallocAsync(&Z, sizeof(double) * ((size_t)m + 2), s) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+    int* ticket = reinterpret_cast<int*>(Z + m);
+    CountLaunch(); WaveInitKernel<<<(m + 255) / 256, 256, 0, s>>>(Z, m, ticket, 1);
+    CountLaunch();
+    if (transposed) {
+      TrsvBwdPollKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dx, Z, ticket);
+    } else {
+      TrsvFwdPollKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dx, Z, ticket);
+    }
+    cudaMemcpyAsync(dx, Z, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, s);
+    cudaFreeAsync(Z, s);
+    return LaunchStatus();
+  }
   int* sync = nullptr;
   if (cudaMallocAsync(&sync, sizeof(int) * ((size_t)nblk + 1), s) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
   cudaMemsetAsync(sync, 0, sizeof(int) * ((size_t)nblk + 1), s);
@@ -1015,6 +1236,26 @@ static int PotrsLowerImpl(cudaStream_t s, int m, const double* dL, long ldl, dou
   if (nrhs > kMaxRhs) return -1;
   ConfigureOnce();
   const int nblk = (m + kNB - 1) / kNB;
+  if (g_trsv_mode == 2) {
+    // forward: dX (b) -> Z (z); backward: Z -> dX. Both outputs are sentinel-filled right before their sweep.
+    const size_t mz = (size_t)m * nrhs;
+    double* Z = nullptr;
+    if (cudaMallocAsync(&Z, sizeof(double) * (mz + (size_t)nrhs + 1), s) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+    int* tickets = reinterpret_cast<int*>(Z + mz);  // 2 * nrhs ints
+    CountLaunch(); WaveInitKernel<<<(unsigned)((std::max<size_t>(mz, 2 * (size_t)nrhs) + 255) / 256), 256, 0, s>>>(Z, (long)mz, tickets, 2 * nrhs);
+    for (int k = 0; k < nrhs; k++) {
+      CountLaunch(); TrsvFwdPollKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, dX + (long)k * ldx, Z + (size_t)k * m, tickets + 2 * k);
+    }
+    if (signs) {
+      CountLaunch(); ApplySignsKernel<<<(m + 255) / 256, 256, 0, s>>>(m, nrhs, signs, Z, m);
+    }
+    for (int k = 0; k < nrhs; k++) {
+      CountLaunch(); WaveInitKernel<<<(m + 255) / 256, 256, 0, s>>>(dX + (long)k * ldx, m, nullptr, 0);
+      CountLaunch(); TrsvBwdPollKernel<<<nblk, 512, kWaveSmem, s>>>(m, dL, ldl, Z + (size_t)k * m, dX + (long)k * ldx, tickets + 2 * k + 1);
+    }
+    cudaFreeAsync(Z, s);
+    return LaunchStatus();
+  }
   if (g_trsv_mode == 0) {
     // one ticket counter + nblk flags per sweep and right-hand side, zeroed once
     const size_t per = (size_t)nblk + 1;

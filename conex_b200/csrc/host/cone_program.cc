@@ -226,8 +226,9 @@ void Program::InitializeWorkspace() {
   sys.m_ = SizeOfKKTSystem();
   sys.residual_only_ = true;
   total += SizeOf(sys);
-  if (total > memory_.size()) memory_.Resize(total);  // only ever grows; a warm start keeps data
-  double* p = memory_.get();
+  DeviceBuffer<double>& arena = workspace_data_->data;
+  if (total > arena.size()) arena.Resize(total);  // only ever grows; a warm start keeps data
+  double* p = arena.get();
   for (auto& c : eqs) {
     Workspace w = c.constraint.workspace();
     Initialize(&w, p);

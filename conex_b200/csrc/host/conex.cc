@@ -806,6 +806,18 @@ void CONEXB200_TridiagonalExtremes(int n, const double* alpha, const double* bet
   out2[1] = mm.second;
 }
 
+void* CONEXB200_CreateConeProgramOnMemoryOf(void* other) {
+  // reference: Program prog2(m, &prog.memory_) (cone_program.h:106-109)
+  if (other == nullptr) return nullptr;
+  try {
+    Program* o = static_cast<Program*>(other);
+    return new Program(0, o->workspace_data_);
+  } catch (const std::exception& e) {
+    std::cerr << e.what() << std::endl;
+    return nullptr;
+  }
+}
+
 int CONEXB200_NumberOfConstraints(void* prog_ptr) {
   return Guard([&]() -> int { return static_cast<Program*>(prog_ptr)->NumberOfConstraints(); }, -1);
 }

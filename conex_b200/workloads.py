@@ -121,6 +121,16 @@ def device_view(ptr, count):
     return torch.as_tensor(_Raw(ptr, count), device="cuda")
 
 
+def maxcut_affine_term_device(n):
+    """C = -L/4 of the C2 graph G(n, 0.5) drawn on the device (torch CUDA generator, seed 2): n x n tensor."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2)
+    upper = torch.triu((torch.rand((n, n), generator=g, device="cuda") < 0.5).double(), 1)
+    adj = upper + upper.T
+    return -(torch.diag(adj.sum(1)) - adj) / 4.0
+
+
 def fill_workload(kind, n, m, row_begin, row_count, A, Cm):
     """Writes this rank's constraint matrices (global indices row_begin .. row_begin+row_count-1) into
     A (row_count x n*n view, column-major n x n blocks) and the affine term into Cm (n x n), in place
@@ -129,11 +139,7 @@ def fill_workload(kind, n, m, row_begin, row_count, A, Cm):
     idx = torch.arange(row_count, device="cuda")
     gi = idx + row_begin
     if kind == "maxcut":  # A_i = -e_i e_i^T, C = -L/4, b = -1
-        g = torch.Generator(device="cuda")
-        g.manual_seed(2)
-        upper = torch.triu((torch.rand((n, n), generator=g, device="cuda") < 0.5).double(), 1)
-        adj = upper + upper.T
-        Cm.copy_(-(torch.diag(adj.sum(1)) - adj) / 4.0)
+        Cm.copy_(maxcut_affine_term_device(n))
         A.zero_()
         A[idx, gi * n + gi] = -1.0
         return -np.ones(row_count)

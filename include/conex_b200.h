@@ -156,6 +156,11 @@ int CONEXB200_GetNumberOfSupernodes(void* prog);
 int CONEXB200_SupernodalAnalysis(int N, int num_cliques, const int* clique_ptr, const int* clique_vars,
                                  int* position, int* node_of, int* node_ptr, int* node_vars, int* sep_ptr,
                                  int* sep_vars, int sep_capacity, double* flops2);
+/* A new program on the memory of `other` (reference `Program prog2(m, &prog.memory_)`, cone_program.h:106-109,
+ * test_warmstart.cc:47-79): after adding the same constraints in the same order, a solve with
+ * initialization_mode = warm start continues from `other`'s iterate (scaling points and scalings live in that
+ * memory). `other` must outlive the new program and the two must not solve concurrently. NULL on failure. */
+void* CONEXB200_CreateConeProgramOnMemoryOf(void* other);
 /* Constraints added so far (Program::NumberOfConstraints, conex/cone_program.h); CONEX_AddLinearInequalities adds
  * zero, one or two (an LP cone for the finite bounds, an equality block for rows with lb == ub). */
 int CONEXB200_NumberOfConstraints(void* prog);

@@ -153,9 +153,26 @@ class DenseKKTSolver : public KKTSolver {
   int iterative_refinement_iterations_ = 0;
 };
 
+// What survives a solve and makes a warm start possible: the device arena (W and temporaries of every cone, the
+// per-cone Schur systems, the residuals) and the iteration statistics, which the reference keeps INSIDE its arena
+// (workspace.h:73-117) so that a second Program constructed on the same memory finds them
+// (cone_program.h:106-109, test_warmstart.cc:47-79).
+struct ProgramMemory {
+  DeviceBuffer<double> data;
+  WorkspaceStats stats;
+};
+
 class Program {
  public:
-  explicit Program(int number_of_variables) { SetNumberOfVariables(number_of_variables); }
+  explicit Program(int number_of_variables) : workspace_data_(&memory_), stats(memory_.stats) {
+    SetNumberOfVariables(number_of_variables);
+  }
+  // Adopts the arena of another program (reference cone_program.h:106-109): after adding the same constraints in the
+  // same order, a warm start continues from that program's iterate. `data` must outlive this object and must not be
+  // used by two programs at the same time.
+  Program(int number_of_variables, ProgramMemory* data) : workspace_data_(data), stats(data->stats) {
+    SetNumberOfVariables(number_of_variables);
+  }
 
   void SetNumberOfVariables(int m) {
     num_variables_ = m;
@@ -217,7 +234,9 @@ class Program {
   std::list<Container> eqs;  // std::list: addresses stay stable (constraint_manager.h:97-98)
   std::vector<Constraint*> constraints_;
   SchurComplementSystem sys;  // residual-only, program level (cone_program.cc:85-86)
-  WorkspaceStats stats;
+  ProgramMemory memory_;            // this program's own arena (unused when another one was adopted)
+  ProgramMemory* workspace_data_;   // the arena in use
+  WorkspaceStats& stats;            // = workspace_data_->stats
   std::unique_ptr<KKTSolver> solver;
   // 0: choose from the clique structure (supernodal when it saves at least half of the dense
   // factorisation's flops), 1: one dense supernode, 2: supernodal (CONEXB200_SetKKTSolverKind)
@@ -227,7 +246,6 @@ class Program {
   int solver_order_ = -1;
   int solver_kind_ = -1;
   bool solver_is_multifrontal_ = false;
-  DeviceBuffer<double> memory_;  // the device arena: W, temporaries, per-cone G/AW/AQc, residuals
   DeviceBuffer<double> vectors_;  // b, y, y2 (device copies of the host loop's m-vectors)
   bool is_initialized = false;
   ConexStatus status_;

@@ -14,7 +14,7 @@
 #include <memory>
 #include <vector>
 
-#include "../../../include/conex_b200_device.h"
+#include "../conex_b200_device.h"
 #include "constraint.h"
 
 namespace conex {

@@ -21,7 +21,8 @@ def run_reference(*extra):
 
 @pytest.mark.parametrize("workload", ["c1", "c2", "sparse"])
 def test_reference_arm_line(workload):
-    d = run_reference("--workload", workload)
+    # c2's own sample is n = m = 1000 (minutes of CPU work): the contract is checked on a smaller one
+    d = run_reference("--workload", workload, *(["--cpu-size", "160"] if workload == "c2" else []))
     assert d["impl"] == "reference" and d["metric"] == "newton_step_ms" and d["unit"] == "ms"
     assert d["higher_is_better"] is False and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert d["value"] > 0 and d["ms_per_step"] == d["value"] and d["dtype"] == "f64" and d["data"] == "synthetic"
@@ -33,6 +34,10 @@ def test_reference_arm_line(workload):
         assert cb["blas3_gram"]["value"] > 0           # the BLAS-3 variant of the port beside the as-written one
     if workload == "c1":
         assert "extrapolat" not in cb["sample"]        # config 1 is measured at its own size
+    if workload == "c2":
+        # the work model is validated on a second sample size, and the bounded sample is declared
+        assert cb["model_check"]["predicted_ms_per_step"] > 0 and cb["model_check"]["measured_ms_per_step"] > 0
+        assert d["sample_steps"] == {"timed": 2, "warmup": 1} and "extrapolat" in d["config"]["measured_on"]
 
 
 def test_other_ranks_of_the_reference_arm_stay_silent():

@@ -113,31 +113,26 @@ def test_c2_maxcut_n2000_dense_path_newton_system(libs, mode, steps):
     release()
 
 
-def test_c2_maxcut_n2000_dense_vs_structured_trajectory(libs):
-    """Same operators through the dense path (64 GB of matrices, DMMA assembly) and through the
-    incremental API (2000 stored entries, gather assembly): the first Newton steps agree step by step and
-    so does the iterate W."""
-    import torch
+def test_c2_maxcut_n2000_structured_path_newton_system(libs):
+    """The same operators through the incremental API (2000 stored entries instead of 64 GB, gather assembly): closed
+    forms at W = I and after 5 Newton steps. (The two paths are not compared step by step: like the reference's
+    HermitianPsdConstraint, the incremental LMI estimates its eigen-bounds from a random Lanczos start with its own
+    breakdown rule and steps with the Taylor exponential, SURVEY.md 8a K9 — its mu sequence differs from the dense
+    LMI's from the first step on; complete solves of the two paths are compared at n = 400 below.)"""
     _, dev = libs
-    n, steps = 2000, 4
-    P, b, C_host, A = device_program(dev, "maxcut", n, n)
-    del A
-    release()
-    P.maximize(b, steps_config(dev, steps))
-    log_d, X_d = P.iteration_log(), P.dual_variable(0)
-    del P
+    n, steps = 2000, 5
+    from conex_b200.workloads import maxcut_affine_term_device
+    C_host = maxcut_affine_term_device(n).cpu().numpy()   # the same graph as the dense C2 program
     release()
     Q = dev.program(n)
     Q.add_entry_lmi(n, [(i, i, i, -1.0) for i in range(n)], C_host)
+    b = -np.ones(n)
+    check_maxcut_system(Q, C_host, True, "structured at W = I")
     Q.maximize(b, steps_config(dev, steps))
     assert dev.lib.CONEXB200_ConstraintIsEntrySparse(Q.h, 0) == 1
-    log_s, X_s = Q.iteration_log(), Q.dual_variable(0)
-    assert len(log_d) == len(log_s) == steps
-    for i, (a, c) in enumerate(zip(log_d, log_s)):
-        for key in ("inv_sqrt_mu", "by", "cx"):
-            assert abs(a[key] - c[key]) <= 1e-7 * max(1.0, abs(a[key])), (i, key, a[key], c[key])
-    assert np.abs(X_d - X_s).max() <= 1e-7 * np.abs(X_d).max()
-    torch.cuda.synchronize()
+    assert len(Q.iteration_log()) == steps
+    W = check_maxcut_system(Q, C_host, False, f"structured after {steps} steps")
+    assert np.linalg.eigvalsh(W).min() > 0
 
 
 def primal_objective(P, C_host):

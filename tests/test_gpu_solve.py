@@ -219,6 +219,30 @@ def test_warmstart_agrees_with_full_solve(libs):
     assert np.linalg.norm(y - yw) < 1e-12
 
 
+def test_second_program_on_the_memory_of_the_first(libs):
+    """test_warmstart.cc:47-79 (`TestWorkspaceInitialization`): a second program constructed on the first one's
+    memory, given the same constraints, warm-starts from the first one's converged iterate — two more steps
+    return the same y (1e-9)."""
+    _, dev = libs
+    n, m = 15, 13
+    mats, Cm = random_dense_lmi(n, m, 31)
+    rng = np.random.Generator(np.random.PCG64(32))
+    Alin, clin = rng.uniform(-1, 1, size=(n, m)), np.ones(n)
+    P = dev.program()
+    P.add_dense_lmi(mats, Cm)
+    P.add_linear(Alin, clin)
+    b = P.feasible_objective()
+    solved, y = P.maximize(b, dev.default_config(final_centering_steps=3, final_centering_tolerance=.01))
+    assert solved == 1
+    P2 = dev.program_on_memory_of(P)
+    P2.add_dense_lmi(mats, Cm)
+    P2.add_linear(Alin, clin)
+    s2, ywarm = P2.maximize(b, dev.default_config(final_centering_steps=3, final_centering_tolerance=.01,
+                                                   initialization_mode=1, max_iterations=2))
+    assert np.linalg.norm(y - ywarm) < 1e-9 * max(1.0, np.linalg.norm(y))
+    del P2   # before P: it lives on P's memory
+
+
 def test_streamed_assembly_gives_the_same_solve(libs):
     """Row-panel streaming of the scaled matrices (the mode that fits config 5 on one GPU) against
     the keep-everything mode and the oracle."""

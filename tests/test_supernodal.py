@@ -300,7 +300,8 @@ def test_iterative_refinement_on_a_sparse_program_takes_the_dense_solver():
     iterative_refinement_iterations > 0 and the default solver kind the program is solved by the dense solver."""
     import devlib
     dev, ora = devlib.product(), oracle()
-    m, cones = block_arrow_program(blocks=4, private=80, shared=10, order=8, seed=3)   # m = 330 >= 256: pays
+    # m = 330 >= 256: the multifrontal solver pays; order 14: 105 free entries per cone >= its 90 variables
+    m, cones = block_arrow_program(blocks=4, private=80, shared=10, order=14, seed=3)
     out = []
     for L, kind in ((ora, None), (dev, 0)):
         P = L.program(m)

@@ -15,8 +15,8 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import devlib as dev  # noqa: E402
+sys.path.insert(0, ROOT)
+import conex_b200.binding as dev  # noqa: E402
 import torch  # noqa: E402
 
 L = dev.product().lib
@@ -55,7 +55,7 @@ def main():
     if "gemv" in which:
         prof_gemv(s, reps, out)
     if "chol" in which:
-        prof_chol(s, reps, out, (10001,) if mode == "once" else (10001, 20000))
+        prof_chol(s, reps, out, (10001,) if mode == "once" else (2000, 10001, 20000))
     if "lanczos" in which or "geo" in which:
         prof_psd(s, reps, out, which)
     for o in out:
@@ -101,12 +101,15 @@ def prof_chol(s, reps, out, sizes):
                             algorithmic_flops=m ** 3 / 3.0, TFLOPs=m ** 3 / 3.0 / (t * 1e-3) / 1e12))
         L.cxb_set_potrf_mode(0)
         x = torch.rand(m, **f64)
-        for mode, name, launches in ((1, "one launch per block", 2 * ((m + 127) // 128)), (0, "wavefront", 2)):
+        reps_solve = max(reps, 5 if reps > 1 else 1) * (4 if reps > 1 else 1)
+        for mode, name, launches in ((1, "one launch per block", 2 * ((m + 127) // 128)), (0, "wavefront, flags", 2),
+                                     (2, "wavefront, solution polled (default)", 4)):
             L.cxb_set_trsv_mode(mode)
-            med, best = timed(lambda: L.cxb_potrs_lower(vp(s), m, vp(Hwork.data_ptr()), ld, vp(x.data_ptr()), m, 1), reps)
+            med, best = timed(lambda: L.cxb_potrs_lower(vp(s), m, vp(Hwork.data_ptr()), ld, vp(x.data_ptr()), m, 1), reps_solve)
             out.append(dict(kernel=f"K5 cxb_potrs_lower ({name})", shape=f"m = {m}, 1 rhs", ms=med, best_ms=best,
                             algorithmic_bytes=8.0 * m * m, GBps=8.0 * m * m / (best * 1e-3) / 1e9,
                             launches=launches))
+        L.cxb_set_trsv_mode(2)
         del H, Hwork, x
         torch.cuda.empty_cache()
 
