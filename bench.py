@@ -848,6 +848,8 @@ def dense_bench(proc, args, w, steps, warmup, full_solve, cpu_leg):
     ph_timed = np.array(phases[warmup:]).mean(axis=0)
     log = P.iteration_log()
     form = L.CONEXB200_GetAssemblyForm(P.h, 0)
+    shard = np.zeros(4)
+    has_shard = L.CONEXB200_GetShardPhaseMilliseconds(P.h, 0, shard.ctypes.data_as(C.POINTER(C.c_double))) == 1
 
     # ---- e2e: exactly K more Newton steps through the C ABI with host buffers (warm start) ----
     cfg_e2e = dev.default_config(max_iterations=steps, final_centering_steps=0,
@@ -888,8 +890,8 @@ def dense_bench(proc, args, w, steps, warmup, full_solve, cpu_leg):
 
     value = float(timed.mean())
     e2e_ms = e2e_wall * 1e3 / e2e_its
-    red = proc.max_over_ranks([value, e2e_ms] + ph_timed.tolist())
-    value, e2e_ms, ph_timed = red[0], red[1], np.array(red[2:])
+    red = proc.max_over_ranks([value, e2e_ms] + ph_timed.tolist() + shard.tolist())
+    value, e2e_ms, ph_timed, shard = red[0], red[1], np.array(red[2:7]), red[7:]
     del P
     proc.release()
     if rank != 0:
@@ -945,6 +947,10 @@ def dense_bench(proc, args, w, steps, warmup, full_solve, cpu_leg):
         "setup_s": setup_s, "first_solve_wall_s": wall_cold,
         "final": {"by": log[-1]["by"], "cx": log[-1]["cx"], "mu": log[-1]["mu"]},
     }
+    if has_shard:
+        line["shard_assembly_ms"] = dict(zip(["local_k1_and_diagonal_block", "stall_waiting_for_peer_chunks",
+                                              "off_diagonal_contractions", "allreduce_of_H"], shard),
+                                         note="last timed assembly, CUDA events on the compute stream, max over ranks")
     if solve:
         line["solve"] = solve
         line["solve_ms"], line["solve_iterations"], line["solved"] = solve["solve_ms"], solve["solve_iterations"], solve["solved"]
@@ -957,7 +963,7 @@ def compact(line):
     """The keys of a secondary workload's record that go inside the main JSON line."""
     if line is None or "error" in line:
         return line
-    keep = ("value", "unit", "n_gpus", "steps", "warmup", "config", "phase_ms", "solve_ms", "programs_per_s",
+    keep = ("value", "unit", "n_gpus", "steps", "warmup", "config", "phase_ms", "shard_assembly_ms", "solve_ms", "programs_per_s",
             "programs_solved", "step_tflops_fp64", "gpu_launches")
     out = {k: line[k] for k in keep if k in line}
     out["roofline"] = {k: line["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac") if k in line["roofline"]}

@@ -61,12 +61,13 @@ extern "C" int cxb_pack_symmetric(void* stream, int n, const double* d_src, doub
   return LaunchStatus();
 }
 
-extern "C" int cxb_schur_dense_lmi_sym(void* stream, int n, int m, const double* dAall, const double* dW,
-                                       double* dX, double* dT, int panel, double* dL, int* d_info,
-                                       double* dHaug, long ldh) {
+// The two phases are separate entry points so that the sharded assembly can start shipping its scaled matrices to
+// the peers as soon as K1 is done, under its own Gram.
+extern "C" int cxb_schur_dense_lmi_sym_scale(void* stream, int n, int m, const double* dAall, const double* dW,
+                                             double* dX, double* dT, int panel, double* dL, int* d_info) {
   using namespace cxb;
   cudaStream_t s = AsStream(stream);
-  if (n < 1 || m < 1 || panel < 1 || ldh < m + 2) return -1;
+  if (n < 1 || m < 1 || panel < 1) return -1;
   const long nn = (long)n * n;
   const long kp = PackedSymmetricSize(n);
   CountLaunch(); CopyLowerKernel<<<dim3((n + 127) / 128, n), 128, 0, s>>>(n, dW, dL);
@@ -85,8 +86,24 @@ extern "C" int cxb_schur_dense_lmi_sym(void* stream, int n, int m, const double*
   // row m + 1 of the Gram: the packed identity, AW_j = tr(S_j) = <I, S_j>
   rc = SetIdentity(s, n, dT);
   if (rc) return rc;
-  if ((rc = cxb_pack_symmetric(stream, n, dT, dX + (long)(m + 1) * kp))) return rc;
-  return Dgemm(s, true, false, m + 2, m + 1, (int)kp, 1.0, dX, kp, 0, dX, kp, 0, 0.0, dHaug, ldh, 0, 1, true);
+  return cxb_pack_symmetric(stream, n, dT, dX + (long)(m + 1) * kp);
+}
+
+extern "C" int cxb_schur_dense_lmi_sym_gram(void* stream, int n, int m, const double* dX, double* dHaug, long ldh) {
+  using namespace cxb;
+  if (n < 1 || m < 1 || ldh < m + 2) return -1;
+  const long kp = PackedSymmetricSize(n);
+  return Dgemm(AsStream(stream), true, false, m + 2, m + 1, (int)kp, 1.0, dX, kp, 0, dX, kp, 0, 0.0, dHaug, ldh, 0, 1,
+               true);
+}
+
+extern "C" int cxb_schur_dense_lmi_sym(void* stream, int n, int m, const double* dAall, const double* dW,
+                                       double* dX, double* dT, int panel, double* dL, int* d_info,
+                                       double* dHaug, long ldh) {
+  if (ldh < m + 2) return -1;
+  const int rc = cxb_schur_dense_lmi_sym_scale(stream, n, m, dAall, dW, dX, dT, panel, dL, d_info);
+  if (rc) return rc;
+  return cxb_schur_dense_lmi_sym_gram(stream, n, m, dX, dHaug, ldh);
 }
 
 extern "C" int cxb_schur_dense_lmi(void* stream, int n, int m, const double* dAall, const double* dW,

@@ -659,6 +659,17 @@ int CONEXB200_GetAssemblyForm(void* prog, int id) {
   return -1;
 }
 
+int CONEXB200_GetShardPhaseMilliseconds(void* prog, int id, double* out4) {
+  Program& program = *static_cast<Program*>(prog);
+  int k = 0;
+  for (auto& c : program.eqs) {
+    if (k++ != id) continue;
+    if (auto* d = std::any_cast<conex::DenseLMIConstraint>(&c.obj)) return d->shard_phase_milliseconds(out4) ? 1 : 0;
+    return 0;
+  }
+  return 0;
+}
+
 int CONEXB200_SizeOfKKTSystem(void* prog) { return static_cast<Program*>(prog)->SizeOfKKTSystem(); }
 
 // Host-logic probe: pivot order of the regularised LDL^T from the diagonal (RLDLT.h:328-356).

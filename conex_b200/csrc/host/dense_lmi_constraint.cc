@@ -41,7 +41,14 @@ struct DenseLMIConstraint::Storage {
   cudaEvent_t arrived[2] = {nullptr, nullptr};
   cudaEvent_t consumed[2] = {nullptr, nullptr};
   cudaEvent_t start = nullptr;
+  // timing of the last sharded assembly (CUDA events on the compute stream): begin, local block done, before the
+  // all-reduce, end; per exchanged chunk: before the wait for its arrival, after it, after its contraction
+  cudaEvent_t t_mark[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> t_chunk;
+  size_t t_chunks_used = 0;
   ~Storage() {
+    for (auto e : t_mark) if (e) cudaEventDestroy(e);
+    for (auto e : t_chunk) if (e) cudaEventDestroy(e);
     for (auto e : arrived) if (e) cudaEventDestroy(e);
     for (auto e : consumed) if (e) cudaEventDestroy(e);
     if (start) cudaEventDestroy(start);
@@ -111,6 +118,26 @@ DenseLMIConstraint::DenseLMIConstraint(int n, int m, EntrySparse)
     : n_(n), m_(m), m_local_(m), workspace_(n), data_(std::make_shared<Storage>()) {}
 
 bool DenseLMIConstraint::entry_sparse() const { return data_->sparse; }
+
+bool DenseLMIConstraint::shard_phase_milliseconds(double* out4) const {
+  const Storage& d = *data_;
+  if (!sharded_ || d.t_mark[3] == nullptr || cudaEventSynchronize(d.t_mark[3]) != cudaSuccess) return false;
+  float local = 0, allreduce = 0, stall = 0, offdiag = 0;
+  cudaEventElapsedTime(&local, d.t_mark[0], d.t_mark[1]);
+  cudaEventElapsedTime(&allreduce, d.t_mark[2], d.t_mark[3]);
+  for (size_t c = 0; c < d.t_chunks_used; c++) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, d.t_chunk[3 * c], d.t_chunk[3 * c + 1]);
+    cudaEventElapsedTime(&b, d.t_chunk[3 * c + 1], d.t_chunk[3 * c + 2]);
+    stall += a;
+    offdiag += b;
+  }
+  out4[0] = local;
+  out4[1] = stall;
+  out4[2] = offdiag;
+  out4[3] = allreduce;
+  return true;
+}
 
 int DenseLMIConstraint::assembly_form() const {
   const Storage& d = *data_;
@@ -423,6 +450,10 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
   const double* send_source = sym ? d.X.get() : d.Aall.get();
   int* flag = ctx_->flags() + 4;
 
+  for (auto& e : d.t_mark) {
+    if (!e) CudaCheck(cudaEventCreate(&e), "cudaEventCreate");
+  }
+  CudaCheck(cudaEventRecord(d.t_mark[0], s), "cudaEventRecord");
   CudaCheck(cudaMemsetAsync(G, 0, sizeof(double) * ldg * (m + 1), s), "memset of H");
 
   // -- exchange schedule: a flat list of chunks over all distances --------------------------------
@@ -478,10 +509,13 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
 
   // -- 1. local diagonal block ----------------------------------------------------------------------
   if (sym) {
-    DeviceCheck(cxb_schur_dense_lmi_sym(s, n, ml, d.Aall.get(), workspace_.W.data, d.X.get(), d.T.get(), d.panel,
-                                        d.Lw.get(), flag, d.Hloc.get(), ldl),
-                "cxb_schur_dense_lmi_sym(local block)");
+    // K1 first; the scaled matrices can travel from here on, under the local Gram
+    DeviceCheck(cxb_schur_dense_lmi_sym_scale(s, n, ml, d.Aall.get(), workspace_.W.data, d.X.get(), d.T.get(), d.panel,
+                                              d.Lw.get(), flag),
+                "cxb_schur_dense_lmi_sym_scale(local block)");
     release_side_stream();
+    DeviceCheck(cxb_schur_dense_lmi_sym_gram(s, n, ml, d.X.get(), d.Hloc.get(), ldl),
+                "cxb_schur_dense_lmi_sym_gram(local block)");
   } else {
     DeviceCheck(cxb_schur_dense_lmi(s, n, ml, d.Aall.get(), workspace_.W.data, d.B.get(), d.T.get(),
                                     d.panel, d.Hloc.get(), ldl),
@@ -501,12 +535,22 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
               "copy of the scalars");
   }
 
+  CudaCheck(cudaEventRecord(d.t_mark[1], s), "cudaEventRecord");
+  while (d.t_chunk.size() < 3 * chunks.size()) {
+    cudaEvent_t e = nullptr;
+    CudaCheck(cudaEventCreate(&e), "cudaEventCreate");
+    d.t_chunk.push_back(e);
+  }
+  d.t_chunks_used = chunks.size();
+
   // -- 2. off-diagonal blocks ----------------------------------------------------------------------
   for (size_t c = 0; c < chunks.size(); c++) {
     if (c + 1 < chunks.size()) post(c + 1);
     const Chunk& ch = chunks[c];
     const int buf = static_cast<int>(c % 2);
+    CudaCheck(cudaEventRecord(d.t_chunk[3 * c], s), "cudaEventRecord");
     CudaCheck(cudaStreamWaitEvent(s, d.arrived[buf], 0), "cudaStreamWaitEvent");
+    CudaCheck(cudaEventRecord(d.t_chunk[3 * c + 1], s), "cudaEventRecord");
     if (ch.recv_count > 0) {
       const PairTask& t = *ch.task;
       const double* Bl = local_scaled + static_cast<long>(t.row_begin - rb) * stride;
@@ -525,9 +569,12 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
       }
     }
     CudaCheck(cudaEventRecord(d.consumed[buf], s), "cudaEventRecord");
+    CudaCheck(cudaEventRecord(d.t_chunk[3 * c + 2], s), "cudaEventRecord");
   }
   // -- 3. one all-reduce over the augmented H -------------------------------------------------------
+  CudaCheck(cudaEventRecord(d.t_mark[2], s), "cudaEventRecord");
   comm.AllReduceSum(G, static_cast<size_t>(ldg) * (m + 1), s);
+  CudaCheck(cudaEventRecord(d.t_mark[3], s), "cudaEventRecord");
   if (sym) {
     // W is replicated bit-identically, so every rank sees the same flag and takes the same branch.
     int w_not_pd = 0;

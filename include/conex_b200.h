@@ -95,6 +95,11 @@ int CONEXB200_CholeskySchedule(int N, int block, int world, int rank, int* out3,
  * *info = 0, or non-zero on every rank if the matrix is not positive definite. Returns 0 / 1. */
 int CONEXB200_DistributedPotrf(int N, double* d_H, long ld, int block, int* info);
 
+/* Where the last sharded assembly of LMI constraint `id` spent its device time on THIS rank (CUDA events on the
+ * compute stream): out4 = {local K1 + diagonal block, stalls waiting for a peer's chunk (exchange not hidden),
+ * off-diagonal contractions, all-reduce of H} in ms. Returns 1, or 0 when the constraint is not sharded. */
+int CONEXB200_GetShardPhaseMilliseconds(void* prog, int id, double* out4);
+
 /* Zero-copy variant for operators that only fit once: the library allocates this rank's storage
  * (local_count = CONEXB200_ShardRange(m, world, rank) matrices, then C) and returns device pointers
  * that the caller fills in place (column-major n x n blocks) before the first solve. With world == 1

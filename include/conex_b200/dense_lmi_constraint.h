@@ -74,6 +74,9 @@ class DenseLMIConstraint {
   // Dense storage for a block created with the EntrySparse constructor (allocated on first use).
   void LoadDense(const std::vector<Entry>& lower_entries, const double* C);
   bool entry_sparse() const;
+  // Sharded blocks: device milliseconds of the last assembly on this rank — {local K1 + diagonal block, stalls of
+  // the compute stream waiting for a peer's chunk, off-diagonal contractions, all-reduce of H}. False if not sharded.
+  bool shard_phase_milliseconds(double* out4) const;
   // How this block assembles its Schur complement: 0 undecided (before the first assembly), 1 classic
   // (all W A_i W kept), 2 row panels, 3 symmetric (packed L^T A_i L), 4 entry-sparse gathers.
   int assembly_form() const;

@@ -65,6 +65,11 @@ size_t cxb_packed_symmetric_size(int n);
 int cxb_pack_symmetric(void* stream, int n, const double* d_src, double* d_dst);
 int cxb_schur_dense_lmi_sym(void* stream, int n, int m, const double* dAall, const double* dW, double* dX,
                             double* dT, int panel, double* dL, int* d_info, double* dHaug, long ldh);
+/* The two phases of cxb_schur_dense_lmi_sym on their own: K1 (factor W, scale and pack every matrix, the packed
+ * identity in row m + 1 of X) and K2 (the Gram of the packed rows). */
+int cxb_schur_dense_lmi_sym_scale(void* stream, int n, int m, const double* dAall, const double* dW, double* dX,
+                                  double* dT, int panel, double* dL, int* d_info);
+int cxb_schur_dense_lmi_sym_gram(void* stream, int n, int m, const double* dX, double* dHaug, long ldh);
 
 /* ---- entry-sparse LMI operators (MaxCut, Lovasz theta, ...; sparse_lmi.cu) -----------------------
  * A_i given by their non-zero entries (both triangles listed): entries offsets[i] .. offsets[i+1]-1 of
