@@ -643,7 +643,8 @@ bool NewtonDriver::Run(double* primal_variable) {
     st.num_iter = i + 1;
     st.sqrt_inv_mu[i] = k;
     prog_.log.push_back({k, mu, d_2, d_inf, by, cx, kkt_error, opt.step_size, ms,
-                         {phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3], phase_ms[4]}});
+                         {phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3], phase_ms[4]},
+                         {2 * r[2], r[1], k * r[3] * st.c_scaling}});
     if (prog_.verbose) {
       std::cout << "i: " << std::setw(2) << i << ", mu: " << std::scientific << std::setprecision(2)
                 << mu << ", d_2: " << d_2 << ", d_inf: " << d_inf << ", by: " << by << ", cx: " << cx

@@ -741,6 +741,14 @@ int CONEXB200_GetIterationLog(void* prog, int iter, double* out8) {
   return 1;
 }
 
+int CONEXB200_GetObjectiveTerms(void* prog, int iter, double* out3) {
+  const auto& log = static_cast<Program*>(prog)->log;
+  if (iter < 0) iter += static_cast<int>(log.size());
+  if (iter < 0 || iter >= static_cast<int>(log.size())) return 0;
+  for (int p = 0; p < 3; p++) out3[p] = log[iter].cx_terms[p];
+  return 1;
+}
+
 int CONEXB200_GetIterationMilliseconds(void* prog, int iter, double* ms) {
   const auto& log = static_cast<Program*>(prog)->log;
   if (iter < 0 || iter >= static_cast<int>(log.size())) return 0;

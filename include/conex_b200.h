@@ -23,6 +23,12 @@ void CONEXB200_GetStatus(void* prog, int* out4);
  * Returns 1, or 0 when `iter` is out of range. */
 int CONEXB200_GetIterationLog(void* prog, int iter, double* out8);
 
+/* The three terms the logged cx of iteration `iter` (negative: from the end) is formed from (reference
+ * cone_program.cc:447-452):  k b_s cx = out3[0] + out3[1] - out3[2] = 2 <c,w> + <AQc, y> - k c_s <c,Qc>. Late in a solve
+ * the last two are ~k^2 times larger than their difference: (|out3[0]| + |out3[1]| + |out3[2]|) / |their sum| is the
+ * condition number of that formula, i.e. what the rounding errors of the inner products are amplified by in cx. */
+int CONEXB200_GetObjectiveTerms(void* prog, int iter, double* out3);
+
 /* Device time (ms, CUDA events on the program's stream) of Newton step `iter` of the last solve;
  * returns 0 when out of range. */
 int CONEXB200_GetIterationMilliseconds(void* prog, int iter, double* ms);

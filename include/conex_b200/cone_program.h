@@ -71,6 +71,9 @@ struct IterationRecord {
   double inv_sqrt_mu, mu, d_2, d_inf, by, cx, kkt_error, step_size;
   float milliseconds;  // device time of the whole Newton step (CUDA events on the program stream)
   float phase_ms[5];   // assemble, factor, mu, solve, update (same events)
+  // the three terms cx is formed from, k cx b_s = 2 <c,w> + <AQc, y> - k c_s <c,Qc> (cone_program.cc:447-452): the last
+  // two are ~k^2 times larger than their difference late in a solve, which is what bounds the accuracy of cx
+  double cx_terms[3];
 };
 struct PhaseSeconds {
   double assemble = 0, factor = 0, solve = 0, update = 0, mu = 0;

@@ -71,15 +71,31 @@ def oracle_trajectory_horizon(ora, mats, Cm, b, variables=None, m=None, **cfg_kw
     return h
 
 
+def cx_formula_tolerance(Pd, order):
+    """The solver's logged primal estimate cx is formed by cancellation (cone_program.cc:447-452):
+    k b_s cx = 2 <c,w> + <AQc, y> - k c_s <c,Qc>, whose last two terms are ~k^2 = 1/mu times larger than their
+    difference at the end of a solve. Rounding errors of the inner products behind those terms (length n^2, relative
+    error ~ n eps for random signs) are amplified by the condition number of that sum,
+    cond = (|t0| + |t1| + |t2|) / |t0 + t1 - t2|, which the product reports for its own run
+    (CONEXB200_GetObjectiveTerms). The oracle's logged cx moves by (1..5) eps cond between its own summation
+    orders (as-written / BLAS-3 / symmetric Gram: 1e-7 .. 4e-7 on MaxCut n = 40..150,
+    profiles/r01_e_assembly_form_parity.txt), so 1e-7 is not attainable for THIS diagnostic; the primal objective
+    itself, <C, X> of the dual variable the API returns, is compared at 1e-7 (primal_objective below)."""
+    import ctypes as C
+    t = (C.c_double * 3)()
+    if Pd.L.lib.CONEXB200_GetObjectiveTerms(Pd.h, -1, t) != 1:
+        return 1e-7
+    total = abs(t[0] + t[1] - t[2])
+    cond = (abs(t[0]) + abs(t[1]) + abs(t[2])) / max(total, 1e-300)
+    return max(1e-7, 4.0 * order * 2.220446049250313e-16 * cond)
+
+
 def check_parity(res, obj_tol=1e-7, cx_tol=None, horizon=None):
-    """`by` (the maximised dual objective b'y) must agree within obj_tol. The solver's primal
-    estimate `cx` is formed by cancellation (cone_program.cc:447-452) from a solve with the badly
-    conditioned final Schur complement (mu ~ 1e-9 after rescaling); for such instances the oracle
-    run under two summation orders already differs by ~1e-7 relative
-    (tests/test_oracle_golden.py::test_rounding_sensitivity_of_final_objectives), so cx_tol may be
-    set looser there and says so at the call site."""
-    cx_tol = obj_tol if cx_tol is None else cx_tol
+    """`by` (the maximised dual objective b'y) must agree within obj_tol; the logged `cx` within the error bound of
+    its own formula (cx_formula_tolerance) unless the caller passes a tighter cx_tol."""
     (Po, so, yo, bo), (Pd, sd, yd, bd) = res
+    if cx_tol is None:
+        cx_tol = cx_formula_tolerance(Pd, max(r for r, _ in Pd.cone_shapes))
     assert so == sd
     lo, ld = Po.iteration_log(), Pd.iteration_log()
     assert abs(len(lo) - len(ld)) <= 1, (len(lo), len(ld))
@@ -87,7 +103,7 @@ def check_parity(res, obj_tol=1e-7, cx_tol=None, horizon=None):
     # objectives of the final iterate
     for key, tol in (("by", obj_tol), ("cx", cx_tol)):
         a, c = lo[-1][key], ld[-1][key]
-        assert abs(a - c) <= tol * max(1.0, abs(a)), (key, a, c)
+        assert abs(a - c) <= tol * max(1.0, abs(a)), (key, a, c, tol)
     # trajectories agree step by step while both run (mu rule, step size, distance to the path)
     steps = min(len(lo), len(ld)) - 1
     if horizon is None:
@@ -97,6 +113,14 @@ def check_parity(res, obj_tol=1e-7, cx_tol=None, horizon=None):
     for i in range(steps):
         assert abs(lo[i]["inv_sqrt_mu"] - ld[i]["inv_sqrt_mu"]) <= 1e-6 * abs(lo[i]["inv_sqrt_mu"]), i
     assert np.abs(yo - yd).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+
+
+def check_primal_objective(res, Cm, tol=1e-7):
+    """BASELINE gate "primal objective within 1e-7": <C, X> of the dual variable CONEX_GetDualVariable returns (needs
+    prepare_dual_variables = 1), oracle vs device."""
+    (Po, _, _, _), (Pd, _, _, _) = res
+    po, pd = float(np.sum(Cm * Po.dual_variable(0))), float(np.sum(Cm * Pd.dual_variable(0)))
+    assert abs(po - pd) <= tol * max(1.0, abs(po)), (po, pd)
 
 
 def test_newton_system_entries_c1(libs):
@@ -124,6 +148,7 @@ def test_c1_random_dense_lmi_solve(libs, mode):
     mats, Cm = random_dense_lmi(50, 100, 1)
     res = solve_both(libs, mats, Cm, prepare_dual_variables=1, assembly_mode=mode)
     check_parity(res)
+    check_primal_objective(res, Cm)
     Pd, solved, y, b = res[1]
     assert solved == 1
     # reference property checks (test_sdp.cc:187-197)
@@ -144,7 +169,8 @@ def test_profile_sdp_shapes(libs, n, m):
     """The reference's property harness shapes (test_sdp.cc:170-208), incl. n = 1..3 edge cases."""
     mats, Cm = random_dense_lmi(n, m, 100 + n * 31 + m)
     res = solve_both(libs, mats, Cm, prepare_dual_variables=1)
-    check_parity(res, obj_tol=1e-6)
+    check_parity(res)
+    check_primal_objective(res, Cm)
     Pd, solved, y, b = res[1]
     X = Pd.dual_variable(0)
     slack = Cm - sum(y[i] * mats[i] for i in range(m))
@@ -279,11 +305,10 @@ def test_maxcut_small(libs, mode):
     # BASELINE gates (objectives, iteration count) on the whole solve.
     horizon = res.horizon
     assert horizon >= 2
-    # final mu ~ 2e-9: see check_parity. The symmetric form reaches H through the Cholesky factor of W;
-    # on this instance (A_i = -e_i e_i^T makes the classic products exact) the cancellation in cx
-    # then moves it by up to 3e-6 relative while by, y and the iteration count stay put — measured for
-    # the oracle's own symmetric variant and the device in profiles/r01_e_assembly_form_parity.txt.
-    check_parity(res, cx_tol=1e-6 if mode == CLASSIC else 1e-5, horizon=horizon)
+    # by / iterations / y at the BASELINE gates; the logged cx at the error bound of its own formula (both forms);
+    # the primal objective <C, X> at 1e-7
+    check_parity(res, horizon=horizon)
+    check_primal_objective(res, Cm)
     X = res[1][0].dual_variable(0)
     assert np.abs(np.diag(X) - 1.0).max() < 1e-6
 
@@ -292,8 +317,9 @@ def test_maxcut_small(libs, mode):
 def test_lovasz_theta_small(libs, mode):
     """BASELINE config 4 shape at n = 30, 80 edges."""
     mats, Cm, b = lovasz_theta_lmi(30, 80, 4)
-    res = solve_both(libs, mats, Cm, b=b, assembly_mode=mode)
-    check_parity(res, cx_tol=1e-6)
+    res = solve_both(libs, mats, Cm, b=b, assembly_mode=mode, prepare_dual_variables=1)
+    check_parity(res)
+    check_primal_objective(res, Cm)
 
 
 def test_infeasible_status_flags(libs):
