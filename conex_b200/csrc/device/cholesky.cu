@@ -959,6 +959,33 @@ __global__ void SymPermuteLowerKernel(int N, const double* __restrict__ K, long 
   Kp[(long)j * ldp + i] = K[(long)c * ldk + r];
 }
 
+// A front (rows x s lower trapezoid: the s x s diagonal block stored by its lower triangle on top of the
+// (rows - s) x s separator block) under the pivot order `perm` of its supernode: the diagonal block becomes
+// P F11 P^T, the separator block gets its columns permuted.
+__global__ void FrontPermuteKernel(int rows, int s, const double* __restrict__ F, long ld,
+                                   const int* __restrict__ perm, double* Out, long ldo) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= rows || r < c) return;
+  const int pc = perm[c];
+  if (r < s) {
+    const int pr = perm[r];
+    const int a = pr > pc ? pr : pc, b = pr > pc ? pc : pr;
+    Out[(long)c * ldo + r] = F[(long)b * ld + a];
+  } else {
+    Out[(long)c * ldo + r] = F[(long)pc * ld + r];
+  }
+}
+
+// Out[:, c] = A[:, c] * signs[c]
+__global__ void ScaleColumnsKernel(int rows, int cols, const double* __restrict__ A, long lda,
+                                   const double* __restrict__ signs, double* Out, long ldo) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= rows || c >= cols) return;
+  Out[(long)c * ldo + r] = A[(long)c * lda + r] * signs[c];
+}
+
 // out[i] = in[perm[i]] (gather) or out[perm[i]] = in[i] (scatter)
 __global__ void PermuteVecKernel(int N, const int* __restrict__ perm, const double* __restrict__ in,
                                  double* out, int scatter) {
@@ -1338,6 +1365,72 @@ int cxb_ldlt_lower(void* stream, int N, double* dK, long ldk, double* d_signs, d
                            dK + (long)(i0 + nb) * ldk + (i0 + nb), ldk, 0, 1, true, false, 0);
     if (rc != 0) return rc;
   }
+  return LaunchStatus();
+}
+
+// ---- LDL^T over fronts (multifrontal solver with equality multipliers) ---------------------------------
+// Signed factorisation of the first `cols` columns of a rows x cols lower trapezoid (rows >= cols): on top
+// L11 with F11 = L11 S L11^T, below G = F21 L11^{-T} S, so that the front is [L11; G] S [L11; G]^T and the Schur
+// complement of the rows below is F22 - G S G^T. Trailing updates stay inside the `cols` columns. d_signs: cols
+// entries (+-1); d_work: rows * 128 doubles; d_info[1] reports regularised pivots and is NOT reset here.
+int cxb_ldlt_partial(void* stream, int rows, int cols, double* dF, long ld, double* d_signs, double* d_work,
+                     int* d_info) {
+  cudaStream_t s = AsStream(stream);
+  if (rows < cols || cols < 0) return -1;
+  if (cols == 0) return 0;
+  ConfigureOnce();
+  for (int i0 = 0; i0 < cols; i0 += kNB) {
+    const int nb = min(kNB, cols - i0);
+    double* Kii = dF + (long)i0 * ld + i0;
+    CountLaunch(); PotrfDiagKernel<true><<<1, 512, kDiagSmem, s>>>(nb, Kii, ld, i0, d_info, d_signs);
+    const int below = rows - i0 - nb;
+    if (below <= 0) continue;
+    double* A21 = Kii + nb;
+    CountLaunch(); TrsmPanelKernel<<<(below + kNB - 1) / kNB, kNB, kTrsmSmem, s>>>(nb, Kii, ld, A21, below, d_info);
+    dim3 grid((below + 127) / 128, nb);
+    CountLaunch(); SignedPanelKernel<<<grid, 128, 0, s>>>(below, nb, A21, ld, d_signs + i0, d_work);
+    const int rest = cols - i0 - nb;  // columns of the front still to be updated
+    if (rest > 0) {
+      const int rc = DgemmEx(s, -1, 1, false, true, below, rest, nb, -1.0, d_work, below, 0, A21, ld, 0, 1.0,
+                             dF + (long)(i0 + nb) * ld + (i0 + nb), ld, 0, 1, true, false, 0);
+      if (rc != 0) return rc;
+    }
+  }
+  return LaunchStatus();
+}
+
+int cxb_ldlt_begin(void* stream, int* d_info) {
+  CountLaunch(); ResetInfo2Kernel<<<1, 1, 0, AsStream(stream)>>>(d_info);
+  return LaunchStatus();
+}
+
+int cxb_front_permute(void* stream, int rows, int s_cols, const double* dF, long ld, const int* d_perm, double* dOut,
+                      long ldo) {
+  if (rows <= 0 || s_cols <= 0) return 0;
+  dim3 grid((rows + 127) / 128, s_cols);
+  CountLaunch(); FrontPermuteKernel<<<grid, 128, 0, AsStream(stream)>>>(rows, s_cols, dF, ld, d_perm, dOut, ldo);
+  return LaunchStatus();
+}
+
+int cxb_scale_columns(void* stream, int rows, int cols, const double* dA, long lda, const double* d_signs,
+                      double* dOut, long ldo) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((rows + 127) / 128, cols);
+  CountLaunch(); ScaleColumnsKernel<<<grid, 128, 0, AsStream(stream)>>>(rows, cols, dA, lda, d_signs, dOut, ldo);
+  return LaunchStatus();
+}
+
+// out[i] = in[perm[i]] (scatter == 0) or out[perm[i]] = in[i] (scatter != 0)
+int cxb_permute_vec(void* stream, int N, const int* d_perm, const double* d_in, double* d_out, int scatter) {
+  if (N <= 0) return 0;
+  CountLaunch(); PermuteVecKernel<<<(N + 255) / 256, 256, 0, AsStream(stream)>>>(N, d_perm, d_in, d_out, scatter);
+  return LaunchStatus();
+}
+
+// x[i] *= signs[i]
+int cxb_apply_signs(void* stream, int N, const double* d_signs, double* dx) {
+  if (N <= 0) return 0;
+  CountLaunch(); ApplySignsKernel<<<(N + 255) / 256, 256, 0, AsStream(stream)>>>(N, 1, d_signs, dx, N);
   return LaunchStatus();
 }
 

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) SchurKernel(ConeArgs c, double* G, l
 
 // Dense LMI blocks of order n <= 32, n % 4 == 0: the DMMA kernel of small_psd_mma.cuh (one CTA of 8 warps per
 // program, scaled matrices kept in shared memory).
+template <int NT>
 __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArgs c, double* G, long ldg, long gstride,
                                                                        double* AW, double* AQc, long vstride,
                                                                        double* scal, long sstride, int accumulate,
@@ -89,9 +90,9 @@ __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArg
   extern __shared__ __align__(16) double sm[];
   const int p = blockIdx.x;
   if (active && !active[p]) return;
-  psdmma::PsdSchurMma(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride,
-                      c.work + p * c.work_stride, sm, G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride,
-                      scal + p * sstride, accumulate != 0);
+  psdmma::PsdSchurMma<NT>(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride,
+                          c.work + p * c.work_stride, sm, G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride,
+                          scal + p * sstride, accumulate != 0);
 }
 
 __global__ void __launch_bounds__(kThreads) EigenKernel(ConeArgs c, const double* y, long ystride,
@@ -264,11 +265,19 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
   size_t mma_smem = 0;
   if (c.type == CXB_CONE_PSD && g_small_psd_mma && psdmma::Supported(c.n, c.m, &mma_smem) &&
       (c.data_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0) {
-    int rc = EnsureSmem(PsdSchurMmaKernel, mma_smem);
-    if (rc) return rc;
-    CountLaunch(); PsdSchurMmaKernel<<<batch, psdmma::kThreads, mma_smem, AsStream(stream)>>>(
-        c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
-    return LaunchStatus();
+    auto launch = [&](auto kernel) -> int {
+      int rc = EnsureSmem(kernel, mma_smem);
+      if (rc) return rc;
+      CountLaunch(); kernel<<<batch, psdmma::kThreads, mma_smem, AsStream(stream)>>>(
+          c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
+      return LaunchStatus();
+    };
+    switch ((c.n + 7) / 8) {
+      case 1: return launch(PsdSchurMmaKernel<1>);
+      case 2: return launch(PsdSchurMmaKernel<2>);
+      case 3: return launch(PsdSchurMmaKernel<3>);
+      default: return launch(PsdSchurMmaKernel<4>);
+    }
   }
   const size_t smem = SchurSmemBytes(c);
   int rc = EnsureSmem(SchurKernel, smem);

@@ -22,7 +22,10 @@
 namespace cxb {
 namespace psdmma {
 
-constexpr int kWarps = 8;
+// 16 warps per CTA (one CTA per SM: the scaled matrices of one program fill most of its shared memory): the phases are
+// chains of shared-memory loads and DMMAs, so the warps of ONE program are all the latency hiding there is
+// (8 warps: 32 us per program, profiles/r02_c_c3_launches_1024_programs.txt).
+constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 
 // smallest p >= x with p == 4 (mod 16): row pitch (doubles) that makes the 8 x 4 / 4 x 8 DMMA fragment loads
@@ -50,9 +53,18 @@ __host__ __device__ inline Layout MakeLayout(int n, int m) {
   const int mt = (m + 2 + 7) / 8;
   const int nb = (mt + 1) / 2;
   y.nblk = nb * (nb + 1) / 2;
-  y.ksplit = (2 * kWarps + y.nblk - 1) / y.nblk;
-  if (y.ksplit < 1) y.ksplit = 1;
-  if (y.ksplit > 8) y.ksplit = 8;
+  // split of the packed length: the (block, split) tasks should fill the warps evenly
+  y.ksplit = 1;
+  double best = 0;
+  for (int sp = 1; sp <= 8; sp++) {
+    const int tasks = y.nblk * sp;
+    const int rounds = (tasks + kWarps - 1) / kWarps;
+    const double eff = (double)tasks / (double)(rounds * kWarps);
+    if (eff > best + 1e-9) {
+      best = eff;
+      y.ksplit = sp;
+    }
+  }
   const long a_size = (long)(m + 1) * n * y.pa + 16;
   const long p_size = (long)y.ksplit * y.nblk * 256;
   y.off_l = 64;
@@ -89,6 +101,7 @@ __device__ __forceinline__ void WaitPending(int pending) {
 
 // AC: (m + 1) column-major n x n matrices; W: n x n (global). sm: dynamic shared memory (MakeLayout(n, m).total
 // doubles, at least the fallback's size). work: global scratch of the classic fallback.
+template <int NT>  // NT = ceil(n / 8): 8-wide tiles per side
 __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, const double* __restrict__ W,
                                    double* work, double* sm, double* G, long ldg, double* AW, double* AQc,
                                    double* scal, bool acc) {
@@ -168,8 +181,8 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
   }
 
   // ---- phase A: S_i = L^T (A_i L), packed ------------------------------------------------------------------
-  const int nt = (n + 7) / 8;  // 8-wide tiles per side (the last one may be ragged: its extra rows / columns
-                               // re-read row / column n - 1 and are never stored)
+  // the last of the NT 8-wide tiles per side may be ragged: its extra rows / columns re-read row / column n - 1
+  // and are never stored
   const double kSqrt2 = 1.4142135623730951;
   for (int r = 0; r < rounds; r++) {
     WaitPending(rounds - 1 - r);
@@ -177,21 +190,19 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
     const int i = r * kWarps + warp;
     if (i > m) continue;
     double* Ai = sA + (long)i * n * pa;
-    double accT[4][4][2];
+    double accT[NT][NT][2];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < NT; a++)
 #pragma unroll
-      for (int b = 0; b < 4; b++) accT[a][b][0] = accT[a][b][1] = 0.0;
+      for (int b = 0; b < NT; b++) accT[a][b][0] = accT[a][b][1] = 0.0;
     // T = A_i L: a = A(r0 + gid, k + tig) = Ai[(k + tig) * pa + r0 + gid] (A_i symmetric, column-major),
     //            b = L(k + tig, c0 + gid)
 #pragma unroll
-    for (int tc = 0; tc < 4; tc++) {
-      if (tc >= nt) break;
+    for (int tc = 0; tc < NT; tc++) {
       for (int k = tc * 8; k < n; k += 4) {
         const double b = sL[(k + tig) * pl + min(tc * 8 + gid, n - 1)];
 #pragma unroll
-        for (int tr = 0; tr < 4; tr++) {
-          if (tr >= nt) break;
+        for (int tr = 0; tr < NT; tr++) {
           const double a = Ai[(k + tig) * pa + min(tr * 8 + gid, n - 1)];
           Dmma884(accT[tr][tc][0], accT[tr][tc][1], a, b);
         }
@@ -200,11 +211,9 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
     __syncwarp();
     // T(row, col) -> Ai[row * pa + col] (row = the k index of the next product)
 #pragma unroll
-    for (int tr = 0; tr < 4; tr++) {
-      if (tr >= nt) break;
+    for (int tr = 0; tr < NT; tr++) {
 #pragma unroll
-      for (int tc = 0; tc < 4; tc++) {
-        if (tc >= nt) break;
+      for (int tc = 0; tc < NT; tc++) {
         const int row = tr * 8 + gid, col = tc * 8 + tig * 2;
         if (row < n) {
           if (col < n) Ai[row * pa + col] = accT[tr][tc][0];
@@ -217,22 +226,21 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
     // for k < r: the k loop starts at the tile's first row
     double* Xi = sX + (long)i * px;
 #pragma unroll
-    for (int tr = 0; tr < 4; tr++) {
-      if (tr >= nt) break;
-      double accS[4][2];
+    for (int tr = 0; tr < NT; tr++) {
+      double accS[NT][2];
 #pragma unroll
-      for (int b = 0; b < 4; b++) accS[b][0] = accS[b][1] = 0.0;
+      for (int b = 0; b < NT; b++) accS[b][0] = accS[b][1] = 0.0;
       for (int k = tr * 8; k < n; k += 4) {
         const double a = sL[(k + tig) * pl + min(tr * 8 + gid, n - 1)];
 #pragma unroll
-        for (int tc = 0; tc < 4; tc++) {
+        for (int tc = 0; tc < NT; tc++) {
           if (tc > tr) break;
           const double b = Ai[(k + tig) * pa + min(tc * 8 + gid, n - 1)];
           Dmma884(accS[tc][0], accS[tc][1], a, b);
         }
       }
 #pragma unroll
-      for (int tc = 0; tc < 4; tc++) {
+      for (int tc = 0; tc < NT; tc++) {
         if (tc > tr) break;
         const int row = tr * 8 + gid;
 #pragma unroll

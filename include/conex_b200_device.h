@@ -153,6 +153,24 @@ int cxb_ldlt_lower(void* stream, int N, double* dK, long ldk, double* d_signs, d
  * at pivot position i; d_tmp: N doubles. */
 int cxb_ldlt_solve(void* stream, int N, const double* dL, long ldl, const double* d_signs,
                    const int* d_perm, double* dx, double* d_tmp);
+/* ---- LDL^T over the fronts of the multifrontal solver (reference BlockLDLTInPlace,
+ * block_triangular_operations.cc:315-349: Eigen::RLDLT of every supernode's diagonal block, pivoting inside it) ----
+ * cxb_front_permute: dOut <- the front dF (rows x s lower trapezoid) under the supernode's pivot order: diagonal
+ *   block P F11 P^T, separator block with permuted columns.
+ * cxb_ldlt_partial: signed factorisation of the first `cols` columns of a rows x cols trapezoid: on top L11 with
+ *   F11 = L11 S L11^T, below G = F21 L11^{-T} S; the Schur complement of the rows below is F22 - G S G^T.
+ *   d_work: rows * 128 doubles. d_info[1] (regularised pivots, RLDLT.h:378-389) is reset by cxb_ldlt_begin only.
+ * cxb_scale_columns: dOut[:, c] = dA[:, c] * d_signs[c]   (G S for that Schur complement).
+ * cxb_permute_vec / cxb_apply_signs: the per-supernode permutations and S of the solves. */
+int cxb_ldlt_begin(void* stream, int* d_info);
+int cxb_front_permute(void* stream, int rows, int s_cols, const double* dF, long ld, const int* d_perm, double* dOut,
+                      long ldo);
+int cxb_ldlt_partial(void* stream, int rows, int cols, double* dF, long ld, double* d_signs, double* d_work,
+                     int* d_info);
+int cxb_scale_columns(void* stream, int rows, int cols, const double* dA, long lda, const double* d_signs,
+                      double* dOut, long ldo);
+int cxb_permute_vec(void* stream, int N, const int* d_perm, const double* d_in, double* d_out, int scatter);
+int cxb_apply_signs(void* stream, int N, const double* d_signs, double* dx);
 
 /* ---- K6: negative slack  out = sum_j coef[j] * Aall[:, j]  (dense_lmi_constraint.cc:8-27);
  * Aall is nn x cols column-major (ld = nn), d_coef has `cols` entries (y followed by -k for C). */
