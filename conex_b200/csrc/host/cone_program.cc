@@ -280,8 +280,7 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
   // factors its fronts in place and keeps no copy, so a configuration that asks for refinement gets the dense
   // solver unless the multifrontal one was requested explicitly (kind 2, which then fails loudly in SolveInPlace).
   const bool refinement_needs_dense = config.iterative_refinement_iterations > 0 && prog.kkt_solver_kind != 2;
-  if (prog.kkt_solver_kind != 1 && prog.NumberOfMultipliers() == 0 && !prog.ctx_.collective &&
-      !refinement_needs_dense) {
+  if (prog.kkt_solver_kind != 1 && !prog.ctx_.collective && !refinement_needs_dense) {
     std::vector<std::vector<int>> cliques;
     bool some_cone_couples_everything = false;
     for (const auto& c : prog.eqs) {
@@ -307,8 +306,7 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
       }
     }
   } else if (prog.kkt_solver_kind == 2) {
-    throw std::runtime_error("conex-b200: the supernodal KKT solver handles neither equality multipliers nor "
-                             "collective (multi-GPU) programs");
+    throw std::runtime_error("conex-b200: the supernodal KKT solver does not handle collective (multi-GPU) programs");
   }
   if (!reused) {
     prog.solver_is_multifrontal_ = fresh != nullptr;

@@ -341,9 +341,8 @@ bool SupernodalKKTSolver::Factor() {
   if (mode_ == CONEX_QR_FACTORIZATION) {
     throw std::runtime_error("conex-b200: the QR KKT mode is not implemented on the device");
   }
-  if (num_dual_ > 0) {
-    throw std::runtime_error("conex-b200: equality multipliers need the dense LDL^T solver");
-  }
+  if (num_dual_ > 0) return FactorLDLT();  // reference kkt_solver.cc:180-193
+  ldlt_factored_ = false;
   void* s = ctx_->stream();
   cudaStream_t main = ctx_->cuda_stream();
   int* info = ctx_->flags();
@@ -405,11 +404,101 @@ void SupernodalKKTSolver::EnqueueLeaf(size_t leaf_number, int* info) {
   CudaCheck(cudaEventRecord(lane.factored, lane.stream), "cudaEventRecord");
 }
 
+// Every front in node order on the main stream: pivot order of the supernode from the current diagonal of its block
+// (one small D2H per front), the front permuted into fronts_p_, signed partial factorisation, Schur complement
+// (G S) G^T scattered into the ancestors. The regularised factorisation never fails (kkt_solver.cc:187-193).
+bool SupernodalKKTSolver::FactorLDLT() {
+  void* s = ctx_->stream();
+  if (fronts_p_.size() == 0) {
+    size_t max_rows = 1, max_s = 1, max_ps = 1;
+    for (const Front& f : fronts_meta_) {
+      max_rows = std::max<size_t>(max_rows, f.s + f.p);
+      max_s = std::max<size_t>(max_s, f.s);
+      max_ps = std::max<size_t>(max_ps, static_cast<size_t>(f.p) * f.s);
+    }
+    fronts_p_.Resize(static_cast<size_t>(std::max<long>(total_, 1)));
+    signs_.Resize(static_cast<size_t>(std::max(N_, 1)));
+    pivots_.Resize(static_cast<size_t>(std::max(N_, 1)));
+    ldlt_work_.Resize(max_rows * 128 + max_rows);
+    gs_.Resize(max_ps);
+    diag_.Resize(max_s);
+    host_pivots_.assign(std::max(N_, 1), 0);
+  }
+  int* info = ctx_->flags() + 2;
+  DeviceCheck(cxb_ldlt_begin(s, info), "cxb_ldlt_begin");
+  std::vector<double> d;
+  for (const Front& f : fronts_meta_) {
+    double* F = fronts_.get() + f.offset;
+    double* Fp = fronts_p_.get() + f.offset;
+    const long ld = f.s + f.p;
+    DeviceCheck(cxb_copy_strided(s, f.s, F, ld + 1, diag_.get(), 1), "cxb_copy_strided");
+    d.resize(f.s);
+    ctx_->Download(d.data(), diag_.get(), f.s);
+    const std::vector<int> order = RldltPivotOrderForTest(d);
+    std::copy(order.begin(), order.end(), host_pivots_.begin() + f.first);
+    // (pageable source: staged before the call returns)
+    CudaCheck(cudaMemcpyAsync(pivots_.get() + f.first, host_pivots_.data() + f.first, sizeof(int) * f.s,
+                              cudaMemcpyHostToDevice, ctx_->cuda_stream()),
+              "upload of a supernode's pivot order");
+    DeviceCheck(cxb_front_permute(s, f.s + f.p, f.s, F, ld, pivots_.get() + f.first, Fp, ld), "cxb_front_permute");
+    DeviceCheck(cxb_ldlt_partial(s, f.s + f.p, f.s, Fp, ld, signs_.get() + f.first, ldlt_work_.get(), info),
+                "cxb_ldlt_partial");
+    if (f.p == 0) continue;
+    const double* G = Fp + f.s;
+    DeviceCheck(cxb_scale_columns(s, f.p, f.s, G, ld, signs_.get() + f.first, gs_.get(), f.p), "cxb_scale_columns");
+    DeviceCheck(cxb_dgemm(s, 0, 1, f.p, f.p, f.s, 1.0, gs_.get(), f.p, 0, G, ld, 0, 0.0, schur_.get(), f.p, 0, 1, 1),
+                "cxb_dgemm(Schur complement of a front, LDL^T)");
+    DeviceCheck(cxb_scatter_lower_indexed(s, f.p, schur_.get(), f.p, update_idx_.get() + f.update_offset, -1.0,
+                                          fronts_.get()),
+                "cxb_scatter_lower_indexed(update)");
+  }
+  int host_info[2] = {0, 0};
+  ctx_->DownloadInts(host_info, info, 2);
+  factorization_regularized_ = host_info[1] != 0;
+  ldlt_factored_ = true;
+  return true;
+}
+
+// x = Pi^T M^{-T} S M^{-1} Pi b with Pi = diag(P_k) and M the block lower-triangular factor [L_k; G_k].
+void SupernodalKKTSolver::SolveLDLT(double* y) const {
+  void* s = ctx_->stream();
+  double* tmp = diag_.get();  // >= the largest supernode
+  DeviceCheck(cxb_gather_vec(s, N_, y, perm_.get(), x_.get()), "cxb_gather_vec");
+  for (const Front& f : fronts_meta_) {
+    const double* Fp = fronts_p_.get() + f.offset;
+    const long ld = f.s + f.p;
+    double* xk = x_.get() + f.first;
+    DeviceCheck(cxb_permute_vec(s, f.s, pivots_.get() + f.first, xk, tmp, 0), "cxb_permute_vec");
+    ctx_->CopyOnDevice(xk, tmp, f.s);
+    DeviceCheck(cxb_trsv_lower(s, f.s, Fp, ld, xk, 0), "cxb_trsv_lower");
+    DeviceCheck(cxb_front_forward(s, f.p, f.s, Fp + f.s, ld, xk, sep_pos_.get() + f.sep_offset, x_.get()),
+                "cxb_front_forward");
+  }
+  DeviceCheck(cxb_apply_signs(s, N_, signs_.get(), x_.get()), "cxb_apply_signs");
+  for (auto it = fronts_meta_.rbegin(); it != fronts_meta_.rend(); ++it) {
+    const Front& f = *it;
+    const double* Fp = fronts_p_.get() + f.offset;
+    const long ld = f.s + f.p;
+    double* xk = x_.get() + f.first;
+    DeviceCheck(cxb_front_backward(s, f.p, f.s, Fp + f.s, ld, xk, sep_pos_.get() + f.sep_offset, x_.get()),
+                "cxb_front_backward");
+    DeviceCheck(cxb_trsv_lower(s, f.s, Fp, ld, xk, 1), "cxb_trsv_lower");
+    DeviceCheck(cxb_permute_vec(s, f.s, pivots_.get() + f.first, xk, tmp, 1), "cxb_permute_vec");
+    ctx_->CopyOnDevice(xk, tmp, f.s);
+  }
+  ctx_->Zero(y, N_);
+  DeviceCheck(cxb_scatter_add_vec(s, N_, x_.get(), perm_.get(), y), "cxb_scatter_add_vec");
+}
+
 void SupernodalKKTSolver::SolveInPlace(Ref* b) const {
   if (iterative_refinement_iterations_ > 0) {
     throw std::runtime_error("conex-b200: iterative refinement is implemented for the dense KKT solver only");
   }
   void* s = ctx_->stream();
+  if (ldlt_factored_) {
+    for (int col = 0; col < b->cols; col++) SolveLDLT(b->col(col));
+    return;
+  }
   for (int col = 0; col < b->cols; col++) {
     double* y = b->col(col);
     DeviceCheck(cxb_gather_vec(s, N_, y, perm_.get(), x_.get()), "cxb_gather_vec");

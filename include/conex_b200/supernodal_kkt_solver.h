@@ -55,6 +55,7 @@ class SupernodalKKTSolver : public KKTSolver {
   void SetIterativeRefinementIterations(int x) override { iterative_refinement_iterations_ = x; }
   void SetNumberOfMultipliers(int n) override { num_dual_ = n; }
   int NumberOfSupernodes() const override { return static_cast<int>(st_.supernodes.size()); }
+  bool factorization_regularized() const { return factorization_regularized_; }
 
  private:
   struct Front {
@@ -90,6 +91,17 @@ class SupernodalKKTSolver : public KKTSolver {
   std::vector<int> leaves_;                   // node indices without children, ascending
   std::vector<char> is_leaf_;
   void EnqueueLeaf(size_t leaf_number, int* info);
+  // LDL^T over the fronts (programs with equality multipliers; reference BlockLDLTInPlace,
+  // block_triangular_operations.cc:315-349): every supernode's diagonal block is factored as P^T L S L^T P with the
+  // pivot order Eigen::RLDLT derives from the block's diagonal at that point, S = diag(+-1), regularised pivots as in
+  // RLDLT.h:378-389. The permuted, factored fronts live in fronts_p_ (the Schur updates still go to fronts_).
+  bool FactorLDLT();
+  void SolveLDLT(double* y) const;
+  DeviceBuffer<double> fronts_p_, signs_, ldlt_work_, gs_, diag_;
+  DeviceBuffer<int> pivots_;                  // per supernode (at its first elimination position): its pivot order
+  std::vector<int> host_pivots_;
+  bool ldlt_factored_ = false;
+  bool factorization_regularized_ = false;
   mutable DeviceBuffer<double> x_;            // right-hand side in elimination order
   mutable DeviceBuffer<double> dense_;        // KKTMatrix() export
   std::vector<DeviceBuffer<long>> cone_idx_;  // per cone: destinations of the lower triangle of its G

@@ -294,6 +294,56 @@ def test_sparse_programs_match_oracle_and_dense_solver(shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", ["chain", "arrow", "two_blocks_on_one_clique"])
+def test_sparse_programs_with_equality_constraints_take_ldlt_fronts(shape):
+    """Equality constraints (conex/test/equality_constraints_test.cc: Basic / Many / ManySeparate shapes) placed on the
+    cliques of chordal-sparse programs: the multipliers are extra unknowns of their clique, the fronts are factored
+    by the regularised LDL^T with pivoting inside every supernode (reference BlockLDLTInPlace,
+    block_triangular_operations.cc:315-349, driven by kkt_solver.cc:180-193) instead of falling back to one dense
+    supernode. Oracle vs dense device solver vs multifrontal device solver."""
+    import devlib
+    dev, ora = devlib.product(), oracle()
+    rng = np.random.default_rng(17)
+    if shape == "arrow":
+        m, cones = block_arrow_program(blocks=4, private=6, shared=3, order=7, seed=1)
+        eq_sets = [[0, 1, 2], [24, 25, 26, 7]]          # inside cone 0; shared variables + one of cone 1
+    else:
+        m, cones = chain_program(links=5, width=6, overlap=2, order=6, seed=2)
+        eq_sets = [[4, 5, 6]] if shape == "chain" else [[8, 9, 10], [9, 11, 12, 13]]   # one / two blocks on clique 2
+    y0 = 0.02 * rng.standard_normal(m)
+    equalities = []
+    for variables in eq_sets:
+        rows = 2 if len(variables) > 3 else 1
+        A = rng.uniform(-1, 1, size=(rows, len(variables)))
+        equalities.append((A, A @ y0[variables], variables))
+    out = []
+    for L, kind in ((ora, None), (dev, 1), (dev, 2)):
+        P = L.program(m)
+        if kind is not None:
+            L.lib.CONEXB200_SetKKTSolverKind.argtypes = [C.c_void_p, C.c_int]
+            L.lib.CONEXB200_SetKKTSolverKind.restype = None
+            L.lib.CONEXB200_SetKKTSolverKind(P.h, kind)
+        for mats, Cm, variables in cones:
+            P.add_dense_lmi(mats, Cm, variables)
+        for A, beq, variables in equalities:
+            P.add_equality(A, beq, variables)
+        b = P.feasible_objective()
+        solved, y = P.maximize(b, L.default_config())
+        nodes = L.lib.CONEXB200_GetNumberOfSupernodes(P.h) if kind is not None else 1
+        out.append((solved, y, P.iteration_log(), nodes))
+    (so, yo, lo, _), (sd, yd, ld, nd), (ss, ys, ls, ns) = out
+    assert nd == 1 and ns > 1
+    assert so == sd == ss == 1
+    assert abs(len(lo) - len(ls)) <= 1 and abs(len(ld) - len(ls)) <= 1
+    for ref in (lo, ld):
+        assert abs(ref[-1]["by"] - ls[-1]["by"]) <= 1e-7 * max(1.0, abs(ref[-1]["by"]))
+    assert np.abs(yo - ys).max() <= 1e-6 * max(1.0, np.abs(yo).max())
+    assert np.abs(yd - ys).max() <= 1e-6 * max(1.0, np.abs(yd).max())
+    for A, beq, variables in equalities:
+        assert np.abs(A @ ys[variables] - beq).max() <= 1e-8
+
+
+@pytest.mark.gpu
 def test_iterative_refinement_on_a_sparse_program_takes_the_dense_solver():
     """A configuration that is valid in the reference (kkt_solver.cc:248-261, kkt_solver_options_test.cc) must not
     turn into "not solved" because the clique structure made the library pick the multifrontal solver: with
