@@ -40,11 +40,43 @@ size_t SchurSmemBytes(const ConeArgs& c) {
   return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? (size_t)small::PsdSchurSmemDoubles(c.n, c.m, kThreads) : 0));
 }
 
-__global__ void __launch_bounds__(kThreads) SetIdentityKernel(ConeArgs c, const int* active) {
+// Two thread layouts for the same phase-structured math (small_cone_math.cuh):
+//   WARP == false: one CTA of kThreads threads per program (DeviceTeam, block barriers between phases);
+//   WARP == true : one WARP per program, several programs per CTA (WarpTeam: __syncwarp + shuffles). The phases of
+//                  these cones are short (a 20 x 20 Lanczos step, a column of a 40 x 40 Cholesky), so the barrier, not
+//                  the arithmetic, is what a phase costs; default for everything but the team version of the LMI Schur
+//                  kernel (cxb_set_small_team_mode).
+// `per` = doubles of dynamic shared memory per program.
+template <bool WARP>
+struct TeamOf {
+  using type = DeviceTeam;
+  static __device__ __forceinline__ DeviceTeam Make(double* base) { return DeviceTeam(base); }
+};
+template <>
+struct TeamOf<true> {
+  using type = WarpTeam;
+  static __device__ __forceinline__ WarpTeam Make(double*) { return WarpTeam(); }
+};
+template <bool WARP>
+__device__ __forceinline__ bool Slot(int batch, long per, double* sm, const int* active, int* p, double** base) {
+  if (WARP) {
+    const int w = threadIdx.x >> 5;
+    *p = blockIdx.x * (blockDim.x >> 5) + w;
+    *base = sm + w * per;
+  } else {
+    *p = blockIdx.x;
+    *base = sm;
+  }
+  return *p < batch && !(active && !active[*p]);
+}
+
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) SetIdentityKernel(int batch, long per, ConeArgs c, const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
   double* st = c.state + p * c.state_stride;
   if (c.type == CXB_CONE_LP) {
     t.par(c.n, [&](int i) { st[i] = 1.0; });
@@ -55,14 +87,16 @@ __global__ void __launch_bounds__(kThreads) SetIdentityKernel(ConeArgs c, const 
   }
 }
 
-__global__ void __launch_bounds__(kThreads) SchurKernel(ConeArgs c, double* G, long ldg, long gstride,
-                                                        double* AW, double* AQc, long vstride,
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) SchurKernel(int batch, long per, ConeArgs c, double* G, long ldg,
+                                                        long gstride, double* AW, double* AQc, long vstride,
                                                         double* scal, long sstride, int accumulate,
                                                         const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
   const double* data = c.data + p * c.data_stride;
   double* st = c.state + p * c.state_stride;
   double* work = c.work ? c.work + p * c.work_stride : nullptr;
@@ -76,11 +110,11 @@ __global__ void __launch_bounds__(kThreads) SchurKernel(ConeArgs c, double* G, l
   } else if (c.type == CXB_CONE_SOC) {
     small::SocSchur(t, c.n + 1, c.m, data, st, work, g, ldg, aw, aq, sc, acc);
   } else {
-    small::PsdSchur(t, c.n, c.m, data, st, work, sm + 64, g, ldg, aw, aq, sc, acc);
+    small::PsdSchur(t, c.n, c.m, data, st, work, base + 64, g, ldg, aw, aq, sc, acc);
   }
 }
 
-// Dense LMI blocks of order n <= 32, n % 4 == 0: the DMMA kernel of small_psd_mma.cuh (one CTA of 8 warps per
+// Dense LMI blocks of order n <= 32, n % 4 == 0: the DMMA kernel of small_psd_mma.cuh (one CTA of 16 warps per
 // program, scaled matrices kept in shared memory).
 template <int NT>
 __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArgs c, double* G, long ldg, long gstride,
@@ -95,13 +129,15 @@ __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArg
                           scal + p * sstride, accumulate != 0);
 }
 
-__global__ void __launch_bounds__(kThreads) EigenKernel(ConeArgs c, const double* y, long ystride,
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) EigenKernel(int batch, long per, ConeArgs c, const double* y, long ystride,
                                                         double cw, const double* cw_p, double* out4,
                                                         long ostride, const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
   const double* data = c.data + p * c.data_stride;
   double* st = c.state + p * c.state_stride;
   double* work = c.work ? c.work + p * c.work_stride : nullptr;
@@ -115,18 +151,20 @@ __global__ void __launch_bounds__(kThreads) EigenKernel(ConeArgs c, const double
     small::SocEigen(t, c.n + 1, c.m, data, yp, k, st, work, out);
   } else {
     const long nnp = Align4((long)c.n * c.n);
-    small::PsdEigen(t, c.n, c.m, data, yp, k, st, st + nnp, st + 2 * nnp, sm + 64, out);
+    small::PsdEigen(t, c.n, c.m, data, yp, k, st, st + nnp, st + 2 * nnp, base + 64, out);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) PrepareKernel(ConeArgs c, const double* y, long ystride,
-                                                          int affine, double cw, const double* cw_p,
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) PrepareKernel(int batch, long per, ConeArgs c, const double* y,
+                                                          long ystride, int affine, double cw, const double* cw_p,
                                                           double ew, double* out2, long ostride,
                                                           const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
   const double* data = c.data + p * c.data_stride;
   double* st = c.state + p * c.state_stride;
   double* work = c.work ? c.work + p * c.work_stride : nullptr;
@@ -141,16 +179,19 @@ __global__ void __launch_bounds__(kThreads) PrepareKernel(ConeArgs c, const doub
     small::SocPrepare(t, c.n + 1, c.m, data, yp, k, st, st + op, work, out);
   } else {
     const long nnp = Align4((long)c.n * c.n);
-    small::PsdPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + nnp, st + 2 * nnp, sm + 64, out);
+    small::PsdPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + nnp, st + 2 * nnp, base + 64, out);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) TakeStepKernel(ConeArgs c, double step, const double* step_p,
-                                                           double ew, int* info, const int* active) {
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) TakeStepKernel(int batch, long per, ConeArgs c, double step,
+                                                           const double* step_p, double ew, int* info,
+                                                           const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
   double* st = c.state + p * c.state_stride;
   double* work = c.work ? c.work + p * c.work_stride : nullptr;
   const double s = step_p ? step_p[p] : step;
@@ -162,26 +203,30 @@ __global__ void __launch_bounds__(kThreads) TakeStepKernel(ConeArgs c, double st
     small::SocTakeStep(t, c.n + 1, s, st, st + op, work);
   } else {
     const long nnp = Align4((long)c.n * c.n);
-    small::PsdTakeStep(t, c.n, s, ew, st, st + 2 * nnp, sm + 64, info + p);
+    small::PsdTakeStep(t, c.n, s, ew, st, st + 2 * nnp, base + 64, info + p);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) PotrfKernel(int N, double* H, long ldh, long hstride, int* info,
-                                                        const int* active) {
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) PotrfKernel(int batch, long per, int N, double* H, long ldh, long hstride,
+                                                        int* info, const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
-  small::SmallPotrf(t, N, H + p * hstride, ldh, sm + 64, info + p);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
+  small::SmallPotrf(t, N, H + p * hstride, ldh, base + 64, info + p);
 }
 
-__global__ void __launch_bounds__(kThreads) PotrsKernel(int N, const double* L, long ldl, long lstride,
-                                                        double* X, long xstride, const int* active) {
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) PotrsKernel(int batch, long per, int N, const double* L, long ldl,
+                                                        long lstride, double* X, long xstride, const int* active) {
   extern __shared__ double sm[];
-  const int p = blockIdx.x;
-  if (active && !active[p]) return;
-  DeviceTeam t(sm);
-  small::SmallPotrs(t, N, L + p * lstride, ldl, X + p * xstride, sm + 64);
+  int p;
+  double* base;
+  if (!Slot<WARP>(batch, per, sm, active, &p, &base)) return;
+  auto t = TeamOf<WARP>::Make(base);
+  small::SmallPotrs(t, N, L + p * lstride, ldl, X + p * xstride, base + 64);
 }
 
 __global__ void LincombKernel(int n, const double* a, const double* x, long xs, const double* b,
@@ -219,7 +264,8 @@ int EnsureSmem(K kernel, size_t bytes) {
   return 0;
 }
 
-int g_small_psd_mma = 1;  // cxb_set_small_psd_mma(0): A/B switch back to the DFMA team kernel
+int g_small_psd_mma = 1;   // cxb_set_small_psd_mma(0): A/B switch back to the DFMA team kernel
+int g_small_team_mode = 1;  // cxb_set_small_team_mode(0): one CTA per program instead of one warp per program
 
 bool ValidCone(const cxb_small_cone* c) {
   if (!c || c->n < 1 || c->m < 1 || !c->data || !c->state) return false;
@@ -248,11 +294,46 @@ size_t cxb_small_work_size(int type, int n, int m) {
   return (size_t)(m + 2) * n * n;
 }
 
+namespace {
+// Launch geometry of the two layouts: `per` doubles of shared memory per program. Warp layout: as many programs
+// per CTA (<= 4 warps) as fit in ~100 KB, so that at least two CTAs share an SM.
+struct Geometry {
+  bool warp;
+  int grid, threads;
+  long per;
+  size_t smem;
+};
+Geometry MakeGeometry(int batch, size_t per_program_bytes) {
+  Geometry g;
+  g.per = (long)(per_program_bytes / sizeof(double));
+  // a single program (the LP / SOC plugins of CONEX_Maximize) keeps the whole CTA: its cones can be large
+  g.warp = g_small_team_mode != 0 && batch >= 8;
+  if (g.warp) {
+    int w = (int)((100 * 1024) / (per_program_bytes > 0 ? per_program_bytes : 1));
+    w = w < 1 ? 1 : (w > 4 ? 4 : w);
+    g.threads = 32 * w;
+    g.grid = (batch + w - 1) / w;
+    g.smem = per_program_bytes * w;
+  } else {
+    g.threads = kThreads;
+    g.grid = batch;
+    g.smem = per_program_bytes;
+  }
+  return g;
+}
+}  // namespace
+
 int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active) {
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
-  CountLaunch(); SetIdentityKernel<<<batch, kThreads, sizeof(double) * 64, AsStream(stream)>>>(c, d_active);
+  const Geometry g = MakeGeometry(batch, sizeof(double) * 64);
+  CountLaunch();
+  if (g.warp) {
+    SetIdentityKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(batch, g.per, c, d_active);
+  } else {
+    SetIdentityKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(batch, g.per, c, d_active);
+  }
   return LaunchStatus();
 }
 
@@ -279,15 +360,31 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
       default: return launch(PsdSchurMmaKernel<4>);
     }
   }
-  const size_t smem = SchurSmemBytes(c);
-  int rc = EnsureSmem(SchurKernel, smem);
-  if (rc) return rc;
-  CountLaunch(); SchurKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dG, ldg, gstride, dAW, dAQc, vstride,
-                                                            d_scal, sstride, accumulate, d_active);
+  // LP / SOC cones: warp layout; the team version of the LMI Schur kernel keeps the CTA layout (its register tiles
+  // and staging groups are sized for 128 threads)
+  Geometry g = MakeGeometry(batch, SchurSmemBytes(c));
+  if (c.type == CXB_CONE_PSD && g.warp) {
+    g.warp = false;
+    g.threads = kThreads;
+    g.grid = batch;
+    g.smem = SchurSmemBytes(c);
+  }
+  if (g.warp) {
+    int rc = EnsureSmem(SchurKernel<true>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); SchurKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
+  } else {
+    int rc = EnsureSmem(SchurKernel<false>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); SchurKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
+  }
   return LaunchStatus();
 }
 
 void cxb_set_small_psd_mma(int enabled) { g_small_psd_mma = enabled; }
+void cxb_set_small_team_mode(int mode) { g_small_team_mode = mode; }
 
 int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const double* dy, long ystride,
                     double c_weight, const double* d_cw, double* d_out4, long ostride,
@@ -295,11 +392,18 @@ int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const d
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
-  const size_t smem = SmemBytes(c);
-  int rc = EnsureSmem(EigenKernel, smem);
-  if (rc) return rc;
-  CountLaunch(); EigenKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dy, ystride, c_weight, d_cw, d_out4,
-                                                            ostride, d_active);
+  const Geometry g = MakeGeometry(batch, SmemBytes(c));
+  if (g.warp) {
+    int rc = EnsureSmem(EigenKernel<true>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); EigenKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, dy, ystride, c_weight, d_cw, d_out4, ostride, d_active);
+  } else {
+    int rc = EnsureSmem(EigenKernel<false>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); EigenKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, dy, ystride, c_weight, d_cw, d_out4, ostride, d_active);
+  }
   return LaunchStatus();
 }
 
@@ -309,11 +413,18 @@ int cxb_small_prepare(void* stream, int batch, const cxb_small_cone* cone, const
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
-  const size_t smem = SmemBytes(c);
-  int rc = EnsureSmem(PrepareKernel, smem);
-  if (rc) return rc;
-  CountLaunch(); PrepareKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, dy, ystride, affine, c_weight, d_cw,
-                                                              e_weight, d_out2, ostride, d_active);
+  const Geometry g = MakeGeometry(batch, SmemBytes(c));
+  if (g.warp) {
+    int rc = EnsureSmem(PrepareKernel<true>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); PrepareKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, dy, ystride, affine, c_weight, d_cw, e_weight, d_out2, ostride, d_active);
+  } else {
+    int rc = EnsureSmem(PrepareKernel<false>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); PrepareKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, dy, ystride, affine, c_weight, d_cw, e_weight, d_out2, ostride, d_active);
+  }
   return LaunchStatus();
 }
 
@@ -323,31 +434,54 @@ int cxb_small_take_step(void* stream, int batch, const cxb_small_cone* cone, dou
   if (!ValidCone(cone)) return -1;
   if (cone->type == CXB_CONE_PSD && !d_info) return -1;
   const ConeArgs c = Convert(cone);
-  const size_t smem = SmemBytes(c);
-  int rc = EnsureSmem(TakeStepKernel, smem);
-  if (rc) return rc;
-  CountLaunch(); TakeStepKernel<<<batch, kThreads, smem, AsStream(stream)>>>(c, step, d_step, e_weight, d_info,
-                                                               d_active);
+  const Geometry g = MakeGeometry(batch, SmemBytes(c));
+  if (g.warp) {
+    int rc = EnsureSmem(TakeStepKernel<true>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); TakeStepKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, step, d_step, e_weight, d_info, d_active);
+  } else {
+    int rc = EnsureSmem(TakeStepKernel<false>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); TakeStepKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(
+        batch, g.per, c, step, d_step, e_weight, d_info, d_active);
+  }
   return LaunchStatus();
 }
 
 int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long hstride, int* d_info,
                     const int* d_active) {
   if (batch <= 0 || N <= 0) return 0;
-  const size_t smem = sizeof(double) * (64 + (size_t)N * N);
-  int rc = EnsureSmem(PotrfKernel, smem);
-  if (rc) return rc;
-  CountLaunch(); PotrfKernel<<<batch, kThreads, smem, AsStream(stream)>>>(N, dH, ldh, hstride, d_info, d_active);
+  const Geometry g = MakeGeometry(batch, sizeof(double) * (64 + (size_t)N * N));
+  if (g.warp) {
+    int rc = EnsureSmem(PotrfKernel<true>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); PotrfKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(batch, g.per, N, dH, ldh, hstride,
+                                                                                   d_info, d_active);
+  } else {
+    int rc = EnsureSmem(PotrfKernel<false>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); PotrfKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(batch, g.per, N, dH, ldh, hstride,
+                                                                                    d_info, d_active);
+  }
   return LaunchStatus();
 }
 
 int cxb_small_potrs(void* stream, int batch, int N, const double* dL, long ldl, long lstride, double* dX,
                     long xstride, const int* d_active) {
   if (batch <= 0 || N <= 0) return 0;
-  const size_t smem = sizeof(double) * (64 + (size_t)N);
-  int rc = EnsureSmem(PotrsKernel, smem);
-  if (rc) return rc;
-  CountLaunch(); PotrsKernel<<<batch, kThreads, smem, AsStream(stream)>>>(N, dL, ldl, lstride, dX, xstride, d_active);
+  const Geometry g = MakeGeometry(batch, sizeof(double) * (64 + (size_t)N));
+  if (g.warp) {
+    int rc = EnsureSmem(PotrsKernel<true>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); PotrsKernel<true><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(batch, g.per, N, dL, ldl, lstride, dX,
+                                                                                   xstride, d_active);
+  } else {
+    int rc = EnsureSmem(PotrsKernel<false>, g.smem);
+    if (rc) return rc;
+    CountLaunch(); PotrsKernel<false><<<g.grid, g.threads, g.smem, AsStream(stream)>>>(batch, g.per, N, dL, ldl, lstride, dX,
+                                                                                    xstride, d_active);
+  }
   return LaunchStatus();
 }
 

@@ -77,4 +77,66 @@ struct DeviceTeam {
   }
 };
 
+// The same team interface on ONE WARP: every phase boundary is a __syncwarp() and the reductions are shuffles, so a
+// small problem whose phases are short (Lanczos on a 20 x 20 block: ~10 steps of two 20-entry matvecs and two dot
+// products; a 40 x 40 Cholesky: 40 columns) pays a few cycles per phase instead of a 128-thread barrier, and four
+// problems share a CTA. Reductions combine in a fixed order (shfl_down tree, result broadcast from lane 0).
+struct WarpTeam {
+  int tid;
+  static constexpr unsigned kFull = 0xffffffffu;
+
+  __device__ WarpTeam() : tid(threadIdx.x & 31) {}
+
+  __device__ __forceinline__ int size() const { return 32; }
+
+  template <class F>
+  __device__ __forceinline__ void par(int n, F f) {
+    for (int i = tid; i < n; i += 32) f(i);
+    __syncwarp();
+  }
+  template <class F>
+  __device__ __forceinline__ double sum(int n, F f) {
+    double v = 0;
+    for (int i = tid; i < n; i += 32) v += f(i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
+    v = __shfl_sync(kFull, v, 0);
+    __syncwarp();
+    return v;
+  }
+  template <class F>
+  __device__ __forceinline__ double maxv(int n, F f) {
+    double v = -1.7976931348623157e308;
+    for (int i = tid; i < n; i += 32) v = fmax(v, f(i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    __syncwarp();
+    return v;
+  }
+  template <class F>
+  __device__ __forceinline__ double minv(int n, F f) {
+    double v = 1.7976931348623157e308;
+    for (int i = tid; i < n; i += 32) v = fmin(v, f(i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    __syncwarp();
+    return v;
+  }
+  template <class F>
+  __device__ __forceinline__ double bcast(F f) {
+    __syncwarp();
+    double v = 0;
+    if (tid == 0) v = f();
+    v = __shfl_sync(kFull, v, 0);
+    __syncwarp();
+    return v;
+  }
+  template <class F>
+  __device__ __forceinline__ void single(F f) {
+    __syncwarp();
+    if (tid == 0) f();
+    __syncwarp();
+  }
+};
+
 }  // namespace cxb

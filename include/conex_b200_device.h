@@ -291,6 +291,10 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
 /* A/B switch of the dense-LMI branch of cxb_small_schur: 1 (default) = DMMA kernel with the scaled matrices in
  * shared memory for blocks of order n <= 32, n % 4 == 0 (device/small_psd_mma.cuh); 0 = the DFMA team kernel. */
 void cxb_set_small_psd_mma(int enabled);
+/* Thread layout of the other small-cone kernels (eigen-bounds, PrepareStep, TakeStep, the small Cholesky and its
+ * solves, the LP / SOC Schur systems): 1 (default) = one WARP per program, several programs per CTA (phases separated
+ * by __syncwarp, reductions by shuffles); 0 = one CTA of 128 threads per program (block barriers). Same arithmetic. */
+void cxb_set_small_team_mode(int mode);
 /* out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} of Q(w^{1/2})(c_weight c - A y)
  * (GetWeightedSlackEigenvalues). c_weight: per-program device array d_cw (stride 1) when not NULL,
  * else the scalar. */

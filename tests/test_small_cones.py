@@ -110,9 +110,10 @@ SHAPES = [(LP, 1, 1), (LP, 7, 3), (LP, 40, 40), (SOC, 1, 2), (SOC, 10, 40), (SOC
 @pytest.mark.parametrize("kind,n,m", SHAPES)
 def test_cone_trajectory_matches_oracle(be, kind, n, m):
     """Schur system, eigen-bounds, step norms and the updated scaling point along three damped
-    Newton-like steps, for a batch of 3 independent problems."""
+    Newton-like steps, for a batch of 9 independent problems (from 8 programs on the device kernels run one WARP per
+    program, below that one CTA per program: test_both_thread_layouts_give_the_same_results covers the other one)."""
     rng = np.random.Generator(np.random.PCG64(1000 * kind + 10 * n + m))
-    B = 3
+    B = 9
     data = np.stack([random_cone_data(kind, n, m, rng) for _ in range(B)])
     cone = be.cone(kind, n, m, data)
     refs = [OracleCone(kind, n, m, data[p]) for p in range(B)]
@@ -182,7 +183,7 @@ def test_schur_accumulates_over_cones(be):
 @pytest.mark.parametrize("N", [1, 2, 17, 40, 100])
 def test_small_cholesky_and_solve(be, N):
     rng = np.random.Generator(np.random.PCG64(N))
-    B = 3
+    B = 9
     H = []
     for _ in range(B):
         R = rng.uniform(-1, 1, size=(N, N + 3))
@@ -263,4 +264,36 @@ def test_dmma_schur_kernel_against_the_dfma_team_kernel(n, m):
             close(x, y, 1e-12, name)
     for x, y in zip(out[0][0], out[0][1]):
         close(2 * x, y, 1e-12, "accumulate")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,m", [(LP, 40, 40), (SOC, 10, 40), (PSD, 20, 40), (PSD, 9, 4)])
+def test_both_thread_layouts_give_the_same_results(kind, n, m):
+    """cxb_set_small_team_mode: one warp per program (default for batches) against one CTA per program, on the same
+    batch: Schur system, eigen-bounds, step norms, updated scaling point."""
+    be = Backend("device")
+    rng = np.random.Generator(np.random.PCG64(31 * kind + n + m))
+    B = 11
+    data = np.stack([random_cone_data(kind, n, m, rng) for _ in range(B)])
+    y = rng.uniform(-0.05, 0.05, size=(B, m))
+    out = []
+    for mode in (1, 0):
+        be.lib.cxb_set_small_team_mode(mode)
+        try:
+            cone = be.cone(kind, n, m, data)
+            res = [cone.schur()]
+            res.append(cone.eigen(y, 1.0))
+            res.append(cone.prepare(y, 1.0))
+            cone.take_step(0.5)
+            res.append(cone.get_state())
+            res.append(cone.schur())
+            out.append(res)
+        finally:
+            be.lib.cxb_set_small_team_mode(1)
+    for a, b in zip(out[0], out[1]):
+        if isinstance(a, tuple):
+            for x, z in zip(a, b):
+                close(x, z, 1e-11, "schur")
+        else:
+            close(a, b, 1e-8, "eigen / prepare / state")
 
