@@ -375,39 +375,93 @@ __global__ void ResetInfoKernel2(int* info) { *info = 0; }
 
 }  // namespace
 
-// In-place LU with partial pivoting: P A = L U.
+namespace {
+// Per host thread: a high-priority side stream for the look-ahead of LuFactor (see cholesky.cu for the same scheme).
+struct LuLookAhead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t updated = nullptr, factored = nullptr;
+  int device = -1;
+  bool Prepare() {
+    int current = 0;
+    if (cudaGetDevice(&current) != cudaSuccess) return false;
+    if (side && device == current) return true;
+    if (side) {
+      cudaStreamDestroy(side);
+      cudaEventDestroy(updated);
+      cudaEventDestroy(factored);
+      side = nullptr;
+    }
+    device = current;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+    return cudaEventCreateWithFlags(&updated, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&factored, cudaEventDisableTiming) == cudaSuccess;
+  }
+};
+thread_local LuLookAhead t_lu_lookahead;
+int g_lu_lookahead = 1;  // cxb_set_lu_mode(0): sequential schedule (A/B)
+
+void LaunchPanel(cudaStream_t s, int n, int j0, int nb, double* A, long lda, int* ipiv, int* info) {
+  // sub-panel width by what fits on chip: 8 columns up to 3200 rows, 4 up to 6400, else the global-memory kernel
+  const size_t rows = (size_t)(n - j0);
+  CountLaunch();
+  if (rows * 8 * sizeof(double) <= (size_t)kLuPanelSmemBytes) {
+    LuPanelSmemKernel<8><<<1, 1024, rows * 8 * sizeof(double), s>>>(n, j0, nb, A, lda, ipiv, info);
+  } else if (rows * 4 * sizeof(double) <= (size_t)kLuPanelSmemBytes) {
+    LuPanelSmemKernel<4><<<1, 1024, rows * 4 * sizeof(double), s>>>(n, j0, nb, A, lda, ipiv, info);
+  } else {
+    LuPanelKernel<<<1, 1024, 0, s>>>(n, j0, nb, A, lda, ipiv, info);
+  }
+}
+
+// Panel (j0, nb) -> columns [c0, c1) right of it: row interchanges, U12 = L11^{-1} A12, A22 -= L21 U12.
+int ApplyPanel(cudaStream_t s, int n, int j0, int nb, double* A, long lda, const int* ipiv, int c0, int c1) {
+  const int cols = c1 - c0;
+  if (cols <= 0) return 0;
+  CountLaunch(); LaswpKernel<<<(cols + 127) / 128, 128, 0, s>>>(j0, nb, ipiv, A, lda, c0, c1);
+  double* A12 = A + (long)c0 * lda + j0;
+  CountLaunch(); TrsmDiagKernel<false><<<(cols + kRhsCols - 1) / kRhsCols, 256, TrsmSmem(nb), s>>>(
+      nb, A + (long)j0 * lda + j0, lda, A12, lda, cols);
+  const int below = n - j0 - nb;
+  if (below <= 0) return 0;
+  const double* L21 = A + (long)j0 * lda + j0 + nb;
+  return Dgemm(s, false, false, below, cols, nb, -1.0, L21, lda, 0, A12, lda, 0, 1.0, A12 + nb, lda, 0, 1, false);
+}
+}  // namespace
+
+// In-place LU with partial pivoting: P A = L U. Right-looking with a look-ahead of one panel: after panel J the
+// columns of panel J + 1 are updated first and that panel is factored on a high-priority side stream (one CTA: 32
+// dependent pivot columns) WHILE the main stream applies panel J to everything right of it. Every entry receives
+// the same operations in the same order as in the sequential schedule: the factors are bit-identical.
 int LuFactor(cudaStream_t s, int n, double* A, long lda, int* ipiv, int* info) {
   ConfigureOnce();
   CountLaunch(); ResetInfoKernel2<<<1, 1, 0, s>>>(info);
+  LuLookAhead& la = t_lu_lookahead;
+  const bool ahead = g_lu_lookahead && n > 4 * kLuNB && la.Prepare();
+  LaunchPanel(s, n, 0, min(kLuNB, n), A, lda, ipiv, info);
   for (int j0 = 0; j0 < n; j0 += kLuNB) {
     const int nb = min(kLuNB, n - j0);
-    // sub-panel width by what fits on chip: 8 columns up to 3200 rows, 4 up to 6400, else the
-    // global-memory kernel
-    const size_t rows = (size_t)(n - j0);
-    CountLaunch();
-    if (rows * 8 * sizeof(double) <= (size_t)kLuPanelSmemBytes) {
-      LuPanelSmemKernel<8><<<1, 1024, rows * 8 * sizeof(double), s>>>(n, j0, nb, A, lda, ipiv, info);
-    } else if (rows * 4 * sizeof(double) <= (size_t)kLuPanelSmemBytes) {
-      LuPanelSmemKernel<4><<<1, 1024, rows * 4 * sizeof(double), s>>>(n, j0, nb, A, lda, ipiv, info);
+    // panel (j0, nb) is factored and visible to the main stream here
+    if (j0 > 0) {
+      CountLaunch(); LaswpKernel<<<(j0 + 127) / 128, 128, 0, s>>>(j0, nb, ipiv, A, lda, 0, j0);
+    }
+    const int n0 = j0 + nb;  // first column of the next panel
+    if (n0 >= n) break;
+    const int nb1 = min(kLuNB, n - n0);
+    int rc = ApplyPanel(s, n, j0, nb, A, lda, ipiv, n0, n0 + nb1);
+    if (rc != 0) return rc;
+    if (ahead) {
+      cudaEventRecord(la.updated, s);
+      cudaStreamWaitEvent(la.side, la.updated, 0);
+      LaunchPanel(la.side, n, n0, nb1, A, lda, ipiv, info);
+      cudaEventRecord(la.factored, la.side);
     } else {
-      LuPanelKernel<<<1, 1024, 0, s>>>(n, j0, nb, A, lda, ipiv, info);
+      LaunchPanel(s, n, n0, nb1, A, lda, ipiv, info);
     }
-    if (j0 > 0) CountLaunch();
-    if (j0 > 0) LaswpKernel<<<(j0 + 127) / 128, 128, 0, s>>>(j0, nb, ipiv, A, lda, 0, j0);
-    const int rest = n - j0 - nb;
-    if (rest > 0) {
-      CountLaunch(); LaswpKernel<<<(rest + 127) / 128, 128, 0, s>>>(j0, nb, ipiv, A, lda, j0 + nb, n);
-      // U12 = L11^{-1} A12
-      double* A12 = A + (long)(j0 + nb) * lda + j0;
-      CountLaunch(); TrsmDiagKernel<false><<<(rest + kRhsCols - 1) / kRhsCols, 256, TrsmSmem(nb), s>>>(
-          nb, A + (long)j0 * lda + j0, lda, A12, lda, rest);
-      // A22 -= L21 U12
-      const double* L21 = A + (long)j0 * lda + j0 + nb;
-      double* A22 = A + (long)(j0 + nb) * lda + j0 + nb;
-      const int rc = Dgemm(s, false, false, rest, rest, nb, -1.0, L21, lda, 0, A12, lda, 0, 1.0, A22,
-                           lda, 0, 1, false);
-      if (rc != 0) return rc;
-    }
+    rc = ApplyPanel(s, n, j0, nb, A, lda, ipiv, n0 + nb1, n);
+    if (rc != 0) return rc;
+    if (ahead) cudaStreamWaitEvent(s, la.factored, 0);
   }
   return LaunchStatus();
 }
@@ -475,6 +529,8 @@ int PadeExpm(cudaStream_t s, int n, const double* X, double* out, double* work, 
 using namespace cxb;
 
 extern "C" {
+
+void cxb_set_lu_mode(int lookahead) { g_lu_lookahead = lookahead; }
 
 size_t cxb_geodesic_worksize(int n) { return (size_t)4 * n * n; }
 

@@ -231,6 +231,8 @@ int cxb_pade_expm(void* stream, int n, const double* d_X, double* d_out, double*
 /* Partial-pivot LU solve A X = B (A n x n destroyed, B n x nrhs overwritten by X). */
 int cxb_lu_solve(void* stream, int n, double* dA, long lda, int nrhs, double* dB, long ldb,
                  int* d_ipiv, int* d_info);
+/* A/B switch of the LU factorisation's schedule: 1 (default) = look-ahead of one panel on a side stream, 0 = sequential. */
+void cxb_set_lu_mode(int lookahead);
 
 /* ---- small vector / matrix helpers used by the host loop -------------------------------------*/
 /* W <- I (psd_constraint.cc:92-95) */
