@@ -470,6 +470,10 @@ def batched_bench(proc, args, w, cpu_leg):
 
 def run_b200_batched(args):
     proc = Process()
+    if args.small_psd_mma >= 0:
+        proc.L.cxb_set_small_psd_mma(args.small_psd_mma)
+    if args.small_team_mode >= 0:
+        proc.L.cxb_set_small_team_mode(args.small_team_mode)
     line = batched_bench(proc, args, workload_shape(args), cpu_leg=not args.no_cpu_baseline)
     if line is not None:
         print(json.dumps(line))
@@ -1037,6 +1041,8 @@ def main():
     ap.add_argument("--no-full-solve", action="store_true", help="skip the default-configuration solve to termination")
     ap.add_argument("--no-extra", action="store_true", help="c2: skip the C5 and C3 blocks that ride along in the line")
     ap.add_argument("--cpu-size", type=int, default=0, help="override n = m of the CPU sample (testing)")
+    ap.add_argument("--small-psd-mma", type=int, default=-1, help="c3 A/B: cxb_set_small_psd_mma (2 default, 1, 0)")
+    ap.add_argument("--small-team-mode", type=int, default=-1, help="c3 A/B: cxb_set_small_team_mode (1 default, 0)")
     ap.add_argument("--replicated-cholesky", action="store_true",
                     help="N > 1: factor the Schur complement on every rank instead of across the ranks")
     ap.add_argument("--cholesky-block", type=int, default=0, help="N > 1: block-column width (<= 512)")

@@ -130,6 +130,20 @@ __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArg
                           accumulate != 0);
 }
 
+template <int NT>
+__global__ void __launch_bounds__(psdmma::kThreads2, 2) PsdSchurMma2Kernel(ConeArgs c, double* G, long ldg, long gstride,
+                                                                         double* AW, double* AQc, long vstride,
+                                                                         double* scal, long sstride, int accumulate,
+                                                                         const int* active) {
+  extern __shared__ __align__(16) double sm[];
+  const int p = blockIdx.x;
+  if (active && !active[p]) return;
+  double* work = c.work + p * c.work_stride;
+  psdmma::PsdSchurMma2<NT>(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride, work, work, sm,
+                           G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride, scal + p * sstride,
+                           accumulate != 0);
+}
+
 // L = chol(W) of every program's block, one warp per program, into the head of the program's `work` area.
 __global__ void __launch_bounds__(128) PsdFactorKernel(int batch, ConeArgs c, const int* active) {
   extern __shared__ double sm[];
@@ -275,7 +289,10 @@ int EnsureSmem(K kernel, size_t bytes) {
   return 0;
 }
 
-int g_small_psd_mma = 1;   // cxb_set_small_psd_mma(0): A/B switch back to the DFMA team kernel
+// dense-LMI branch of cxb_small_schur (cxb_set_small_psd_mma): 2 = DMMA kernel, 8 warps per CTA, two CTAs per SM
+// (default; falls back to 1 when its shared memory does not fit twice); 1 = DMMA kernel, 16 warps, whole operator in
+// shared memory, one CTA per SM; 0 = the DFMA team kernel
+int g_small_psd_mma = 2;
 int g_small_team_mode = 1;  // cxb_set_small_team_mode(0): one CTA per program instead of one warp per program
 
 bool ValidCone(const cxb_small_cone* c) {
@@ -355,18 +372,29 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
   size_t mma_smem = 0;
-  if (c.type == CXB_CONE_PSD && g_small_psd_mma && psdmma::Supported(c.n, c.m, &mma_smem) &&
-      (c.data_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0) {
+  const bool aligned = (c.data_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0;
+  const bool two_per_sm = g_small_psd_mma == 2 && c.type == CXB_CONE_PSD && aligned && psdmma::Supported2(c.n, c.m, &mma_smem);
+  if (two_per_sm || (c.type == CXB_CONE_PSD && g_small_psd_mma && aligned && psdmma::Supported(c.n, c.m, &mma_smem))) {
+    const int threads = two_per_sm ? psdmma::kThreads2 : psdmma::kThreads;
     auto launch = [&](auto kernel) -> int {
       int rc = EnsureSmem(kernel, mma_smem);
       if (rc) return rc;
       CountLaunch(); PsdFactorKernel<<<(batch + 3) / 4, 128, sizeof(double) * 4 * (psdmma::LImageDoubles(c.n) + 2),
                                        AsStream(stream)>>>(batch, c, d_active);
-      CountLaunch(); kernel<<<batch, psdmma::kThreads, mma_smem, AsStream(stream)>>>(
+      CountLaunch(); kernel<<<batch, threads, mma_smem, AsStream(stream)>>>(
           c, dG, ldg, gstride, dAW, dAQc, vstride, d_scal, sstride, accumulate, d_active);
       return LaunchStatus();
     };
-    switch ((c.n + 7) / 8) {
+    const int nt = (c.n + 7) / 8;
+    if (two_per_sm) {
+      switch (nt) {
+        case 1: return launch(PsdSchurMma2Kernel<1>);
+        case 2: return launch(PsdSchurMma2Kernel<2>);
+        case 3: return launch(PsdSchurMma2Kernel<3>);
+        default: return launch(PsdSchurMma2Kernel<4>);
+      }
+    }
+    switch (nt) {
       case 1: return launch(PsdSchurMmaKernel<1>);
       case 2: return launch(PsdSchurMmaKernel<2>);
       case 3: return launch(PsdSchurMmaKernel<3>);

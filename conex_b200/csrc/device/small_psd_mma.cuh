@@ -328,5 +328,193 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
   }
 }
 
+// ---- second layout: 8 warps per CTA, two CTAs per SM ---------------------------------------------------------------
+// The kernel above keeps the whole operator of its program in shared memory (one CTA per SM), so its phases — wait
+// for the data, scale, Gram, write — run strictly one after the other on that SM. Here a warp owns ONE slot of n x pa
+// doubles: it streams its matrices i = warp, warp + 8, ... through it (cp.async by its own lanes, T = A_i L in
+// place, S_i packed into X), so a CTA needs the packed X plus eight slots (100.7 KB at n = 20, m = 40) and two CTAs
+// share an SM: while one waits for data or runs its Gram, the other scales. The Gram is not split along the packed
+// length: a warp takes whole 16 x 16 blocks and writes its results straight from the accumulators.
+constexpr int kWarps2 = 8;
+constexpr int kThreads2 = kWarps2 * 32;
+
+struct Layout2 {
+  int kp, k4, pa, pl, px;
+  long off_l, off_x, off_s, total;
+};
+__host__ __device__ inline Layout2 MakeLayout2(int n, int m) {
+  Layout2 y;
+  y.kp = n * (n + 1) / 2;
+  y.k4 = (y.kp + 3) / 4 * 4;
+  y.pa = Pitch4Mod16(n);
+  y.pl = Pitch4Mod16(n);
+  y.px = Pitch4Mod16(y.k4);
+  y.off_l = 64;
+  y.off_x = y.off_l + LImageDoubles(n);
+  y.off_s = y.off_x + (long)(m + 2) * y.px;
+  y.total = y.off_s + (long)kWarps2 * n * y.pa + 16;
+  return y;
+}
+__host__ inline bool Supported2(int n, int m, size_t* smem_bytes) {
+  if (n < 4 || n > 32 || (n % 4) != 0 || m < 1 || m + 2 > 1024) return false;
+  const Layout2 y = MakeLayout2(n, m);
+  const long fallback = 64 + small::PsdSchurSmemDoubles(n, m, kThreads2);
+  const long total = y.total > fallback ? y.total : fallback;
+  *smem_bytes = sizeof(double) * (size_t)total;
+  return *smem_bytes <= 113 * 1024;  // two CTAs per SM
+}
+
+template <int NT>
+__device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC, const double* __restrict__ W,
+                                    const double* __restrict__ factor, double* work, double* sm, double* G, long ldg,
+                                    double* AW, double* AQc, double* scal, bool acc) {
+  const Layout2 y = MakeLayout2(n, m);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nn = n * n, pa = y.pa, pl = y.pl, px = y.px, kp = y.kp;
+  double* sL = sm + y.off_l;
+  double* sX = sm + y.off_x;
+  double* Ai = sm + y.off_s + (long)warp * n * pa;  // this warp's slot
+  const int half = n / 2;                            // 16-byte chunks per column
+  auto fetch = [&](int i) {  // matrix i -> the slot, by this warp's lanes
+    const double* src = AC + (long)i * nn;
+    for (int q = lane; q < n * half; q += 32) {
+      const int col = q / half, within = q - col * half;
+      CpAsync16(Ai + (long)col * pa + 2 * within, src + (long)col * n + 2 * within, 16);
+    }
+    CpAsyncCommit();
+  };
+  for (int q = tid; q < LImageDoubles(n) / 2; q += kThreads2) CpAsync16(sL + 2 * q, factor + 2 * q, 16);
+  CpAsyncCommit();
+  if (warp <= m) fetch(warp);
+  for (int e = tid; e < (m + 2) * (px - kp); e += kThreads2) {
+    const int row = e / (px - kp), q = kp + e % (px - kp);
+    sX[(long)row * px + q] = 0.0;
+  }
+  for (int e = tid; e < kp; e += kThreads2) sX[(long)(m + 1) * px + e] = 0.0;
+  __syncthreads();
+  for (int c = tid; c < n; c += kThreads2) sX[(long)(m + 1) * px + c * n - c * (c - 1) / 2] = 1.0;
+  CpAsyncWait<0>();
+  __syncthreads();  // L, the first matrix of every warp, the padding of X
+  if (factor[LImageDoubles(n)] != 0.0) {
+    DeviceTeam t(sm);
+    small::PsdSchurClassic(t, n, m, AC, W, work, sm + 64, G, ldg, AW, AQc, scal, acc);
+    return;
+  }
+  const double kSqrt2 = 1.4142135623730951;
+  for (int i = warp; i <= m; i += kWarps2) {
+    double accT[NT][NT][2];
+#pragma unroll
+    for (int a = 0; a < NT; a++)
+#pragma unroll
+      for (int b = 0; b < NT; b++) accT[a][b][0] = accT[a][b][1] = 0.0;
+#pragma unroll
+    for (int tc = 0; tc < NT; tc++) {
+      for (int k = tc * 8; k < n; k += 4) {
+        const double b = sL[(k + tig) * pl + min(tc * 8 + gid, n - 1)];
+#pragma unroll
+        for (int tr = 0; tr < NT; tr++) {
+          const double a = Ai[(k + tig) * pa + min(tr * 8 + gid, n - 1)];
+          Dmma884(accT[tr][tc][0], accT[tr][tc][1], a, b);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int tr = 0; tr < NT; tr++) {
+#pragma unroll
+      for (int tc = 0; tc < NT; tc++) {
+        const int row = tr * 8 + gid, col = tc * 8 + tig * 2;
+        if (row < n) {
+          if (col < n) Ai[row * pa + col] = accT[tr][tc][0];
+          if (col + 1 < n) Ai[row * pa + col + 1] = accT[tr][tc][1];
+        }
+      }
+    }
+    __syncwarp();
+    double accS[NT][NT][2];
+#pragma unroll
+    for (int tr = 0; tr < NT; tr++) {
+#pragma unroll
+      for (int b = 0; b < NT; b++) accS[tr][b][0] = accS[tr][b][1] = 0.0;
+      for (int k = tr * 8; k < n; k += 4) {
+        const double a = sL[(k + tig) * pl + min(tr * 8 + gid, n - 1)];
+#pragma unroll
+        for (int tc = 0; tc < NT; tc++) {
+          if (tc > tr) break;
+          const double b = Ai[(k + tig) * pa + min(tc * 8 + gid, n - 1)];
+          Dmma884(accS[tr][tc][0], accS[tr][tc][1], a, b);
+        }
+      }
+    }
+    __syncwarp();  // the slot is free: the next matrix travels while S_i is packed
+    if (i + kWarps2 <= m) fetch(i + kWarps2);
+    double* Xi = sX + (long)i * px;
+#pragma unroll
+    for (int tr = 0; tr < NT; tr++) {
+#pragma unroll
+      for (int tc = 0; tc < NT; tc++) {
+        if (tc > tr) break;
+        const int row = tr * 8 + gid;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int col = tc * 8 + tig * 2 + e;
+          if (row < n && col <= row) {
+            Xi[col * n - col * (col - 1) / 2 + (row - col)] =
+                (row == col) ? accS[tr][tc][e] : kSqrt2 * accS[tr][tc][e];
+          }
+        }
+      }
+    }
+    CpAsyncWait<0>();
+    __syncwarp();
+  }
+  __syncthreads();  // X complete
+
+  const int MI = m + 2, MJ = m + 1;
+  const int nb = ((MI + 7) / 8 + 1) / 2;
+  const int nblk = nb * (nb + 1) / 2;
+  const int ksteps = y.k4 / 4;
+  for (int blk = warp; blk < nblk; blk += kWarps2) {
+    int bj = 0, rem = blk;
+    while (rem >= nb - bj) {
+      rem -= nb - bj;
+      bj++;
+    }
+    const int bi = bj + rem;
+    const double* xa0 = sX + (long)min(16 * bi + gid, MI - 1) * px + tig;
+    const double* xa1 = sX + (long)min(16 * bi + 8 + gid, MI - 1) * px + tig;
+    const double* xb0 = sX + (long)min(16 * bj + gid, MI - 1) * px + tig;
+    const double* xb1 = sX + (long)min(16 * bj + 8 + gid, MI - 1) * px + tig;
+    double c00[2] = {0, 0}, c01[2] = {0, 0}, c10[2] = {0, 0}, c11[2] = {0, 0};
+    for (int k = 0; k < ksteps; k++) {
+      const double a0 = xa0[4 * k], a1 = xa1[4 * k], b0 = xb0[4 * k], b1 = xb1[4 * k];
+      Dmma884(c00[0], c00[1], a0, b0);
+      if (bi != bj) Dmma884(c01[0], c01[1], a0, b1);  // above the diagonal inside a diagonal block
+      Dmma884(c10[0], c10[1], a1, b0);
+      Dmma884(c11[0], c11[1], a1, b1);
+    }
+    auto put = [&](int i, int j, double s) {
+      if (i >= MI || j >= MJ || i < j) return;
+      if (i < m) {
+        small::Accumulate(G + (long)j * ldg + i, s, acc);
+      } else if (i == m) {
+        small::Accumulate(j < m ? AQc + j : scal + 1, s, acc);
+      } else {
+        small::Accumulate(j < m ? AW + j : scal + 0, s, acc);
+      }
+    };
+    const int i0 = 16 * bi + gid, j0 = 16 * bj + tig * 2;
+    put(i0, j0, c00[0]);
+    put(i0, j0 + 1, c00[1]);
+    put(i0, j0 + 8, c01[0]);
+    put(i0, j0 + 9, c01[1]);
+    put(i0 + 8, j0, c10[0]);
+    put(i0 + 8, j0 + 1, c10[1]);
+    put(i0 + 8, j0 + 8, c11[0]);
+    put(i0 + 8, j0 + 9, c11[1]);
+  }
+}
+
 }  // namespace psdmma
 }  // namespace cxb

@@ -290,8 +290,9 @@ int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, 
 int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double* dG, long ldg,
                     long gstride, double* dAW, double* dAQc, long vstride, double* d_scal,
                     long sstride, int accumulate, const int* d_active);
-/* A/B switch of the dense-LMI branch of cxb_small_schur: 1 (default) = DMMA kernel with the scaled matrices in
- * shared memory for blocks of order n <= 32, n % 4 == 0 (device/small_psd_mma.cuh); 0 = the DFMA team kernel. */
+/* A/B switch of the dense-LMI branch of cxb_small_schur for blocks of order n <= 32, n % 4 == 0
+ * (device/small_psd_mma.cuh): 2 (default) = DMMA kernel, one slot per warp, two CTAs per SM; 1 = DMMA kernel with the
+ * whole operator of a program in shared memory, one CTA per SM; 0 = the DFMA team kernel. */
 void cxb_set_small_psd_mma(int enabled);
 /* Thread layout of the other small-cone kernels (eigen-bounds, PrepareStep, TakeStep, the small Cholesky and its
  * solves, the LP / SOC Schur systems): 1 (default) = one WARP per program, several programs per CTA (phases separated

@@ -249,7 +249,7 @@ def test_dmma_schur_kernel_against_the_dfma_team_kernel(n, m):
         R = rng.uniform(-1, 1, size=(n, n))
         Ws.append((R @ R.T / n + 0.5 * np.eye(n)).ravel(order="F"))
     out = []
-    for enabled in (1, 0):
+    for enabled in (2, 1, 0):
         be.lib.cxb_set_small_psd_mma(enabled)
         try:
             cone = be.cone(PSD, n, m, data)
@@ -258,10 +258,11 @@ def test_dmma_schur_kernel_against_the_dfma_team_kernel(n, m):
             second = cone.schur(accumulate_into=cone.last)   # G <- 2 G
             out.append((first, second))
         finally:
-            be.lib.cxb_set_small_psd_mma(1)
-    for (a, b) in zip(out[0], out[1]):
-        for x, y, name in zip(a, b, ("H", "AW", "AQc", "scalars")):
-            close(x, y, 1e-12, name)
+            be.lib.cxb_set_small_psd_mma(2)
+    for variant in (0, 1):   # both DMMA layouts against the DFMA team kernel
+        for (a, b) in zip(out[variant], out[2]):
+            for x, y, name in zip(a, b, ("H", "AW", "AQc", "scalars")):
+                close(x, y, 1e-12, name)
     for x, y in zip(out[0][0], out[0][1]):
         close(2 * x, y, 1e-12, "accumulate")
 
