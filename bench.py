@@ -802,7 +802,11 @@ def run_reference(args):
 ASSEMBLY_TRAFFIC_C2 = {
     1: dict(bytes=61 * (2.381e9 + 1.998e9) + 1.3545e12, source="profiles/r01_d_c2_dgemm_ncu_full.txt (classic form: 61 panels x "
             "(K1a 2.38 GB + K1b 2.00 GB) + K2 1354.5 GB of tile re-reads at 36 % L2 hit)"),
-    3: None,
+    3: dict(bytes=60 * (1.348e9 + 1.027e9 + 0.648e9 + 0.547e9) + (0.861e9 + 0.644e9 + 0.419e9 + 0.340e9) + 400.12e9,
+            source="profiles/r02_e_c2_symmetric_assembly_ncu_full.txt (symmetric form: 60 panels of 33 matrices x (K1a A_i L 2.38 GB "
+                   "+ K1b L^T T with packed store 1.20 GB) + one of 21 + K2 packed Gram 400 GB read at 58 % L2 hit for 35 GB of "
+                   "operand; all three kernels run at 91-92 % DMMA-pipe active, i.e. tensor-bound; algorithmic minimum 64 GB of A "
+                   "read + 35 GB of packed matrices written and read once)"),
 }
 FORM_NAMES = {0: "undecided", 1: "classic (W A_i W kept)", 2: "row panels (classic, streamed)", 3: "symmetric (packed L^T A_i L)",
               4: "entry-sparse gathers"}
@@ -1006,6 +1010,8 @@ def compact(line):
 
 def run_b200(args):
     proc = Process()
+    if args.gemm_max_ktiles >= 0:
+        proc.L.cxb_set_gemm_split_policy(args.gemm_max_ktiles)
     w = workload_shape(args)
     line = dense_bench(proc, args, w, args.steps, args.warmup, full_solve=not args.no_full_solve,
                        cpu_leg=not args.no_cpu_baseline and proc.rank == 0 and proc.world == 1)
@@ -1041,6 +1047,7 @@ def main():
     ap.add_argument("--no-full-solve", action="store_true", help="skip the default-configuration solve to termination")
     ap.add_argument("--no-extra", action="store_true", help="c2: skip the C5 and C3 blocks that ride along in the line")
     ap.add_argument("--cpu-size", type=int, default=0, help="override n = m of the CPU sample (testing)")
+    ap.add_argument("--gemm-max-ktiles", type=int, default=-1, help="A/B: cxb_set_gemm_split_policy")
     ap.add_argument("--small-psd-mma", type=int, default=-1, help="c3 A/B: cxb_set_small_psd_mma (2 default, 1, 0)")
     ap.add_argument("--small-team-mode", type=int, default=-1, help="c3 A/B: cxb_set_small_team_mode (1 default, 0)")
     ap.add_argument("--replicated-cholesky", action="store_true",

@@ -297,6 +297,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
   }
 }
 
+int g_max_ktiles_per_cta = 0;  // cxb_set_gemm_split_policy: 0 = split K only to fill the machine
+
 // C = alpha * sum_s partials[s] + beta * C (fixed summation order s = 0, 1, ...).
 __global__ void __launch_bounds__(256) SplitKReduceKernel(int M, int N, int splits,
                                                           const double* __restrict__ partials,
@@ -369,6 +371,29 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
           splits = s;
         }
       }
+    }
+  }
+  if (g_max_ktiles_per_cta > 0 && batch == 1 && kt_total > g_max_ktiles_per_cta) {
+    // Deep contractions (the Gram over K = n^2 or the packed length): a CTA that walks 10^4 k-tiles drifts away from
+    // the CTAs sharing its operand panels by more than L2 holds, and the panels are re-read from DRAM (K2 of C2:
+    // 400 GB for 35 GB of operand, profiles/r02_e_c2_symmetric_assembly_ncu_full.txt). Shorter CTAs stay aligned.
+    // Bounded by a partial-sum workspace of 768 MB.
+    const long ws_cap = (768L << 20) / ((long)g.M * g.N * 8);
+    int want = (kt_total + g_max_ktiles_per_cta - 1) / g_max_ktiles_per_cta;
+    if (want > ws_cap) want = (int)ws_cap;
+    if (want > splits) {
+      int best_s = want;
+      double best_eff = 0;
+      for (int s = want; s < want + 8 && s <= ws_cap; s++) {
+        const long ctas = active * s;
+        const long waves = (ctas + kSlots - 1) / kSlots;
+        const double eff = (double)ctas / (double)(waves * kSlots);
+        if (eff > best_eff + 1e-9) {
+          best_eff = eff;
+          best_s = s;
+        }
+      }
+      splits = best_s;
     }
   }
   if (batch != 1 || g.mirror || g.pack || g.tri) splits = 1;
@@ -521,3 +546,4 @@ extern "C" int cxb_dgemm_ex(void* stream, int config, int splits, int transA, in
 }
 
 extern "C" void cxb_set_default_gemm_config(int config) { cxb::SetDefaultGemmConfig(config); }
+extern "C" void cxb_set_gemm_split_policy(int max_ktiles_per_cta) { cxb::g_max_ktiles_per_cta = max_ktiles_per_cta; }

@@ -33,9 +33,39 @@ CXB_HD void Accumulate(double* dst, double v, bool acc) { *dst = acc ? *dst + v 
 template <class T>
 CXB_HD void NegativeSlack(T& t, int rows, int m, const double* data, const double* y, double k,
                           double* out) {
-  // Eight independent loads in flight per thread and step: the columns are 8 * rows bytes apart in HBM, and a loop
-  // that consumes each load before issuing the next one pays the full memory latency m times per row (this phase
-  // reads the whole cone data and was latency-bound: 1.6 TB/s with 32 warps per SM). Same summation order.
+  // Independent loads in flight per thread: the columns are 8 * rows bytes apart in HBM, and a loop that consumes each
+  // load before issuing the next one pays the full memory latency m times per row (this phase reads the whole cone
+  // data and was latency-bound: 1.6 TB/s with 32 warps per SM). Even row counts on 16-byte aligned data: two rows per
+  // thread, eight 16-byte loads in flight. Same summation order per row.
+#ifdef __CUDA_ARCH__
+  if ((rows & 1) == 0 && (reinterpret_cast<unsigned long long>(data) & 15) == 0) {
+    t.par(rows / 2, [&](int q) {
+      const double2* col = reinterpret_cast<const double2*>(data) + q;
+      const long stride = rows / 2;
+      double s0 = 0, s1 = 0;
+      int j = 0;
+      for (; j + 8 <= m; j += 8) {
+        double2 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) a[u] = col[(long)(j + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          s0 += a[u].x * y[j + u];
+          s1 += a[u].y * y[j + u];
+        }
+      }
+      const double2 c = col[(long)m * stride];
+      for (; j < m; j++) {
+        const double2 a = col[(long)j * stride];
+        s0 += a.x * y[j];
+        s1 += a.y * y[j];
+      }
+      out[2 * q] = s0 - k * c.x;
+      out[2 * q + 1] = s1 - k * c.y;
+    });
+    return;
+  }
+#endif
   t.par(rows, [&](int r) {
     double s = 0;
     int j = 0;
@@ -55,9 +85,48 @@ CXB_HD void NegativeSlack(T& t, int rows, int m, const double* data, const doubl
 // =================================================================================================
 // LP cone. state: W[n], t1[n], t2[n].
 // =================================================================================================
+// sm: nullptr, or LpSchurSmemDoubles(n, m) doubles of team-shared scratch: the scaled operator [W A | W c] is staged
+// there once (coalesced read of the cone data) and the m (m + 1) / 2 inner products run out of it; without it every
+// pair re-reads two columns of the operator from global memory with a stride of n doubles between threads. Same
+// products, same summation order.
+CXB_HOST_DEVICE long LpSchurSmemDoubles(int n, int m) { return (long)(n | 1) * (m + 1); }
 template <class T>
 CXB_HD void LpSchur(T& t, int n, int m, const double* Ac, const double* W, double* G, long ldg,
-                    double* AW, double* AQc, double* scal, bool acc) {
+                    double* AW, double* AQc, double* scal, bool acc, double* sm = nullptr) {
+  if (sm != nullptr) {
+    const int P = n | 1;  // odd pitch: threads on consecutive columns hit different banks
+    t.par(n * (m + 1), [&](int e) {
+      const int r = e % n, j = e / n;
+      sm[(long)j * P + r] = W[r] * Ac[e];
+    });
+    const double* wc = sm + (long)m * P;
+    t.par(m * m, [&](int e) {
+      const int i = e % m, j = e / m;
+      if (i < j) return;
+      const double* ai = sm + (long)i * P;
+      const double* aj = sm + (long)j * P;
+      double s = 0;
+      for (int r = 0; r < n; r++) s += ai[r] * aj[r];
+      Accumulate(G + (long)j * ldg + i, s, acc);
+    });
+    t.par(m, [&](int j) {
+      const double* aj = sm + (long)j * P;
+      double aw = 0, aq = 0;
+      for (int r = 0; r < n; r++) {
+        aw += aj[r];
+        aq += aj[r] * wc[r];
+      }
+      Accumulate(AW + j, aw, acc);
+      Accumulate(AQc + j, aq, acc);
+    });
+    const double s1 = t.sum(n, [&](int r) { return wc[r]; });
+    const double s2 = t.sum(n, [&](int r) { return wc[r] * wc[r]; });
+    t.single([&]() {
+      Accumulate(scal + 0, s1, acc);
+      Accumulate(scal + 1, s2, acc);
+    });
+    return;
+  }
   const double* c = Ac + (long)m * n;
   t.par(m * m, [&](int e) {
     const int i = e % m, j = e / m;

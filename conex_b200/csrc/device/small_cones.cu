@@ -33,11 +33,29 @@ ConeArgs Convert(const cxb_small_cone* c) {
 // Shared memory (doubles) needed by the PSD paths: 6 n^2 matrices + Lanczos vectors + slack + the scratch of the
 // multi-section eigenvalue brackets.
 size_t PsdSmemDoubles(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64 + 2 * small::kSections + 16; }
+// Second-order cones keep their scratch (o (m + 2) doubles: w^{1/2} and the scaled operator) in shared memory
+// instead of the global `work` area: every use of it is local to one call.
+// (Cones too large for that — more than kStagedLimit doubles — keep the global paths.)
+constexpr long kStagedLimit = 12 * 1024;  // 96 KB
+__host__ __device__ inline long SocScratchDoubles(int n, int m) { return (long)(n + 1) * (m + 2) + 4 * (long)(n + 1); }
 size_t SmemBytes(const ConeArgs& c) {
+  if (c.type == CXB_CONE_SOC) {
+    const long need = SocScratchDoubles(c.n, c.m);
+    return sizeof(double) * (64 + (need <= kStagedLimit ? need : 0));
+  }
   return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? PsdSmemDoubles(c.n) : 0));
 }
 size_t SchurSmemBytes(const ConeArgs& c) {
-  return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? (size_t)small::PsdSchurSmemDoubles(c.n, c.m, kThreads) : 0));
+  if (c.type == CXB_CONE_SOC) return SmemBytes(c);
+  if (c.type == CXB_CONE_LP) {
+    const long need = small::LpSchurSmemDoubles(c.n, c.m);
+    return sizeof(double) * (64 + (need <= kStagedLimit ? need : 0));
+  }
+  return sizeof(double) * (64 + (size_t)small::PsdSchurSmemDoubles(c.n, c.m, kThreads));
+}
+// The scratch of a second-order cone: shared memory when the launch reserved it, else the global work area.
+__device__ __forceinline__ double* SocScratch(const ConeArgs& c, long per, double* base, double* work) {
+  return per >= 64 + SocScratchDoubles(c.n, c.m) ? base + 64 : work;
 }
 
 // Two thread layouts for the same phase-structured math (small_cone_math.cuh):
@@ -100,15 +118,16 @@ __global__ void __launch_bounds__(kThreads) SchurKernel(int batch, long per, Con
   const double* data = c.data + p * c.data_stride;
   double* st = c.state + p * c.state_stride;
   double* work = c.work ? c.work + p * c.work_stride : nullptr;
+  const bool lp_staged = per >= 64 + small::LpSchurSmemDoubles(c.n, c.m);  // large LP cones: straight from global
   double* g = G + p * gstride;
   double* aw = AW + p * vstride;
   double* aq = AQc + p * vstride;
   double* sc = scal + p * sstride;
   const bool acc = accumulate != 0;
   if (c.type == CXB_CONE_LP) {
-    small::LpSchur(t, c.n, c.m, data, st, g, ldg, aw, aq, sc, acc);
+    small::LpSchur(t, c.n, c.m, data, st, g, ldg, aw, aq, sc, acc, lp_staged ? base + 64 : nullptr);
   } else if (c.type == CXB_CONE_SOC) {
-    small::SocSchur(t, c.n + 1, c.m, data, st, work, g, ldg, aw, aq, sc, acc);
+    small::SocSchur(t, c.n + 1, c.m, data, st, SocScratch(c, per, base, work), g, ldg, aw, aq, sc, acc);
   } else {
     small::PsdSchur(t, c.n, c.m, data, st, work, base + 64, g, ldg, aw, aq, sc, acc);
   }
@@ -173,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) EigenKernel(int batch, long per, Con
     const long np = Align4(c.n);
     small::LpEigen(t, c.n, c.m, data, yp, k, st, st + np, st + 2 * np, out);
   } else if (c.type == CXB_CONE_SOC) {
-    small::SocEigen(t, c.n + 1, c.m, data, yp, k, st, work, out);
+    small::SocEigen(t, c.n + 1, c.m, data, yp, k, st, SocScratch(c, per, base, work), out);
   } else {
     const long nnp = Align4((long)c.n * c.n);
     small::PsdEigen(t, c.n, c.m, data, yp, k, st, st + nnp, st + 2 * nnp, base + 64, out);
@@ -201,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) PrepareKernel(int batch, long per, C
     small::LpPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + np, st + 2 * np, out);
   } else if (c.type == CXB_CONE_SOC) {
     const long op = Align4(c.n + 1);
-    small::SocPrepare(t, c.n + 1, c.m, data, yp, k, st, st + op, work, out);
+    small::SocPrepare(t, c.n + 1, c.m, data, yp, k, st, st + op, SocScratch(c, per, base, work), out);
   } else {
     const long nnp = Align4((long)c.n * c.n);
     small::PsdPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + nnp, st + 2 * nnp, base + 64, out);
@@ -225,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) TakeStepKernel(int batch, long per, 
     small::LpTakeStep(t, c.n, s, st, st + 2 * np);
   } else if (c.type == CXB_CONE_SOC) {
     const long op = Align4(c.n + 1);
-    small::SocTakeStep(t, c.n + 1, s, st, st + op, work);
+    small::SocTakeStep(t, c.n + 1, s, st, st + op, SocScratch(c, per, base, work));
   } else {
     const long nnp = Align4((long)c.n * c.n);
     small::PsdTakeStep(t, c.n, s, ew, st, st + 2 * nnp, base + 64, info + p);
@@ -293,7 +312,11 @@ int EnsureSmem(K kernel, size_t bytes) {
 // (default; falls back to 1 when its shared memory does not fit twice); 1 = DMMA kernel, 16 warps, whole operator in
 // shared memory, one CTA per SM; 0 = the DFMA team kernel
 int g_small_psd_mma = 2;
-int g_small_team_mode = 1;  // cxb_set_small_team_mode(0): one CTA per program instead of one warp per program
+// cxb_set_small_team_mode: 2 (default) = one warp per program for the triangular solves of the small KKT systems only
+// (the one kernel whose phases are all a single dependent chain), one CTA per program elsewhere; 1 = one warp per
+// program everywhere; 0 = one CTA per program everywhere. Measured on C3 (profiles/r02_e_bench_c3_variants.txt): the
+// warp layout is 1.8x faster for the solves and 1.3-1.5x SLOWER for the kernels that have real parallel phases.
+int g_small_team_mode = 2;
 
 bool ValidCone(const cxb_small_cone* c) {
   if (!c || c->n < 1 || c->m < 1 || !c->data || !c->state) return false;
@@ -331,11 +354,11 @@ struct Geometry {
   long per;
   size_t smem;
 };
-Geometry MakeGeometry(int batch, size_t per_program_bytes) {
+Geometry MakeGeometry(int batch, size_t per_program_bytes, bool chain_only = false) {
   Geometry g;
   g.per = (long)(per_program_bytes / sizeof(double));
   // a single program (the LP / SOC plugins of CONEX_Maximize) keeps the whole CTA: its cones can be large
-  g.warp = g_small_team_mode != 0 && batch >= 8;
+  g.warp = (g_small_team_mode == 1 || (g_small_team_mode == 2 && chain_only)) && batch >= 8;
   if (g.warp) {
     int w = (int)((100 * 1024) / (per_program_bytes > 0 ? per_program_bytes : 1));
     w = w < 1 ? 1 : (w > 4 ? 4 : w);
@@ -511,7 +534,7 @@ int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long h
 int cxb_small_potrs(void* stream, int batch, int N, const double* dL, long ldl, long lstride, double* dX,
                     long xstride, const int* d_active) {
   if (batch <= 0 || N <= 0) return 0;
-  const Geometry g = MakeGeometry(batch, sizeof(double) * (64 + (size_t)N));
+  const Geometry g = MakeGeometry(batch, sizeof(double) * (64 + (size_t)N), /*chain_only=*/true);
   if (g.warp) {
     int rc = EnsureSmem(PotrsKernel<true>, g.smem);
     if (rc) return rc;

@@ -287,6 +287,35 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
       cliques.push_back(c.variables);
       some_cone_couples_everything = some_cone_couples_everything || static_cast<int>(c.variables.size()) == N;
     }
+    // Equality multipliers (indices >= number of variables) have a zero diagonal entry until the variables they couple
+    // are eliminated; the LDL^T pivots only inside a supernode (like the reference's BlockLDLTInPlace), so a multiplier
+    // eliminated before its variables would meet an exact zero pivot (regularised to 1e-9: a penalty method, 1e-8
+    // residuals). For the symbolic step every clique that shares a variable with an equality block therefore also
+    // carries that block's multipliers: a multiplier is then eliminated in a node at or above the nodes of all its
+    // variables, and inside that node the pivot order by |diagonal| takes it after them.
+    std::vector<std::vector<int>> analysis_cliques = cliques;
+    {
+      const int nv = prog.GetNumberOfVariables();
+      for (size_t e = 0; e < cliques.size(); e++) {
+        std::vector<int> multipliers;
+        std::vector<char> touched(nv, 0);
+        for (int v : cliques[e]) {
+          if (v >= nv) multipliers.push_back(v); else touched[v] = 1;
+        }
+        if (multipliers.empty()) continue;
+        for (size_t k = 0; k < cliques.size(); k++) {
+          if (k == e) continue;
+          bool shares = false;
+          for (int v : cliques[k]) shares = shares || (v < nv && touched[v]);
+          if (!shares) continue;
+          for (int l : multipliers) {
+            if (std::find(analysis_cliques[k].begin(), analysis_cliques[k].end(), l) == analysis_cliques[k].end()) {
+              analysis_cliques[k].push_back(l);
+            }
+          }
+        }
+      }
+    }
     // The symbolic step depends on the cliques alone: a repeated cold start of the same program keeps
     // the multifrontal solver with its destination lists (hundreds of ms of host work at order 10^4).
     if (prog.solver && prog.solver_is_multifrontal_ && prog.solver_order_ == N &&
@@ -296,7 +325,7 @@ bool Initialize(Program& prog, const SolverConfiguration& config) {
       // one clique on all the variables (unique indices: VariablesAreUnique): a single dense supernode,
       // nothing to analyse
     } else {
-      SupernodalStructure st = AnalyzeCliques(N, cliques);
+      SupernodalStructure st = AnalyzeCliques(N, analysis_cliques);
       const bool pays = st.supernodes.size() > 1 && N >= 256 && st.factor_flops < 0.5 * st.dense_flops;
       if (prog.kkt_solver_kind == 2 || pays) {
         fresh = std::make_unique<SupernodalKKTSolver>(&prog.ctx_, N, std::move(st));

@@ -41,6 +41,9 @@ int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, i
                  int lower_only, int mirror, int diag_off);
 /* Tile configuration used for large shapes when config < 0 (process-wide; tuning only). */
 void cxb_set_default_gemm_config(int config);
+/* Deterministic split-K policy of deep contractions: 0 (default) = split only to fill the machine; k > 0 = additionally
+ * cap the k-tiles (of 16) one CTA walks at k, so that CTAs sharing operand panels stay within L2 of each other. */
+void cxb_set_gemm_split_policy(int max_ktiles_per_cta);
 
 /* ---- K1+K2: Schur complement of one dense LMI block -----------------------------------------
  * dAall: (m+1) contiguous column-major n x n matrices: A_0..A_{m-1} followed by C.
@@ -294,9 +297,9 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
  * (device/small_psd_mma.cuh): 2 (default) = DMMA kernel, one slot per warp, two CTAs per SM; 1 = DMMA kernel with the
  * whole operator of a program in shared memory, one CTA per SM; 0 = the DFMA team kernel. */
 void cxb_set_small_psd_mma(int enabled);
-/* Thread layout of the other small-cone kernels (eigen-bounds, PrepareStep, TakeStep, the small Cholesky and its
- * solves, the LP / SOC Schur systems): 1 (default) = one WARP per program, several programs per CTA (phases separated
- * by __syncwarp, reductions by shuffles); 0 = one CTA of 128 threads per program (block barriers). Same arithmetic. */
+/* Thread layout of the other small-cone kernels: 2 (default) = one WARP per program for the triangular solves of the
+ * small KKT systems (several programs per CTA, __syncwarp + shuffles), one CTA of 128 threads per program for the
+ * kernels with parallel phases; 1 = warp layout everywhere; 0 = CTA layout everywhere. Same arithmetic. */
 void cxb_set_small_team_mode(int mode);
 /* out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} of Q(w^{1/2})(c_weight c - A y)
  * (GetWeightedSlackEigenvalues). c_weight: per-program device array d_cw (stride 1) when not NULL,

@@ -81,7 +81,8 @@ int emul_small_schur(int batch, const cxb_small_cone* c, double* G, long ldg, lo
     double* work = c->work ? c->work + p * c->work_stride : nullptr;
     double *g = G + p * gstride, *aw = AW + p * vstride, *aq = AQc + p * vstride, *sc = scal + p * sstride;
     if (c->type == CXB_CONE_LP) {
-      LpSchur(t, c->n, c->m, data, st, g, ldg, aw, aq, sc, accumulate != 0);
+      std::vector<double> staged(static_cast<size_t>(LpSchurSmemDoubles(c->n, c->m)));
+      LpSchur(t, c->n, c->m, data, st, g, ldg, aw, aq, sc, accumulate != 0, staged.data());
     } else if (c->type == CXB_CONE_SOC) {
       SocSchur(t, c->n + 1, c->m, data, st, work, g, ldg, aw, aq, sc, accumulate != 0);
     } else {

@@ -290,7 +290,7 @@ def test_both_thread_layouts_give_the_same_results(kind, n, m):
             res.append(cone.schur())
             out.append(res)
         finally:
-            be.lib.cxb_set_small_team_mode(1)
+            be.lib.cxb_set_small_team_mode(2)
     for a, b in zip(out[0], out[1]):
         if isinstance(a, tuple):
             for x, z in zip(a, b):
