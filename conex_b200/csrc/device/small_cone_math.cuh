@@ -937,7 +937,7 @@ CXB_HD void PsdEigen(T& t, int n, int m, const double* AC, const double* y, doub
   PsdWeightedSlack(t, n, m, AC, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
   double* ritz = sm + 3 * nn;
   // start vector: column `index` of the true -S
-  LanczosExtremes(t, n, sm + 2 * nn, sm, sm + nn + index * n, sm + 3 * nn + 2, ritz);
+  t.warp0([&](auto& w) { LanczosExtremes(w, n, sm + 2 * nn, sm, sm + nn + index * n, sm + 3 * nn + 2, ritz); });
   t.single([&]() {
     out4[0] = -ritz[1];
     out4[1] = -ritz[0];
@@ -970,7 +970,7 @@ CXB_HD void PsdPrepare(T& t, int n, int m, const double* AC, const double* y, bo
   }
   double* ritz = sm + 3 * nn;
   // the reference starts from a column of WS here (minus_s aliases WS, psd_constraint.cc:48-69)
-  LanczosExtremes(t, n, sm + 2 * nn, sm, sm + 2 * nn + index * n, sm + 3 * nn + 2, ritz);
+  t.warp0([&](auto& w) { LanczosExtremes(w, n, sm + 2 * nn, sm, sm + 2 * nn + index * n, sm + 3 * nn + 2, ritz); });
   t.single([&]() {
     out2[0] = fmax(fabs(ew + ritz[0]), fabs(ew + ritz[1]));
     out2[1] = trsq + 2 * tr + n;

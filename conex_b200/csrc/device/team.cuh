@@ -9,75 +9,7 @@
 
 namespace cxb {
 
-struct DeviceTeam {
-  int tid, nt;
-  double* red;  // >= 40 doubles of shared memory
-
-  __device__ DeviceTeam(double* scratch) : tid(threadIdx.x), nt(blockDim.x), red(scratch) {}
-
-  __device__ __forceinline__ int size() const { return nt; }
-
-  template <class F>
-  __device__ __forceinline__ void par(int n, F f) {
-    for (int i = tid; i < n; i += nt) f(i);
-    __syncthreads();
-  }
-  template <class F>
-  __device__ __forceinline__ double sum(int n, F f) {
-    double v = 0;
-    for (int i = tid; i < n; i += nt) v += f(i);
-    return BlockSum(v, red);
-  }
-  template <class F>
-  __device__ __forceinline__ double maxv(int n, F f) {
-    double v = -1.7976931348623157e308;
-    for (int i = tid; i < n; i += nt) v = fmax(v, f(i));
-    return BlockMax(v);
-  }
-  template <class F>
-  __device__ __forceinline__ double minv(int n, F f) {
-    double v = -1.7976931348623157e308;
-    for (int i = tid; i < n; i += nt) v = fmax(v, -f(i));
-    return -BlockMax(v);
-  }
-  // f() evaluated by one thread, result given to all.
-  template <class F>
-  __device__ __forceinline__ double bcast(F f) {
-    __syncthreads();
-    if (tid == 0) red[34] = f();
-    __syncthreads();
-    const double v = red[34];
-    __syncthreads();
-    return v;
-  }
-  template <class F>
-  __device__ __forceinline__ void single(F f) {
-    __syncthreads();
-    if (tid == 0) f();
-    __syncthreads();
-  }
-
- private:
-  __device__ __forceinline__ double BlockMax(double v) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nwarps = (nt + 31) >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      double t = (lane < nwarps) ? red[lane] : -1.7976931348623157e308;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
-      if (lane == 0) red[32] = t;
-    }
-    __syncthreads();
-    return red[32];
-  }
-};
-
-// The same team interface on ONE WARP: every phase boundary is a __syncwarp() and the reductions are shuffles, so a
+// The team interface on ONE WARP: every phase boundary is a __syncwarp() and the reductions are shuffles, so a
 // small problem whose phases are short (Lanczos on a 20 x 20 block: ~10 steps of two 20-entry matvecs and two dot
 // products; a 40 x 40 Cholesky: 40 columns) pays a few cycles per phase instead of a 128-thread barrier, and four
 // problems share a CTA. Reductions combine in a fixed order (shfl_down tree, result broadcast from lane 0).
@@ -136,6 +68,92 @@ struct WarpTeam {
     __syncwarp();
     if (tid == 0) f();
     __syncwarp();
+  }
+  // a section that only has warp-sized parallelism (see DeviceTeam::warp0): here it is simply the team itself
+  template <class F>
+  __device__ __forceinline__ void warp0(F f) {
+    f(*this);
+  }
+};
+
+
+struct DeviceTeam {
+  int tid, nt;
+  double* red;  // >= 40 doubles of shared memory
+
+  __device__ DeviceTeam(double* scratch) : tid(threadIdx.x), nt(blockDim.x), red(scratch) {}
+
+  __device__ __forceinline__ int size() const { return nt; }
+
+  template <class F>
+  __device__ __forceinline__ void par(int n, F f) {
+    for (int i = tid; i < n; i += nt) f(i);
+    __syncthreads();
+  }
+  template <class F>
+  __device__ __forceinline__ double sum(int n, F f) {
+    double v = 0;
+    for (int i = tid; i < n; i += nt) v += f(i);
+    return BlockSum(v, red);
+  }
+  template <class F>
+  __device__ __forceinline__ double maxv(int n, F f) {
+    double v = -1.7976931348623157e308;
+    for (int i = tid; i < n; i += nt) v = fmax(v, f(i));
+    return BlockMax(v);
+  }
+  template <class F>
+  __device__ __forceinline__ double minv(int n, F f) {
+    double v = -1.7976931348623157e308;
+    for (int i = tid; i < n; i += nt) v = fmax(v, -f(i));
+    return -BlockMax(v);
+  }
+  // f() evaluated by one thread, result given to all.
+  template <class F>
+  __device__ __forceinline__ double bcast(F f) {
+    __syncthreads();
+    if (tid == 0) red[34] = f();
+    __syncthreads();
+    const double v = red[34];
+    __syncthreads();
+    return v;
+  }
+  template <class F>
+  __device__ __forceinline__ void single(F f) {
+    __syncthreads();
+    if (tid == 0) f();
+    __syncthreads();
+  }
+  // A section whose phases never have more than a warp's worth of parallel work (the Lanczos recurrence on a small
+  // block: 20-entry matvecs and dot products, then the multi-section of the Ritz values): warp 0 runs it as a
+  // WarpTeam — __syncwarp and shuffles between its ~200 phases instead of block barriers — the other warps wait once.
+  template <class F>
+  __device__ __forceinline__ void warp0(F f) {
+    __syncthreads();
+    if ((tid >> 5) == 0) {
+      WarpTeam w;
+      f(w);
+    }
+    __syncthreads();
+  }
+
+ private:
+  __device__ __forceinline__ double BlockMax(double v) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (nt + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      double t = (lane < nwarps) ? red[lane] : -1.7976931348623157e308;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+      if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
   }
 };
 

@@ -45,6 +45,10 @@ struct HostTeam {
   void single(F f) {
     f();
   }
+  template <class F>
+  void warp0(F f) {
+    f(*this);
+  }
 };
 
 long Align4(long n) { return (n + 3) & ~3L; }
