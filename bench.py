@@ -837,6 +837,8 @@ def dense_bench(proc, args, w, steps, warmup, full_solve, cpu_leg):
     P = dev.program()
     if args.assembly_mode:
         L.CONEXB200_SetAssemblyMode(P.h, args.assembly_mode)
+    if args.no_peer_memory:
+        L.CONEXB200_SetPeerMemoryExchange(P.h, 0)
     try:
         A, Cm, rb, rc = P.dense_lmi_storage(n, m, world, rank)
     except AssertionError as e:
@@ -941,8 +943,9 @@ def dense_bench(proc, args, w, steps, warmup, full_solve, cpu_leg):
                    "l2": f"inputs ({8e-9 * m * n * n:.1f} GB) vs 126 MB L2: " +
                          ("no flush needed" if 8.0 * m * n * n > 4 * 126e6 else "L2-resident workload"),
                    "multi_gpu": (f"one Newton step sharded over {world} ranks: constraint matrices and the rows "
-                                 "of H partitioned 1-D (K1/K2/K6 sharded, peer matrices over NCCL "
-                                 "send/recv, H by all-reduce); Cholesky " + cholesky_note(args, world, m) +
+                                 "of H partitioned 1-D (K1/K2/K6 sharded, peers' scaled matrices pulled from "
+                                 "peer memory over NVLink" + (" [A/B: ncclSend/ncclRecv]" if args.no_peer_memory else "") +
+                                 ", H by all-reduce); Cholesky " + cholesky_note(args, world, m) +
                                  "; solve/eigen-bound/geodesic update replicated") if world > 1 else "n/a"},
         "newton_steps_per_s": 1e3 / value,
         "step_tflops_fp64": fl["tensor"] / (value * 1e-3) / 1e12,
@@ -1056,6 +1059,8 @@ def main():
     ap.add_argument("--no-full-solve", action="store_true", help="skip the default-configuration solve to termination")
     ap.add_argument("--no-extra", action="store_true", help="c2: skip the C5 and C3 blocks that ride along in the line")
     ap.add_argument("--cpu-size", type=int, default=0, help="override n = m of the CPU sample (testing)")
+    ap.add_argument("--no-peer-memory", action="store_true",
+                    help="N > 1 A/B: exchange the scaled matrices through ncclSend / ncclRecv instead of peer memory")
     ap.add_argument("--gemm-max-ktiles", type=int, default=-1, help="A/B: cxb_set_gemm_split_policy")
     ap.add_argument("--small-psd-mma", type=int, default=-1, help="c3 A/B: cxb_set_small_psd_mma (2 default, 1, 0)")
     ap.add_argument("--small-team-mode", type=int, default=-1, help="c3 A/B: cxb_set_small_team_mode (1 default, 0)")

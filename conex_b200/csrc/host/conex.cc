@@ -659,6 +659,10 @@ int CONEXB200_GetAssemblyForm(void* prog, int id) {
   return -1;
 }
 
+void CONEXB200_SetPeerMemoryExchange(void* prog, int enabled) {
+  static_cast<Program*>(prog)->ctx_.peer_memory_exchange = enabled != 0;
+}
+
 int CONEXB200_GetShardPhaseMilliseconds(void* prog, int id, double* out4) {
   Program& program = *static_cast<Program*>(prog);
   int k = 0;

@@ -41,12 +41,20 @@ struct DenseLMIConstraint::Storage {
   cudaEvent_t arrived[2] = {nullptr, nullptr};
   cudaEvent_t consumed[2] = {nullptr, nullptr};
   cudaEvent_t start = nullptr;
+  // Peer memory (CUDA IPC over NVLink): peer_x[p] = rank p's packed scaled matrices X mapped into this process, so
+  // that a chunk is PULLED by a copy engine straight from the peer's HBM instead of travelling through
+  // ncclSend / ncclRecv (measured at 2 GPUs: 122 GB/s through NCCL's point-to-point channels, the exchange stalled
+  // the contractions for 10 % of the assembly, profiles/r02_f_bench_c2_2gpu.json). ipc_ready: agreed on by all ranks.
+  std::vector<double*> peer_x;
+  bool ipc_ready = false;
+  DeviceBuffer<int> ipc_words;
   // timing of the last sharded assembly (CUDA events on the compute stream): begin, local block done, before the
   // all-reduce, end; per exchanged chunk: before the wait for its arrival, after it, after its contraction
   cudaEvent_t t_mark[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> t_chunk;
   size_t t_chunks_used = 0;
   ~Storage() {
+    for (double* p : peer_x) if (p) cudaIpcCloseMemHandle(p);
     for (auto e : t_mark) if (e) cudaEventDestroy(e);
     for (auto e : t_chunk) if (e) cudaEventDestroy(e);
     for (auto e : arrived) if (e) cudaEventDestroy(e);
@@ -360,6 +368,7 @@ void DenseLMIConstraint::EnsureScratch() {
     for (auto& e : d.arrived) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
     for (auto& e : d.consumed) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
     CudaCheck(cudaEventCreateWithFlags(&d.start, cudaEventDisableTiming), "event");
+    if (d.symmetric && ctx_->peer_memory_exchange) ExchangePeerHandles();
   }
   const size_t work = std::max(cxb_lanczos_worksize(n_), cxb_geodesic_worksize(n_));
   d.scratch.Resize(work);
@@ -367,6 +376,62 @@ void DenseLMIConstraint::EnsureScratch() {
   d.small.Resize(2 * (n_ / 2 + 2) + 8);
   d.iwork.Resize(2 * n_ + 8);
   d.rstart.Resize(n_);
+}
+
+// Every rank publishes the CUDA IPC handle of its X buffer (64 bytes as 32 sixteen-bit words + an "ok" word, combined
+// by an integer max all-reduce against zeros) and maps the others'. Any failure on any rank (IPC not permitted, no peer
+// access) leaves ipc_ready false on ALL ranks and the exchange stays on ncclSend / ncclRecv.
+void DenseLMIConstraint::ExchangePeerHandles() {
+  Storage& d = *data_;
+  Communicator& comm = Communicator::Get();
+  const int world = comm.world(), rank = comm.rank();
+  constexpr int kWords = 33;
+  std::vector<int> words(static_cast<size_t>(world) * kWords + 1, 0);
+  cudaIpcMemHandle_t mine;
+  const bool have = cudaIpcGetMemHandle(&mine, d.X.get()) == cudaSuccess;
+  if (!have) cudaGetLastError();
+  if (have) {
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(&mine);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    int* slot = words.data() + static_cast<size_t>(rank) * kWords;
+    slot[0] = 1;
+    for (int i = 0; i < 32; i++) slot[1 + i] = bytes[2 * i] | (bytes[2 * i + 1] << 8);
+  }
+  d.ipc_words.Resize(words.size());
+  cudaStream_t s = ctx_->cuda_stream();
+  CudaCheck(cudaMemcpyAsync(d.ipc_words.get(), words.data(), sizeof(int) * words.size(), cudaMemcpyHostToDevice, s),
+            "H2D copy");
+  comm.AllReduceMaxInt(d.ipc_words.get(), words.size(), s);
+  ctx_->DownloadInts(words.data(), d.ipc_words.get(), words.size());
+  d.peer_x.assign(world, nullptr);
+  int failed = 0;
+  for (int p = 0; p < world; p++) {
+    if (p == rank) continue;
+    const int* slot = words.data() + static_cast<size_t>(p) * kWords;
+    if (slot[0] != 1) {
+      failed = 1;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(&h);
+    for (int i = 0; i < 32; i++) {
+      bytes[2 * i] = static_cast<unsigned char>(slot[1 + i] & 0xff);
+      bytes[2 * i + 1] = static_cast<unsigned char>((slot[1 + i] >> 8) & 0xff);
+    }
+    void* mapped = nullptr;
+    if (cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      failed = 1;
+      continue;
+    }
+    d.peer_x[p] = static_cast<double*>(mapped);
+  }
+  // one decision for the whole communicator
+  int* flag = d.ipc_words.get() + words.size() - 1;
+  CudaCheck(cudaMemcpyAsync(flag, &failed, sizeof(int), cudaMemcpyHostToDevice, s), "H2D copy");
+  comm.AllReduceMaxInt(flag, 1, s);
+  ctx_->DownloadInts(&failed, flag, 1);
+  d.ipc_ready = failed == 0;
 }
 
 void SetIdentity(DenseLMIConstraint* o) {
@@ -489,18 +554,33 @@ void DenseLMIConstraint::AssembleSharded(SchurComplementSystem* sys) {
       chunks.push_back(ch);
     }
   }
+  // Symmetric form with peer memory mapped: chunks are pulled from the peer's X by a copy engine over NVLink.
+  const bool pull = sym && d.ipc_ready;
   auto post = [&](size_t c) {  // enqueue the transfer of chunk c on the side stream
     const Chunk& ch = chunks[c];
     const int buf = static_cast<int>(c % 2);
     if (c >= 2) CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.consumed[buf], 0), "cudaStreamWaitEvent");
-    const double* src = ch.send_count ? send_source + static_cast<long>(ch.send_begin - rb) * stride : nullptr;
-    comm.SendRecv(src, static_cast<size_t>(ch.send_count) * stride, ch.to, d.recv[buf].get(),
-                  static_cast<size_t>(ch.recv_count) * stride, ch.from, d.comm_stream);
+    if (pull) {
+      if (ch.recv_count > 0) {
+        const int peer_begin = ShardBegin(m, comm.world(), ch.from);
+        CudaCheck(cudaMemcpyAsync(d.recv[buf].get(), d.peer_x[ch.from] + static_cast<long>(ch.recv_begin - peer_begin) * stride,
+                                  sizeof(double) * static_cast<size_t>(ch.recv_count) * stride, cudaMemcpyDefault,
+                                  d.comm_stream),
+                  "peer copy of a chunk of scaled matrices");
+      }
+    } else {
+      const double* src = ch.send_count ? send_source + static_cast<long>(ch.send_begin - rb) * stride : nullptr;
+      comm.SendRecv(src, static_cast<size_t>(ch.send_count) * stride, ch.to, d.recv[buf].get(),
+                    static_cast<size_t>(ch.recv_count) * stride, ch.from, d.comm_stream);
+    }
     CudaCheck(cudaEventRecord(d.arrived[buf], d.comm_stream), "cudaEventRecord");
   };
   auto release_side_stream = [&]() {
     CudaCheck(cudaEventRecord(d.start, s), "cudaEventRecord");
     CudaCheck(cudaStreamWaitEvent(d.comm_stream, d.start, 0), "cudaStreamWaitEvent");
+    // every rank's X must be complete before anyone pulls from it: a one-word all-reduce on the side streams is that
+    // barrier (each rank enqueues it behind its own K1)
+    if (pull) comm.AllReduceMaxInt(d.ipc_words.get(), 1, d.comm_stream);
     if (!chunks.empty()) post(0);
   };
   // Classic form: the raw matrices can travel while the local block is computed. Symmetric form: the

@@ -101,6 +101,12 @@ int CONEXB200_CholeskySchedule(int N, int block, int world, int rank, int* out3,
  * *info = 0, or non-zero on every rank if the matrix is not positive definite. Returns 0 / 1. */
 int CONEXB200_DistributedPotrf(int N, double* d_H, long ld, int block, int* info);
 
+/* Sharded LMI blocks (symmetric form) exchange their packed scaled matrices through PEER MEMORY by default: every rank
+ * maps the others' buffers (CUDA IPC) and pulls its chunks with copy engines over NVLink, behind a one-word all-reduce
+ * that says everyone's matrices are complete; 0 = always ncclSend / ncclRecv (also the automatic fallback when IPC
+ * mapping fails on any rank). Call before the first solve, with the same value on every rank. */
+void CONEXB200_SetPeerMemoryExchange(void* prog, int enabled);
+
 /* Where the last sharded assembly of LMI constraint `id` spent its device time on THIS rank (CUDA events on the
  * compute stream): out4 = {local K1 + diagonal block, stalls waiting for a peer's chunk (exchange not hidden),
  * off-diagonal contractions, all-reduce of H} in ms. Returns 1, or 0 when the constraint is not sharded. */

@@ -104,6 +104,7 @@ class DenseLMIConstraint {
  private:
   struct Storage;
   void EnsureScratch();
+  void ExchangePeerHandles();  // sharded blocks: map the peers' scaled matrices (CUDA IPC)
   // minus_s = sum_i y_i A_i - k C  (reference ComputeNegativeSlack, dense_lmi_constraint.cc:22-27)
   void ComputeNegativeSlack(double k, const Ref& y, Ref* minus_s);
   // Two-sided Lanczos extreme Ritz values of WS w.r.t. W started from column `index` of R, plus

@@ -130,6 +130,9 @@ class DeviceContext {
   // and calls its solves in lock step (set by the sharded LMI constructors and by
   // CONEXB200_SetCollective): the factorisation may then be distributed (distributed_cholesky.h).
   bool collective = false;
+  // Sharded LMI blocks exchange their scaled matrices through peer memory (CUDA IPC mappings pulled by copy engines
+  // over NVLink) when every rank can map every other's; false: always ncclSend / ncclRecv (A/B, CONEXB200_SetPeerMemoryExchange).
+  bool peer_memory_exchange = true;
 
   void* stream() const { return reinterpret_cast<void*>(stream_); }
   cudaStream_t cuda_stream() const { return stream_; }
