@@ -452,6 +452,8 @@ def product():
         L.cxb_dgemm_ex.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, vp, C.c_long, C.c_long, vp, C.c_long, C.c_long, C.c_double,
                                    vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.cxb_dgemm_bulk.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, C.c_long, vp, C.c_long, C.c_long, vp,
+                                     C.c_long, C.c_long, C.c_int, C.c_int]
         L.cxb_set_default_gemm_config.argtypes = [C.c_int]
         L.cxb_set_default_gemm_config.restype = None
         L.cxb_schur_dense_lmi.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_long]

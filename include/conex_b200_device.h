@@ -40,6 +40,11 @@ int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, i
                  long strideB, double beta, double* dC, long ldc, long strideC, int batch,
                  int lower_only, int mirror, int diag_off);
 /* Tile configuration used for large shapes when config < 0 (process-wide; tuning only). */
+/* A/B arm: C = A B (plain NN, strided batch; tri = 1: B lower triangular) with the operand tiles staged by the TMA
+ * engine's bulk copies (cp.async.bulk + mbarrier) into the same padded shared-memory layout; bit-identical results.
+ * Needs K % 16 == 0, even M / leading dimensions / strides, 16-byte aligned operands; returns -1 otherwise. */
+int cxb_dgemm_bulk(void* stream, int M, int N, int K, const double* dA, long lda, long strideA, const double* dB,
+                   long ldb, long strideB, double* dC, long ldc, long strideC, int batch, int tri);
 void cxb_set_default_gemm_config(int config);
 /* Deterministic split-K policy of deep contractions: 0 (default) = split only to fill the machine; k > 0 = additionally
  * cap the k-tiles (of 16) one CTA walks at k, so that CTAs sharing operand panels stay within L2 of each other. */

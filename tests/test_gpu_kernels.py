@@ -595,3 +595,34 @@ def test_triangular_gemm_and_symmetric_packing(dev, n):
     H = dev.from_dev(dH, 4, 3)
     assert abs(H[0, 0] - np.trace(X @ W @ X @ W)) <= 1e-10 * abs(np.trace(X @ W @ X @ W))
     assert abs(H[2, 0] - np.trace(X @ W)) <= 1e-10 * max(1.0, np.abs(X @ W).sum())
+
+
+@pytest.mark.parametrize("M,N,K,batch,tri", [(64, 64, 16, 1, 0), (128, 192, 64, 2, 0), (200, 200, 208, 3, 1), (2000, 2000, 2000, 2, 1),
+                                             (1000, 130, 48, 1, 0)])
+def test_dgemm_with_tma_bulk_copies_is_bit_identical(dev, M, N, K, batch, tri):
+    """The A/B arm of the DMMA GEMM whose operand tiles are staged by cp.async.bulk (TMA engine, mbarrier completion)
+    into the same padded layout: same fragment loads and k order, so the result is bit-identical to gemm.cu's."""
+    rng = np.random.Generator(np.random.PCG64(M + N + K))
+    A = rng.uniform(-1, 1, size=(batch, K, M))      # batch of column-major M x K blocks
+    B = rng.uniform(-1, 1, size=(batch, N, K))      # batch of column-major K x N blocks
+    if tri:
+        for b in range(batch):
+            B[b] = np.triu(B[b])                     # B(k, c) = 0 for k < c  (stored [c][k])
+    import torch
+    L = dev.product().lib
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    out = []
+    for bulk in (0, 1):
+        dC = torch.zeros((batch, N, M), dtype=torch.float64, device="cuda")
+        if bulk:
+            rc = L.cxb_dgemm_bulk(None, M, N, K, dev.ptr(dA), M, M * K, dev.ptr(dB), K, K * N, dev.ptr(dC), M, M * N, batch, tri)
+        else:
+            rc = L.cxb_dgemm_ex(None, 2, 1, 0, 0, M, N, K, 1.0, dev.ptr(dA), M, M * K, dev.ptr(dB), K, K * N, 0.0, dev.ptr(dC),
+                                M, M * N, batch, 0, 0, 0)
+        assert rc == 0
+        torch.cuda.synchronize()
+        out.append(dC.cpu().numpy())
+    ref = np.einsum("bkm,bnk->bnm", A, B)
+    assert np.abs(out[0] - ref).max() <= 1e-12 * K
+    assert np.array_equal(out[0], out[1])
+
