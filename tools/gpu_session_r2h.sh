@@ -22,4 +22,6 @@ for wl in c2s c4s sparse c4; do
 done
 timeout 200 python tools/prof_hbm_kernels.py time geo,lanczos > gpurun_out/r02_h_kernel_timings_k7_k8.jsonl 2> gpurun_out/h_tmp.err
 cut -c1-200 gpurun_out/r02_h_kernel_timings_k7_k8.jsonl
+timeout 200 python tools/gemm_bulk_ab.py > gpurun_out/r02_h_gemm_tma_bulk_ab.jsonl 2> gpurun_out/h_tmp.err
+cut -c1-220 gpurun_out/r02_h_gemm_tma_bulk_ab.jsonl; tail -2 gpurun_out/h_tmp.err
 du -sh gpurun_out
