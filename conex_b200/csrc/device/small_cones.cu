@@ -38,12 +38,19 @@ size_t PsdSmemDoubles(int n) { return 6 * (size_t)n * n + 8 * (size_t)n + 64 + 2
 // (Cones too large for that — more than kStagedLimit doubles — keep the global paths.)
 constexpr long kStagedLimit = 12 * 1024;  // 96 KB
 __host__ __device__ inline long SocScratchDoubles(int n, int m) { return (long)(n + 1) * (m + 2) + 4 * (long)(n + 1); }
+// PsdEigen / PsdPrepare only touch sW | sS | sWS and the Lanczos vectors: 3 n^2 matrices instead of the 6 of the
+// exponential map, so twice as many of their (latency-bound) CTAs fit on an SM.
+size_t PsdSpectralSmemDoubles(int n) { return 3 * (size_t)n * n + 8 * (size_t)n + 64 + 2 * small::kSections + 16; }
 size_t SmemBytes(const ConeArgs& c) {
   if (c.type == CXB_CONE_SOC) {
     const long need = SocScratchDoubles(c.n, c.m);
     return sizeof(double) * (64 + (need <= kStagedLimit ? need : 0));
   }
   return sizeof(double) * (64 + (c.type == CXB_CONE_PSD ? PsdSmemDoubles(c.n) : 0));
+}
+size_t SpectralSmemBytes(const ConeArgs& c) {
+  if (c.type == CXB_CONE_PSD) return sizeof(double) * (64 + PsdSpectralSmemDoubles(c.n));
+  return SmemBytes(c);
 }
 size_t SchurSmemBytes(const ConeArgs& c) {
   if (c.type == CXB_CONE_SOC) return SmemBytes(c);
@@ -89,7 +96,7 @@ __device__ __forceinline__ bool Slot(int batch, long per, double* sm, const int*
 }
 
 template <bool WARP>
-__global__ void __launch_bounds__(kThreads) SetIdentityKernel(int batch, long per, ConeArgs c, const int* active) {
+__device__ __forceinline__ void SetIdentityBody(int batch, long per, const ConeArgs& c, const int* active) {
   extern __shared__ double sm[];
   int p;
   double* base;
@@ -174,9 +181,9 @@ __global__ void __launch_bounds__(128) PsdFactorKernel(int batch, ConeArgs c, co
 }
 
 template <bool WARP>
-__global__ void __launch_bounds__(kThreads) EigenKernel(int batch, long per, ConeArgs c, const double* y, long ystride,
-                                                        double cw, const double* cw_p, double* out4,
-                                                        long ostride, const int* active) {
+__device__ __forceinline__ void EigenBody(int batch, long per, const ConeArgs& c, const double* y, long ystride,
+                                          double cw, const double* cw_p, double* out4, long ostride,
+                                          const int* active) {
   extern __shared__ double sm[];
   int p;
   double* base;
@@ -200,10 +207,9 @@ __global__ void __launch_bounds__(kThreads) EigenKernel(int batch, long per, Con
 }
 
 template <bool WARP>
-__global__ void __launch_bounds__(kThreads) PrepareKernel(int batch, long per, ConeArgs c, const double* y,
-                                                          long ystride, int affine, double cw, const double* cw_p,
-                                                          double ew, double* out2, long ostride,
-                                                          const int* active) {
+__device__ __forceinline__ void PrepareBody(int batch, long per, const ConeArgs& c, const double* y, long ystride,
+                                            int affine, double cw, const double* cw_p, double ew, double* out2,
+                                            long ostride, const int* active) {
   extern __shared__ double sm[];
   int p;
   double* base;
@@ -228,9 +234,8 @@ __global__ void __launch_bounds__(kThreads) PrepareKernel(int batch, long per, C
 }
 
 template <bool WARP>
-__global__ void __launch_bounds__(kThreads) TakeStepKernel(int batch, long per, ConeArgs c, double step,
-                                                           const double* step_p, double ew, int* info,
-                                                           const int* active) {
+__device__ __forceinline__ void TakeStepBody(int batch, long per, const ConeArgs& c, double step,
+                                             const double* step_p, double ew, int* info, const int* active) {
   extern __shared__ double sm[];
   int p;
   double* base;
@@ -249,6 +254,59 @@ __global__ void __launch_bounds__(kThreads) TakeStepKernel(int batch, long per, 
     const long nnp = Align4((long)c.n * c.n);
     small::PsdTakeStep(t, c.n, s, ew, st, st + 2 * nnp, base + 64, info + p);
   }
+}
+
+
+// One launch per cone (any layout) and one launch for a list of cones (CTA layout, blockIdx.y = cone): the lock step of
+// a batch of multi-cone programs runs the same operation on every cone, and launched one after the other the cones'
+// dependent chains (Lanczos, Gaussian elimination) serialise while most of the SMs idle when the batch is small.
+constexpr int kMaxFused = 8;
+struct ConeList {
+  ConeArgs c[kMaxFused];
+};
+
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) SetIdentityKernel(int batch, long per, ConeArgs c, const int* active) {
+  SetIdentityBody<WARP>(batch, per, c, active);
+}
+__global__ void __launch_bounds__(kThreads) SetIdentityMultiKernel(int batch, long per, ConeList l, const int* active) {
+  SetIdentityBody<false>(batch, per, l.c[blockIdx.y], active);
+}
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) EigenKernel(int batch, long per, ConeArgs c, const double* y, long ystride,
+                                                        double cw, const double* cw_p, double* out4,
+                                                        long ostride, const int* active) {
+  EigenBody<WARP>(batch, per, c, y, ystride, cw, cw_p, out4, ostride, active);
+}
+__global__ void __launch_bounds__(kThreads, 8) EigenMultiKernel(int batch, long per, ConeList l, const double* y,
+                                                             long ystride, double cw, const double* cw_p, double* out4,
+                                                             long ostride, const int* active) {
+  EigenBody<false>(batch, per, l.c[blockIdx.y], y, ystride, cw, cw_p, out4 + 4 * blockIdx.y, ostride, active);
+}
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) PrepareKernel(int batch, long per, ConeArgs c, const double* y,
+                                                          long ystride, int affine, double cw, const double* cw_p,
+                                                          double ew, double* out2, long ostride,
+                                                          const int* active) {
+  PrepareBody<WARP>(batch, per, c, y, ystride, affine, cw, cw_p, ew, out2, ostride, active);
+}
+__global__ void __launch_bounds__(kThreads, 8) PrepareMultiKernel(int batch, long per, ConeList l, const double* y,
+                                                               long ystride, int affine, double cw, const double* cw_p,
+                                                               double ew, double* out2, long ostride,
+                                                               const int* active) {
+  PrepareBody<false>(batch, per, l.c[blockIdx.y], y, ystride, affine, cw, cw_p, ew, out2 + 4 * blockIdx.y, ostride,
+                     active);
+}
+template <bool WARP>
+__global__ void __launch_bounds__(kThreads) TakeStepKernel(int batch, long per, ConeArgs c, double step,
+                                                           const double* step_p, double ew, int* info,
+                                                           const int* active) {
+  TakeStepBody<WARP>(batch, per, c, step, step_p, ew, info, active);
+}
+__global__ void __launch_bounds__(kThreads) TakeStepMultiKernel(int batch, long per, ConeList l, double step,
+                                                                const double* step_p, double ew, int* info,
+                                                                const int* active) {
+  TakeStepBody<false>(batch, per, l.c[blockIdx.y], step, step_p, ew, info, active);
 }
 
 template <bool WARP>
@@ -354,7 +412,9 @@ struct Geometry {
   long per;
   size_t smem;
 };
-Geometry MakeGeometry(int batch, size_t per_program_bytes, bool chain_only = false) {
+// CTA size of the spectral kernels (cxb_small_eigen / cxb_small_prepare) in the CTA layout (cxb_set_small_cone_threads).
+int g_spectral_threads = kThreads;
+Geometry MakeGeometry(int batch, size_t per_program_bytes, bool chain_only = false, int threads = kThreads) {
   Geometry g;
   g.per = (long)(per_program_bytes / sizeof(double));
   // a single program (the LP / SOC plugins of CONEX_Maximize) keeps the whole CTA: its cones can be large
@@ -366,12 +426,27 @@ Geometry MakeGeometry(int batch, size_t per_program_bytes, bool chain_only = fal
     g.grid = (batch + w - 1) / w;
     g.smem = per_program_bytes * w;
   } else {
-    g.threads = kThreads;
+    g.threads = threads;
     g.grid = batch;
     g.smem = per_program_bytes;
   }
   return g;
 }
+
+// The cones [first, first + count) of a list as kernel arguments; *smem = the largest per-cone requirement.
+extern "C++" template <class SmemOf>
+bool MakeList(int count, const cxb_small_cone* cones, SmemOf smem_of, ConeList* list, size_t* smem) {
+  *smem = 0;
+  for (int k = 0; k < count; k++) {
+    if (!ValidCone(cones + k)) return false;
+    list->c[k] = Convert(cones + k);
+    const size_t b = smem_of(list->c[k]);
+    if (b > *smem) *smem = b;
+  }
+  return true;
+}
+// the fused launches use the CTA layout; with the warp layout forced everywhere the cones are launched one by one
+bool FusedLayout(int batch) { return !(g_small_team_mode == 1 && batch >= 8); }
 }  // namespace
 
 int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active) {
@@ -448,6 +523,9 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
 }
 
 void cxb_set_small_psd_mma(int enabled) { g_small_psd_mma = enabled; }
+void cxb_set_small_cone_threads(int threads) {
+  if (threads == 32 || threads == 64 || threads == 128) g_spectral_threads = threads;
+}
 void cxb_set_small_team_mode(int mode) { g_small_team_mode = mode; }
 
 int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const double* dy, long ystride,
@@ -456,7 +534,7 @@ int cxb_small_eigen(void* stream, int batch, const cxb_small_cone* cone, const d
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
-  const Geometry g = MakeGeometry(batch, SmemBytes(c));
+  const Geometry g = MakeGeometry(batch, SpectralSmemBytes(c), false, g_spectral_threads);
   if (g.warp) {
     int rc = EnsureSmem(EigenKernel<true>, g.smem);
     if (rc) return rc;
@@ -477,7 +555,7 @@ int cxb_small_prepare(void* stream, int batch, const cxb_small_cone* cone, const
   if (batch <= 0) return 0;
   if (!ValidCone(cone)) return -1;
   const ConeArgs c = Convert(cone);
-  const Geometry g = MakeGeometry(batch, SmemBytes(c));
+  const Geometry g = MakeGeometry(batch, SpectralSmemBytes(c), false, g_spectral_threads);
   if (g.warp) {
     int rc = EnsureSmem(PrepareKernel<true>, g.smem);
     if (rc) return rc;
@@ -511,6 +589,121 @@ int cxb_small_take_step(void* stream, int batch, const cxb_small_cone* cone, dou
         batch, g.per, c, step, d_step, e_weight, d_info, d_active);
   }
   return LaunchStatus();
+}
+
+// ---- the same operations on a list of cones of every program, one launch per kMaxFused cones ----------------------
+int cxb_small_set_identity_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones,
+                                 const int* d_active) {
+  if (batch <= 0 || ncones <= 0) return 0;
+  if (!cones) return -1;
+  for (int first = 0; first < ncones; first += kMaxFused) {
+    const int count = ncones - first < kMaxFused ? ncones - first : kMaxFused;
+    if (!FusedLayout(batch)) {
+      for (int k = 0; k < count; k++) {
+        int rc = cxb_small_set_identity(stream, batch, cones + first + k, d_active);
+        if (rc) return rc;
+      }
+      continue;
+    }
+    ConeList l;
+    size_t smem;
+    if (!MakeList(count, cones + first, [](const ConeArgs&) { return sizeof(double) * 64; }, &l, &smem)) return -1;
+    CountLaunch();
+    SetIdentityMultiKernel<<<dim3(batch, count), kThreads, smem, AsStream(stream)>>>(batch, (long)(smem / 8), l,
+                                                                                     d_active);
+    int rc = LaunchStatus();
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int cxb_small_eigen_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, const double* dy,
+                          long ystride, double c_weight, const double* d_cw, double* d_out4, long ostride,
+                          const int* d_active) {
+  if (batch <= 0 || ncones <= 0) return 0;
+  if (!cones) return -1;
+  for (int first = 0; first < ncones; first += kMaxFused) {
+    const int count = ncones - first < kMaxFused ? ncones - first : kMaxFused;
+    if (!FusedLayout(batch)) {
+      for (int k = 0; k < count; k++) {
+        int rc = cxb_small_eigen(stream, batch, cones + first + k, dy, ystride, c_weight, d_cw,
+                                 d_out4 + 4 * (first + k), ostride, d_active);
+        if (rc) return rc;
+      }
+      continue;
+    }
+    ConeList l;
+    size_t smem;
+    if (!MakeList(count, cones + first, SpectralSmemBytes, &l, &smem)) return -1;
+    int rc = EnsureSmem(EigenMultiKernel, smem);
+    if (rc) return rc;
+    CountLaunch();
+    EigenMultiKernel<<<dim3(batch, count), g_spectral_threads, smem, AsStream(stream)>>>(
+        batch, (long)(smem / 8), l, dy, ystride, c_weight, d_cw, d_out4 + 4 * first, ostride, d_active);
+    rc = LaunchStatus();
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int cxb_small_prepare_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, const double* dy,
+                            long ystride, int affine, double c_weight, const double* d_cw, double e_weight,
+                            double* d_out2, long ostride, const int* d_active) {
+  if (batch <= 0 || ncones <= 0) return 0;
+  if (!cones) return -1;
+  for (int first = 0; first < ncones; first += kMaxFused) {
+    const int count = ncones - first < kMaxFused ? ncones - first : kMaxFused;
+    if (!FusedLayout(batch)) {
+      for (int k = 0; k < count; k++) {
+        int rc = cxb_small_prepare(stream, batch, cones + first + k, dy, ystride, affine, c_weight, d_cw, e_weight,
+                                   d_out2 + 4 * (first + k), ostride, d_active);
+        if (rc) return rc;
+      }
+      continue;
+    }
+    ConeList l;
+    size_t smem;
+    if (!MakeList(count, cones + first, SpectralSmemBytes, &l, &smem)) return -1;
+    int rc = EnsureSmem(PrepareMultiKernel, smem);
+    if (rc) return rc;
+    CountLaunch();
+    PrepareMultiKernel<<<dim3(batch, count), g_spectral_threads, smem, AsStream(stream)>>>(
+        batch, (long)(smem / 8), l, dy, ystride, affine, c_weight, d_cw, e_weight, d_out2 + 4 * first, ostride,
+        d_active);
+    rc = LaunchStatus();
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int cxb_small_take_step_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, double step,
+                              const double* d_step, double e_weight, int* d_info, const int* d_active) {
+  if (batch <= 0 || ncones <= 0) return 0;
+  if (!cones) return -1;
+  for (int first = 0; first < ncones; first += kMaxFused) {
+    const int count = ncones - first < kMaxFused ? ncones - first : kMaxFused;
+    bool psd = false;
+    for (int k = 0; k < count; k++) psd = psd || cones[first + k].type == CXB_CONE_PSD;
+    if (psd && !d_info) return -1;
+    if (!FusedLayout(batch)) {
+      for (int k = 0; k < count; k++) {
+        int rc = cxb_small_take_step(stream, batch, cones + first + k, step, d_step, e_weight, d_info, d_active);
+        if (rc) return rc;
+      }
+      continue;
+    }
+    ConeList l;
+    size_t smem;
+    if (!MakeList(count, cones + first, SmemBytes, &l, &smem)) return -1;
+    int rc = EnsureSmem(TakeStepMultiKernel, smem);
+    if (rc) return rc;
+    CountLaunch();
+    TakeStepMultiKernel<<<dim3(batch, count), kThreads, smem, AsStream(stream)>>>(batch, (long)(smem / 8), l, step,
+                                                                                  d_step, e_weight, d_info, d_active);
+    rc = LaunchStatus();
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long hstride, int* d_info,

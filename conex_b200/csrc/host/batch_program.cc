@@ -28,6 +28,7 @@ size_t Align4(size_t n) { return (n + 3) & ~static_cast<size_t>(3); }
 struct BatchProgram::Impl {
   DeviceContext ctx;
   std::vector<ConeSlot> cones;
+  std::vector<cxb_small_cone> descs;  // the descriptors of `cones`, contiguous, for the fused launches
   int B = 0, m = 0;
   long ldh = 0;
   size_t vstride = 0;
@@ -131,6 +132,7 @@ BatchProgram::BatchProgram(const std::vector<Program*>& programs) : impl_(std::m
     c.desc.state_stride = static_cast<long>(c.state_size);
     c.desc.work = c.work_size ? c.work.get() : nullptr;
     c.desc.work_stride = static_cast<long>(c.work_size);
+    d.descs.push_back(c.desc);
   }
   // ---- pack the cone data -----------------------------------------------------------------------
   for (int p = 0; p < B; p++) {
@@ -256,9 +258,8 @@ int BatchProgram::Maximize(const double* b_in, const SolverConfiguration& cfg, d
             "H2D cost vectors");
   d.ctx.Synchronize();  // hcoef is reused below
   d.ctx.Zero(d.y.get(), vs * B);
-  for (auto& c : d.cones) {
-    DeviceCheck(cxb_small_set_identity(s, B, &c.desc, nullptr), "cxb_small_set_identity");
-  }
+  const int ncones = static_cast<int>(nc);
+  DeviceCheck(cxb_small_set_identity_multi(s, B, ncones, d.descs.data(), nullptr), "cxb_small_set_identity_multi");
   cudaEvent_t ev_begin, ev_end, ev_a, ev_b;
   CudaCheck(cudaEventCreate(&ev_begin), "cudaEventCreate");
   CudaCheck(cudaEventCreate(&ev_end), "cudaEventCreate");
@@ -354,11 +355,9 @@ int BatchProgram::Maximize(const double* b_in, const SolverConfiguration& cfg, d
                                       d.y.get(), vs, mu_mask),
                   "cxb_batched_lincomb");
       DeviceCheck(cxb_small_potrs(s, B, m, d.H.get(), d.ldh, d.ldh * m, d.y.get(), vs, mu_mask), "cxb_small_potrs");
-      for (size_t k = 0; k < nc; k++) {
-        DeviceCheck(cxb_small_eigen(s, B, &d.cones[k].desc, d.y.get(), vs, 0.0, coef_cw, cone_out + 4 * k, ostride,
-                                    mu_mask),
-                    "cxb_small_eigen");
-      }
+      DeviceCheck(cxb_small_eigen_multi(s, B, ncones, d.descs.data(), d.y.get(), vs, 0.0, coef_cw, cone_out, ostride,
+                                        mu_mask),
+                  "cxb_small_eigen_multi");
       d.DownloadOut(static_cast<size_t>(B) * 4 * nc);
       for (int p = 0; p < B; p++) {
         ProgramState& q = st[p];
@@ -410,11 +409,9 @@ int BatchProgram::Maximize(const double* b_in, const SolverConfiguration& cfg, d
                                     d.y.get(), vs, active),
                 "cxb_batched_lincomb");
     DeviceCheck(cxb_small_potrs(s, B, m, d.H.get(), d.ldh, d.ldh * m, d.y.get(), vs, active), "cxb_small_potrs");
-    for (size_t k = 0; k < nc; k++) {
-      DeviceCheck(cxb_small_prepare(s, B, &d.cones[k].desc, d.y.get(), vs, 0, 0.0, coef_cw, 1.0, cone_out + 4 * k,
-                                    ostride, active),
-                  "cxb_small_prepare");
-    }
+    DeviceCheck(cxb_small_prepare_multi(s, B, ncones, d.descs.data(), d.y.get(), vs, 0, 0.0, coef_cw, 1.0, cone_out,
+                                        ostride, active),
+                "cxb_small_prepare_multi");
     d.DownloadOut(static_cast<size_t>(B) * 4 * nc);
     std::vector<double> normsq(B, 0.0);
     for (int p = 0; p < B; p++) {
@@ -432,10 +429,8 @@ int BatchProgram::Maximize(const double* b_in, const SolverConfiguration& cfg, d
       d.hcoef[4 * static_cast<size_t>(B) + p] = std::min(1.0, 2.0 / (ninf * ninf));
     }
     d.UploadCoef(4 * static_cast<size_t>(B), B);
-    for (size_t k = 0; k < nc; k++) {
-      DeviceCheck(cxb_small_take_step(s, B, &d.cones[k].desc, 1.0, coef_step, 1.0, d.info.get() + B, active),
-                  "cxb_small_take_step");
-    }
+    DeviceCheck(cxb_small_take_step_multi(s, B, ncones, d.descs.data(), 1.0, coef_step, 1.0, d.info.get() + B, active),
+                "cxb_small_take_step_multi");
     // ---- objectives (cone_program.cc:441-467) -------------------------------------------------------
     DeviceCheck(cxb_batched_dot(s, B, m, d.b.get(), vs, d.y.get(), vs, dots + 0, 4), "cxb_batched_dot");
     DeviceCheck(cxb_batched_dot(s, B, m, d.AQc.get(), vs, d.y.get(), vs, dots + 1, 4), "cxb_batched_dot");
@@ -520,11 +515,9 @@ int BatchProgram::Maximize(const double* b_in, const SolverConfiguration& cfg, d
                                     d.y2.get(), vs, active),
                 "cxb_batched_lincomb");
     DeviceCheck(cxb_small_potrs(s, B, m, d.H.get(), d.ldh, d.ldh * m, d.y2.get(), vs, active), "cxb_small_potrs");
-    for (size_t k = 0; k < nc; k++) {
-      DeviceCheck(cxb_small_prepare(s, B, &d.cones[k].desc, d.y2.get(), vs, 1, 0.0, nullptr, 0.0, cone_out + 4 * k,
-                                    ostride, active),
-                  "cxb_small_prepare");
-    }
+    DeviceCheck(cxb_small_prepare_multi(s, B, ncones, d.descs.data(), d.y2.get(), vs, 1, 0.0, nullptr, 0.0, cone_out,
+                                        ostride, active),
+                "cxb_small_prepare_multi");
   }
   CudaCheck(cudaEventRecord(ev_end, cs), "cudaEventRecord");
   d.ctx.Synchronize();

@@ -319,6 +319,23 @@ int cxb_small_prepare(void* stream, int batch, const cxb_small_cone* cone, const
 /* TakeStep with step size `step` (or d_step[p]); d_info[p] != 0 reports a singular Padé system. */
 int cxb_small_take_step(void* stream, int batch, const cxb_small_cone* cone, double step,
                         const double* d_step, double e_weight, int* d_info, const int* d_active);
+/* The four per-cone operations on `ncones` cones of every program in ONE launch (grid = programs x cones; up to 8
+ * cones per launch, longer lists are chunked): the lock step of a batch of multi-cone programs (reference
+ * cone_program.cc:173-214, :416-436 loop over the constraints) otherwise serialises the cones' dependent chains.
+ * Cone k writes d_out + 4 k (+ p * ostride). Same arithmetic as the per-cone calls, bit for bit. */
+int cxb_small_set_identity_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones,
+                                 const int* d_active);
+int cxb_small_eigen_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, const double* dy,
+                          long ystride, double c_weight, const double* d_cw, double* d_out4, long ostride,
+                          const int* d_active);
+int cxb_small_prepare_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, const double* dy,
+                            long ystride, int affine, double c_weight, const double* d_cw, double e_weight,
+                            double* d_out2, long ostride, const int* d_active);
+int cxb_small_take_step_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, double step,
+                              const double* d_step, double e_weight, int* d_info, const int* d_active);
+/* CTA size (32, 64 or 128 threads; default 128) of cxb_small_eigen / cxb_small_prepare in the CTA layout: their
+ * phases are short dependent chains, so what bounds them is the number of cones resident per SM. */
+void cxb_set_small_cone_threads(int threads);
 /* Cholesky of `batch` N x N matrices (lower, ld, stride) and solves with nrhs = 1; d_info[p] = 0 or
  * 1 + first non-positive pivot (block_triangular_operations.cc:184-219, :114-182). */
 int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long hstride, int* d_info,
