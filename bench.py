@@ -474,6 +474,10 @@ def run_b200_batched(args):
         proc.L.cxb_set_small_psd_mma(args.small_psd_mma)
     if args.small_team_mode >= 0:
         proc.L.cxb_set_small_team_mode(args.small_team_mode)
+    if args.small_cone_threads > 0:
+        proc.L.cxb_set_small_cone_threads(args.small_cone_threads)
+    if args.small_fused_launches >= 0:
+        proc.L.cxb_set_small_fused_launches(args.small_fused_launches)
     line = batched_bench(proc, args, workload_shape(args), cpu_leg=not args.no_cpu_baseline)
     if line is not None:
         print(json.dumps(line))
@@ -1063,6 +1067,8 @@ def main():
                     help="N > 1 A/B: exchange the scaled matrices through ncclSend / ncclRecv instead of peer memory")
     ap.add_argument("--gemm-max-ktiles", type=int, default=-1, help="A/B: cxb_set_gemm_split_policy")
     ap.add_argument("--small-psd-mma", type=int, default=-1, help="c3 A/B: cxb_set_small_psd_mma (2 default, 1, 0)")
+    ap.add_argument("--small-cone-threads", type=int, default=0, help="c3 A/B: cxb_set_small_cone_threads (32/64/128)")
+    ap.add_argument("--small-fused-launches", type=int, default=-1, help="c3 A/B: cxb_set_small_fused_launches (0/1)")
     ap.add_argument("--small-team-mode", type=int, default=-1, help="c3 A/B: cxb_set_small_team_mode (1 default, 0)")
     ap.add_argument("--replicated-cholesky", action="store_true",
                     help="N > 1: factor the Schur complement on every rank instead of across the ranks")

@@ -759,78 +759,60 @@ CXB_HD void ExtremeTridiagonal(const double* a, const double* b, int k, double* 
 }
 
 // The same two eigenvalues by multi-section with the whole team: every round evaluates the Sturm count at
-// kSections interior points of each of the two brackets at once (one point per thread) and keeps the
-// sub-interval that still holds the wanted eigenvalue, so a bracket shrinks by kSections + 1 per round
-// (12 rounds to full double precision) instead of by 2 per serial bisection step (60 - 200 steps of k
-// dependent divisions on ONE thread — that serial section used to be most of the time of the batched
-// eigen-bound kernels). Converges to the same eigenvalues as ExtremeTridiagonal up to the final bracket width.
-// scratch: 2 * kSections + 8 doubles.
+// kSections interior points of a bracket at once (one point per thread) and keeps the sub-interval that still holds the
+// wanted eigenvalue — the first point whose count exceeds `which`, found with a team-wide first_true (a ballot in the
+// warp layout) — so a bracket shrinks by kSections + 1 per round (11 rounds to full double precision) instead of by 2
+// per serial bisection step. The brackets are uniform values held in registers by every thread: a round is one phase
+// per bracket, with no serial section. (The first version selected the sub-interval in a single-thread loop over the
+// kSections counts — 2 x 32 dependent shared-memory reads and divisions per round, more than the Sturm counts
+// themselves and the largest part of the batched eigen-bound kernels.) Converges to the same eigenvalues as
+// ExtremeTridiagonal up to the final bracket width. `scratch` is unused (kept for the callers' layout).
 constexpr int kSections = 32;
 template <class T>
 CXB_HD void ExtremeTridiagonalTeam(T& t, const double* a, const double* b, int k, double* scratch, double* emin,
                                    double* emax) {
+  (void)scratch;
   if (k == 1) {
     t.single([&]() { *emin = *emax = a[0]; });
     return;
   }
-  double* cnt = scratch;                  // [2][kSections] Sturm counts (as doubles)
-  double* br = scratch + 2 * kSections;   // lo_min, hi_min, lo_max, hi_max, tiny, done_min, done_max
-  t.single([&]() {
-    const double eps = 2.220446049250313e-16;
-    double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308, scale = 0;
-    for (int i = 0; i < k; i++) {
-      const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < k ? fabs(b[i]) : 0.0);
-      lo = fmin(lo, a[i] - r);
-      hi = fmax(hi, a[i] + r);
-      scale = fmax(scale, fabs(a[i]) + r);
+  // Gershgorin bounds: every thread computes the same values (k <= n / 2 entries)
+  const double eps = 2.220446049250313e-16;
+  double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308, scale = 0;
+  for (int i = 0; i < k; i++) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < k ? fabs(b[i]) : 0.0);
+    lo = fmin(lo, a[i] - r);
+    hi = fmax(hi, a[i] + r);
+    scale = fmax(scale, fabs(a[i]) + r);
+  }
+  const double pad = 4 * eps * (scale + 1e-300) * (double)k;
+  lo -= pad;
+  hi += pad;
+  double tiny = 2.2250738585072014e-308 / eps + 1e-30 * scale * scale;
+  tiny = fmax(tiny, eps * eps * scale);
+  double result[2];
+  for (int side = 0; side < 2; side++) {
+    const int which = side == 0 ? 0 : k - 1;
+    double l = lo, h = hi;
+    for (int round = 0; round < 64; round++) {
+      const double w = h - l;
+      const double first = l + w * (1.0 / (double)(kSections + 1));
+      const double last = l + w * ((double)kSections / (double)(kSections + 1));
+      if (!(first > l) || !(last < h)) break;  // the interior points no longer resolve the bracket: converged
+      const int q = t.first_true(kSections, [&](int i) {
+        const double x = l + w * ((double)(i + 1) / (double)(kSections + 1));
+        return SturmCountBelow(a, b, k, x, tiny) > which;
+      });
+      const double nl = q == 0 ? l : l + w * ((double)q / (double)(kSections + 1));
+      const double nh = q == kSections ? h : l + w * ((double)(q + 1) / (double)(kSections + 1));
+      l = nl;
+      h = nh;
     }
-    const double pad = 4 * eps * (scale + 1e-300) * (double)k;
-    lo -= pad;
-    hi += pad;
-    double tiny = 2.2250738585072014e-308 / eps + 1e-30 * scale * scale;
-    tiny = fmax(tiny, eps * eps * scale);
-    br[0] = br[2] = lo;
-    br[1] = br[3] = hi;
-    br[4] = tiny;
-    br[5] = br[6] = 0.0;
-  });
-  for (int round = 0; round < 64; round++) {
-    if (br[5] != 0.0 && br[6] != 0.0) break;  // uniform: read after the barrier that ends the last phase
-    t.par(2 * kSections, [&](int e) {
-      const int side = e / kSections, q = e % kSections;
-      if (br[5 + side] != 0.0) return;
-      const double lo = br[2 * side], hi = br[2 * side + 1];
-      const double x = lo + (hi - lo) * ((double)(q + 1) / (double)(kSections + 1));
-      cnt[e] = (double)SturmCountBelow(a, b, k, x, br[4]);
-    });
-    t.single([&]() {
-      for (int side = 0; side < 2; side++) {
-        if (br[5 + side] != 0.0) continue;
-        const int which = side == 0 ? 0 : k - 1;
-        const double lo = br[2 * side], hi = br[2 * side + 1];
-        const double first = lo + (hi - lo) * (1.0 / (double)(kSections + 1));
-        const double last = lo + (hi - lo) * ((double)kSections / (double)(kSections + 1));
-        if (!(first > lo) || !(last < hi)) {  // the interior points no longer resolve the bracket: converged
-          br[5 + side] = 1.0;
-          continue;
-        }
-        double nlo = lo, nhi = hi;
-        for (int q = 0; q < kSections; q++) {
-          const double x = lo + (hi - lo) * ((double)(q + 1) / (double)(kSections + 1));
-          if ((int)cnt[side * kSections + q] > which) {
-            nhi = x;
-            break;
-          }
-          nlo = x;
-        }
-        br[2 * side] = nlo;
-        br[2 * side + 1] = nhi;
-      }
-    });
+    result[side] = 0.5 * (l + h);
   }
   t.single([&]() {
-    *emin = 0.5 * (br[0] + br[1]);
-    *emax = 0.5 * (br[2] + br[3]);
+    *emin = result[0];
+    *emax = result[1];
   });
 }
 
@@ -1003,19 +985,11 @@ CXB_HD void PsdTakeStep(T& t, int n, double step, double ew, double* W, const do
   });
   // Gaussian elimination with partial (row) pivoting on the n x 2n augmented matrix
   for (int k = 0; k < n; k++) {
-    const int p = (int)t.bcast([&]() {
-      int best = k;
-      double bv = fabs(M[k * n + k]);
-      for (int i = k + 1; i < n; i++) {
-        const double v = fabs(M[k * n + i]);
-        if (v > bv) {
-          bv = v;
-          best = i;
-        }
-      }
-      if (bv == 0.0 && *info == 0) *info = k + 1;
-      return (double)best;
-    });
+    // pivot = the first entry of largest magnitude in column k, rows k..n-1 (a team reduction instead of a serial
+    // scan by one thread: 20 dependent shared-memory reads per column were a third of this function's chain)
+    double bv;
+    const int p = k + t.argmax_first(n - k, [&](int i) { return fabs(M[k * n + k + i]); }, &bv);
+    if (bv == 0.0) t.single([&]() { if (*info == 0) *info = k + 1; });
     if (p != k) {
       t.par(2 * n, [&](int c) {
         const double tmp = M[c * n + k];

@@ -446,7 +446,8 @@ bool MakeList(int count, const cxb_small_cone* cones, SmemOf smem_of, ConeList* 
   return true;
 }
 // the fused launches use the CTA layout; with the warp layout forced everywhere the cones are launched one by one
-bool FusedLayout(int batch) { return !(g_small_team_mode == 1 && batch >= 8); }
+int g_small_fused = 1;  // cxb_set_small_fused_launches: A/B switch
+bool FusedLayout(int batch) { return g_small_fused && !(g_small_team_mode == 1 && batch >= 8); }
 }  // namespace
 
 int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active) {
@@ -523,6 +524,7 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
 }
 
 void cxb_set_small_psd_mma(int enabled) { g_small_psd_mma = enabled; }
+void cxb_set_small_fused_launches(int enabled) { g_small_fused = enabled; }
 void cxb_set_small_cone_threads(int threads) {
   if (threads == 32 || threads == 64 || threads == 128) g_spectral_threads = threads;
 }

@@ -54,6 +54,47 @@ struct WarpTeam {
     __syncwarp();
     return v;
   }
+  // index of the FIRST largest f(i), i in [0, n) (n >= 1), and that value
+  template <class F>
+  __device__ __forceinline__ int argmax_first(int n, F f, double* vmax) {
+    double v = -1.7976931348623157e308;
+    int idx = 0;  // stays valid when every f(i) is NaN
+    for (int i = tid; i < n; i += 32) {
+      const double x = f(i);
+      if (x > v) {
+        v = x;
+        idx = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(kFull, v, o);
+      const int oi = __shfl_xor_sync(kFull, idx, o);
+      if (ov > v || (ov == v && oi < idx)) {
+        v = ov;
+        idx = oi;
+      }
+    }
+    __syncwarp();
+    *vmax = v;
+    return idx;
+  }
+  // smallest i in [0, n) with pred(i), or n
+  template <class F>
+  __device__ __forceinline__ int first_true(int n, F pred) {
+    int found = n;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + tid;
+      const bool p = (i < n) && pred(i);
+      const unsigned mask = __ballot_sync(kFull, p);
+      if (mask) {
+        found = base + __ffs(mask) - 1;
+        break;
+      }
+    }
+    __syncwarp();
+    return found;
+  }
   template <class F>
   __device__ __forceinline__ double bcast(F f) {
     __syncwarp();
@@ -107,6 +148,60 @@ struct DeviceTeam {
     double v = -1.7976931348623157e308;
     for (int i = tid; i < n; i += nt) v = fmax(v, -f(i));
     return -BlockMax(v);
+  }
+  // index of the FIRST largest f(i), i in [0, n) (n >= 1), and that value. Two barriers; at most 16 warps.
+  template <class F>
+  __device__ __forceinline__ int argmax_first(int n, F f, double* vmax) {
+    double v = -1.7976931348623157e308;
+    int idx = 0;  // stays valid when every f(i) is NaN
+    for (int i = tid; i < n; i += nt) {
+      const double x = f(i);
+      if (x > v) {
+        v = x;
+        idx = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) {
+        v = ov;
+        idx = oi;
+      }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (nt + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) {
+      red[warp] = v;
+      red[16 + warp] = (double)idx;
+    }
+    __syncthreads();
+    v = red[0];
+    idx = (int)red[16];
+    for (int w = 1; w < nwarps; w++) {
+      const double ov = red[w];
+      const int oi = (int)red[16 + w];
+      if (ov > v || (ov == v && oi < idx)) {
+        v = ov;
+        idx = oi;
+      }
+    }
+    *vmax = v;
+    return idx;
+  }
+  // smallest i in [0, n) with pred(i), or n
+  template <class F>
+  __device__ __forceinline__ int first_true(int n, F pred) {
+    double v = -1.7976931348623157e308;
+    for (int i = tid; i < n; i += nt)
+      if (pred(i)) {
+        v = -(double)i;
+        break;  // this thread's later candidates are larger
+      }
+    v = BlockMax(v);
+    return v < -1e300 ? n : (int)(-v);
   }
   // f() evaluated by one thread, result given to all.
   template <class F>

@@ -336,6 +336,8 @@ int cxb_small_take_step_multi(void* stream, int batch, int ncones, const cxb_sma
 /* CTA size (32, 64 or 128 threads; default 128) of cxb_small_eigen / cxb_small_prepare in the CTA layout: their
  * phases are short dependent chains, so what bounds them is the number of cones resident per SM. */
 void cxb_set_small_cone_threads(int threads);
+/* A/B switch: 0 = the *_multi entry points launch their cones one after the other (default 1). */
+void cxb_set_small_fused_launches(int enabled);
 /* Cholesky of `batch` N x N matrices (lower, ld, stride) and solves with nrhs = 1; d_info[p] = 0 or
  * 1 + first non-positive pivot (block_triangular_operations.cc:184-219, :114-182). */
 int cxb_small_potrf(void* stream, int batch, int N, double* dH, long ldh, long hstride, int* d_info,

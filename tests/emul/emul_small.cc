@@ -38,6 +38,24 @@ struct HostTeam {
     return v;
   }
   template <class F>
+  int argmax_first(int n, F f, double* vmax) {
+    int best = 0;
+    double bv = f(0);
+    for (int i = 1; i < n; i++)
+      if (f(i) > bv) {
+        bv = f(i);
+        best = i;
+      }
+    *vmax = bv;
+    return best;
+  }
+  template <class F>
+  int first_true(int n, F pred) {
+    for (int i = 0; i < n; i++)
+      if (pred(i)) return i;
+    return n;
+  }
+  template <class F>
   double bcast(F f) {
     return f();
   }

@@ -298,3 +298,73 @@ def test_both_thread_layouts_give_the_same_results(kind, n, m):
         else:
             close(a, b, 1e-8, "eigen / prepare / state")
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", [128, 64, 32])
+def test_fused_launch_over_the_cones_of_a_program_is_bit_identical(threads):
+    """cxb_small_*_multi (one launch, grid = programs x cones — what the batched lock step uses) against the per-cone
+    entry points on the same batch of {PSD 20, PSD 8, SOC 10, LP 40, PSD 12 ... } cones: eigen-bounds, step norms and
+    the updated scaling points must agree bit for bit, for every CTA size of cxb_set_small_cone_threads. Ten cones, so
+    the list is also split over two launches."""
+    from small_backend import ConeDesc
+    be = Backend("device")
+    vp = C.c_void_p
+    rng = np.random.Generator(np.random.PCG64(2024))
+    B, m = 13, 12
+    shapes = [(PSD, 20), (PSD, 8), (SOC, 10), (LP, 40), (PSD, 12), (SOC, 3), (LP, 5), (PSD, 4), (PSD, 16), (LP, 17)]
+    data = [np.stack([random_cone_data(kind, n, m, rng) for _ in range(B)]) for kind, n in shapes]
+    y = rng.uniform(-0.05, 0.05, size=(B, m))
+    cw = rng.uniform(0.5, 1.5, size=B)
+    steps = rng.uniform(0.3, 1.0, size=B)
+    nc = len(shapes)
+
+    def run(fused):
+        cones = [be.cone(kind, n, m, d) for (kind, n), d in zip(shapes, data)]
+        if not fused:
+            ev = np.stack([c.eigen(y, cw) for c in cones], axis=1)                  # B x nc x 4
+            pr = np.stack([c.prepare(y, cw, 1.0) for c in cones], axis=1)           # B x nc x 2
+            for c in cones:
+                assert (c.take_step(steps, 1.0) == 0).all()
+            return ev, pr, [c.get_state() for c in cones]
+        descs = (ConeDesc * nc)(*[c.desc for c in cones])
+        lib = be.lib
+        yd, cwd, sd = be.upload(y), be.upload(cw), be.upload(steps)
+        out = be.alloc(B * nc * 4)
+        info = be.alloc(B, np.int32)
+        for f in (lib.cxb_small_set_identity_multi, lib.cxb_small_eigen_multi, lib.cxb_small_prepare_multi,
+                  lib.cxb_small_take_step_multi):
+            f.restype = C.c_int
+        assert lib.cxb_small_set_identity_multi(vp(None), C.c_int(B), C.c_int(nc), descs, vp(None)) == 0
+        assert lib.cxb_small_eigen_multi(vp(None), C.c_int(B), C.c_int(nc), descs, be.ptr(yd), C.c_long(m),
+                                         C.c_double(0.0), be.ptr(cwd), be.ptr(out), C.c_long(4 * nc), vp(None)) == 0
+        ev = be.download(out).reshape(B, nc, 4).copy()
+        assert lib.cxb_small_prepare_multi(vp(None), C.c_int(B), C.c_int(nc), descs, be.ptr(yd), C.c_long(m),
+                                           C.c_int(0), C.c_double(0.0), be.ptr(cwd), C.c_double(1.0), be.ptr(out),
+                                           C.c_long(4 * nc), vp(None)) == 0
+        pr = be.download(out).reshape(B, nc, 4)[:, :, :2].copy()
+        assert lib.cxb_small_take_step_multi(vp(None), C.c_int(B), C.c_int(nc), descs, C.c_double(1.0), be.ptr(sd),
+                                             C.c_double(1.0), be.ptr(info), vp(None)) == 0
+        assert (be.download(info) == 0).all()
+        return ev, pr, [c.get_state() for c in cones]
+
+    be.lib.cxb_set_small_cone_threads.restype = None
+    reference = run(False)                      # per-cone launches, 128 threads
+    be.lib.cxb_set_small_cone_threads(threads)
+    try:
+        fused = run(True)
+        single = run(False) if threads != 128 else reference
+    finally:
+        be.lib.cxb_set_small_cone_threads(128)
+    for got in (fused, single):
+        # the reductions of a 128-thread team and of a smaller one combine in different orders: bitwise only at 128
+        if threads == 128:
+            assert np.array_equal(got[0], reference[0]) and np.array_equal(got[1], reference[1])
+            for a, b in zip(got[2], reference[2]):
+                assert np.array_equal(a, b)
+        else:
+            close(got[0], reference[0], 1e-9, "eigen")
+            close(got[1], reference[1], 1e-9, "prepare")
+            for a, b in zip(got[2], reference[2]):
+                close(a, b, 1e-12, "state")
+    assert np.array_equal(fused[0], single[0]) and np.array_equal(fused[1], single[1])
