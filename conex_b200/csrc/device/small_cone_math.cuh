@@ -901,12 +901,8 @@ CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double*
   });
   *trace = t.sum(n, [&](int i) { return sWS[i * n + i]; });
   *trace_sq = t.sum(nn, [&](int e) { return sWS[e] * sWS[(e % n) * n + e / n]; });
-  *index = (int)t.bcast([&]() {
-    int best = 0;
-    for (int i = 1; i < n; i++)
-      if (sWS[i * n + i] > sWS[best * n + best]) best = i;
-    return (double)best;
-  });
+  double largest;
+  *index = t.argmax_first(n, [&](int i) { return sWS[i * n + i]; }, &largest);
 }
 
 // out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} (psd_constraint.cc:97-128)
