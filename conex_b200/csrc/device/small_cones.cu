@@ -413,7 +413,7 @@ struct Geometry {
   size_t smem;
 };
 // CTA size of the spectral kernels (cxb_small_eigen / cxb_small_prepare) in the CTA layout (cxb_set_small_cone_threads).
-int g_spectral_threads = kThreads;
+int g_spectral_threads = 64;  // measured on C3: 57.0 ms (64) / 57.6 (32) / 59.5 (128), profiles/r02_j_bench_c3_variants.txt
 Geometry MakeGeometry(int batch, size_t per_program_bytes, bool chain_only = false, int threads = kThreads) {
   Geometry g;
   g.per = (long)(per_program_bytes / sizeof(double));

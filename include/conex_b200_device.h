@@ -333,7 +333,7 @@ int cxb_small_prepare_multi(void* stream, int batch, int ncones, const cxb_small
                             double* d_out2, long ostride, const int* d_active);
 int cxb_small_take_step_multi(void* stream, int batch, int ncones, const cxb_small_cone* cones, double step,
                               const double* d_step, double e_weight, int* d_info, const int* d_active);
-/* CTA size (32, 64 or 128 threads; default 128) of cxb_small_eigen / cxb_small_prepare in the CTA layout: their
+/* CTA size (32, 64 or 128 threads; default 64) of cxb_small_eigen / cxb_small_prepare in the CTA layout: their
  * phases are short dependent chains, so what bounds them is the number of cones resident per SM. */
 void cxb_set_small_cone_threads(int threads);
 /* A/B switch: 0 = the *_multi entry points launch their cones one after the other (default 1). */

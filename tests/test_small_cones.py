@@ -349,13 +349,14 @@ def test_fused_launch_over_the_cones_of_a_program_is_bit_identical(threads):
         return ev, pr, [c.get_state() for c in cones]
 
     be.lib.cxb_set_small_cone_threads.restype = None
-    reference = run(False)                      # per-cone launches, 128 threads
-    be.lib.cxb_set_small_cone_threads(threads)
     try:
+        be.lib.cxb_set_small_cone_threads(128)
+        reference = run(False)                      # per-cone launches, 128 threads
+        be.lib.cxb_set_small_cone_threads(threads)
         fused = run(True)
         single = run(False) if threads != 128 else reference
     finally:
-        be.lib.cxb_set_small_cone_threads(128)
+        be.lib.cxb_set_small_cone_threads(64)       # the default
     for got in (fused, single):
         # the reductions of a 128-thread team and of a smaller one combine in different orders: bitwise only at 128
         if threads == 128:
