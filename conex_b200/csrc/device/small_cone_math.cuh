@@ -29,6 +29,25 @@ namespace small {
 
 CXB_HD void Accumulate(double* dst, double v, bool acc) { *dst = acc ? *dst + v : v; }
 
+// e -> (e % d, e / d) for 0 <= e < 2^31 with e / d < 2^22 (every use below: the quotient is a row or column index)
+// without the ~25-instruction integer division by a run-time divisor — the element loops map a flat index to
+// (row, column) for every element, and in the issue-bound kernels those two divisions were most of the instructions.
+// The float product is off by less than one from the true quotient and one comparison each way makes it exact, so
+// the loops visit the same elements in the same order.
+struct Divider {
+  int d;
+  float inv;
+  CXB_HD explicit Divider(int divisor) : d(divisor), inv(1.0f / (float)divisor) {}
+  CXB_HD int quot(int e) const {
+    int q = (int)(((float)e + 0.5f) * inv);
+    const int r = e - q * d;
+    if (r < 0) q--;
+    if (r >= d) q++;
+    return q;
+  }
+  CXB_HD int rem(int e) const { return e - quot(e) * d; }
+};
+
 // out[r] = sum_j data[r + j * rows] y[j] - k * data[r + m * rows]
 template <class T>
 CXB_HD void NegativeSlack(T& t, int rows, int m, const double* data, const double* y, double k,
@@ -95,13 +114,14 @@ CXB_HD void LpSchur(T& t, int n, int m, const double* Ac, const double* W, doubl
                     double* AW, double* AQc, double* scal, bool acc, double* sm = nullptr) {
   if (sm != nullptr) {
     const int P = n | 1;  // odd pitch: threads on consecutive columns hit different banks
+    const Divider by_n(n), by_m(m);
     t.par(n * (m + 1), [&](int e) {
-      const int r = e % n, j = e / n;
+      const int j = by_n.quot(e), r = e - j * n;
       sm[(long)j * P + r] = W[r] * Ac[e];
     });
     const double* wc = sm + (long)m * P;
     t.par(m * m, [&](int e) {
-      const int i = e % m, j = e / m;
+      const int j = by_m.quot(e), i = e - j * m;
       if (i < j) return;
       const double* ai = sm + (long)i * P;
       const double* aj = sm + (long)j * P;
@@ -128,8 +148,9 @@ CXB_HD void LpSchur(T& t, int n, int m, const double* Ac, const double* W, doubl
     return;
   }
   const double* c = Ac + (long)m * n;
+  const Divider by_m(m);
   t.par(m * m, [&](int e) {
-    const int i = e % m, j = e / m;
+    const int j = by_m.quot(e), i = e - j * m;
     if (i < j) return;
     const double* ai = Ac + (long)i * n;
     const double* aj = Ac + (long)j * n;
@@ -283,8 +304,9 @@ CXB_HD void SocSchur(T& t, int o, int m, const double* Ac, const double* Wv, dou
   const double det = SpinDet(t, o, wsqrt);
   t.par(m + 1, [&](int j) { QuadRepSerial(o, wsqrt, det, Ac + (long)j * o, WA + (long)j * o); });
   const double* WC = WA + (long)m * o;
+  const Divider by_m(m);
   t.par(m * m, [&](int e) {
-    const int i = e % m, j = e / m;
+    const int j = by_m.quot(e), i = e - j * m;
     if (i < j) return;
     double s = 0;
     for (int r = 0; r < o; r++) s += WA[(long)i * o + r] * WA[(long)j * o + r];
@@ -367,8 +389,9 @@ CXB_HD void SocTakeStep(T& t, int o, double step, double* Wv, const double* d, d
 // C = A * B (n x n, column-major, all three distinct)
 template <class T>
 CXB_HD void MatMul(T& t, int n, const double* A, const double* B, double* C) {
+  const Divider by_n(n);
   t.par(n * n, [&](int e) {
-    const int r = e % n, c = e / n;
+    const int c = by_n.quot(e), r = e - c * n;
     double s = 0;
     for (int k = 0; k < n; k++) s += A[k * n + r] * B[c * n + k];
     C[e] = s;
@@ -377,7 +400,7 @@ CXB_HD void MatMul(T& t, int n, const double* A, const double* B, double* C) {
 
 template <class T>
 CXB_HD void PsdSetIdentity(T& t, int n, double* W) {
-  t.par(n * n, [&](int e) { W[e] = (e % n == e / n) ? 1.0 : 0.0; });
+  t.par(n * n, [&](int e) { W[e] = (e % (n + 1) == 0) ? 1.0 : 0.0; });
 }
 
 // H_ij = <W A_i W, A_j> (lower), AW_j = <W, A_j>, AQc_j = <W C W, A_j>, <w,c> = <W, C>,
@@ -900,7 +923,11 @@ CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double*
     T2[e] = sWS[e];
   });
   *trace = t.sum(n, [&](int i) { return sWS[i * n + i]; });
-  *trace_sq = t.sum(nn, [&](int e) { return sWS[e] * sWS[(e % n) * n + e / n]; });
+  const Divider by_n(n);
+  *trace_sq = t.sum(nn, [&](int e) {
+    const int c = by_n.quot(e), r = e - c * n;
+    return sWS[e] * sWS[r * n + c];
+  });
   double largest;
   *index = t.argmax_first(n, [&](int i) { return sWS[i * n + i]; }, &largest);
 }
@@ -966,15 +993,16 @@ CXB_HD void PsdTakeStep(T& t, int n, double step, double ew, double* W, const do
   double* U = sm + 2 * nn;
   double* M = sm + 3 * nn;  // n x 2n: [V - U | V + U]
   double* sW = sm + 5 * nn;
+  const Divider by_n(n), by_diag(n + 1);  // e is a diagonal entry iff e % (n + 1) == 0
   t.par(nn, [&](int e) {
-    X[e] = (T2[e] + ((e % n == e / n) ? ew : 0.0)) * step;
+    X[e] = (T2[e] + ((by_diag.rem(e) == 0) ? ew : 0.0)) * step;
     sW[e] = W[e];
   });
   MatMul(t, n, X, X, X2);
-  t.par(nn, [&](int e) { M[e] = X2[e] + ((e % n == e / n) ? 60.0 : 0.0); });
+  t.par(nn, [&](int e) { M[e] = X2[e] + ((by_diag.rem(e) == 0) ? 60.0 : 0.0); });
   MatMul(t, n, X, M, U);  // U = X (X^2 + 60 I)
   t.par(nn, [&](int e) {
-    const double v = 12.0 * X2[e] + ((e % n == e / n) ? 120.0 : 0.0);
+    const double v = 12.0 * X2[e] + ((by_diag.rem(e) == 0) ? 120.0 : 0.0);
     const double u = U[e];
     M[e] = v - u;
     M[nn + e] = v + u;
@@ -993,12 +1021,12 @@ CXB_HD void PsdTakeStep(T& t, int n, double step, double ew, double* W, const do
         M[c * n + p] = tmp;
       });
     }
+    // One phase per column: rows on lanes, columns on warps; the multiplier of a row is computed by every thread that
+    // needs it and is not stored (the back substitution below only reads the upper triangle and the right-hand sides).
     const double piv = M[k * n + k];
-    t.par(n - k - 1, [&](int i) { M[k * n + k + 1 + i] /= piv; });
-    t.par((n - k - 1) * (2 * n - k - 1), [&](int e) {
-      const int i = k + 1 + e % (n - k - 1), c = k + 1 + e / (n - k - 1);
-      M[c * n + i] -= M[k * n + i] * M[c * n + k];
-    });
+    t.par2(
+        n - k - 1, 2 * n - k - 1, [&](int i) { return M[k * n + k + 1 + i] / piv; },
+        [&](int i, int c, double l) { M[(k + 1 + c) * n + k + 1 + i] -= l * M[(k + 1 + c) * n + k]; });
   }
   // back substitution, one right-hand-side column per thread
   t.par(n, [&](int c) {
@@ -1010,7 +1038,10 @@ CXB_HD void PsdTakeStep(T& t, int n, double step, double ew, double* W, const do
     }
   });
   MatMul(t, n, M + nn, sW, X);  // E W
-  t.par(nn, [&](int e) { W[e] = 0.5 * (X[e] + X[(e % n) * n + e / n]); });
+  t.par(nn, [&](int e) {
+    const int c = by_n.quot(e), r = e - c * n;
+    W[e] = 0.5 * (X[e] + X[r * n + c]);
+  });
 }
 
 // =================================================================================================
@@ -1019,8 +1050,9 @@ CXB_HD void PsdTakeStep(T& t, int n, double step, double ew, double* W, const do
 // sH: N*N doubles of shared memory. info: 0 or 1 + column of the first non-positive pivot.
 template <class T>
 CXB_HD void SmallPotrf(T& t, int N, double* H, long ld, double* sH, int* info) {
+  const Divider by_N(N);
   t.par(N * N, [&](int e) {
-    const int r = e % N, c = e / N;
+    const int c = by_N.quot(e), r = e - c * N;
     sH[e] = (r >= c) ? H[(long)c * ld + r] : 0.0;
   });
   int failed = 0;
@@ -1035,17 +1067,18 @@ CXB_HD void SmallPotrf(T& t, int N, double* H, long ld, double* sH, int* info) {
     const double rd = sqrt(d);
     t.par(N - j - 1, [&](int i) { sH[j * N + j + 1 + i] /= rd; });
     const int w = N - j - 1;
-    t.par(w * w, [&](int e) {
-      const int r = j + 1 + e % w, c = j + 1 + e / w;
-      if (r >= c) sH[c * N + r] -= sH[j * N + r] * sH[j * N + c];
-    });
+    t.par2(
+        w, w, [&](int i) { return sH[j * N + j + 1 + i]; },
+        [&](int i, int c, double lr) {
+          if (i >= c) sH[(j + 1 + c) * N + j + 1 + i] -= lr * sH[j * N + j + 1 + c];
+        });
   }
   if (failed) {
     t.single([&]() { *info = failed; });
     return;
   }
   t.par(N * N, [&](int e) {
-    const int r = e % N, c = e / N;
+    const int c = by_N.quot(e), r = e - c * N;
     if (r > c) H[(long)c * ld + r] = sH[e];
     if (r == c) H[(long)c * ld + r] = sqrt(sH[e]);
   });

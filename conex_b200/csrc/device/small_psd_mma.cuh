@@ -338,9 +338,14 @@ __device__ inline void PsdSchurMma(int n, int m, const double* __restrict__ AC, 
 constexpr int kWarps2 = 8;
 constexpr int kThreads2 = kWarps2 * 32;
 
+// (m + 1) mod 8 matrices are left for a last round in which only that many warps would work (m = 40: ONE warp, a
+// sixth of the scaling phase with seven warps idle). When there are at most kCoopMax of them — and their extra slots
+// still let two CTAs share an SM — they are loaded at the start and scaled by the whole CTA instead, one 8 x 8 tile of
+// each product per warp.
+constexpr int kCoopMax = 2;
 struct Layout2 {
-  int kp, k4, pa, pl, px;
-  long off_l, off_x, off_s, total;
+  int kp, k4, pa, pl, px, ncoop;
+  long off_l, off_x, off_s, off_c, total;
 };
 __host__ __device__ inline Layout2 MakeLayout2(int n, int m) {
   Layout2 y;
@@ -352,7 +357,11 @@ __host__ __device__ inline Layout2 MakeLayout2(int n, int m) {
   y.off_l = 64;
   y.off_x = y.off_l + LImageDoubles(n);
   y.off_s = y.off_x + (long)(m + 2) * y.px;
-  y.total = y.off_s + (long)kWarps2 * n * y.pa + 16;
+  y.off_c = y.off_s + (long)kWarps2 * n * y.pa;
+  y.ncoop = (m + 1) % kWarps2;
+  if (y.ncoop > kCoopMax || m + 1 < kWarps2) y.ncoop = 0;
+  if (sizeof(double) * (size_t)(y.off_c + (long)y.ncoop * n * y.pa + 16) > 113 * 1024) y.ncoop = 0;
+  y.total = y.off_c + (long)y.ncoop * n * y.pa + 16;
   return y;
 }
 __host__ inline bool Supported2(int n, int m, size_t* smem_bytes) {
@@ -385,8 +394,15 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
     CpAsyncCommit();
   };
   for (int q = tid; q < LImageDoubles(n) / 2; q += kThreads2) CpAsync16(sL + 2 * q, factor + 2 * q, 16);
+  const int mfull = m + 1 - y.ncoop;  // matrices 0 .. mfull-1 go through the warps' slots, the rest is shared work
+  for (int q = tid; q < y.ncoop * n * half; q += kThreads2) {
+    const int which = q / (n * half), e = q - which * n * half;
+    const int col = e / half, within = e - col * half;
+    CpAsync16(sm + y.off_c + ((long)which * n + col) * pa + 2 * within,
+              AC + (long)(mfull + which) * nn + (long)col * n + 2 * within, 16);
+  }
   CpAsyncCommit();
-  if (warp <= m) fetch(warp);
+  if (warp < mfull) fetch(warp);
   for (int e = tid; e < (m + 2) * (px - kp); e += kThreads2) {
     const int row = e / (px - kp), q = kp + e % (px - kp);
     sX[(long)row * px + q] = 0.0;
@@ -402,7 +418,15 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
     return;
   }
   const double kSqrt2 = 1.4142135623730951;
-  for (int i = warp; i <= m; i += kWarps2) {
+  for (int i = warp; i < mfull; i += kWarps2) {
+    // The slot is busy until S_i is done, so the next matrix cannot travel to shared memory yet: ask for it in L2 now,
+    // and the cp.async issued after the second product pays an L2 round trip instead of a DRAM one.
+    if (i + kWarps2 < mfull) {
+      const double* next = AC + (long)(i + kWarps2) * nn;
+      for (int off = lane * 16; off < nn; off += 512) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(next + off));
+      }
+    }
     double accT[NT][NT][2];
 #pragma unroll
     for (int a = 0; a < NT; a++)
@@ -448,7 +472,7 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
       }
     }
     __syncwarp();  // the slot is free: the next matrix travels while S_i is packed
-    if (i + kWarps2 <= m) fetch(i + kWarps2);
+    if (i + kWarps2 < mfull) fetch(i + kWarps2);
     double* Xi = sX + (long)i * px;
 #pragma unroll
     for (int tr = 0; tr < NT; tr++) {
@@ -469,50 +493,117 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
     CpAsyncWait<0>();
     __syncwarp();
   }
-  __syncthreads();  // X complete
+  __syncthreads();  // rows 0 .. mfull-1 of X complete; every warp's slot is free
+  for (int q = 0; q < y.ncoop; q++) {
+    // the same two products, tile by tile: T = A L into the (free) slot of warp q, then S = L^T T into row mfull + q
+    const double* Aq = sm + y.off_c + (long)q * n * pa;
+    double* Tq = sm + y.off_s + (long)q * n * pa;
+    for (int task = warp; task < NT * NT; task += kWarps2) {
+      const int tr = task / NT, tc = task - tr * NT;
+      double t0 = 0.0, t1 = 0.0;
+      for (int k = tc * 8; k < n; k += 4) {
+        const double b = sL[(k + tig) * pl + min(tc * 8 + gid, n - 1)];
+        const double a = Aq[(k + tig) * pa + min(tr * 8 + gid, n - 1)];
+        Dmma884(t0, t1, a, b);
+      }
+      const int row = tr * 8 + gid, col = tc * 8 + tig * 2;
+      if (row < n) {
+        if (col < n) Tq[row * pa + col] = t0;
+        if (col + 1 < n) Tq[row * pa + col + 1] = t1;
+      }
+    }
+    __syncthreads();
+    double* Xi = sX + (long)(mfull + q) * px;
+    for (int task = warp; task < NT * (NT + 1) / 2; task += kWarps2) {
+      int tr = 0, tc = task;
+      while (tc > tr) {
+        tc -= tr + 1;
+        tr++;
+      }
+      double s0 = 0.0, s1 = 0.0;
+      for (int k = tr * 8; k < n; k += 4) {
+        const double a = sL[(k + tig) * pl + min(tr * 8 + gid, n - 1)];
+        const double b = Tq[(k + tig) * pa + min(tc * 8 + gid, n - 1)];
+        Dmma884(s0, s1, a, b);
+      }
+      const int row = tr * 8 + gid;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int col = tc * 8 + tig * 2 + e;
+        if (row < n && col <= row) {
+          Xi[col * n - col * (col - 1) / 2 + (row - col)] = (row == col) ? (e ? s1 : s0) : kSqrt2 * (e ? s1 : s0);
+        }
+      }
+    }
+  }
+  if (y.ncoop) __syncthreads();  // X complete
 
+  // Gram X X^T, lower triangle, in 8 x 8 DMMA tiles: the tiles (row-major over the lower triangle) are dealt to the warps
+  // in runs of `chunk` consecutive tiles, so that all warps carry the same number of DMMA per k-step (21 tiles on 8
+  // warps for m = 40: 3 each on 7 warps; the 16 x 16 blocks this replaces were 6 blocks of 4 on 6 warps). Tiles of a
+  // run that share their row (or lie on the diagonal) share the fragment load. Same k order per entry as before.
   const int MI = m + 2, MJ = m + 1;
-  const int nb = ((MI + 7) / 8 + 1) / 2;
-  const int nblk = nb * (nb + 1) / 2;
+  const int nt8 = (MI + 7) / 8;
+  const int ntiles = nt8 * (nt8 + 1) / 2;
+  constexpr int CH = 4;
+  int chunk = (ntiles + kWarps2 - 1) / kWarps2;
+  if (chunk > CH) chunk = CH;
   const int ksteps = y.k4 / 4;
-  for (int blk = warp; blk < nblk; blk += kWarps2) {
-    int bj = 0, rem = blk;
-    while (rem >= nb - bj) {
-      rem -= nb - bj;
-      bj++;
+  for (int base = warp * chunk; base < ntiles; base += kWarps2 * chunk) {
+    const int cnt = min(chunk, ntiles - base);
+    int ti = 0, tj = base;
+    while (tj >= ti + 1) {
+      tj -= ti + 1;
+      ti++;
     }
-    const int bi = bj + rem;
-    const double* xa0 = sX + (long)min(16 * bi + gid, MI - 1) * px + tig;
-    const double* xa1 = sX + (long)min(16 * bi + 8 + gid, MI - 1) * px + tig;
-    const double* xb0 = sX + (long)min(16 * bj + gid, MI - 1) * px + tig;
-    const double* xb1 = sX + (long)min(16 * bj + 8 + gid, MI - 1) * px + tig;
-    double c00[2] = {0, 0}, c01[2] = {0, 0}, c10[2] = {0, 0}, c11[2] = {0, 0};
+    const double* xa[CH];
+    const double* xb[CH];
+    int row0[CH], col0[CH];
+    bool same_a[CH], diag[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      row0[c] = 8 * ti;
+      col0[c] = 8 * tj;
+      same_a[c] = c > 0 && row0[c] == row0[c - 1];
+      diag[c] = ti == tj;
+      xa[c] = sX + (long)min(8 * ti + gid, MI - 1) * px + tig;
+      xb[c] = sX + (long)min(8 * tj + gid, MI - 1) * px + tig;
+      if (++tj > ti) {
+        ti++;
+        tj = 0;
+      }
+    }
+    double accG[CH][2];
+#pragma unroll
+    for (int c = 0; c < CH; c++) accG[c][0] = accG[c][1] = 0.0;
     for (int k = 0; k < ksteps; k++) {
-      const double a0 = xa0[4 * k], a1 = xa1[4 * k], b0 = xb0[4 * k], b1 = xb1[4 * k];
-      Dmma884(c00[0], c00[1], a0, b0);
-      if (bi != bj) Dmma884(c01[0], c01[1], a0, b1);  // above the diagonal inside a diagonal block
-      Dmma884(c10[0], c10[1], a1, b0);
-      Dmma884(c11[0], c11[1], a1, b1);
+      double a = 0.0;
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        if (c < cnt) {
+          if (!same_a[c]) a = xa[c][4 * k];
+          const double b = diag[c] ? a : xb[c][4 * k];
+          Dmma884(accG[c][0], accG[c][1], a, b);
+        }
+      }
     }
-    auto put = [&](int i, int j, double s) {
+    auto put = [&](int i, int j, double v) {
       if (i >= MI || j >= MJ || i < j) return;
       if (i < m) {
-        small::Accumulate(G + (long)j * ldg + i, s, acc);
+        small::Accumulate(G + (long)j * ldg + i, v, acc);
       } else if (i == m) {
-        small::Accumulate(j < m ? AQc + j : scal + 1, s, acc);
+        small::Accumulate(j < m ? AQc + j : scal + 1, v, acc);
       } else {
-        small::Accumulate(j < m ? AW + j : scal + 0, s, acc);
+        small::Accumulate(j < m ? AW + j : scal + 0, v, acc);
       }
     };
-    const int i0 = 16 * bi + gid, j0 = 16 * bj + tig * 2;
-    put(i0, j0, c00[0]);
-    put(i0, j0 + 1, c00[1]);
-    put(i0, j0 + 8, c01[0]);
-    put(i0, j0 + 9, c01[1]);
-    put(i0 + 8, j0, c10[0]);
-    put(i0 + 8, j0 + 1, c10[1]);
-    put(i0 + 8, j0 + 8, c11[0]);
-    put(i0 + 8, j0 + 9, c11[1]);
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      if (c < cnt) {
+        put(row0[c] + gid, col0[c] + tig * 2, accG[c][0]);
+        put(row0[c] + gid, col0[c] + tig * 2 + 1, accG[c][1]);
+      }
+    }
   }
 }
 

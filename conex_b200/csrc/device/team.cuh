@@ -26,6 +26,16 @@ struct WarpTeam {
     for (int i = tid; i < n; i += 32) f(i);
     __syncwarp();
   }
+  // f(i, c, row_value(i)) for every (i, c) in rows x cols: rows on lanes, columns in sequence. row_value must only read
+  // data that f does not write.
+  template <class R, class F>
+  __device__ __forceinline__ void par2(int rows, int cols, R row_value, F f) {
+    for (int i = tid; i < rows; i += 32) {
+      const double rv = row_value(i);
+      for (int c = 0; c < cols; c++) f(i, c, rv);
+    }
+    __syncwarp();
+  }
   template <class F>
   __device__ __forceinline__ double sum(int n, F f) {
     double v = 0;
@@ -129,6 +139,17 @@ struct DeviceTeam {
   template <class F>
   __device__ __forceinline__ void par(int n, F f) {
     for (int i = tid; i < n; i += nt) f(i);
+    __syncthreads();
+  }
+  // f(i, c, row_value(i)) for every (i, c) in rows x cols: rows on lanes, columns on warps (no index division, and a
+  // per-row value is computed once per thread and row). row_value must only read data that f does not write.
+  template <class R, class F>
+  __device__ __forceinline__ void par2(int rows, int cols, R row_value, F f) {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
+    for (int i = lane; i < rows; i += 32) {
+      const double rv = row_value(i);
+      for (int c = warp; c < cols; c += nwarps) f(i, c, rv);
+    }
     __syncthreads();
   }
   template <class F>

@@ -19,6 +19,13 @@ struct HostTeam {
   void par(int n, F f) {
     for (int i = 0; i < n; i++) f(i);
   }
+  template <class R, class F>
+  void par2(int rows, int cols, R row_value, F f) {
+    for (int i = 0; i < rows; i++) {
+      const double rv = row_value(i);
+      for (int c = 0; c < cols; c++) f(i, c, rv);
+    }
+  }
   template <class F>
   double sum(int n, F f) {
     double v = 0;

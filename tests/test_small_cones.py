@@ -235,11 +235,13 @@ def test_psd_schur_with_indefinite_scaling_point_uses_the_classic_form(be, n, m)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,m", [(20, 40), (8, 3), (32, 12)])
+@pytest.mark.parametrize("n,m", [(20, 40), (8, 3), (32, 12), (12, 9), (16, 15), (24, 16), (4, 8), (8, 60)])
 def test_dmma_schur_kernel_against_the_dfma_team_kernel(n, m):
     """A/B of the two device kernels behind cxb_small_schur for dense LMI blocks (cxb_set_small_psd_mma): the DMMA
     kernel with the scaled matrices in shared memory against the DFMA team kernel, on a random positive definite
-    scaling point, with and without accumulation into an existing system."""
+    scaling point, with and without accumulation into an existing system. The shapes cover the leftover matrices of
+    the slot-per-warp layout ((m + 1) mod 8 = 1 or 2: scaled by the whole CTA; else by their warps), one to four DMMA
+    tiles per side, and Gram tile lists of one and two passes."""
     be = Backend("device")
     rng = np.random.Generator(np.random.PCG64(7 * n + m))
     B = 5
