@@ -907,8 +907,9 @@ CXB_HD void LanczosExtremes(T& t, int n, const double* WS, const double* W, cons
 // S -> T1, WS = W S -> T2 (global state) and shared copies; returns tr(WS), tr(WS WS) and the
 // index of the largest diagonal entry of WS (first occurrence).
 // sm layout: sW | sS | sWS | vec...
+// packed (may be null): the lower triangles of the matrices of AC (symmetric matrices: same sums, half the reads).
 template <class T>
-CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double* y, double cw,
+CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double* packed, const double* y, double cw,
                              const double* W, double* T1, double* T2, double* sm, double* trace,
                              double* trace_sq, int* index) {
   const int nn = n * n;
@@ -916,7 +917,18 @@ CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double*
   double* sS = sm + nn;
   double* sWS = sm + 2 * nn;
   t.par(nn, [&](int e) { sW[e] = W[e]; });
-  NegativeSlack(t, nn, m, AC, y, cw, sS);
+  if (packed != nullptr) {
+    double* sP = sWS;  // n (n + 1) / 2 doubles, free until the product below
+    NegativeSlack(t, n * (n + 1) / 2, m, packed, y, cw, sP);
+    const Divider by_rows(n);
+    t.par(nn, [&](int e) {
+      const int c = by_rows.quot(e), r = e - c * n;
+      const int lo = r < c ? r : c, hi = r < c ? c : r;  // entry (hi, lo) of the lower triangle
+      sS[e] = sP[lo * n - lo * (lo - 1) / 2 + (hi - lo)];
+    });
+  } else {
+    NegativeSlack(t, nn, m, AC, y, cw, sS);
+  }
   MatMul(t, n, sW, sS, sWS);
   t.par(nn, [&](int e) {
     T1[e] = sS[e];
@@ -935,11 +947,11 @@ CXB_HD void PsdWeightedSlack(T& t, int n, int m, const double* AC, const double*
 // out4 = {lambda_min, lambda_max, frobenius_norm_squared, trace} (psd_constraint.cc:97-128)
 template <class T>
 CXB_HD void PsdEigen(T& t, int n, int m, const double* AC, const double* y, double cw, const double* W,
-                     double* T1, double* T2, double* sm, double* out4) {
+                     double* T1, double* T2, double* sm, double* out4, const double* packed = nullptr) {
   const int nn = n * n;
   double tr, trsq;
   int index;
-  PsdWeightedSlack(t, n, m, AC, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
+  PsdWeightedSlack(t, n, m, AC, packed, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
   double* ritz = sm + 3 * nn;
   // start vector: column `index` of the true -S
   t.warp0([&](auto& w) { LanczosExtremes(w, n, sm + 2 * nn, sm, sm + nn + index * n, sm + 3 * nn + 2, ritz); });
@@ -954,11 +966,12 @@ CXB_HD void PsdEigen(T& t, int n, int m, const double* AC, const double* y, doub
 // out2 = {norminfd, normsqrd} (psd_constraint.cc:45-84); affine: W <- (1 + ew) W + (W S) W (:33-43)
 template <class T>
 CXB_HD void PsdPrepare(T& t, int n, int m, const double* AC, const double* y, bool affine, double cw,
-                       double ew, double* W, double* T1, double* T2, double* sm, double* out2) {
+                       double ew, double* W, double* T1, double* T2, double* sm, double* out2,
+                       const double* packed = nullptr) {
   const int nn = n * n;
   double tr, trsq;
   int index;
-  PsdWeightedSlack(t, n, m, AC, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
+  PsdWeightedSlack(t, n, m, AC, packed, y, cw, W, T1, T2, sm, &tr, &trsq, &index);
   if (affine) {
     double* sT = sm + nn;  // the slack is no longer needed
     MatMul(t, n, sm + 2 * nn, sm, sT);

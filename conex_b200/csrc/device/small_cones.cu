@@ -23,11 +23,13 @@ struct ConeArgs {
   long state_stride;
   double* work;
   long work_stride;
+  const double* packed;
+  long packed_stride;
 };
 
 ConeArgs Convert(const cxb_small_cone* c) {
   return ConeArgs{c->type, c->n, c->m, c->data, c->data_stride, c->state, c->state_stride, c->work,
-                  c->work_stride};
+                  c->work_stride, c->type == CXB_CONE_PSD ? c->packed : nullptr, c->packed_stride};
 }
 
 // Shared memory (doubles) needed by the PSD paths: 6 n^2 matrices + Lanczos vectors + slack + the scratch of the
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(psdmma::kThreads, 1) PsdSchurMmaKernel(ConeArg
                           accumulate != 0);
 }
 
-template <int NT>
+template <int N4>
 __global__ void __launch_bounds__(psdmma::kThreads2, 2) PsdSchurMma2Kernel(ConeArgs c, double* G, long ldg, long gstride,
                                                                          double* AW, double* AQc, long vstride,
                                                                          double* scal, long sstride, int accumulate,
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(psdmma::kThreads2, 2) PsdSchurMma2Kernel(ConeA
   const int p = blockIdx.x;
   if (active && !active[p]) return;
   double* work = c.work + p * c.work_stride;
-  psdmma::PsdSchurMma2<NT>(c.n, c.m, c.data + p * c.data_stride, c.state + p * c.state_stride, work, work, sm,
+  psdmma::PsdSchurMma2<N4>(c.m, c.data + p * c.data_stride, c.state + p * c.state_stride, work, work, sm,
                            G + p * gstride, ldg, AW + p * vstride, AQc + p * vstride, scal + p * sstride,
                            accumulate != 0);
 }
@@ -202,7 +204,8 @@ __device__ __forceinline__ void EigenBody(int batch, long per, const ConeArgs& c
     small::SocEigen(t, c.n + 1, c.m, data, yp, k, st, SocScratch(c, per, base, work), out);
   } else {
     const long nnp = Align4((long)c.n * c.n);
-    small::PsdEigen(t, c.n, c.m, data, yp, k, st, st + nnp, st + 2 * nnp, base + 64, out);
+    small::PsdEigen(t, c.n, c.m, data, yp, k, st, st + nnp, st + 2 * nnp, base + 64, out,
+                    c.packed ? c.packed + p * c.packed_stride : nullptr);
   }
 }
 
@@ -229,7 +232,8 @@ __device__ __forceinline__ void PrepareBody(int batch, long per, const ConeArgs&
     small::SocPrepare(t, c.n + 1, c.m, data, yp, k, st, st + op, SocScratch(c, per, base, work), out);
   } else {
     const long nnp = Align4((long)c.n * c.n);
-    small::PsdPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + nnp, st + 2 * nnp, base + 64, out);
+    small::PsdPrepare(t, c.n, c.m, data, yp, affine != 0, k, ew, st, st + nnp, st + 2 * nnp, base + 64, out,
+                      c.packed ? c.packed + p * c.packed_stride : nullptr);
   }
 }
 
@@ -307,6 +311,25 @@ __global__ void __launch_bounds__(kThreads) TakeStepMultiKernel(int batch, long 
                                                                 const double* step_p, double ew, int* info,
                                                                 const int* active) {
   TakeStepBody<false>(batch, per, l.c[blockIdx.y], step, step_p, ew, info, active);
+}
+
+// Lower triangles of the m + 1 matrices of a PSD cone, one CTA per program; flags matrices that are not symmetric.
+__global__ void __launch_bounds__(kThreads) PackSymmetricKernel(ConeArgs c, double* packed, long packed_stride,
+                                                               int* asymmetric) {
+  const int p = blockIdx.x;
+  const int n = c.n, kp = n * (n + 1) / 2;
+  const double* data = c.data + p * c.data_stride;
+  double* out = packed + p * packed_stride;
+  bool bad = false;
+  for (int e = threadIdx.x; e < (c.m + 1) * n * n; e += blockDim.x) {
+    const int j = e / (n * n), q = e - j * n * n;
+    const int col = q / n, row = q - col * n;
+    if (row < col) continue;
+    const double v = data[e];
+    bad = bad || !(v == data[(long)j * n * n + (long)row * n + col]);
+    out[(long)j * kp + col * n - col * (col - 1) / 2 + (row - col)] = v;
+  }
+  if (bad) *asymmetric = 1;
 }
 
 template <bool WARP>
@@ -464,6 +487,17 @@ int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, 
   return LaunchStatus();
 }
 
+int cxb_small_pack_symmetric(void* stream, int batch, const cxb_small_cone* cone, double* d_packed, long packed_stride,
+                             int* d_asymmetric) {
+  if (batch <= 0) return 0;
+  if (!ValidCone(cone) || cone->type != CXB_CONE_PSD || !d_packed || !d_asymmetric) return -1;
+  if (packed_stride < (long)(cone->m + 1) * (cone->n * (cone->n + 1) / 2)) return -1;
+  ConeArgs c = Convert(cone);
+  CountLaunch();
+  PackSymmetricKernel<<<batch, kThreads, 0, AsStream(stream)>>>(c, d_packed, packed_stride, d_asymmetric);
+  return LaunchStatus();
+}
+
 int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double* dG, long ldg,
                     long gstride, double* dAW, double* dAQc, long vstride, double* d_scal, long sstride,
                     int accumulate, const int* d_active) {
@@ -486,11 +520,15 @@ int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double*
     };
     const int nt = (c.n + 7) / 8;
     if (two_per_sm) {
-      switch (nt) {
+      switch (c.n / 4) {  // Supported2: n = 4, 8, ..., 32
         case 1: return launch(PsdSchurMma2Kernel<1>);
         case 2: return launch(PsdSchurMma2Kernel<2>);
         case 3: return launch(PsdSchurMma2Kernel<3>);
-        default: return launch(PsdSchurMma2Kernel<4>);
+        case 4: return launch(PsdSchurMma2Kernel<4>);
+        case 5: return launch(PsdSchurMma2Kernel<5>);
+        case 6: return launch(PsdSchurMma2Kernel<6>);
+        case 7: return launch(PsdSchurMma2Kernel<7>);
+        default: return launch(PsdSchurMma2Kernel<8>);
       }
     }
     switch (nt) {

@@ -30,10 +30,8 @@ constexpr int kThreads = kWarps * 32;
 
 // smallest p >= x with p == 4 (mod 16): row pitch (doubles) that makes the 8 x 4 / 4 x 8 DMMA fragment loads
 // bank-conflict free in both orientations
-__host__ __device__ inline int Pitch4Mod16(int x) {
-  int p = (x + 15) / 16 * 16 + 4;
-  if (p - 16 >= x) p -= 16;
-  return p;
+__host__ __device__ constexpr int Pitch4Mod16(int x) {
+  return ((x + 15) / 16 * 16 + 4) - 16 >= x ? ((x + 15) / 16 * 16 + 4) - 16 : (x + 15) / 16 * 16 + 4;
 }
 
 struct Layout {
@@ -373,23 +371,31 @@ __host__ inline bool Supported2(int n, int m, size_t* smem_bytes) {
   return *smem_bytes <= 113 * 1024;  // two CTAs per SM
 }
 
-template <int NT>
-__device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC, const double* __restrict__ W,
+// N4 = n / 4: the order of the block is a compile-time constant, so the k loops of the two products unroll completely
+// (their shared-memory loads are hoisted ahead of the DMMA chains instead of being issued and waited for k-step by
+// k-step) and the index arithmetic of the loads, of the cp.async chunks and of the packing folds into immediates.
+template <int N4>
+__device__ inline void PsdSchurMma2(int m, const double* __restrict__ AC, const double* __restrict__ W,
                                     const double* __restrict__ factor, double* work, double* sm, double* G, long ldg,
                                     double* AW, double* AQc, double* scal, bool acc) {
+  constexpr int n = 4 * N4, NT = (n + 7) / 8, nn = n * n, half = n / 2;
+  constexpr int pa = Pitch4Mod16(n), pl = Pitch4Mod16(n);
   const Layout2 y = MakeLayout2(n, m);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
-  const int nn = n * n, pa = y.pa, pl = y.pl, px = y.px, kp = y.kp;
+  const int px = y.px, kp = y.kp;
   double* sL = sm + y.off_l;
   double* sX = sm + y.off_x;
   double* Ai = sm + y.off_s + (long)warp * n * pa;  // this warp's slot
-  const int half = n / 2;                            // 16-byte chunks per column
   auto fetch = [&](int i) {  // matrix i -> the slot, by this warp's lanes
     const double* src = AC + (long)i * nn;
-    for (int q = lane; q < n * half; q += 32) {
-      const int col = q / half, within = q - col * half;
-      CpAsync16(Ai + (long)col * pa + 2 * within, src + (long)col * n + 2 * within, 16);
+#pragma unroll
+    for (int q0 = 0; q0 < n * half; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < n * half) {
+        const int col = q / half, within = q - col * half;
+        CpAsync16(Ai + col * pa + 2 * within, src + col * n + 2 * within, 16);
+      }
     }
     CpAsyncCommit();
   };
@@ -411,13 +417,17 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
   __syncthreads();
   for (int c = tid; c < n; c += kThreads2) sX[(long)(m + 1) * px + c * n - c * (c - 1) / 2] = 1.0;
   CpAsyncWait<0>();
-  __syncthreads();  // L, the first matrix of every warp, the padding of X
+  __syncthreads();  // L, the first matrix of every warp, the shared matrices, the padding of X
   if (factor[LImageDoubles(n)] != 0.0) {
     DeviceTeam t(sm);
     small::PsdSchurClassic(t, n, m, AC, W, work, sm + 64, G, ldg, AW, AQc, scal, acc);
     return;
   }
   const double kSqrt2 = 1.4142135623730951;
+  // fragment rows of the 8-row tiles, clamped into the block (rows >= n are computed and never stored)
+  int frow[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) frow[t] = min(t * 8 + gid, n - 1);
   for (int i = warp; i < mfull; i += kWarps2) {
     // The slot is busy until S_i is done, so the next matrix cannot travel to shared memory yet: ask for it in L2 now,
     // and the cp.async issued after the second product pays an L2 round trip instead of a DRAM one.
@@ -434,11 +444,12 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
       for (int b = 0; b < NT; b++) accT[a][b][0] = accT[a][b][1] = 0.0;
 #pragma unroll
     for (int tc = 0; tc < NT; tc++) {
+#pragma unroll
       for (int k = tc * 8; k < n; k += 4) {
-        const double b = sL[(k + tig) * pl + min(tc * 8 + gid, n - 1)];
+        const double b = sL[(k + tig) * pl + frow[tc]];
 #pragma unroll
         for (int tr = 0; tr < NT; tr++) {
-          const double a = Ai[(k + tig) * pa + min(tr * 8 + gid, n - 1)];
+          const double a = Ai[(k + tig) * pa + frow[tr]];
           Dmma884(accT[tr][tc][0], accT[tr][tc][1], a, b);
         }
       }
@@ -461,12 +472,12 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
     for (int tr = 0; tr < NT; tr++) {
 #pragma unroll
       for (int b = 0; b < NT; b++) accS[tr][b][0] = accS[tr][b][1] = 0.0;
-      for (int k = tr * 8; k < n; k += 4) {
-        const double a = sL[(k + tig) * pl + min(tr * 8 + gid, n - 1)];
 #pragma unroll
-        for (int tc = 0; tc < NT; tc++) {
-          if (tc > tr) break;
-          const double b = Ai[(k + tig) * pa + min(tc * 8 + gid, n - 1)];
+      for (int k = tr * 8; k < n; k += 4) {
+        const double a = sL[(k + tig) * pl + frow[tr]];
+#pragma unroll
+        for (int tc = 0; tc <= tr; tc++) {
+          const double b = Ai[(k + tig) * pa + frow[tc]];
           Dmma884(accS[tr][tc][0], accS[tr][tc][1], a, b);
         }
       }
@@ -477,8 +488,7 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
 #pragma unroll
     for (int tr = 0; tr < NT; tr++) {
 #pragma unroll
-      for (int tc = 0; tc < NT; tc++) {
-        if (tc > tr) break;
+      for (int tc = 0; tc <= tr; tc++) {
         const int row = tr * 8 + gid;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
@@ -500,10 +510,11 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
     double* Tq = sm + y.off_s + (long)q * n * pa;
     for (int task = warp; task < NT * NT; task += kWarps2) {
       const int tr = task / NT, tc = task - tr * NT;
+      const int ra = min(tr * 8 + gid, n - 1), rb = min(tc * 8 + gid, n - 1);
       double t0 = 0.0, t1 = 0.0;
       for (int k = tc * 8; k < n; k += 4) {
-        const double b = sL[(k + tig) * pl + min(tc * 8 + gid, n - 1)];
-        const double a = Aq[(k + tig) * pa + min(tr * 8 + gid, n - 1)];
+        const double b = sL[(k + tig) * pl + rb];
+        const double a = Aq[(k + tig) * pa + ra];
         Dmma884(t0, t1, a, b);
       }
       const int row = tr * 8 + gid, col = tc * 8 + tig * 2;
@@ -520,10 +531,11 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
         tc -= tr + 1;
         tr++;
       }
+      const int ra = min(tr * 8 + gid, n - 1), rb = min(tc * 8 + gid, n - 1);
       double s0 = 0.0, s1 = 0.0;
       for (int k = tr * 8; k < n; k += 4) {
-        const double a = sL[(k + tig) * pl + min(tr * 8 + gid, n - 1)];
-        const double b = Tq[(k + tig) * pa + min(tc * 8 + gid, n - 1)];
+        const double a = sL[(k + tig) * pl + ra];
+        const double b = Tq[(k + tig) * pa + rb];
         Dmma884(s0, s1, a, b);
       }
       const int row = tr * 8 + gid;
@@ -538,72 +550,53 @@ __device__ inline void PsdSchurMma2(int n, int m, const double* __restrict__ AC,
   }
   if (y.ncoop) __syncthreads();  // X complete
 
-  // Gram X X^T, lower triangle, in 8 x 8 DMMA tiles: the tiles (row-major over the lower triangle) are dealt to the warps
-  // in runs of `chunk` consecutive tiles, so that all warps carry the same number of DMMA per k-step (21 tiles on 8
-  // warps for m = 40: 3 each on 7 warps; the 16 x 16 blocks this replaces were 6 blocks of 4 on 6 warps). Tiles of a
-  // run that share their row (or lie on the diagonal) share the fragment load. Same k order per entry as before.
+  // Gram X X^T (lower) in 16 x 16 blocks of four DMMA tiles, one block per warp and pass, results written straight
+  // from the accumulators. (Dealing 8 x 8 tiles evenly to the warps was tried: the per-tile pointer selection cost more
+  // issue slots than the better balance returned — 391 vs 353 us per launch, profiles/r02_l_*.)
   const int MI = m + 2, MJ = m + 1;
-  const int nt8 = (MI + 7) / 8;
-  const int ntiles = nt8 * (nt8 + 1) / 2;
-  constexpr int CH = 4;
-  int chunk = (ntiles + kWarps2 - 1) / kWarps2;
-  if (chunk > CH) chunk = CH;
-  const int ksteps = y.k4 / 4;
-  for (int base = warp * chunk; base < ntiles; base += kWarps2 * chunk) {
-    const int cnt = min(chunk, ntiles - base);
-    int ti = 0, tj = base;
-    while (tj >= ti + 1) {
-      tj -= ti + 1;
-      ti++;
+  const int nb = ((MI + 7) / 8 + 1) / 2;
+  const int nblk = nb * (nb + 1) / 2;
+  constexpr int ksteps = (n * (n + 1) / 2 + 3) / 4;
+  for (int blk = warp; blk < nblk; blk += kWarps2) {
+    int bj = 0, rem = blk;
+    while (rem >= nb - bj) {
+      rem -= nb - bj;
+      bj++;
     }
-    const double* xa[CH];
-    const double* xb[CH];
-    int row0[CH], col0[CH];
-    bool same_a[CH], diag[CH];
-#pragma unroll
-    for (int c = 0; c < CH; c++) {
-      row0[c] = 8 * ti;
-      col0[c] = 8 * tj;
-      same_a[c] = c > 0 && row0[c] == row0[c - 1];
-      diag[c] = ti == tj;
-      xa[c] = sX + (long)min(8 * ti + gid, MI - 1) * px + tig;
-      xb[c] = sX + (long)min(8 * tj + gid, MI - 1) * px + tig;
-      if (++tj > ti) {
-        ti++;
-        tj = 0;
-      }
-    }
-    double accG[CH][2];
-#pragma unroll
-    for (int c = 0; c < CH; c++) accG[c][0] = accG[c][1] = 0.0;
+    const int bi = bj + rem;
+    const double* xa0 = sX + (long)min(16 * bi + gid, MI - 1) * px + tig;
+    const double* xa1 = sX + (long)min(16 * bi + 8 + gid, MI - 1) * px + tig;
+    const double* xb0 = sX + (long)min(16 * bj + gid, MI - 1) * px + tig;
+    const double* xb1 = sX + (long)min(16 * bj + 8 + gid, MI - 1) * px + tig;
+    double c00[2] = {0, 0}, c01[2] = {0, 0}, c10[2] = {0, 0}, c11[2] = {0, 0};
+    const bool off_diagonal = bi != bj;
+#pragma unroll 4
     for (int k = 0; k < ksteps; k++) {
-      double a = 0.0;
-#pragma unroll
-      for (int c = 0; c < CH; c++) {
-        if (c < cnt) {
-          if (!same_a[c]) a = xa[c][4 * k];
-          const double b = diag[c] ? a : xb[c][4 * k];
-          Dmma884(accG[c][0], accG[c][1], a, b);
-        }
-      }
+      const double a0 = xa0[4 * k], a1 = xa1[4 * k], b0 = xb0[4 * k], b1 = xb1[4 * k];
+      Dmma884(c00[0], c00[1], a0, b0);
+      if (off_diagonal) Dmma884(c01[0], c01[1], a0, b1);  // above the diagonal inside a diagonal block
+      Dmma884(c10[0], c10[1], a1, b0);
+      Dmma884(c11[0], c11[1], a1, b1);
     }
-    auto put = [&](int i, int j, double v) {
+    auto put = [&](int i, int j, double s) {
       if (i >= MI || j >= MJ || i < j) return;
       if (i < m) {
-        small::Accumulate(G + (long)j * ldg + i, v, acc);
+        small::Accumulate(G + (long)j * ldg + i, s, acc);
       } else if (i == m) {
-        small::Accumulate(j < m ? AQc + j : scal + 1, v, acc);
+        small::Accumulate(j < m ? AQc + j : scal + 1, s, acc);
       } else {
-        small::Accumulate(j < m ? AW + j : scal + 0, v, acc);
+        small::Accumulate(j < m ? AW + j : scal + 0, s, acc);
       }
     };
-#pragma unroll
-    for (int c = 0; c < CH; c++) {
-      if (c < cnt) {
-        put(row0[c] + gid, col0[c] + tig * 2, accG[c][0]);
-        put(row0[c] + gid, col0[c] + tig * 2 + 1, accG[c][1]);
-      }
-    }
+    const int i0 = 16 * bi + gid, j0 = 16 * bj + tig * 2;
+    put(i0, j0, c00[0]);
+    put(i0, j0 + 1, c00[1]);
+    put(i0, j0 + 8, c01[0]);
+    put(i0, j0 + 9, c01[1]);
+    put(i0 + 8, j0, c10[0]);
+    put(i0 + 8, j0 + 1, c10[1]);
+    put(i0 + 8, j0 + 8, c11[0]);
+    put(i0 + 8, j0 + 9, c11[1]);
   }
 }
 

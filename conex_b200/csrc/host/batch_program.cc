@@ -17,6 +17,7 @@ struct ConeSlot {
   int type = 0, n = 0, m = 0, rows = 0;
   size_t state_size = 0, work_size = 0;
   DeviceBuffer<double> data, state, work;
+  DeviceBuffer<double> packed;  // LMI blocks: lower triangles of the matrices, for the slack passes
   cxb_small_cone desc;
   int rank = 0;
 };
@@ -132,7 +133,8 @@ BatchProgram::BatchProgram(const std::vector<Program*>& programs) : impl_(std::m
     c.desc.state_stride = static_cast<long>(c.state_size);
     c.desc.work = c.work_size ? c.work.get() : nullptr;
     c.desc.work_stride = static_cast<long>(c.work_size);
-    d.descs.push_back(c.desc);
+    c.desc.packed = nullptr;
+    c.desc.packed_stride = 0;
   }
   // ---- pack the cone data -----------------------------------------------------------------------
   for (int p = 0; p < B; p++) {
@@ -166,6 +168,34 @@ BatchProgram::BatchProgram(const std::vector<Program*>& programs) : impl_(std::m
     }
   }
   d.ctx.Synchronize();
+  // ---- packed copies of the LMI operators (symmetric matrices: the slack passes read half the bytes) -------------
+  {
+    DeviceBuffer<int> flags;
+    flags.Resize(nc);
+    CudaCheck(cudaMemsetAsync(flags.get(), 0, sizeof(int) * nc, d.ctx.cuda_stream()), "memset");
+    for (size_t k = 0; k < nc; k++) {
+      ConeSlot& c = d.cones[k];
+      if (c.type != CXB_CONE_PSD) continue;
+      const size_t stride = Align4(static_cast<size_t>(m + 1) * (static_cast<size_t>(c.n) * (c.n + 1) / 2));
+      c.packed.Resize(stride * B);
+      DeviceCheck(cxb_small_pack_symmetric(d.s(), B, &c.desc, c.packed.get(), static_cast<long>(stride),
+                                           flags.get() + k),
+                  "cxb_small_pack_symmetric");
+    }
+    std::vector<int> asymmetric(nc, 0);
+    d.ctx.DownloadInts(asymmetric.data(), flags.get(), nc);
+    for (size_t k = 0; k < nc; k++) {
+      ConeSlot& c = d.cones[k];
+      if (c.type == CXB_CONE_PSD && !asymmetric[k]) {
+        c.desc.packed = c.packed.get();
+        c.desc.packed_stride =
+            static_cast<long>(Align4(static_cast<size_t>(m + 1) * (static_cast<size_t>(c.n) * (c.n + 1) / 2)));
+      } else {
+        c.packed.Resize(0);
+      }
+    }
+    for (auto& c : d.cones) d.descs.push_back(c.desc);
+  }
   // ---- Newton-system storage ------------------------------------------------------------------------
   d.ldh = static_cast<long>(Align4(m));
   d.vstride = Align4(m);

@@ -40,6 +40,8 @@ cxb_small_cone SmallConeConstraint::Descriptor() {
   c.state_stride = 0;
   c.work = d.work.get();
   c.work_stride = 0;
+  c.packed = nullptr;
+  c.packed_stride = 0;
   return c;
 }
 

@@ -289,10 +289,21 @@ typedef struct {
   long state_stride;
   double* work;
   long work_stride;
+  /* optional, PSD only: the lower triangles of the m + 1 matrices, column by column, n (n + 1) / 2 doubles each
+   * (cxb_small_pack_symmetric); when not NULL the slack kernels (cxb_small_eigen / cxb_small_prepare) read it instead of
+   * the full matrices — half the HBM traffic of the two passes a Newton step makes over the operator for its slacks. */
+  const double* packed;
+  long packed_stride;
 } cxb_small_cone;
 size_t cxb_small_state_size(int type, int n);
 size_t cxb_small_work_size(int type, int n, int m);
 int cxb_small_set_identity(void* stream, int batch, const cxb_small_cone* cone, const int* d_active);
+/* Packed copy of a PSD cone's operator: d_packed[p * packed_stride + j * kp + c n - c (c - 1) / 2 + (r - c)] = A_j[r, c],
+ * r >= c, kp = n (n + 1) / 2. *d_asymmetric (device int, zeroed by the caller) is set when some A_j[r, c] != A_j[c, r]:
+ * the packed copy then does not represent the operator and must not be used (the reference forms the slack from the
+ * full matrices, dense_lmi_constraint.cc:8-20). */
+int cxb_small_pack_symmetric(void* stream, int batch, const cxb_small_cone* cone, double* d_packed, long packed_stride,
+                             int* d_asymmetric);
 /* G (ldg, lower triangle), AW, AQc (m each, stride vstride), scal[2] = {<w,c>, <c,Qc>} (stride
  * sstride): assigned (accumulate == 0) or added to (ConstructSchurComplementSystem, initialize flag). */
 int cxb_small_schur(void* stream, int batch, const cxb_small_cone* cone, double* dG, long ldg,

@@ -138,7 +138,7 @@ int emul_small_eigen(int batch, const cxb_small_cone* c, const double* y, long y
     } else {
       const long nnp = Align4((long)c->n * c->n);
       PsdEigen(t, c->n, c->m, data, y + p * ystride, k, st, st + nnp, st + 2 * nnp, sm.data(),
-               out4 + p * ostride);
+               out4 + p * ostride, c->packed ? c->packed + p * c->packed_stride : nullptr);
     }
   }
   return 0;
@@ -163,7 +163,7 @@ int emul_small_prepare(int batch, const cxb_small_cone* c, const double* y, long
     } else {
       const long nnp = Align4((long)c->n * c->n);
       PsdPrepare(t, c->n, c->m, data, y + p * ystride, affine != 0, k, ew, st, st + nnp, st + 2 * nnp,
-                 sm.data(), out2 + p * ostride);
+                 sm.data(), out2 + p * ostride, c->packed ? c->packed + p * c->packed_stride : nullptr);
     }
   }
   return 0;

@@ -26,7 +26,8 @@ vp = C.c_void_p
 
 class ConeDesc(C.Structure):
     _fields_ = [("type", C.c_int), ("n", C.c_int), ("m", C.c_int), ("data", vp), ("data_stride", C.c_long),
-                ("state", vp), ("state_stride", C.c_long), ("work", vp), ("work_stride", C.c_long)]
+                ("state", vp), ("state_stride", C.c_long), ("work", vp), ("work_stride", C.c_long),
+                ("packed", vp), ("packed_stride", C.c_long)]
 
 
 def align4(n):
@@ -145,6 +146,36 @@ class SmallCone:
         self.desc = ConeDesc(kind, n, m, be.ptr(self.data), self.rows * (m + 1), be.ptr(self.state), self.ss,
                              be.ptr(self.work), self.ws)
         be.call("set_identity", C.c_int(self.batch), C.byref(self.desc))
+
+    def pack(self):
+        """PSD: attach the packed copy of the operator (lower triangles of the m + 1 matrices) to the descriptor.
+        Returns True when some matrix is not symmetric (the copy is then left detached, as the library does)."""
+        be, n, m, B = self.be, self.n, self.m, self.batch
+        kp = n * (n + 1) // 2
+        stride = align4((m + 1) * kp)
+        if be.kind == "emul":
+            full = np.asarray(self.data).reshape(B, m + 1, n, n)          # [p, j, col, row]
+            packed = np.zeros((B, stride))
+            idx = [(c, r) for c in range(n) for r in range(c, n)]
+            cols, rows = np.array([c for c, _ in idx]), np.array([r for _, r in idx])
+            packed[:, :(m + 1) * kp] = full[:, :, cols, rows].reshape(B, (m + 1) * kp)
+            asymmetric = not np.array_equal(full, full.transpose(0, 1, 3, 2))
+            self.packed = packed.ravel().copy()
+        else:
+            self.packed = be.alloc(B * stride)
+            flag = be.alloc(1, np.int32)
+            f = be.lib.cxb_small_pack_symmetric
+            f.restype = C.c_int
+            assert f(vp(None), C.c_int(B), C.byref(self.desc), be.ptr(self.packed), C.c_long(stride),
+                     be.ptr(flag)) == 0
+            asymmetric = bool(be.download(flag)[0])
+        if not asymmetric:
+            self.desc.packed = be.ptr(self.packed)
+            self.desc.packed_stride = stride
+        return asymmetric
+
+    def packed_host(self):
+        return self.be.download(self.packed)
 
     def get_state(self):
         s = self.be.download(self.state).reshape(self.batch, self.ss)

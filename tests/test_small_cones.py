@@ -371,3 +371,47 @@ def test_fused_launch_over_the_cones_of_a_program_is_bit_identical(threads):
             for a, b in zip(got[2], reference[2]):
                 close(a, b, 1e-12, "state")
     assert np.array_equal(fused[0], single[0]) and np.array_equal(fused[1], single[1])
+
+
+def _packed_vs_full(be, n, m, B, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    data = np.stack([random_cone_data(PSD, n, m, rng) for _ in range(B)])
+    y = rng.uniform(-0.05, 0.05, size=(B, m))
+    cw = rng.uniform(0.5, 1.5, size=B)
+    out = []
+    for packed in (False, True):
+        cone = be.cone(PSD, n, m, data)
+        if packed:
+            assert cone.pack() is False
+            kp = n * (n + 1) // 2
+            got = cone.packed_host().reshape(B, -1)[:, :(m + 1) * kp].reshape(B, m + 1, kp)
+            for p in (0, B - 1):
+                for j in (0, m):
+                    A = data[p][j * n * n:(j + 1) * n * n].reshape(n, n, order="F")
+                    assert np.array_equal(got[p, j], np.concatenate([A[c:, c] for c in range(n)]))
+        res = [cone.eigen(y, cw), cone.prepare(y, cw, 1.0)]
+        cone.take_step(np.full(B, 0.7), 1.0)
+        res.append(cone.get_state())
+        res.append(cone.prepare(y, cw, 0.0, affine=True))
+        res.append(cone.get_state())
+        out.append(res)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)          # same sums in the same order: bit for bit
+    # a matrix that is not symmetric: the copy is refused
+    bad = data.copy()
+    bad[B - 1][(m // 2) * n * n + 1] += 1e-9      # entry (1, 0) of one matrix
+    assert be.cone(PSD, n, m, bad).pack() is True
+
+
+@pytest.mark.parametrize("n,m", [(6, 4), (5, 3), (20, 7)])
+def test_slack_from_the_packed_lower_triangles_is_bit_identical_host_emulation(n, m):
+    """The slack passes of the LMI blocks read the packed lower triangles of the (symmetric) matrices when the batch
+    has made that copy (cxb_small_cone.packed): eigen-bounds, step norms, dual-recovery update and the scaling point
+    after a step must not change by a bit; index arithmetic checked here through the host stand-in of the team."""
+    _packed_vs_full(Backend("emul"), n, m, 3, 100 * n + m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(6, 4), (5, 3), (20, 40), (32, 9)])
+def test_slack_from_the_packed_lower_triangles_is_bit_identical(n, m):
+    _packed_vs_full(Backend("device"), n, m, 7, 100 * n + m)

@@ -47,7 +47,8 @@ def main():
     table = line_table(obj, kernel)
     base = None
     by_line, by_reason = defaultdict(int), defaultdict(lambda: defaultdict(int))
-    total = 0
+    by_inst = defaultdict(int)
+    total = total_inst = 0
     reasons = [c for c in cols if c.startswith("stall_") and "Not Issued" not in c]
     for r in rows[head + 1:]:
         if len(r) < len(cols) or r[0] == "Address":
@@ -58,12 +59,18 @@ def main():
         n = int(r[cols["# Samples"]] or 0)
         by_line[key] += n
         total += n
+        ni = int(r[cols["Instructions Executed"]] or 0)
+        by_inst[key] += ni
+        total_inst += ni
         for c in reasons:
             by_reason[key][c] += int(r[cols[c]] or 0)
     print(f"# {rows[0][1][:100]}: {total} stall samples")
     for key, n in sorted(by_line.items(), key=lambda kv: -kv[1])[:top]:
         rs = sorted(by_reason[key].items(), key=lambda kv: -kv[1])[:3]
         print(f"{100.0 * n / total:6.2f}%  {key}  " + ", ".join(f"{a[6:]} {b}" for a, b in rs if b))
+    print(f"# warp instructions executed by source line ({total_inst} in all)")
+    for key, n in sorted(by_inst.items(), key=lambda kv: -kv[1])[:top]:
+        print(f"{100.0 * n / total_inst:6.2f}%  {key}")
 
 
 if __name__ == "__main__":
