@@ -164,6 +164,7 @@ struct DeviceTeam {
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     for (int i = lane; i < rows; i += 32) {
       const double rv = row_value(i);
+#pragma unroll 4
       for (int c = warp; c < cols; c += nwarps) f(i, c, rv);
     }
     __syncthreads();
@@ -189,6 +190,22 @@ struct DeviceTeam {
   // index of the FIRST largest f(i), i in [0, n) (n >= 1), and that value. Two barriers; at most 16 warps.
   template <class F>
   __device__ __forceinline__ int argmax_first(int n, F f, double* vmax) {
+    if (n <= 32) {
+      // all candidates sit on warp 0: the other warps only wait for its result
+      __syncthreads();
+      if ((tid >> 5) == 0) {
+        WarpTeam w;
+        double v;
+        const int idx = w.argmax_first(n, f, &v);
+        if (tid == 0) {
+          red[0] = v;
+          red[16] = (double)idx;
+        }
+      }
+      __syncthreads();
+      *vmax = red[0];
+      return (int)red[16];
+    }
     double v = -1.7976931348623157e308;
     int idx = 0;  // stays valid when every f(i) is NaN
     for (int i = tid; i < n; i += nt) {
