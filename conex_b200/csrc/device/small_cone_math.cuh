@@ -770,26 +770,6 @@ CXB_HD int SturmCountBelow(const double* a, const double* b, int k, double x, do
   }
   return count;
 }
-// Two counts at once (x0 against the chain of side 0, x1 against that of side 1): the two recurrences are independent, so
-// their divisions overlap instead of running back to back. Each count is computed exactly as by SturmCountBelow.
-CXB_HD void SturmCountBelow2(const double* a, const double* b, int k, double x0, double x1, double tiny, int* c0,
-                             int* c1) {
-  int n0 = 0, n1 = 0;
-  double q0 = 1, q1 = 1;
-  for (int i = 0; i < k; i++) {
-    const double bb = (i == 0) ? 0.0 : b[i - 1] * b[i - 1];
-    const double off0 = (i == 0) ? 0.0 : bb / q0;
-    const double off1 = (i == 0) ? 0.0 : bb / q1;
-    q0 = a[i] - x0 - off0;
-    q1 = a[i] - x1 - off1;
-    if (fabs(q0) < tiny) q0 = -tiny;
-    if (fabs(q1) < tiny) q1 = -tiny;
-    if (q0 < 0) n0++;
-    if (q1 < 0) n1++;
-  }
-  *c0 = n0;
-  *c1 = n1;
-}
 CXB_HD double SturmKth(const double* a, const double* b, int k, int which, double lo, double hi,
                        double tiny) {
   for (int it = 0; it < 200; it++) {
@@ -857,42 +837,29 @@ CXB_HD void ExtremeTridiagonalTeam(T& t, const double* a, const double* b, int k
   hi += pad;
   double tiny = 2.2250738585072014e-308 / eps + 1e-30 * scale * scale;
   tiny = fmax(tiny, eps * eps * scale);
-  // both brackets advance in the same round: one pass over the sections evaluates a point of each (two independent
-  // division chains per thread); a bracket that has converged is simply no longer updated
-  double l[2] = {lo, lo}, h[2] = {hi, hi};
-  bool done[2] = {false, false};
-  for (int round = 0; round < 64; round++) {
-    for (int s = 0; s < 2; s++) {
-      const double w = h[s] - l[s];
-      const double first = l[s] + w * (1.0 / (double)(kSections + 1));
-      const double last = l[s] + w * ((double)kSections / (double)(kSections + 1));
-      if (!(first > l[s]) || !(last < h[s])) done[s] = true;  // the interior points no longer resolve the bracket
+  double result[2];
+  for (int side = 0; side < 2; side++) {
+    const int which = side == 0 ? 0 : k - 1;
+    double l = lo, h = hi;
+    for (int round = 0; round < 64; round++) {
+      const double w = h - l;
+      const double first = l + w * (1.0 / (double)(kSections + 1));
+      const double last = l + w * ((double)kSections / (double)(kSections + 1));
+      if (!(first > l) || !(last < h)) break;  // the interior points no longer resolve the bracket: converged
+      const int q = t.first_true(kSections, [&](int i) {
+        const double x = l + w * ((double)(i + 1) / (double)(kSections + 1));
+        return SturmCountBelow(a, b, k, x, tiny) > which;
+      });
+      const double nl = q == 0 ? l : l + w * ((double)q / (double)(kSections + 1));
+      const double nh = q == kSections ? h : l + w * ((double)(q + 1) / (double)(kSections + 1));
+      l = nl;
+      h = nh;
     }
-    if (done[0] && done[1]) break;
-    const double w0 = h[0] - l[0], w1 = h[1] - l[1];
-    int q[2];
-    t.first_true2(
-        kSections,
-        [&](int i, bool* p0, bool* p1) {
-          const double f = (double)(i + 1) / (double)(kSections + 1);
-          int c0, c1;
-          SturmCountBelow2(a, b, k, l[0] + w0 * f, l[1] + w1 * f, tiny, &c0, &c1);
-          *p0 = c0 > 0;
-          *p1 = c1 > k - 1;
-        },
-        &q[0], &q[1]);
-    for (int s = 0; s < 2; s++) {
-      if (done[s]) continue;
-      const double w = h[s] - l[s];
-      const double nl = q[s] == 0 ? l[s] : l[s] + w * ((double)q[s] / (double)(kSections + 1));
-      const double nh = q[s] == kSections ? h[s] : l[s] + w * ((double)(q[s] + 1) / (double)(kSections + 1));
-      l[s] = nl;
-      h[s] = nh;
-    }
+    result[side] = 0.5 * (l + h);
   }
   t.single([&]() {
-    *emin = 0.5 * (l[0] + h[0]);
-    *emax = 0.5 * (l[1] + h[1]);
+    *emin = result[0];
+    *emax = result[1];
   });
 }
 

@@ -105,22 +105,6 @@ struct WarpTeam {
     __syncwarp();
     return found;
   }
-  // first_true for two predicates evaluated together: pred(i, &p0, &p1)
-  template <class F>
-  __device__ __forceinline__ void first_true2(int n, F pred, int* q0, int* q1) {
-    int f0 = n, f1 = n;
-    for (int base = 0; base < n && (f0 == n || f1 == n); base += 32) {
-      const int i = base + tid;
-      bool p0 = false, p1 = false;
-      if (i < n) pred(i, &p0, &p1);
-      const unsigned m0 = __ballot_sync(kFull, p0), m1 = __ballot_sync(kFull, p1);
-      if (f0 == n && m0) f0 = base + __ffs(m0) - 1;
-      if (f1 == n && m1) f1 = base + __ffs(m1) - 1;
-    }
-    __syncwarp();
-    *q0 = f0;
-    *q1 = f1;
-  }
   template <class F>
   __device__ __forceinline__ double bcast(F f) {
     __syncwarp();
@@ -164,7 +148,6 @@ struct DeviceTeam {
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     for (int i = lane; i < rows; i += 32) {
       const double rv = row_value(i);
-#pragma unroll 4
       for (int c = warp; c < cols; c += nwarps) f(i, c, rv);
     }
     __syncthreads();
@@ -256,21 +239,6 @@ struct DeviceTeam {
       }
     v = BlockMax(v);
     return v < -1e300 ? n : (int)(-v);
-  }
-  // first_true for two predicates evaluated together: pred(i, &p0, &p1)
-  template <class F>
-  __device__ __forceinline__ void first_true2(int n, F pred, int* q0, int* q1) {
-    double v0 = -1.7976931348623157e308, v1 = v0;
-    for (int i = tid; i < n; i += nt) {
-      bool p0 = false, p1 = false;
-      pred(i, &p0, &p1);
-      if (p0 && v0 < -1e300) v0 = -(double)i;
-      if (p1 && v1 < -1e300) v1 = -(double)i;
-    }
-    v0 = BlockMax(v0);
-    v1 = BlockMax(v1);
-    *q0 = v0 < -1e300 ? n : (int)(-v0);
-    *q1 = v1 < -1e300 ? n : (int)(-v1);
   }
   // f() evaluated by one thread, result given to all.
   template <class F>

@@ -57,16 +57,6 @@ struct HostTeam {
     return best;
   }
   template <class F>
-  void first_true2(int n, F pred, int* q0, int* q1) {
-    *q0 = *q1 = n;
-    for (int i = n - 1; i >= 0; i--) {
-      bool p0 = false, p1 = false;
-      pred(i, &p0, &p1);
-      if (p0) *q0 = i;
-      if (p1) *q1 = i;
-    }
-  }
-  template <class F>
   int first_true(int n, F pred) {
     for (int i = 0; i < n; i++)
       if (pred(i)) return i;
