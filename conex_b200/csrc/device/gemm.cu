@@ -426,6 +426,10 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
 //   3: 128x64, 8 warps of 32x32, 3 stages, 2 CTAs/SM
 //   4: 128x128, BK = 32, 3 stages, 1 CTA/SM
 //   5: 64x128, 8 warps of 32x32, 3 stages, 2 CTAs/SM
+//   6: 64x128, 4 warps of 32x64, 3 stages, 2 CTAs/SM (the shape of cuBLAS's own sm_100 FP64 kernel: 32 DMMA per 12
+//      fragment loads instead of 16 per 8)
+//   7: 128x64, 4 warps of 64x32, 3 stages, 2 CTAs/SM
+//   8: 64x128, 4 warps of 32x64, 2 stages, 3 CTAs/SM
 // Several independent CTAs per SM keep the DMMA pipe busy across each other's barriers and
 // fragment-load latencies (the profile of the one-CTA configurations shows `wait` and
 // `short_scoreboard` stalls at every k-tile boundary).
@@ -438,6 +442,9 @@ int LaunchLayout(cudaStream_t stream, const GemmArgs& g, int batch, int config, 
     case 3: return LaunchCfg<128, 64, 16, 32, 32, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
     case 4: return LaunchCfg<128, 128, 32, 64, 32, 3, 1, AKC, BKC, VEC>(stream, g, batch, splits);
     case 5: return LaunchCfg<64, 128, 16, 32, 32, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 6: return LaunchCfg<64, 128, 16, 32, 64, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 7: return LaunchCfg<128, 64, 16, 64, 32, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 8: return LaunchCfg<64, 128, 16, 32, 64, 2, 3, AKC, BKC, VEC>(stream, g, batch, splits);
     default: return -1;
   }
 }
