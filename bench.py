@@ -1019,6 +1019,10 @@ def run_b200(args):
     proc = Process()
     if args.gemm_max_ktiles >= 0:
         proc.L.cxb_set_gemm_split_policy(args.gemm_max_ktiles)
+    if args.gemm_config >= 0:
+        proc.L.cxb_set_default_gemm_config(args.gemm_config)
+    if args.gram_config >= -1:
+        proc.L.cxb_set_gram_gemm_config(args.gram_config)
     w = workload_shape(args)
     line = dense_bench(proc, args, w, args.steps, args.warmup, full_solve=not args.no_full_solve,
                        cpu_leg=not args.no_cpu_baseline and proc.rank == 0 and proc.world == 1)
@@ -1065,6 +1069,8 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=0, help="override n = m of the CPU sample (testing)")
     ap.add_argument("--no-peer-memory", action="store_true",
                     help="N > 1 A/B: exchange the scaled matrices through ncclSend / ncclRecv instead of peer memory")
+    ap.add_argument("--gemm-config", type=int, default=-1, help="A/B: cxb_set_default_gemm_config (tile configuration of the large GEMMs)")
+    ap.add_argument("--gram-config", type=int, default=-2, help="A/B: cxb_set_gram_gemm_config (-1 = as the other large products)")
     ap.add_argument("--gemm-max-ktiles", type=int, default=-1, help="A/B: cxb_set_gemm_split_policy")
     ap.add_argument("--small-psd-mma", type=int, default=-1, help="c3 A/B: cxb_set_small_psd_mma (2 default, 1, 0)")
     ap.add_argument("--small-cone-threads", type=int, default=0, help="c3 A/B: cxb_set_small_cone_threads (32/64/128)")

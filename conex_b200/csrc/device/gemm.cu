@@ -453,8 +453,14 @@ bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 int g_default_large_config = 2;
 
-int PickConfig(int M, int N) {
+// Deep A^T B contractions (the Gram matrices of the Schur assembly: K = n^2 or its packed length): 64 x 128 tiles with
+// 32 x 64 warp tiles — measured 28.4 against 25.4-26.8 TFLOP/s of lower-triangle flops at m = 2000, K = 1e6, while the
+// 64 x 64 tile stays ahead on the n x n x n scaling products (32.35 vs 32.04; profiles/r02_o_gemm_wide_warp_tiles.jsonl).
+int g_gram_config = 6;
+
+int PickConfig(bool transA, bool transB, int M, int N, int K) {
   if (M <= 96 || N <= 96) return 0;
+  if (transA && !transB && K >= 16384 && g_gram_config >= 0) return g_gram_config;
   return g_default_large_config;
 }
 
@@ -505,7 +511,7 @@ int DgemmStructured(cudaStream_t stream, int config, int splits, bool transA, bo
   g.splits = 1;
   g.k_per_split = K;
   g.partials = nullptr;
-  if (config < 0) config = PickConfig(M, N);
+  if (config < 0) config = PickConfig(transA, transB, M, N, K);
   if (pack && config != 0 && config != 2) config = 2;  // packing needs the 64 x 64 tile
   const bool vec2 = Aligned16(A) && Aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                     (sA % 2 == 0) && (sB % 2 == 0);
@@ -531,6 +537,7 @@ int Dgemm(cudaStream_t stream, bool transA, bool transB, int M, int N, int K, do
 }
 
 void SetDefaultGemmConfig(int config) { g_default_large_config = config; }
+void SetGramGemmConfig(int config) { g_gram_config = config; }
 
 }  // namespace cxb
 
@@ -553,4 +560,5 @@ extern "C" int cxb_dgemm_ex(void* stream, int config, int splits, int transA, in
 }
 
 extern "C" void cxb_set_default_gemm_config(int config) { cxb::SetDefaultGemmConfig(config); }
+extern "C" void cxb_set_gram_gemm_config(int config) { cxb::SetGramGemmConfig(config); }
 extern "C" void cxb_set_gemm_split_policy(int max_ktiles_per_cta) { cxb::g_max_ktiles_per_cta = max_ktiles_per_cta; }
