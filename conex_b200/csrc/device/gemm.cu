@@ -453,10 +453,12 @@ bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 int g_default_large_config = 2;
 
-// Deep A^T B contractions (the Gram matrices of the Schur assembly: K = n^2 or its packed length): 64 x 128 tiles with
-// 32 x 64 warp tiles — measured 28.4 against 25.4-26.8 TFLOP/s of lower-triangle flops at m = 2000, K = 1e6, while the
-// 64 x 64 tile stays ahead on the n x n x n scaling products (32.35 vs 32.04; profiles/r02_o_gemm_wide_warp_tiles.jsonl).
-int g_gram_config = 6;
+// Optional separate configuration for the deep A^T B contractions (the Gram matrices of the Schur assembly: K = n^2 or
+// its packed length); -1 (default) = the same as the other large products. The 64 x 128 tile with 32 x 64 warp tiles (6)
+// wins a stand-alone Gram of random data (28.4 vs 25.4-26.8 TFLOP/s of lower-triangle flops at m = 2000, K = 1e6,
+// profiles/r02_o_gemm_wide_warp_tiles.jsonl) and LOSES inside the C2 step (assembly 986.7 vs 959.7 ms,
+// profiles/r02_p_bench_c2_gram_config.txt), so it is not the default.
+int g_gram_config = -1;
 
 int PickConfig(bool transA, bool transB, int M, int N, int K) {
   if (M <= 96 || N <= 96) return 0;

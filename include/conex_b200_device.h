@@ -46,8 +46,8 @@ int cxb_dgemm_ex(void* stream, int config, int splits, int transA, int transB, i
 int cxb_dgemm_bulk(void* stream, int M, int N, int K, const double* dA, long lda, long strideA, const double* dB,
                    long ldb, long strideB, double* dC, long ldc, long strideC, int batch, int tri);
 void cxb_set_default_gemm_config(int config);
-/* Tile configuration of the deep A^T B contractions (Gram matrices of the Schur assembly); default 6 = 64 x 128 tiles with
- * 32 x 64 warp tiles; -1 = the default configuration of the other large products. A/B switch. */
+/* Tile configuration of the deep A^T B contractions (Gram matrices of the Schur assembly): -1 (default) = the default
+ * configuration of the other large products; 6 = 64 x 128 tiles with 32 x 64 warp tiles. A/B switch. */
 void cxb_set_gram_gemm_config(int config);
 /* Deterministic split-K policy of deep contractions: 0 (default) = split only to fill the machine; k > 0 = additionally
  * cap the k-tiles (of 16) one CTA walks at k, so that CTAs sharing operand panels stay within L2 of each other. */
