@@ -430,6 +430,7 @@ int LaunchCfg(cudaStream_t stream, GemmArgs g, int batch, int splits) {
 //      fragment loads instead of 16 per 8)
 //   7: 128x64, 4 warps of 64x32, 3 stages, 2 CTAs/SM
 //   8: 64x128, 4 warps of 32x64, 2 stages, 3 CTAs/SM
+//   9: 64x64, BK = 32, 4 warps of 32x32, 2 stages, 3 CTAs/SM (half the k-tile barriers of configuration 2)
 // Several independent CTAs per SM keep the DMMA pipe busy across each other's barriers and
 // fragment-load latencies (the profile of the one-CTA configurations shows `wait` and
 // `short_scoreboard` stalls at every k-tile boundary).
@@ -445,6 +446,7 @@ int LaunchLayout(cudaStream_t stream, const GemmArgs& g, int batch, int config, 
     case 6: return LaunchCfg<64, 128, 16, 32, 64, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
     case 7: return LaunchCfg<128, 64, 16, 64, 32, 3, 2, AKC, BKC, VEC>(stream, g, batch, splits);
     case 8: return LaunchCfg<64, 128, 16, 32, 64, 2, 3, AKC, BKC, VEC>(stream, g, batch, splits);
+    case 9: return LaunchCfg<64, 64, 32, 32, 32, 2, 3, AKC, BKC, VEC>(stream, g, batch, splits);
     default: return -1;
   }
 }
@@ -514,7 +516,7 @@ int DgemmStructured(cudaStream_t stream, int config, int splits, bool transA, bo
   g.k_per_split = K;
   g.partials = nullptr;
   if (config < 0) config = PickConfig(transA, transB, M, N, K);
-  if (pack && config != 0 && config != 2) config = 2;  // packing needs the 64 x 64 tile
+  if (pack && config != 0 && config != 2 && config != 9) config = 2;  // packing needs the 64 x 64 tile
   const bool vec2 = Aligned16(A) && Aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                     (sA % 2 == 0) && (sB % 2 == 0);
   const bool akc = transA, bkc = !transB;

@@ -69,7 +69,7 @@ def test_dgemm_batched_and_lower(dev):
     run_gemm(dev, 1, 0, 131, 130, 49, 1.0, 0.0, rng, lower=True)   # odd K -> 8-byte copies
 
 
-@pytest.mark.parametrize("config", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("config", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_dgemm_every_tile_configuration(dev, config, ta, tb):
     """Every compiled tile configuration, split-K (fixed-order reduction) and the mirrored store."""
