@@ -21,3 +21,12 @@ for wl in c2s c4s sparse c4; do
   python -c "import json; raw=open('gpurun_out/r02_r_bench_$wl.json').read(); d=json.loads([l for l in raw.splitlines() if l.startswith('{')][0]); print('$wl', d['value'], d.get('phase_ms'), d['e2e'].get('solve_ms'), d['e2e'].get('solve_iterations'))"
 done
 du -sh gpurun_out
+# compute-sanitizer over the small-cone kernels changed in this part of the round (fused launches, ballot multi-section,
+# compile-time-order DMMA Schur kernel with the shared leftover matrix, packed slack passes, warp-0 pivot search)
+NEW='fused or dmma_schur or packed or both_thread_layouts or (trajectory and device)'
+for tool in memcheck racecheck synccheck; do
+  log=gpurun_out/r02_r_sanitizer_${tool}_small_cones.txt
+  timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_small_cones.py tests/test_gpu_batch.py -m gpu -q -x -p no:cacheprovider -k "$NEW or batch" > $log 2>&1
+  echo "$tool: rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -1) | $(grep -E ' passed| failed| error' $log | tail -1)"
+done
+du -sh gpurun_out
