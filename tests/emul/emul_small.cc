@@ -85,6 +85,19 @@ using namespace cxb::small;
 
 extern "C" {
 
+// Number of (e, d) pairs on which the float-reciprocal Divider of the math header disagrees with integer division.
+long emul_divider_mismatches(int max_divisor, int quotients) {
+  long bad = 0;
+  for (int d = 1; d <= max_divisor; d++) {
+    const Divider v(d);
+    const long limit = (long)d * quotients < 2147483000L ? (long)d * quotients : 2147483000L;
+    const long step = d < 70 ? 1 : 7;
+    for (long e = 0; e < limit; e += step) bad += v.quot((int)e) != e / d || v.rem((int)e) != e % d;
+    for (long e = limit > 50000 ? limit - 50000 : 0; e < limit; e++) bad += v.quot((int)e) != e / d;
+  }
+  return bad;
+}
+
 int emul_small_set_identity(int batch, const cxb_small_cone* c) {
   HostTeam t;
   for (int p = 0; p < batch; p++) {

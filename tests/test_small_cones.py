@@ -415,3 +415,12 @@ def test_slack_from_the_packed_lower_triangles_is_bit_identical_host_emulation(n
 @pytest.mark.parametrize("n,m", [(6, 4), (5, 3), (20, 40), (32, 9)])
 def test_slack_from_the_packed_lower_triangles_is_bit_identical(n, m):
     _packed_vs_full(Backend("device"), n, m, 7, 100 * n + m)
+
+
+def test_index_divider_is_exact():
+    """small_cone_math.cuh replaces the integer division of the flat element index by a float reciprocal with a
+    one-step correction; the element loops rely on it being exact for every quotient below 2^22."""
+    lib = Backend("emul").lib
+    lib.emul_divider_mismatches.restype = C.c_long
+    assert lib.emul_divider_mismatches(C.c_int(700), C.c_int(2500)) == 0
+    assert lib.emul_divider_mismatches(C.c_int(9), C.c_int(4000000)) == 0    # quotients up to 4e6 ~ 2^22
