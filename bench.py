@@ -274,8 +274,9 @@ def batched_flops_per_program_step(m=40, n=20, blocks=3):
 
 
 def batched_bytes_per_program_step(m=40, n=20, blocks=3):
-    """Algorithmic HBM bytes of the Schur kernel per program and step: the cone data read once and
-    the scaled matrices W A_i W written once and read once."""
+    """Algorithmic HBM bytes per program and step: three passes over the operator of the LMI blocks — the Schur system
+    and the two slacks of a Newton step. (The product reads less: the slack passes take the packed
+    lower triangles, 2.5 instead of 3 x the operator; the scaled matrices never leave shared memory.)"""
     return blocks * (m + 1) * n * n * 8.0 * 3
 
 
@@ -451,7 +452,8 @@ def batched_bench(proc, args, w, cpu_leg):
         "solve_ms": dev_ms, "programs_per_s": nprog / (dev_ms * 1e-3), "programs_solved": nsolved,
         "program_steps": program_steps,
         "step_tflops_fp64": flops / (dev_ms * 1e-3) / 1e12,
-        "roofline": {"bound": "hbm", "kernel": "batched Schur assembly of the 20x20 LMI blocks (small_cones.cu)",
+        "roofline": {"bound": "hbm", "kernel": "whole lock step of the batch: PsdSchurMma2Kernel (DMMA, 66 % pipe-active under "
+                                               "ncu, profiles/r02_m_c3_schur_ncu_full.txt) + the eigen-bound / step kernels",
                      "achieved": bytes_ / (dev_ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                      "frac": bytes_ / (dev_ms * 1e-3) / 1e9 / (peak * world), "peak_source": peak_src,
                      "note": "whole-solve time, all kernels; the same work is 2 flop/byte-balanced: "
