@@ -69,10 +69,10 @@ __device__ __forceinline__ double* SocScratch(const ConeArgs& c, long per, doubl
 
 // Two thread layouts for the same phase-structured math (small_cone_math.cuh):
 //   WARP == false: one CTA of kThreads threads per program (DeviceTeam, block barriers between phases);
-//   WARP == true : one WARP per program, several programs per CTA (WarpTeam: __syncwarp + shuffles). The phases of
-//                  these cones are short (a 20 x 20 Lanczos step, a column of a 40 x 40 Cholesky), so the barrier, not
-//                  the arithmetic, is what a phase costs; default for everything but the team version of the LMI Schur
-//                  kernel (cxb_set_small_team_mode).
+//   WARP == true : one WARP per program, several programs per CTA (WarpTeam: __syncwarp + shuffles). Default only
+//                  for the kernel that is one dependent chain (the triangular solves of the small KKT systems):
+//                  everywhere else it measured slower, because the shared memory of a problem, not its threads,
+//                  bounds how many problems an SM holds (cxb_set_small_team_mode).
 // `per` = doubles of dynamic shared memory per program.
 template <bool WARP>
 struct TeamOf {
